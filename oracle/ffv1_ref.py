@@ -1,0 +1,123 @@
+"""ctypes binding of oracle/_ref/libffv1ref.so = the UNMODIFIED reference FFV1 encoder/decoder compiled by
+oracle/Makefile (TEST INFRASTRUCTURE ONLY).  available() is False when the library has not been built
+(e.g. /root/reference absent and no prebuilt file travelled)."""
+import ctypes, os, subprocess
+import numpy as np
+from . import pixfmt
+from .ffv1_oracle import split_planes, _plane_args
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_PATH = os.path.join(_HERE, "_ref", "libffv1ref.so")
+_LIB = None
+
+def build(reference="/root/reference"):
+    if os.path.isdir(reference):
+        subprocess.check_call(["make", "-s", "-j8", "-C", _HERE, "ref", "REF=" + reference])
+
+def available():
+    return os.path.exists(_PATH)
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        L = ctypes.CDLL(_PATH)
+        L.ffv1ref_enc_open.restype = ctypes.c_void_p
+        L.ffv1ref_enc_open.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_char_p] + [ctypes.c_int] * 8
+        L.ffv1ref_enc_extradata.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+        L.ffv1ref_enc_frame.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int)] + \
+            [ctypes.c_int] * 4 + [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
+        L.ffv1ref_enc_close.argtypes = [ctypes.c_void_p]
+        L.ffv1ref_dec_open.restype = ctypes.c_void_p
+        L.ffv1ref_dec_open.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+        L.ffv1ref_dec_packet.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
+                                         ctypes.c_char_p, ctypes.POINTER(ctypes.c_int)]
+        L.ffv1ref_dec_close.argtypes = [ctypes.c_void_p]
+        L.ffv1ref_crc32_ieee.restype = ctypes.c_uint
+        L.ffv1ref_crc32_ieee.argtypes = [ctypes.c_uint, ctypes.c_void_p, ctypes.c_int]
+        _LIB = L
+    return _LIB
+
+class Encoder:
+    def __init__(self, w, h, pix_fmt, gop=12, level=-1, coder=0, context=0, slices=0, slicecrc=-1, threads=1):
+        self.h_ = None
+        self.w, self.h, self.pix_fmt = w, h, pix_fmt
+        self.h_ = lib().ffv1ref_enc_open(w, h, pix_fmt.encode(), gop, level, coder, context, slices, slicecrc, threads, 0)
+        if not self.h_:
+            raise ValueError("reference encoder refused these options")
+        self.cap = 65536 + pixfmt.frame_bytes(pix_fmt, w, h) * 4
+        self.buf = ctypes.create_string_buffer(self.cap)
+    @property
+    def extradata(self):
+        b = ctypes.create_string_buffer(1 << 20)
+        n = lib().ffv1ref_enc_extradata(self.h_, b, 1 << 20)
+        return b.raw[:max(n, 0)]
+    def encode(self, frame, sar=(0, 1), interlaced=0, tff=0):
+        planes = split_planes(np.ascontiguousarray(frame).view(np.uint8).reshape(-1), self.pix_fmt, self.w, self.h)
+        ptrs, strides = _plane_args(planes)
+        key = ctypes.c_int()
+        n = lib().ffv1ref_enc_frame(self.h_, ptrs, strides, sar[0], sar[1], interlaced, tff, self.buf, self.cap, ctypes.byref(key))
+        if n <= 0:
+            raise RuntimeError("reference encode failed %d" % n)
+        return self.buf.raw[:n], bool(key.value)
+    def close(self):
+        if self.h_:
+            lib().ffv1ref_enc_close(self.h_); self.h_ = None
+    def __del__(self):
+        self.close()
+
+class Decoder:
+    def __init__(self, w, h, extradata=b"", threads=1, frame_threads=0):
+        self.h_ = None
+        self.w, self.h = w, h
+        self.h_ = lib().ffv1ref_dec_open(w, h, extradata, len(extradata), threads, frame_threads)
+        if not self.h_:
+            raise ValueError("reference decoder refused extradata")
+    def decode(self, pkt):
+        cap = self.w * self.h * 8 + 64
+        out = np.zeros(cap, np.uint8)
+        name = ctypes.create_string_buffer(32); key = ctypes.c_int()
+        n = lib().ffv1ref_dec_packet(self.h_, pkt, len(pkt), out.ctypes.data, cap, name, ctypes.byref(key))
+        if n <= 0:
+            raise RuntimeError("reference decode failed %d" % n)
+        return out[:n].copy(), name.value.decode(), bool(key.value)
+    def close(self):
+        if self.h_:
+            lib().ffv1ref_dec_close(self.h_); self.h_ = None
+    def __del__(self):
+        self.close()
+
+def crc32(data, init=0):
+    return lib().ffv1ref_crc32_ieee(init, data, len(data))
+
+def fate_avi(raw, nframes, w, h, pix_fmt, level, slices):
+    """encode + mux with the reference's AVI muxer exactly as FATE's enc_dec does; returns the AVI bytes"""
+    L = lib()
+    L.ffv1ref_fate_avi.restype = ctypes.c_int64
+    L.ffv1ref_fate_avi.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_char_p,
+                                   ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64]
+    out = np.zeros(len(raw) + (4 << 20), np.uint8)
+    n = L.ffv1ref_fate_avi(raw.ctypes.data, nframes, w, h, pix_fmt.encode(), level, slices, out.ctypes.data, len(out))
+    if n < 0:
+        raise RuntimeError("fate_avi failed %d" % n)
+    return out[:n].tobytes()
+
+def vsynth(name, reference="/root/reference"):
+    """FATE's synthetic clips made by the reference's own generators (tests/videogen.c, tests/rotozoom.c,
+    tests/Makefile:34-44), compiled into oracle/_ref/.  Returns (uint8 array, w, h)."""
+    import tempfile
+    d = os.path.join(_HERE, "_ref")
+    for tool in ("videogen", "rotozoom"):
+        exe = os.path.join(d, tool)
+        if not os.path.exists(exe):
+            subprocess.check_call(["gcc", "-O2", "-w", "-o", exe, os.path.join(reference, "tests", tool + ".c"), "-lm"])
+    with tempfile.TemporaryDirectory() as td:
+        out = os.path.join(td, name + ".yuv")
+        if name == "vsynth1":
+            subprocess.check_call([os.path.join(d, "videogen"), out]); w, h = 352, 288
+        elif name == "vsynth3":
+            subprocess.check_call([os.path.join(d, "videogen"), out, "34", "34"]); w, h = 34, 34
+        elif name == "vsynth2":
+            subprocess.check_call([os.path.join(d, "rotozoom"), os.path.join(reference, "tests", "reference.pnm"), out]); w, h = 352, 288
+        else:
+            raise ValueError(name)
+        return np.fromfile(out, np.uint8), w, h

@@ -1,0 +1,291 @@
+/*
+ * ref_harness.c -- TEST INFRASTRUCTURE ONLY (never linked into the product).
+ *
+ * A thin C wrapper that drives the UNMODIFIED reference FFV1 encoder/decoder
+ * (/root/reference/libavcodec/ffv1enc.c, ffv1dec.c, compiled as they lie) through
+ * the reference's public libavcodec API: avcodec_register / avcodec_open2 /
+ * avcodec_encode_video2 / avcodec_decode_video2 (libavcodec/utils.c:178,1208,1922,2180).
+ * It exists so that Python tests (ctypes) and bench.py's CPU-baseline leg can obtain the
+ * reference's packets, extradata and decoded frames, and time the reference's
+ * slice-threaded CPU path.  Built into oracle/_ref/libffv1ref.so by oracle/Makefile.
+ */
+#include <string.h>
+#include <stdlib.h>
+#include "libavcodec/avcodec.h"
+#include "libavutil/opt.h"
+#include "libavutil/pixdesc.h"
+#include "libavutil/imgutils.h"
+
+extern AVCodec ff_ffv1_encoder;
+extern AVCodec ff_ffv1_decoder;
+
+static int g_registered;
+static void reg(void)
+{
+    if (!g_registered) {
+        avcodec_register(&ff_ffv1_encoder);
+        avcodec_register(&ff_ffv1_decoder);
+        g_registered = 1;
+        av_log_set_level(AV_LOG_ERROR);
+    }
+}
+
+typedef struct RefEnc {
+    AVCodecContext *ctx;
+    AVFrame *frame;
+    int64_t pts;
+} RefEnc;
+
+/* level<0 / slices==0 / slicecrc<0 mean "leave at the reference default". threads>1 enables the
+ * reference's slice threading (pthread_slice.c). sar_num/den go to every AVFrame (they are coded in
+ * each slice header, ffv1enc.c:1048-1049). */
+void *ffv1ref_enc_open(int w, int h, const char *pix_fmt, int gop, int level, int coder, int context,
+                       int slices, int slicecrc, int threads, int strict_experimental)
+{
+    reg();
+    enum AVPixelFormat pf = av_get_pix_fmt(pix_fmt);
+    if (pf == AV_PIX_FMT_NONE) return NULL;
+    RefEnc *e = calloc(1, sizeof(*e));
+    e->ctx = avcodec_alloc_context3(&ff_ffv1_encoder);
+    e->ctx->width = w; e->ctx->height = h; e->ctx->pix_fmt = pf;
+    e->ctx->time_base = (AVRational){1, 25};
+    e->ctx->gop_size = gop;
+    e->ctx->level = level;
+    e->ctx->slices = slices;
+    e->ctx->flags |= AV_CODEC_FLAG_BITEXACT;
+    if (strict_experimental) e->ctx->strict_std_compliance = FF_COMPLIANCE_EXPERIMENTAL;
+    if (threads > 1) { e->ctx->thread_count = threads; e->ctx->thread_type = FF_THREAD_SLICE; }
+    else e->ctx->thread_count = 1;
+    av_opt_set_int(e->ctx->priv_data, "coder", coder, 0);
+    av_opt_set_int(e->ctx->priv_data, "context", context, 0);
+    av_opt_set_int(e->ctx->priv_data, "slicecrc", slicecrc, 0);
+    if (avcodec_open2(e->ctx, &ff_ffv1_encoder, NULL) < 0) {
+        avcodec_free_context(&e->ctx); free(e); return NULL;
+    }
+    e->frame = av_frame_alloc();
+    return e;
+}
+
+int ffv1ref_enc_extradata(void *h, uint8_t *dst, int cap)
+{
+    RefEnc *e = h;
+    if (e->ctx->extradata_size > cap) return -1;
+    memcpy(dst, e->ctx->extradata, e->ctx->extradata_size);
+    return e->ctx->extradata_size;
+}
+
+/* Encode one frame given plane pointers + linesizes; returns packet size (copied to dst), <0 on error.
+ * *key receives AV_PKT_FLAG_KEY. */
+int ffv1ref_enc_frame(void *h, uint8_t *const planes[4], const int linesize[4], int sar_num, int sar_den,
+                      int interlaced, int tff, uint8_t *dst, int cap, int *key)
+{
+    RefEnc *e = h;
+    AVPacket pkt;
+    int got = 0, ret, i;
+    av_init_packet(&pkt); pkt.data = NULL; pkt.size = 0;
+    /* hand the encoder a refcounted frame (as ffmpeg.c's rawvideo path does): copy the caller's rows in */
+    av_frame_unref(e->frame);
+    e->frame->format = e->ctx->pix_fmt; e->frame->width = e->ctx->width; e->frame->height = e->ctx->height;
+    if ((ret = av_frame_get_buffer(e->frame, 32)) < 0) return ret;
+    for (i = 0; i < 4 && planes[i]; i++) {
+        int bw = av_image_get_linesize(e->ctx->pix_fmt, e->ctx->width, i);
+        int hh = e->ctx->height;
+        const AVPixFmtDescriptor *d = av_pix_fmt_desc_get(e->ctx->pix_fmt);
+        if (i == 1 || i == 2) hh = -((-hh) >> d->log2_chroma_h);
+        av_image_copy_plane(e->frame->data[i], e->frame->linesize[i], planes[i], linesize[i], bw, hh);
+    }
+    e->frame->pts = e->pts++;
+    e->frame->sample_aspect_ratio = (AVRational){sar_num, sar_den};
+    e->frame->interlaced_frame = interlaced;
+    e->frame->top_field_first = tff;
+    ret = avcodec_encode_video2(e->ctx, &pkt, e->frame, &got);
+    if (ret < 0) return ret;
+    if (!got) return 0;
+    if (pkt.size > cap) { av_packet_unref(&pkt); return -2; }
+    memcpy(dst, pkt.data, pkt.size);
+    ret = pkt.size;
+    if (key) *key = !!(pkt.flags & AV_PKT_FLAG_KEY);
+    av_packet_unref(&pkt);
+    return ret;
+}
+
+void ffv1ref_enc_close(void *h)
+{
+    RefEnc *e = h;
+    if (!e) return;
+    av_frame_free(&e->frame);
+    avcodec_close(e->ctx);
+    avcodec_free_context(&e->ctx);
+    free(e);
+}
+
+typedef struct RefDec {
+    AVCodecContext *ctx;
+    AVFrame *frame;
+} RefDec;
+
+void *ffv1ref_dec_open(int w, int h, const uint8_t *extradata, int extradata_size, int threads, int frame_threads)
+{
+    reg();
+    RefDec *d = calloc(1, sizeof(*d));
+    d->ctx = avcodec_alloc_context3(&ff_ffv1_decoder);
+    d->ctx->width = w; d->ctx->height = h;
+    if (extradata_size > 0) {
+        d->ctx->extradata = av_mallocz(extradata_size + AV_INPUT_BUFFER_PADDING_SIZE);
+        memcpy(d->ctx->extradata, extradata, extradata_size);
+        d->ctx->extradata_size = extradata_size;
+    }
+    d->ctx->flags |= AV_CODEC_FLAG_BITEXACT;
+    d->ctx->thread_count = threads > 1 ? threads : 1;
+    if (threads > 1) d->ctx->thread_type = frame_threads ? FF_THREAD_FRAME : FF_THREAD_SLICE;
+    if (avcodec_open2(d->ctx, &ff_ffv1_decoder, NULL) < 0) {
+        avcodec_free_context(&d->ctx); free(d); return NULL;
+    }
+    d->frame = av_frame_alloc();
+    return d;
+}
+
+/* Decode one packet. On success copies the planes tightly packed (plane after plane, width*bytes per row)
+ * into dst, writes the pix_fmt name to fmt_name (cap 32) and returns total bytes; 0 = no frame; <0 error. */
+int ffv1ref_dec_packet(void *h, const uint8_t *data, int size, uint8_t *dst, int cap, char *fmt_name, int *key)
+{
+    RefDec *d = h;
+    AVPacket pkt;
+    int got = 0, ret;
+    uint8_t *buf = av_mallocz(size + AV_INPUT_BUFFER_PADDING_SIZE);
+    memcpy(buf, data, size);
+    av_init_packet(&pkt); pkt.data = buf; pkt.size = size;
+    ret = avcodec_decode_video2(d->ctx, d->frame, &got, &pkt);
+    av_free(buf);
+    if (ret < 0) return ret;
+    if (!got) return 0;
+    ret = av_image_get_buffer_size(d->frame->format, d->frame->width, d->frame->height, 1);
+    if (ret > cap) return -2;
+    av_image_copy_to_buffer(dst, cap, (const uint8_t *const *)d->frame->data, d->frame->linesize,
+                            d->frame->format, d->frame->width, d->frame->height, 1);
+    if (fmt_name) { strncpy(fmt_name, av_get_pix_fmt_name(d->frame->format), 31); fmt_name[31] = 0; }
+    if (key) *key = d->frame->key_frame;
+    av_frame_unref(d->frame);
+    return ret;
+}
+
+void ffv1ref_dec_close(void *h)
+{
+    RefDec *d = h;
+    if (!d) return;
+    av_frame_free(&d->frame);
+    avcodec_close(d->ctx);
+    avcodec_free_context(&d->ctx);
+    free(d);
+}
+
+/* CRC helper so tests can pin libavutil's AV_CRC_32_IEEE convention (crc.c:357-380). */
+#include "libavutil/crc.h"
+unsigned ffv1ref_crc32_ieee(unsigned init, const uint8_t *buf, int len)
+{
+    return av_crc(av_crc_get_table(AV_CRC_32_IEEE), init, buf, len);
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * FATE reproduction: encode a raw clip with the reference encoder and mux it with the reference's
+ * own AVI muxer (libavformat/avienc.c) into memory, the way tests/fate-run.sh:171-193 (enc_dec)
+ * drives ffmpeg.c, so that the MD5 + size in tests/ref/vsynth/vsynth*-ffv1* can be checked.
+ * ---------------------------------------------------------------------------------------------- */
+#include "libavformat/avformat.h"
+#include "libavformat/avio.h"
+
+extern AVOutputFormat ff_avi_muxer;
+
+typedef struct MemOut { uint8_t *buf; int64_t cap, pos, size; } MemOut;
+static int mem_write(void *opaque, uint8_t *buf, int n)
+{
+    MemOut *m = opaque;
+    if (m->pos + n > m->cap) return -1;
+    memcpy(m->buf + m->pos, buf, n);
+    m->pos += n;
+    if (m->pos > m->size) m->size = m->pos;
+    return n;
+}
+static int64_t mem_seek(void *opaque, int64_t off, int whence)
+{
+    MemOut *m = opaque;
+    if (whence == AVSEEK_SIZE) return m->size;
+    if (whence == SEEK_CUR) off += m->pos;
+    else if (whence == SEEK_END) off += m->size;
+    if (off < 0 || off > m->cap) return -1;
+    m->pos = off;
+    return off;
+}
+
+/* raw: nframes tightly packed frames in pix_fmt. Returns AVI size written into out, <0 on error. */
+int64_t ffv1ref_fate_avi(const uint8_t *raw, int nframes, int w, int h, const char *pix_fmt,
+                         int level, int slices, uint8_t *out, int64_t cap)
+{
+    static int fmt_registered;
+    enum AVPixelFormat pf = av_get_pix_fmt(pix_fmt);
+    AVFormatContext *oc = NULL;
+    AVStream *st;
+    AVCodecContext *enc;
+    AVFrame *frame;
+    MemOut mo = { out, cap, 0, 0 };
+    uint8_t *iobuf;
+    int i, ret, fsize;
+    reg();
+    if (!fmt_registered) { av_register_output_format(&ff_avi_muxer); fmt_registered = 1; }
+    if (avformat_alloc_output_context2(&oc, &ff_avi_muxer, NULL, NULL) < 0) return -1;
+    iobuf = av_malloc(32768);
+    oc->pb = avio_alloc_context(iobuf, 32768, 1, &mo, NULL, mem_write, mem_seek);
+    oc->flags |= AVFMT_FLAG_BITEXACT;
+    st = avformat_new_stream(oc, NULL);
+
+    enc = avcodec_alloc_context3(&ff_ffv1_encoder);
+    enc->width = w; enc->height = h; enc->pix_fmt = pf;
+    enc->time_base = (AVRational){1, 25};
+    enc->framerate = (AVRational){25, 1};
+    enc->level = level;
+    enc->slices = slices;
+    enc->thread_count = 1;
+    enc->flags |= AV_CODEC_FLAG_BITEXACT;
+    enc->sample_aspect_ratio = (AVRational){0, 1};
+    if (oc->oformat->flags & AVFMT_GLOBALHEADER) enc->flags |= AV_CODEC_FLAG_GLOBAL_HEADER;
+    if ((ret = avcodec_open2(enc, &ff_ffv1_encoder, NULL)) < 0) return ret;
+    /* ffmpeg.c init_output_stream: avcodec_parameters_from_context + time base / frame rate hints */
+    avcodec_parameters_from_context(st->codecpar, enc);
+    avcodec_copy_context(st->codec, enc);
+    st->time_base = enc->time_base;
+    st->avg_frame_rate = (AVRational){25, 1};
+    st->sample_aspect_ratio = enc->sample_aspect_ratio;
+    av_dict_set(&st->metadata, "encoder", "Lavc ffv1", 0);
+    if ((ret = avformat_write_header(oc, NULL)) < 0) return ret;
+
+    frame = av_frame_alloc();
+    fsize = av_image_get_buffer_size(pf, w, h, 1);
+    for (i = 0; i < nframes; i++) {
+        AVPacket pkt;
+        int got = 0;
+        av_init_packet(&pkt); pkt.data = NULL; pkt.size = 0;
+        frame->format = pf; frame->width = w; frame->height = h;
+        av_frame_get_buffer(frame, 32);
+        {
+            uint8_t *src[4]; int ls[4];
+            av_image_fill_arrays(src, ls, raw + (int64_t)i * fsize, pf, w, h, 1);
+            av_image_copy(frame->data, frame->linesize, (const uint8_t **)src, ls, pf, w, h);
+        }
+        frame->pts = i;
+        frame->sample_aspect_ratio = (AVRational){0, 1};
+        if ((ret = avcodec_encode_video2(enc, &pkt, frame, &got)) < 0) return ret;
+        av_frame_unref(frame);
+        if (got) {
+            av_packet_rescale_ts(&pkt, enc->time_base, st->time_base);
+            pkt.stream_index = 0;
+            if ((ret = av_interleaved_write_frame(oc, &pkt)) < 0) return ret;
+        }
+    }
+    av_write_trailer(oc);
+    avio_flush(oc->pb);
+    av_frame_free(&frame);
+    avcodec_close(enc); avcodec_free_context(&enc);
+    av_freep(&oc->pb->buffer); av_freep(&oc->pb);
+    avformat_free_context(oc);
+    return mo.size;
+}
