@@ -1,0 +1,69 @@
+// ffv1_enc_kernels.cuh -- launch interfaces of the encoder kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include "ffv1_model.h"
+
+namespace ffv1 {
+
+constexpr int kPixelThreads   = 256;
+constexpr int kPixelChunk     = 512;          // samples of one row handled per smem pass
+constexpr int kPixelPadL      = 8;            // int16 elements left of x=0 in a staged row (keeps 16 B alignment)
+constexpr int kPixelRowElems  = kPixelChunk + 16;
+constexpr int kReplayWarps    = 2;            // chains (warps) per CTA of the state-replay kernel
+constexpr int kMaxPrefix      = 8192;         // decisions before the first sample (v0/v1 keyframes carry a whole header)
+
+// per-batch device buffers and scalars handed to the kernels
+struct EncBatch {
+    int32_t nframes;
+    int32_t nseg;                       // GOP segments inside the batch
+    const uint8_t *const *planes;       // [nframes*4] device pointers
+    int32_t linesize[4];
+    uint32_t *rec;                      // [nframes][rec_per_frame]
+    uint32_t *line_cnt;                 // [nframes][lines_per_frame]  decisions per line
+    uint32_t *line_off;                 // [nframes][lines_per_frame]  exclusive scan inside (frame, slice)
+    uint32_t *slice_ndec;               // [nframes][nslices]          decisions of the slice's samples
+    uint64_t *slice_base;               // [nframes][nslices]          first entry in dec[]
+    uint16_t *dec;                      // decision stream: p | bit<<8
+    uint64_t dec_capacity;              // entries
+    const int32_t *seg_first;           // [nseg+1] first frame of each segment
+    const uint8_t *frame_key;           // [nframes]
+    uint8_t *scratch;                   // [nframes][scratch_per_frame]
+    uint32_t *slice_bytes;              // [nframes][nslices] coder output bytes (payload)
+    uint32_t *pkt_size;                 // [nframes]
+    uint64_t *pkt_off;                  // [nframes+1]
+    uint8_t *out;                       // packets, back to back
+    uint64_t out_capacity;
+    // adaptive state
+    uint8_t *state_seg;                 // global-state mode: [nseg][nslices][npc][ctx_count*32]
+    const uint8_t *carry_in;            // [nslices][npc][ctx_count*32]
+    uint8_t *carry_out;
+    // error reporting: [0] dec overflow (needed entries), [1] scratch overflow flag, [2] out overflow
+    unsigned long long *status;
+};
+
+struct EncDeviceTables {
+    Layout layout;                      // by value (kernel parameter)
+    const SliceGeom *slices;
+    const LineDesc *lines;
+    const int32_t *pc_lines;
+    const TileDesc *tiles;
+    const int16_t *quant;               // [5][256]
+    const uint8_t *trans_lut;           // [512]: zero_state, one_state of the slice coders
+    const uint16_t *prefix;             // [nslices][2][kMaxPrefix]
+    const int32_t *prefix_len;          // [nslices][2]
+    int32_t ec;
+    int32_t version;
+    int32_t state_in_smem;
+};
+
+int  pixel_smem_bytes(const Layout &L);
+void launch_pixel(const EncDeviceTables &t, const EncBatch &b, cudaStream_t s);
+void launch_scan(const EncDeviceTables &t, const EncBatch &b, cudaStream_t s);
+int  replay_smem_bytes(const Layout &L);
+void launch_replay(const EncDeviceTables &t, const EncBatch &b, cudaStream_t s);
+void launch_rangecode(const EncDeviceTables &t, const EncBatch &b, cudaStream_t s);
+void launch_pack(const EncDeviceTables &t, const EncBatch &b, cudaStream_t s);
+cudaError_t configure_kernels(const Layout &L);
+
+} // namespace ffv1

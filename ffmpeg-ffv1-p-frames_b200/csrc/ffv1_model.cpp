@@ -1,0 +1,679 @@
+// ffv1_model.cpp -- see ffv1_model.h.  Host-only; no CUDA here.
+#include "ffv1_model.h"
+#include "../../include/ffv1_b200.h"
+#include <cstring>
+#include <cstdlib>
+#include <algorithm>
+
+namespace ffv1 {
+
+// ------------------------------------------------------------------------------------------------
+// constant tables of the bitstream format
+// ------------------------------------------------------------------------------------------------
+
+// Context quantisers (ffv1enc.c:44-118) are odd step functions; {first |d| of level 1, 2, ...}.
+struct QuantCurve { int nlevels; int start[6]; };
+static const QuantCurve kQ11   = {5, {1, 2, 5, 12, 35}};       // quant11      : 11 levels, 8-bit
+static const QuantCurve kQ5    = {2, {1, 4}};                  // quant5       :  5 levels, 8-bit
+static const QuantCurve kQ9hi  = {4, {5, 13, 27, 56}};         // quant9_10bit :  9 levels, >8-bit
+static const QuantCurve kQ5hi  = {2, {11, 50}};                // quant5_10bit :  5 levels, >8-bit
+
+static void expand_curve(const QuantCurve &q, int scale, int16_t out[256])
+{
+    for (int d = 0; d < 128; d++) {
+        int lvl = 0;
+        while (lvl < q.nlevels && d >= q.start[lvl]) lvl++;
+        out[d] = (int16_t)(lvl * scale);
+    }
+    for (int d = 1; d < 128; d++) out[256 - d] = (int16_t)-out[d];
+    out[128] = (int16_t)-out[127];
+}
+
+// "ver2_state": the state-transition table selected by coder=1/2 (ffv1enc.c:120-137), stored as the
+// delta to the identity (one_state[i] - i) to keep the listing compact.
+static const int8_t kCustomDelta[256] = {
+    0,  9,  8,  7,  6, 11, 10,  9, 20,  7,  6, 18, 30, 36,  6, 34, 43,  8,  8,  7,  7, 10, 11, 10,  9,  9,  8, 10, 39,  9,  9,  8,
+    8,  7,  7, 44,  7,  7,  7,  6,  8,  7, 22,  7,  7,  7, 42,  5,  5, 25,  5,  6,  6,  5, 20,  5, 45,  4,  4, 25,  6,  5,  6,  6,
+   23, 17,  5, 30,  5,  4, 12,  4, 39,  4, 20,  3, 11,  4,  5, 18,  5,  2, 12,  3, 15,  4,  4, 12, 23,  3,  3, 43,  3,  5, 11,  3,
+    9, 13,  4,  9,  2, 17,  1,  3,  2,  8,  3,  5,  6,  3,  6, 14,  3,  3,  3,  2, 10,  2,  7,  2,  1,  2, 23,  1,  2,  6,  1,  2,
+   37,  1,  2,  7,  1,  2, 11,  1,  1,  2,  8,  2,  3,  1,  2,  5,  3, 10,  5,  2,  3,  1,  2,  6,  1,  1,  2, 13,  2,  5,  3,  1,
+   12,  2,  7,  1,  2, 19,  1,  3,  9,  5,  1,  2, 10,  3,  6,  3, -1, 12,  1,  2,  6,  2, 10,  2, 16,  2,  5,  1,  2,  8,  3,  5,
+    5,  1,  1,  1,  2,  5,  1,  2, 10,  2,  5,  1,  1,  1,  2,  7,  1,  2, 11,  1,  1,  2, 10,  1,  1,  1,  1,  1,  2,  7,  1,  2,
+    2, -1,  1,  2, 12,  1,  1,  1,  1,  1,  1,  1,  2,  2, -1,  3,  1,  2,  0,  1,  1,  1,  1,  1,  1,  1,  1,  1,  0,  0,  0,  0,
+};
+
+void default_state_tables(uint8_t zero_state[256], uint8_t one_state[256])
+{
+    // rangecoder.c:63-101 with FFV1's arguments factor=(int)(0.05*2^32), max_p=256-8 (ffv1enc.c:562,1288)
+    const int64_t kOne = int64_t(1) << 32;
+    const int64_t kFactor = (int64_t)(int)(0.05 * (double)kOne);
+    const int kMaxP = 248;
+    memset(zero_state, 0, 256);
+    memset(one_state, 0, 256);
+    int64_t prob = kOne / 2;
+    int last = 0;
+    for (int i = 0; i < 128; i++) {
+        int p8 = (int)((256 * prob + kOne / 2) >> 32);
+        p8 = std::max(p8, last + 1);
+        if (last && last < 256 && p8 <= kMaxP) one_state[last] = (uint8_t)p8;
+        prob += ((kOne - prob) * kFactor + kOne / 2) >> 32;
+        last = p8;
+    }
+    for (int i = 256 - kMaxP; i <= kMaxP; i++) {
+        if (one_state[i]) continue;
+        prob = (i * kOne + 128) >> 8;
+        prob += ((kOne - prob) * kFactor + kOne / 2) >> 32;
+        int p8 = (int)((256 * prob + kOne / 2) >> 32);
+        p8 = std::min(std::max(p8, i + 1), kMaxP);
+        one_state[i] = (uint8_t)p8;
+    }
+    for (int i = 1; i < 255; i++) zero_state[i] = (uint8_t)(256 - one_state[256 - i]);
+}
+
+void coder_state_tables(const Config &c, uint8_t zero_state[256], uint8_t one_state[256])
+{
+    // ffv1enc.c:1288 then 1309-1315 (slice 0) / ffv1.c:95-100 (other slices)
+    default_state_tables(zero_state, one_state);
+    if (c.ac == AC_RANGE_CUSTOM)
+        for (int j = 1; j < 256; j++) {
+            one_state[j] = c.state_transition[j];
+            zero_state[256 - j] = (uint8_t)(256 - one_state[j]);
+        }
+}
+
+uint32_t crc32_ieee(uint32_t crc, const uint8_t *buf, size_t len)
+{
+    // libavutil AV_CRC_32_IEEE (crc.c:303,357-380): MSB-first 0x04C11DB7, init 0, no final xor
+    static uint32_t tab[256];
+    static bool init = false;
+    if (!init) {
+        for (uint32_t n = 0; n < 256; n++) {
+            uint32_t c = n << 24;
+            for (int k = 0; k < 8; k++) c = (c & 0x80000000u) ? (c << 1) ^ 0x04C11DB7u : (c << 1);
+            tab[n] = c;
+        }
+        init = true;
+    }
+    while (len--) crc = (crc << 8) ^ tab[(crc >> 24) ^ *buf++];
+    return crc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host binary coder: either produces range-coder bytes (extradata, golomb-mode slice prefixes) or just
+// records the (probability, bit) decisions for the device coder to consume (range-mode slice prefixes).
+// rangecoder.h:52-102, rangecoder.c:42-51,104-116.
+// ------------------------------------------------------------------------------------------------
+class BinCoder {
+public:
+    uint8_t zero_state[256], one_state[256];
+    std::vector<uint8_t> bytes;
+    std::vector<uint16_t> decisions;
+    bool record_only = false;
+
+    BinCoder() { default_state_tables(zero_state, one_state); }
+
+    void put(uint8_t *state, int bit)
+    {
+        decisions.push_back((uint16_t)(*state | (bit ? 0x100 : 0)));
+        if (!record_only) {
+            int r1 = (range_ * *state) >> 8;
+            if (bit) { low_ += range_ - r1; range_ = r1; } else range_ -= r1;
+            renorm();
+        }
+        *state = bit ? one_state[*state] : zero_state[*state];
+    }
+    void put_symbol(uint8_t *st, int v, bool is_signed)
+    {
+        // ffv1enc.c:185-231
+        if (v == 0) { put(st, 1); return; }
+        const int a = std::abs(v);
+        int e = 0;
+        while ((a >> (e + 1)) != 0) e++;
+        put(st, 0);
+        for (int i = 0; i < e; i++) put(st + 1 + std::min(i, 9), 1);
+        put(st + 1 + std::min(e, 9), 0);
+        for (int i = e - 1; i >= 0; i--) put(st + 22 + std::min(i, 9), (a >> i) & 1);
+        if (is_signed) put(st + 11 + std::min(e, 10), v < 0);
+    }
+    void terminate()
+    {
+        range_ = 0xFF; low_ += 0xFF; renorm();
+        range_ = 0xFF; renorm();
+    }
+private:
+    int low_ = 0, range_ = 0xFF00, out_count_ = 0, out_byte_ = -1;
+    void renorm()
+    {
+        while (range_ < 0x100) {
+            if (out_byte_ < 0) out_byte_ = low_ >> 8;
+            else if (low_ <= 0xFF00) { bytes.push_back((uint8_t)out_byte_); flush(0xFF); out_byte_ = low_ >> 8; }
+            else if (low_ >= 0x10000) { bytes.push_back((uint8_t)(out_byte_ + 1)); flush(0x00); out_byte_ = (low_ >> 8) & 0xFF; }
+            else out_count_++;
+            low_ = (low_ & 0xFF) << 8;
+            range_ <<= 8;
+        }
+    }
+    void flush(uint8_t v) { for (; out_count_; out_count_--) bytes.push_back(v); }
+};
+
+// range decoder for the extradata record (rangecoder.h:104-145)
+class BinDecoder {
+public:
+    uint8_t zero_state[256], one_state[256];
+    BinDecoder(const uint8_t *d, int n) : p_(d + 2), end_(d + n)
+    {
+        default_state_tables(zero_state, one_state);
+        low_ = n >= 2 ? (d[0] << 8 | d[1]) : 0;
+    }
+    void shrink_end(int n) { end_ -= n; }
+    int get(uint8_t *state)
+    {
+        int r1 = (range_ * *state) >> 8, bit;
+        range_ -= r1;
+        if (low_ < range_) { *state = zero_state[*state]; bit = 0; }
+        else { low_ -= range_; *state = one_state[*state]; range_ = r1; bit = 1; }
+        if (range_ < 0x100) {
+            range_ <<= 8; low_ <<= 8;
+            if (p_ < end_) low_ += *p_;
+            p_++;
+        }
+        return bit;
+    }
+    int get_symbol(uint8_t *st, bool is_signed)
+    {
+        // ffv1dec.c:42-63
+        if (get(st)) return 0;
+        int e = 0;
+        while (get(st + 1 + std::min(e, 9))) { if (++e > 31) { bad = true; return 0; } }
+        int a = 1;
+        for (int i = e - 1; i >= 0; i--) a += a + get(st + 22 + std::min(i, 9));
+        if (is_signed && get(st + 11 + std::min(e, 10))) return -a;
+        return a;
+    }
+    bool bad = false;
+private:
+    int low_ = 0, range_ = 0xFF00;
+    const uint8_t *p_, *end_;
+};
+
+// ------------------------------------------------------------------------------------------------
+// pixel formats (ffv1enc.c:720-820 / 1425-1439)
+// ------------------------------------------------------------------------------------------------
+static bool parse_pix_fmt(const std::string &name, Config &c)
+{
+    c.pix_fmt = name;
+    c.colorspace = 0; c.bits = 8; c.bytes_per_sample = 1; c.packed_at_lsb = 0; c.ya8 = 0;
+    c.chroma_planes = 0; c.transparency = 0; c.chroma_h_shift = c.chroma_v_shift = 0;
+    for (int i = 0; i < 4; i++) { c.src_hshift[i] = c.src_vshift[i] = 0; c.pixel_bytes[i] = 1; }
+
+    if (name == "bgr0" || name == "bgra") {           // AV_PIX_FMT_0RGB32 / RGB32 on little endian
+        c.colorspace = 1; c.chroma_planes = 1; c.transparency = (name == "bgra");
+        c.nb_src_planes = 1; c.pixel_bytes[0] = 4;
+        return true;
+    }
+    if (name == "ya8") { c.transparency = 1; c.ya8 = 1; c.nb_src_planes = 1; c.pixel_bytes[0] = 2; return true; }
+    if (name == "gray") { c.nb_src_planes = 1; return true; }
+    if (name == "gray16le") { c.bits = 16; c.bytes_per_sample = 2; c.nb_src_planes = 1; c.pixel_bytes[0] = 2; return true; }
+    if (name.compare(0, 4, "gbrp") == 0) {
+        int bits = atoi(name.c_str() + 4);
+        if ((bits != 9 && bits != 10 && bits != 12 && bits != 14) || name != "gbrp" + std::to_string(bits) + "le") return false;
+        c.colorspace = 1; c.chroma_planes = 1; c.bits = bits; c.bytes_per_sample = 2; c.nb_src_planes = 3;
+        for (int i = 0; i < 3; i++) c.pixel_bytes[i] = 2;
+        return true;
+    }
+    // yuv[a]4xyp[9|10|16le]
+    size_t pos = 0;
+    bool alpha = false;
+    if (name.compare(0, 4, "yuva") == 0) { alpha = true; pos = 4; }
+    else if (name.compare(0, 3, "yuv") == 0) pos = 3;
+    else return false;
+    if (name.size() < pos + 4 || name[pos + 3] != 'p') return false;
+    std::string sub = name.substr(pos, 3), depth = name.substr(pos + 4);
+    int hs, vs;
+    if (sub == "420") { hs = 1; vs = 1; } else if (sub == "422") { hs = 1; vs = 0; }
+    else if (sub == "444") { hs = 0; vs = 0; } else if (sub == "440") { hs = 0; vs = 1; }
+    else if (sub == "411") { hs = 2; vs = 0; } else if (sub == "410") { hs = 2; vs = 2; }
+    else return false;
+    int bits = 8;
+    if (!depth.empty()) {
+        if (depth == "9le") bits = 9; else if (depth == "10le") bits = 10; else if (depth == "16le") bits = 16; else return false;
+        if (sub == "440" || sub == "411" || sub == "410") return false;       // not in ff_ffv1_encoder.pix_fmts
+    }
+    if (alpha && (sub == "440" || sub == "411" || sub == "410")) return false;
+    c.bits = bits; c.bytes_per_sample = bits > 8 ? 2 : 1;
+    c.packed_at_lsb = (bits == 9 || bits == 10);
+    c.chroma_planes = 1; c.transparency = alpha;
+    c.chroma_h_shift = hs; c.chroma_v_shift = vs;
+    c.nb_src_planes = alpha ? 4 : 3;
+    c.src_hshift[1] = c.src_hshift[2] = hs; c.src_vshift[1] = c.src_vshift[2] = vs;
+    for (int i = 0; i < 4; i++) c.pixel_bytes[i] = c.bytes_per_sample;
+    return true;
+}
+
+void Config::plane_dims(int i, int *rows, int *row_bytes) const
+{
+    int cw = -((-width) >> src_hshift[i]), ch = -((-height) >> src_vshift[i]);
+    *rows = ch; *row_bytes = cw * pixel_bytes[i];
+}
+int64_t Config::frame_bytes() const
+{
+    int64_t n = 0;
+    for (int i = 0; i < nb_src_planes; i++) { int r, b; plane_dims(i, &r, &b); n += (int64_t)r * b; }
+    return n;
+}
+
+static void fill_quant_tables(Config &c)
+{
+    // ffv1enc.c:846-871
+    const QuantCurve &a = c.bits <= 8 ? kQ11 : kQ9hi, &b = c.bits <= 8 ? kQ5 : kQ5hi;
+    memset(c.quant_tables, 0, sizeof(c.quant_tables));
+    expand_curve(a, 1, c.quant_tables[0][0]);
+    expand_curve(a, 11, c.quant_tables[0][1]);
+    expand_curve(a, 11 * 11, c.quant_tables[0][2]);
+    expand_curve(a, 1, c.quant_tables[1][0]);
+    expand_curve(a, 11, c.quant_tables[1][1]);
+    expand_curve(b, 11 * 11, c.quant_tables[1][2]);
+    expand_curve(b, 5 * 11 * 11, c.quant_tables[1][3]);
+    expand_curve(b, 5 * 5 * 11 * 11, c.quant_tables[1][4]);
+    c.context_count[0] = (11 * 11 * 11 + 1) / 2;
+    c.context_count[1] = (11 * 11 * 5 * 5 * 5 + 1) / 2;
+}
+
+int resolve_encoder(const EncOptions &o, Config &c, std::string &err)
+{
+    c = Config();
+    if (o.width <= 0 || o.height <= 0) { err = "invalid picture size"; return FFV1B200_ERR_INVALIDDATA; }  // ffv1.c:46-47
+    if (o.context < 0 || o.context > 1) { err = "Invalid context model, valid values are 0 and 1"; return FFV1B200_ERR_EINVAL; }
+    if (o.coder < -2 || o.coder > 2 || o.slicecrc < -1 || o.slicecrc > 1) { err = "option out of range"; return FFV1B200_ERR_EINVAL; }
+    c.width = o.width; c.height = o.height;
+    if (!parse_pix_fmt(o.pix_fmt, c)) { err = "format not supported"; return FFV1B200_ERR_ENOSYS; }        // ffv1enc.c:816-818
+
+    // version selection, ffv1enc.c:676-706
+    int version = 0;
+    if (o.slices > 1) version = 2;
+    if (o.slices == 0 && o.level < 0 && o.width * o.height > 720 * 576) version = 2;
+    if (o.level <= 0 && version == 2) version = 3;
+    if (o.level >= 0 && o.level <= 4) {
+        if (o.level < version) { err = "Version " + std::to_string(version) + " needed for requested features but " + std::to_string(o.level) + " requested"; return FFV1B200_ERR_EINVAL; }
+        version = o.level;
+    }
+    c.ec = o.slicecrc < 0 ? (version >= 3) : o.slicecrc;
+    if (version == 2 || version > 3) { err = "FFV1 versions 2 and 4 are experimental in the reference and not provided"; return FFV1B200_ERR_INVALIDDATA; }
+
+    // coder remaps, ffv1enc.c:708-718, 755-759, 810-814
+    int ac = o.coder;
+    if (ac == 1) ac = AC_RANGE_CUSTOM;
+    else if (ac == -2) ac = AC_RANGE_DEFAULT;
+    else if (ac == -1) ac = AC_GOLOMB;
+    const bool high_bits = c.bits > 8;
+    if (high_bits) {
+        if (ac == AC_GOLOMB) ac = AC_RANGE_CUSTOM;       // "bits_per_raw_sample > 8, forcing range coder"
+        version = std::max(version, 1);
+    }
+    c.ac = ac;
+    c.version = version;
+    c.micro_version = version == 3 ? 4 : 0;
+    c.context_model = o.context;
+    c.gop_size = o.gop_size;
+    c.intra = o.gop_size < 2;
+
+    if (c.ac == AC_RANGE_CUSTOM) {
+        for (int i = 1; i < 256; i++) c.state_transition[i] = (uint8_t)(i + kCustomDelta[i]);
+    } else {
+        uint8_t z[256], one[256];
+        default_state_tables(z, one);
+        for (int i = 1; i < 256; i++) c.state_transition[i] = one[i];
+    }
+    fill_quant_tables(c);
+    c.plane_count = c.transparency ? 3 : 2;               // ffv1enc.c:720, 890-891
+
+    c.num_h_slices = c.num_v_slices = 1;
+    if (version > 1) {                                    // ffv1enc.c:988-1000
+        bool found = false;
+        for (int nv = (o.width > 352 || o.height > 288 || !o.slices) ? 2 : 1; nv < 9 && !found; nv++)
+            for (int nh = nv; nh < 2 * nv; nh++)
+                if ((o.slices == nh * nv && o.slices <= 64) || !o.slices) { c.num_h_slices = nh; c.num_v_slices = nv; found = true; break; }
+        if (!found) {
+            err = "Unsupported number " + std::to_string(o.slices) + " of slices requested, please specify a supported number with -slices (ex:4,6,9,12,16, ...)";
+            return FFV1B200_ERR_ENOSYS;
+        }
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// extradata
+// ------------------------------------------------------------------------------------------------
+static void put_quant_table(BinCoder &bc, const int16_t *q)
+{
+    // ffv1enc.c:475-488
+    uint8_t st[kStateSlots];
+    memset(st, 128, sizeof(st));
+    int last = 0;
+    for (int i = 1; i < 128; i++)
+        if (q[i] != q[i - 1]) { bc.put_symbol(st, i - last - 1, false); last = i; }
+    bc.put_symbol(st, 128 - last - 1, false);
+}
+
+std::vector<uint8_t> write_extradata(const Config &c)
+{
+    // ffv1enc.c:545-619 (version >= 2 only; versions 0/1 carry the header in band)
+    if (c.version < 2) return {};
+    BinCoder bc;
+    uint8_t st[kStateSlots];
+    memset(st, 128, sizeof(st));
+    bc.put_symbol(st, c.version, false);
+    if (c.version > 2) bc.put_symbol(st, c.micro_version, false);
+    bc.put_symbol(st, c.ac, false);
+    if (c.ac == AC_RANGE_CUSTOM)
+        for (int i = 1; i < 256; i++) bc.put_symbol(st, c.state_transition[i] - bc.one_state[i], true);
+    bc.put_symbol(st, c.colorspace, false);
+    bc.put_symbol(st, c.bits, false);
+    bc.put(st, c.chroma_planes);
+    bc.put_symbol(st, c.chroma_h_shift, false);
+    bc.put_symbol(st, c.chroma_v_shift, false);
+    bc.put(st, c.transparency);
+    bc.put_symbol(st, c.num_h_slices - 1, false);
+    bc.put_symbol(st, c.num_v_slices - 1, false);
+    bc.put_symbol(st, 2, false);
+    for (int t = 0; t < 2; t++)
+        for (int i = 0; i < 5; i++) put_quant_table(bc, c.quant_tables[t][i]);
+    for (int t = 0; t < 2; t++) bc.put(st, 0);            // initial states stay 128 (2-pass is out of scope)
+    if (c.version > 2) {
+        bc.put_symbol(st, c.ec, false);
+        bc.put_symbol(st, c.intra, false);
+    }
+    bc.terminate();
+    std::vector<uint8_t> out = bc.bytes;
+    uint32_t crc = crc32_ieee(0, out.data(), out.size());
+    for (int s = 24; s >= 0; s -= 8) out.push_back((uint8_t)(crc >> s));
+    return out;
+}
+
+static int read_quant_table(BinDecoder &bd, int16_t *q, int scale)
+{
+    // ffv1dec.c:476-500
+    uint8_t st[kStateSlots];
+    memset(st, 128, sizeof(st));
+    int i = 0, v = 0;
+    for (; i < 128; v++) {
+        unsigned len = (unsigned)bd.get_symbol(st, false) + 1;
+        if (bd.bad || len > (unsigned)(128 - i) || !len) return -1;
+        while (len--) q[i++] = (int16_t)(scale * v);
+    }
+    for (i = 1; i < 128; i++) q[256 - i] = (int16_t)-q[i];
+    q[128] = (int16_t)-q[127];
+    return 2 * v - 1;
+}
+
+static bool select_pix_fmt(Config &c)
+{
+    // ffv1dec.c:698-786
+    std::string name;
+    const int sub = 16 * c.chroma_h_shift + c.chroma_v_shift;
+    auto yuv = [&](bool alpha) -> std::string {
+        const char *s = nullptr;
+        switch (sub) { case 0x00: s = "444"; break; case 0x01: s = "440"; break; case 0x10: s = "422"; break;
+                       case 0x11: s = "420"; break; case 0x20: s = "411"; break; case 0x22: s = "410"; break; }
+        if (!s) return "";
+        if (alpha && (sub == 0x01 || sub == 0x20 || sub == 0x22)) return "";
+        if (c.bits > 8 && (sub == 0x01 || sub == 0x20 || sub == 0x22)) return "";
+        std::string n = std::string(alpha ? "yuva" : "yuv") + s + "p";
+        if (c.bits > 8) n += std::to_string(c.bits) + "le";
+        return n;
+    };
+    if (c.colorspace == 0) {
+        if (!c.transparency && !c.chroma_planes) name = c.bits <= 8 ? "gray" : "gray16le";
+        else if (c.transparency && !c.chroma_planes) { if (c.bits <= 8) name = "ya8"; }
+        else if (c.bits <= 8 || c.bits == 9 || c.bits == 10 || c.bits == 16) name = yuv(c.transparency);
+    } else if (c.colorspace == 1) {
+        if (c.chroma_h_shift || c.chroma_v_shift) return false;
+        if (c.bits <= 8) name = c.transparency ? "bgra" : "bgr0";
+        else if (!c.transparency && (c.bits == 9 || c.bits == 10 || c.bits == 12 || c.bits == 14)) name = "gbrp" + std::to_string(c.bits) + "le";
+    }
+    if (name.empty()) return false;
+    const int bits = c.bits, cp = c.chroma_planes, tr = c.transparency, hs = c.chroma_h_shift, vs = c.chroma_v_shift, cs = c.colorspace;
+    if (!parse_pix_fmt(name, c)) return false;
+    // parse_pix_fmt re-derives the same fields; keep the header's values authoritative
+    c.bits = bits; c.chroma_planes = cp; c.transparency = tr; c.chroma_h_shift = hs; c.chroma_v_shift = vs; c.colorspace = cs;
+    return true;
+}
+
+int parse_extradata(const uint8_t *d, int n, int width, int height, Config &c, std::string &err)
+{
+    // ffv1dec.c:521-636
+    c = Config();
+    c.width = width; c.height = height;
+    if (width <= 0 || height <= 0) { err = "invalid picture size"; return FFV1B200_ERR_INVALIDDATA; }
+    if (n < 2) { err = "extradata too small"; return FFV1B200_ERR_INVALIDDATA; }
+    BinDecoder bd(d, n);
+    uint8_t st[kStateSlots];
+    memset(st, 128, sizeof(st));
+    c.version = bd.get_symbol(st, false);
+    if (c.version < 2) { err = "Invalid version in global header"; return FFV1B200_ERR_INVALIDDATA; }
+    if (c.version > 2) {
+        bd.shrink_end(4);
+        c.micro_version = bd.get_symbol(st, false);
+        if (c.micro_version < 0) return FFV1B200_ERR_INVALIDDATA;
+    }
+    c.ac = bd.get_symbol(st, false);
+    for (int i = 1; i < 256; i++)
+        c.state_transition[i] = (uint8_t)((c.ac == AC_RANGE_CUSTOM ? bd.get_symbol(st, true) : 0) + bd.one_state[i]);
+    c.colorspace = bd.get_symbol(st, false);
+    c.bits = bd.get_symbol(st, false);
+    c.chroma_planes = bd.get(st);
+    c.chroma_h_shift = bd.get_symbol(st, false);
+    c.chroma_v_shift = bd.get_symbol(st, false);
+    c.transparency = bd.get(st);
+    c.plane_count = 1 + (c.chroma_planes || c.version < 4) + c.transparency;
+    c.num_h_slices = 1 + bd.get_symbol(st, false);
+    c.num_v_slices = 1 + bd.get_symbol(st, false);
+    if ((unsigned)c.chroma_h_shift > 4U || (unsigned)c.chroma_v_shift > 4U) { err = "chroma shift parameters are invalid"; return FFV1B200_ERR_INVALIDDATA; }
+    if (c.num_h_slices > width || c.num_h_slices <= 0 || c.num_v_slices > height || c.num_v_slices <= 0) { err = "slice count invalid"; return FFV1B200_ERR_INVALIDDATA; }
+    int qtc = bd.get_symbol(st, false);
+    if (qtc <= 0 || qtc > 8) { err = "quant table count is invalid"; return FFV1B200_ERR_INVALIDDATA; }
+    if (qtc != 2) { err = "streams with quant_table_count != 2 are not produced by the reference encoder; unsupported"; return FFV1B200_ERR_ENOSYS; }
+    for (int t = 0; t < qtc; t++) {
+        int count = 1;
+        for (int i = 0; i < 5; i++) {
+            int r = read_quant_table(bd, c.quant_tables[t][i], count);
+            if (r < 0) { err = "read_quant_table error"; return FFV1B200_ERR_INVALIDDATA; }
+            count *= r;
+            if ((unsigned)count > 32768U) { err = "read_quant_table error"; return FFV1B200_ERR_INVALIDDATA; }
+        }
+        c.context_count[t] = (count + 1) / 2;
+    }
+    for (int t = 0; t < qtc; t++)
+        if (bd.get(st)) { err = "2-pass initial states are not supported"; return FFV1B200_ERR_ENOSYS; }
+    if (c.version > 2) {
+        c.ec = bd.get_symbol(st, false);
+        if (c.micro_version > 2) c.intra = bd.get_symbol(st, false);
+    }
+    if (bd.bad) { err = "damaged global header"; return FFV1B200_ERR_INVALIDDATA; }
+    if (c.version > 2 && (n < 4 || crc32_ieee(0, d, n) != 0)) { err = "CRC mismatch in global header"; return FFV1B200_ERR_INVALIDDATA; }
+    if (c.version != 3) { err = "only FFV1 version 3 extradata is supported"; return FFV1B200_ERR_ENOSYS; }
+    if (!c.bits) c.bits = 8;
+    if (!select_pix_fmt(c)) { err = "format not supported"; return FFV1B200_ERR_ENOSYS; }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// slice geometry and per-slice prefix
+// ------------------------------------------------------------------------------------------------
+void slice_rect(const Config &c, int i, int *x0, int *y0, int *w, int *h)
+{
+    const int sx = i % c.num_h_slices, sy = i / c.num_h_slices;                      // ffv1.c:124-131
+    const int xs = c.width * sx / c.num_h_slices, xe = c.width * (sx + 1) / c.num_h_slices;
+    const int ys = c.height * sy / c.num_v_slices, ye = c.height * (sy + 1) / c.num_v_slices;
+    *x0 = xs; *y0 = ys; *w = xe - xs; *h = ye - ys;
+}
+
+static void put_v01_header(BinCoder &bc, const Config &c)
+{
+    // ffv1enc.c:498-524: versions 0/1 repeat the global parameters in every keyframe (slice 0's coder,
+    // default transition table still active)
+    uint8_t st[kStateSlots];
+    memset(st, 128, sizeof(st));
+    bc.put_symbol(st, c.version, false);
+    bc.put_symbol(st, c.ac, false);
+    if (c.ac == AC_RANGE_CUSTOM)
+        for (int i = 1; i < 256; i++) bc.put_symbol(st, c.state_transition[i] - bc.one_state[i], true);
+    bc.put_symbol(st, c.colorspace, false);
+    if (c.version > 0) bc.put_symbol(st, c.bits, false);
+    bc.put(st, c.chroma_planes);
+    bc.put_symbol(st, c.chroma_h_shift, false);
+    bc.put_symbol(st, c.chroma_v_shift, false);
+    bc.put(st, c.transparency);
+    for (int i = 0; i < 5; i++) put_quant_table(bc, c.quant_tables[c.context_model][i]);
+}
+
+static void put_prefix(BinCoder &bc, const Config &c, int si, bool key, int sar_num, int sar_den, int ps)
+{
+    if (si == 0) {
+        uint8_t keystate = 128;                                                       // ffv1enc.c:1299-1307
+        bc.put(&keystate, key ? 1 : 0);
+        if (key && c.version < 2) put_v01_header(bc, c);
+    }
+    coder_state_tables(c, bc.zero_state, bc.one_state);                               // ffv1enc.c:1309-1315
+    if (c.version > 2) {                                                              // ffv1enc.c:1031-1051
+        int x0, y0, w, h;
+        slice_rect(c, si, &x0, &y0, &w, &h);
+        uint8_t st[kStateSlots];
+        memset(st, 128, sizeof(st));
+        bc.put_symbol(st, (x0 + 1) * c.num_h_slices / c.width, false);
+        bc.put_symbol(st, (y0 + 1) * c.num_v_slices / c.height, false);
+        bc.put_symbol(st, (w + 1) * c.num_h_slices / c.width - 1, false);
+        bc.put_symbol(st, (h + 1) * c.num_v_slices / c.height - 1, false);
+        for (int j = 0; j < c.plane_count; j++) bc.put_symbol(st, c.context_model, false);
+        bc.put_symbol(st, ps, false);
+        bc.put_symbol(st, sar_num, false);
+        bc.put_symbol(st, sar_den, false);
+    }
+}
+
+std::vector<uint16_t> slice_prefix_decisions(const Config &c, int si, bool key, int sar_num, int sar_den, int ps)
+{
+    BinCoder bc;
+    bc.record_only = true;
+    put_prefix(bc, c, si, key, sar_num, sar_den, ps);
+    return bc.decisions;
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel tables
+// ------------------------------------------------------------------------------------------------
+static inline int ceil_rshift(int v, int s) { return -((-v) >> s); }
+
+void build_tables(const Config &c, Tables &t)
+{
+    Layout &L = t.layout;
+    memset(&L, 0, sizeof(L));
+    L.width = c.width; L.height = c.height;
+    L.raw_bits = c.bits;
+    L.rgb = c.colorspace == 1;
+    L.golomb = c.ac == AC_GOLOMB;
+    L.ctx_inputs = c.context_model ? 5 : 3;
+    L.ctx_count = c.context_count[c.context_model];
+    L.sample_shift = (c.bits > 8 && !c.packed_at_lsb && !L.rgb) ? 16 - c.bits : 0;
+    if (L.rgb) {
+        L.src_kind = c.bits <= 8 ? SRC_RGB32 : SRC_GBRP16;
+        L.coded_bits = (c.bits <= 8 ? 8 : c.bits) + 1;                    // ffv1enc.c:465-468
+        L.rct_offset = 1 << (c.bits <= 8 ? 8 : c.bits);
+        L.nplanes = 3 + (c.transparency ? 1 : 0);
+        for (int p = 0; p < L.nplanes; p++) L.plane[p] = PlaneInfo{p, 0, 0, (p + 1) / 2, c.pixel_bytes[0], 0};   // ffv1enc.c:459-469
+    } else {
+        L.src_kind = c.bits <= 8 ? SRC_PLANAR8 : SRC_PLANAR16;
+        L.coded_bits = c.bits <= 8 ? 8 : c.bits;
+        int n = 0;
+        if (c.ya8) {                                                      // ffv1enc.c:1199-1201
+            L.plane[n++] = PlaneInfo{0, 0, 0, 0, 2, 0};
+            L.plane[n++] = PlaneInfo{0, 0, 0, 1, 2, 1};
+        } else {                                                          // ffv1enc.c:1185-1198
+            L.plane[n++] = PlaneInfo{0, 0, 0, 0, c.bytes_per_sample, 0};
+            if (c.chroma_planes) {
+                L.plane[n++] = PlaneInfo{1, c.chroma_h_shift, c.chroma_v_shift, 1, c.bytes_per_sample, 0};
+                L.plane[n++] = PlaneInfo{2, c.chroma_h_shift, c.chroma_v_shift, 1, c.bytes_per_sample, 0};
+            }
+            if (c.transparency) L.plane[n++] = PlaneInfo{3, 0, 0, 2, c.bytes_per_sample, 0};
+        }
+        L.nplanes = n;
+    }
+    L.npc = 0;
+    for (int p = 0; p < L.nplanes; p++) L.npc = std::max(L.npc, L.plane[p].pc + 1);
+    L.nslices = c.slice_count();
+
+    t.slices.assign(L.nslices, SliceGeom());
+    t.lines.clear(); t.pc_lines.clear(); t.tiles.clear();
+    uint32_t rec_cursor = 0, scratch_cursor = 0;
+    for (int si = 0; si < L.nslices; si++) {
+        SliceGeom &g = t.slices[si];
+        memset(&g, 0, sizeof(g));
+        slice_rect(c, si, &g.x0, &g.y0, &g.w, &g.h);
+        for (int p = 0; p < L.nplanes; p++) {
+            const PlaneInfo &pi = L.plane[p];
+            g.pw[p] = ceil_rshift(g.w, pi.hshift);                        // ffv1enc.c:1186-1189
+            g.ph[p] = ceil_rshift(g.h, pi.vshift);
+            g.px0[p] = g.x0 >> pi.hshift;
+            g.py0[p] = g.y0 >> pi.vshift;
+        }
+        g.line_first = (int32_t)t.lines.size();
+        g.rec_first = rec_cursor;
+        uint32_t off = 0, nsamp = 0;
+        auto add_line = [&](int p, int y) {
+            LineDesc ld;
+            ld.rec_off = off; ld.w = (uint16_t)g.pw[p]; ld.pc = (uint8_t)L.plane[p].pc; ld.plane = (uint8_t)p; ld.y = (uint32_t)y;
+            t.lines.push_back(ld);
+            off += (uint32_t)((g.pw[p] + 31) & ~31);
+            nsamp += (uint32_t)g.pw[p];
+        };
+        if (!L.rgb) {
+            for (int p = 0; p < L.nplanes; p++) {
+                for (int y0 = 0; y0 < g.ph[p]; y0 += kTileRows) {
+                    TileDesc td;
+                    td.slice = (uint16_t)si; td.plane = (uint8_t)p; td.nplanes = 1; td.y0 = (uint16_t)y0;
+                    td.nrows = (uint16_t)std::min(kTileRows, g.ph[p] - y0);
+                    td.line_first = (int32_t)t.lines.size() - g.line_first + y0;
+                    td.line_step = 1;
+                    t.tiles.push_back(td);
+                }
+                for (int y = 0; y < g.ph[p]; y++) add_line(p, y);
+            }
+        } else {
+            const int rows = std::max(1, kTileRows / 2);
+            for (int y0 = 0; y0 < g.h; y0 += rows) {
+                TileDesc td;
+                td.slice = (uint16_t)si; td.plane = 0; td.nplanes = (uint8_t)L.nplanes; td.y0 = (uint16_t)y0;
+                td.nrows = (uint16_t)std::min(rows, g.h - y0);
+                td.line_first = y0 * L.nplanes;
+                td.line_step = L.nplanes;
+                t.tiles.push_back(td);
+            }
+            for (int y = 0; y < g.h; y++)
+                for (int p = 0; p < L.nplanes; p++) add_line(p, y);
+        }
+        g.nlines = (int32_t)t.lines.size() - g.line_first;
+        g.rec_count = off;
+        g.nsamples = nsamp;
+        rec_cursor += off;
+        // per-plane-context line lists, coding order
+        for (int pc = 0; pc < 3; pc++) {
+            g.pc_line_first[pc] = (int32_t)t.pc_lines.size();
+            uint32_t ns = 0;
+            for (int li = 0; li < g.nlines; li++)
+                if (t.lines[g.line_first + li].pc == pc) { t.pc_lines.push_back(li); ns += t.lines[g.line_first + li].w; }
+            g.pc_nlines[pc] = (int32_t)t.pc_lines.size() - g.pc_line_first[pc];
+            g.pc_samples[pc] = ns;
+        }
+        // coder output scratch: raw size of the slice + 12.5 % + slack; grown on demand (overflow is detected)
+        const uint64_t raw = (uint64_t)nsamp * (L.coded_bits > 8 ? 2 : 1);
+        g.scratch_off = scratch_cursor;
+        g.scratch_cap = (uint32_t)(((raw + raw / 8 + 4096) + 255) & ~255ull);
+        scratch_cursor += g.scratch_cap;
+    }
+    L.lines_per_frame = (int32_t)t.lines.size();
+    L.tiles_per_frame = (int32_t)t.tiles.size();
+    L.rec_per_frame = rec_cursor;
+    L.scratch_per_frame = scratch_cursor;
+}
+
+} // namespace ffv1

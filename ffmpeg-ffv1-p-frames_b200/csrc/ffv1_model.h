@@ -1,0 +1,151 @@
+// ffv1_model.h -- host-side model of the FFV1 format knobs that are not kernels:
+// option resolution, quantisation / state-transition tables, slice grid and per-slice coding-order
+// tables, the extradata record and the per-slice header decision lists.
+// Mirrors (behaviour, not code) libavcodec/ffv1enc.c:669-1029 (encode_init), 545-619 (write_extradata),
+// 1031-1062 (encode_slice_header), libavcodec/ffv1.c:117-160 and libavcodec/ffv1dec.c:476-636.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace ffv1 {
+
+enum Coder { AC_GOLOMB = 0, AC_RANGE_DEFAULT = 1, AC_RANGE_CUSTOM = 2 };
+
+// how K_pixel fetches raw samples
+enum SrcKind { SRC_PLANAR8 = 0, SRC_PLANAR16 = 1, SRC_RGB32 = 2, SRC_GBRP16 = 3 };
+
+constexpr int kMaxSlices = 256;
+constexpr int kStateSlots = 32;      // CONTEXT_SIZE, ffv1.h:50
+
+// ---- structs shared with the device (plain data) -----------------------------------------------
+
+// one coded sample plane of a slice ("Y", "U", "V", "A" or post-RCT "G'", "B'", "R'", "A")
+struct PlaneInfo {
+    int32_t src_plane;   // AVFrame.data[] index the samples come from (RGB kinds: unused)
+    int32_t hshift, vshift;
+    int32_t pc;          // plane-context index (ffv1.h PlaneContext): Y/G=0, chroma & B/R=1 (shared), alpha=2 (YA8: 1)
+    int32_t pstep;       // bytes between horizontally adjacent samples in the source
+    int32_t poff;        // byte offset of the sample inside a pixel (YA8 alpha = 1)
+};
+
+struct SliceGeom {
+    int32_t x0, y0, w, h;            // luma geometry (ffv1.c:124-143)
+    int32_t pw[4], ph[4];            // size of each coded sample plane
+    int32_t px0[4], py0[4];          // origin of each coded sample plane inside its source plane (samples)
+    int32_t line_first;              // index of this slice's first line in the per-frame line table
+    int32_t nlines;
+    uint32_t rec_first;              // first record of this slice inside a frame's record area
+    uint32_t rec_count;              // records incl. line padding
+    uint32_t nsamples;               // real samples
+    uint32_t scratch_off;            // byte offset of this slice's coder output inside a frame's scratch area
+    uint32_t scratch_cap;
+    int32_t pc_line_first[3];        // per plane-context: start in pc_lines[] (indices into the line table)
+    int32_t pc_nlines[3];
+    uint32_t pc_samples[3];
+};
+
+// one line of samples in coding order
+struct LineDesc {
+    uint32_t rec_off;    // record offset inside the slice's record region (multiple of 32)
+    uint16_t w;
+    uint8_t  pc;
+    uint8_t  plane;
+    uint32_t y;
+};
+
+// unit of work of the per-pixel kernel: up to kTileRows rows of one plane (all planes for RGB) of one slice
+struct TileDesc {
+    uint16_t slice;
+    uint8_t  plane;      // first coded plane handled
+    uint8_t  nplanes;    // 1 (YUV) or 3/4 (RGB: planes are produced together by the RCT)
+    uint16_t y0;
+    uint16_t nrows;
+    int32_t  line_first; // line-table index (slice relative) of (y0, plane)
+    int32_t  line_step;  // distance between consecutive rows of the same plane in the line table
+};
+
+struct Layout {
+    int32_t width, height;
+    int32_t src_kind;        // SrcKind
+    int32_t raw_bits;        // bits_per_raw_sample
+    int32_t coded_bits;      // bits the residual is folded to (raw_bits, +1 for RGB; 8-bit RGB = 9)
+    int32_t sample_shift;    // right shift applied to 16-bit containers (16 - bits when not packed at lsb)
+    int32_t nplanes;         // coded sample planes per slice
+    int32_t ctx_inputs;      // 3 or 5 (context model)
+    int32_t ctx_count;       // 666 / 7563
+    int32_t npc;             // plane contexts in use (1..3)
+    int32_t nslices;
+    int32_t lines_per_frame;
+    int32_t tiles_per_frame;
+    int32_t rgb;             // colorspace == 1
+    int32_t golomb;
+    uint32_t rec_per_frame;  // records per frame incl. padding
+    uint32_t scratch_per_frame;
+    int32_t rct_offset;      // 1 << bits for RGB
+    PlaneInfo plane[4];
+};
+
+// ---- resolved configuration ---------------------------------------------------------------------
+struct Config {
+    int width = 0, height = 0;
+    std::string pix_fmt;
+    int version = 0, micro_version = 0;
+    int ac = 0;
+    int colorspace = 0, bits = 8;
+    int chroma_planes = 0, chroma_h_shift = 0, chroma_v_shift = 0, transparency = 0;
+    int packed_at_lsb = 0;
+    int ya8 = 0;
+    int context_model = 0;
+    int ec = 0, intra = 0, gop_size = 0;
+    int num_h_slices = 1, num_v_slices = 1;
+    int plane_count = 2;                       // quant_table_index entries per slice header
+    uint8_t state_transition[256] = {0};
+    int16_t quant_tables[2][5][256];
+    int context_count[2] = {0, 0};
+    int bytes_per_sample = 1;
+    int nb_src_planes = 0;                     // AVFrame planes of the pix_fmt
+    int src_hshift[4] = {0,0,0,0}, src_vshift[4] = {0,0,0,0};
+    int pixel_bytes[4] = {1,1,1,1};            // bytes per pixel in each source plane
+
+    int slice_count() const { return num_h_slices * num_v_slices; }
+    int64_t frame_bytes() const;               // tightly packed (av_image_get_buffer_size(align=1))
+    void plane_dims(int i, int *rows, int *row_bytes) const;
+};
+
+struct EncOptions {
+    int width, height; std::string pix_fmt; int gop_size, level, slices, coder, context, slicecrc;
+};
+
+// encode_init: returns 0 or a negative AVERROR-style code with a message in err
+int resolve_encoder(const EncOptions &o, Config &c, std::string &err);
+// read_extra_header + pix_fmt selection of read_header (version >= 2 streams)
+int parse_extradata(const uint8_t *data, int size, int width, int height, Config &c, std::string &err);
+
+std::vector<uint8_t> write_extradata(const Config &c);
+
+void default_state_tables(uint8_t zero_state[256], uint8_t one_state[256]);
+// transition tables a slice coder runs with: default table, custom entries 1..255 overriding for AC_RANGE_CUSTOM
+void coder_state_tables(const Config &c, uint8_t zero_state[256], uint8_t one_state[256]);
+
+// (probability state, bit) pairs, packed p | bit<<8, of everything a slice codes BEFORE its first sample:
+// [keyframe bit on slice 0] + slice header symbols (version 3) [+ the state-129 bit in golomb mode].
+std::vector<uint16_t> slice_prefix_decisions(const Config &c, int slice_index, bool key_frame,
+                                             int sar_num, int sar_den, int picture_structure);
+
+void slice_rect(const Config &c, int i, int *x0, int *y0, int *w, int *h);
+
+// Builds every geometry table the kernels use.
+struct Tables {
+    Layout layout;
+    std::vector<SliceGeom> slices;
+    std::vector<LineDesc>  lines;       // all slices, coding order inside a slice
+    std::vector<int32_t>   pc_lines;    // per slice, per plane context: slice-relative line indices
+    std::vector<TileDesc>  tiles;
+};
+constexpr int kTileRows = 16;
+void build_tables(const Config &c, Tables &t);
+
+uint32_t crc32_ieee(uint32_t crc, const uint8_t *buf, size_t len);
+
+} // namespace ffv1

@@ -1,0 +1,184 @@
+/*
+ * ffv1_b200.h -- C ABI of the B200-native FFV1 encode/decode hot path (libffv1_b200.so).
+ *
+ * This is the drop-in boundary: plain C, pointers and sizes only.  Each entry point replaces one
+ * callback of the reference's AVCodec pair (file:line relative to the reference tree, an FFmpeg
+ * 3.0.git checkout):
+ *
+ *   ffv1b200_enc_open            <- ff_ffv1_encoder.init    = encode_init   libavcodec/ffv1enc.c:669-1029
+ *   ffv1b200_enc_extradata       <- avctx->extradata written by write_extradata       ffv1enc.c:545-619
+ *   ffv1b200_enc_encode_*        <- ff_ffv1_encoder.encode2 = encode_frame  libavcodec/ffv1enc.c:1222-1373
+ *                                   (batched: CAP_DELAY lets a codec hold frames, ffv1enc.c:1424)
+ *   ffv1b200_enc_close           <- ff_ffv1_encoder.close   = encode_close  libavcodec/ffv1enc.c:1375-1379
+ *   ffv1b200_dec_open            <- ff_ffv1_decoder.init    = decode_init   libavcodec/ffv1dec.c:876-893
+ *   ffv1b200_dec_decode_*        <- ff_ffv1_decoder.decode  = decode_frame  libavcodec/ffv1dec.c:895-1035
+ *   ffv1b200_dec_close           <- ff_ffv1_decoder.close   = ff_ffv1_close libavcodec/ffv1.c:205-243
+ *
+ * The AVCodec shim that binds these into libavcodec is integration/ffv1_b200_avcodec.c.
+ * There is NO CPU fallback: every compute entry point fails with FFV1B200_ERR_EXTERNAL when no CUDA
+ * device / sm_100 kernel image is usable.
+ *
+ * Return values follow libavcodec: 0 (or a non-negative count) on success, negative AVERROR-style code on
+ * failure.  ffv1b200_strerror() maps them to text; ffv1b200_last_error() gives the detailed message of the
+ * last failure on the calling thread (what the reference would have sent to av_log(AV_LOG_ERROR)).
+ */
+#ifndef FFV1_B200_H
+#define FFV1_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FFV1B200_ERR_EINVAL      (-22)           /* AVERROR(EINVAL)  */
+#define FFV1B200_ERR_ENOMEM      (-12)           /* AVERROR(ENOMEM)  */
+#define FFV1B200_ERR_ENOSYS      (-38)           /* AVERROR(ENOSYS)  */
+#define FFV1B200_ERR_INVALIDDATA (-1094995529)   /* AVERROR_INVALIDDATA */
+#define FFV1B200_ERR_EXTERNAL    (-542398533)    /* AVERROR_EXTERNAL: CUDA runtime / device failure */
+#define FFV1B200_ERR_BUFFER_TOO_SMALL (-1397118274) /* AVERROR_BUFFER_TOO_SMALL: caller's output buffer */
+
+#define FFV1B200_PKT_FLAG_KEY 1                  /* = AV_PKT_FLAG_KEY */
+
+typedef struct FFV1B200Encoder FFV1B200Encoder;
+typedef struct FFV1B200Decoder FFV1B200Decoder;
+
+/* Encoder options: exactly what encode_init reads from AVCodecContext + the private AVOptions
+ * (ffv1enc.c:1383-1399; SURVEY.md 8(b) "Inputs read from AVCodecContext"). */
+typedef struct FFV1B200EncParams {
+    int width, height;        /* AVCodecContext.width/height */
+    const char *pix_fmt;      /* av_get_pix_fmt_name(avctx->pix_fmt), e.g. "yuv420p", "yuv422p10le", "gbrp14le", "bgr0" */
+    int gop_size;             /* AVCodecContext.gop_size (-g); frame n is a keyframe iff gop_size==0 || n % gop_size == 0 */
+    int level;                /* AVCodecContext.level: -1 unset, 0/1/3 = FFV1 version */
+    int slices;               /* AVCodecContext.slices: 0 unset */
+    int coder;                /* private option "coder":   0 rice, 1 ac (=2), 2 range_tab, -2 range_def */
+    int context;              /* private option "context": 0 small (666 contexts), 1 large (7563 contexts) */
+    int slicecrc;             /* private option "slicecrc": -1 auto, 0, 1 */
+    int device;               /* CUDA device ordinal */
+    int max_batch_frames;     /* capacity of one ffv1b200_enc_encode_* call (0 = default 64) */
+    int64_t first_picture_number; /* picture_number of the first frame this instance will see (GOP-aligned multi-GPU
+                                     shards continue the global count); normally 0 */
+} FFV1B200EncParams;
+
+/* Per-frame side information that is coded into every slice header (ffv1enc.c:1044-1049). */
+typedef struct FFV1B200FrameProps {
+    int sar_num, sar_den;     /* AVFrame.sample_aspect_ratio; rawvideo default 0/1 */
+    int picture_structure;    /* 3 progressive, 1 interlaced TFF, 2 interlaced BFF */
+} FFV1B200FrameProps;
+
+/* One encoded packet inside the caller's output buffer. */
+typedef struct FFV1B200Packet {
+    int64_t offset;           /* byte offset inside the output buffer */
+    int32_t size;             /* pkt->size */
+    int32_t flags;            /* FFV1B200_PKT_FLAG_KEY on keyframes (ffv1enc.c:1368) */
+    int64_t picture_number;   /* coded picture number (pts order = coded order) */
+} FFV1B200Packet;
+
+/* Timing / counters of the last encode call (device times from CUDA events on the codec's stream). */
+typedef struct FFV1B200EncStats {
+    int   frames;
+    int   kernel_launches;         /* launches of this library's kernels in the call */
+    float ms_total;                /* first H2D (or first kernel) .. last D2H, device clock */
+    float ms_pixel_kernel;         /* per-pixel pass (prediction/context/residual) */
+    float ms_model_kernel;         /* adaptive-state replay  */
+    float ms_coder_kernel;         /* range-coder interval arithmetic / golomb bit packing */
+    float ms_pack_kernel;          /* packet assembly + CRC */
+    int64_t h2d_bytes, d2h_bytes;
+    int64_t samples;               /* coded samples */
+    int64_t decisions;             /* binary range-coder decisions (0 in golomb mode) */
+    int64_t packet_bytes;
+    int   retries;                 /* internal re-runs after a scratch buffer had to grow */
+} FFV1B200EncStats;
+
+const char *ffv1b200_version(void);
+const char *ffv1b200_strerror(int err);
+const char *ffv1b200_last_error(void);
+/* Number of usable CUDA devices with an sm_100 kernel image, or a negative error (never a CPU fallback). */
+int ffv1b200_device_count(void);
+
+/* ------------------------------------------------------------------ encoder */
+
+int  ffv1b200_enc_open(FFV1B200Encoder **enc, const FFV1B200EncParams *params);
+void ffv1b200_enc_close(FFV1B200Encoder *enc);
+
+/* avctx->extradata: valid until close.  size 0 for FFV1 version 0/1 (in-band header). */
+int  ffv1b200_enc_extradata(const FFV1B200Encoder *enc, const uint8_t **data, int *size);
+
+/* Resolved configuration, for logging / INTEGRATION (what encode_init derived). */
+typedef struct FFV1B200EncInfo {
+    int version, micro_version, ac, colorspace, bits_per_raw_sample, chroma_planes, chroma_h_shift, chroma_v_shift,
+        transparency, num_h_slices, num_v_slices, slice_count, ec, intra, context_count, plane_count, max_batch_frames;
+    int64_t samples_per_frame;   /* coded samples (chroma overlap of unaligned slices included) */
+    int64_t frame_bytes;         /* tightly packed input frame size */
+} FFV1B200EncInfo;
+int  ffv1b200_enc_info(const FFV1B200Encoder *enc, FFV1B200EncInfo *info);
+
+void ffv1b200_enc_set_frame_props(FFV1B200Encoder *enc, const FFV1B200FrameProps *props);
+
+/* Encode nframes (1..max_batch_frames) consecutive frames held in HOST memory.
+ *   planes[f*4 + i], linesizes[f*4 + i] : AVFrame.data[i] / linesize[i] of frame f (unused planes NULL/0).
+ *   out/out_cap    : host buffer receiving the packets back to back.
+ *   pkts[nframes]  : filled with offset/size/flags per frame, in input order.
+ * Blocking.  Returns nframes, or a negative error; FFV1B200_ERR_BUFFER_TOO_SMALL leaves the encoder state
+ * unchanged (the call may be repeated with a larger buffer; *needed, if non-NULL, receives the size). */
+int  ffv1b200_enc_encode_host(FFV1B200Encoder *enc, int nframes,
+                              const uint8_t *const *planes, const int *linesizes,
+                              uint8_t *out, size_t out_cap, FFV1B200Packet *pkts, size_t *needed);
+
+/* Same, for frames already resident in DEVICE memory (AV_PIX_FMT_CUDA AVFrames: data[i] are CUdeviceptr,
+ * hwcontext_cuda.h:31-40).  Packets are produced in device memory (d_out, d_out_cap bytes); sizes/offsets are
+ * returned in pkts (host).  If stream is non-NULL it is a cudaStream_t the work is ordered on. */
+int  ffv1b200_enc_encode_device(FFV1B200Encoder *enc, int nframes,
+                                const void *const *d_planes, const int *linesizes,
+                                void *d_out, size_t d_out_cap, FFV1B200Packet *pkts, size_t *needed,
+                                void *stream);
+
+int  ffv1b200_enc_stats(const FFV1B200Encoder *enc, FFV1B200EncStats *stats);
+
+/* Test hook: run only the per-pixel pass on frames already uploaded by the last encode call and copy the
+ * (context<<16 | diff&0xffff) records of one frame/slice (coding order) to host.  Returns the record count. */
+int64_t ffv1b200_enc_debug_records(FFV1B200Encoder *enc, int frame_in_batch, int slice, uint32_t *dst, int64_t cap);
+
+/* ------------------------------------------------------------------ decoder */
+
+typedef struct FFV1B200DecParams {
+    int width, height;              /* AVCodecContext.width/height (container) */
+    const uint8_t *extradata;       /* AVCodecContext.extradata (version >= 2 streams) */
+    int extradata_size;
+    int device;
+    int max_batch_frames;           /* 0 = default 64 */
+} FFV1B200DecParams;
+
+typedef struct FFV1B200DecInfo {
+    int version, micro_version, ac, colorspace, bits_per_raw_sample, chroma_planes, chroma_h_shift, chroma_v_shift,
+        transparency, num_h_slices, num_v_slices, ec, intra;
+    char pix_fmt[32];               /* the AVPixelFormat name read_header would select (ffv1dec.c:698-786) */
+    int64_t frame_bytes;            /* tightly packed output frame size */
+} FFV1B200DecInfo;
+
+int  ffv1b200_dec_open(FFV1B200Decoder **dec, const FFV1B200DecParams *params);
+void ffv1b200_dec_close(FFV1B200Decoder *dec);
+int  ffv1b200_dec_info(const FFV1B200Decoder *dec, FFV1B200DecInfo *info);
+
+/* Decode npackets consecutive packets (host memory) into tightly packed frames (host memory):
+ *   pkt_data[i]/pkt_size[i]  : AVPacket.data/size
+ *   out + i*frame_bytes      : decoded frame i (planes back to back, as av_image_copy_to_buffer(align=1))
+ *   key_flags[i]             : AVFrame.key_frame;  damaged[i] : bit s set = slice s failed CRC/end check
+ *                              (and was concealed from the previous frame, ffv1dec.c:998-1021)
+ * The first packet of a shard must be a keyframe (ffv1dec.c:930-935) unless state carried over from the previous call. */
+int  ffv1b200_dec_decode_host(FFV1B200Decoder *dec, int npackets,
+                              const uint8_t *const *pkt_data, const int *pkt_size,
+                              uint8_t *out, size_t out_cap, int *key_flags, uint64_t *damaged);
+
+typedef struct FFV1B200DecStats {
+    int frames, kernel_launches;
+    float ms_total, ms_decode_kernel;
+    int64_t h2d_bytes, d2h_bytes;
+} FFV1B200DecStats;
+int  ffv1b200_dec_stats(const FFV1B200Decoder *dec, FFV1B200DecStats *stats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FFV1_B200_H */

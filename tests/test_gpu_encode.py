@@ -1,0 +1,100 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA encoder, called through the C ABI, must produce
+extradata and packets byte-identical to the oracle (which is pinned to the reference build) on the whole matrix,
+including state-carry-over non-keyframes, batches that split GOPs, and the per-pixel kernel's records."""
+import hashlib, json, os, numpy as np, pytest
+from cases import CASES, make_frames
+from oracle import ffv1_oracle as O
+
+pytestmark = pytest.mark.gpu
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "ref_packets.json")))
+RANGE_CASES = [c for c in CASES if O.resolve(c[1], c[2], c[3], **c[4]).ac != 0 and O.resolve(c[1], c[2], c[3], **c[4]).version == 3]
+
+def md5(b):
+    return hashlib.md5(bytes(b)).hexdigest()
+
+def gpu_opts(opts):
+    o = dict(opts)
+    if "gop" in o:
+        o["g"] = o.pop("gop")
+    return o
+
+@pytest.fixture(scope="module")
+def B():
+    import ffv1_b200
+    assert ffv1_b200.device_count() >= 1
+    return ffv1_b200
+
+@pytest.mark.parametrize("case", RANGE_CASES, ids=[c[0] for c in RANGE_CASES])
+def test_packets_match_oracle(B, case):
+    cid, w, h, fmt, opts, kind, n = case
+    frames = make_frames(case)
+    o = O.Encoder(w, h, fmt, **opts)
+    g = B.FFV1Encoder(w, h, fmt, max_batch_frames=4, **gpu_opts(opts))       # batches of 4 split the GOPs
+    assert g.extradata == o.extradata
+    got = g.encode_batch(frames)
+    gold = GOLD[cid]
+    for i, f in enumerate(frames):
+        exp, key = o.encode(f)
+        assert got[i][1] == key, "key flag of frame %d" % i
+        assert len(got[i][0]) == len(exp), "packet %d: %d bytes, oracle %d" % (i, len(got[i][0]), len(exp))
+        assert got[i][0] == exp, "packet %d differs" % i
+        if md5(b"".join(x.tobytes() for x in frames)) == gold["input_md5"]:
+            assert [len(got[i][0]), md5(got[i][0])] == gold["packets"][i][:2]   # the reference build's own output
+
+@pytest.mark.parametrize("case", [c for c in CASES if c[0] in ("c2_gop_range_24sl", "c3_422p10_ctx1", "c4_gbrp14_30sl",
+                                                              "bgra_range_ctx1", "yuv410p_odd", "fate_v3_444p16", "ya8")],
+                         ids=lambda c: c[0])
+def test_pixel_kernel_records(B, case):
+    """k_pixel in isolation: (context, folded residual) records of every slice == oracle's encode_line inputs"""
+    cid, w, h, fmt, opts, kind, n = case
+    frames = make_frames(case)[:2]
+    g = B.FFV1Encoder(w, h, fmt, max_batch_frames=2, **gpu_opts(opts))
+    g.encode_batch(frames)
+    p = O.resolve(w, h, fmt, **opts)
+    for fi, f in enumerate(frames):
+        for s in range(p.num_h_slices * p.num_v_slices):
+            exp = O.slice_records(p, f, fmt, s)
+            got = g.debug_records(fi, s)
+            assert len(got) == len(exp)
+            assert np.array_equal(got, exp), "frame %d slice %d: first mismatch at %d" % (fi, s, int(np.argmax(got != exp)))
+
+def test_encode2_delay_and_flush(B):
+    case = [c for c in CASES if c[0] == "c2_gop_range_24sl"][0]
+    cid, w, h, fmt, opts, kind, n = case
+    frames = make_frames(case)
+    o = O.Encoder(w, h, fmt, **opts)
+    g = B.FFV1Encoder(w, h, fmt, max_batch_frames=4, **gpu_opts(opts))
+    out = []
+    for f in frames:
+        p = g.encode2(f)
+        if p is not None:
+            out.append(p)
+    out += g.flush()
+    assert len(out) == len(frames)
+    for i, f in enumerate(frames):
+        assert out[i][0] == o.encode(f)[0]
+
+def test_s2_noisy1080_c2_golden(B):
+    """BASELINE.json configs[1] at full size against the reference build's packets (SURVEY App. B known answers)"""
+    from oracle import synth
+    g0 = GOLD["s2_noisy1080_c2"]
+    gen = synth.Noisy(1920, 1080, "yuv420p", 1234)
+    frames = [gen.next() for _ in range(32)]
+    if md5(b"".join(f.tobytes() for f in frames)) != g0["input_md5"]:
+        pytest.skip("synthetic input differs from the fixture's")
+    enc = B.FFV1Encoder(1920, 1080, "yuv420p", g=16, level=3, coder=1, context=0, slices=24, max_batch_frames=24)
+    assert md5(enc.extradata) == g0["extradata_md5"]
+    got = enc.encode_batch(frames)
+    for i in range(32):
+        assert [len(got[i][0]), md5(got[i][0]), int(got[i][1])] == g0["packets"][i], "packet %d" % i
+
+def test_errors_match_reference_behaviour(B):
+    with pytest.raises(B.FFV1Error) as e:
+        B.FFV1Encoder(1920, 1080, "yuv420p", g=16, level=3, coder=1, slices=32)
+    assert e.value.code == -38          # AVERROR(ENOSYS) "Unsupported number 32 of slices"
+    with pytest.raises(B.FFV1Error) as e:
+        B.FFV1Encoder(1920, 1080, "rgb48le", g=16, level=3)
+    assert e.value.code == -38
+    with pytest.raises(B.FFV1Error) as e:
+        B.FFV1Encoder(352, 288, "yuv420p", level=1, slices=4)
+    assert e.value.code == -22
