@@ -197,8 +197,8 @@ class FFV1Encoder:
     def encode_device(self, plane_ptrs, linesizes, d_out_ptr, d_out_cap, nframes, stream=None):
         """Frames already in device memory. plane_ptrs/linesizes: flat sequences of 4*nframes ints.
         Returns the Packet array (offsets into d_out)."""
-        planes = (ctypes.c_void_p * (4 * nframes))(*plane_ptrs)
-        ls = (ctypes.c_int * (4 * nframes))(*linesizes)
+        planes = plane_ptrs if isinstance(plane_ptrs, ctypes.Array) else (ctypes.c_void_p * (4 * nframes))(*plane_ptrs)
+        ls = linesizes if isinstance(linesizes, ctypes.Array) else (ctypes.c_int * (4 * nframes))(*linesizes)
         pk = (Packet * nframes)()
         needed = ctypes.c_size_t()
         _check(lib().ffv1b200_enc_encode_device(self._h, nframes, planes, ls, d_out_ptr, d_out_cap, pk, ctypes.byref(needed), stream))
