@@ -1,12 +1,11 @@
 // ffv1_enc_kernels.cu -- hand-written sm_100a kernels of the FFV1 encode hot path.
 //
 //   k_pixel      per-pixel pass: sample fetch (+RCT), slice-local neighbourhood, get_context, median predictor,
-//                residual, sign flip, fold  ->  (context<<16 | diff) records in coding order + decisions per line.
+//                residual, sign flip, fold  ->  (context<<16 | diff) records in coding order.
 //                Reference: encode_plane / encode_rgb_frame / encode_line up to the symbol call
 //                (ffv1enc.c:373-473, 271-321; ffv1.h:148-190).  HBM bound: 1-2 B read + 4 B written per sample.
-//   k_scan_*     exclusive scans that place every line's decisions in one compact decision stream.
 //   k_replay     adaptive-state replay: put_symbol_inline's binarisation (ffv1enc.c:185-231) applied to the
-//                per-context 32-byte states, one warp per (GOP segment, slice, plane context), lane = state slot.
+//                per-context 32-byte states, one warp per (GOP segment, slice, plane context), lane = sample.
 //                Emits the (probability, bit) pair of every binary decision; carries state across frames of a GOP
 //                (the reference's "P-frames": state is only reset on keyframes, ffv1enc.c:1171-1172).
 //   k_rangecode  put_rac / renorm_encoder / ff_rac_terminate (rangecoder.h:52-102, rangecoder.c:104-116):
@@ -81,13 +80,11 @@ k_pixel(const EncDeviceTables T, const EncBatch B)
     constexpr bool RGB = (SRC == SRC_RGB32 || SRC == SRC_GBRP16);
 
     int16_t *s_quant = reinterpret_cast<int16_t *>(smem_raw);
-    uint32_t *s_cnt = reinterpret_cast<uint32_t *>(s_quant + NIN * 256);
     const int npl = td.nplanes, nrows = td.nrows;
-    int16_t *S = reinterpret_cast<int16_t *>(s_cnt + 4 * kTileRows);
+    int16_t *S = s_quant + NIN * 256;
     const int plane_stride = (kTileRows + 2) * kPixelRowElems;
 
     for (int i = tid; i < NIN * 256; i += kPixelThreads) s_quant[i] = T.quant[i];
-    for (int i = tid; i < 4 * kTileRows; i += kPixelThreads) s_cnt[i] = 0;
 
     const uint8_t *pl[4];
     int32_t ls[4];
@@ -136,7 +133,6 @@ k_pixel(const EncDeviceTables T, const EncBatch B)
                 const int16_t *top2 = top - kPixelRowElems;
                 const LineDesc ld = lines[td.line_first + r * td.line_step + pp];
                 uint32_t *rec_line = rec_slice + ld.rec_off + cx0;
-                uint32_t cnt = 0;
                 for (int gi = lane; gi < groups; gi += 32) {
                     const int x = gi << 2;
                     // cur[x-2..x+3], top[x-1..x+4], top2[x..x+3]
@@ -171,8 +167,6 @@ k_pixel(const EncDeviceTables T, const EncBatch B)
                         int diff = X - mid3(Lf, Lf + Tp - LT, Tp);
                         if (ctx < 0) { ctx = -ctx; diff = -diff; }
                         diff = (diff << (32 - bits)) >> (32 - bits);        // fold(): sign-extend the low `bits` bits
-                        const int ad = abs(diff);
-                        if (x + i < cw) cnt += diff ? (uint32_t)(2 * (31 - __clz(ad)) + 3) : 1u;
                         out[i] = ((uint32_t)ctx << 16) | ((uint32_t)diff & 0xFFFFu);
                     }
                     if (x + 3 < cw) {
@@ -183,24 +177,15 @@ k_pixel(const EncDeviceTables T, const EncBatch B)
                             if (x + i < cw) rec_line[x + i] = out[i];
                     }
                 }
-                cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);
-                if (lane == 0) s_cnt[pp * kTileRows + r] += cnt;     // each (plane,row) is owned by one warp
             }
         }
-    }
-    __syncthreads();
-    // decisions per line (range-coder mode; ignored by the golomb path)
-    uint32_t *cnt_slice = B.line_cnt + (size_t)f * L.lines_per_frame + g.line_first;
-    for (int i = tid; i < npl * nrows; i += kPixelThreads) {
-        const int pp = i / nrows, r = i - pp * nrows;
-        cnt_slice[td.line_first + r * td.line_step + pp] = s_cnt[pp * kTileRows + r];
     }
 }
 
 int pixel_smem_bytes(const Layout &L)
 {
     const int planes = L.rgb ? L.nplanes : 1;
-    return L.ctx_inputs * 256 * 2 + 4 * kTileRows * 4 + planes * (kTileRows + 2) * kPixelRowElems * 2;
+    return L.ctx_inputs * 256 * 2 + planes * (kTileRows + 2) * kPixelRowElems * 2;
 }
 
 template <int SRC, int NIN>
@@ -222,8 +207,12 @@ void launch_pixel(const EncDeviceTables &t, const EncBatch &b, cudaStream_t s)
 }
 
 // =================================================================================================
-// k_scan_lines / k_scan_slices
+// k_replay: adaptive state replay, one warp per (GOP segment, slice, plane context) chain
 // =================================================================================================
+// The 32 lanes take 32 consecutive samples of a line.  Samples that fall into DIFFERENT contexts touch disjoint
+// 32-byte state rows, so they are replayed in parallel; samples sharing a context are ordered by their position
+// (match.any groups -> rank -> one round per rank).  Inside one symbol (ffv1enc.c:202-229) all decisions hit
+// distinct state slots as long as e <= 9, so their probability loads are issued together.
 __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane)
 {
 #pragma unroll
@@ -234,117 +223,133 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane)
     return v;
 }
 
-// one warp per (frame, slice): exclusive scan of the slice's per-line decision counts
-__global__ void __launch_bounds__(256) k_scan_lines(const EncDeviceTables T, const EncBatch B)
-{
-    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    const int n = B.nframes * T.layout.nslices;
-    if (gw >= n) return;
-    const int f = gw / T.layout.nslices, s = gw - f * T.layout.nslices;
-    const SliceGeom &g = T.slices[s];
-    const uint32_t *cnt = B.line_cnt + (size_t)f * T.layout.lines_per_frame + g.line_first;
-    uint32_t *off = B.line_off + (size_t)f * T.layout.lines_per_frame + g.line_first;
-    uint32_t run = 0;
-    for (int i0 = 0; i0 < g.nlines; i0 += 32) {
-        const int i = i0 + lane;
-        const uint32_t v = i < g.nlines ? cnt[i] : 0;
-        const uint32_t inc = warp_incl_scan(v, lane);
-        if (i < g.nlines) off[i] = run + inc - v;
-        run += __shfl_sync(0xFFFFFFFFu, inc, 31);
-    }
-    if (lane == 0) B.slice_ndec[gw] = run;
-}
+constexpr int kStateStride = 36;      // shared-memory bytes per context row: 9 words, so consecutive contexts start in different banks
+constexpr int kOnePowBytes = 33 * 256;
 
-// single CTA: exclusive scan over all (frame, slice) of the 8-entry-aligned decision counts
-__global__ void __launch_bounds__(1024) k_scan_slices(const EncDeviceTables T, const EncBatch B)
-{
-    __shared__ unsigned long long s_warp[32];
-    __shared__ unsigned long long s_run;
-    const int n = B.nframes * T.layout.nslices;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_run = 0;
-    __syncthreads();
-    for (int i0 = 0; i0 < n; i0 += 1024) {
-        const int i = i0 + tid;
-        unsigned long long v = i < n ? (((unsigned long long)B.slice_ndec[i] + 7ull) & ~7ull) : 0ull;
-        unsigned long long inc = v;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            unsigned long long o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
-            if (lane >= d) inc += o;
-        }
-        if (lane == 31) s_warp[warp] = inc;
-        __syncthreads();
-        if (warp == 0) {
-            unsigned long long w = s_warp[lane], winc = w;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                unsigned long long o = __shfl_up_sync(0xFFFFFFFFu, winc, d);
-                if (lane >= d) winc += o;
-            }
-            s_warp[lane] = winc - w;       // exclusive prefix of the warp totals
-        }
-        __syncthreads();
-        const unsigned long long base = s_run + s_warp[warp];
-        if (i < n) B.slice_base[i] = base + inc - v;
-        __syncthreads();
-        if (tid == 1023) s_run = base + inc;
-        __syncthreads();
-    }
-    if (tid == 0) {
-        B.status[3] = s_run;                                   // entries used
-        if (s_run > B.dec_capacity) B.status[0] = s_run;       // overflow: the host grows dec[] and re-runs
-    }
-}
+template <bool SMEM> struct StateIO;
+template <> struct StateIO<true> {
+    static __device__ __forceinline__ uint32_t ld(const uint8_t *p) { return *p; }
+    static __device__ __forceinline__ void st(uint8_t *p, uint32_t v) { *p = (uint8_t)v; }
+};
+template <> struct StateIO<false> {   // state rows in global memory, cached by the SM's L1: only this warp touches them
+    static __device__ __forceinline__ uint32_t ld(const uint8_t *p) { return *p; }
+    static __device__ __forceinline__ void st(uint8_t *p, uint32_t v) { *p = (uint8_t)v; }
+};
 
-void launch_scan(const EncDeviceTables &t, const EncBatch &b, cudaStream_t s)
+// large magnitudes (e > 9, ffv1enc.c:217-228): slots 1+9 and 22+9 repeat, so the decisions are walked one by one
+template <bool SMEM>
+__device__ __noinline__ void replay_symbol_slow(uint8_t *row, const uint8_t *lut, uint16_t *o, int d, bool wr)
 {
-    const int n = b.nframes * t.layout.nslices;
-    k_scan_lines<<<(n * 32 + 255) / 256, 256, 0, s>>>(t, b);
-    k_scan_slices<<<1, 1024, 0, s>>>(t, b);
-}
-
-// =================================================================================================
-// k_replay: adaptive state replay, one warp per (GOP segment, slice, plane context)
-// =================================================================================================
-// Lane <-> state slot permutation.  put_symbol_inline visits the slots in the order
-//   0 | 1..e+1 | 22+e-1 .. 22 | 11+e                                  (ffv1enc.c:202-229, e <= 9)
-// With slots 22..31 stored in REVERSE order in lanes 11..20 and slots 11..21 in lanes 21..31, that order is
-// increasing in lane index for every e, so the position of a lane's decision inside the symbol is simply
-// popc(visited_mask & lanes_below).
-__device__ __forceinline__ int lane_of_slot(int slot)
-{
-    return slot <= 10 ? slot : (slot >= 22 ? 42 - slot : slot + 10);
-}
-
-struct SymMasks { uint32_t visit, bits; int nd; };
-
-// masks in lane space for a symbol with e <= 9
-__device__ __forceinline__ SymMasks symbol_masks(int d)
-{
-    SymMasks m;
-    if (d == 0) { m.visit = 1u; m.bits = 1u; m.nd = 1; return m; }
+    typedef StateIO<SMEM> IO;
     const uint32_t a = (uint32_t)abs(d);
     const int e = 31 - __clz(a);
-    const uint32_t ones_e = (1u << e) - 1u;
-    const uint32_t mant = e ? (__brev(a & ones_e) >> (32 - e)) : 0u;    // bit k <- bit e-1-k of a
-    m.visit = 1u | (((2u << e) - 1u) << 1) | (ones_e << (21 - e)) | (1u << (21 + e));
-    m.bits = (ones_e << 1) | (mant << (21 - e)) | ((d < 0 ? 1u : 0u) << (21 + e));
-    m.nd = 2 * e + 3;
-    return m;
+    const uint32_t sign = d < 0 ? 0x100u : 0u;
+    int k = 1;
+    for (int i = 0; i < e; i++, k++) {
+        uint8_t *q = row + 1 + min(i, 9);
+        const uint32_t p = IO::ld(q);
+        if (wr) o[k] = (uint16_t)(p | 0x100u);
+        IO::st(q, lut[256 + p]);
+    }
+    {
+        uint8_t *q = row + 1 + 9;
+        const uint32_t p = IO::ld(q);
+        if (wr) o[k] = (uint16_t)p;
+        IO::st(q, lut[p]);
+        k++;
+    }
+    for (int i = e - 1; i >= 0; i--, k++) {
+        uint8_t *q = row + 22 + min(i, 9);
+        const uint32_t p = IO::ld(q), bit = ((a >> i) & 1u) << 8;
+        if (wr) o[k] = (uint16_t)(p | bit);
+        IO::st(q, lut[bit + p]);
+    }
+    uint8_t *q = row + 11 + 10;
+    const uint32_t p = IO::ld(q);
+    if (wr) o[k] = (uint16_t)(p | sign);
+    IO::st(q, lut[sign + p]);
 }
 
-template <bool SMEM_STATE, bool HIGH_E>
+// One round: every lane with `mine` set replays put_symbol_inline(c, state, d, is_signed=1) (ffv1enc.c:185-231) on
+// its own context row (rows of the participating lanes are distinct).  Emits p | bit<<8 per decision and updates
+// the row.  Loops are bounded by the largest exponent in the round (warp-uniform), loads are issued before the
+// dependent table lookups and stores.
+template <bool SMEM, int MAXE, bool HIGH_E>
+__device__ __forceinline__ void replay_round(bool mine, uint8_t *row, const uint8_t *lut, uint16_t *o, int d, bool wr)
+{
+    typedef StateIO<SMEM> IO;
+    const uint32_t a = (uint32_t)abs(d);
+    const int e = 31 - __clz(a | 1u);
+    const bool slow = HIGH_E && mine && e > 9;
+    const bool nz = mine && d != 0 && !slow;
+    const int el = nz ? e : -1;
+    const int emax = __reduce_max_sync(0xFFFFFFFFu, el);
+    const uint32_t sign = d < 0 ? 0x100u : 0u;
+    const bool wm = wr && mine, wz = wr && nz;
+
+    uint32_t p0 = 0, ps = 0, pu[MAXE + 1], pm[MAXE];
+    if (mine) p0 = IO::ld(row);
+    if (emax >= 0) {
+#pragma unroll
+        for (int i = 0; i <= MAXE; i++) {
+            if (i > emax) break;
+            pu[i] = (i <= el) ? IO::ld(row + 1 + i) : 0u;
+        }
+#pragma unroll
+        for (int i = 0; i < MAXE; i++) {
+            if (i >= emax) break;
+            pm[i] = (i < el) ? IO::ld(row + 22 + i) : 0u;
+        }
+        if (nz) ps = IO::ld(row + 11 + e);
+    }
+    {
+        const uint32_t bit = d == 0 ? 0x100u : 0u;                      // "is zero" flag
+        if (wm) o[0] = (uint16_t)(p0 | bit);
+        if (mine) IO::st(row, lut[bit + p0]);
+    }
+    if (emax >= 0) {
+#pragma unroll
+        for (int i = 0; i <= MAXE; i++) {
+            if (i > emax) break;
+            const uint32_t bit = i < el ? 0x100u : 0u;                  // unary exponent, then its terminator
+            if (i <= el) {
+                if (wz) o[1 + i] = (uint16_t)(pu[i] | bit);
+                IO::st(row + 1 + i, lut[bit + pu[i]]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < MAXE; i++) {
+            if (i >= emax) break;
+            const uint32_t bit = ((a >> i) & 1u) << 8;                  // mantissa, most significant bit first
+            if (i < el) {
+                if (wz) o[2 * e + 1 - i] = (uint16_t)(pm[i] | bit);
+                IO::st(row + 22 + i, lut[bit + pm[i]]);
+            }
+        }
+        if (nz) {
+            if (wz) o[2 * e + 2] = (uint16_t)(ps | sign);
+            IO::st(row + 11 + e, lut[sign + ps]);
+        }
+    }
+    if (HIGH_E && __any_sync(0xFFFFFFFFu, slow)) {
+        if (slow) replay_symbol_slow<SMEM>(row, lut, o, d, wr);
+    }
+}
+
+template <bool SMEM, int MAXE, bool HIGH_E>
 __global__ void __launch_bounds__(kReplayWarps * 32)
 k_replay(const EncDeviceTables T, const EncBatch B)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const Layout &L = T.layout;
     uint8_t *s_lut = smem_raw;                               // [0..255] zero_state, [256..511] one_state
+    uint8_t *s_pow = smem_raw + 512;                         // [k][p]: one_state applied k times, k = 0..32
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < 512; i += blockDim.x) s_lut[i] = T.trans_lut[i];
+    for (int i = threadIdx.x; i < 512 / 4; i += blockDim.x)
+        reinterpret_cast<uint32_t *>(s_lut)[i] = reinterpret_cast<const uint32_t *>(T.trans_lut)[i];
+    for (int i = threadIdx.x; i < kOnePowBytes / 4; i += blockDim.x)
+        reinterpret_cast<uint32_t *>(s_pow)[i] = reinterpret_cast<const uint32_t *>(T.one_pow)[i];
     __syncthreads();
-    if (B.status[0]) return;                                 // decision stream does not fit: host will retry
 
     const int nchains = B.nseg * L.nslices * L.npc;
     const int chain = blockIdx.x * kReplayWarps + warp;
@@ -353,151 +358,171 @@ k_replay(const EncDeviceTables T, const EncBatch B)
     const int s = (chain / L.npc) % L.nslices;
     const int seg = chain / (L.npc * L.nslices);
     const SliceGeom &g = T.slices[s];
+    const int nl = g.pc_nlines[pc];
+    if (nl == 0) return;
     const int f0 = B.seg_first[seg], f1 = B.seg_first[seg + 1];
-    const size_t state_bytes = (size_t)L.ctx_count * 32;
+    const int nctx = L.ctx_count;
+    constexpr int RS = SMEM ? kStateStride : 32;
+    const int state_smem = (nctx * kStateStride + 15) & ~15;
 
     uint8_t *st;
-    if (SMEM_STATE) st = smem_raw + 512 + (size_t)warp * state_bytes;
-    else            st = B.state_seg + ((size_t)(seg * L.nslices + s) * L.npc + pc) * state_bytes;
+    if (SMEM) st = smem_raw + 512 + kOnePowBytes + (size_t)warp * state_smem;
+    else      st = B.state_seg + ((size_t)(seg * L.nslices + s) * L.npc + pc) * ((size_t)nctx * 32);
 
     // ---- initial state: 128 on keyframes (ffv1.c:177-202), else carried over from the previous batch
+    const size_t coff = ((size_t)s * L.npc + pc) * ((size_t)nctx * 32);
     {
-        const size_t coff = ((size_t)s * L.npc + pc) * state_bytes;
         const bool key = B.frame_key[f0];
-        uint32_t *st4 = reinterpret_cast<uint32_t *>(st);
         const uint32_t *in4 = reinterpret_cast<const uint32_t *>(B.carry_in + coff);
-        for (size_t i = lane; i < state_bytes / 4; i += 32) st4[i] = key ? 0x80808080u : in4[i];
+        uint32_t *st4 = reinterpret_cast<uint32_t *>(st);
+        for (int i = lane; i < nctx * 8; i += 32)
+            st4[(i >> 3) * (RS / 4) + (i & 7)] = key ? 0x80808080u : in4[i];
         __syncwarp();
     }
 
     const uint32_t lt_mask = (1u << lane) - 1u;
     const int32_t *my_lines = T.pc_lines + g.pc_line_first[pc];
-    const int nl = g.pc_nlines[pc];
+    const LineDesc *slice_lines = T.lines + g.line_first;
+    const uint32_t cap = g.dec_cap[pc];
+    uint32_t need = 0;
+    unsigned long long ndec = 0;
+    bool overflow = false;
 
     for (int f = f0; f < f1; f++) {
         const uint32_t *rec_slice = B.rec + (size_t)f * L.rec_per_frame + g.rec_first;
-        const uint32_t *loff = B.line_off + (size_t)f * L.lines_per_frame + g.line_first;
-        uint16_t *dec_slice = B.dec + B.slice_base[f * L.nslices + s];
+        uint16_t *out = B.dec + (size_t)f * L.dec_per_frame + g.dec_off[pc];
+        uint32_t *run_cnt = B.run_cnt + (size_t)f * L.runs_per_frame + g.run_first;
+        uint32_t pos = 0, run_start = 0;
+        LineDesc ld = slice_lines[my_lines[0]];
+        uint32_t cur_run = ld.run;
+        uint32_t r_next = lane < ld.w ? rec_slice[ld.rec_off + lane] : 0u;
         for (int li = 0; li < nl; li++) {
-            const int line = my_lines[li];
-            const LineDesc ld = T.lines[g.line_first + line];
+            LineDesc ld_next = ld;
+            if (li + 1 < nl) ld_next = slice_lines[my_lines[li + 1]];
+            if (ld.run != cur_run) {                                     // a run of this plane context ended
+                if (lane == 0) run_cnt[cur_run] = pos - run_start;
+                pos = (pos + 7u) & ~7u;
+                run_start = pos; cur_run = ld.run;
+            }
             const uint32_t *recp = rec_slice + ld.rec_off;
-            uint16_t *out = dec_slice + loff[line];
             const int w = ld.w;
             for (int x0 = 0; x0 < w; x0 += 32) {
                 const int n = min(32, w - x0);
-                const uint32_t r = (lane < n) ? recp[x0 + lane] : 0u;
-                const int d_own = (int)(int16_t)(r & 0xFFFFu);
-                SymMasks m = symbol_masks(d_own);
-                int e_own = 0;
-                if (HIGH_E) {
-                    e_own = d_own ? 31 - __clz((uint32_t)abs(d_own)) : 0;
-                    if (e_own > 9) m.nd = 2 * e_own + 3;
-                }
-                uint32_t incl = warp_incl_scan(lane < n ? (uint32_t)m.nd : 0u, lane);
-                const uint32_t pos_own = incl - (lane < n ? (uint32_t)m.nd : 0u);
+                const uint32_t r = r_next;
+                if (x0 + 32 < w)     r_next = (x0 + 32 + lane < w) ? recp[x0 + 32 + lane] : 0u;
+                else if (li + 1 < nl) r_next = lane < ld_next.w ? rec_slice[ld_next.rec_off + lane] : 0u;
+                const bool act = lane < n;
+                const int ctx = (int)(r >> 16);
+                const int d = (int)(int16_t)(r & 0xFFFFu);
+                uint32_t nd = 0;
+                if (act) nd = d ? (uint32_t)(2 * (31 - __clz((uint32_t)abs(d))) + 3) : 1u;
+                const uint32_t incl = warp_incl_scan(nd, lane);
                 const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-                for (int j = 0; j < n; j++) {
-                    const uint32_t rj = __shfl_sync(0xFFFFFFFFu, r, j);
-                    const uint32_t vis = __shfl_sync(0xFFFFFFFFu, m.visit, j);
-                    const uint32_t bts = __shfl_sync(0xFFFFFFFFu, m.bits, j);
-                    const uint32_t pj = __shfl_sync(0xFFFFFFFFu, pos_own, j);
-                    uint8_t *row = st + (size_t)(rj >> 16) * 32;
-                    if (HIGH_E) {
-                        const int ej = __shfl_sync(0xFFFFFFFFu, e_own, j);
-                        if (ej > 9) {
-                            // rare large-magnitude branch (ffv1enc.c:217-228): slots 1+9 and 22+9 are visited
-                            // repeatedly, so the decisions are walked one by one (warp-uniform loop).
-                            const int dj = (int)(int16_t)(rj & 0xFFFFu);
-                            const uint32_t a = (uint32_t)abs(dj);
-                            const int ndj = 2 * ej + 3;
-                            for (int k = 0; k < ndj; k++) {
-                                int slot, bit;
-                                if (k == 0) { slot = 0; bit = 0; }
-                                else if (k <= ej) { slot = 1 + min(k - 1, 9); bit = 1; }
-                                else if (k == ej + 1) { slot = 1 + 9; bit = 0; }
-                                else if (k <= 2 * ej + 1) { const int i = ej - 1 - (k - ej - 2); slot = 22 + min(i, 9); bit = (a >> i) & 1; }
-                                else { slot = 11 + 10; bit = dj < 0; }
-                                if (lane == lane_of_slot(slot)) {
-                                    const uint8_t p = row[lane];
-                                    out[pj + k] = (uint16_t)(p | (bit << 8));
-                                    row[lane] = s_lut[(bit << 8) + p];
-                                }
-                                __syncwarp();
-                            }
-                            continue;
-                        }
-                    }
-                    const uint8_t p = row[lane];
-                    const uint32_t bit = (bts >> lane) & 1u;
-                    if ((vis >> lane) & 1u) {
-                        out[pj + __popc(vis & lt_mask)] = (uint16_t)(p | (bit << 8));
-                        row[lane] = s_lut[(bit << 8) + p];
+                const bool wr = pos + total <= cap;                      // warp-uniform
+                overflow |= !wr;
+                uint16_t *o = out + pos + incl - nd;
+                uint8_t *row = st + (size_t)ctx * RS;
+                const int ctx0 = __shfl_sync(0xFFFFFFFFu, ctx, 0);
+                if (__all_sync(0xFFFFFFFFu, !act || (d == 0 && ctx == ctx0))) {
+                    // a run of zero residuals in one context: lane j sees the state after j "is zero" decisions
+                    const uint32_t p0 = StateIO<SMEM>::ld(st + (size_t)ctx0 * RS);
+                    if (act && wr) o[0] = (uint16_t)(s_pow[lane * 256 + p0] | 0x100u);
+                    __syncwarp();
+                    if (lane == 0) StateIO<SMEM>::st(st + (size_t)ctx0 * RS, s_pow[n * 256 + p0]);
+                    __syncwarp();
+                } else {
+                    const uint32_t grp = __match_any_sync(0xFFFFFFFFu, act ? (uint32_t)ctx : 0x10000u + lane);
+                    const int rank = __popc(grp & lt_mask);
+                    const int last = __reduce_max_sync(0xFFFFFFFFu, act ? rank : 0);
+                    for (int round = 0; round <= last; round++) {
+                        replay_round<SMEM, MAXE, HIGH_E>(act && rank == round, row, s_lut, o, d, wr);
+                        __syncwarp();
                     }
                 }
-                out += total;
+                pos += total;
+                ndec += total;
             }
+            ld = ld_next;
+        }
+        if (lane == 0) run_cnt[cur_run] = pos - run_start;
+        need = max(need, pos + 8u);
+    }
+    if (lane == 0) {
+        atomicAdd(&B.status[3], ndec);
+        if (overflow) {
+            const unsigned long long ns = g.pc_samples[pc];
+            atomicMax(&B.status[0], ((unsigned long long)need * 256ull + ns - 1) / ns + 1ull);
         }
     }
     // ---- hand the state to the next batch when this segment runs to the end of the batch
     if (f1 == B.nframes) {
         __syncwarp();
-        const size_t coff = ((size_t)s * L.npc + pc) * state_bytes;
         const uint32_t *st4 = reinterpret_cast<const uint32_t *>(st);
         uint32_t *out4 = reinterpret_cast<uint32_t *>(B.carry_out + coff);
-        for (size_t i = lane; i < state_bytes / 4; i += 32) out4[i] = st4[i];
+        for (int i = lane; i < nctx * 8; i += 32) out4[i] = st4[(i >> 3) * (RS / 4) + (i & 7)];
     }
 }
 
 int replay_smem_bytes(const Layout &L)
 {
-    return 512 + kReplayWarps * L.ctx_count * 32;
+    return 512 + kOnePowBytes + kReplayWarps * ((L.ctx_count * kStateStride + 15) & ~15);
+}
+
+template <bool SMEM>
+static void launch_replay_t(const EncDeviceTables &t, const EncBatch &b, cudaStream_t s, int grid, int smem)
+{
+    const int bits = t.layout.coded_bits;
+    if (bits <= 8)       k_replay<SMEM, 7, false><<<grid, kReplayWarps * 32, smem, s>>>(t, b);
+    else if (bits <= 10) k_replay<SMEM, 9, false><<<grid, kReplayWarps * 32, smem, s>>>(t, b);
+    else                 k_replay<SMEM, 9, true><<<grid, kReplayWarps * 32, smem, s>>>(t, b);
 }
 
 void launch_replay(const EncDeviceTables &t, const EncBatch &b, cudaStream_t s)
 {
     const int nchains = b.nseg * t.layout.nslices * t.layout.npc;
     const int grid = (nchains + kReplayWarps - 1) / kReplayWarps;
-    const bool high = t.layout.coded_bits > 10;
-    if (t.state_in_smem) {
-        const int smem = replay_smem_bytes(t.layout);
-        if (high) k_replay<true, true><<<grid, kReplayWarps * 32, smem, s>>>(t, b);
-        else      k_replay<true, false><<<grid, kReplayWarps * 32, smem, s>>>(t, b);
-    } else {
-        if (high) k_replay<false, true><<<grid, kReplayWarps * 32, 512, s>>>(t, b);
-        else      k_replay<false, false><<<grid, kReplayWarps * 32, 512, s>>>(t, b);
-    }
+    if (t.state_in_smem) launch_replay_t<true>(t, b, s, grid, replay_smem_bytes(t.layout));
+    else                 launch_replay_t<false>(t, b, s, grid, 512 + kOnePowBytes);
 }
 
 // =================================================================================================
-// k_rangecode: one interval coder per (frame, slice)
+// k_rangecode: one interval coder per (frame, slice); put_rac / renorm_encoder / ff_rac_terminate
+// (rangecoder.h:52-102, rangecoder.c:104-116).  The adaptive part already happened in k_replay, so a step is
+// range1 = range*p >> 8 plus the carry-propagating byte output.
 // =================================================================================================
 struct Rac {
     uint32_t low, range;
     int out_byte;        // -1: none pending
     uint32_t out_count;  // pending 0xFF bytes
-    uint8_t *buf;
-    uint32_t pos, cap;
+    uint32_t *buf;       // output, written one 32-bit word at a time
+    uint32_t pos, cap, acc;
 };
 
-__device__ __forceinline__ void rac_emit(Rac &c, int b)
+__device__ __forceinline__ void rac_emit(Rac &c, uint32_t b)
 {
-    if (c.pos < c.cap) c.buf[c.pos] = (uint8_t)b;
+    c.acc |= b << (8u * (c.pos & 3u));
     c.pos++;
+    if ((c.pos & 3u) == 0u) {
+        if (c.pos <= c.cap) c.buf[(c.pos >> 2) - 1u] = c.acc;
+        c.acc = 0u;
+    }
 }
 
 __device__ __forceinline__ void rac_shift(Rac &c)
 {
-    // one iteration of renorm_encoder's loop (rangecoder.h:52-75)
-    if (c.out_byte < 0) {
+    // one iteration of renorm_encoder's loop (rangecoder.h:52-75); the first branch is the common case
+    if (c.out_byte >= 0 && c.out_count == 0u && c.low <= 0xFF00u) {
+        rac_emit(c, (uint32_t)c.out_byte);
+        c.out_byte = c.low >> 8;
+    } else if (c.out_byte < 0) {
         c.out_byte = c.low >> 8;
     } else if (c.low <= 0xFF00u) {
-        rac_emit(c, c.out_byte);
-        for (; c.out_count; c.out_count--) rac_emit(c, 0xFF);
+        rac_emit(c, (uint32_t)c.out_byte);
+        for (; c.out_count; c.out_count--) rac_emit(c, 0xFFu);
         c.out_byte = c.low >> 8;
     } else if (c.low >= 0x10000u) {
-        rac_emit(c, c.out_byte + 1);
-        for (; c.out_count; c.out_count--) rac_emit(c, 0x00);
+        rac_emit(c, (uint32_t)(c.out_byte + 1) & 0xFFu);
+        for (; c.out_count; c.out_count--) rac_emit(c, 0x00u);
         c.out_byte = (c.low >> 8) & 0xFF;
     } else {
         c.out_count++;
@@ -516,7 +541,39 @@ __device__ __forceinline__ void rac_code(Rac &c, uint32_t entry)
     if (c.range < 0x100u) rac_shift(c);       // p >= 1 and range >= 0x100 before: at most one shift
 }
 
-__global__ void __launch_bounds__(128) k_rangecode(const EncDeviceTables T, const EncBatch B)
+__device__ __forceinline__ uint4 dec_load(const uint4 *src, uint32_t i, uint32_t nvec)
+{
+    return i < nvec ? __ldg(src + i) : make_uint4(0u, 0u, 0u, 0u);
+}
+
+// n decisions starting at a 16-byte aligned address.  Four 16-byte vectors (32 decisions) stay in flight; the loop
+// body is deliberately NOT unrolled beyond one 32-bit word (2 decisions): the 32 lanes of a warp sit at different
+// points of their streams, so a compact body that stays in the instruction cache beats a long unrolled one.
+__device__ __forceinline__ void rac_code_run(Rac &c, const uint4 *src, uint32_t n)
+{
+    const uint32_t nwords = (n + 1u) >> 1, nvec = (nwords + 3u) >> 2;
+    uint4 v0 = dec_load(src, 0, nvec), v1 = dec_load(src, 1, nvec), v2 = dec_load(src, 2, nvec), v3 = dec_load(src, 3, nvec);
+    uint32_t done = 0;
+#pragma unroll 1
+    for (uint32_t i = 0; i < nvec; i++) {
+        uint4 v = v0;
+        v0 = v1; v1 = v2; v2 = v3;
+        v3 = dec_load(src, i + 4u, nvec);
+        const uint32_t wc = min(4u, nwords - 4u * i);
+#pragma unroll 1
+        for (uint32_t w = 0; w < wc; w++) {
+            const uint32_t word = v.x;
+            v.x = v.y; v.y = v.z; v.z = v.w;
+            rac_code(c, word & 0xFFFFu);
+            if (done + 1u < n) rac_code(c, word >> 16);
+            done += 2u;
+        }
+    }
+}
+
+constexpr int kRangeThreads = 32;
+
+__global__ void __launch_bounds__(kRangeThreads) k_rangecode(const EncDeviceTables T, const EncBatch B)
 {
     const Layout &L = T.layout;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -528,36 +585,43 @@ __global__ void __launch_bounds__(128) k_rangecode(const EncDeviceTables T, cons
 
     Rac c;
     c.low = 0; c.range = 0xFF00u; c.out_byte = -1; c.out_count = 0;       // ff_init_range_encoder
-    c.buf = B.scratch + (size_t)f * L.scratch_per_frame + g.scratch_off;
-    c.pos = 0; c.cap = g.scratch_cap;
+    c.buf = reinterpret_cast<uint32_t *>(B.scratch + (size_t)f * L.scratch_per_frame + g.scratch_off);
+    c.pos = 0; c.cap = g.scratch_cap; c.acc = 0;
 
-    const uint16_t *pre = T.prefix + (size_t)(s * 2 + key) * kMaxPrefix;
-    const int npre = T.prefix_len[s * 2 + key];
-    for (int i = 0; i < npre; i++) rac_code(c, pre[i]);
-
-    const uint32_t n = B.slice_ndec[idx];
-    const uint4 *src = reinterpret_cast<const uint4 *>(B.dec + B.slice_base[idx]);
-    const uint32_t nvec = n >> 3;
-    uint4 v = nvec ? src[0] : make_uint4(0, 0, 0, 0);
-    for (uint32_t i = 0; i < nvec; i++) {
-        const uint4 nx = (i + 1 < nvec || (n & 7u)) ? src[i + 1] : make_uint4(0, 0, 0, 0);
-        rac_code(c, v.x & 0xFFFFu); rac_code(c, v.x >> 16);
-        rac_code(c, v.y & 0xFFFFu); rac_code(c, v.y >> 16);
-        rac_code(c, v.z & 0xFFFFu); rac_code(c, v.z >> 16);
-        rac_code(c, v.w & 0xFFFFu); rac_code(c, v.w >> 16);
-        v = nx;
+    const uint16_t *dec_frame = B.dec + (size_t)f * L.dec_per_frame;
+    const uint32_t *run_cnt = B.run_cnt + (size_t)f * L.runs_per_frame + g.run_first;
+    const uint8_t *run_pc = T.run_pc + g.run_first;
+    uint32_t cur0 = 0u, cur1 = 0u, cur2 = 0u;
+    // source -1: the slice's prefix (keyframe bit, slice header); 0..nruns-1: sample runs; nruns: the closing
+    // put_rac(state 129, 0) of ffv1enc.c:1331-1333.  One loop so that the coder body exists once in the binary.
+#pragma unroll 1
+    for (int r = -1; r <= g.nruns; r++) {
+        const uint16_t *src;
+        uint32_t n;
+        if (r < 0) {
+            src = T.prefix + (size_t)(s * 2 + key) * kMaxPrefix;
+            n = (uint32_t)T.prefix_len[s * 2 + key];
+        } else if (r == g.nruns) {
+            src = T.prefix + (size_t)L.nslices * 2 * kMaxPrefix;          // one extra row holding the entry "129"
+            n = 1u;
+        } else {
+            const int pc = run_pc[r];
+            n = run_cnt[r];
+            const uint32_t at = pc == 0 ? cur0 : (pc == 1 ? cur1 : cur2);
+            src = dec_frame + g.dec_off[pc] + at;
+            const uint32_t nx = (at + n + 7u) & ~7u;
+            if (pc == 0) cur0 = nx; else if (pc == 1) cur1 = nx; else cur2 = nx;
+        }
+        rac_code_run(c, reinterpret_cast<const uint4 *>(src), n);
     }
-    if (n & 7u) {
-        if (!nvec) v = src[0];
-        const uint32_t wds[4] = {v.x, v.y, v.z, v.w};
-        for (uint32_t k = 0; k < (n & 7u); k++) rac_code(c, (wds[k >> 1] >> ((k & 1u) * 16)) & 0xFFFFu);
+    // ff_rac_terminate (rangecoder.c:104-116): two forced renormalisations
+#pragma unroll 1
+    for (int t = 0; t < 2; t++) {
+        c.range = 0xFFu;
+        if (t == 0) c.low += 0xFFu;
+        while (c.range < 0x100u) rac_shift(c);
     }
-    rac_code(c, 129u);                                        // put_rac(state 129, 0): ffv1enc.c:1331-1333
-    // ff_rac_terminate (rangecoder.c:104-116)
-    c.range = 0xFFu; c.low += 0xFFu;
-    while (c.range < 0x100u) rac_shift(c);
-    c.range = 0xFFu;
-    while (c.range < 0x100u) rac_shift(c);
+    if ((c.pos & 3u) && c.pos <= c.cap) c.buf[c.pos >> 2] = c.acc;
 
     B.slice_bytes[idx] = c.pos;
     if (c.pos > c.cap) atomicMax(&B.status[1], (unsigned long long)c.pos);
@@ -566,7 +630,7 @@ __global__ void __launch_bounds__(128) k_rangecode(const EncDeviceTables T, cons
 void launch_rangecode(const EncDeviceTables &t, const EncBatch &b, cudaStream_t s)
 {
     const int n = b.nframes * t.layout.nslices;
-    k_rangecode<<<(n + 127) / 128, 128, 0, s>>>(t, b);
+    k_rangecode<<<(n + kRangeThreads - 1) / kRangeThreads, kRangeThreads, 0, s>>>(t, b);
 }
 
 // =================================================================================================
@@ -697,8 +761,9 @@ cudaError_t configure_kernels(const Layout &L)
 #undef SET_PIXEL
     const int rsm = replay_smem_bytes(L);
     if (rsm <= 227 * 1024) {
-        e = cudaFuncSetAttribute(k_replay<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, rsm); if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(k_replay<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, rsm); if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(k_replay<true, 7, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, rsm); if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(k_replay<true, 9, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, rsm); if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(k_replay<true, 9, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, rsm); if (e != cudaSuccess) return e;
     }
     return cudaSuccess;
 }

@@ -20,12 +20,9 @@ struct EncBatch {
     const uint8_t *const *planes;       // [nframes*4] device pointers
     int32_t linesize[4];
     uint32_t *rec;                      // [nframes][rec_per_frame]
-    uint32_t *line_cnt;                 // [nframes][lines_per_frame]  decisions per line
-    uint32_t *line_off;                 // [nframes][lines_per_frame]  exclusive scan inside (frame, slice)
-    uint32_t *slice_ndec;               // [nframes][nslices]          decisions of the slice's samples
-    uint64_t *slice_base;               // [nframes][nslices]          first entry in dec[]
-    uint16_t *dec;                      // decision stream: p | bit<<8
-    uint64_t dec_capacity;              // entries
+    uint32_t *run_cnt;                  // [nframes][runs_per_frame]   decisions of every run (written by k_replay)
+    uint16_t *dec;                      // [nframes][dec_per_frame]    decision entries p | bit<<8, one region per
+                                        //                             (slice, plane context), runs 8-entry aligned
     const int32_t *seg_first;           // [nseg+1] first frame of each segment
     const uint8_t *frame_key;           // [nframes]
     uint8_t *scratch;                   // [nframes][scratch_per_frame]
@@ -38,7 +35,8 @@ struct EncBatch {
     uint8_t *state_seg;                 // global-state mode: [nseg][nslices][npc][ctx_count*32]
     const uint8_t *carry_in;            // [nslices][npc][ctx_count*32]
     uint8_t *carry_out;
-    // error reporting: [0] dec overflow (needed entries), [1] scratch overflow flag, [2] out overflow
+    // [0] decision-region overflow: needed entries per sample * 256, [1] scratch overflow (bytes needed),
+    // [2] out overflow (bytes needed), [3] total binary decisions of the batch
     unsigned long long *status;
 };
 
@@ -50,6 +48,8 @@ struct EncDeviceTables {
     const TileDesc *tiles;
     const int16_t *quant;               // [5][256]
     const uint8_t *trans_lut;           // [512]: zero_state, one_state of the slice coders
+    const uint8_t *one_pow;             // [33][256]: one_state applied k times (runs of zero residuals in one context)
+    const uint8_t *run_pc;              // [runs_per_frame] plane context of every run
     const uint16_t *prefix;             // [nslices][2][kMaxPrefix]
     const int32_t *prefix_len;          // [nslices][2]
     int32_t ec;
@@ -59,11 +59,14 @@ struct EncDeviceTables {
 
 int  pixel_smem_bytes(const Layout &L);
 void launch_pixel(const EncDeviceTables &t, const EncBatch &b, cudaStream_t s);
-void launch_scan(const EncDeviceTables &t, const EncBatch &b, cudaStream_t s);
 int  replay_smem_bytes(const Layout &L);
 void launch_replay(const EncDeviceTables &t, const EncBatch &b, cudaStream_t s);
 void launch_rangecode(const EncDeviceTables &t, const EncBatch &b, cudaStream_t s);
 void launch_pack(const EncDeviceTables &t, const EncBatch &b, cudaStream_t s);
 cudaError_t configure_kernels(const Layout &L);
+// tuned per-pixel pass for planar sources (ffv1_pixel_fast.cu)
+bool pixel_fast_geometry_ok(const Layout &L, const SliceGeom *slices, int nslices);
+cudaError_t configure_pixel_fast(const Layout &L);
+void launch_pixel_fast(const EncDeviceTables &t, const EncBatch &b, int max_plane_width, int num_sms, cudaStream_t s);
 
 } // namespace ffv1

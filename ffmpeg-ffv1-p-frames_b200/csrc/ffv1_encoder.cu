@@ -6,6 +6,7 @@
 #include "ffv1_internal.h"
 #include <cuda_runtime.h>
 #include <cstring>
+#include <cstdlib>
 #include <cstdio>
 #include <string>
 #include <vector>
@@ -30,8 +31,9 @@ struct FFV1B200Encoder {
     // batch buffers
     DevBuf<uint8_t> d_in; size_t in_plane_off[4] = {0,0,0,0}; int in_pitch[4] = {0,0,0,0}; size_t in_frame_stride = 0;
     DevBuf<const uint8_t *> d_planes; PinnedBuf<const uint8_t *> h_planes;
-    DevBuf<uint32_t> d_rec, d_line_cnt, d_line_off, d_slice_ndec, d_slice_bytes, d_pkt_size;
-    DevBuf<uint64_t> d_slice_base, d_pkt_off;
+    DevBuf<uint32_t> d_rec, d_run_cnt, d_slice_bytes, d_pkt_size;
+    DevBuf<uint64_t> d_pkt_off;
+    DevBuf<uint8_t> d_one_pow, d_run_pc;
     DevBuf<uint16_t> d_dec;
     DevBuf<int32_t> d_seg_first; DevBuf<uint8_t> d_frame_key;
     PinnedBuf<int32_t> h_seg_first; PinnedBuf<uint8_t> h_frame_key;
@@ -42,6 +44,8 @@ struct FFV1B200Encoder {
     double dec_per_sample = 5.0;      // sizing of the decision stream (entries per sample), grows on demand
     double scratch_scale = 1.0;
     bool state_in_smem = true;
+    bool fast_pixel = false;          // geometry allows the TMA-staged per-pixel kernel (pointer alignment is checked per call)
+    int max_plane_width = 0, num_sms = 148;
     FFV1B200EncStats stats{};
     int last_nframes = 0;
 };
@@ -55,7 +59,8 @@ int fail(int code, const std::string &msg) { set_last_error(msg); return code; }
 int upload_prefixes(FFV1B200Encoder *e)
 {
     const int ns = e->cfg.slice_count();
-    std::vector<uint16_t> pre((size_t)ns * 2 * kMaxPrefix, 0);
+    std::vector<uint16_t> pre((size_t)(ns * 2 + 1) * kMaxPrefix, 0);
+    pre[(size_t)ns * 2 * kMaxPrefix] = 129;                              // the decision that closes every slice (state 129, bit 0)
     std::vector<int32_t> len((size_t)ns * 2, 0);
     for (int s = 0; s < ns; s++)
         for (int key = 0; key < 2; key++) {
@@ -87,26 +92,24 @@ int alloc_batch_buffers(FFV1B200Encoder *e)
     CU_TRY(e->d_in.alloc(e->in_frame_stride * F));
     CU_TRY(e->d_planes.alloc(F * 4)); CU_TRY(e->h_planes.alloc(F * 4));
     CU_TRY(e->d_rec.alloc((size_t)L.rec_per_frame * F));
-    CU_TRY(e->d_line_cnt.alloc((size_t)L.lines_per_frame * F));
-    CU_TRY(e->d_line_off.alloc((size_t)L.lines_per_frame * F));
-    CU_TRY(e->d_slice_ndec.alloc((size_t)L.nslices * F));
+    CU_TRY(e->d_run_cnt.alloc((size_t)L.runs_per_frame * F));
     CU_TRY(e->d_slice_bytes.alloc((size_t)L.nslices * F));
-    CU_TRY(e->d_slice_base.alloc((size_t)L.nslices * F));
     CU_TRY(e->d_pkt_size.alloc(F)); CU_TRY(e->d_pkt_off.alloc(F + 1));
     CU_TRY(e->h_pkt_size.alloc(F)); CU_TRY(e->h_pkt_off.alloc(F + 1));
     CU_TRY(e->d_seg_first.alloc(F + 1)); CU_TRY(e->h_seg_first.alloc(F + 1));
     CU_TRY(e->d_frame_key.alloc(F)); CU_TRY(e->h_frame_key.alloc(F));
     CU_TRY(e->d_status.alloc(8)); CU_TRY(e->h_status.alloc(8));
     CU_TRY(e->d_scratch.alloc((size_t)L.scratch_per_frame * F));
-    size_t samples = 0;
-    for (auto &g : e->tab.slices) samples += g.nsamples;
-    if (!L.golomb) CU_TRY(e->d_dec.alloc((size_t)((double)samples * F * e->dec_per_sample) + 4096));
+    if (!L.golomb) CU_TRY(e->d_dec.alloc((size_t)L.dec_per_frame * F + 64));
     const size_t state_bytes = (size_t)L.nslices * L.npc * L.ctx_count * 32;
     for (int k = 0; k < 2; k++) {
         CU_TRY(e->d_carry[k].alloc(state_bytes));
         CU_TRY(cudaMemsetAsync(e->d_carry[k].p, 128, state_bytes, e->stream));
     }
-    if (!e->state_in_smem && !L.golomb) CU_TRY(e->d_state_seg.alloc(state_bytes * F));   // worst case: every frame a keyframe
+    if (!e->state_in_smem && !L.golomb) {
+        const int g = e->cfg.gop_size > 0 ? e->cfg.gop_size : 1;
+        CU_TRY(e->d_state_seg.alloc(state_bytes * ((F + g - 1) / g + 1)));               // one state set per GOP segment of a batch
+    }
     return 0;
 }
 
@@ -115,7 +118,7 @@ EncDeviceTables device_tables(FFV1B200Encoder *e)
     EncDeviceTables t;
     t.layout = e->tab.layout;
     t.slices = e->d_slices.p; t.lines = e->d_lines.p; t.pc_lines = e->d_pc_lines.p; t.tiles = e->d_tiles.p;
-    t.quant = e->d_quant.p; t.trans_lut = e->d_lut.p; t.prefix = e->d_prefix.p; t.prefix_len = e->d_prefix_len.p;
+    t.quant = e->d_quant.p; t.trans_lut = e->d_lut.p; t.one_pow = e->d_one_pow.p; t.run_pc = e->d_run_pc.p; t.prefix = e->d_prefix.p; t.prefix_len = e->d_prefix_len.p;
     t.ec = e->cfg.ec; t.version = e->cfg.version; t.state_in_smem = e->state_in_smem ? 1 : 0;
     return t;
 }
@@ -147,9 +150,7 @@ int run_pipeline(FFV1B200Encoder *e, int nframes, const int linesizes[4], uint8_
         b.nframes = nframes; b.nseg = nseg;
         b.planes = e->d_planes.p;
         for (int i = 0; i < 4; i++) b.linesize[i] = linesizes[i];
-        b.rec = e->d_rec.p; b.line_cnt = e->d_line_cnt.p; b.line_off = e->d_line_off.p;
-        b.slice_ndec = e->d_slice_ndec.p; b.slice_base = e->d_slice_base.p;
-        b.dec = e->d_dec.p; b.dec_capacity = e->d_dec.n;
+        b.rec = e->d_rec.p; b.run_cnt = e->d_run_cnt.p; b.dec = e->d_dec.p;
         b.seg_first = e->d_seg_first.p; b.frame_key = e->d_frame_key.p;
         b.scratch = e->d_scratch.p; b.slice_bytes = e->d_slice_bytes.p;
         b.pkt_size = e->d_pkt_size.p; b.pkt_off = e->d_pkt_off.p;
@@ -158,17 +159,20 @@ int run_pipeline(FFV1B200Encoder *e, int nframes, const int linesizes[4], uint8_
         b.carry_in = e->d_carry[e->carry_idx].p; b.carry_out = e->d_carry[e->carry_idx ^ 1].p;
         b.status = e->d_status.p;
 
+        bool fast = e->fast_pixel;
+        for (int i = 0; i < 4 && fast; i++) fast = (linesizes[i] & 15) == 0;
+        for (int i = 0; i < nframes * 4 && fast; i++) fast = (reinterpret_cast<uintptr_t>(e->h_planes.p[i]) & 15) == 0;
         cudaEventRecord(e->ev[0], s);
-        launch_pixel(t, b, s);
+        if (fast) launch_pixel_fast(t, b, e->max_plane_width, e->num_sms, s);
+        else      launch_pixel(t, b, s);
         cudaEventRecord(e->ev[1], s);
-        launch_scan(t, b, s);
         launch_replay(t, b, s);
         cudaEventRecord(e->ev[2], s);
         launch_rangecode(t, b, s);
         cudaEventRecord(e->ev[3], s);
         launch_pack(t, b, s);
         cudaEventRecord(e->ev[4], s);
-        e->stats.kernel_launches += 7;
+        e->stats.kernel_launches += 5;
         CU_TRY(cudaGetLastError());
         CU_TRY(cudaMemcpyAsync(e->h_status.p, e->d_status.p, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost, s));
         CU_TRY(cudaMemcpyAsync(e->h_pkt_size.p, e->d_pkt_size.p, sizeof(uint32_t) * nframes, cudaMemcpyDeviceToHost, s));
@@ -177,9 +181,12 @@ int run_pipeline(FFV1B200Encoder *e, int nframes, const int linesizes[4], uint8_
         e->stats.d2h_bytes += 64 + 12 * (int64_t)nframes + 8;
 
         const unsigned long long *st = e->h_status.p;
-        if (st[0]) {            // decision stream too small: grow and re-run
+        if (st[0]) {            // a decision region overflowed: st[0] = needed entries per sample * 256; grow and re-run
+            e->dec_per_sample = std::max(e->dec_per_sample * 1.25, (double)st[0] / 256.0 * 1.1);
+            layout_decisions(e->tab, e->dec_per_sample);
             e->d_dec.release();
-            CU_TRY(e->d_dec.alloc((size_t)(st[0] + st[0] / 8 + 4096)));
+            CU_TRY(e->d_dec.alloc((size_t)e->tab.layout.dec_per_frame * e->max_batch + 64));
+            CU_TRY(e->d_slices.upload(e->tab.slices.data(), e->tab.slices.size(), s));
             e->stats.retries++;
             continue;
         }
@@ -259,7 +266,13 @@ int ffv1b200_enc_open(FFV1B200Encoder **out, const FFV1B200EncParams *p)
     build_tables(e->cfg, e->tab);
     const Layout &L = e->tab.layout;
     e->state_in_smem = replay_smem_bytes(L) <= 227 * 1024;
+    if (const char *v = getenv("FFV1B200_REPLAY_STATE")) { if (!strcmp(v, "global")) e->state_in_smem = false; }
     CU_TRY(configure_kernels(L));
+    e->fast_pixel = pixel_fast_geometry_ok(L, e->tab.slices.data(), (int)e->tab.slices.size());
+    if (const char *v = getenv("FFV1B200_PIXEL")) { if (!strcmp(v, "generic")) e->fast_pixel = false; }
+    if (e->fast_pixel) CU_TRY(configure_pixel_fast(L));
+    for (auto &g : e->tab.slices) for (int p = 0; p < L.nplanes; p++) e->max_plane_width = std::max(e->max_plane_width, g.pw[p]);
+    CU_TRY(cudaDeviceGetAttribute(&e->num_sms, cudaDevAttrMultiProcessorCount, e->device));
 
     CU_TRY(e->d_slices.upload(e->tab.slices.data(), e->tab.slices.size(), e->stream));
     CU_TRY(e->d_lines.upload(e->tab.lines.data(), e->tab.lines.size(), e->stream));
@@ -269,7 +282,13 @@ int ffv1b200_enc_open(FFV1B200Encoder **out, const FFV1B200EncParams *p)
     uint8_t lut[512];
     coder_state_tables(e->cfg, lut, lut + 256);
     CU_TRY(e->d_lut.upload(lut, 512, e->stream));
-    CU_TRY(e->d_prefix.alloc((size_t)L.nslices * 2 * kMaxPrefix));
+    std::vector<uint8_t> one_pow(33 * 256);                      // one_state applied k times (k_replay's zero-run shortcut)
+    for (int p = 0; p < 256; p++) one_pow[p] = (uint8_t)p;
+    for (int k = 1; k <= 32; k++)
+        for (int p = 0; p < 256; p++) one_pow[k * 256 + p] = lut[256 + one_pow[(k - 1) * 256 + p]];
+    CU_TRY(e->d_one_pow.upload(one_pow.data(), one_pow.size(), e->stream));
+    CU_TRY(e->d_run_pc.upload(e->tab.run_pc.data(), e->tab.run_pc.size(), e->stream));
+    CU_TRY(e->d_prefix.alloc((size_t)(L.nslices * 2 + 1) * kMaxPrefix));
     CU_TRY(e->d_prefix_len.alloc((size_t)L.nslices * 2));
     r = alloc_batch_buffers(e.get());
     if (r < 0) return r;

@@ -603,7 +603,7 @@ void build_tables(const Config &c, Tables &t)
     L.nslices = c.slice_count();
 
     t.slices.assign(L.nslices, SliceGeom());
-    t.lines.clear(); t.pc_lines.clear(); t.tiles.clear();
+    t.lines.clear(); t.pc_lines.clear(); t.tiles.clear(); t.run_pc.clear();
     uint32_t rec_cursor = 0, scratch_cursor = 0;
     for (int si = 0; si < L.nslices; si++) {
         SliceGeom &g = t.slices[si];
@@ -617,11 +617,15 @@ void build_tables(const Config &c, Tables &t)
             g.py0[p] = g.y0 >> pi.vshift;
         }
         g.line_first = (int32_t)t.lines.size();
+        g.run_first = (int32_t)t.run_pc.size();
+        g.nruns = 0;
         g.rec_first = rec_cursor;
         uint32_t off = 0, nsamp = 0;
         auto add_line = [&](int p, int y) {
             LineDesc ld;
             ld.rec_off = off; ld.w = (uint16_t)g.pw[p]; ld.pc = (uint8_t)L.plane[p].pc; ld.plane = (uint8_t)p; ld.y = (uint32_t)y;
+            if (g.nruns == 0 || t.run_pc.back() != ld.pc) { t.run_pc.push_back(ld.pc); g.nruns++; }
+            ld.run = (uint32_t)(g.nruns - 1);
             t.lines.push_back(ld);
             off += (uint32_t)((g.pw[p] + 31) & ~31);
             nsamp += (uint32_t)g.pw[p];
@@ -674,6 +678,26 @@ void build_tables(const Config &c, Tables &t)
     L.tiles_per_frame = (int32_t)t.tiles.size();
     L.rec_per_frame = rec_cursor;
     L.scratch_per_frame = scratch_cursor;
+    L.runs_per_frame = (int32_t)t.run_pc.size();
+    layout_decisions(t, 5.0);
+}
+
+void layout_decisions(Tables &t, double entries_per_sample)
+{
+    // one region per (slice, plane context); every run starts on an 8-entry (16 byte) boundary inside its region
+    uint64_t cur = 0;
+    for (auto &g : t.slices) {
+        int runs_of_pc[3] = {0, 0, 0};
+        for (int r = 0; r < g.nruns; r++) runs_of_pc[t.run_pc[g.run_first + r]]++;
+        for (int pc = 0; pc < 3; pc++) {
+            uint64_t cap = g.pc_samples[pc] ? (uint64_t)((double)g.pc_samples[pc] * entries_per_sample) + 8ull * runs_of_pc[pc] + 64 : 0;
+            cap = (cap + 7) & ~7ull;
+            g.dec_off[pc] = (uint32_t)cur;
+            g.dec_cap[pc] = (uint32_t)cap;
+            cur += cap;
+        }
+    }
+    t.layout.dec_per_frame = (uint32_t)cur;
 }
 
 } // namespace ffv1

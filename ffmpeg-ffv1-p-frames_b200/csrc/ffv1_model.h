@@ -43,6 +43,10 @@ struct SliceGeom {
     int32_t pc_line_first[3];        // per plane-context: start in pc_lines[] (indices into the line table)
     int32_t pc_nlines[3];
     uint32_t pc_samples[3];
+    int32_t run_first;               // first entry of this slice in the per-frame run table
+    int32_t nruns;                   // runs = maximal groups of consecutive lines (coding order) of one plane context
+    uint32_t dec_off[3];             // per plane-context: first entry of its decision region inside a frame's dec area
+    uint32_t dec_cap[3];             // capacity of that region in entries (multiple of 8)
 };
 
 // one line of samples in coding order
@@ -52,6 +56,7 @@ struct LineDesc {
     uint8_t  pc;
     uint8_t  plane;
     uint32_t y;
+    uint32_t run;        // slice-relative index of the run this line belongs to
 };
 
 // unit of work of the per-pixel kernel: up to kTileRows rows of one plane (all planes for RGB) of one slice
@@ -82,6 +87,8 @@ struct Layout {
     int32_t golomb;
     uint32_t rec_per_frame;  // records per frame incl. padding
     uint32_t scratch_per_frame;
+    int32_t runs_per_frame;
+    uint32_t dec_per_frame;  // decision entries per frame (all regions; set by layout_decisions)
     int32_t rct_offset;      // 1 << bits for RGB
     PlaneInfo plane[4];
 };
@@ -142,9 +149,12 @@ struct Tables {
     std::vector<LineDesc>  lines;       // all slices, coding order inside a slice
     std::vector<int32_t>   pc_lines;    // per slice, per plane context: slice-relative line indices
     std::vector<TileDesc>  tiles;
+    std::vector<uint8_t>   run_pc;      // per frame: plane context of every run, slices back to back
 };
 constexpr int kTileRows = 16;
 void build_tables(const Config &c, Tables &t);
+// Sizes the per-(slice, plane context) decision regions for `entries_per_sample` binary decisions per coded sample.
+void layout_decisions(Tables &t, double entries_per_sample);
 
 uint32_t crc32_ieee(uint32_t crc, const uint8_t *buf, size_t len);
 
