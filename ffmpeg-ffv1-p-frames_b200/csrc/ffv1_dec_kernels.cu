@@ -1,0 +1,496 @@
+// ffv1_dec_kernels.cu -- hand-written sm_100a kernels of the FFV1 decode path.
+//
+//   k_dec_crc   per-slice CRC-32 check (ffv1dec.c:963-976): chunk CRCs in parallel, combined in GF(2).
+//   k_decode    decode_slice / decode_slice_header / decode_plane / decode_rgb_frame / decode_line
+//               (ffv1dec.c:361-474, 282-359, 183-280, 100-181) with get_symbol_inline / get_rac (ffv1dec.c:42-63,
+//               rangecoder.h:104-145) or the Golomb-Rice reader (ffv1dec.c:70-98, golomb.h:270-300, 367-372).
+//               Decoding is strictly serial inside a slice (every context needs the reconstructed left neighbour), and
+//               a non-keyframe needs the model state the previous frame left behind, so the unit of parallelism is the
+//               chain (GOP segment, slice): one warp per chain.  Lane 0 runs the entropy decoder and reconstruction
+//               into an int16 line ring (the reference's sample_buffer); after every line the whole warp converts
+//               the line (inverse RCT for RGB) and writes it to the output frame with coalesced stores.
+//   k_conceal   damaged slices are replaced by the co-located pixels of the previous frame (ffv1dec.c:998-1021).
+#include "ffv1_dec_kernels.cuh"
+
+namespace ffv1 {
+
+__constant__ uint8_t c_log2_run[41] = {
+    0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7,
+    8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24,
+};
+
+// ------------------------------------------------------------------------------------------------ CRC
+__device__ __forceinline__ uint32_t gf_mulmod32(uint32_t a, uint32_t b)
+{
+    // a(x)*b(x) mod P(x) over GF(2), P = x^32 + 0x04C11DB7, bit k = coefficient of x^k
+    uint32_t r = 0;
+#pragma unroll 8
+    for (int i = 31; i >= 0; i--) {
+        r = (r << 1) ^ ((r & 0x80000000u) ? 0x04C11DB7u : 0u);
+        if ((b >> i) & 1u) r ^= a;
+    }
+    return r;
+}
+
+constexpr int kCrcThreads = 128;
+
+__global__ void __launch_bounds__(kCrcThreads) k_dec_crc(const DecDeviceTables T, const DecBatch B)
+{
+    __shared__ uint32_t s_tab[256];
+    __shared__ uint32_t s_part[kCrcThreads];
+    const int f = blockIdx.x / T.max_slices, s = blockIdx.x - f * T.max_slices;
+    const int tid = threadIdx.x;
+    if (s >= B.slice_count[f]) return;
+    for (int n = tid; n < 256; n += kCrcThreads) {
+        uint32_t c = (uint32_t)n << 24;
+#pragma unroll
+        for (int k = 0; k < 8; k++) c = (c & 0x80000000u) ? (c << 1) ^ 0x04C11DB7u : (c << 1);
+        s_tab[n] = c;
+    }
+    __syncthreads();
+    const uint8_t *src = B.pkt + B.pkt_off[f] + B.slice_start[f * T.max_slices + s];
+    const uint32_t len = B.slice_size[f * T.max_slices + s];
+    const uint32_t chunk = (len + kCrcThreads - 1) / kCrcThreads;
+    // chunks are aligned to the END of the slice: leading zero bytes do not change a CRC whose initial value is 0
+    const long long beg = (long long)len - (long long)(kCrcThreads - tid) * chunk;
+    uint32_t crc = 0;
+    for (long long i = beg < 0 ? 0 : beg; i < beg + (long long)chunk; i++) crc = (crc << 8) ^ s_tab[(crc >> 24) ^ src[i]];
+    uint32_t mult = 1u, base = 0x100u;                        // x^(8*chunk) mod P
+    for (uint32_t e = chunk; e; e >>= 1) {
+        if (e & 1u) mult = gf_mulmod32(mult, base);
+        base = gf_mulmod32(base, base);
+    }
+    s_part[tid] = crc;
+    __syncthreads();
+    for (int stride = 1; stride < kCrcThreads; stride <<= 1) {
+        uint32_t v = 0;
+        const bool active = (tid % (2 * stride)) == 0;
+        if (active) v = gf_mulmod32(s_part[tid], mult) ^ s_part[tid + stride];
+        __syncthreads();
+        if (active) s_part[tid] = v;
+        mult = gf_mulmod32(mult, mult);
+        __syncthreads();
+    }
+    if (tid == 0 && s_part[0] != 0) B.damaged[f * T.max_slices + s] |= 1u;
+}
+
+void launch_dec_crc(const DecDeviceTables &t, const DecBatch &b, cudaStream_t s)
+{
+    if (!t.ec) return;
+    k_dec_crc<<<b.nframes * t.max_slices, kCrcThreads, 0, s>>>(t, b);
+}
+
+// ------------------------------------------------------------------------------------------------ entropy readers
+struct RDec {                // rangecoder.h:35-45, decoder side
+    uint32_t low, range;
+    const uint8_t *ptr, *end, *start;
+};
+
+__device__ __forceinline__ void rd_init(RDec &c, const uint8_t *buf, uint32_t size)
+{
+    // ff_init_range_decoder (rangecoder.c:53-61)
+    c.start = buf; c.end = buf + size;
+    c.range = 0xFF00u;
+    c.low = size >= 2 ? ((uint32_t)buf[0] << 8 | buf[1]) : (size == 1 ? (uint32_t)buf[0] << 8 : 0u);
+    c.ptr = buf + 2;
+}
+
+__device__ __forceinline__ int rd_get(RDec &c, uint8_t *state, const uint8_t *lut)
+{
+    // get_rac + refill (rangecoder.h:104-145)
+    const uint32_t s = *state;
+    const uint32_t range1 = (c.range * s) >> 8;
+    int bit;
+    c.range -= range1;
+    if (c.low < c.range) {
+        *state = lut[s];
+        bit = 0;
+    } else {
+        c.low -= c.range;
+        *state = lut[256 + s];
+        c.range = range1;
+        bit = 1;
+    }
+    if (c.range < 0x100u) {
+        c.range <<= 8;
+        c.low <<= 8;
+        if (c.ptr < c.end) c.low += *c.ptr;
+        c.ptr++;
+    }
+    return bit;
+}
+
+__device__ int rd_symbol(RDec &c, uint8_t *state, const uint8_t *lut, bool is_signed, int &err)
+{
+    // get_symbol_inline (ffv1dec.c:42-63)
+    if (rd_get(c, state, lut)) return 0;
+    int e = 0;
+    while (rd_get(c, state + 1 + min(e, 9), lut)) {
+        if (++e > 31) { err = 1; return 0; }
+    }
+    int a = 1;
+    for (int i = e - 1; i >= 0; i--) a += a + rd_get(c, state + 22 + min(i, 9), lut);
+    if (is_signed && rd_get(c, state + 11 + min(e, 10), lut)) return -a;
+    return a;
+}
+
+struct BitR {                // MSB-first reader (get_bits.h), zero bits past the end
+    const uint8_t *buf;
+    uint32_t nbytes;
+    uint32_t pos;            // bit position
+    uint32_t wbyte;          // first byte held in `win`
+    unsigned long long win;  // bytes wbyte .. wbyte+7, big endian
+};
+
+__device__ __forceinline__ void br_load(BitR &r, uint32_t byte)
+{
+    unsigned long long w = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        w <<= 8;
+        if (byte + i < r.nbytes) w |= r.buf[byte + i];
+    }
+    r.win = w; r.wbyte = byte;
+}
+
+__device__ __forceinline__ uint32_t br_peek32(BitR &r)
+{
+    const uint32_t byte = r.pos >> 3;
+    if (byte - r.wbyte > 3u) br_load(r, byte);           // also true when byte < wbyte (never happens: pos only grows)
+    const uint32_t sh = r.pos - r.wbyte * 8u;            // 0..31
+    return (uint32_t)((r.win << sh) >> 32);
+}
+
+__device__ __forceinline__ uint32_t br_get(BitR &r, int n)
+{
+    if (!n) return 0u;
+    const uint32_t v = br_peek32(r) >> (32 - n);
+    r.pos += n;
+    return v;
+}
+
+struct __align__(8) VlcDev { int16_t drift; uint16_t error_sum; int8_t bias; uint8_t count; uint16_t pad; };
+
+__device__ __forceinline__ int fold_bits(int d, int bits) { return (d << (32 - bits)) >> (32 - bits); }
+
+__device__ int br_vlc(BitR &r, VlcDev *sp, int bits)
+{
+    // get_vlc_symbol (ffv1dec.c:70-98) + get_sr_golomb (golomb.h:270-300, 367-372) + update_vlc_state (ffv1.h:192-224)
+    VlcDev s = *sp;
+    int k = 0;
+    for (int i = s.count; i < s.error_sum; i += i) k++;
+    const uint32_t buf = br_peek32(r);
+    const int lz = buf ? __clz(buf) : 32;
+    uint32_t u;
+    if (lz < 12) {
+        r.pos += lz + 1;
+        u = ((uint32_t)lz << k) + br_get(r, k);
+    } else {
+        r.pos += 12;
+        u = br_get(r, bits) + 11u;
+    }
+    int v = (int)(u >> 1) ^ -(int)(u & 1u);
+    v ^= (2 * s.drift + s.count) >> 31;
+    const int ret = fold_bits(v + s.bias, bits);
+    // update
+    int drift = s.drift, count = s.count, esum = s.error_sum, bias = s.bias;
+    esum += abs(v);
+    drift += v;
+    if (count == 128) { count >>= 1; drift >>= 1; esum >>= 1; }
+    count++;
+    if (drift <= -count) {
+        if (bias > -128) bias--;
+        drift += count;
+        if (drift <= -count) drift = -count + 1;
+    } else if (drift > 0) {
+        if (bias < 127) bias++;
+        drift -= count;
+        if (drift > 0) drift = 0;
+    }
+    s.drift = (int16_t)drift; s.count = (uint8_t)count; s.error_sum = (uint16_t)esum; s.bias = (int8_t)bias;
+    *sp = s;
+    return ret;
+}
+
+__device__ __forceinline__ int median3(int a, int b, int c) { return max(min(a, b), min(max(a, b), c)); }
+
+struct SliceRd {
+    RDec rc;
+    BitR br;
+    int golomb;
+    int run_index;
+    int err;
+};
+
+// one line of one plane into the ring (ffv1dec.c:100-181).  cur/top/top2 point at x = 0 of the ring rows.
+__device__ void dec_line(SliceRd &sr, uint8_t *model, const int16_t *q, const uint8_t *lut, int16_t *cur, const int16_t *top,
+                         const int16_t *top2, int w, int bits)
+{
+    const bool five = q[3 * 256 + 127] != 0;
+    const int mask = (1 << bits) - 1;
+    int run_count = 0, run_mode = 0;
+    int L = cur[-1], LL = cur[-2], LT = top[-1], Tp = top[0];
+    for (int x = 0; x < w; x++) {
+        const int RT = top[x + 1];
+        int ctx = q[(L - LT) & 0xFF] + q[256 + ((LT - Tp) & 0xFF)] + q[512 + ((Tp - RT) & 0xFF)];
+        if (five) ctx += q[768 + ((LL - L) & 0xFF)] + q[1024 + ((top2[x] - Tp) & 0xFF)];
+        bool sign = false;
+        if (ctx < 0) { ctx = -ctx; sign = true; }
+        int diff;
+        if (!sr.golomb) {
+            diff = rd_symbol(sr.rc, model + (size_t)ctx * 32, lut, true, sr.err);
+        } else {
+            VlcDev *vs = reinterpret_cast<VlcDev *>(model) + ctx;
+            if (ctx == 0 && run_mode == 0) run_mode = 1;
+            if (run_mode) {
+                if (run_count == 0 && run_mode == 1) {
+                    if (br_get(sr.br, 1)) {
+                        run_count = 1 << c_log2_run[sr.run_index];
+                        if (x + run_count <= w) sr.run_index++;
+                    } else {
+                        const int lr = c_log2_run[sr.run_index];
+                        run_count = lr ? (int)br_get(sr.br, lr) : 0;
+                        if (sr.run_index) sr.run_index--;
+                        run_mode = 2;
+                    }
+                }
+                run_count--;
+                if (run_count < 0) {
+                    run_mode = 0; run_count = 0;
+                    diff = br_vlc(sr.br, vs, bits);
+                    if (diff >= 0) diff++;
+                } else
+                    diff = 0;
+            } else
+                diff = br_vlc(sr.br, vs, bits);
+        }
+        if (sign) diff = -diff;
+        const int v = (int)(int16_t)((median3(L, Tp, L + Tp - LT) + diff) & mask);      // ffv1dec.c:178, int16 line buffer
+        cur[x] = (int16_t)v;
+        LL = L; L = v; LT = Tp; Tp = RT;
+    }
+}
+
+constexpr int kDecSmemQuant = 2 * 5 * 256;
+
+__global__ void __launch_bounds__(32) k_decode(const DecDeviceTables T, const DecBatch B)
+{
+    __shared__ int16_t s_quant[kDecSmemQuant];
+    __shared__ uint8_t s_lut[512];
+    const int lane = threadIdx.x;
+    for (int i = lane; i < kDecSmemQuant; i += 32) s_quant[i] = T.quant[i];
+    for (int i = lane; i < 512; i += 32) s_lut[i] = T.lut[i];
+    __syncwarp();
+
+    const int chain = blockIdx.x;
+    const int seg = chain / T.max_slices, si = chain - seg * T.max_slices;
+    const int f0 = B.seg_first[seg], f1 = B.seg_first[seg + 1];
+    uint8_t *models = B.state + ((size_t)B.seg_set[seg] * T.max_slices + si) * 3 * T.state_stride;
+    int16_t *ring = B.ring + (size_t)chain * 4 * 3 * T.ring_w + kDecRingPad;
+    const int golomb = T.ac == 0;
+    const int bits = T.coded_bits;
+    const int nplanes = T.colorspace ? 3 + T.transparency : (T.ya8 ? 2 : 1 + 2 * T.chroma_planes + T.transparency);
+
+    for (int f = f0; f < f1; f++) {
+        if (si >= B.slice_count[f]) continue;
+        const int fs = f * T.max_slices + si;
+        const uint8_t *sbeg = B.pkt + B.pkt_off[f] + B.slice_start[fs];
+        const uint32_t ssize = B.slice_size[fs];
+        const bool key = B.frame_key[f] != 0;
+
+        // ---- lane 0: coder init, keyframe bit, slice header (ffv1dec.c:282-359)
+        SliceRd sr;
+        int sx = 0, sy = 0, sw = 0, sh = 0, qti[3] = {0, 0, 0};
+        int bad = 0;
+        if (lane == 0) {
+            sr.golomb = golomb; sr.run_index = 0; sr.err = 0;
+            rd_init(sr.rc, sbeg, ssize);
+            if (si == 0) { uint8_t ks = 128; rd_get(sr.rc, &ks, s_lut); }              // keyframe bit (ffv1dec.c:924)
+            uint8_t st[32];
+            for (int i = 0; i < 32; i++) st[i] = 128;
+            const uint32_t ux = (uint32_t)rd_symbol(sr.rc, st, s_lut, false, sr.err) * (uint32_t)T.width;
+            const uint32_t uy = (uint32_t)rd_symbol(sr.rc, st, s_lut, false, sr.err) * (uint32_t)T.height;
+            const uint32_t uw = ((uint32_t)rd_symbol(sr.rc, st, s_lut, false, sr.err) + 1u) * (uint32_t)T.width + ux;
+            const uint32_t uh = ((uint32_t)rd_symbol(sr.rc, st, s_lut, false, sr.err) + 1u) * (uint32_t)T.height + uy;
+            const uint32_t x0 = ux / T.num_h_slices, y0 = uy / T.num_v_slices;
+            const uint32_t w0 = uw / T.num_h_slices - x0, h0 = uh / T.num_v_slices - y0;
+            if (w0 > (uint32_t)T.width || h0 > (uint32_t)T.height || (unsigned long long)x0 + w0 > (uint32_t)T.width ||
+                (unsigned long long)y0 + h0 > (uint32_t)T.height || w0 == 0 || h0 == 0 || sr.err) bad = 1;
+            sx = (int)x0; sy = (int)y0; sw = (int)w0; sh = (int)h0;
+            for (int k = 0; k < T.plane_count && !bad; k++) {
+                const int idx = rd_symbol(sr.rc, st, s_lut, false, sr.err);
+                if ((unsigned)idx >= 2u) bad = 1; else if (k < 3) qti[k] = idx;
+            }
+            if (!bad) {
+                rd_symbol(sr.rc, st, s_lut, false, sr.err);      // picture structure
+                rd_symbol(sr.rc, st, s_lut, false, sr.err);      // sample aspect ratio num
+                rd_symbol(sr.rc, st, s_lut, false, sr.err);      // sample aspect ratio den
+            }
+            if (sw + 2 * kDecRingPad > T.ring_w) bad = 1;
+            if (!bad && golomb) {                                                       // ffv1dec.c:427-434
+                if (T.micro_version > 1 || T.version > 3) { uint8_t s129 = 129; rd_get(sr.rc, &s129, s_lut); }
+                const uint32_t acb = (uint32_t)(sr.rc.ptr - sr.rc.start) - 1u;
+                sr.br.buf = sr.rc.start + acb;
+                sr.br.nbytes = ssize - acb;
+                sr.br.pos = 0;
+                br_load(sr.br, 0);
+            }
+        }
+        bad = __shfl_sync(0xFFFFFFFFu, bad, 0);
+        if (bad) { if (lane == 0) B.damaged[fs] |= 2u; continue; }
+        sx = __shfl_sync(0xFFFFFFFFu, sx, 0); sy = __shfl_sync(0xFFFFFFFFu, sy, 0);
+        sw = __shfl_sync(0xFFFFFFFFu, sw, 0); sh = __shfl_sync(0xFFFFFFFFu, sh, 0);
+        qti[0] = __shfl_sync(0xFFFFFFFFu, qti[0], 0); qti[1] = __shfl_sync(0xFFFFFFFFu, qti[1], 0);
+        qti[2] = __shfl_sync(0xFFFFFFFFu, qti[2], 0);
+
+        // ---- keyframe: reset the models (ffv1.c:177-202)
+        if (key) {
+            for (int pc = 0; pc < 3; pc++) {
+                uint8_t *m = models + (size_t)pc * T.state_stride;
+                const int nctx = T.ctx_count[qti[pc < T.plane_count ? pc : 0]];
+                if (!golomb) {
+                    uint32_t *m4 = reinterpret_cast<uint32_t *>(m);
+                    for (int i = lane; i < nctx * 8; i += 32) m4[i] = 0x80808080u;
+                } else {
+                    uint2 *m8 = reinterpret_cast<uint2 *>(m);
+                    // VlcState {drift 0, error_sum 4, bias 0, count 1}
+                    for (int i = lane; i < nctx; i += 32) m8[i] = make_uint2(0x00040000u, 0x00000100u);
+                }
+            }
+        }
+        __syncwarp();
+
+        uint8_t *frame = B.out + (size_t)f * T.frame_bytes;
+        if (!T.colorspace) {
+            // ---- decode_plane per plane (ffv1dec.c:183-224, 436-455)
+            for (int p = 0; p < nplanes; p++) {
+                int src, hs = 0, vs = 0, pc, pstep = T.bits > 8 ? 2 : 1, poff = 0;
+                if (T.ya8) { src = 0; pc = p; pstep = 2; poff = p; }
+                else if (p == 0) { src = 0; pc = 0; }
+                else if (T.chroma_planes && p <= 2) { src = p; hs = T.hshift; vs = T.vshift; pc = 1; }
+                else { src = 3; pc = 2; }
+                const int w = -((-sw) >> hs), h = -((-sh) >> vs);
+                const int px0 = sx >> hs, py0 = sy >> vs;
+                const int16_t *q = s_quant + qti[pc < T.plane_count ? pc : 0] * 5 * 256;
+                uint8_t *model = models + (size_t)pc * T.state_stride;
+                int16_t *rows = ring;                                                    // plane slot 0: three rows
+                for (int i = lane - kDecRingPad; i < 3 * T.ring_w - kDecRingPad; i += 32) rows[i] = 0;
+                __syncwarp();
+                if (lane == 0) sr.run_index = 0;
+                for (int y = 0; y < h; y++) {
+                    int16_t *cur = rows + (y % 3) * T.ring_w;
+                    int16_t *top = rows + ((y + 2) % 3) * T.ring_w;
+                    int16_t *top2 = rows + ((y + 1) % 3) * T.ring_w;
+                    if (lane == 0) {
+                        cur[-1] = top[0];                 // ffv1dec.c:199-200
+                        top[w] = top[w - 1];
+                        dec_line(sr, model, q, s_lut, cur, top, top2, w, bits);
+                    }
+                    __syncwarp();
+                    uint8_t *dst = frame + T.plane_off[src] + (size_t)(py0 + y) * T.plane_pitch[src];
+                    if (T.bits <= 8) {
+                        for (int x = lane; x < w; x += 32) dst[(px0 + x) * pstep + poff] = (uint8_t)cur[x];
+                    } else {
+                        const int shl = T.packed_at_lsb ? 0 : 16 - T.bits;              // ffv1dec.c:211-219
+                        uint16_t *d16 = reinterpret_cast<uint16_t *>(dst) + px0;
+                        for (int x = lane; x < w; x += 32) d16[x] = (uint16_t)((uint16_t)cur[x] << shl);
+                    }
+                    __syncwarp();
+                }
+            }
+        } else {
+            // ---- decode_rgb_frame (ffv1dec.c:226-280): planes interleaved per row, shared run_index
+            for (int i = lane - kDecRingPad; i < 4 * 3 * T.ring_w - kDecRingPad; i += 32) ring[i] = 0;
+            __syncwarp();
+            if (lane == 0) sr.run_index = 0;
+            const int offset = 1 << (T.bits <= 8 ? 8 : T.bits);
+            for (int y = 0; y < sh; y++) {
+                if (lane == 0) {
+                    for (int p = 0; p < nplanes; p++) {
+                        int16_t *rows = ring + p * 3 * T.ring_w;
+                        int16_t *cur = rows + (y % 3) * T.ring_w;
+                        int16_t *top = rows + ((y + 2) % 3) * T.ring_w;
+                        int16_t *top2 = rows + ((y + 1) % 3) * T.ring_w;
+                        const int pc = (p + 1) / 2;
+                        cur[-1] = top[0];
+                        top[sw] = top[sw - 1];
+                        dec_line(sr, models + (size_t)pc * T.state_stride, s_quant + qti[pc < T.plane_count ? pc : 0] * 5 * 256, s_lut,
+                                 cur, top, top2, sw, bits);
+                    }
+                }
+                __syncwarp();
+                const int16_t *gr = ring + (y % 3) * T.ring_w, *br = gr + 3 * T.ring_w, *rr = gr + 6 * T.ring_w, *ar = gr + 9 * T.ring_w;
+                for (int x = lane; x < sw; x += 32) {
+                    int g = gr[x], b = br[x], r = rr[x];
+                    const int a = nplanes == 4 ? ar[x] : 0;
+                    b -= offset; r -= offset;
+                    g -= (b + r) >> 2;
+                    b += g; r += g;
+                    if (T.rgb32) {
+                        uint32_t *d = reinterpret_cast<uint32_t *>(frame + T.plane_off[0] + (size_t)(sy + y) * T.plane_pitch[0]) + sx + x;
+                        *d = (uint32_t)(b & 0xFF) | ((uint32_t)(g & 0xFF) << 8) | ((uint32_t)(r & 0xFF) << 16) | ((uint32_t)(a & 0xFF) << 24);
+                    } else {
+                        // planar RGB keeps the reference's naming quirk: data[0] <- b, data[1] <- g, data[2] <- r (ffv1dec.c:274-276)
+                        reinterpret_cast<uint16_t *>(frame + T.plane_off[0] + (size_t)(sy + y) * T.plane_pitch[0])[sx + x] = (uint16_t)b;
+                        reinterpret_cast<uint16_t *>(frame + T.plane_off[1] + (size_t)(sy + y) * T.plane_pitch[1])[sx + x] = (uint16_t)g;
+                        reinterpret_cast<uint16_t *>(frame + T.plane_off[2] + (size_t)(sy + y) * T.plane_pitch[2])[sx + x] = (uint16_t)r;
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        // ---- end-of-slice check (ffv1dec.c:459-467)
+        if (lane == 0) {
+            uint32_t flag = sr.err ? 2u : 0u;
+            if (!golomb) {
+                uint8_t s129 = 129;
+                rd_get(sr.rc, &s129, s_lut);
+                const long long v = (long long)(sr.rc.end - sr.rc.ptr) - 2 - 5 * T.ec;
+                if (v) flag |= 2u;
+            }
+            if (flag) B.damaged[fs] |= flag;
+        }
+        __syncwarp();
+    }
+}
+
+void launch_decode(const DecDeviceTables &t, const DecBatch &b, cudaStream_t s)
+{
+    k_decode<<<b.nseg * t.max_slices, 32, 0, s>>>(t, b);
+}
+
+// ------------------------------------------------------------------------------------------------ concealment
+__global__ void __launch_bounds__(256) k_conceal(const DecDeviceTables T, const DecBatch B, const int f)
+{
+    const int si = blockIdx.x;
+    if (si >= B.slice_count[f] || !B.damaged[f * T.max_slices + si]) return;
+    const uint8_t *prev = f > 0 ? B.out + (size_t)(f - 1) * T.frame_bytes : B.prev_frame;
+    if (!prev) return;
+    uint8_t *cur = B.out + (size_t)f * T.frame_bytes;
+    // the reference copies the rectangle of the slice grid position (ffv1dec.c:1006-1018)
+    const int gx = si % T.num_h_slices, gy = si / T.num_h_slices;
+    const int x0 = T.width * gx / T.num_h_slices, x1 = T.width * (gx + 1) / T.num_h_slices;
+    const int y0 = T.height * gy / T.num_v_slices, y1 = T.height * (gy + 1) / T.num_v_slices;
+    const int nsrc = T.colorspace ? (T.rgb32 ? 1 : 3) : (T.ya8 ? 1 : 1 + 2 * T.chroma_planes + T.transparency);
+    for (int p = 0; p < nsrc; p++) {
+        const bool chroma = !T.colorspace && !T.ya8 && T.chroma_planes && (p == 1 || p == 2);
+        const int hs = chroma ? T.hshift : 0, vs = chroma ? T.vshift : 0;
+        const int src_plane = (!T.colorspace && !T.ya8 && !T.chroma_planes && p == 1) ? 3 : p;
+        const int bpp = T.rgb32 ? 4 : (T.ya8 ? 2 : (T.bits > 8 ? 2 : 1));
+        const int bx0 = (x0 >> hs) * bpp, bx1 = (-((-x1) >> hs)) * bpp;
+        const int ry0 = y0 >> vs, ry1 = -((-y1) >> vs);
+        const int rb = bx1 - bx0;
+        for (int i = threadIdx.x; i < rb * (ry1 - ry0); i += blockDim.x) {
+            const int y = ry0 + i / rb, x = bx0 + i % rb;
+            const size_t o = (size_t)T.plane_off[src_plane] + (size_t)y * T.plane_pitch[src_plane] + x;
+            cur[o] = prev[o];
+        }
+    }
+}
+
+void launch_conceal(const DecDeviceTables &t, const DecBatch &b, int frame, cudaStream_t s)
+{
+    k_conceal<<<t.max_slices, 256, 0, s>>>(t, b, frame);
+}
+
+} // namespace ffv1
