@@ -634,6 +634,155 @@ void launch_rangecode(const EncDeviceTables &t, const EncBatch &b, cudaStream_t 
 }
 
 // =================================================================================================
+// k_golomb: Golomb-Rice / run-mode coder (ffv1enc.c:240-269, 327-367; golomb.h:508-563; put_bits.h), one warp per
+// (GOP segment, slice) chain: the VlcState of a context carries over from frame to frame inside a GOP.
+// First version: lane 0 walks the records sequentially (the other lanes only move state and prefix bytes).
+// =================================================================================================
+__constant__ uint8_t c_enc_log2_run[41] = {
+    0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7,
+    8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24,
+};
+
+struct BitW {                 // MSB-first bit writer (put_bits.h:152-195)
+    uint8_t *buf;
+    uint32_t pos, cap;        // bytes written / capacity
+    unsigned long long acc;
+    int nbits;
+};
+
+__device__ __forceinline__ void bw_put(BitW &w, int n, uint32_t v)
+{
+    w.acc = (w.acc << n) | v;
+    w.nbits += n;
+    while (w.nbits >= 8) {
+        w.nbits -= 8;
+        if (w.pos < w.cap) w.buf[w.pos] = (uint8_t)(w.acc >> w.nbits);
+        w.pos++;
+    }
+}
+
+struct __align__(8) VlcEnc { int16_t drift; uint16_t error_sum; int8_t bias; uint8_t count; uint16_t pad; };
+
+__device__ __forceinline__ void vlc_put(BitW &w, VlcEnc *sp, int v, int bits)
+{
+    // put_vlc_symbol (ffv1enc.c:240-269) + set_sr_golomb (golomb.h:554-563) + update_vlc_state (ffv1.h:192-224)
+    VlcEnc s = *sp;
+    v = ((v - s.bias) << (32 - bits)) >> (32 - bits);                     // fold
+    int k = 0;
+    for (int i = s.count; i < s.error_sum; i += i) k++;
+    const int code = v ^ ((2 * s.drift + s.count) >> 31);
+    int m = -2 * code - 1;
+    m ^= m >> 31;
+    const int e = m >> k;
+    if (e < 12) bw_put(w, e + k + 1, (1u << k) + ((uint32_t)m & ((1u << k) - 1u)));
+    else        bw_put(w, 12 + bits, (uint32_t)(m - 11));
+    int drift = s.drift, count = s.count, esum = s.error_sum, bias = s.bias;
+    esum += abs(v);
+    drift += v;
+    if (count == 128) { count >>= 1; drift >>= 1; esum >>= 1; }
+    count++;
+    if (drift <= -count) {
+        if (bias > -128) bias--;
+        drift += count;
+        if (drift <= -count) drift = -count + 1;
+    } else if (drift > 0) {
+        if (bias < 127) bias++;
+        drift -= count;
+        if (drift > 0) drift = 0;
+    }
+    s.drift = (int16_t)drift; s.count = (uint8_t)count; s.error_sum = (uint16_t)esum; s.bias = (int8_t)bias;
+    *sp = s;
+}
+
+__global__ void __launch_bounds__(32) k_golomb(const EncDeviceTables T, const EncBatch B)
+{
+    const Layout &L = T.layout;
+    const int lane = threadIdx.x;
+    const int chain = blockIdx.x;
+    const int seg = chain / L.nslices, s = chain - seg * L.nslices;
+    const SliceGeom &g = T.slices[s];
+    const int f0 = B.seg_first[seg], f1 = B.seg_first[seg + 1];
+    const size_t pc_bytes = (size_t)L.ctx_count * 32;                     // same footprint as a range-coder model
+    uint8_t *st = B.state_seg + (size_t)chain * L.npc * pc_bytes;
+    const size_t coff = (size_t)s * L.npc * pc_bytes;
+    {
+        const bool key = B.frame_key[f0];
+        const uint2 *in8 = reinterpret_cast<const uint2 *>(B.carry_in + coff);
+        uint2 *st8 = reinterpret_cast<uint2 *>(st);
+        // VlcState {drift 0, error_sum 4, bias 0, count 1} (ffv1.c:194-199)
+        for (int pc = 0; pc < L.npc; pc++)
+            for (int i = lane; i < L.ctx_count; i += 32)
+                st8[pc * (pc_bytes / 8) + i] = key ? make_uint2(0x00040000u, 0x00000100u) : in8[pc * (pc_bytes / 8) + i];
+        __syncwarp();
+    }
+    const int bits = L.coded_bits;
+    for (int f = f0; f < f1; f++) {
+        const int key = B.frame_key[f] ? 1 : 0;
+        uint8_t *out = B.scratch + (size_t)f * L.scratch_per_frame + g.scratch_off;
+        const int npre = T.gprefix_len[s * 2 + key];
+        const uint8_t *pre = T.gprefix + (size_t)(s * 2 + key) * kMaxGolombPrefix;
+        for (int i = lane; i < npre; i += 32) out[i] = pre[i];
+        if (lane == 0) {
+            BitW w;
+            w.buf = out; w.pos = (uint32_t)npre; w.cap = g.scratch_cap; w.acc = 0; w.nbits = 0;
+            const uint32_t *rec_slice = B.rec + (size_t)f * L.rec_per_frame + g.rec_first;
+            int run_index = 0;
+            for (int li = 0; li < g.nlines; li++) {
+                const LineDesc ld = T.lines[g.line_first + li];
+                if (!L.rgb && ld.y == 0) run_index = 0;                   // encode_plane starts a new plane (ffv1enc.c:379)
+                VlcEnc *vs = reinterpret_cast<VlcEnc *>(st + (size_t)ld.pc * pc_bytes);
+                const uint32_t *recp = rec_slice + ld.rec_off;
+                int run_count = 0, run_mode = 0;
+                for (int x = 0; x < ld.w; x++) {
+                    const uint32_t r = recp[x];
+                    const int ctx = (int)(r >> 16);
+                    int diff = (int)(int16_t)(r & 0xFFFFu);
+                    if (ctx == 0) run_mode = 1;
+                    if (run_mode) {
+                        if (diff) {
+                            while (run_count >= 1 << c_enc_log2_run[run_index]) {
+                                run_count -= 1 << c_enc_log2_run[run_index];
+                                run_index++;
+                                bw_put(w, 1, 1u);
+                            }
+                            bw_put(w, 1 + c_enc_log2_run[run_index], (uint32_t)run_count);
+                            if (run_index) run_index--;
+                            run_count = 0; run_mode = 0;
+                            if (diff > 0) diff--;
+                        } else
+                            run_count++;
+                    }
+                    if (!run_mode) vlc_put(w, vs + ctx, diff, bits);
+                }
+                if (run_mode) {                                            // end-of-line run flush (ffv1enc.c:358-367)
+                    while (run_count >= 1 << c_enc_log2_run[run_index]) {
+                        run_count -= 1 << c_enc_log2_run[run_index];
+                        run_index++;
+                        bw_put(w, 1, 1u);
+                    }
+                    if (run_count) bw_put(w, 1, 1u);
+                }
+            }
+            if (w.nbits) bw_put(w, 8 - w.nbits, 0u);                      // flush_put_bits: zero padding to a byte
+            B.slice_bytes[f * L.nslices + s] = w.pos;
+            if (w.pos > w.cap) atomicMax(&B.status[1], (unsigned long long)w.pos);
+        }
+        __syncwarp();
+    }
+    if (f1 == B.nframes) {
+        const uint2 *st8 = reinterpret_cast<const uint2 *>(st);
+        uint2 *out8 = reinterpret_cast<uint2 *>(B.carry_out + coff);
+        for (int pc = 0; pc < L.npc; pc++)
+            for (int i = lane; i < L.ctx_count; i += 32) out8[pc * (pc_bytes / 8) + i] = st8[pc * (pc_bytes / 8) + i];
+    }
+}
+
+void launch_golomb(const EncDeviceTables &t, const EncBatch &b, cudaStream_t s)
+{
+    k_golomb<<<b.nseg * t.layout.nslices, 32, 0, s>>>(t, b);
+}
+
+// =================================================================================================
 // k_pack_layout / k_pack_slices: packet assembly + CRC
 // =================================================================================================
 __global__ void __launch_bounds__(1024) k_pack_layout(const EncDeviceTables T, const EncBatch B)

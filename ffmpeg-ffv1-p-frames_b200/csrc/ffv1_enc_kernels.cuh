@@ -11,6 +11,7 @@ constexpr int kPixelChunk     = 512;          // samples of one row handled per 
 constexpr int kPixelPadL      = 8;            // int16 elements left of x=0 in a staged row (keeps 16 B alignment)
 constexpr int kPixelRowElems  = kPixelChunk + 16;
 constexpr int kReplayWarps    = 2;            // chains (warps) per CTA of the state-replay kernel
+ constexpr int kMaxGolombPrefix = 4096;        // bytes (a version 0/1 keyframe carries the whole header)
 constexpr int kMaxPrefix      = 8192;         // decisions before the first sample (v0/v1 keyframes carry a whole header)
 
 // per-batch device buffers and scalars handed to the kernels
@@ -50,6 +51,8 @@ struct EncDeviceTables {
     const uint8_t *trans_lut;           // [512]: zero_state, one_state of the slice coders
     const uint8_t *one_pow;             // [33][256]: one_state applied k times (runs of zero residuals in one context)
     const uint8_t *run_pc;              // [runs_per_frame] plane context of every run
+    const uint8_t *gprefix;             // Golomb-Rice mode: [nslices][2][kMaxGolombPrefix] bytes every slice starts with
+    const int32_t *gprefix_len;         // [nslices][2]
     const uint16_t *prefix;             // [nslices][2][kMaxPrefix]
     const int32_t *prefix_len;          // [nslices][2]
     int32_t ec;
@@ -62,6 +65,7 @@ void launch_pixel(const EncDeviceTables &t, const EncBatch &b, cudaStream_t s);
 int  replay_smem_bytes(const Layout &L);
 void launch_replay(const EncDeviceTables &t, const EncBatch &b, cudaStream_t s);
 void launch_rangecode(const EncDeviceTables &t, const EncBatch &b, cudaStream_t s);
+void launch_golomb(const EncDeviceTables &t, const EncBatch &b, cudaStream_t s);
 void launch_pack(const EncDeviceTables &t, const EncBatch &b, cudaStream_t s);
 cudaError_t configure_kernels(const Layout &L);
 // tuned per-pixel pass for planar sources (ffv1_pixel_fast.cu)

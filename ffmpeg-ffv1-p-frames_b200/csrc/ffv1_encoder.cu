@@ -28,6 +28,7 @@ struct FFV1B200Encoder {
     // static device tables
     DevBuf<SliceGeom> d_slices; DevBuf<LineDesc> d_lines; DevBuf<int32_t> d_pc_lines; DevBuf<TileDesc> d_tiles;
     DevBuf<int16_t> d_quant; DevBuf<uint8_t> d_lut; DevBuf<uint16_t> d_prefix; DevBuf<int32_t> d_prefix_len;
+    DevBuf<uint8_t> d_gprefix; DevBuf<int32_t> d_gprefix_len;
     // batch buffers
     DevBuf<uint8_t> d_in; size_t in_plane_off[4] = {0,0,0,0}; int in_pitch[4] = {0,0,0,0}; size_t in_frame_stride = 0;
     DevBuf<const uint8_t *> d_planes; PinnedBuf<const uint8_t *> h_planes;
@@ -59,6 +60,22 @@ int fail(int code, const std::string &msg) { set_last_error(msg); return code; }
 int upload_prefixes(FFV1B200Encoder *e)
 {
     const int ns = e->cfg.slice_count();
+    if (e->tab.layout.golomb) {
+        std::vector<uint8_t> gp((size_t)ns * 2 * kMaxGolombPrefix, 0);
+        std::vector<int32_t> gl((size_t)ns * 2, 0);
+        for (int s = 0; s < ns; s++)
+            for (int key = 0; key < 2; key++) {
+                std::vector<uint8_t> b = slice_prefix_bytes(e->cfg, s, key != 0, e->props.sar_num, e->props.sar_den, e->props.picture_structure);
+                if ((int)b.size() > kMaxGolombPrefix) return fail(FFV1B200_ERR_EINVAL, "slice header too long");
+                std::copy(b.begin(), b.end(), gp.begin() + (size_t)(s * 2 + key) * kMaxGolombPrefix);
+                gl[s * 2 + key] = (int32_t)b.size();
+            }
+        CU_TRY(e->d_gprefix.upload(gp.data(), gp.size(), e->stream));
+        CU_TRY(e->d_gprefix_len.upload(gl.data(), gl.size(), e->stream));
+        CU_TRY(cudaStreamSynchronize(e->stream));
+        e->prefix_dirty = false;
+        return 0;
+    }
     std::vector<uint16_t> pre((size_t)(ns * 2 + 1) * kMaxPrefix, 0);
     pre[(size_t)ns * 2 * kMaxPrefix] = 129;                              // the decision that closes every slice (state 129, bit 0)
     std::vector<int32_t> len((size_t)ns * 2, 0);
@@ -106,7 +123,7 @@ int alloc_batch_buffers(FFV1B200Encoder *e)
         CU_TRY(e->d_carry[k].alloc(state_bytes));
         CU_TRY(cudaMemsetAsync(e->d_carry[k].p, 128, state_bytes, e->stream));
     }
-    if (!e->state_in_smem && !L.golomb) {
+    if (!e->state_in_smem || L.golomb) {
         const int g = e->cfg.gop_size > 0 ? e->cfg.gop_size : 1;
         CU_TRY(e->d_state_seg.alloc(state_bytes * ((F + g - 1) / g + 1)));               // one state set per GOP segment of a batch
     }
@@ -118,7 +135,7 @@ EncDeviceTables device_tables(FFV1B200Encoder *e)
     EncDeviceTables t;
     t.layout = e->tab.layout;
     t.slices = e->d_slices.p; t.lines = e->d_lines.p; t.pc_lines = e->d_pc_lines.p; t.tiles = e->d_tiles.p;
-    t.quant = e->d_quant.p; t.trans_lut = e->d_lut.p; t.one_pow = e->d_one_pow.p; t.run_pc = e->d_run_pc.p; t.prefix = e->d_prefix.p; t.prefix_len = e->d_prefix_len.p;
+    t.quant = e->d_quant.p; t.trans_lut = e->d_lut.p; t.one_pow = e->d_one_pow.p; t.run_pc = e->d_run_pc.p; t.gprefix = e->d_gprefix.p; t.gprefix_len = e->d_gprefix_len.p; t.prefix = e->d_prefix.p; t.prefix_len = e->d_prefix_len.p;
     t.ec = e->cfg.ec; t.version = e->cfg.version; t.state_in_smem = e->state_in_smem ? 1 : 0;
     return t;
 }
@@ -127,7 +144,6 @@ EncDeviceTables device_tables(FFV1B200Encoder *e)
 int run_pipeline(FFV1B200Encoder *e, int nframes, const int linesizes[4], uint8_t *d_out, size_t d_out_cap, cudaStream_t s)
 {
     const Layout &L = e->tab.layout;
-    if (L.golomb) return fail(FFV1B200_ERR_ENOSYS, "coder=0 (Golomb-Rice) GPU path is not built yet");
     if (e->prefix_dirty) { int r = upload_prefixes(e); if (r < 0) return r; }
 
     // GOP segments of this batch (keyframe rule: ffv1enc.c:1299)
@@ -166,13 +182,13 @@ int run_pipeline(FFV1B200Encoder *e, int nframes, const int linesizes[4], uint8_
         if (fast) launch_pixel_fast(t, b, e->max_plane_width, e->num_sms, s);
         else      launch_pixel(t, b, s);
         cudaEventRecord(e->ev[1], s);
-        launch_replay(t, b, s);
+        if (!L.golomb) launch_replay(t, b, s);
         cudaEventRecord(e->ev[2], s);
-        launch_rangecode(t, b, s);
+        if (!L.golomb) launch_rangecode(t, b, s); else launch_golomb(t, b, s);
         cudaEventRecord(e->ev[3], s);
         launch_pack(t, b, s);
         cudaEventRecord(e->ev[4], s);
-        e->stats.kernel_launches += 5;
+        e->stats.kernel_launches += L.golomb ? 4 : 5;
         CU_TRY(cudaGetLastError());
         CU_TRY(cudaMemcpyAsync(e->h_status.p, e->d_status.p, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost, s));
         CU_TRY(cudaMemcpyAsync(e->h_pkt_size.p, e->d_pkt_size.p, sizeof(uint32_t) * nframes, cudaMemcpyDeviceToHost, s));

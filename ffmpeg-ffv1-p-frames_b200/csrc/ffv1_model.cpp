@@ -559,6 +559,16 @@ std::vector<uint16_t> slice_prefix_decisions(const Config &c, int si, bool key, 
     return bc.decisions;
 }
 
+std::vector<uint8_t> slice_prefix_bytes(const Config &c, int si, bool key, int sar_num, int sar_den, int ps)
+{
+    // Golomb-Rice mode (ffv1enc.c:1176-1183): the range-coded part of a slice is closed before the bit stream starts
+    BinCoder bc;
+    put_prefix(bc, c, si, key, sar_num, sar_den, ps);
+    if (c.version > 2) { uint8_t s129 = 129; bc.put(&s129, 0); }
+    if (c.version > 2 || si == 0) { bc.terminate(); return bc.bytes; }
+    return std::vector<uint8_t>();
+}
+
 // ------------------------------------------------------------------------------------------------
 // kernel tables
 // ------------------------------------------------------------------------------------------------

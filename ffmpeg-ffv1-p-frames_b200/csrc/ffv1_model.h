@@ -140,6 +140,11 @@ void coder_state_tables(const Config &c, uint8_t zero_state[256], uint8_t one_st
 std::vector<uint16_t> slice_prefix_decisions(const Config &c, int slice_index, bool key_frame,
                                              int sar_num, int sar_den, int picture_structure);
 
+// Golomb-Rice mode: the BYTES a slice starts with (range-coded key bit / header, the state-129 bit of version 3,
+// ff_rac_terminate); the MSB-first bit stream of the samples follows them (ffv1enc.c:1176-1183).
+std::vector<uint8_t> slice_prefix_bytes(const Config &c, int slice_index, bool key_frame,
+                                        int sar_num, int sar_den, int picture_structure);
+
 void slice_rect(const Config &c, int i, int *x0, int *y0, int *w, int *h);
 
 // Builds every geometry table the kernels use.
