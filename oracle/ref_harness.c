@@ -39,14 +39,36 @@ typedef struct RefEnc {
 /* level<0 / slices==0 / slicecrc<0 mean "leave at the reference default". threads>1 enables the
  * reference's slice threading (pthread_slice.c). sar_num/den go to every AVFrame (they are coded in
  * each slice header, ffv1enc.c:1048-1049). */
+static void *enc_open_impl(AVCodec *codec, int w, int h, const char *pix_fmt, int gop, int level, int coder, int context,
+                           int slices, int slicecrc, int threads, int strict_experimental, int batch);
+
 void *ffv1ref_enc_open(int w, int h, const char *pix_fmt, int gop, int level, int coder, int context,
                        int slices, int slicecrc, int threads, int strict_experimental)
 {
     reg();
+    return enc_open_impl(&ff_ffv1_encoder, w, h, pix_fmt, gop, level, coder, context, slices, slicecrc, threads, strict_experimental, 0);
+}
+
+/* Drop-in test support: register an out-of-tree AVCodec (the ffv1_b200 shim) with THIS libavcodec and open it by
+ * name through the same public API path (avcodec_find_encoder_by_name, utils.c:3051). */
+void ffv1ref_register_codec(AVCodec *codec) { reg(); avcodec_register(codec); }
+
+void *ffv1ref_enc_open_named(const char *name, int w, int h, const char *pix_fmt, int gop, int level, int coder, int context,
+                             int slices, int slicecrc, int batch)
+{
+    reg();
+    AVCodec *codec = avcodec_find_encoder_by_name(name);
+    if (!codec) return NULL;
+    return enc_open_impl(codec, w, h, pix_fmt, gop, level, coder, context, slices, slicecrc, 1, 0, batch);
+}
+
+static void *enc_open_impl(AVCodec *codec, int w, int h, const char *pix_fmt, int gop, int level, int coder, int context,
+                           int slices, int slicecrc, int threads, int strict_experimental, int batch)
+{
     enum AVPixelFormat pf = av_get_pix_fmt(pix_fmt);
     if (pf == AV_PIX_FMT_NONE) return NULL;
     RefEnc *e = calloc(1, sizeof(*e));
-    e->ctx = avcodec_alloc_context3(&ff_ffv1_encoder);
+    e->ctx = avcodec_alloc_context3(codec);
     e->ctx->width = w; e->ctx->height = h; e->ctx->pix_fmt = pf;
     e->ctx->time_base = (AVRational){1, 25};
     e->ctx->gop_size = gop;
@@ -59,7 +81,8 @@ void *ffv1ref_enc_open(int w, int h, const char *pix_fmt, int gop, int level, in
     av_opt_set_int(e->ctx->priv_data, "coder", coder, 0);
     av_opt_set_int(e->ctx->priv_data, "context", context, 0);
     av_opt_set_int(e->ctx->priv_data, "slicecrc", slicecrc, 0);
-    if (avcodec_open2(e->ctx, &ff_ffv1_encoder, NULL) < 0) {
+    if (batch > 0) av_opt_set_int(e->ctx->priv_data, "batch", batch, 0);
+    if (avcodec_open2(e->ctx, codec, NULL) < 0) {
         avcodec_free_context(&e->ctx); free(e); return NULL;
     }
     e->frame = av_frame_alloc();
@@ -83,6 +106,17 @@ int ffv1ref_enc_frame(void *h, uint8_t *const planes[4], const int linesize[4], 
     AVPacket pkt;
     int got = 0, ret, i;
     av_init_packet(&pkt); pkt.data = NULL; pkt.size = 0;
+    if (!planes) {                                  /* drain a delayed encoder (AV_CODEC_CAP_DELAY): frame = NULL */
+        ret = avcodec_encode_video2(e->ctx, &pkt, NULL, &got);
+        if (ret < 0) return ret;
+        if (!got) return 0;
+        if (pkt.size > cap) { av_packet_unref(&pkt); return -2; }
+        memcpy(dst, pkt.data, pkt.size);
+        ret = pkt.size;
+        if (key) *key = !!(pkt.flags & AV_PKT_FLAG_KEY);
+        av_packet_unref(&pkt);
+        return ret;
+    }
     /* hand the encoder a refcounted frame (as ffmpeg.c's rawvideo path does): copy the caller's rows in */
     av_frame_unref(e->frame);
     e->frame->format = e->ctx->pix_fmt; e->frame->width = e->ctx->width; e->frame->height = e->ctx->height;
@@ -124,11 +158,26 @@ typedef struct RefDec {
     AVFrame *frame;
 } RefDec;
 
+static void *dec_open_impl(AVCodec *codec, int w, int h, const uint8_t *extradata, int extradata_size, int threads, int frame_threads);
+
 void *ffv1ref_dec_open(int w, int h, const uint8_t *extradata, int extradata_size, int threads, int frame_threads)
 {
     reg();
+    return dec_open_impl(&ff_ffv1_decoder, w, h, extradata, extradata_size, threads, frame_threads);
+}
+
+void *ffv1ref_dec_open_named(const char *name, int w, int h, const uint8_t *extradata, int extradata_size)
+{
+    reg();
+    AVCodec *codec = avcodec_find_decoder_by_name(name);
+    if (!codec) return NULL;
+    return dec_open_impl(codec, w, h, extradata, extradata_size, 1, 0);
+}
+
+static void *dec_open_impl(AVCodec *codec, int w, int h, const uint8_t *extradata, int extradata_size, int threads, int frame_threads)
+{
     RefDec *d = calloc(1, sizeof(*d));
-    d->ctx = avcodec_alloc_context3(&ff_ffv1_decoder);
+    d->ctx = avcodec_alloc_context3(codec);
     d->ctx->width = w; d->ctx->height = h;
     if (extradata_size > 0) {
         d->ctx->extradata = av_mallocz(extradata_size + AV_INPUT_BUFFER_PADDING_SIZE);
@@ -138,7 +187,7 @@ void *ffv1ref_dec_open(int w, int h, const uint8_t *extradata, int extradata_siz
     d->ctx->flags |= AV_CODEC_FLAG_BITEXACT;
     d->ctx->thread_count = threads > 1 ? threads : 1;
     if (threads > 1) d->ctx->thread_type = frame_threads ? FF_THREAD_FRAME : FF_THREAD_SLICE;
-    if (avcodec_open2(d->ctx, &ff_ffv1_decoder, NULL) < 0) {
+    if (avcodec_open2(d->ctx, codec, NULL) < 0) {
         avcodec_free_context(&d->ctx); free(d); return NULL;
     }
     d->frame = av_frame_alloc();

@@ -1,0 +1,86 @@
+"""Drop-in test at the reference's plugin boundary (run with -m gpu): the AVCodec shim integration/ffv1_b200_avcodec.c is
+registered with the REFERENCE's own libavcodec (oracle/_ref/libffv1ref.so, unmodified sources) via avcodec_register and
+driven through avcodec_open2 / avcodec_encode_video2 / avcodec_decode_video2 with the same AVOptions as "ffv1".
+Packets and extradata must be byte-identical to what the reference encoder produces in the same process, and the
+reference decoder / our decoder must both give back the source frames."""
+import ctypes, os, numpy as np, pytest
+from cases import CASES, make_frames
+from oracle import ffv1_ref, pixfmt
+from oracle.ffv1_oracle import split_planes, _plane_args
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SHIM = os.path.join(ROOT, "integration", "_build", "libffv1_b200_avcodec.so")
+
+@pytest.fixture(scope="module")
+def lavc():
+    if not ffv1_ref.available() or not os.path.exists(SHIM):
+        pytest.skip("reference build / shim not present (built only where /root/reference exists)")
+    import ffv1_b200
+    assert ffv1_b200.device_count() >= 1
+    ctypes.CDLL(os.path.join(ROOT, "oracle", "_ref", "libffv1ref.so"), mode=ctypes.RTLD_GLOBAL)   # the reference's lavc/lavu symbols
+    L = ffv1_ref.lib()
+    shim = ctypes.CDLL(SHIM, mode=ctypes.RTLD_GLOBAL)
+    L.ffv1ref_register_codec.argtypes = [ctypes.c_void_p]
+    L.ffv1ref_register_codec(ctypes.addressof(ctypes.c_char.in_dll(shim, "ff_ffv1_b200_encoder")))
+    L.ffv1ref_register_codec(ctypes.addressof(ctypes.c_char.in_dll(shim, "ff_ffv1_b200_decoder")))
+    L.ffv1ref_enc_open_named.restype = ctypes.c_void_p
+    L.ffv1ref_enc_open_named.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_char_p] + [ctypes.c_int] * 7
+    L.ffv1ref_dec_open_named.restype = ctypes.c_void_p
+    L.ffv1ref_dec_open_named.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
+    return L
+
+def encode_named(L, name, case, batch):
+    cid, w, h, fmt, opts, kind, n = case
+    o = dict(gop=12, level=-1, coder=0, context=0, slices=0, slicecrc=-1); o.update(opts)
+    hnd = L.ffv1ref_enc_open_named(name.encode(), w, h, fmt.encode(), o["gop"], o["level"], o["coder"], o["context"],
+                                   o["slices"], o["slicecrc"], batch)
+    assert hnd, "avcodec_open2(%s) failed" % name
+    ed = ctypes.create_string_buffer(1 << 16)
+    ned = L.ffv1ref_enc_extradata(hnd, ed, 1 << 16)
+    cap = 65536 + pixfmt.frame_bytes(fmt, w, h) * 4
+    buf = ctypes.create_string_buffer(cap)
+    key = ctypes.c_int()
+    pkts = []
+    for f in make_frames(case):
+        planes = split_planes(np.ascontiguousarray(f).view(np.uint8).reshape(-1), fmt, w, h)
+        ptrs, strides = _plane_args(planes)
+        r = L.ffv1ref_enc_frame(hnd, ptrs, strides, 0, 1, 0, 0, buf, cap, ctypes.byref(key))
+        assert r >= 0
+        if r:
+            pkts.append((buf.raw[:r], bool(key.value)))
+    while True:                                            # drain (frame = NULL), as ffmpeg.c flush_encoders does
+        r = L.ffv1ref_enc_frame(hnd, None, None, 0, 1, 0, 0, buf, cap, ctypes.byref(key))
+        assert r >= 0
+        if not r:
+            break
+        pkts.append((buf.raw[:r], bool(key.value)))
+    L.ffv1ref_enc_close(hnd)
+    return ed.raw[:max(ned, 0)], pkts
+
+DROPIN = [c for c in CASES if c[0] in ("c1_cif_intra", "c2_gop_range_24sl", "c3_422p10_ctx1", "c4_gbrp14_30sl",
+                                       "fate_ffv1_golomb", "fate_v3_bgr0", "yuva420p", "range_def")]
+
+@pytest.mark.parametrize("case", DROPIN, ids=[c[0] for c in DROPIN])
+def test_same_packets_through_avcodec_api(lavc, case):
+    ref_ed, ref_pkts = encode_named(lavc, "ffv1", case, 0)
+    our_ed, our_pkts = encode_named(lavc, "ffv1_b200", case, 5)           # batches of 5 frames: delayed output + drain
+    assert our_ed == ref_ed
+    assert len(our_pkts) == len(ref_pkts) == case[6]
+    for i, (a, b) in enumerate(zip(our_pkts, ref_pkts)):
+        assert a[1] == b[1], "AV_PKT_FLAG_KEY of packet %d" % i
+        assert a[0] == b[0], "packet %d differs from the reference encoder's" % i
+
+def test_decode_through_avcodec_api(lavc):
+    case = [c for c in CASES if c[0] == "c2_gop_range_24sl"][0]
+    cid, w, h, fmt, opts, kind, n = case
+    ed, pkts = encode_named(lavc, "ffv1", case, 0)
+    hnd = lavc.ffv1ref_dec_open_named(b"ffv1_b200", w, h, ed, len(ed))
+    assert hnd
+    cap = w * h * 8 + 64
+    out = np.zeros(cap, np.uint8); name = ctypes.create_string_buffer(32); key = ctypes.c_int()
+    for i, f in enumerate(make_frames(case)):
+        r = lavc.ffv1ref_dec_packet(hnd, pkts[i][0], len(pkts[i][0]), out.ctypes.data, cap, name, ctypes.byref(key))
+        assert r == pixfmt.frame_bytes(fmt, w, h) and name.value.decode() == fmt and bool(key.value) == pkts[i][1]
+        assert np.array_equal(out[:r], np.ascontiguousarray(f).view(np.uint8).reshape(-1))
+    lavc.ffv1ref_dec_close(hnd)
