@@ -12,6 +12,7 @@ Option names and meaning follow the reference encoder (ffv1enc.c:1383-1399 and t
 """
 from .codec import (FFV1Encoder, FFV1Decoder, FFV1Error, lib, library_path, device_count, frame_bytes,
                     plane_shapes, EncStats, Packet)
+from .partition import gop_aligned_ranges, reinterleave
 
 __all__ = ["FFV1Encoder", "FFV1Decoder", "FFV1Error", "lib", "library_path", "device_count", "frame_bytes",
-           "plane_shapes", "EncStats", "Packet"]
+           "plane_shapes", "EncStats", "Packet", "gop_aligned_ranges", "reinterleave"]
