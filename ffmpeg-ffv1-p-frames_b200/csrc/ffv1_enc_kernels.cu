@@ -14,6 +14,7 @@
 //                computed in parallel chunks and combined in GF(2) (libavutil/crc.c semantics).
 #include "ffv1_enc_kernels.cuh"
 #include <cstdio>
+#include <cstdlib>
 
 namespace ffv1 {
 
@@ -490,40 +491,35 @@ void launch_replay(const EncDeviceTables &t, const EncBatch &b, cudaStream_t s)
 // (rangecoder.h:52-102, rangecoder.c:104-116).  The adaptive part already happened in k_replay, so a step is
 // range1 = range*p >> 8 plus the carry-propagating byte output.
 // =================================================================================================
+// Carry handling follows renorm_encoder (rangecoder.h:52-75) with one simplification that keeps the output identical:
+// instead of an "no outstanding byte yet" state, the coder starts with a dummy outstanding byte that is written to the
+// kScratchLead-1'th byte of the slice's scratch region and never read back (a carry into it is harmless), so the
+// payload starts at byte kScratchLead.  Bytes are shifted into a 32-bit word and stored four at a time.
 struct Rac {
     uint32_t low, range;
-    int out_byte;        // -1: none pending
-    uint32_t out_count;  // pending 0xFF bytes
-    uint32_t *buf;       // output, written one 32-bit word at a time
+    uint32_t out_byte;   // outstanding byte (its final value depends on a carry that may still arrive)
+    uint32_t out_count;  // 0xFF bytes behind it that a carry would turn into 0x00
+    uint32_t *buf;
     uint32_t pos, cap, acc;
 };
 
 __device__ __forceinline__ void rac_emit(Rac &c, uint32_t b)
 {
-    c.acc |= b << (8u * (c.pos & 3u));
+    c.acc = __funnelshift_r(c.acc, b, 8);                 // (acc >> 8) | (b << 24): little-endian word assembly
     c.pos++;
-    if ((c.pos & 3u) == 0u) {
-        if (c.pos <= c.cap) c.buf[(c.pos >> 2) - 1u] = c.acc;
-        c.acc = 0u;
-    }
+    if ((c.pos & 3u) == 0u && c.pos <= c.cap) c.buf[(c.pos >> 2) - 1u] = c.acc;
 }
 
 __device__ __forceinline__ void rac_shift(Rac &c)
 {
-    // one iteration of renorm_encoder's loop (rangecoder.h:52-75); the first branch is the common case
-    if (c.out_byte >= 0 && c.out_count == 0u && c.low <= 0xFF00u) {
-        rac_emit(c, (uint32_t)c.out_byte);
+    if (c.low <= 0xFF00u) {                               // common case: no carry, byte below 0xFF
+        rac_emit(c, c.out_byte);
+        if (c.out_count) { do rac_emit(c, 0xFFu); while (--c.out_count); }
         c.out_byte = c.low >> 8;
-    } else if (c.out_byte < 0) {
-        c.out_byte = c.low >> 8;
-    } else if (c.low <= 0xFF00u) {
-        rac_emit(c, (uint32_t)c.out_byte);
-        for (; c.out_count; c.out_count--) rac_emit(c, 0xFFu);
-        c.out_byte = c.low >> 8;
-    } else if (c.low >= 0x10000u) {
-        rac_emit(c, (uint32_t)(c.out_byte + 1) & 0xFFu);
-        for (; c.out_count; c.out_count--) rac_emit(c, 0x00u);
-        c.out_byte = (c.low >> 8) & 0xFF;
+    } else if (c.low >= 0x10000u) {                       // carry
+        rac_emit(c, (c.out_byte + 1u) & 0xFFu);
+        if (c.out_count) { do rac_emit(c, 0x00u); while (--c.out_count); }
+        c.out_byte = (c.low >> 8) & 0xFFu;
     } else {
         c.out_count++;
     }
@@ -531,13 +527,14 @@ __device__ __forceinline__ void rac_shift(Rac &c)
     c.range <<= 8;
 }
 
-__device__ __forceinline__ void rac_code(Rac &c, uint32_t entry)
+// put_rac (rangecoder.h:85-102) for the decision in bits [SH, SH+9) of `word`; the state update already happened in k_replay
+template <int SH>
+__device__ __forceinline__ void rac_code(Rac &c, uint32_t word)
 {
-    // put_rac (rangecoder.h:85-102); the state update already happened in k_replay
-    const uint32_t p = entry & 0xFFu;
+    const uint32_t p = (word >> SH) & 0xFFu;
     const uint32_t r1 = (c.range * p) >> 8;
     const uint32_t r0 = c.range - r1;
-    if (entry & 0x100u) { c.low += r0; c.range = r1; } else c.range = r0;
+    if (word & (0x100u << SH)) { c.low += r0; c.range = r1; } else c.range = r0;
     if (c.range < 0x100u) rac_shift(c);       // p >= 1 and range >= 0x100 before: at most one shift
 }
 
@@ -564,19 +561,23 @@ __device__ __forceinline__ void rac_code_run(Rac &c, const uint4 *src, uint32_t 
         for (uint32_t w = 0; w < wc; w++) {
             const uint32_t word = v.x;
             v.x = v.y; v.y = v.z; v.z = v.w;
-            rac_code(c, word & 0xFFFFu);
-            if (done + 1u < n) rac_code(c, word >> 16);
+            rac_code<0>(c, word);
+            if (done + 1u < n) rac_code<16>(c, word);
             done += 2u;
         }
     }
 }
 
+// Coders per warp.  The kernel is bound by instruction latency, not by issue slots: every lane that renormalises drags
+// the whole warp through the byte-output path, and a slice offers only one coder.  Using a few lanes per warp gives
+// several times more warps to hide that latency behind (and makes the renormalisation branch rarer per warp).
 constexpr int kRangeThreads = 32;
 
-__global__ void __launch_bounds__(kRangeThreads) k_rangecode(const EncDeviceTables T, const EncBatch B)
+__global__ void __launch_bounds__(kRangeThreads) k_rangecode(const EncDeviceTables T, const EncBatch B, const int lanes)
 {
     const Layout &L = T.layout;
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if ((int)threadIdx.x >= lanes) return;
+    const int idx = blockIdx.x * lanes + threadIdx.x;
     if (idx >= B.nframes * L.nslices) return;
     if (B.status[0]) return;
     const int f = idx / L.nslices, s = idx - f * L.nslices;
@@ -584,9 +585,9 @@ __global__ void __launch_bounds__(kRangeThreads) k_rangecode(const EncDeviceTabl
     const int key = B.frame_key[f] ? 1 : 0;
 
     Rac c;
-    c.low = 0; c.range = 0xFF00u; c.out_byte = -1; c.out_count = 0;       // ff_init_range_encoder
+    c.low = 0; c.range = 0xFF00u; c.out_byte = 0; c.out_count = 0;        // ff_init_range_encoder (+ dummy outstanding byte)
     c.buf = reinterpret_cast<uint32_t *>(B.scratch + (size_t)f * L.scratch_per_frame + g.scratch_off);
-    c.pos = 0; c.cap = g.scratch_cap; c.acc = 0;
+    c.pos = kScratchLead - 1; c.cap = g.scratch_cap; c.acc = 0;
 
     const uint16_t *dec_frame = B.dec + (size_t)f * L.dec_per_frame;
     const uint32_t *run_cnt = B.run_cnt + (size_t)f * L.runs_per_frame + g.run_first;
@@ -621,16 +622,23 @@ __global__ void __launch_bounds__(kRangeThreads) k_rangecode(const EncDeviceTabl
         if (t == 0) c.low += 0xFFu;
         while (c.range < 0x100u) rac_shift(c);
     }
-    if ((c.pos & 3u) && c.pos <= c.cap) c.buf[c.pos >> 2] = c.acc;
+    if ((c.pos & 3u) && c.pos + 4u <= c.cap) c.buf[c.pos >> 2] = c.acc >> (8u * (4u - (c.pos & 3u)));
 
-    B.slice_bytes[idx] = c.pos;
-    if (c.pos > c.cap) atomicMax(&B.status[1], (unsigned long long)c.pos);
+    B.slice_bytes[idx] = c.pos - kScratchLead;
+    if (c.pos + 4u > c.cap) atomicMax(&B.status[1], (unsigned long long)c.pos + 4ull);
 }
 
 void launch_rangecode(const EncDeviceTables &t, const EncBatch &b, cudaStream_t s)
 {
     const int n = b.nframes * t.layout.nslices;
-    k_rangecode<<<(n + kRangeThreads - 1) / kRangeThreads, kRangeThreads, 0, s>>>(t, b);
+    static int forced = -1;
+    if (forced < 0) { const char *v = getenv("FFV1B200_RANGE_LANES"); forced = v ? atoi(v) : 0; if (forced < 0 || forced > 32) forced = 0; }
+    int lanes = forced;
+    if (!lanes) {                                  // aim at ~12 warps per SM
+        lanes = 2;
+        while (lanes < 32 && n / lanes > 148 * 12) lanes *= 2;
+    }
+    k_rangecode<<<(n + lanes - 1) / lanes, kRangeThreads, 0, s>>>(t, b, lanes);
 }
 
 // =================================================================================================
@@ -718,13 +726,13 @@ __global__ void __launch_bounds__(32) k_golomb(const EncDeviceTables T, const En
     const int bits = L.coded_bits;
     for (int f = f0; f < f1; f++) {
         const int key = B.frame_key[f] ? 1 : 0;
-        uint8_t *out = B.scratch + (size_t)f * L.scratch_per_frame + g.scratch_off;
+        uint8_t *out = B.scratch + (size_t)f * L.scratch_per_frame + g.scratch_off + kScratchLead;
         const int npre = T.gprefix_len[s * 2 + key];
         const uint8_t *pre = T.gprefix + (size_t)(s * 2 + key) * kMaxGolombPrefix;
         for (int i = lane; i < npre; i += 32) out[i] = pre[i];
         if (lane == 0) {
             BitW w;
-            w.buf = out; w.pos = (uint32_t)npre; w.cap = g.scratch_cap; w.acc = 0; w.nbits = 0;
+            w.buf = out; w.pos = (uint32_t)npre; w.cap = g.scratch_cap - kScratchLead; w.acc = 0; w.nbits = 0;
             const uint32_t *rec_slice = B.rec + (size_t)f * L.rec_per_frame + g.rec_first;
             int run_index = 0;
             for (int li = 0; li < g.nlines; li++) {
@@ -845,7 +853,7 @@ __global__ void __launch_bounds__(kPackThreads) k_pack_slices(const EncDeviceTab
     unsigned long long off = B.pkt_off[f];
     for (int k = 0; k < s; k++) off += B.slice_bytes[f * ns + k] + ((T.version > 2 || k > 0) ? 3 : 0) + (T.ec ? 5 : 0);
     const uint32_t nb = B.slice_bytes[f * ns + s];
-    const uint8_t *src = B.scratch + (size_t)f * L.scratch_per_frame + T.slices[s].scratch_off;
+    const uint8_t *src = B.scratch + (size_t)f * L.scratch_per_frame + T.slices[s].scratch_off + kScratchLead;
     uint8_t *dst = B.out + off;
     __syncthreads();
 

@@ -12,6 +12,7 @@ constexpr int kPixelPadL      = 8;            // int16 elements left of x=0 in a
 constexpr int kPixelRowElems  = kPixelChunk + 16;
 constexpr int kReplayWarps    = 2;            // chains (warps) per CTA of the state-replay kernel
  constexpr int kMaxGolombPrefix = 4096;        // bytes (a version 0/1 keyframe carries the whole header)
+constexpr int kScratchLead    = 4;            // bytes of a slice's scratch region before its payload (see struct Rac)
 constexpr int kMaxPrefix      = 8192;         // decisions before the first sample (v0/v1 keyframes carry a whole header)
 
 // per-batch device buffers and scalars handed to the kernels
@@ -32,6 +33,14 @@ struct EncBatch {
     uint64_t *pkt_off;                  // [nframes+1]
     uint8_t *out;                       // packets, back to back
     uint64_t out_capacity;
+    // per-context replay (ffv1_ctx_replay.cu)
+    const int32_t *frame_seg;           // [nframes] GOP segment of every frame
+    uint32_t *line_pos;                 // [nframes][lines_per_frame] decisions per line, then first decision of the line
+    uint32_t *ctx_hist;                 // [nframes][ctiles_per_frame][ctx_count]
+    uint32_t *list_start;               // [chains][ctx_count] first entry of a context's list inside the chain's area
+    uint32_t *list_count;               // [chains][ctx_count]
+    uint16_t *list_order;               // [chains][ctx_count] contexts, longest list first
+    uint2 *lists;                       // [nframes * samples_per_frame] {decision position, residual | frame << 16}
     // adaptive state
     uint8_t *state_seg;                 // global-state mode: [nseg][nslices][npc][ctx_count*32]
     const uint8_t *carry_in;            // [nslices][npc][ctx_count*32]
@@ -47,6 +56,7 @@ struct EncDeviceTables {
     const LineDesc *lines;
     const int32_t *pc_lines;
     const TileDesc *tiles;
+    const CtxTile *ctiles;
     const int16_t *quant;               // [5][256]
     const uint8_t *trans_lut;           // [512]: zero_state, one_state of the slice coders
     const uint8_t *one_pow;             // [33][256]: one_state applied k times (runs of zero residuals in one context)
@@ -68,6 +78,10 @@ void launch_rangecode(const EncDeviceTables &t, const EncBatch &b, cudaStream_t 
 void launch_golomb(const EncDeviceTables &t, const EncBatch &b, cudaStream_t s);
 void launch_pack(const EncDeviceTables &t, const EncBatch &b, cudaStream_t s);
 cudaError_t configure_kernels(const Layout &L);
+// context-decomposed state replay (ffv1_ctx_replay.cu)
+bool ctx_replay_supported(const Layout &L);
+cudaError_t configure_ctx_replay(const Layout &L);
+void launch_ctx_replay(const EncDeviceTables &t, const EncBatch &b, cudaStream_t s);
 // tuned per-pixel pass for planar sources (ffv1_pixel_fast.cu)
 bool pixel_fast_geometry_ok(const Layout &L, const SliceGeom *slices, int nslices);
 cudaError_t configure_pixel_fast(const Layout &L);

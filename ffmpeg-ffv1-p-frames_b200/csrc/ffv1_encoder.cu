@@ -35,6 +35,12 @@ struct FFV1B200Encoder {
     DevBuf<uint32_t> d_rec, d_run_cnt, d_slice_bytes, d_pkt_size;
     DevBuf<uint64_t> d_pkt_off;
     DevBuf<uint8_t> d_one_pow, d_run_pc;
+    DevBuf<CtxTile> d_ctiles;
+    DevBuf<int32_t> d_frame_seg; PinnedBuf<int32_t> h_frame_seg;
+    DevBuf<uint32_t> d_line_pos, d_ctx_hist, d_list_start, d_list_count;
+    DevBuf<uint16_t> d_list_order;
+    DevBuf<uint2> d_lists;
+    bool ctx_replay = false;          // context-decomposed replay (small context model) instead of one warp per chain
     DevBuf<uint16_t> d_dec;
     DevBuf<int32_t> d_seg_first; DevBuf<uint8_t> d_frame_key;
     PinnedBuf<int32_t> h_seg_first; PinnedBuf<uint8_t> h_frame_key;
@@ -123,7 +129,18 @@ int alloc_batch_buffers(FFV1B200Encoder *e)
         CU_TRY(e->d_carry[k].alloc(state_bytes));
         CU_TRY(cudaMemsetAsync(e->d_carry[k].p, 128, state_bytes, e->stream));
     }
-    if (!e->state_in_smem || L.golomb) {
+    const size_t nseg_max = (F + (e->cfg.gop_size > 0 ? e->cfg.gop_size : 1) - 1) / (e->cfg.gop_size > 0 ? e->cfg.gop_size : 1) + 1;
+    if (e->ctx_replay) {
+        const size_t nchains = nseg_max * L.nslices * L.npc;
+        CU_TRY(e->d_frame_seg.alloc(F)); CU_TRY(e->h_frame_seg.alloc(F));
+        CU_TRY(e->d_line_pos.alloc((size_t)L.lines_per_frame * F));
+        CU_TRY(e->d_ctx_hist.alloc((size_t)L.ctiles_per_frame * L.ctx_count * F));
+        CU_TRY(e->d_list_start.alloc(nchains * L.ctx_count));
+        CU_TRY(e->d_list_count.alloc(nchains * L.ctx_count));
+        CU_TRY(e->d_list_order.alloc(nchains * L.ctx_count));
+        CU_TRY(e->d_lists.alloc((size_t)L.samples_per_frame * F));
+    }
+    if ((!e->state_in_smem && !e->ctx_replay) || L.golomb) {
         const int g = e->cfg.gop_size > 0 ? e->cfg.gop_size : 1;
         CU_TRY(e->d_state_seg.alloc(state_bytes * ((F + g - 1) / g + 1)));               // one state set per GOP segment of a batch
     }
@@ -135,6 +152,7 @@ EncDeviceTables device_tables(FFV1B200Encoder *e)
     EncDeviceTables t;
     t.layout = e->tab.layout;
     t.slices = e->d_slices.p; t.lines = e->d_lines.p; t.pc_lines = e->d_pc_lines.p; t.tiles = e->d_tiles.p;
+    t.ctiles = e->d_ctiles.p;
     t.quant = e->d_quant.p; t.trans_lut = e->d_lut.p; t.one_pow = e->d_one_pow.p; t.run_pc = e->d_run_pc.p; t.gprefix = e->d_gprefix.p; t.gprefix_len = e->d_gprefix_len.p; t.prefix = e->d_prefix.p; t.prefix_len = e->d_prefix_len.p;
     t.ec = e->cfg.ec; t.version = e->cfg.version; t.state_in_smem = e->state_in_smem ? 1 : 0;
     return t;
@@ -153,12 +171,14 @@ int run_pipeline(FFV1B200Encoder *e, int nframes, const int linesizes[4], uint8_
         const bool key = e->cfg.gop_size == 0 || (pn % e->cfg.gop_size) == 0;
         e->h_frame_key.p[f] = key ? 1 : 0;
         if (f == 0 || key) e->h_seg_first.p[nseg++] = f;
+        if (e->ctx_replay) e->h_frame_seg.p[f] = nseg - 1;
     }
     e->h_seg_first.p[nseg] = nframes;
 
     for (int attempt = 0; attempt < 6; attempt++) {
         CU_TRY(cudaMemcpyAsync(e->d_seg_first.p, e->h_seg_first.p, sizeof(int32_t) * (nseg + 1), cudaMemcpyHostToDevice, s));
         CU_TRY(cudaMemcpyAsync(e->d_frame_key.p, e->h_frame_key.p, nframes, cudaMemcpyHostToDevice, s));
+        if (e->ctx_replay) CU_TRY(cudaMemcpyAsync(e->d_frame_seg.p, e->h_frame_seg.p, sizeof(int32_t) * nframes, cudaMemcpyHostToDevice, s));
         CU_TRY(cudaMemsetAsync(e->d_status.p, 0, sizeof(unsigned long long) * 8, s));
 
         EncDeviceTables t = device_tables(e);
@@ -174,6 +194,8 @@ int run_pipeline(FFV1B200Encoder *e, int nframes, const int linesizes[4], uint8_
         b.state_seg = e->d_state_seg.p;
         b.carry_in = e->d_carry[e->carry_idx].p; b.carry_out = e->d_carry[e->carry_idx ^ 1].p;
         b.status = e->d_status.p;
+        b.frame_seg = e->d_frame_seg.p; b.line_pos = e->d_line_pos.p; b.ctx_hist = e->d_ctx_hist.p;
+        b.list_start = e->d_list_start.p; b.list_count = e->d_list_count.p; b.list_order = e->d_list_order.p; b.lists = e->d_lists.p;
 
         bool fast = e->fast_pixel;
         for (int i = 0; i < 4 && fast; i++) fast = (linesizes[i] & 15) == 0;
@@ -182,13 +204,14 @@ int run_pipeline(FFV1B200Encoder *e, int nframes, const int linesizes[4], uint8_
         if (fast) launch_pixel_fast(t, b, e->max_plane_width, e->num_sms, s);
         else      launch_pixel(t, b, s);
         cudaEventRecord(e->ev[1], s);
-        if (!L.golomb) launch_replay(t, b, s);
+        if (e->ctx_replay) launch_ctx_replay(t, b, s);
+        else if (!L.golomb) launch_replay(t, b, s);
         cudaEventRecord(e->ev[2], s);
         if (!L.golomb) launch_rangecode(t, b, s); else launch_golomb(t, b, s);
         cudaEventRecord(e->ev[3], s);
         launch_pack(t, b, s);
         cudaEventRecord(e->ev[4], s);
-        e->stats.kernel_launches += L.golomb ? 4 : 5;
+        e->stats.kernel_launches += L.golomb ? 4 : (e->ctx_replay ? 9 : 5);
         CU_TRY(cudaGetLastError());
         CU_TRY(cudaMemcpyAsync(e->h_status.p, e->d_status.p, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost, s));
         CU_TRY(cudaMemcpyAsync(e->h_pkt_size.p, e->d_pkt_size.p, sizeof(uint32_t) * nframes, cudaMemcpyDeviceToHost, s));
@@ -287,6 +310,10 @@ int ffv1b200_enc_open(FFV1B200Encoder **out, const FFV1B200EncParams *p)
     e->fast_pixel = pixel_fast_geometry_ok(L, e->tab.slices.data(), (int)e->tab.slices.size());
     if (const char *v = getenv("FFV1B200_PIXEL")) { if (!strcmp(v, "generic")) e->fast_pixel = false; }
     if (e->fast_pixel) CU_TRY(configure_pixel_fast(L));
+    e->ctx_replay = ctx_replay_supported(L);
+    if (const char *v = getenv("FFV1B200_REPLAY")) { if (!strcmp(v, "warp")) e->ctx_replay = false; }
+    if (e->ctx_replay) CU_TRY(configure_ctx_replay(L));
+    CU_TRY(e->d_ctiles.upload(e->tab.ctiles.data(), e->tab.ctiles.size(), e->stream));
     for (auto &g : e->tab.slices) for (int p = 0; p < L.nplanes; p++) e->max_plane_width = std::max(e->max_plane_width, g.pw[p]);
     CU_TRY(cudaDeviceGetAttribute(&e->num_sms, cudaDevAttrMultiProcessorCount, e->device));
 

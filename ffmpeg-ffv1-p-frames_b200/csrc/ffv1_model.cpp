@@ -613,7 +613,8 @@ void build_tables(const Config &c, Tables &t)
     L.nslices = c.slice_count();
 
     t.slices.assign(L.nslices, SliceGeom());
-    t.lines.clear(); t.pc_lines.clear(); t.tiles.clear(); t.run_pc.clear();
+    t.lines.clear(); t.pc_lines.clear(); t.tiles.clear(); t.run_pc.clear(); t.ctiles.clear();
+    uint32_t list_cursor = 0;
     uint32_t rec_cursor = 0, scratch_cursor = 0;
     for (int si = 0; si < L.nslices; si++) {
         SliceGeom &g = t.slices[si];
@@ -677,6 +678,16 @@ void build_tables(const Config &c, Tables &t)
                 if (t.lines[g.line_first + li].pc == pc) { t.pc_lines.push_back(li); ns += t.lines[g.line_first + li].w; }
             g.pc_nlines[pc] = (int32_t)t.pc_lines.size() - g.pc_line_first[pc];
             g.pc_samples[pc] = ns;
+            g.ct_first[pc] = (int32_t)t.ctiles.size();
+            for (int l0 = 0; l0 < g.pc_nlines[pc]; l0 += kCtxTileLines) {
+                CtxTile ct;
+                ct.slice = (uint16_t)si; ct.pc = (uint8_t)pc; ct.first = (uint32_t)l0;
+                ct.nlines = (uint8_t)std::min(kCtxTileLines, g.pc_nlines[pc] - l0);
+                t.ctiles.push_back(ct);
+            }
+            g.ct_count[pc] = (int32_t)t.ctiles.size() - g.ct_first[pc];
+            g.list_off[pc] = list_cursor;
+            list_cursor += ns;
         }
         // coder output scratch: raw size of the slice + 12.5 % + slack; grown on demand (overflow is detected)
         const uint64_t raw = (uint64_t)nsamp * (L.coded_bits > 8 ? 2 : 1);
@@ -689,6 +700,8 @@ void build_tables(const Config &c, Tables &t)
     L.rec_per_frame = rec_cursor;
     L.scratch_per_frame = scratch_cursor;
     L.runs_per_frame = (int32_t)t.run_pc.size();
+    L.ctiles_per_frame = (int32_t)t.ctiles.size();
+    L.samples_per_frame = list_cursor;
     layout_decisions(t, 5.0);
 }
 

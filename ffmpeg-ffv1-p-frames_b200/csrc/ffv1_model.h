@@ -47,6 +47,9 @@ struct SliceGeom {
     int32_t nruns;                   // runs = maximal groups of consecutive lines (coding order) of one plane context
     uint32_t dec_off[3];             // per plane-context: first entry of its decision region inside a frame's dec area
     uint32_t dec_cap[3];             // capacity of that region in entries (multiple of 8)
+    int32_t ct_first[3];             // per plane-context: first context tile (see CtxTile) in the per-frame table
+    int32_t ct_count[3];
+    uint32_t list_off[3];            // samples of all (slice, plane context) pairs that precede this one in a frame
 };
 
 // one line of samples in coding order
@@ -70,6 +73,15 @@ struct TileDesc {
     int32_t  line_step;  // distance between consecutive rows of the same plane in the line table
 };
 
+// unit of work of the per-context list builder: up to kCtxTileLines consecutive lines of one (slice, plane context)
+struct CtxTile {
+    uint16_t slice;
+    uint8_t  pc;
+    uint8_t  nlines;
+    uint32_t first;      // index of its first line in the (slice, plane context) line list
+};
+constexpr int kCtxTileLines = 16;
+
 struct Layout {
     int32_t width, height;
     int32_t src_kind;        // SrcKind
@@ -88,6 +100,8 @@ struct Layout {
     uint32_t rec_per_frame;  // records per frame incl. padding
     uint32_t scratch_per_frame;
     int32_t runs_per_frame;
+    int32_t ctiles_per_frame;
+    uint32_t samples_per_frame;  // coded samples (no padding)
     uint32_t dec_per_frame;  // decision entries per frame (all regions; set by layout_decisions)
     int32_t rct_offset;      // 1 << bits for RGB
     PlaneInfo plane[4];
@@ -155,6 +169,7 @@ struct Tables {
     std::vector<int32_t>   pc_lines;    // per slice, per plane context: slice-relative line indices
     std::vector<TileDesc>  tiles;
     std::vector<uint8_t>   run_pc;      // per frame: plane context of every run, slices back to back
+    std::vector<CtxTile>   ctiles;
 };
 constexpr int kTileRows = 16;
 void build_tables(const Config &c, Tables &t);
