@@ -12,16 +12,16 @@
 //                  longest-first processing order
 //   k_dec_layout   per (frame, slice, plane context): where every line's decisions start in the decision region
 //   k_ctx_scatter  stable scatter of (decision position, residual) into the per-context lists (coding order kept)
-//   k_replay_ctx   one thread per (chain, context) list, longest lists first: put_symbol_inline's binarisation
-//                  (ffv1enc.c:185-231) on a 32-byte state held in shared memory; writes p | bit<<8 at the recorded
-//                  positions of the decision stream that k_rangecode consumes
+//   k_replay_ctx   one warp per (chain, context) list, longest lists first, lane = state slot: put_symbol_inline's
+//                  binarisation (ffv1enc.c:185-231) with the context's 32-byte state in registers; writes p | bit<<8
+//                  at the recorded positions of the decision stream that k_rangecode consumes
 #include "ffv1_enc_kernels.cuh"
 
 namespace ffv1 {
 
 constexpr int kHistThreads = 256;
 constexpr int kScatterThreads = 32 * kCtxTileLines;
-constexpr int kCtxThreads = 128;
+constexpr int kCtxThreads = 256;
 constexpr int kMaxListCtx = 1024;
 
 __device__ __forceinline__ uint32_t cr_incl_scan(uint32_t v, int lane)
@@ -230,20 +230,51 @@ __global__ void __launch_bounds__(kScatterThreads) k_ctx_scatter(const EncDevice
 }
 
 // ------------------------------------------------------------------------------------------------ k_replay_ctx
-constexpr int kCtxStateStride = kCtxThreads + 4;
+// Lane <-> state slot permutation.  put_symbol_inline visits the slots of a symbol in the order
+//   0 | 1..e+1 | 22+e-1 .. 22 | 11+e                                  (ffv1enc.c:202-229, e <= 9)
+// With slots 22..31 held in REVERSE order by lanes 11..20 and slots 11..21 by lanes 21..31, that order is increasing
+// in lane index for every e, so a lane's decision sits at popc(visit & lanes_below) inside the symbol.
+__device__ __forceinline__ int slot_of_lane(int lane) { return lane <= 10 ? lane : (lane <= 20 ? 42 - lane : lane - 10); }
+__device__ __forceinline__ int lane_of_slot(int slot) { return slot <= 10 ? slot : (slot >= 22 ? 42 - slot : slot + 10); }
 
-// Every thread walks per-context lists (longest first, taken from a shared counter); the 32 lanes of a warp advance in
-// lock step, one symbol of each lane's current list per iteration, so the loads of all decisions of 32 symbols are in
-// flight together: slots visited by one symbol are distinct for e <= 9, hence phase 1 loads every probability, phase 2
-// looks every successor up, phase 3 stores states and emits the decisions.
-template <int MAXE>
+__device__ __forceinline__ void symbol_masks(int d, uint32_t &visit, uint32_t &bits)
+{
+    if (d == 0) { visit = 1u; bits = 1u; return; }                         // "is zero" flag = 1
+    const uint32_t a = (uint32_t)abs(d);
+    const int e = min(31 - __clz(a), 9);                                   // e > 9 symbols take the sequential path
+    const uint32_t ones_e = (1u << e) - 1u;
+    const uint32_t mant = e ? (__brev(a & ones_e) >> (32 - e)) : 0u;       // lane 21-e+t <- bit e-1-t of |d|
+    visit = 1u | (((2u << e) - 1u) << 1) | (ones_e << (21 - e)) | (1u << (21 + e));
+    bits = (ones_e << 1) | (mant << (21 - e)) | ((d < 0 ? 1u : 0u) << (21 + e));
+}
+
+// One warp per context list, lane = state slot: the 32-byte state of the context lives in one register per lane, a
+// symbol costs a handful of instructions (its visit / bit masks are computed 32 symbols at a time and broadcast), and
+// the only serial dependency is state -> table lookup -> state of the slots a symbol touches.  The warps of a CTA
+// (one CTA per chain) take the chain's lists from a shared counter, longest first.
+__device__ __forceinline__ uint32_t lut_ld(uint32_t saddr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+
+__device__ __forceinline__ void visit_step(uint16_t *addr, uint32_t val, uint32_t &st, uint32_t saddr, uint32_t pred)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %4, 0;\n\t@p st.global.u16 [%1], %2;\n\t@p ld.shared.u8 %0, [%3];\n\t}"
+                 : "+r"(st) : "l"(addr), "h"((unsigned short)val), "r"(saddr), "r"(pred) : "memory");
+}
+
+template <bool HIGH_E>
 __global__ void __launch_bounds__(kCtxThreads) k_replay_ctx(const EncDeviceTables T, const EncBatch B)
 {
-    __shared__ uint8_t s_state[32 * kCtxStateStride];
     __shared__ uint8_t s_lut[512];
+    __shared__ uint4 s_blk_all[kCtxThreads];
     __shared__ int s_next;
     const Layout &L = T.layout;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
+    uint4 *s_blk = s_blk_all + (tid & ~31);
+    const uint32_t lut_base = (uint32_t)__cvta_generic_to_shared(s_lut);
     for (int i = tid; i < 512; i += kCtxThreads) s_lut[i] = T.trans_lut[i];
     if (tid == 0) s_next = 0;
     if (B.status[0]) return;
@@ -255,12 +286,13 @@ __global__ void __launch_bounds__(kCtxThreads) k_replay_ctx(const EncDeviceTable
     const bool key = B.frame_key[f0] != 0;
     const bool hand_over = f1 == B.nframes;
     const size_t coff = ((size_t)s * L.npc + pc) * ((size_t)nctx * 32);
-    const uint4 *cin = reinterpret_cast<const uint4 *>(B.carry_in + coff);
-    uint4 *cout = reinterpret_cast<uint4 *>(B.carry_out + coff);
     // contexts without symbols in this batch still hand their state to the next one
-    if (hand_over)
+    if (hand_over) {
+        const uint4 *cin4 = reinterpret_cast<const uint4 *>(B.carry_in + coff);
+        uint4 *cout4 = reinterpret_cast<uint4 *>(B.carry_out + coff);
         for (int i = tid; i < nctx * 2; i += kCtxThreads)
-            cout[i] = key ? make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u) : cin[i];
+            cout4[i] = key ? make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u) : cin4[i];
+    }
     __syncthreads();
 
     const uint2 *chain_list = B.lists + (size_t)f0 * L.samples_per_frame + (size_t)(f1 - f0) * g.list_off[pc];
@@ -268,125 +300,80 @@ __global__ void __launch_bounds__(kCtxThreads) k_replay_ctx(const EncDeviceTable
     const uint32_t *lcount = B.list_count + (size_t)chain * nctx;
     const uint16_t *order = B.list_order + (size_t)chain * nctx;
     uint16_t *dec_pc = B.dec + g.dec_off[pc];
-    uint8_t *S = s_state + tid;
-    constexpr int ST = kCtxStateStride;
+    const int slot = slot_of_lane(lane);
+    const uint32_t lanebit = 1u << lane, lt_mask = lanebit - 1u;
 
-    uint32_t n = 0, j = 0;
-    int c = -1;
-    bool done = false;
-    const uint2 *lp = chain_list;
-    uint2 nx = make_uint2(0u, 0u);
     for (;;) {
-        if (!done && j == n) {
-            if (c >= 0 && hand_over) {                          // the finished context's state goes to the next batch
-                uint32_t w[8];
-#pragma unroll
-                for (int k = 0; k < 8; k++)
-                    w[k] = (uint32_t)S[(4 * k) * ST] | ((uint32_t)S[(4 * k + 1) * ST] << 8) |
-                           ((uint32_t)S[(4 * k + 2) * ST] << 16) | ((uint32_t)S[(4 * k + 3) * ST] << 24);
-                cout[c * 2] = make_uint4(w[0], w[1], w[2], w[3]);
-                cout[c * 2 + 1] = make_uint4(w[4], w[5], w[6], w[7]);
-            }
-            const int oi = atomicAdd(&s_next, 1);
-            c = oi < nctx ? (int)order[oi] : -1;
-            n = c >= 0 ? lcount[c] : 0u;
-            if (n == 0u) { done = true; c = -1; }               // lists are ordered longest first
-            else {
-                if (key) {
-#pragma unroll
-                    for (int k = 0; k < 32; k++) S[k * ST] = 128;
-                } else {
-                    const uint4 a = cin[c * 2], b = cin[c * 2 + 1];
-                    const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-                    for (int k = 0; k < 32; k++) S[k * ST] = (uint8_t)(w[k >> 2] >> (8 * (k & 3)));
+        int oi = 0;
+        if (lane == 0) oi = atomicAdd(&s_next, 1);
+        oi = __shfl_sync(0xFFFFFFFFu, oi, 0);
+        if (oi >= nctx) break;
+        const int c = order[oi];
+        const uint32_t n = lcount[c];
+        if (n == 0u) break;                                     // lists are ordered longest first
+        uint32_t st = key ? 128u : (uint32_t)B.carry_in[coff + (size_t)c * 32 + slot];
+        const uint2 *lp = chain_list + lstart[c];
+        uint2 nx = lane < n ? lp[lane] : make_uint2(0u, 0u);
+        for (uint32_t j0 = 0; j0 < n; j0 += 32u) {
+            const uint32_t m = min(32u, n - j0);
+            const uint2 en = nx;
+            if (j0 + 32u + lane < n) nx = lp[j0 + 32u + lane];
+            const int d = (int)(int16_t)(en.y & 0xFFFFu);
+            uint32_t vis, bts;
+            symbol_masks(d, vis, bts);
+            if (HIGH_E && (uint32_t)abs(d) >= 1024u) vis = 0u;  // marks a symbol for the sequential path
+            // decision positions relative to the block's first symbol (a list never jumps more than one frame inside a block)
+            const unsigned long long off = (unsigned long long)(en.y >> 16) * L.dec_per_frame + en.x;
+            const unsigned long long off0 = __shfl_sync(0xFFFFFFFFu, off, 0);
+            const uint32_t rel = (uint32_t)(off - off0);
+            const bool wide = __any_sync(0xFFFFFFFFu, lane < m && ((off - off0) >> 32) != 0ull);   // rare context, huge GOP
+            uint16_t *o0 = dec_pc + off0;
+            // the block's (visit, bits, position) triples go through shared memory: one broadcast 16-byte load per symbol
+            __syncwarp();
+            s_blk[lane] = make_uint4(vis, bts, rel, 0u);
+            __syncwarp();
+            if (!wide && !(HIGH_E && __any_sync(0xFFFFFFFFu, lane < m && vis == 0u))) {
+#pragma unroll 4
+                for (uint32_t k = 0; k < m; k++) {
+                    const uint4 q = s_blk[k];
+                    const uint32_t idx = q.z + __popc(q.x & lt_mask);
+                    const uint32_t bit = (q.y & lanebit) ? 0x100u : 0u;
+                    // predicated (not branched): emit the decision and step the state only in the lanes the symbol visits
+                    visit_step(o0 + idx, st | bit, st, lut_base + bit + st, q.x & lanebit);
                 }
-                lp = chain_list + lstart[c];
-                j = 0;
-                nx = lp[0];
+            } else {
+                for (uint32_t k = 0; k < m; k++) {
+                    const uint4 q = s_blk[k];
+                    uint16_t *ok = wide ? dec_pc + __shfl_sync(0xFFFFFFFFu, off, k) : o0 + q.z;
+                    if (HIGH_E && q.x == 0u) {
+                        // large magnitudes (ffv1enc.c:217-228): slots 1+9 and 22+9 repeat, walk the decisions one by one
+                        const int dk = __shfl_sync(0xFFFFFFFFu, d, k);
+                        const uint32_t a = (uint32_t)abs(dk);
+                        const int ex = 31 - __clz(a);
+                        const int nd = 2 * ex + 3;
+                        for (int qi = 0; qi < nd; qi++) {
+                            int sl; uint32_t bit;
+                            if (qi == 0) { sl = 0; bit = 0u; }
+                            else if (qi <= ex) { sl = 1 + min(qi - 1, 9); bit = 0x100u; }
+                            else if (qi == ex + 1) { sl = 1 + 9; bit = 0u; }
+                            else if (qi <= 2 * ex + 1) { const int i = ex - 1 - (qi - ex - 2); sl = 22 + min(i, 9); bit = ((a >> i) & 1u) << 8; }
+                            else { sl = 11 + 10; bit = dk < 0 ? 0x100u : 0u; }
+                            if (slot == sl) {
+                                ok[qi] = (uint16_t)(st | bit);
+                                st = lut_ld(lut_base + bit + st);
+                            }
+                        }
+                        continue;
+                    }
+                    if (q.x & lanebit) {
+                        const uint32_t bit = (q.y & lanebit) ? 0x100u : 0u;
+                        ok[__popc(q.x & lt_mask)] = (uint16_t)(st | bit);
+                        st = lut_ld(lut_base + bit + st);
+                    }
+                }
             }
         }
-        if (__all_sync(0xFFFFFFFFu, done)) break;
-        const bool act = !done;
-        const uint2 en = nx;
-        if (act && j + 1u < n) nx = lp[j + 1u];
-        j += act ? 1u : 0u;
-
-        const int d = act ? (int)(int16_t)(en.y & 0xFFFFu) : 0;
-        const uint32_t a = (uint32_t)abs(d);
-        const int ex = 31 - __clz(a | 1u);
-        const bool slow = act && d != 0 && ex > MAXE;           // only deeper-than-10-bit content can get here
-        const bool nz = act && d != 0 && !slow;
-        const int el = nz ? ex : -1;
-        const int emax = __reduce_max_sync(0xFFFFFFFFu, el);
-        uint16_t *o = dec_pc + (size_t)(en.y >> 16) * L.dec_per_frame + en.x;
-        const uint32_t sign = d < 0 ? 0x100u : 0u;
-
-        uint32_t p0 = 0, ps = 0, pu[MAXE + 1], pm[MAXE];
-        if (act) p0 = S[0];
-        if (emax >= 0) {
-#pragma unroll
-            for (int i = 0; i <= MAXE; i++) {
-                if (i > emax) break;
-                pu[i] = (i <= el) ? S[(1 + i) * ST] : 0u;
-            }
-#pragma unroll
-            for (int i = 0; i < MAXE; i++) {
-                if (i >= emax) break;
-                pm[i] = (i < el) ? S[(22 + i) * ST] : 0u;
-            }
-            if (nz) ps = S[(11 + ex) * ST];
-        }
-        uint32_t n0 = 0, ns = 0, nu[MAXE + 1], nm[MAXE];
-        const uint32_t bit0 = d == 0 ? 0x100u : 0u;             // "is zero" flag
-        if (act) n0 = s_lut[bit0 + p0];
-        if (emax >= 0) {
-#pragma unroll
-            for (int i = 0; i <= MAXE; i++) {
-                if (i > emax) break;
-                nu[i] = (i <= el) ? s_lut[(i < el ? 0x100u : 0u) + pu[i]] : 0u;
-            }
-#pragma unroll
-            for (int i = 0; i < MAXE; i++) {
-                if (i >= emax) break;
-                nm[i] = (i < el) ? s_lut[(((a >> i) & 1u) << 8) + pm[i]] : 0u;
-            }
-            if (nz) ns = s_lut[sign + ps];
-        }
-        if (act) { S[0] = (uint8_t)n0; o[0] = (uint16_t)(p0 | bit0); }
-        if (emax >= 0) {
-#pragma unroll
-            for (int i = 0; i <= MAXE; i++) {
-                if (i > emax) break;
-                if (i <= el) { S[(1 + i) * ST] = (uint8_t)nu[i]; o[1 + i] = (uint16_t)(pu[i] | (i < el ? 0x100u : 0u)); }
-            }
-#pragma unroll
-            for (int i = 0; i < MAXE; i++) {
-                if (i >= emax) break;
-                if (i < el) { S[(22 + i) * ST] = (uint8_t)nm[i]; o[2 * ex + 1 - i] = (uint16_t)(pm[i] | (((a >> i) & 1u) << 8)); }
-            }
-            if (nz) { S[(11 + ex) * ST] = (uint8_t)ns; o[2 * ex + 2] = (uint16_t)(ps | sign); }
-        }
-        if (slow) {
-            // large magnitudes (ffv1enc.c:217-228): slots 1+9 and 22+9 repeat, the decisions are walked one by one
-            int k = 1;
-            for (int i = 0; i <= ex; i++, k++) {
-                uint8_t *q = S + (1 + min(i, 9)) * ST;
-                const uint32_t p = *q, bit = i < ex ? 0x100u : 0u;
-                o[k] = (uint16_t)(p | bit);
-                *q = s_lut[bit + p];
-            }
-            for (int i = ex - 1; i >= 0; i--, k++) {
-                uint8_t *q = S + (22 + min(i, 9)) * ST;
-                const uint32_t p = *q, bit = ((a >> i) & 1u) << 8;
-                o[k] = (uint16_t)(p | bit);
-                *q = s_lut[bit + p];
-            }
-            uint8_t *q = S + (11 + min(ex, 10)) * ST;
-            const uint32_t p = *q;
-            o[k] = (uint16_t)(p | sign);
-            *q = s_lut[sign + p];
-        }
+        if (hand_over) B.carry_out[coff + (size_t)c * 32 + slot] = (uint8_t)st;
     }
 }
 
@@ -412,8 +399,8 @@ void launch_ctx_replay(const EncDeviceTables &t, const EncBatch &b, cudaStream_t
     const int n = b.nframes * L.nslices * L.npc;
     k_dec_layout<<<(n + 127) / 128, 128, 0, s>>>(t, b);
     k_ctx_scatter<<<tiles, kScatterThreads, ctx_scatter_smem_bytes(L), s>>>(t, b);
-    if (L.coded_bits <= 8) k_replay_ctx<7><<<nchains, kCtxThreads, 0, s>>>(t, b);
-    else                   k_replay_ctx<9><<<nchains, kCtxThreads, 0, s>>>(t, b);
+    if (L.coded_bits <= 10) k_replay_ctx<false><<<nchains, kCtxThreads, 0, s>>>(t, b);
+    else                    k_replay_ctx<true><<<nchains, kCtxThreads, 0, s>>>(t, b);
 }
 
 } // namespace ffv1
