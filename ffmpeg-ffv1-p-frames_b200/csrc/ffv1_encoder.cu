@@ -1,5 +1,14 @@
 // ffv1_encoder.cu -- C-ABI encoder entry points (include/ffv1_b200.h) and batch orchestration.
 // Replaces encode_init / encode_frame / encode_close of the reference (ffv1enc.c:669-1029, 1222-1373, 1375-1379).
+//
+// A batch goes through three engines that run concurrently for consecutive batches:
+//   copy-in stream : host frames -> device (merged into as few, as large copies as the host layout allows)
+//   compute stream : per-pixel pass -> state replay -> range coder / Golomb coder -> packet assembly
+//   copy-out stream: packets -> host
+// Two "slots" hold what must be private to a batch in flight (input frames, packets, small control arrays); the large
+// intermediates (records, decisions, context lists, coder scratch) are shared because the compute stream is serial.
+// ffv1b200_enc_submit_host / ffv1b200_enc_collect expose the pipeline (AV_CODEC_CAP_DELAY semantics: packets of batch
+// k come back while batch k+1 is being coded); ffv1b200_enc_encode_host is submit + collect.
 #include "../../include/ffv1_b200.h"
 #include "ffv1_model.h"
 #include "ffv1_enc_kernels.cuh"
@@ -14,47 +23,57 @@
 
 using namespace ffv1;
 
+namespace {
+constexpr int kSlots = 2;
+constexpr int kCarry = 4;       // ring of model-state buffers: batch k reads [k % 4] and writes [(k+1) % 4]
+
+struct Slot {
+    DevBuf<uint8_t> d_in, d_out;
+    DevBuf<const uint8_t *> d_planes; PinnedBuf<const uint8_t *> h_planes;
+    DevBuf<int32_t> d_seg_first, d_frame_seg; PinnedBuf<int32_t> h_seg_first, h_frame_seg;
+    DevBuf<uint8_t> d_frame_key; PinnedBuf<uint8_t> h_frame_key;
+    DevBuf<unsigned long long> d_status; PinnedBuf<unsigned long long> h_status;
+    DevBuf<uint32_t> d_pkt_size; PinnedBuf<uint32_t> h_pkt_size;
+    DevBuf<uint64_t> d_pkt_off; PinnedBuf<uint64_t> h_pkt_off;
+    cudaEvent_t ev_h2d = nullptr, ev_small = nullptr, ev[6] = {nullptr};
+    int nframes = 0, nseg = 0, carry_in = 0;
+    int64_t first_pn = 0;
+    int ls[4] = {0, 0, 0, 0};
+    bool busy = false, fast = false;
+    uint8_t *out = nullptr;          // where the packets are assembled (own d_out, or the caller's device buffer)
+    size_t out_cap = 0;
+    int64_t h2d_bytes = 0;
+};
+} // namespace
+
 struct FFV1B200Encoder {
     Config cfg;
     Tables tab;
     std::vector<uint8_t> extradata;
     int device = 0, max_batch = 64;
-    int64_t picture_number = 0;
+    int64_t picture_number = 0;      // of the next frame to be SUBMITTED
     FFV1B200FrameProps props{0, 1, 3};
     bool prefix_dirty = true;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev[8] = {nullptr};
+    cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
 
     // static device tables
     DevBuf<SliceGeom> d_slices; DevBuf<LineDesc> d_lines; DevBuf<int32_t> d_pc_lines; DevBuf<TileDesc> d_tiles;
-    DevBuf<int16_t> d_quant; DevBuf<uint8_t> d_lut; DevBuf<uint16_t> d_prefix; DevBuf<int32_t> d_prefix_len;
-    DevBuf<uint8_t> d_gprefix; DevBuf<int32_t> d_gprefix_len;
-    // batch buffers
-    DevBuf<uint8_t> d_in; size_t in_plane_off[4] = {0,0,0,0}; int in_pitch[4] = {0,0,0,0}; size_t in_frame_stride = 0;
-    DevBuf<const uint8_t *> d_planes; PinnedBuf<const uint8_t *> h_planes;
-    DevBuf<uint32_t> d_rec, d_run_cnt, d_slice_bytes, d_pkt_size;
-    DevBuf<uint64_t> d_pkt_off;
-    DevBuf<uint8_t> d_one_pow, d_run_pc;
     DevBuf<CtxTile> d_ctiles;
-    DevBuf<int32_t> d_frame_seg; PinnedBuf<int32_t> h_frame_seg;
-    DevBuf<uint32_t> d_line_pos, d_ctx_hist, d_list_start, d_list_count;
-    DevBuf<uint16_t> d_list_order;
+    DevBuf<int16_t> d_quant; DevBuf<uint8_t> d_lut, d_one_pow, d_run_pc; DevBuf<uint16_t> d_prefix; DevBuf<int32_t> d_prefix_len;
+    DevBuf<uint8_t> d_gprefix; DevBuf<int32_t> d_gprefix_len;
+    // shared intermediates
+    DevBuf<uint32_t> d_rec, d_run_cnt, d_slice_bytes, d_line_pos, d_ctx_hist, d_list_start, d_list_count;
+    DevBuf<uint16_t> d_dec, d_list_order;
     DevBuf<uint2> d_lists;
-    bool ctx_replay = false;          // context-decomposed replay (small context model) instead of one warp per chain
-    DevBuf<uint16_t> d_dec;
-    DevBuf<int32_t> d_seg_first; DevBuf<uint8_t> d_frame_key;
-    PinnedBuf<int32_t> h_seg_first; PinnedBuf<uint8_t> h_frame_key;
-    DevBuf<uint8_t> d_scratch, d_out, d_state_seg, d_carry[2];
-    int carry_idx = 0;
-    DevBuf<unsigned long long> d_status; PinnedBuf<unsigned long long> h_status;
-    PinnedBuf<uint32_t> h_pkt_size; PinnedBuf<uint64_t> h_pkt_off;
-    double dec_per_sample = 5.0;      // sizing of the decision stream (entries per sample), grows on demand
-    double scratch_scale = 1.0;
-    bool state_in_smem = true;
-    bool fast_pixel = false;          // geometry allows the TMA-staged per-pixel kernel (pointer alignment is checked per call)
+    DevBuf<uint8_t> d_scratch, d_state_seg, d_carry[kCarry];
+    Slot slot[kSlots];
+    uint64_t submitted = 0, collected = 0;      // batch counters; slot of batch k = k % kSlots
+    int carry_next = 0;                          // ring index holding the state after the last submitted batch
+    double dec_per_sample = 5.0;
+    bool state_in_smem = true, fast_pixel = false, ctx_replay = false;
     int max_plane_width = 0, num_sms = 148;
     FFV1B200EncStats stats{};
-    int last_nframes = 0;
+    int last_slot = 0;
 };
 
 namespace {
@@ -66,73 +85,61 @@ int fail(int code, const std::string &msg) { set_last_error(msg); return code; }
 int upload_prefixes(FFV1B200Encoder *e)
 {
     const int ns = e->cfg.slice_count();
+    cudaStream_t s = e->s_comp;
     if (e->tab.layout.golomb) {
         std::vector<uint8_t> gp((size_t)ns * 2 * kMaxGolombPrefix, 0);
         std::vector<int32_t> gl((size_t)ns * 2, 0);
-        for (int s = 0; s < ns; s++)
+        for (int sl = 0; sl < ns; sl++)
             for (int key = 0; key < 2; key++) {
-                std::vector<uint8_t> b = slice_prefix_bytes(e->cfg, s, key != 0, e->props.sar_num, e->props.sar_den, e->props.picture_structure);
+                std::vector<uint8_t> b = slice_prefix_bytes(e->cfg, sl, key != 0, e->props.sar_num, e->props.sar_den, e->props.picture_structure);
                 if ((int)b.size() > kMaxGolombPrefix) return fail(FFV1B200_ERR_EINVAL, "slice header too long");
-                std::copy(b.begin(), b.end(), gp.begin() + (size_t)(s * 2 + key) * kMaxGolombPrefix);
-                gl[s * 2 + key] = (int32_t)b.size();
+                std::copy(b.begin(), b.end(), gp.begin() + (size_t)(sl * 2 + key) * kMaxGolombPrefix);
+                gl[sl * 2 + key] = (int32_t)b.size();
             }
-        CU_TRY(e->d_gprefix.upload(gp.data(), gp.size(), e->stream));
-        CU_TRY(e->d_gprefix_len.upload(gl.data(), gl.size(), e->stream));
-        CU_TRY(cudaStreamSynchronize(e->stream));
+        CU_TRY(cudaStreamSynchronize(s));                 // earlier batches may still read the old tables
+        CU_TRY(e->d_gprefix.upload(gp.data(), gp.size(), s));
+        CU_TRY(e->d_gprefix_len.upload(gl.data(), gl.size(), s));
+        CU_TRY(cudaStreamSynchronize(s));
         e->prefix_dirty = false;
         return 0;
     }
     std::vector<uint16_t> pre((size_t)(ns * 2 + 1) * kMaxPrefix, 0);
     pre[(size_t)ns * 2 * kMaxPrefix] = 129;                              // the decision that closes every slice (state 129, bit 0)
     std::vector<int32_t> len((size_t)ns * 2, 0);
-    for (int s = 0; s < ns; s++)
+    for (int sl = 0; sl < ns; sl++)
         for (int key = 0; key < 2; key++) {
-            std::vector<uint16_t> d = slice_prefix_decisions(e->cfg, s, key != 0, e->props.sar_num, e->props.sar_den, e->props.picture_structure);
+            std::vector<uint16_t> d = slice_prefix_decisions(e->cfg, sl, key != 0, e->props.sar_num, e->props.sar_den, e->props.picture_structure);
             if ((int)d.size() > kMaxPrefix) return fail(FFV1B200_ERR_EINVAL, "slice header too long");
-            std::copy(d.begin(), d.end(), pre.begin() + (size_t)(s * 2 + key) * kMaxPrefix);
-            len[s * 2 + key] = (int32_t)d.size();
+            std::copy(d.begin(), d.end(), pre.begin() + (size_t)(sl * 2 + key) * kMaxPrefix);
+            len[sl * 2 + key] = (int32_t)d.size();
         }
-    CU_TRY(e->d_prefix.upload(pre.data(), pre.size(), e->stream));
-    CU_TRY(e->d_prefix_len.upload(len.data(), len.size(), e->stream));
-    CU_TRY(cudaStreamSynchronize(e->stream));
+    CU_TRY(cudaStreamSynchronize(s));
+    CU_TRY(e->d_prefix.upload(pre.data(), pre.size(), s));
+    CU_TRY(e->d_prefix_len.upload(len.data(), len.size(), s));
+    CU_TRY(cudaStreamSynchronize(s));
     e->prefix_dirty = false;
     return 0;
 }
 
-int alloc_batch_buffers(FFV1B200Encoder *e)
+int alloc_buffers(FFV1B200Encoder *e)
 {
     const Layout &L = e->tab.layout;
     const size_t F = (size_t)e->max_batch;
-    // staged input frames: our own pitch (128 B multiples) per plane
-    size_t off = 0;
-    for (int i = 0; i < e->cfg.nb_src_planes; i++) {
-        int rows, rb; e->cfg.plane_dims(i, &rows, &rb);
-        e->in_pitch[i] = (rb + 127) & ~127;
-        e->in_plane_off[i] = off;
-        off += (size_t)e->in_pitch[i] * rows;
-    }
-    e->in_frame_stride = (off + 255) & ~(size_t)255;
-    CU_TRY(e->d_in.alloc(e->in_frame_stride * F));
-    CU_TRY(e->d_planes.alloc(F * 4)); CU_TRY(e->h_planes.alloc(F * 4));
+    cudaStream_t s = e->s_comp;
     CU_TRY(e->d_rec.alloc((size_t)L.rec_per_frame * F));
     CU_TRY(e->d_run_cnt.alloc((size_t)L.runs_per_frame * F));
     CU_TRY(e->d_slice_bytes.alloc((size_t)L.nslices * F));
-    CU_TRY(e->d_pkt_size.alloc(F)); CU_TRY(e->d_pkt_off.alloc(F + 1));
-    CU_TRY(e->h_pkt_size.alloc(F)); CU_TRY(e->h_pkt_off.alloc(F + 1));
-    CU_TRY(e->d_seg_first.alloc(F + 1)); CU_TRY(e->h_seg_first.alloc(F + 1));
-    CU_TRY(e->d_frame_key.alloc(F)); CU_TRY(e->h_frame_key.alloc(F));
-    CU_TRY(e->d_status.alloc(8)); CU_TRY(e->h_status.alloc(8));
     CU_TRY(e->d_scratch.alloc((size_t)L.scratch_per_frame * F));
     if (!L.golomb) CU_TRY(e->d_dec.alloc((size_t)L.dec_per_frame * F + 64));
     const size_t state_bytes = (size_t)L.nslices * L.npc * L.ctx_count * 32;
-    for (int k = 0; k < 2; k++) {
+    for (int k = 0; k < kCarry; k++) {
         CU_TRY(e->d_carry[k].alloc(state_bytes));
-        CU_TRY(cudaMemsetAsync(e->d_carry[k].p, 128, state_bytes, e->stream));
+        CU_TRY(cudaMemsetAsync(e->d_carry[k].p, 128, state_bytes, s));
     }
-    const size_t nseg_max = (F + (e->cfg.gop_size > 0 ? e->cfg.gop_size : 1) - 1) / (e->cfg.gop_size > 0 ? e->cfg.gop_size : 1) + 1;
+    const size_t g = e->cfg.gop_size > 0 ? e->cfg.gop_size : 1;
+    const size_t nseg_max = (F + g - 1) / g + 1;
     if (e->ctx_replay) {
         const size_t nchains = nseg_max * L.nslices * L.npc;
-        CU_TRY(e->d_frame_seg.alloc(F)); CU_TRY(e->h_frame_seg.alloc(F));
         CU_TRY(e->d_line_pos.alloc((size_t)L.lines_per_frame * F));
         CU_TRY(e->d_ctx_hist.alloc((size_t)L.ctiles_per_frame * L.ctx_count * F));
         CU_TRY(e->d_list_start.alloc(nchains * L.ctx_count));
@@ -140,9 +147,18 @@ int alloc_batch_buffers(FFV1B200Encoder *e)
         CU_TRY(e->d_list_order.alloc(nchains * L.ctx_count));
         CU_TRY(e->d_lists.alloc((size_t)L.samples_per_frame * F));
     }
-    if ((!e->state_in_smem && !e->ctx_replay) || L.golomb) {
-        const int g = e->cfg.gop_size > 0 ? e->cfg.gop_size : 1;
-        CU_TRY(e->d_state_seg.alloc(state_bytes * ((F + g - 1) / g + 1)));               // one state set per GOP segment of a batch
+    if ((!e->state_in_smem && !e->ctx_replay) || L.golomb)
+        CU_TRY(e->d_state_seg.alloc(state_bytes * nseg_max));            // one state set per GOP segment of a batch
+    for (Slot &sl : e->slot) {
+        CU_TRY(sl.d_planes.alloc(F * 4)); CU_TRY(sl.h_planes.alloc(F * 4));
+        CU_TRY(sl.d_seg_first.alloc(F + 1)); CU_TRY(sl.h_seg_first.alloc(F + 1));
+        CU_TRY(sl.d_frame_seg.alloc(F)); CU_TRY(sl.h_frame_seg.alloc(F));
+        CU_TRY(sl.d_frame_key.alloc(F)); CU_TRY(sl.h_frame_key.alloc(F));
+        CU_TRY(sl.d_status.alloc(8)); CU_TRY(sl.h_status.alloc(8));
+        CU_TRY(sl.d_pkt_size.alloc(F)); CU_TRY(sl.h_pkt_size.alloc(F));
+        CU_TRY(sl.d_pkt_off.alloc(F + 1)); CU_TRY(sl.h_pkt_off.alloc(F + 1));
+        CU_TRY(cudaEventCreate(&sl.ev_h2d)); CU_TRY(cudaEventCreate(&sl.ev_small));
+        for (auto &ev : sl.ev) CU_TRY(cudaEventCreate(&ev));
     }
     return 0;
 }
@@ -153,129 +169,160 @@ EncDeviceTables device_tables(FFV1B200Encoder *e)
     t.layout = e->tab.layout;
     t.slices = e->d_slices.p; t.lines = e->d_lines.p; t.pc_lines = e->d_pc_lines.p; t.tiles = e->d_tiles.p;
     t.ctiles = e->d_ctiles.p;
-    t.quant = e->d_quant.p; t.trans_lut = e->d_lut.p; t.one_pow = e->d_one_pow.p; t.run_pc = e->d_run_pc.p; t.gprefix = e->d_gprefix.p; t.gprefix_len = e->d_gprefix_len.p; t.prefix = e->d_prefix.p; t.prefix_len = e->d_prefix_len.p;
+    t.quant = e->d_quant.p; t.trans_lut = e->d_lut.p; t.one_pow = e->d_one_pow.p; t.run_pc = e->d_run_pc.p;
+    t.gprefix = e->d_gprefix.p; t.gprefix_len = e->d_gprefix_len.p; t.prefix = e->d_prefix.p; t.prefix_len = e->d_prefix_len.p;
     t.ec = e->cfg.ec; t.version = e->cfg.version; t.state_in_smem = e->state_in_smem ? 1 : 0;
     return t;
 }
 
-// runs the whole device pipeline for frames whose plane pointers are already in d_planes
-int run_pipeline(FFV1B200Encoder *e, int nframes, const int linesizes[4], uint8_t *d_out, size_t d_out_cap, cudaStream_t s)
+// keyframe flags and GOP segments of a batch that starts at picture number pn (keyframe rule: ffv1enc.c:1299)
+void plan_batch(FFV1B200Encoder *e, Slot &sl, int nframes, int64_t pn)
 {
-    const Layout &L = e->tab.layout;
-    if (e->prefix_dirty) { int r = upload_prefixes(e); if (r < 0) return r; }
-
-    // GOP segments of this batch (keyframe rule: ffv1enc.c:1299)
     int nseg = 0;
     for (int f = 0; f < nframes; f++) {
-        const int64_t pn = e->picture_number + f;
-        const bool key = e->cfg.gop_size == 0 || (pn % e->cfg.gop_size) == 0;
-        e->h_frame_key.p[f] = key ? 1 : 0;
-        if (f == 0 || key) e->h_seg_first.p[nseg++] = f;
-        if (e->ctx_replay) e->h_frame_seg.p[f] = nseg - 1;
+        const bool key = e->cfg.gop_size == 0 || ((pn + f) % e->cfg.gop_size) == 0;
+        sl.h_frame_key.p[f] = key ? 1 : 0;
+        if (f == 0 || key) sl.h_seg_first.p[nseg++] = f;
+        sl.h_frame_seg.p[f] = nseg - 1;
     }
-    e->h_seg_first.p[nseg] = nframes;
+    sl.h_seg_first.p[nseg] = nframes;
+    sl.nframes = nframes; sl.nseg = nseg; sl.first_pn = pn;
+}
 
-    for (int attempt = 0; attempt < 6; attempt++) {
-        CU_TRY(cudaMemcpyAsync(e->d_seg_first.p, e->h_seg_first.p, sizeof(int32_t) * (nseg + 1), cudaMemcpyHostToDevice, s));
-        CU_TRY(cudaMemcpyAsync(e->d_frame_key.p, e->h_frame_key.p, nframes, cudaMemcpyHostToDevice, s));
-        if (e->ctx_replay) CU_TRY(cudaMemcpyAsync(e->d_frame_seg.p, e->h_frame_seg.p, sizeof(int32_t) * nframes, cudaMemcpyHostToDevice, s));
-        CU_TRY(cudaMemsetAsync(e->d_status.p, 0, sizeof(unsigned long long) * 8, s));
+// enqueues the whole device pipeline of a slot on stream s (plane pointers already in sl.h_planes)
+int enqueue_kernels(FFV1B200Encoder *e, Slot &sl, cudaStream_t s)
+{
+    const Layout &L = e->tab.layout;
+    const int nframes = sl.nframes;
+    CU_TRY(cudaMemcpyAsync(sl.d_planes.p, sl.h_planes.p, sizeof(void *) * 4 * nframes, cudaMemcpyHostToDevice, s));
+    CU_TRY(cudaMemcpyAsync(sl.d_seg_first.p, sl.h_seg_first.p, sizeof(int32_t) * (sl.nseg + 1), cudaMemcpyHostToDevice, s));
+    CU_TRY(cudaMemcpyAsync(sl.d_frame_key.p, sl.h_frame_key.p, nframes, cudaMemcpyHostToDevice, s));
+    CU_TRY(cudaMemcpyAsync(sl.d_frame_seg.p, sl.h_frame_seg.p, sizeof(int32_t) * nframes, cudaMemcpyHostToDevice, s));
+    CU_TRY(cudaMemsetAsync(sl.d_status.p, 0, sizeof(unsigned long long) * 8, s));
 
-        EncDeviceTables t = device_tables(e);
-        EncBatch b{};
-        b.nframes = nframes; b.nseg = nseg;
-        b.planes = e->d_planes.p;
-        for (int i = 0; i < 4; i++) b.linesize[i] = linesizes[i];
-        b.rec = e->d_rec.p; b.run_cnt = e->d_run_cnt.p; b.dec = e->d_dec.p;
-        b.seg_first = e->d_seg_first.p; b.frame_key = e->d_frame_key.p;
-        b.scratch = e->d_scratch.p; b.slice_bytes = e->d_slice_bytes.p;
-        b.pkt_size = e->d_pkt_size.p; b.pkt_off = e->d_pkt_off.p;
-        b.out = d_out; b.out_capacity = d_out_cap;
-        b.state_seg = e->d_state_seg.p;
-        b.carry_in = e->d_carry[e->carry_idx].p; b.carry_out = e->d_carry[e->carry_idx ^ 1].p;
-        b.status = e->d_status.p;
-        b.frame_seg = e->d_frame_seg.p; b.line_pos = e->d_line_pos.p; b.ctx_hist = e->d_ctx_hist.p;
-        b.list_start = e->d_list_start.p; b.list_count = e->d_list_count.p; b.list_order = e->d_list_order.p; b.lists = e->d_lists.p;
+    EncDeviceTables t = device_tables(e);
+    EncBatch b{};
+    b.nframes = nframes; b.nseg = sl.nseg;
+    b.planes = sl.d_planes.p;
+    for (int i = 0; i < 4; i++) b.linesize[i] = sl.ls[i];
+    b.rec = e->d_rec.p; b.run_cnt = e->d_run_cnt.p; b.dec = e->d_dec.p;
+    b.seg_first = sl.d_seg_first.p; b.frame_key = sl.d_frame_key.p; b.frame_seg = sl.d_frame_seg.p;
+    b.scratch = e->d_scratch.p; b.slice_bytes = e->d_slice_bytes.p;
+    b.pkt_size = sl.d_pkt_size.p; b.pkt_off = sl.d_pkt_off.p;
+    b.out = sl.out; b.out_capacity = sl.out_cap;
+    b.state_seg = e->d_state_seg.p;
+    b.carry_in = e->d_carry[sl.carry_in].p; b.carry_out = e->d_carry[(sl.carry_in + 1) % kCarry].p;
+    b.status = sl.d_status.p;
+    b.line_pos = e->d_line_pos.p; b.ctx_hist = e->d_ctx_hist.p;
+    b.list_start = e->d_list_start.p; b.list_count = e->d_list_count.p; b.list_order = e->d_list_order.p; b.lists = e->d_lists.p;
 
-        bool fast = e->fast_pixel;
-        for (int i = 0; i < 4 && fast; i++) fast = (linesizes[i] & 15) == 0;
-        for (int i = 0; i < nframes * 4 && fast; i++) fast = (reinterpret_cast<uintptr_t>(e->h_planes.p[i]) & 15) == 0;
-        cudaEventRecord(e->ev[0], s);
-        if (fast) launch_pixel_fast(t, b, e->max_plane_width, e->num_sms, s);
-        else      launch_pixel(t, b, s);
-        cudaEventRecord(e->ev[1], s);
-        if (e->ctx_replay) launch_ctx_replay(t, b, s);
-        else if (!L.golomb) launch_replay(t, b, s);
-        cudaEventRecord(e->ev[2], s);
-        if (!L.golomb) launch_rangecode(t, b, s); else launch_golomb(t, b, s);
-        cudaEventRecord(e->ev[3], s);
-        launch_pack(t, b, s);
-        cudaEventRecord(e->ev[4], s);
-        e->stats.kernel_launches += L.golomb ? 4 : (e->ctx_replay ? 9 : 5);
-        CU_TRY(cudaGetLastError());
-        CU_TRY(cudaMemcpyAsync(e->h_status.p, e->d_status.p, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost, s));
-        CU_TRY(cudaMemcpyAsync(e->h_pkt_size.p, e->d_pkt_size.p, sizeof(uint32_t) * nframes, cudaMemcpyDeviceToHost, s));
-        CU_TRY(cudaMemcpyAsync(e->h_pkt_off.p, e->d_pkt_off.p, sizeof(uint64_t) * (nframes + 1), cudaMemcpyDeviceToHost, s));
+    cudaEventRecord(sl.ev[0], s);
+    if (sl.fast) launch_pixel_fast(t, b, e->max_plane_width, e->num_sms, s);
+    else         launch_pixel(t, b, s);
+    cudaEventRecord(sl.ev[1], s);
+    if (e->ctx_replay) launch_ctx_replay(t, b, s);
+    else if (!L.golomb) launch_replay(t, b, s);
+    cudaEventRecord(sl.ev[2], s);
+    if (!L.golomb) launch_rangecode(t, b, s); else launch_golomb(t, b, s);
+    cudaEventRecord(sl.ev[3], s);
+    launch_pack(t, b, s);
+    cudaEventRecord(sl.ev[4], s);
+    e->stats.kernel_launches += L.golomb ? 4 : (e->ctx_replay ? 9 : 5);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(sl.h_status.p, sl.d_status.p, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaMemcpyAsync(sl.h_pkt_size.p, sl.d_pkt_size.p, sizeof(uint32_t) * nframes, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaMemcpyAsync(sl.h_pkt_off.p, sl.d_pkt_off.p, sizeof(uint64_t) * (nframes + 1), cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaEventRecord(sl.ev_small, s));
+    e->stats.d2h_bytes += 64 + 12 * (int64_t)nframes + 8;
+    return 0;
+}
+
+// A scratch area was too small: grow it and run every batch in flight again, oldest first (their inputs and the
+// model state they start from are still intact: the state ring is deeper than the pipeline).
+int recover(FFV1B200Encoder *e, bool own_out, cudaStream_t s)
+{
+    for (int attempt = 0; attempt < 8; attempt++) {
+        CU_TRY(cudaStreamSynchronize(e->s_in));
         CU_TRY(cudaStreamSynchronize(s));
-        e->stats.d2h_bytes += 64 + 12 * (int64_t)nframes + 8;
-
-        const unsigned long long *st = e->h_status.p;
-        if (st[0]) {            // a decision region overflowed: st[0] = needed entries per sample * 256; grow and re-run
-            e->dec_per_sample = std::max(e->dec_per_sample * 1.25, (double)st[0] / 256.0 * 1.1);
-            layout_decisions(e->tab, e->dec_per_sample);
-            e->d_dec.release();
-            CU_TRY(e->d_dec.alloc((size_t)e->tab.layout.dec_per_frame * e->max_batch + 64));
-            CU_TRY(e->d_slices.upload(e->tab.slices.data(), e->tab.slices.size(), s));
-            e->stats.retries++;
-            continue;
-        }
-        if (st[1]) {            // a slice's coder output overflowed its scratch region: rebuild with larger regions
-            double need = 1.0;
-            for (auto &g : e->tab.slices) need = std::max(need, (double)st[1] / (double)g.scratch_cap);
-            e->scratch_scale *= need * 1.25;
-            uint32_t cur = 0;
-            for (auto &g : e->tab.slices) {
-                g.scratch_cap = (uint32_t)((((uint64_t)(g.scratch_cap * need * 1.25)) + 255) & ~255ull);
-                g.scratch_off = cur; cur += g.scratch_cap;
+        bool again = false;
+        for (uint64_t k = e->collected; k < e->submitted && !again; k++) {
+            Slot &sl = e->slot[k % kSlots];
+            const unsigned long long *st = sl.h_status.p;
+            if (st[0]) {            // a decision region overflowed: st[0] = needed entries per sample * 256
+                e->dec_per_sample = std::max(e->dec_per_sample * 1.25, (double)st[0] / 256.0 * 1.1);
+                layout_decisions(e->tab, e->dec_per_sample);
+                e->d_dec.release();
+                CU_TRY(e->d_dec.alloc((size_t)e->tab.layout.dec_per_frame * e->max_batch + 64));
+                CU_TRY(e->d_slices.upload(e->tab.slices.data(), e->tab.slices.size(), s));
+                again = true;
+            } else if (st[1]) {     // a slice's coder output overflowed its scratch region
+                double need = 1.0;
+                for (auto &g : e->tab.slices) need = std::max(need, (double)st[1] / (double)g.scratch_cap);
+                uint32_t cur = 0;
+                for (auto &g : e->tab.slices) {
+                    g.scratch_cap = (uint32_t)((((uint64_t)(g.scratch_cap * need * 1.25)) + 255) & ~255ull);
+                    g.scratch_off = cur; cur += g.scratch_cap;
+                }
+                e->tab.layout.scratch_per_frame = cur;
+                e->d_scratch.release();
+                CU_TRY(e->d_scratch.alloc((size_t)cur * e->max_batch));
+                CU_TRY(e->d_slices.upload(e->tab.slices.data(), e->tab.slices.size(), s));
+                again = true;
+            } else if (st[2]) {     // the packet area was too small
+                if (!own_out) {
+                    set_last_error("output buffer too small: need " + std::to_string(st[2]) + " bytes");
+                    return FFV1B200_ERR_BUFFER_TOO_SMALL;
+                }
+                sl.d_out.release();
+                CU_TRY(sl.d_out.alloc((size_t)st[2] + (size_t)st[2] / 8 + 65536));
+                sl.out = sl.d_out.p; sl.out_cap = sl.d_out.n;
+                again = true;
             }
-            e->tab.layout.scratch_per_frame = cur;
-            e->d_scratch.release();
-            CU_TRY(e->d_scratch.alloc((size_t)cur * e->max_batch));
-            CU_TRY(e->d_slices.upload(e->tab.slices.data(), e->tab.slices.size(), s));
-            e->stats.retries++;
-            continue;
         }
-        if (st[2]) {
-            set_last_error("output buffer too small: need " + std::to_string(st[2]) + " bytes");
-            return FFV1B200_ERR_BUFFER_TOO_SMALL;
+        if (!again) return 0;
+        e->stats.retries++;
+        for (uint64_t k = e->collected; k < e->submitted; k++) {
+            int r = enqueue_kernels(e, e->slot[k % kSlots], s);
+            if (r < 0) return r;
         }
-        float ms;
-        cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]); e->stats.ms_pixel_kernel += ms;
-        cudaEventElapsedTime(&ms, e->ev[1], e->ev[2]); e->stats.ms_model_kernel += ms;
-        cudaEventElapsedTime(&ms, e->ev[2], e->ev[3]); e->stats.ms_coder_kernel += ms;
-        cudaEventElapsedTime(&ms, e->ev[3], e->ev[4]); e->stats.ms_pack_kernel += ms;
-        e->stats.decisions += (int64_t)st[3];
-        return 0;
+        for (uint64_t k = e->collected; k < e->submitted; k++) CU_TRY(cudaEventSynchronize(e->slot[k % kSlots].ev_small));
     }
     return fail(FFV1B200_ERR_EXTERNAL, "scratch buffers kept overflowing");
 }
 
-void finish_batch(FFV1B200Encoder *e, int nframes, FFV1B200Packet *pkts)
+void account(FFV1B200Encoder *e, Slot &sl)
 {
-    for (int f = 0; f < nframes; f++) {
-        pkts[f].offset = (int64_t)e->h_pkt_off.p[f];
-        pkts[f].size = (int32_t)e->h_pkt_size.p[f];
-        pkts[f].flags = e->h_frame_key.p[f] ? FFV1B200_PKT_FLAG_KEY : 0;
-        pkts[f].picture_number = e->picture_number + f;
-    }
-    e->stats.frames += nframes;
-    e->stats.packet_bytes += (int64_t)e->h_pkt_off.p[nframes];
+    float ms;
+    cudaEventElapsedTime(&ms, sl.ev[0], sl.ev[1]); e->stats.ms_pixel_kernel += ms;
+    cudaEventElapsedTime(&ms, sl.ev[1], sl.ev[2]); e->stats.ms_model_kernel += ms;
+    cudaEventElapsedTime(&ms, sl.ev[2], sl.ev[3]); e->stats.ms_coder_kernel += ms;
+    cudaEventElapsedTime(&ms, sl.ev[3], sl.ev[4]); e->stats.ms_pack_kernel += ms;
+    cudaEventElapsedTime(&ms, sl.ev[0], sl.ev[4]); e->stats.ms_total += ms;
+    e->stats.decisions += (int64_t)sl.h_status.p[3];
+    e->stats.frames += sl.nframes;
+    e->stats.packet_bytes += (int64_t)sl.h_pkt_off.p[sl.nframes];
     uint64_t samples = 0;
     for (auto &g : e->tab.slices) samples += g.nsamples;
-    e->stats.samples += (int64_t)samples * nframes;
-    e->picture_number += nframes;
-    e->carry_idx ^= 1;
-    e->last_nframes = nframes;
+    e->stats.samples += (int64_t)samples * sl.nframes;
+    e->stats.h2d_bytes += sl.h2d_bytes;
+}
+
+void fill_packets(const Slot &sl, FFV1B200Packet *pkts)
+{
+    for (int f = 0; f < sl.nframes; f++) {
+        pkts[f].offset = (int64_t)sl.h_pkt_off.p[f];
+        pkts[f].size = (int32_t)sl.h_pkt_size.p[f];
+        pkts[f].flags = sl.h_frame_key.p[f] ? FFV1B200_PKT_FLAG_KEY : 0;
+        pkts[f].picture_number = sl.first_pn + f;
+    }
+}
+
+bool pixel_fast_ok(const FFV1B200Encoder *e, const Slot &sl)
+{
+    bool fast = e->fast_pixel;
+    for (int i = 0; i < 4 && fast; i++) fast = (sl.ls[i] & 15) == 0;
+    for (int i = 0; i < sl.nframes * 4 && fast; i++) fast = (reinterpret_cast<uintptr_t>(sl.h_planes.p[i]) & 15) == 0;
+    return fast;
 }
 
 } // namespace
@@ -296,10 +343,12 @@ int ffv1b200_enc_open(FFV1B200Encoder **out, const FFV1B200EncParams *p)
     if (p->device < 0 || p->device >= ndev) return fail(FFV1B200_ERR_EINVAL, "no such CUDA device");
     e->device = p->device;
     e->max_batch = p->max_batch_frames > 0 ? p->max_batch_frames : 64;
+    if (e->max_batch > 65535) return fail(FFV1B200_ERR_EINVAL, "max_batch_frames must be below 65536");
     e->picture_number = p->first_picture_number;
     CU_TRY(cudaSetDevice(e->device));
-    CU_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
-    for (auto &ev : e->ev) CU_TRY(cudaEventCreate(&ev));
+    CU_TRY(cudaStreamCreateWithFlags(&e->s_in, cudaStreamNonBlocking));
+    CU_TRY(cudaStreamCreateWithFlags(&e->s_comp, cudaStreamNonBlocking));
+    CU_TRY(cudaStreamCreateWithFlags(&e->s_out, cudaStreamNonBlocking));
 
     e->extradata = write_extradata(e->cfg);
     build_tables(e->cfg, e->tab);
@@ -313,29 +362,30 @@ int ffv1b200_enc_open(FFV1B200Encoder **out, const FFV1B200EncParams *p)
     e->ctx_replay = ctx_replay_supported(L);
     if (const char *v = getenv("FFV1B200_REPLAY")) { if (!strcmp(v, "warp")) e->ctx_replay = false; }
     if (e->ctx_replay) CU_TRY(configure_ctx_replay(L));
-    CU_TRY(e->d_ctiles.upload(e->tab.ctiles.data(), e->tab.ctiles.size(), e->stream));
-    for (auto &g : e->tab.slices) for (int p = 0; p < L.nplanes; p++) e->max_plane_width = std::max(e->max_plane_width, g.pw[p]);
+    for (auto &g : e->tab.slices) for (int pl = 0; pl < L.nplanes; pl++) e->max_plane_width = std::max(e->max_plane_width, g.pw[pl]);
     CU_TRY(cudaDeviceGetAttribute(&e->num_sms, cudaDevAttrMultiProcessorCount, e->device));
 
-    CU_TRY(e->d_slices.upload(e->tab.slices.data(), e->tab.slices.size(), e->stream));
-    CU_TRY(e->d_lines.upload(e->tab.lines.data(), e->tab.lines.size(), e->stream));
-    CU_TRY(e->d_pc_lines.upload(e->tab.pc_lines.data(), e->tab.pc_lines.size(), e->stream));
-    CU_TRY(e->d_tiles.upload(e->tab.tiles.data(), e->tab.tiles.size(), e->stream));
-    CU_TRY(e->d_quant.upload(&e->cfg.quant_tables[e->cfg.context_model][0][0], 5 * 256, e->stream));
+    cudaStream_t s = e->s_comp;
+    CU_TRY(e->d_slices.upload(e->tab.slices.data(), e->tab.slices.size(), s));
+    CU_TRY(e->d_lines.upload(e->tab.lines.data(), e->tab.lines.size(), s));
+    CU_TRY(e->d_pc_lines.upload(e->tab.pc_lines.data(), e->tab.pc_lines.size(), s));
+    CU_TRY(e->d_tiles.upload(e->tab.tiles.data(), e->tab.tiles.size(), s));
+    CU_TRY(e->d_ctiles.upload(e->tab.ctiles.data(), e->tab.ctiles.size(), s));
+    CU_TRY(e->d_quant.upload(&e->cfg.quant_tables[e->cfg.context_model][0][0], 5 * 256, s));
     uint8_t lut[512];
     coder_state_tables(e->cfg, lut, lut + 256);
-    CU_TRY(e->d_lut.upload(lut, 512, e->stream));
+    CU_TRY(e->d_lut.upload(lut, 512, s));
     std::vector<uint8_t> one_pow(33 * 256);                      // one_state applied k times (k_replay's zero-run shortcut)
-    for (int p = 0; p < 256; p++) one_pow[p] = (uint8_t)p;
+    for (int q = 0; q < 256; q++) one_pow[q] = (uint8_t)q;
     for (int k = 1; k <= 32; k++)
-        for (int p = 0; p < 256; p++) one_pow[k * 256 + p] = lut[256 + one_pow[(k - 1) * 256 + p]];
-    CU_TRY(e->d_one_pow.upload(one_pow.data(), one_pow.size(), e->stream));
-    CU_TRY(e->d_run_pc.upload(e->tab.run_pc.data(), e->tab.run_pc.size(), e->stream));
+        for (int q = 0; q < 256; q++) one_pow[k * 256 + q] = lut[256 + one_pow[(k - 1) * 256 + q]];
+    CU_TRY(e->d_one_pow.upload(one_pow.data(), one_pow.size(), s));
+    CU_TRY(e->d_run_pc.upload(e->tab.run_pc.data(), e->tab.run_pc.size(), s));
     CU_TRY(e->d_prefix.alloc((size_t)(L.nslices * 2 + 1) * kMaxPrefix));
     CU_TRY(e->d_prefix_len.alloc((size_t)L.nslices * 2));
-    r = alloc_batch_buffers(e.get());
+    r = alloc_buffers(e.get());
     if (r < 0) return r;
-    CU_TRY(cudaStreamSynchronize(e->stream));
+    CU_TRY(cudaStreamSynchronize(s));
     *out = e.release();
     return 0;
 }
@@ -344,8 +394,12 @@ void ffv1b200_enc_close(FFV1B200Encoder *e)
 {
     if (!e) return;
     cudaSetDevice(e->device);
-    if (e->stream) { cudaStreamSynchronize(e->stream); cudaStreamDestroy(e->stream); }
-    for (auto &ev : e->ev) if (ev) cudaEventDestroy(ev);
+    for (cudaStream_t s : {e->s_in, e->s_comp, e->s_out}) if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
+    for (Slot &sl : e->slot) {
+        if (sl.ev_h2d) cudaEventDestroy(sl.ev_h2d);
+        if (sl.ev_small) cudaEventDestroy(sl.ev_small);
+        for (auto &ev : sl.ev) if (ev) cudaEventDestroy(ev);
+    }
     delete e;
 }
 
@@ -382,47 +436,137 @@ void ffv1b200_enc_set_frame_props(FFV1B200Encoder *e, const FFV1B200FrameProps *
     }
 }
 
-int ffv1b200_enc_encode_host(FFV1B200Encoder *e, int nframes, const uint8_t *const *planes, const int *linesizes,
-                             uint8_t *out, size_t out_cap, FFV1B200Packet *pkts, size_t *needed)
+int ffv1b200_enc_submit_host(FFV1B200Encoder *e, int nframes, const uint8_t *const *planes, const int *linesizes)
 {
-    if (!e || !planes || !linesizes || !out || !pkts) return fail(FFV1B200_ERR_EINVAL, "null argument");
+    if (!e || !planes || !linesizes) return fail(FFV1B200_ERR_EINVAL, "null argument");
     if (nframes < 1 || nframes > e->max_batch) return fail(FFV1B200_ERR_EINVAL, "nframes outside 1..max_batch_frames");
+    if (e->submitted - e->collected >= (uint64_t)kSlots) return fail(FFV1B200_ERR_EINVAL, "two batches are already in flight: collect one first");
     CU_TRY(cudaSetDevice(e->device));
-    cudaStream_t s = e->stream;
-    cudaEventRecord(e->ev[5], s);
-    // host -> device: every plane of every frame into the staging area (our pitch)
-    int ls[4] = {0, 0, 0, 0};
+    if (e->prefix_dirty) { int r = upload_prefixes(e); if (r < 0) return r; }
+    Slot &sl = e->slot[e->submitted % kSlots];
+    const Config &c = e->cfg;
+    const int np = c.nb_src_planes;
+
+    // ---- device layout of the staged frames: the host layout itself when its linesizes are 16-byte multiples (one
+    //      contiguous copy per run of adjacent planes / frames), else rows are re-pitched to 128 bytes
+    bool direct = true;
+    for (int i = 0; i < np; i++) {
+        if (!planes[i]) return fail(FFV1B200_ERR_EINVAL, "missing plane pointer");
+        int rows, rb; c.plane_dims(i, &rows, &rb);
+        if (linesizes[i] < rb) return fail(FFV1B200_ERR_EINVAL, "linesize smaller than a row");
+        if (linesizes[i] & 15) direct = false;
+    }
+    for (int f = 1; f < nframes && direct; f++)
+        for (int i = 0; i < np; i++) if (linesizes[f * 4 + i] != linesizes[i]) direct = false;
+    size_t plane_off[4] = {0, 0, 0, 0}, off = 0;
+    int pitch[4] = {0, 0, 0, 0};
+    for (int i = 0; i < np; i++) {
+        int rows, rb; c.plane_dims(i, &rows, &rb);
+        pitch[i] = direct ? linesizes[i] : ((rb + 127) & ~127);
+        plane_off[i] = off;
+        off += (size_t)pitch[i] * rows;
+    }
+    const size_t stride = (off + 255) & ~(size_t)255;
+    if (sl.d_in.n < stride * (size_t)e->max_batch) CU_TRY(sl.d_in.alloc(stride * (size_t)e->max_batch));   // the slot is idle
+
+    cudaStream_t s = e->s_in;
+    sl.h2d_bytes = 0;
+    const uint8_t *run_src = nullptr; uint8_t *run_dst = nullptr; size_t run_len = 0;
+    auto flush = [&]() -> cudaError_t {
+        cudaError_t ce = cudaSuccess;
+        if (run_len) ce = cudaMemcpyAsync(run_dst, run_src, run_len, cudaMemcpyHostToDevice, s);
+        sl.h2d_bytes += (int64_t)run_len;
+        run_len = 0;
+        return ce;
+    };
     for (int f = 0; f < nframes; f++)
         for (int i = 0; i < 4; i++) {
             const uint8_t *dptr = nullptr;
-            if (i < e->cfg.nb_src_planes) {
-                int rows, rb; e->cfg.plane_dims(i, &rows, &rb);
-                if (!planes[f * 4 + i]) return fail(FFV1B200_ERR_EINVAL, "missing plane pointer");
-                uint8_t *dst = e->d_in.p + (size_t)f * e->in_frame_stride + e->in_plane_off[i];
-                CU_TRY(cudaMemcpy2DAsync(dst, e->in_pitch[i], planes[f * 4 + i], linesizes[f * 4 + i], rb, rows, cudaMemcpyHostToDevice, s));
-                e->stats.h2d_bytes += (int64_t)rb * rows;
-                dptr = dst; ls[i] = e->in_pitch[i];
+            if (i < np) {
+                const uint8_t *src = planes[f * 4 + i];
+                if (!src) return fail(FFV1B200_ERR_EINVAL, "missing plane pointer");
+                int rows, rb; c.plane_dims(i, &rows, &rb);
+                uint8_t *dst = sl.d_in.p + (size_t)f * stride + plane_off[i];
+                if (direct) {
+                    const size_t bytes = (size_t)pitch[i] * (rows - 1) + rb;      // never read past the last row's samples
+                    const size_t span = (size_t)pitch[i] * rows;
+                    if (run_len && src == run_src + run_len && dst == run_dst + run_len) run_len += bytes;
+                    else { CU_TRY(flush()); run_src = src; run_dst = dst; run_len = bytes; }
+                    // planes that really are adjacent on both sides continue the run across the row padding
+                    const bool more = i + 1 < np ? planes[f * 4 + i + 1] == src + span
+                                                 : (f + 1 < nframes && planes[(f + 1) * 4] == src + span && stride == off);
+                    if (more) run_len = run_len - bytes + span;
+                } else {
+                    CU_TRY(flush());
+                    CU_TRY(cudaMemcpy2DAsync(dst, pitch[i], src, linesizes[f * 4 + i], rb, rows, cudaMemcpyHostToDevice, s));
+                    sl.h2d_bytes += (int64_t)rb * rows;
+                }
+                dptr = dst;
             }
-            e->h_planes.p[f * 4 + i] = dptr;
+            sl.h_planes.p[f * 4 + i] = dptr;
         }
-    CU_TRY(cudaMemcpyAsync(e->d_planes.p, e->h_planes.p, sizeof(void *) * 4 * nframes, cudaMemcpyHostToDevice, s));
-    // packets are assembled in our device buffer, then copied out
-    const size_t want = std::max<size_t>(out_cap, 1 << 20);
-    if (e->d_out.n < want) { e->d_out.release(); CU_TRY(e->d_out.alloc(want)); }
-    int r = run_pipeline(e, nframes, ls, e->d_out.p, std::min(e->d_out.n, out_cap), s);
-    if (r < 0) {
-        if (r == FFV1B200_ERR_BUFFER_TOO_SMALL && needed) *needed = (size_t)e->h_status.p[2];
-        return r;
-    }
-    const size_t total = (size_t)e->h_pkt_off.p[nframes];
-    CU_TRY(cudaMemcpyAsync(out, e->d_out.p, total, cudaMemcpyDeviceToHost, s));
-    cudaEventRecord(e->ev[6], s);
-    CU_TRY(cudaStreamSynchronize(s));
-    e->stats.d2h_bytes += (int64_t)total;
-    float ms; cudaEventElapsedTime(&ms, e->ev[5], e->ev[6]); e->stats.ms_total += ms;
-    if (needed) *needed = total;
-    finish_batch(e, nframes, pkts);
+    CU_TRY(flush());
+    CU_TRY(cudaEventRecord(sl.ev_h2d, s));
+    for (int i = 0; i < 4; i++) sl.ls[i] = pitch[i];
+
+    plan_batch(e, sl, nframes, e->picture_number);
+    sl.carry_in = e->carry_next;
+    sl.fast = pixel_fast_ok(e, sl);
+    if (!sl.d_out.p) CU_TRY(sl.d_out.alloc((size_t)e->max_batch * ((size_t)c.frame_bytes() / 2 + 65536)));
+    sl.out = sl.d_out.p; sl.out_cap = sl.d_out.n;
+    CU_TRY(cudaStreamWaitEvent(e->s_comp, sl.ev_h2d, 0));
+    int r = enqueue_kernels(e, sl, e->s_comp);
+    if (r < 0) return r;
+    sl.busy = true;
+    e->picture_number += nframes;
+    e->carry_next = (e->carry_next + 1) % kCarry;
+    e->submitted++;
     return nframes;
+}
+
+int ffv1b200_enc_collect(FFV1B200Encoder *e, uint8_t *out, size_t out_cap, FFV1B200Packet *pkts, size_t *needed)
+{
+    if (!e || !out || !pkts) return fail(FFV1B200_ERR_EINVAL, "null argument");
+    if (e->collected == e->submitted) return fail(FFV1B200_ERR_EINVAL, "no batch in flight");
+    CU_TRY(cudaSetDevice(e->device));
+    Slot &sl = e->slot[e->collected % kSlots];
+    CU_TRY(cudaEventSynchronize(sl.ev_small));
+    if (sl.h_status.p[0] | sl.h_status.p[1] | sl.h_status.p[2]) {
+        int r = recover(e, true, e->s_comp);
+        if (r < 0) return r;
+    }
+    const size_t total = (size_t)sl.h_pkt_off.p[sl.nframes];
+    if (needed) *needed = total;
+    if (total > out_cap) {
+        set_last_error("output buffer too small: need " + std::to_string(total) + " bytes");
+        return FFV1B200_ERR_BUFFER_TOO_SMALL;                   // the batch stays collectable
+    }
+    CU_TRY(cudaMemcpyAsync(out, sl.out, total, cudaMemcpyDeviceToHost, e->s_out));
+    CU_TRY(cudaStreamSynchronize(e->s_out));
+    e->stats.d2h_bytes += (int64_t)total;
+    account(e, sl);
+    fill_packets(sl, pkts);
+    sl.busy = false;
+    e->last_slot = (int)(e->collected % kSlots);
+    e->collected++;
+    return sl.nframes;
+}
+
+int ffv1b200_enc_pending(const FFV1B200Encoder *e)
+{
+    return e ? (int)(e->submitted - e->collected) : FFV1B200_ERR_EINVAL;
+}
+
+int ffv1b200_enc_encode_host(FFV1B200Encoder *e, int nframes, const uint8_t *const *planes, const int *linesizes,
+                             uint8_t *out, size_t out_cap, FFV1B200Packet *pkts, size_t *needed)
+{
+    if (!e || !out || !pkts) return fail(FFV1B200_ERR_EINVAL, "null argument");
+    // a previous call that failed with BUFFER_TOO_SMALL left its batch in flight: that one is handed out first
+    if (e->submitted == e->collected) {
+        int r = ffv1b200_enc_submit_host(e, nframes, planes, linesizes);
+        if (r < 0) return r;
+    }
+    return ffv1b200_enc_collect(e, out, out_cap, pkts, needed);
 }
 
 int ffv1b200_enc_encode_device(FFV1B200Encoder *e, int nframes, const void *const *d_planes, const int *linesizes,
@@ -430,26 +574,41 @@ int ffv1b200_enc_encode_device(FFV1B200Encoder *e, int nframes, const void *cons
 {
     if (!e || !d_planes || !linesizes || !d_out || !pkts) return fail(FFV1B200_ERR_EINVAL, "null argument");
     if (nframes < 1 || nframes > e->max_batch) return fail(FFV1B200_ERR_EINVAL, "nframes outside 1..max_batch_frames");
+    if (e->submitted != e->collected) return fail(FFV1B200_ERR_EINVAL, "collect the batches in flight first");
     CU_TRY(cudaSetDevice(e->device));
-    cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
-    int ls[4] = {linesizes[0], linesizes[1], linesizes[2], linesizes[3]};
+    if (e->prefix_dirty) { int r = upload_prefixes(e); if (r < 0) return r; }
+    cudaStream_t s = stream ? (cudaStream_t)stream : e->s_comp;
+    Slot &sl = e->slot[e->submitted % kSlots];
+    for (int i = 0; i < 4; i++) sl.ls[i] = linesizes[i];
     for (int f = 0; f < nframes; f++)
         for (int i = 0; i < 4; i++) {
-            if (linesizes[f * 4 + i] != ls[i]) return fail(FFV1B200_ERR_EINVAL, "all frames of a batch must share linesizes");
-            e->h_planes.p[f * 4 + i] = (const uint8_t *)d_planes[f * 4 + i];
+            if (linesizes[f * 4 + i] != sl.ls[i]) return fail(FFV1B200_ERR_EINVAL, "all frames of a batch must share linesizes");
+            sl.h_planes.p[f * 4 + i] = (const uint8_t *)d_planes[f * 4 + i];
         }
-    cudaEventRecord(e->ev[5], s);
-    CU_TRY(cudaMemcpyAsync(e->d_planes.p, e->h_planes.p, sizeof(void *) * 4 * nframes, cudaMemcpyHostToDevice, s));
-    int r = run_pipeline(e, nframes, ls, (uint8_t *)d_out, d_out_cap, s);
-    if (r < 0) {
-        if (r == FFV1B200_ERR_BUFFER_TOO_SMALL && needed) *needed = (size_t)e->h_status.p[2];
-        return r;
+    plan_batch(e, sl, nframes, e->picture_number);
+    sl.carry_in = e->carry_next;
+    sl.fast = pixel_fast_ok(e, sl);
+    sl.out = (uint8_t *)d_out; sl.out_cap = d_out_cap;
+    sl.h2d_bytes = 0;
+    int r = enqueue_kernels(e, sl, s);
+    if (r < 0) return r;
+    e->submitted++;                                             // so that recover() sees the batch
+    CU_TRY(cudaEventSynchronize(sl.ev_small));
+    if (sl.h_status.p[0] | sl.h_status.p[1] | sl.h_status.p[2]) {
+        r = recover(e, false, s);
+        if (r < 0) {
+            e->submitted--;                                     // state unchanged: the call may be repeated
+            if (r == FFV1B200_ERR_BUFFER_TOO_SMALL && needed) *needed = (size_t)sl.h_status.p[2];
+            return r;
+        }
     }
-    cudaEventRecord(e->ev[6], s);
-    CU_TRY(cudaStreamSynchronize(s));
-    float ms; cudaEventElapsedTime(&ms, e->ev[5], e->ev[6]); e->stats.ms_total += ms;
-    if (needed) *needed = (size_t)e->h_pkt_off.p[nframes];
-    finish_batch(e, nframes, pkts);
+    if (needed) *needed = (size_t)sl.h_pkt_off.p[nframes];
+    account(e, sl);
+    fill_packets(sl, pkts);
+    e->last_slot = (int)((e->submitted - 1) % kSlots);
+    e->collected++;
+    e->picture_number += nframes;
+    e->carry_next = (e->carry_next + 1) % kCarry;
     return nframes;
 }
 
@@ -463,7 +622,8 @@ int ffv1b200_enc_stats(const FFV1B200Encoder *e, FFV1B200EncStats *s)
 int64_t ffv1b200_enc_debug_records(FFV1B200Encoder *e, int frame, int slice, uint32_t *dst, int64_t cap)
 {
     if (!e || !dst) return FFV1B200_ERR_EINVAL;
-    if (frame < 0 || frame >= e->last_nframes || slice < 0 || slice >= e->cfg.slice_count()) return fail(FFV1B200_ERR_EINVAL, "bad frame/slice");
+    if (e->submitted != e->collected) return fail(FFV1B200_ERR_EINVAL, "collect the batches in flight first");
+    if (frame < 0 || frame >= e->slot[e->last_slot].nframes || slice < 0 || slice >= e->cfg.slice_count()) return fail(FFV1B200_ERR_EINVAL, "bad frame/slice");
     cudaSetDevice(e->device);
     const Layout &L = e->tab.layout;
     const SliceGeom &g = e->tab.slices[slice];

@@ -75,6 +75,9 @@ def lib():
         L.ffv1b200_enc_set_frame_props.restype = None
         L.ffv1b200_enc_encode_host.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int),
                                                ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(Packet), ctypes.POINTER(ctypes.c_size_t)]
+        L.ffv1b200_enc_submit_host.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int)]
+        L.ffv1b200_enc_collect.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(Packet), ctypes.POINTER(ctypes.c_size_t)]
+        L.ffv1b200_enc_pending.argtypes = [ctypes.c_void_p]
         L.ffv1b200_enc_encode_device.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int),
                                                  ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(Packet), ctypes.POINTER(ctypes.c_size_t),
                                                  ctypes.c_void_p]
@@ -193,6 +196,59 @@ class FFV1Encoder:
             _check(r)
             break
         return [(buf[pk[i].offset:pk[i].offset + pk[i].size].tobytes(), bool(pk[i].flags & 1)) for i in range(n)]
+
+    # -- pipelined form: up to two batches in flight, copies of one overlap the kernels of the other -------------
+    def _plane_table(self, frames):
+        n = len(frames)
+        fb = int(self.info.frame_bytes)
+        planes = (ctypes.c_void_p * (4 * n))()
+        ls = (ctypes.c_int * (4 * n))()
+        keep = []
+        for f, fr in enumerate(frames):
+            a = np.ascontiguousarray(fr).view(np.uint8).reshape(-1)
+            if a.nbytes != fb:
+                raise ValueError("frame %d has %d bytes, expected %d" % (f, a.nbytes, fb))
+            keep.append(a)
+            off = 0
+            for i, (rows, rb) in enumerate(self._shapes):
+                planes[4 * f + i] = a.ctypes.data + off
+                ls[4 * f + i] = rb
+                off += rows * rb
+        return planes, ls, keep
+
+    def prepare(self, frames):
+        """Build the plane-pointer table of a batch once (reusable across submits of the same host buffers)."""
+        planes, ls, keep = self._plane_table(frames)
+        return (planes, ls, keep, len(frames))
+
+    def submit(self, frames):
+        """Queue one batch (<= max_batch frames, or a prepare()d table); the frames must stay alive until collect()."""
+        planes, ls, keep, n = frames if isinstance(frames, tuple) else self.prepare(frames)
+        _check(lib().ffv1b200_enc_submit_host(self._h, n, planes, ls))
+        self._inflight = getattr(self, "_inflight", [])
+        self._inflight.append((keep, n))
+
+    def collect(self, out=None, copy=True):
+        """Wait for the oldest submitted batch. Returns [(bytes, key)] (or the Packet array when copy=False)."""
+        keep, n = self._inflight.pop(0)
+        fb = int(self.info.frame_bytes)
+        cap = n * (fb + fb // 4 + 65536) if out is None else out.nbytes
+        pk = (Packet * n)()
+        needed = ctypes.c_size_t()
+        while True:
+            buf = self._out_buffer(cap) if out is None else out
+            r = lib().ffv1b200_enc_collect(self._h, buf.ctypes.data, cap, pk, ctypes.byref(needed))
+            if r == ERR_BUFFER_TOO_SMALL and out is None:
+                cap = int(needed.value) + 4096
+                continue
+            _check(r)
+            break
+        if not copy:
+            return pk
+        return [(buf[pk[i].offset:pk[i].offset + pk[i].size].tobytes(), bool(pk[i].flags & 1)) for i in range(n)]
+
+    def pending(self):
+        return _check(lib().ffv1b200_enc_pending(self._h))
 
     def encode_device(self, plane_ptrs, linesizes, d_out_ptr, d_out_cap, nframes, stream=None):
         """Frames already in device memory. plane_ptrs/linesizes: flat sequences of 4*nframes ints.

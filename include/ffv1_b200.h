@@ -7,7 +7,8 @@
  *
  *   ffv1b200_enc_open            <- ff_ffv1_encoder.init    = encode_init   libavcodec/ffv1enc.c:669-1029
  *   ffv1b200_enc_extradata       <- avctx->extradata written by write_extradata       ffv1enc.c:545-619
- *   ffv1b200_enc_encode_*        <- ff_ffv1_encoder.encode2 = encode_frame  libavcodec/ffv1enc.c:1222-1373
+ *   ffv1b200_enc_encode_* / _submit_host / _collect
+ *                                <- ff_ffv1_encoder.encode2 = encode_frame  libavcodec/ffv1enc.c:1222-1373
  *                                   (batched: CAP_DELAY lets a codec hold frames, ffv1enc.c:1424)
  *   ffv1b200_enc_close           <- ff_ffv1_encoder.close   = encode_close  libavcodec/ffv1enc.c:1375-1379
  *   ffv1b200_dec_open            <- ff_ffv1_decoder.init    = decode_init   libavcodec/ffv1dec.c:876-893
@@ -125,6 +126,15 @@ void ffv1b200_enc_set_frame_props(FFV1B200Encoder *enc, const FFV1B200FrameProps
 int  ffv1b200_enc_encode_host(FFV1B200Encoder *enc, int nframes,
                               const uint8_t *const *planes, const int *linesizes,
                               uint8_t *out, size_t out_cap, FFV1B200Packet *pkts, size_t *needed);
+
+/* Pipelined form of the same call (the AV_CODEC_CAP_DELAY way of using the codec, ffv1enc.c:1424): submit queues the
+ * host->device copies and all kernels of a batch and returns; collect blocks until the OLDEST submitted batch is done and
+ * copies its packets out.  Up to two batches may be in flight, so the copies of one batch overlap the kernels of the
+ * other.  Frames passed to submit must stay valid until that batch has been collected.
+ * collect returns the batch's frame count; FFV1B200_ERR_BUFFER_TOO_SMALL leaves the batch collectable (*needed = size). */
+int  ffv1b200_enc_submit_host(FFV1B200Encoder *enc, int nframes, const uint8_t *const *planes, const int *linesizes);
+int  ffv1b200_enc_collect(FFV1B200Encoder *enc, uint8_t *out, size_t out_cap, FFV1B200Packet *pkts, size_t *needed);
+int  ffv1b200_enc_pending(const FFV1B200Encoder *enc);      /* batches submitted and not yet collected (0..2) */
 
 /* Same, for frames already resident in DEVICE memory (AV_PIX_FMT_CUDA AVFrames: data[i] are CUdeviceptr,
  * hwcontext_cuda.h:31-40).  Packets are produced in device memory (d_out, d_out_cap bytes); sizes/offsets are

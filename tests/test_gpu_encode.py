@@ -98,3 +98,26 @@ def test_errors_match_reference_behaviour(B):
     with pytest.raises(B.FFV1Error) as e:
         B.FFV1Encoder(352, 288, "yuv420p", level=1, slices=4)
     assert e.value.code == -22
+
+def test_pipelined_submit_collect(B):
+    """two batches in flight (copies of one overlap kernels of the other): same packets as the oracle, GOPs split"""
+    case = [c for c in CASES if c[0] == "c2_gop_range_24sl"][0]
+    cid, w, h, fmt, opts, kind, n = case
+    frames = make_frames(case) * 3                       # 18 frames
+    o = O.Encoder(w, h, fmt, **opts)
+    exp = [o.encode(f) for f in frames]
+    g = B.FFV1Encoder(w, h, fmt, max_batch_frames=5, **gpu_opts(opts))
+    chunks = [frames[i:i + 5] for i in range(0, len(frames), 5)]
+    got = []
+    g.submit(chunks[0])
+    for ch in chunks[1:]:
+        g.submit(ch)
+        assert g.pending() == 2
+        got += g.collect()
+    got += g.collect()
+    assert g.pending() == 0 and len(got) == len(exp)
+    for i in range(len(exp)):
+        assert got[i] == exp[i], "packet %d" % i
+    with pytest.raises(B.FFV1Error):
+        lib_pending = B.lib().ffv1b200_enc_collect(g._h, None, 0, None, None)
+        raise B.FFV1Error(lib_pending, "no batch in flight") if lib_pending < 0 else AssertionError
