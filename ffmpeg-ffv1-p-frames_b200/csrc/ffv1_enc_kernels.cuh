@@ -85,6 +85,7 @@ void launch_ctx_replay(const EncDeviceTables &t, const EncBatch &b, cudaStream_t
 // tuned per-pixel pass for planar sources (ffv1_pixel_fast.cu)
 bool pixel_fast_geometry_ok(const Layout &L, const SliceGeom *slices, int nslices);
 cudaError_t configure_pixel_fast(const Layout &L);
-void launch_pixel_fast(const EncDeviceTables &t, const EncBatch &b, int max_plane_width, int num_sms, cudaStream_t s);
+void launch_pixel_fast(const EncDeviceTables &t, const EncBatch &b, int max_plane_width, int num_sms, cudaStream_t s,
+                       const uint8_t *const *frame0_planes, long long frame_stride);
 
 } // namespace ffv1

@@ -217,7 +217,14 @@ int enqueue_kernels(FFV1B200Encoder *e, Slot &sl, cudaStream_t s)
     b.list_start = e->d_list_start.p; b.list_count = e->d_list_count.p; b.list_order = e->d_list_order.p; b.lists = e->d_lists.p;
 
     cudaEventRecord(sl.ev[0], s);
-    if (sl.fast) launch_pixel_fast(t, b, e->max_plane_width, e->num_sms, s);
+    if (sl.fast) {
+        // tensor-map TMA needs the frames of the batch at a constant distance (true for the staged host path)
+        long long fstride = nframes > 1 ? (long long)(sl.h_planes.p[4] - sl.h_planes.p[0]) : 0;
+        for (int f = 1; f < nframes && fstride >= 0; f++)
+            for (int i = 0; i < e->cfg.nb_src_planes; i++)
+                if ((long long)(sl.h_planes.p[f * 4 + i] - sl.h_planes.p[(f - 1) * 4 + i]) != fstride) { fstride = -1; break; }
+        launch_pixel_fast(t, b, e->max_plane_width, e->num_sms, s, sl.h_planes.p, fstride);
+    }
     else         launch_pixel(t, b, s);
     cudaEventRecord(sl.ev[1], s);
     if (e->ctx_replay) launch_ctx_replay(t, b, s);

@@ -171,7 +171,7 @@ struct Tables {
     std::vector<uint8_t>   run_pc;      // per frame: plane context of every run, slices back to back
     std::vector<CtxTile>   ctiles;
 };
-constexpr int kTileRows = 16;
+constexpr int kTileRows = 32;
 void build_tables(const Config &c, Tables &t);
 // Sizes the per-(slice, plane context) decision regions for `entries_per_sample` binary decisions per coded sample.
 void layout_decisions(Tables &t, double entries_per_sample);

@@ -9,24 +9,35 @@
 //   * the quantisation tables live in shared memory replicated once per lane (entry e of lane l at e*256 + l*4), so the
 //     data-dependent lookups of a warp never collide in a bank; entries are indexed by (difference*256) & 0xFF00,
 //     which is what a byte extraction with PRMT (value << 8) yields for free;
-//   * each thread handles 4 consecutive samples held in registers and writes one 16-byte record vector.
+//   * each thread handles 8 consecutive samples held in registers and writes one 32-byte (256-bit) record vector.
 // Requirements checked on the host (else the generic kernel runs): 8- or 16-bit planar source, every source plane
 // 16-byte aligned with a 16-byte multiple linesize, every slice-plane starting at a multiple of 4 samples.
 #include "ffv1_enc_kernels.cuh"
+#include <cuda.h>
+#include <cudaTypedefs.h>
 #include <algorithm>
+#include <cstring>
+#include <cstdlib>
 
 namespace ffv1 {
 
-constexpr int kFastThreads  = 256;
-constexpr int kFastChunk    = 512;                       // samples of a row per work item
+constexpr int kFastThreads  = 1024;                      // one CTA per SM: two groups of 512 threads share the tables
+constexpr int kFastGroup    = 512;                       // threads working on one item
+constexpr int kFastBufs     = 3;                         // staging buffers per group (TMA runs two items ahead)
+constexpr int kFastChunkBytes = 512;                     // bytes of a row per work item (512 / 256 samples for 8- / 16-bit sources)
 constexpr int kFastRows     = kTileRows + 2;             // two rows above the tile are needed (T, and LT of x=0 / TT)
 constexpr int kFastTabAB    = 256 * 256;                 // [e][A: 32 lanes x (Q1,Q2) | B: 32 lanes x (Q0,Q3)]
 constexpr int kFastTabC     = 256 * 128;                 // [e][32 lanes x (Q4,-)]   (large context model only)
 
 template <int BYTES> struct FastGeom {
-    static constexpr int kRowBytes = 16 + 16 + kFastChunk * BYTES + 16;     // left block | misalignment | chunk | one more sample + padding
-    static constexpr int kBufBytes = kFastRows * kRowBytes;
+    static constexpr int kChunk = kFastChunkBytes / BYTES;
+    static constexpr int kRowBytes = 16 + 16 + kFastChunkBytes + 32;        // left block | misalignment | chunk | next sample + padding (multiple of 64)
+    static constexpr int kBufBytes = (kFastRows + 2) * kRowBytes;           // +2: a slice's first tile lands two rows down
 };
+
+// One tiled tensor map per source plane: {linesize / 4 (32-bit elements), rows, frames}; the box is one staging buffer
+// worth of rows, so a work item is fetched by a single TMA request (SASS UTMALDG) instead of one bulk copy per row.
+struct FastMaps { CUtensorMap m[4]; };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -81,8 +92,8 @@ __device__ __forceinline__ bool fast_decode(const EncDeviceTables &T, long item,
     it.slice = td.slice; it.plane = td.plane; it.y0 = td.y0; it.nrows = td.nrows;
     it.line_first = td.line_first; it.line_step = td.line_step;
     it.w = g.pw[td.plane];
-    it.cx0 = ch * kFastChunk;
-    it.cw = min(kFastChunk, it.w - it.cx0);
+    it.cx0 = ch * FastGeom<BYTES>::kChunk;
+    it.cw = min(FastGeom<BYTES>::kChunk, it.w - it.cx0);
     it.last_chunk = it.cx0 + it.cw >= it.w;
     it.m = ((g.px0[td.plane] + it.cx0) * BYTES) & 15;
     return it.cw > 0;
@@ -107,35 +118,72 @@ __device__ __forceinline__ void fast_issue(const EncDeviceTables &T, const EncBa
         bytes = (uint32_t)(b - a);
         const int ytop = it.y0 - 2;
         nvalid = (uint32_t)(it.nrows + 2 - (ytop < 0 ? -ytop : 0));
-        const int y = ytop + lane;
-        if (lane < it.nrows + 2 && y >= 0) {
-            src = B.planes[it.f * 4 + pi.src_plane] + (size_t)(g.py0[it.plane] + y) * B.linesize[pi.src_plane] + a;
-            dst = buf + lane * FastGeom<BYTES>::kRowBytes + (a - a0);
-        }
+        src = B.planes[it.f * 4 + pi.src_plane] + a;
+        dst = buf + (a - a0);
     }
+    // rows above the slice are zero (ffv1enc.c:376): written here, while the buffer is idle; the release of the
+    // mbarrier arrival below publishes them to the consumers
+    if (valid && it.y0 < 2)
+        for (int rr = 0; rr < 2 - it.y0; rr++)
+            for (int i = lane * 16; i < FastGeom<BYTES>::kRowBytes; i += 32 * 16)
+                *reinterpret_cast<uint4 *>(buf + rr * FastGeom<BYTES>::kRowBytes + i) = make_uint4(0u, 0u, 0u, 0u);
+    __syncwarp();
     if (lane == 0) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_expect_tx(bar, bytes * nvalid);
     }
     __syncwarp();
-    if (src) tma_row(dst, src, bytes, bar);
+    if (valid) {
+        const int ls = B.linesize[T.layout.plane[it.plane].src_plane];
+        const int row0 = T.slices[it.slice].py0[it.plane] + it.y0 - 2;            // plane row staged at buffer row 0
+        for (int rr = lane; rr < it.nrows + 2; rr += 32)
+            if (it.y0 - 2 + rr >= 0) tma_row(dst + rr * FastGeom<BYTES>::kRowBytes, src + (ptrdiff_t)(row0 + rr) * ls, bytes, bar);
+    }
 }
 
-template <int BYTES, int NIN>
-__global__ void __launch_bounds__(kFastThreads, 2)
-k_pixel_fast(const EncDeviceTables T, const EncBatch B, const int maxchunks)
+// warp 0 of a group: one tensor-map TMA request for the whole item
+template <int BYTES>
+__device__ __forceinline__ void fast_issue_tensor(const EncDeviceTables &T, const FastMaps &maps, const FastItem &it, bool valid,
+                                                  unsigned char *buf, uint64_t *bar, int lane)
+{
+    typedef FastGeom<BYTES> G;
+    const bool top = valid && it.y0 == 0;          // first tile of a slice: the two rows above it are zero, not the neighbour slice
+    if (top)
+        for (int i = lane * 16; i < 2 * G::kRowBytes; i += 32 * 16)
+            *reinterpret_cast<uint4 *>(buf + i) = make_uint4(0u, 0u, 0u, 0u);
+    __syncwarp();
+    if (lane == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (!valid) { mbar_expect_tx(bar, 0u); return; }
+        const SliceGeom &g = T.slices[it.slice];
+        const int src_plane = T.layout.plane[it.plane].src_plane;
+        const int gx = (g.px0[it.plane] + it.cx0) * BYTES;            // byte column of the chunk's first sample
+        const int c0 = ((gx & ~15) - 16) >> 2;                          // may be negative: out-of-bounds elements read as zero
+        const int c1 = g.py0[it.plane] + it.y0 - (top ? 0 : 2);
+        mbar_expect_tx(bar, (uint32_t)(kFastRows * G::kRowBytes));
+        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                     :: "r"(smem_u32(buf + (top ? 2 * G::kRowBytes : 0))), "l"(reinterpret_cast<uint64_t>(&maps.m[src_plane])),
+                        "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(it.f) : "memory");
+    }
+}
+
+template <int BYTES, int NIN, bool TENSOR>
+__global__ void __launch_bounds__(kFastThreads, 1)
+k_pixel_fast(const EncDeviceTables T, const EncBatch B, const int maxchunks, const __grid_constant__ FastMaps maps)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
     typedef FastGeom<BYTES> G;
     const Layout &L = T.layout;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x & (kFastGroup - 1), lane = tid & 31, warp = tid >> 5;
+    const int group = threadIdx.x / kFastGroup;
+    constexpr int kGroups = kFastThreads / kFastGroup;
     unsigned char *tabAB = smem;
     unsigned char *tabC = smem + kFastTabAB;
-    unsigned char *bufs = smem + kFastTabAB + (NIN == 5 ? kFastTabC : 0);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(bufs + 2 * G::kBufBytes);
+    unsigned char *bufs = smem + kFastTabAB + (NIN == 5 ? kFastTabC : 0) + group * kFastBufs * G::kBufBytes;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kFastTabAB + (NIN == 5 ? kFastTabC : 0) + kGroups * kFastBufs * G::kBufBytes) + group * kFastBufs;
 
     // ---- lane-replicated quantisation tables
-    for (int i = tid; i < 256 * 32; i += kFastThreads) {
+    for (int i = threadIdx.x; i < 256 * 32; i += kFastThreads) {
         const int e = i >> 5, l = i & 31;
         const uint32_t q0 = (uint16_t)T.quant[e], q1 = (uint16_t)T.quant[256 + e], q2 = (uint16_t)T.quant[512 + e];
         const uint32_t q3 = NIN == 5 ? (uint16_t)T.quant[768 + e] : 0u;
@@ -144,8 +192,7 @@ k_pixel_fast(const EncDeviceTables T, const EncBatch B, const int maxchunks)
         if (NIN == 5) *reinterpret_cast<uint32_t *>(tabC + e * 128 + l * 4) = (uint16_t)T.quant[1024 + e];
     }
     if (tid == 0) {
-        mbar_init(&bars[0], 1);
-        mbar_init(&bars[1], 1);
+        for (int i = 0; i < kFastBufs; i++) mbar_init(&bars[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -154,49 +201,32 @@ k_pixel_fast(const EncDeviceTables T, const EncBatch B, const int maxchunks)
     const long total = (long)items_per_frame * B.nframes;
     const int bits = L.coded_bits;
     const uint32_t lane4 = (uint32_t)lane * 4u;
+    const long step = (long)gridDim.x * kGroups;
 
-    FastItem cur, nxt;
-    bool cur_valid = false, nxt_valid = false;
-    long item = blockIdx.x;
-    if (item < total) {
-        cur_valid = fast_decode<BYTES>(T, item, items_per_frame, maxchunks, cur);
-        if (warp == 0) fast_issue<BYTES>(T, B, cur, cur_valid, bufs, &bars[0], lane);
-    }
-    for (int k = 0; item < total; item += gridDim.x, k++) {
-        unsigned char *buf = bufs + (k & 1) * G::kBufBytes;
-        const long nitem = item + gridDim.x;
-        if (nitem < total) {
-            nxt_valid = fast_decode<BYTES>(T, nitem, items_per_frame, maxchunks, nxt);
-            if (warp == 0) fast_issue<BYTES>(T, B, nxt, nxt_valid, bufs + ((k + 1) & 1) * G::kBufBytes, &bars[(k + 1) & 1], lane);
-        }
-        mbar_wait(&bars[k & 1], (uint32_t)(k >> 1) & 1u);
-        if (cur_valid) {
-            const int o0 = 16 + cur.m;                     // smem offset of the chunk's first sample inside a staged row
-            // ---- slice-local edge rules (ffv1enc.c:381-388), written into the staged rows
-            if (tid < cur.nrows + 2) {
-                unsigned char *row = buf + tid * G::kRowBytes;
-                const int y = cur.y0 - 2 + tid;
-                if (y < 0) {
-                    for (int i = 0; i < G::kRowBytes; i += 16) *reinterpret_cast<uint4 *>(row + i) = make_uint4(0, 0, 0, 0);
-                } else {
-                    if (cur.cx0 == 0) {
-                        // sample[-1] = the sample above x=0 (0 on the first row); sample[-2] = 0
-                        if (BYTES == 1) {
-                            row[o0 - 1] = (tid > 0 && y > 0) ? (row - G::kRowBytes)[o0] : 0;
-                            row[o0 - 2] = 0;
-                        } else {
-                            reinterpret_cast<uint16_t *>(row + o0)[-1] = (tid > 0 && y > 0) ? *reinterpret_cast<uint16_t *>(row - G::kRowBytes + o0) : 0;
-                            reinterpret_cast<uint16_t *>(row + o0)[-2] = 0;
-                        }
-                    }
-                    if (cur.last_chunk) {
-                        if (BYTES == 1) row[o0 + cur.cw] = row[o0 + cur.cw - 1];
-                        else reinterpret_cast<uint16_t *>(row + o0)[cur.cw] = reinterpret_cast<uint16_t *>(row + o0)[cur.cw - 1];
-                    }
-                }
+    FastItem cur, pre;
+    long item = (long)blockIdx.x * kGroups + group;
+    // ---- prologue: the TMA unit starts on the first kFastBufs-1 items of this group
+    if (warp == 0)
+        for (int j = 0; j < kFastBufs - 1; j++) {
+            const long it = item + j * step;
+            if (it < total) {
+                const bool v = fast_decode<BYTES>(T, it, items_per_frame, maxchunks, pre);
+                if (TENSOR) fast_issue_tensor<BYTES>(T, maps, pre, v, bufs + j * G::kBufBytes, &bars[j], lane);
+                else        fast_issue<BYTES>(T, B, pre, v, bufs + j * G::kBufBytes, &bars[j], lane);
             }
         }
-        __syncthreads();
+    int bi = 0, pi = kFastBufs - 1;           // buffer of the current item / of the item fetched now
+    uint32_t phase = 0;
+    for (; item < total; item += step) {
+        unsigned char *buf = bufs + bi * G::kBufBytes;
+        const long pitem = item + (kFastBufs - 1) * step;
+        if (warp == 0 && pitem < total) {
+            const bool v = fast_decode<BYTES>(T, pitem, items_per_frame, maxchunks, pre);
+            if (TENSOR) fast_issue_tensor<BYTES>(T, maps, pre, v, bufs + pi * G::kBufBytes, &bars[pi], lane);
+            else        fast_issue<BYTES>(T, B, pre, v, bufs + pi * G::kBufBytes, &bars[pi], lane);
+        }
+        const bool cur_valid = fast_decode<BYTES>(T, item, items_per_frame, maxchunks, cur);
+        mbar_wait(&bars[bi], phase);
         if (cur_valid) {
             const SliceGeom &g = T.slices[cur.slice];
             const int o0 = 16 + cur.m;
@@ -204,66 +234,96 @@ k_pixel_fast(const EncDeviceTables T, const EncBatch B, const int maxchunks)
             // lines of one plane follow each other in the record area, each padded to 32 records
             uint32_t *rec_tile = rec_slice + T.lines[g.line_first + cur.line_first].rec_off + cur.cx0;
             const uint32_t rec_stride = (uint32_t)(cur.w + 31) & ~31u;
-            const int upr = (cur.cw + 3) >> 2;                                  // 4-sample units per row
-            const uint32_t magic = (1048576u + (uint32_t)upr - 1u) / (uint32_t)upr;   // exact u / upr for u < 2^11
+            constexpr int U = 8;                                                // samples per thread and iteration
+            const int upr = (cur.cw + U - 1) / U;                               // units per row
+            const uint32_t magic = (1048576u + (uint32_t)upr - 1u) / (uint32_t)upr;   // exact u / upr for u < 2^12
             const int nunits = upr * cur.nrows;
-            for (int u = tid; u < nunits; u += kFastThreads) {
-                const int r = (int)(((uint32_t)u * magic) >> 20);
+            for (int u = tid; u < nunits; u += kFastGroup) {
+                const int r = (int)__umulhi((uint32_t)u << 12, magic);      // u * magic >> 20
                 const int ux = u - r * upr;
-                const unsigned char *crow = buf + (r + 2) * G::kRowBytes + o0 + ux * 4 * BYTES;
+                const unsigned char *crow = buf + (r + 2) * G::kRowBytes + o0 + ux * U * BYTES;
                 const unsigned char *trow = crow - G::kRowBytes;
                 // values are kept multiplied by 256: (a - b) & 0xFF00 is then directly the byte offset of table entry
                 // (a - b) & 255 (ffv1.h:181-189 masks the differences with 0xFF even for deeper samples)
-                int X[4], Tt[6], Lx, LLx = 0, TT[4] = {0, 0, 0, 0};
+                int X[U], Tt[U + 2], Lx, LLx = 0, TT[U];
+                const bool first = cur.cx0 == 0 && ux == 0;
                 if (BYTES == 1) {
-                    const uint32_t c4 = *reinterpret_cast<const uint32_t *>(crow);
-                    const uint32_t cp = *reinterpret_cast<const uint32_t *>(crow - 4);
-                    const uint32_t t4 = *reinterpret_cast<const uint32_t *>(trow);
-                    const uint32_t tp = *reinterpret_cast<const uint32_t *>(trow - 4);
-                    const uint32_t tn = *reinterpret_cast<const uint32_t *>(trow + 4);
-                    X[0] = __byte_perm(c4, 0, 0x4404); X[1] = __byte_perm(c4, 0, 0x4414);
-                    X[2] = __byte_perm(c4, 0, 0x4424); X[3] = __byte_perm(c4, 0, 0x4434);
-                    Lx = __byte_perm(cp, 0, 0x4434);
-                    Tt[0] = __byte_perm(tp, 0, 0x4434);
-                    Tt[1] = __byte_perm(t4, 0, 0x4404); Tt[2] = __byte_perm(t4, 0, 0x4414);
-                    Tt[3] = __byte_perm(t4, 0, 0x4424); Tt[4] = __byte_perm(t4, 0, 0x4434);
-                    Tt[5] = __byte_perm(tn, 0, 0x4404);
+                    const uint32_t c0 = *reinterpret_cast<const uint32_t *>(crow), c1 = *reinterpret_cast<const uint32_t *>(crow + 4);
+                    const uint32_t t0 = *reinterpret_cast<const uint32_t *>(trow), t1 = *reinterpret_cast<const uint32_t *>(trow + 4);
+                    const uint32_t tn = *reinterpret_cast<const uint32_t *>(trow + 8);
+                    X[0] = __byte_perm(c0, 0, 0x4404); X[1] = __byte_perm(c0, 0, 0x4414);
+                    X[2] = __byte_perm(c0, 0, 0x4424); X[3] = __byte_perm(c0, 0, 0x4434);
+                    X[4] = __byte_perm(c1, 0, 0x4404); X[5] = __byte_perm(c1, 0, 0x4414);
+                    X[6] = __byte_perm(c1, 0, 0x4424); X[7] = __byte_perm(c1, 0, 0x4434);
+                    Tt[1] = __byte_perm(t0, 0, 0x4404); Tt[2] = __byte_perm(t0, 0, 0x4414);
+                    Tt[3] = __byte_perm(t0, 0, 0x4424); Tt[4] = __byte_perm(t0, 0, 0x4434);
+                    Tt[5] = __byte_perm(t1, 0, 0x4404); Tt[6] = __byte_perm(t1, 0, 0x4414);
+                    Tt[7] = __byte_perm(t1, 0, 0x4424); Tt[8] = __byte_perm(t1, 0, 0x4434);
+                    Tt[9] = __byte_perm(tn, 0, 0x4404);
+                    if (first) {
+                        // slice-local left edge (ffv1enc.c:381-388): L = T, LT = the sample two rows up, LL = 0
+                        Lx = Tt[1];
+                        Tt[0] = __byte_perm(*reinterpret_cast<const uint32_t *>(trow - G::kRowBytes), 0, 0x4404);
+                    } else {
+                        const uint32_t cp = *reinterpret_cast<const uint32_t *>(crow - 4);
+                        Lx = __byte_perm(cp, 0, 0x4434);
+                        Tt[0] = __byte_perm(*reinterpret_cast<const uint32_t *>(trow - 4), 0, 0x4434);
+                        if (NIN == 5) LLx = __byte_perm(cp, 0, 0x4424);
+                    }
                     if (NIN == 5) {
-                        LLx = __byte_perm(cp, 0, 0x4424);
-                        const uint32_t u4 = *reinterpret_cast<const uint32_t *>(trow - G::kRowBytes);
-                        TT[0] = __byte_perm(u4, 0, 0x4404); TT[1] = __byte_perm(u4, 0, 0x4414);
-                        TT[2] = __byte_perm(u4, 0, 0x4424); TT[3] = __byte_perm(u4, 0, 0x4434);
+                        const uint32_t u0 = *reinterpret_cast<const uint32_t *>(trow - G::kRowBytes);
+                        const uint32_t u1 = *reinterpret_cast<const uint32_t *>(trow - G::kRowBytes + 4);
+                        TT[0] = __byte_perm(u0, 0, 0x4404); TT[1] = __byte_perm(u0, 0, 0x4414);
+                        TT[2] = __byte_perm(u0, 0, 0x4424); TT[3] = __byte_perm(u0, 0, 0x4434);
+                        TT[4] = __byte_perm(u1, 0, 0x4404); TT[5] = __byte_perm(u1, 0, 0x4414);
+                        TT[6] = __byte_perm(u1, 0, 0x4424); TT[7] = __byte_perm(u1, 0, 0x4434);
                     }
                 } else {
                     // 16-bit containers: LSB-aligned 9..15-bit values as they are; 16-bit values wrap into int16 like the
                     // reference's int16_t sample_buffer (ffv1enc.c:396-403); MSB-aligned input is shifted down first
                     const int sh = L.sample_shift;
-                    const uint2 c4 = *reinterpret_cast<const uint2 *>(crow);
-                    const uint32_t cp = *reinterpret_cast<const uint32_t *>(crow - 4);
-                    const uint2 t4 = *reinterpret_cast<const uint2 *>(trow);
-                    const uint32_t tp = *reinterpret_cast<const uint32_t *>(trow - 4);
-                    const uint32_t tn = *reinterpret_cast<const uint32_t *>(trow + 8);
 #define S16(v) (((int)(int16_t)(((v) & 0xFFFFu) >> sh)) << 8)
-                    X[0] = S16(c4.x); X[1] = S16(c4.x >> 16); X[2] = S16(c4.y); X[3] = S16(c4.y >> 16);
-                    Lx = S16(cp >> 16);
-                    Tt[0] = S16(tp >> 16);
-                    Tt[1] = S16(t4.x); Tt[2] = S16(t4.x >> 16); Tt[3] = S16(t4.y); Tt[4] = S16(t4.y >> 16);
-                    Tt[5] = S16(tn);
+                    const uint2 ca = *reinterpret_cast<const uint2 *>(crow), cb = *reinterpret_cast<const uint2 *>(crow + 8);
+                    const uint2 ta = *reinterpret_cast<const uint2 *>(trow), tb = *reinterpret_cast<const uint2 *>(trow + 8);
+                    const uint32_t tn = *reinterpret_cast<const uint32_t *>(trow + 16);
+                    X[0] = S16(ca.x); X[1] = S16(ca.x >> 16); X[2] = S16(ca.y); X[3] = S16(ca.y >> 16);
+                    X[4] = S16(cb.x); X[5] = S16(cb.x >> 16); X[6] = S16(cb.y); X[7] = S16(cb.y >> 16);
+                    Tt[1] = S16(ta.x); Tt[2] = S16(ta.x >> 16); Tt[3] = S16(ta.y); Tt[4] = S16(ta.y >> 16);
+                    Tt[5] = S16(tb.x); Tt[6] = S16(tb.x >> 16); Tt[7] = S16(tb.y); Tt[8] = S16(tb.y >> 16);
+                    Tt[9] = S16(tn);
+                    if (first) {
+                        Lx = Tt[1];
+                        Tt[0] = S16(*reinterpret_cast<const uint32_t *>(trow - G::kRowBytes));
+                    } else {
+                        const uint32_t cp = *reinterpret_cast<const uint32_t *>(crow - 4);
+                        Lx = S16(cp >> 16);
+                        Tt[0] = S16(*reinterpret_cast<const uint32_t *>(trow - 4) >> 16);
+                        if (NIN == 5) LLx = S16(cp);
+                    }
                     if (NIN == 5) {
-                        LLx = S16(cp);
-                        const uint2 u4 = *reinterpret_cast<const uint2 *>(trow - G::kRowBytes);
-                        TT[0] = S16(u4.x); TT[1] = S16(u4.x >> 16); TT[2] = S16(u4.y); TT[3] = S16(u4.y >> 16);
+                        const uint2 ua = *reinterpret_cast<const uint2 *>(trow - G::kRowBytes), ub = *reinterpret_cast<const uint2 *>(trow - G::kRowBytes + 8);
+                        TT[0] = S16(ua.x); TT[1] = S16(ua.x >> 16); TT[2] = S16(ua.y); TT[3] = S16(ua.y >> 16);
+                        TT[4] = S16(ub.x); TT[5] = S16(ub.x >> 16); TT[6] = S16(ub.y); TT[7] = S16(ub.y >> 16);
                     }
 #undef S16
                 }
-                uint32_t out[4];
+                // slice-local right edge: RT of the last sample = its T
+                const bool lastu = cur.last_chunk && ux == upr - 1;
+                if ((cur.cw & (U - 1)) == 0) {                 // (uniform) the usual geometry: the row ends with a full unit
+                    if (lastu) Tt[U + 1] = Tt[U];
+                } else if (lastu) {
+                    const int il = (cur.cw - 1) & (U - 1);
+#pragma unroll
+                    for (int i = 0; i < U - 1; i++) if (il == i) Tt[i + 2] = Tt[i + 1];
+                }
+                uint32_t out[U];
                 // Q1 term of sample i uses the difference LT-T = Tt[i]-Tt[i+1]; the same difference is the T-RT term
                 // (Q2) of sample i-1, so one address serves both tables (A holds Q1 low, Q2 high)
                 uint32_t aA = ((uint32_t)(Tt[0] - Tt[1]) & 0xFF00u) | lane4;
                 int q1 = *reinterpret_cast<const int16_t *>(tabAB + aA);
                 int Lv = Lx, LLv = LLx;
 #pragma unroll
-                for (int i = 0; i < 4; i++) {
+                for (int i = 0; i < U; i++) {
                     const int LT = Tt[i], Tp = Tt[i + 1], RT = Tt[i + 2];
                     aA = ((uint32_t)(Tp - RT) & 0xFF00u) | lane4;
                     const int q2 = *reinterpret_cast<const int16_t *>(tabAB + aA + 2);
@@ -288,18 +348,18 @@ k_pixel_fast(const EncDeviceTables T, const EncBatch B, const int maxchunks)
                     }
                     LLv = Lv; Lv = X[i];
                 }
-                uint32_t *dst = rec_tile + ((uint32_t)r * rec_stride + (uint32_t)ux * 4u);
-                if (ux * 4 + 3 < cur.cw) {
-                    *reinterpret_cast<uint4 *>(dst) = make_uint4(out[0], out[1], out[2], out[3]);
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 4; i++)
-                        if (ux * 4 + i < cur.cw) dst[i] = out[i];
-                }
+                // one 256-bit store per thread (a full 32-byte sector; record lines are padded to 32 records, so the
+                // last, possibly partial, unit may store all eight)
+                char *dst = reinterpret_cast<char *>(rec_tile) + (size_t)((uint32_t)r * rec_stride + (uint32_t)ux * U) * 4u;
+                asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                             :: "l"(dst), "r"(out[0]), "r"(out[1]), "r"(out[2]), "r"(out[3]), "r"(out[4]), "r"(out[5]), "r"(out[6]), "r"(out[7])
+                             : "memory");
             }
         }
-        __syncthreads();
-        cur = nxt; cur_valid = nxt_valid;
+        // the group is done with this buffer: two items later the TMA unit may overwrite it
+        asm volatile("bar.sync %0, %1;" :: "r"(group + 1), "r"(kFastGroup) : "memory");
+        pi = bi;
+        if (++bi == kFastBufs) { bi = 0; phase ^= 1u; }
     }
 }
 
@@ -307,7 +367,7 @@ int pixel_fast_smem_bytes(const Layout &L)
 {
     const int bytes = L.src_kind == SRC_PLANAR16 ? 2 : 1;
     const int buf = bytes == 2 ? FastGeom<2>::kBufBytes : FastGeom<1>::kBufBytes;
-    return kFastTabAB + (L.ctx_inputs == 5 ? kFastTabC : 0) + 2 * buf + 16;
+    return kFastTabAB + (L.ctx_inputs == 5 ? kFastTabC : 0) + (kFastThreads / kFastGroup) * kFastBufs * buf + 64 + 1024;
 }
 
 // static part of the eligibility test (geometry); pointer / linesize alignment is checked per call by the host
@@ -322,31 +382,84 @@ bool pixel_fast_geometry_ok(const Layout &L, const SliceGeom *slices, int nslice
     return true;
 }
 
+template <int BYTES, int NIN>
+static cudaError_t set_attr(int sm)
+{
+    cudaError_t e = cudaFuncSetAttribute(k_pixel_fast<BYTES, NIN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_pixel_fast<BYTES, NIN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+}
+
 cudaError_t configure_pixel_fast(const Layout &L)
 {
     const int sm = pixel_fast_smem_bytes(L);
     cudaError_t e;
-    e = cudaFuncSetAttribute(k_pixel_fast<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm); if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_pixel_fast<1, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm); if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_pixel_fast<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm); if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_pixel_fast<2, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm); if (e != cudaSuccess) return e;
-    return cudaSuccess;
+    if ((e = set_attr<1, 3>(sm)) != cudaSuccess) return e;
+    if ((e = set_attr<1, 5>(sm)) != cudaSuccess) return e;
+    if ((e = set_attr<2, 3>(sm)) != cudaSuccess) return e;
+    return set_attr<2, 5>(sm);
 }
 
-void launch_pixel_fast(const EncDeviceTables &t, const EncBatch &b, int max_plane_width, int num_sms, cudaStream_t s)
+static PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder()
+{
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+        cudaGetLastError();
+    }
+    return fn;
+}
+
+template <int BYTES, int NIN>
+static void launch_t(const EncDeviceTables &t, const EncBatch &b, int maxchunks, int grid, int sm, cudaStream_t s,
+                     const uint8_t *const *frame0_planes, long long frame_stride)
+{
+    FastMaps maps;
+    memset(&maps, 0, sizeof(maps));
+    bool tensor = frame_stride >= 0 && (frame_stride & 15) == 0 && getenv("FFV1B200_PIXEL_ROWCOPY") == nullptr;
+    PFN_cuTensorMapEncodeTiled_v12000 enc = tensor ? tensor_map_encoder() : nullptr;
+    tensor = tensor && enc != nullptr;
+    const Layout &L = t.layout;
+    for (int p = 0; p < L.nplanes && tensor; p++) {
+        const int sp = L.plane[p].src_plane;
+        const int rows = (L.height + (1 << L.plane[p].vshift) - 1) >> L.plane[p].vshift;
+        const cuuint64_t dims[3] = {(cuuint64_t)(b.linesize[sp] / 4), (cuuint64_t)rows, (cuuint64_t)b.nframes};
+        const cuuint64_t strides[2] = {(cuuint64_t)b.linesize[sp], (cuuint64_t)(b.nframes > 1 ? frame_stride : b.linesize[sp] * (long long)rows)};
+        const cuuint32_t box[3] = {(cuuint32_t)(FastGeom<BYTES>::kRowBytes / 4), (cuuint32_t)kFastRows, 1u};
+        const cuuint32_t estr[3] = {1u, 1u, 1u};
+        if (strides[1] & 15) { tensor = false; break; }
+        CUresult r = enc(&maps.m[sp], CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<uint8_t *>(frame0_planes[sp]), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) tensor = false;
+    }
+    if (tensor) k_pixel_fast<BYTES, NIN, true><<<grid, kFastThreads, sm, s>>>(t, b, maxchunks, maps);
+    else        k_pixel_fast<BYTES, NIN, false><<<grid, kFastThreads, sm, s>>>(t, b, maxchunks, maps);
+}
+
+// frame0_planes: host copy of the first frame's plane pointers; frame_stride: bytes between the same plane of consecutive
+// frames when that distance is constant over the batch (tensor-map TMA), else -1 (one bulk copy per row)
+void launch_pixel_fast(const EncDeviceTables &t, const EncBatch &b, int max_plane_width, int num_sms, cudaStream_t s,
+                       const uint8_t *const *frame0_planes, long long frame_stride)
 {
     const Layout &L = t.layout;
-    const int maxchunks = (max_plane_width + kFastChunk - 1) / kFastChunk;
+    const int chunk = kFastChunkBytes / (L.src_kind == SRC_PLANAR16 ? 2 : 1);
+    const int maxchunks = (max_plane_width + chunk - 1) / chunk;
     const long total = (long)L.tiles_per_frame * maxchunks * b.nframes;
-    const int grid = (int)std::min<long>(total, 2L * num_sms);
+    const int grid = (int)std::min<long>((total + 1) / 2, (long)num_sms);
     const int sm = pixel_fast_smem_bytes(L);
     const bool five = L.ctx_inputs == 5;
     if (L.src_kind == SRC_PLANAR8) {
-        if (five) k_pixel_fast<1, 5><<<grid, kFastThreads, sm, s>>>(t, b, maxchunks);
-        else      k_pixel_fast<1, 3><<<grid, kFastThreads, sm, s>>>(t, b, maxchunks);
+        if (five) launch_t<1, 5>(t, b, maxchunks, grid, sm, s, frame0_planes, frame_stride);
+        else      launch_t<1, 3>(t, b, maxchunks, grid, sm, s, frame0_planes, frame_stride);
     } else {
-        if (five) k_pixel_fast<2, 5><<<grid, kFastThreads, sm, s>>>(t, b, maxchunks);
-        else      k_pixel_fast<2, 3><<<grid, kFastThreads, sm, s>>>(t, b, maxchunks);
+        if (five) launch_t<2, 5>(t, b, maxchunks, grid, sm, s, frame0_planes, frame_stride);
+        else      launch_t<2, 3>(t, b, maxchunks, grid, sm, s, frame0_planes, frame_stride);
     }
 }
 
