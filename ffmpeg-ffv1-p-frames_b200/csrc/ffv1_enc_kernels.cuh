@@ -86,6 +86,6 @@ void launch_ctx_replay(const EncDeviceTables &t, const EncBatch &b, cudaStream_t
 bool pixel_fast_geometry_ok(const Layout &L, const SliceGeom *slices, int nslices);
 cudaError_t configure_pixel_fast(const Layout &L);
 void launch_pixel_fast(const EncDeviceTables &t, const EncBatch &b, int max_plane_width, int num_sms, cudaStream_t s,
-                       const uint8_t *const *frame0_planes, long long frame_stride);
+                       const uint8_t *const *frame0_planes, long long frame_stride, const SliceGeom *host_slices, int nslices);
 
 } // namespace ffv1

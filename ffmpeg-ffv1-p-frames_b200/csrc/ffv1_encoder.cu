@@ -223,7 +223,7 @@ int enqueue_kernels(FFV1B200Encoder *e, Slot &sl, cudaStream_t s)
         for (int f = 1; f < nframes && fstride >= 0; f++)
             for (int i = 0; i < e->cfg.nb_src_planes; i++)
                 if ((long long)(sl.h_planes.p[f * 4 + i] - sl.h_planes.p[(f - 1) * 4 + i]) != fstride) { fstride = -1; break; }
-        launch_pixel_fast(t, b, e->max_plane_width, e->num_sms, s, sl.h_planes.p, fstride);
+        launch_pixel_fast(t, b, e->max_plane_width, e->num_sms, s, sl.h_planes.p, fstride, e->tab.slices.data(), (int)e->tab.slices.size());
     }
     else         launch_pixel(t, b, s);
     cudaEventRecord(sl.ev[1], s);

@@ -37,7 +37,7 @@ template <int BYTES> struct FastGeom {
 
 // One tiled tensor map per source plane: {linesize / 4 (32-bit elements), rows, frames}; the box is one staging buffer
 // worth of rows, so a work item is fetched by a single TMA request (SASS UTMALDG) instead of one bulk copy per row.
-struct FastMaps { CUtensorMap m[4]; };
+struct FastMaps { CUtensorMap m[4]; int32_t row_bytes[4]; };    // row_bytes: box width = staged row pitch for that plane
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -146,10 +146,10 @@ template <int BYTES>
 __device__ __forceinline__ void fast_issue_tensor(const EncDeviceTables &T, const FastMaps &maps, const FastItem &it, bool valid,
                                                   unsigned char *buf, uint64_t *bar, int lane)
 {
-    typedef FastGeom<BYTES> G;
+    const int rowb = valid ? maps.row_bytes[T.layout.plane[it.plane].src_plane] : 0;
     const bool top = valid && it.y0 == 0;          // first tile of a slice: the two rows above it are zero, not the neighbour slice
     if (top)
-        for (int i = lane * 16; i < 2 * G::kRowBytes; i += 32 * 16)
+        for (int i = lane * 16; i < 2 * rowb; i += 32 * 16)
             *reinterpret_cast<uint4 *>(buf + i) = make_uint4(0u, 0u, 0u, 0u);
     __syncwarp();
     if (lane == 0) {
@@ -160,9 +160,9 @@ __device__ __forceinline__ void fast_issue_tensor(const EncDeviceTables &T, cons
         const int gx = (g.px0[it.plane] + it.cx0) * BYTES;            // byte column of the chunk's first sample
         const int c0 = ((gx & ~15) - 16) >> 2;                          // may be negative: out-of-bounds elements read as zero
         const int c1 = g.py0[it.plane] + it.y0 - (top ? 0 : 2);
-        mbar_expect_tx(bar, (uint32_t)(kFastRows * G::kRowBytes));
+        mbar_expect_tx(bar, (uint32_t)(kFastRows * rowb));
         asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-                     :: "r"(smem_u32(buf + (top ? 2 * G::kRowBytes : 0))), "l"(reinterpret_cast<uint64_t>(&maps.m[src_plane])),
+                     :: "r"(smem_u32(buf + (top ? 2 * rowb : 0))), "l"(reinterpret_cast<uint64_t>(&maps.m[src_plane])),
                         "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(it.f) : "memory");
     }
 }
@@ -235,14 +235,15 @@ k_pixel_fast(const EncDeviceTables T, const EncBatch B, const int maxchunks, con
             uint32_t *rec_tile = rec_slice + T.lines[g.line_first + cur.line_first].rec_off + cur.cx0;
             const uint32_t rec_stride = (uint32_t)(cur.w + 31) & ~31u;
             constexpr int U = 8;                                                // samples per thread and iteration
+            const int rowb = TENSOR ? maps.row_bytes[L.plane[cur.plane].src_plane] : G::kRowBytes;   // pitch of the staged rows
             const int upr = (cur.cw + U - 1) / U;                               // units per row
             const uint32_t magic = (1048576u + (uint32_t)upr - 1u) / (uint32_t)upr;   // exact u / upr for u < 2^12
             const int nunits = upr * cur.nrows;
             for (int u = tid; u < nunits; u += kFastGroup) {
                 const int r = (int)__umulhi((uint32_t)u << 12, magic);      // u * magic >> 20
                 const int ux = u - r * upr;
-                const unsigned char *crow = buf + (r + 2) * G::kRowBytes + o0 + ux * U * BYTES;
-                const unsigned char *trow = crow - G::kRowBytes;
+                const unsigned char *crow = buf + (r + 2) * rowb + o0 + ux * U * BYTES;
+                const unsigned char *trow = crow - rowb;
                 // values are kept multiplied by 256: (a - b) & 0xFF00 is then directly the byte offset of table entry
                 // (a - b) & 255 (ffv1.h:181-189 masks the differences with 0xFF even for deeper samples)
                 int X[U], Tt[U + 2], Lx, LLx = 0, TT[U];
@@ -263,7 +264,7 @@ k_pixel_fast(const EncDeviceTables T, const EncBatch B, const int maxchunks, con
                     if (first) {
                         // slice-local left edge (ffv1enc.c:381-388): L = T, LT = the sample two rows up, LL = 0
                         Lx = Tt[1];
-                        Tt[0] = __byte_perm(*reinterpret_cast<const uint32_t *>(trow - G::kRowBytes), 0, 0x4404);
+                        Tt[0] = __byte_perm(*reinterpret_cast<const uint32_t *>(trow - rowb), 0, 0x4404);
                     } else {
                         const uint32_t cp = *reinterpret_cast<const uint32_t *>(crow - 4);
                         Lx = __byte_perm(cp, 0, 0x4434);
@@ -271,8 +272,8 @@ k_pixel_fast(const EncDeviceTables T, const EncBatch B, const int maxchunks, con
                         if (NIN == 5) LLx = __byte_perm(cp, 0, 0x4424);
                     }
                     if (NIN == 5) {
-                        const uint32_t u0 = *reinterpret_cast<const uint32_t *>(trow - G::kRowBytes);
-                        const uint32_t u1 = *reinterpret_cast<const uint32_t *>(trow - G::kRowBytes + 4);
+                        const uint32_t u0 = *reinterpret_cast<const uint32_t *>(trow - rowb);
+                        const uint32_t u1 = *reinterpret_cast<const uint32_t *>(trow - rowb + 4);
                         TT[0] = __byte_perm(u0, 0, 0x4404); TT[1] = __byte_perm(u0, 0, 0x4414);
                         TT[2] = __byte_perm(u0, 0, 0x4424); TT[3] = __byte_perm(u0, 0, 0x4434);
                         TT[4] = __byte_perm(u1, 0, 0x4404); TT[5] = __byte_perm(u1, 0, 0x4414);
@@ -293,7 +294,7 @@ k_pixel_fast(const EncDeviceTables T, const EncBatch B, const int maxchunks, con
                     Tt[9] = S16(tn);
                     if (first) {
                         Lx = Tt[1];
-                        Tt[0] = S16(*reinterpret_cast<const uint32_t *>(trow - G::kRowBytes));
+                        Tt[0] = S16(*reinterpret_cast<const uint32_t *>(trow - rowb));
                     } else {
                         const uint32_t cp = *reinterpret_cast<const uint32_t *>(crow - 4);
                         Lx = S16(cp >> 16);
@@ -301,7 +302,7 @@ k_pixel_fast(const EncDeviceTables T, const EncBatch B, const int maxchunks, con
                         if (NIN == 5) LLx = S16(cp);
                     }
                     if (NIN == 5) {
-                        const uint2 ua = *reinterpret_cast<const uint2 *>(trow - G::kRowBytes), ub = *reinterpret_cast<const uint2 *>(trow - G::kRowBytes + 8);
+                        const uint2 ua = *reinterpret_cast<const uint2 *>(trow - rowb), ub = *reinterpret_cast<const uint2 *>(trow - rowb + 8);
                         TT[0] = S16(ua.x); TT[1] = S16(ua.x >> 16); TT[2] = S16(ua.y); TT[3] = S16(ua.y >> 16);
                         TT[4] = S16(ub.x); TT[5] = S16(ub.x >> 16); TT[6] = S16(ub.y); TT[7] = S16(ub.y >> 16);
                     }
@@ -320,16 +321,16 @@ k_pixel_fast(const EncDeviceTables T, const EncBatch B, const int maxchunks, con
                 // Q1 term of sample i uses the difference LT-T = Tt[i]-Tt[i+1]; the same difference is the T-RT term
                 // (Q2) of sample i-1, so one address serves both tables (A holds Q1 low, Q2 high)
                 uint32_t aA = ((uint32_t)(Tt[0] - Tt[1]) & 0xFF00u) | lane4;
-                int q1 = *reinterpret_cast<const int16_t *>(tabAB + aA);
-                int Lv = Lx, LLv = LLx;
+                int q1 = *reinterpret_cast<const volatile int16_t *>(tabAB + aA);       // volatile: keep the two halves as two
+                int Lv = Lx, LLv = LLx;                                                  // LDS.S16 (LSU) instead of LDS + 2 PRMT (ALU)
 #pragma unroll
                 for (int i = 0; i < U; i++) {
                     const int LT = Tt[i], Tp = Tt[i + 1], RT = Tt[i + 2];
                     aA = ((uint32_t)(Tp - RT) & 0xFF00u) | lane4;
-                    const int q2 = *reinterpret_cast<const int16_t *>(tabAB + aA + 2);
+                    const int q2 = *reinterpret_cast<const volatile int16_t *>(tabAB + aA + 2);
                     const uint32_t aB = ((uint32_t)(Lv - LT) & 0xFF00u) | lane4;
                     int ctx = *reinterpret_cast<const int16_t *>(tabAB + aB + 128) + q1 + q2;
-                    q1 = *reinterpret_cast<const int16_t *>(tabAB + aA);
+                    q1 = *reinterpret_cast<const volatile int16_t *>(tabAB + aA);
                     if (NIN == 5) {
                         const uint32_t a3 = ((uint32_t)(LLv - Lv) & 0xFF00u) | lane4;
                         const uint32_t a4 = (((uint32_t)(TT[i] - Tp) >> 1) & 0x7F80u) | lane4;
@@ -417,7 +418,7 @@ static PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder()
 
 template <int BYTES, int NIN>
 static void launch_t(const EncDeviceTables &t, const EncBatch &b, int maxchunks, int grid, int sm, cudaStream_t s,
-                     const uint8_t *const *frame0_planes, long long frame_stride)
+                     const uint8_t *const *frame0_planes, long long frame_stride, const SliceGeom *slices, int nslices)
 {
     FastMaps maps;
     memset(&maps, 0, sizeof(maps));
@@ -430,7 +431,13 @@ static void launch_t(const EncDeviceTables &t, const EncBatch &b, int maxchunks,
         const int rows = (L.height + (1 << L.plane[p].vshift) - 1) >> L.plane[p].vshift;
         const cuuint64_t dims[3] = {(cuuint64_t)(b.linesize[sp] / 4), (cuuint64_t)rows, (cuuint64_t)b.nframes};
         const cuuint64_t strides[2] = {(cuuint64_t)b.linesize[sp], (cuuint64_t)(b.nframes > 1 ? frame_stride : b.linesize[sp] * (long long)rows)};
-        const cuuint32_t box[3] = {(cuuint32_t)(FastGeom<BYTES>::kRowBytes / 4), (cuuint32_t)kFastRows, 1u};
+        // box width: left block + misalignment + the widest chunk of this plane + next sample, as a multiple of 64 bytes
+        // (so that two rows are a multiple of the 128-byte alignment TMA wants for its shared-memory destination)
+        int wmax = 0;
+        for (int si = 0; si < nslices; si++) wmax = std::max(wmax, slices[si].pw[p]);
+        const int rowb = std::min(FastGeom<BYTES>::kRowBytes, (16 + 15 + std::min(wmax, FastGeom<BYTES>::kChunk) * BYTES + BYTES + 63) & ~63);
+        maps.row_bytes[sp] = std::max(maps.row_bytes[sp], rowb);
+        const cuuint32_t box[3] = {(cuuint32_t)(maps.row_bytes[sp] / 4), (cuuint32_t)kFastRows, 1u};
         const cuuint32_t estr[3] = {1u, 1u, 1u};
         if (strides[1] & 15) { tensor = false; break; }
         CUresult r = enc(&maps.m[sp], CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<uint8_t *>(frame0_planes[sp]), dims, strides, box, estr,
@@ -445,7 +452,7 @@ static void launch_t(const EncDeviceTables &t, const EncBatch &b, int maxchunks,
 // frame0_planes: host copy of the first frame's plane pointers; frame_stride: bytes between the same plane of consecutive
 // frames when that distance is constant over the batch (tensor-map TMA), else -1 (one bulk copy per row)
 void launch_pixel_fast(const EncDeviceTables &t, const EncBatch &b, int max_plane_width, int num_sms, cudaStream_t s,
-                       const uint8_t *const *frame0_planes, long long frame_stride)
+                       const uint8_t *const *frame0_planes, long long frame_stride, const SliceGeom *slices, int nslices)
 {
     const Layout &L = t.layout;
     const int chunk = kFastChunkBytes / (L.src_kind == SRC_PLANAR16 ? 2 : 1);
@@ -455,11 +462,11 @@ void launch_pixel_fast(const EncDeviceTables &t, const EncBatch &b, int max_plan
     const int sm = pixel_fast_smem_bytes(L);
     const bool five = L.ctx_inputs == 5;
     if (L.src_kind == SRC_PLANAR8) {
-        if (five) launch_t<1, 5>(t, b, maxchunks, grid, sm, s, frame0_planes, frame_stride);
-        else      launch_t<1, 3>(t, b, maxchunks, grid, sm, s, frame0_planes, frame_stride);
+        if (five) launch_t<1, 5>(t, b, maxchunks, grid, sm, s, frame0_planes, frame_stride, slices, nslices);
+        else      launch_t<1, 3>(t, b, maxchunks, grid, sm, s, frame0_planes, frame_stride, slices, nslices);
     } else {
-        if (five) launch_t<2, 5>(t, b, maxchunks, grid, sm, s, frame0_planes, frame_stride);
-        else      launch_t<2, 3>(t, b, maxchunks, grid, sm, s, frame0_planes, frame_stride);
+        if (five) launch_t<2, 5>(t, b, maxchunks, grid, sm, s, frame0_planes, frame_stride, slices, nslices);
+        else      launch_t<2, 3>(t, b, maxchunks, grid, sm, s, frame0_planes, frame_stride, slices, nslices);
     }
 }
 
