@@ -24,6 +24,9 @@ GOP = 16
 FRAME_BYTES = W * H * 3 // 2
 SAMPLES = W * H * 3 // 2
 ALGO_BYTES_PER_SAMPLE = 5          # 1 B read + 4 B (context,diff) record written
+# dram__bytes_read.sum + dram__bytes_write.sum of k_pixel_fast per frame, from the ncu --set full capture summarised in
+# profiles/r01_k_pixel_fast.txt (870.6 MB + 3128.2 MB for a 256-frame launch)
+TRAFFIC_BYTES_PER_FRAME = (870576896 + 3128153000) / 256
 METRIC = "1080p yuv420p8 FFV1 level-3 GOP-16 encode throughput (bit-exact)"
 WORKLOAD = "1080p yuv420p8 synthetic noise clip, FFV1 level 3, GOP 16 (P-frames), coder=1, context=0, 24 slices, slicecrc"
 
@@ -289,8 +292,9 @@ def main():
             "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": B, "input_bytes_per_step_per_gpu": B * FRAME_BYTES,
                        "l2_policy": "input (%.0f MB) and intermediate streams are far larger than the 126 MB L2" % (B * FRAME_BYTES / 1e6),
                        "parallelism": "GOP-aligned frame ranges per GPU, no collective", "packet_bytes_per_frame": pkt_bytes_step / B},
-            "roofline": {"kernel": "k_pixel (prediction/context/residual pass)", "bound": "hbm", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": None,
+            "roofline": {"kernel": "k_pixel_fast (prediction/context/residual pass)", "bound": "hbm", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": TRAFFIC_BYTES_PER_FRAME * B,
+                         "traffic_source": "ncu dram__bytes_read+write per launch, profiles/r01_k_pixel_fast.txt, scaled to this batch",
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": algo, "launch_ms": px_ms},
             "kernels_ms_per_step": {"pixel": px_ms, "state_replay": d["ms_model_kernel"] / args.steps,
                                     "range_coder": d["ms_coder_kernel"] / args.steps, "pack_crc": d["ms_pack_kernel"] / args.steps},
