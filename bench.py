@@ -191,6 +191,7 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
+        os.environ["NCCL_DEBUG"] = "WARN"      # stdout carries exactly one JSON line (NCCL_DEBUG=VERSION would add a banner)
         dist.init_process_group("nccl", device_id=dev)
 
     B = max(GOP, args.batch // GOP * GOP)
