@@ -827,77 +827,115 @@ __device__ __forceinline__ uint32_t gf_mulmod(uint32_t a, uint32_t b)
     return r;
 }
 
-constexpr int kPackThreads = 128;
+constexpr int kPackThreads = 256;
 
 // One CTA per (frame, slice): copy the coder output to its final place, append the 24-bit length and the
-// error-check trailer.  CRC: every thread runs a table CRC over one contiguous chunk; partial CRCs are
-// merged pairwise, crc(A|B) = crc(A)*x^(8|B|) + crc(B)  (init 0, no final xor => plain polynomial remainder).
+// error-check trailer.
+//   CRC (libavutil AV_CRC_32_IEEE: MSB-first 0x04C11DB7, init 0, no final xor = plain polynomial remainder):
+//   every thread runs a slicing-by-4 table CRC over one contiguous, word-aligned chunk of the payload; by linearity
+//   crc(message) = XOR over chunks of crc(chunk) * x^(8 * bytes after the chunk) mod P, so each thread scales its
+//   own partial CRC (square-and-multiply over precomputed x^(8*2^j)) and a XOR reduction finishes the job.
+//   Copy: the packet position has arbitrary byte alignment, so destination-aligned 32-bit words are built from two
+//   source words with a funnel shift; the stores of a warp are contiguous.
 __global__ void __launch_bounds__(kPackThreads) k_pack_slices(const EncDeviceTables T, const EncBatch B)
 {
-    __shared__ uint32_t s_tab[256];
-    __shared__ uint32_t s_part[kPackThreads];
+    __shared__ uint32_t s_tab[4][256];          // s_tab[k][b] = (b * x^(8k+32)) mod P
+    __shared__ uint32_t s_pow[32];              // x^(8 * 2^j) mod P
+    __shared__ uint32_t s_red[kPackThreads / 32];
     const Layout &L = T.layout;
     const int ns = L.nslices;
     const int f = blockIdx.x / ns, s = blockIdx.x - f * ns;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
     if (B.status[0] | B.status[1] | B.status[2]) return;
 
     for (int n = tid; n < 256; n += kPackThreads) {
         uint32_t c = (uint32_t)n << 24;
 #pragma unroll
         for (int k = 0; k < 8; k++) c = (c & 0x80000000u) ? (c << 1) ^ 0x04C11DB7u : (c << 1);
-        s_tab[n] = c;
+        s_tab[0][n] = c;
+    }
+    if (tid == 0) {
+        uint32_t p = 0x100u;                    // x^8
+        for (int j = 0; j < 32; j++) { s_pow[j] = p; p = gf_mulmod(p, p); }
+    }
+    __syncthreads();
+    for (int n = tid; n < 256; n += kPackThreads) {
+        uint32_t c = s_tab[0][n];
+        for (int k = 1; k < 4; k++) { c = (c << 8) ^ s_tab[0][c >> 24]; s_tab[k][n] = c; }
     }
     const bool has_len = (T.version > 2) || s > 0;
-    const int trailer = (has_len ? 3 : 0) + (T.ec ? 5 : 0);
     unsigned long long off = B.pkt_off[f];
     for (int k = 0; k < s; k++) off += B.slice_bytes[f * ns + k] + ((T.version > 2 || k > 0) ? 3 : 0) + (T.ec ? 5 : 0);
     const uint32_t nb = B.slice_bytes[f * ns + s];
-    const uint8_t *src = B.scratch + (size_t)f * L.scratch_per_frame + T.slices[s].scratch_off + kScratchLead;
+    const uint8_t *src = B.scratch + (size_t)f * L.scratch_per_frame + T.slices[s].scratch_off + kScratchLead;   // 4-byte aligned
     uint8_t *dst = B.out + off;
     __syncthreads();
 
-    // message covered by the CRC: payload | len24 | 0x00
-    const uint32_t mlen = nb + (has_len ? 3 : 0) + (T.ec ? 1 : 0);
-    const uint32_t chunk = (mlen + kPackThreads - 1) / kPackThreads;
-    // chunks are aligned to the END of the message; a short/empty first chunk is equivalent to leading zero
-    // bytes, which do not change a CRC with zero initial value.
-    const long long beg = (long long)mlen - (long long)(kPackThreads - tid) * chunk;
-    uint32_t crc = 0;
-    for (long long i = beg < 0 ? 0 : beg; i < beg + (long long)chunk; i++) {
-        uint32_t byte;
-        if (i < nb) byte = src[i];
-        else {
-            const uint32_t k = (uint32_t)i - nb;
-            byte = (has_len && k < 3) ? ((nb >> (16 - 8 * k)) & 0xFFu) : 0u;
+    // ---- copy: head bytes up to the first aligned destination word, aligned words, tail bytes
+    {
+        const uint32_t head = min(nb, (uint32_t)((4u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 3u)) & 3u));
+        if ((uint32_t)tid < head) dst[tid] = src[tid];
+        const uint32_t nwords = (nb - head) >> 2;
+        const uint32_t *src32 = reinterpret_cast<const uint32_t *>(src);
+        uint32_t *dst32 = reinterpret_cast<uint32_t *>(dst + head);
+        const uint32_t sh = head * 8u;                                    // source byte offset inside a word
+        for (uint32_t w = tid; w < nwords; w += kPackThreads) {
+            const uint32_t lo = src32[w];
+            const uint32_t hi = head ? src32[w + 1] : 0u;                 // within the scratch region (cap is padded)
+            dst32[w] = head ? __funnelshift_r(lo, hi, sh) : lo;
         }
-        dst[i] = (uint8_t)byte;
-        crc = (crc << 8) ^ s_tab[(crc >> 24) ^ byte];
+        const uint32_t done = head + nwords * 4u;
+        if ((uint32_t)tid < nb - done) dst[done + tid] = src[done + tid];
+        // trailer: 24-bit big-endian payload length, then 0x00 (the CRC itself is written below)
+        if (tid == 0) {
+            uint32_t q = nb;
+            if (has_len) { dst[q] = (uint8_t)(nb >> 16); dst[q + 1] = (uint8_t)(nb >> 8); dst[q + 2] = (uint8_t)nb; q += 3; }
+            if (T.ec) dst[q] = 0;
+        }
     }
     if (!T.ec) return;
-    // x^(8*chunk) mod P by square-and-multiply
-    uint32_t mult = 1u, base = 0x100u;
-    for (uint32_t e = chunk; e; e >>= 1) {
-        if (e & 1u) mult = gf_mulmod(mult, base);
-        base = gf_mulmod(base, base);
+
+    // ---- CRC over payload | len24 | 0x00
+    const uint32_t tail_bytes = (has_len ? 3u : 0u) + 1u;
+    const uint32_t nw_all = nb >> 2;                                      // whole source words
+    const uint32_t per = (nw_all + kPackThreads - 1) / kPackThreads;      // words per thread
+    const uint32_t w0 = min(nw_all, (uint32_t)tid * per), w1 = min(nw_all, w0 + per);
+    uint32_t crc = 0;
+    {
+        const uint32_t *src32 = reinterpret_cast<const uint32_t *>(src);
+        for (uint32_t w = w0; w < w1; w++) {
+            const uint32_t v = src32[w] ^ __byte_perm(crc, 0, 0x0123);    // message bytes are MSB-first: fold crc in byte order
+            crc = s_tab[3][v & 0xFFu] ^ s_tab[2][(v >> 8) & 0xFFu] ^ s_tab[1][(v >> 16) & 0xFFu] ^ s_tab[0][v >> 24];
+        }
     }
-    s_part[tid] = crc;
+    uint32_t after = (nw_all - w1) * 4u + (nb & 3u) + tail_bytes;         // message bytes behind this thread's chunk
+    if (tid == kPackThreads - 1) {
+        // the last thread also takes the 0..3 payload bytes behind the last whole word and the trailer bytes
+        for (uint32_t i = nw_all * 4u; i < nb; i++) crc = (crc << 8) ^ s_tab[0][(crc >> 24) ^ src[i]];
+        if (has_len) {
+            crc = (crc << 8) ^ s_tab[0][(crc >> 24) ^ ((nb >> 16) & 0xFFu)];
+            crc = (crc << 8) ^ s_tab[0][(crc >> 24) ^ ((nb >> 8) & 0xFFu)];
+            crc = (crc << 8) ^ s_tab[0][(crc >> 24) ^ (nb & 0xFFu)];
+        }
+        crc = (crc << 8) ^ s_tab[0][crc >> 24];                          // the 0x00 byte
+        after = 0;
+    }
+    if (crc) {
+        uint32_t mult = 1u;
+        for (int j = 0; after; j++, after >>= 1) if (after & 1u) mult = gf_mulmod(mult, s_pow[j]);
+        crc = gf_mulmod(crc, mult);
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) crc ^= __shfl_xor_sync(0xFFFFFFFFu, crc, d);
+    if (lane == 0) s_red[tid >> 5] = crc;
     __syncthreads();
-    for (int stride = 1; stride < kPackThreads; stride <<= 1) {
-        uint32_t v = 0;
-        const bool active = (tid % (2 * stride)) == 0;
-        if (active) v = gf_mulmod(s_part[tid], mult) ^ s_part[tid + stride];
-        __syncthreads();
-        if (active) s_part[tid] = v;
-        mult = gf_mulmod(mult, mult);
-        __syncthreads();
-    }
     if (tid == 0) {
-        const uint32_t c = s_part[0];
+        uint32_t c = 0;
+        for (int i = 0; i < kPackThreads / 32; i++) c ^= s_red[i];
+        const uint32_t mlen = nb + tail_bytes;
         dst[mlen + 0] = (uint8_t)(c >> 24); dst[mlen + 1] = (uint8_t)(c >> 16);
         dst[mlen + 2] = (uint8_t)(c >> 8);  dst[mlen + 3] = (uint8_t)c;
     }
-    (void)trailer;
 }
 
 void launch_pack(const EncDeviceTables &t, const EncBatch &b, cudaStream_t s)
