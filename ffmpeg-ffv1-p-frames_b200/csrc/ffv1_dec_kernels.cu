@@ -305,6 +305,21 @@ __global__ void __launch_bounds__(32) k_decode(const DecDeviceTables T, const De
         if (lane == 0) {
             sr.golomb = golomb; sr.run_index = 0; sr.err = 0;
             rd_init(sr.rc, sbeg, ssize);
+            if (T.version < 2) {
+                // versions 0/1: one slice = the frame; the host has read the keyframe bit and the in-band header
+                // (ffv1dec.c:646-696) and hands over the coder state behind them
+                const uint32_t *is = B.init_state + (size_t)f * 3;
+                sr.rc.low = is[0]; sr.rc.range = is[1]; sr.rc.ptr = sbeg + is[2];
+                sx = 0; sy = 0; sw = T.width; sh = T.height;
+                if (sw + 2 * kDecRingPad > T.ring_w) bad = 1;
+                if (golomb) {                                                           // ffv1dec.c:427-434 (no state-129 bit before version 3.2)
+                    const uint32_t acb = (uint32_t)(sr.rc.ptr - sr.rc.start) - 1u;
+                    sr.br.buf = sr.rc.start + acb;
+                    sr.br.nbytes = ssize - acb;
+                    sr.br.pos = 0;
+                    br_load(sr.br, 0);
+                }
+            } else {
             if (si == 0) { uint8_t ks = 128; rd_get(sr.rc, &ks, s_lut); }              // keyframe bit (ffv1dec.c:924)
             uint8_t st[32];
             for (int i = 0; i < 32; i++) st[i] = 128;
@@ -334,6 +349,7 @@ __global__ void __launch_bounds__(32) k_decode(const DecDeviceTables T, const De
                 sr.br.nbytes = ssize - acb;
                 sr.br.pos = 0;
                 br_load(sr.br, 0);
+            }
             }
         }
         bad = __shfl_sync(0xFFFFFFFFu, bad, 0);
@@ -442,7 +458,7 @@ __global__ void __launch_bounds__(32) k_decode(const DecDeviceTables T, const De
         // ---- end-of-slice check (ffv1dec.c:459-467)
         if (lane == 0) {
             uint32_t flag = sr.err ? 2u : 0u;
-            if (!golomb) {
+            if (!golomb && T.version > 2) {
                 uint8_t s129 = 129;
                 rd_get(sr.rc, &s129, s_lut);
                 const long long v = (long long)(sr.rc.end - sr.rc.ptr) - 2 - 5 * T.ec;

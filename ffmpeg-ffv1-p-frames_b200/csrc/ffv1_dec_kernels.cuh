@@ -35,6 +35,7 @@ struct DecBatch {
     const uint8_t *prev_frame;          // last frame of the previous batch (concealment source for frame 0) or null
     uint8_t *state;                     // [sets][max_slices][3][state_stride]
     int16_t *ring;                      // [nseg*max_slices][4][3][ring_w]
+    const uint32_t *init_state;         // version 0/1: [nframes][3] range-coder low, range, bytes consumed behind the in-band header
     uint32_t *damaged;                  // [nframes][max_slices]: bit0 CRC mismatch, bit1 header/end-of-slice check failed
 };
 

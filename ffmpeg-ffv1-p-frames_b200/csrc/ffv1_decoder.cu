@@ -25,7 +25,9 @@ struct FFV1B200Decoder {
     DevBuf<uint64_t> d_pkt_off; PinnedBuf<uint64_t> h_pkt_off;
     DevBuf<uint32_t> d_slice_start, d_slice_size, d_damaged; PinnedBuf<uint32_t> h_slice_start, h_slice_size, h_damaged;
     DevBuf<int32_t> d_slice_count, d_seg_first, d_seg_set; PinnedBuf<int32_t> h_slice_count, h_seg_first, h_seg_set;
-    int nsets = 0, cur_set = 0;
+    DevBuf<uint32_t> d_init_state; PinnedBuf<uint32_t> h_init_state;
+    int nsets = 0, cur_set = 0, width = 0, height = 0;
+    bool configured = false;          // version 0/1 streams are configured by their first keyframe
     bool key_frame_ok = false, have_prev = false;
     int slice_count = 0;
     int64_t frame_bytes = 0;
@@ -37,27 +39,9 @@ int dfail(int code, const std::string &msg) { set_last_error(msg); return code; 
 #define CU_TRY(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) return dfail(FFV1B200_ERR_EXTERNAL, std::string(#expr) + ": " + cudaGetErrorString(e_)); } while (0)
 }
 
-extern "C" {
-
-int ffv1b200_dec_open(FFV1B200Decoder **out, const FFV1B200DecParams *p)
+// builds the device tables and buffers once the stream parameters are known
+static int configure(FFV1B200Decoder *d)
 {
-    if (!out || !p) return dfail(FFV1B200_ERR_EINVAL, "null argument");
-    *out = nullptr;
-    if (!p->extradata || p->extradata_size <= 0)
-        return dfail(FFV1B200_ERR_ENOSYS, "FFV1 version 0/1 streams (in-band header, no extradata) are not decoded by this build");
-    std::unique_ptr<FFV1B200Decoder> d(new FFV1B200Decoder());
-    std::string err;
-    int r = parse_extradata(p->extradata, p->extradata_size, p->width, p->height, d->cfg, err);
-    if (r < 0) return dfail(r, err);
-    int ndev = ffv1b200_device_count();
-    if (ndev < 0) return ndev;
-    if (p->device < 0 || p->device >= ndev) return dfail(FFV1B200_ERR_EINVAL, "no such CUDA device");
-    d->device = p->device;
-    d->max_batch = p->max_batch_frames > 0 ? p->max_batch_frames : 64;
-    CU_TRY(cudaSetDevice(d->device));
-    CU_TRY(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
-    for (auto &ev : d->ev) CU_TRY(cudaEventCreate(&ev));
-
     const Config &c = d->cfg;
     DecDeviceTables &t = d->tab;
     d->max_slices = c.slice_count();
@@ -80,13 +64,8 @@ int ffv1b200_dec_open(FFV1B200Decoder **out, const FFV1B200DecParams *p)
     t.frame_bytes = d->frame_bytes;
     const int maxctx = std::max(c.context_count[0], c.context_count[1]);
     t.state_stride = (int64_t)maxctx * 32;                    // golomb models need 8 bytes per context: fits as well
-    int maxw = 0;
-    for (int i = 0; i < d->max_slices; i++) { int x, y, w, h; slice_rect(c, i, &x, &y, &w, &h); maxw = std::max(maxw, w); }
-    // a slice header may announce any rectangle of the grid; the widest legal one is the frame width / 1 when the
-    // grid has one column.  Rows are sized for the widest grid cell plus one cell of slack.
-    t.ring_w = ((maxw + c.width / c.num_h_slices + 2 * kDecRingPad + 31) / 32) * 32;
-    t.ring_w = std::min(t.ring_w, ((c.width + 2 * kDecRingPad + 31) / 32) * 32);
-    t.ring_w = std::max(t.ring_w, ((maxw + 2 * kDecRingPad + 31) / 32) * 32);
+    // a slice header may announce any rectangle of the grid: rows are sized for the frame width
+    t.ring_w = ((c.width + 2 * kDecRingPad + 31) / 32) * 32;
 
     CU_TRY(d->d_quant.upload(&c.quant_tables[0][0][0], 2 * 5 * 256, d->stream));
     uint8_t lut[512];
@@ -108,7 +87,36 @@ int ffv1b200_dec_open(FFV1B200Decoder **out, const FFV1B200DecParams *p)
     CU_TRY(d->d_slice_count.alloc(F)); CU_TRY(d->h_slice_count.alloc(F));
     CU_TRY(d->d_seg_first.alloc(F + 1)); CU_TRY(d->h_seg_first.alloc(F + 1));
     CU_TRY(d->d_seg_set.alloc(F)); CU_TRY(d->h_seg_set.alloc(F));
+    CU_TRY(d->d_init_state.alloc(F * 3)); CU_TRY(d->h_init_state.alloc(F * 3));
     CU_TRY(cudaStreamSynchronize(d->stream));
+    d->configured = true;
+    return 0;
+}
+
+extern "C" {
+
+int ffv1b200_dec_open(FFV1B200Decoder **out, const FFV1B200DecParams *p)
+{
+    if (!out || !p) return dfail(FFV1B200_ERR_EINVAL, "null argument");
+    *out = nullptr;
+    if (p->width <= 0 || p->height <= 0) return dfail(FFV1B200_ERR_EINVAL, "invalid picture size");
+    std::unique_ptr<FFV1B200Decoder> d(new FFV1B200Decoder());
+    d->width = p->width; d->height = p->height;
+    const bool inband = !p->extradata || p->extradata_size <= 0;     // FFV1 version 0/1: parameters come with every keyframe
+    if (!inband) {
+        std::string err;
+        int r = parse_extradata(p->extradata, p->extradata_size, p->width, p->height, d->cfg, err);
+        if (r < 0) return dfail(r, err);
+    }
+    int ndev = ffv1b200_device_count();
+    if (ndev < 0) return ndev;
+    if (p->device < 0 || p->device >= ndev) return dfail(FFV1B200_ERR_EINVAL, "no such CUDA device");
+    d->device = p->device;
+    d->max_batch = p->max_batch_frames > 0 ? p->max_batch_frames : 64;
+    CU_TRY(cudaSetDevice(d->device));
+    CU_TRY(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+    for (auto &ev : d->ev) CU_TRY(cudaEventCreate(&ev));
+    if (!inband) { int r = configure(d.get()); if (r < 0) return r; }
     *out = d.release();
     return 0;
 }
@@ -141,12 +149,20 @@ int ffv1b200_dec_decode_host(FFV1B200Decoder *d, int n, const uint8_t *const *pk
 {
     if (!d || !pkt_data || !pkt_size || !out) return dfail(FFV1B200_ERR_EINVAL, "null argument");
     if (n < 1 || n > d->max_batch) return dfail(FFV1B200_ERR_EINVAL, "npackets outside 1..max_batch_frames");
-    if (out_cap < (size_t)n * d->frame_bytes) return dfail(FFV1B200_ERR_BUFFER_TOO_SMALL, "output buffer too small");
     CU_TRY(cudaSetDevice(d->device));
+    if (!d->configured) {
+        // version 0/1: the first keyframe carries the parameters (ffv1dec.c:646-696)
+        PrefixState ps; std::string err;
+        int r = parse_frame_prefix_v01(pkt_data[0], pkt_size[0], d->width, d->height, d->cfg, false, ps, err);
+        if (r < 0) return dfail(r, err);
+        if ((r = configure(d)) < 0) return r;
+    }
+    if (out_cap < (size_t)n * d->frame_bytes) return dfail(FFV1B200_ERR_BUFFER_TOO_SMALL, "output buffer too small (see ffv1b200_dec_info)");
     cudaStream_t s = d->stream;
     const Config &c = d->cfg;
     const int ms = d->max_slices;
     const int trailer = 3 + 5 * (c.ec ? 1 : 0);
+    const bool inband = c.version < 2;
 
     // ---- packet staging + slice tables (ffv1dec.c:924-937, 804-813, 948-989): host work is a few byte reads per slice
     size_t total = 0;
@@ -169,6 +185,21 @@ int ffv1b200_dec_decode_host(FFV1B200Decoder *d, int n, const uint8_t *const *pk
         // keyframe bit: get_rac on a fresh state 128 (range 0xFF00 -> range1 0x7F80)
         const unsigned low = (unsigned)pk[0] << 8 | pk[1];
         const bool key = low >= 0x7F80u;
+        if (inband) {
+            PrefixState ps; std::string err;
+            int r = parse_frame_prefix_v01(pk, (int)size, d->width, d->height, d->cfg, true, ps, err);
+            if (r < 0) return dfail(r, err);
+            d->h_init_state.p[f * 3 + 0] = ps.low; d->h_init_state.p[f * 3 + 1] = ps.range; d->h_init_state.p[f * 3 + 2] = ps.pos;
+            if (key) { scount = 1; kfo = true; }
+            else if (!kfo) return dfail(FFV1B200_ERR_INVALIDDATA, "Cannot decode non-keyframe without valid keyframe");
+            d->h_frame_key.p[f] = key ? 1 : 0;
+            d->h_slice_count.p[f] = 1;
+            d->h_slice_start.p[f * ms] = 0;
+            d->h_slice_size.p[f * ms] = (uint32_t)size;
+            if (f == 0 || key) d->h_seg_first.p[nseg++] = f;
+            if (key_flags) key_flags[f] = key ? 1 : 0;
+            continue;
+        }
         if (key) {
             const uint8_t *q = pk + size;
             int cnt = 0;
@@ -211,6 +242,7 @@ int ffv1b200_dec_decode_host(FFV1B200Decoder *d, int n, const uint8_t *const *pk
     CU_TRY(cudaMemcpyAsync(d->d_seg_first.p, d->h_seg_first.p, sizeof(int32_t) * (nseg + 1), cudaMemcpyHostToDevice, s));
     CU_TRY(cudaMemcpyAsync(d->d_seg_set.p, d->h_seg_set.p, sizeof(int32_t) * nseg, cudaMemcpyHostToDevice, s));
     CU_TRY(cudaMemsetAsync(d->d_damaged.p, 0, sizeof(uint32_t) * n * ms, s));
+    if (inband) CU_TRY(cudaMemcpyAsync(d->d_init_state.p, d->h_init_state.p, sizeof(uint32_t) * 3 * n, cudaMemcpyHostToDevice, s));
     // samples no slice covers (chroma columns cut off by a slice edge that is not on the chroma grid) stay 0
     CU_TRY(cudaMemsetAsync(d->d_out.p, 0, (size_t)n * d->frame_bytes, s));
 
@@ -219,7 +251,7 @@ int ffv1b200_dec_decode_host(FFV1B200Decoder *d, int n, const uint8_t *const *pk
     b.seg_first = d->d_seg_first.p; b.seg_set = d->d_seg_set.p; b.frame_key = d->d_frame_key.p;
     b.pkt = d->d_pkt.p; b.pkt_off = d->d_pkt_off.p; b.slice_start = d->d_slice_start.p; b.slice_size = d->d_slice_size.p;
     b.slice_count = d->d_slice_count.p; b.out = d->d_out.p; b.prev_frame = d->have_prev ? d->d_prev.p : nullptr;
-    b.state = d->d_state.p; b.ring = d->d_ring.p; b.damaged = d->d_damaged.p;
+    b.state = d->d_state.p; b.ring = d->d_ring.p; b.damaged = d->d_damaged.p; b.init_state = d->d_init_state.p;
 
     cudaEventRecord(d->ev[1], s);
     launch_dec_crc(d->tab, b, s);

@@ -191,6 +191,9 @@ public:
         return a;
     }
     bool bad = false;
+    int low() const { return low_; }
+    int range() const { return range_; }
+    const uint8_t *pos() const { return p_; }
 private:
     int low_ = 0, range_ = 0xFF00;
     const uint8_t *p_, *end_;
@@ -494,6 +497,61 @@ int parse_extradata(const uint8_t *d, int n, int width, int height, Config &c, s
     if (c.version != 3) { err = "only FFV1 version 3 extradata is supported"; return FFV1B200_ERR_ENOSYS; }
     if (!c.bits) c.bits = 8;
     if (!select_pix_fmt(c)) { err = "format not supported"; return FFV1B200_ERR_ENOSYS; }
+    return 0;
+}
+
+int parse_frame_prefix_v01(const uint8_t *pkt, int size, int width, int height, Config &c, bool have_config,
+                           PrefixState &ps, std::string &err)
+{
+    // decode_frame + read_header for version 0/1 streams (ffv1dec.c:920-937, 646-696, 788-795): keyframe bit, then on
+    // keyframes the whole parameter set, coded with the default state table by the slice coder itself
+    if (size < 2) { err = "packet too small"; return FFV1B200_ERR_INVALIDDATA; }
+    BinDecoder bd(pkt, size);
+    uint8_t keystate = 128;
+    ps.key = bd.get(&keystate) != 0;
+    if (ps.key) {
+        Config n;
+        n.width = width; n.height = height;
+        uint8_t st[kStateSlots];
+        memset(st, 128, sizeof(st));
+        n.version = bd.get_symbol(st, false);
+        if (n.version < 0 || n.version >= 2) { err = "Invalid version in frame header"; return FFV1B200_ERR_INVALIDDATA; }
+        n.ac = bd.get_symbol(st, false);
+        for (int i = 1; i < 256; i++)
+            n.state_transition[i] = (uint8_t)((n.ac == AC_RANGE_CUSTOM ? bd.get_symbol(st, true) : 0) + bd.one_state[i]);
+        n.colorspace = bd.get_symbol(st, false);
+        n.bits = n.version > 0 ? bd.get_symbol(st, false) : 8;
+        if (!n.bits) n.bits = 8;
+        n.chroma_planes = bd.get(st);
+        n.chroma_h_shift = bd.get_symbol(st, false);
+        n.chroma_v_shift = bd.get_symbol(st, false);
+        n.transparency = bd.get(st);
+        n.plane_count = 2 + n.transparency;
+        n.num_h_slices = n.num_v_slices = 1;
+        if ((unsigned)n.chroma_h_shift > 4U || (unsigned)n.chroma_v_shift > 4U || bd.bad) { err = "damaged frame header"; return FFV1B200_ERR_INVALIDDATA; }
+        int count = 1;
+        for (int i = 0; i < 5; i++) {
+            int r = read_quant_table(bd, n.quant_tables[0][i], count);
+            if (r < 0) { err = "read_quant_table error"; return FFV1B200_ERR_INVALIDDATA; }
+            count *= r;
+            if ((unsigned)count > 32768U) { err = "read_quant_table error"; return FFV1B200_ERR_INVALIDDATA; }
+        }
+        memcpy(n.quant_tables[1], n.quant_tables[0], sizeof(n.quant_tables[0]));
+        n.context_count[0] = n.context_count[1] = (count + 1) / 2;
+        n.context_model = 0;
+        if (!select_pix_fmt(n)) { err = "format not supported"; return FFV1B200_ERR_ENOSYS; }
+        if (have_config) {
+            // the device tables are built once: a stream that changes its parameters mid-way is refused
+            if (n.version != c.version || n.ac != c.ac || n.pix_fmt != c.pix_fmt || n.context_count[0] != c.context_count[0] ||
+                memcmp(n.quant_tables[0], c.quant_tables[0], sizeof(n.quant_tables[0])) || memcmp(n.state_transition, c.state_transition, 256)) {
+                err = "stream parameters changed at a keyframe"; return FFV1B200_ERR_ENOSYS;
+            }
+        } else
+            c = n;
+    } else if (!have_config) {
+        err = "Cannot decode non-keyframe without valid keyframe"; return FFV1B200_ERR_INVALIDDATA;
+    }
+    ps.low = (uint32_t)bd.low(); ps.range = (uint32_t)bd.range(); ps.pos = (uint32_t)(bd.pos() - pkt);
     return 0;
 }
 

@@ -143,6 +143,12 @@ int resolve_encoder(const EncOptions &o, Config &c, std::string &err);
 // read_extra_header + pix_fmt selection of read_header (version >= 2 streams)
 int parse_extradata(const uint8_t *data, int size, int width, int height, Config &c, std::string &err);
 
+// Version 0/1 streams carry their parameters in every keyframe, coded by slice 0's own range coder.  The host reads that
+// prefix (keyframe bit [+ header]) and hands the coder state behind it to the decode kernel.
+struct PrefixState { bool key; uint32_t low, range, pos; };
+int parse_frame_prefix_v01(const uint8_t *pkt, int size, int width, int height, Config &c, bool have_config,
+                           PrefixState &ps, std::string &err);
+
 std::vector<uint8_t> write_extradata(const Config &c);
 
 void default_state_tables(uint8_t zero_state[256], uint8_t one_state[256]);

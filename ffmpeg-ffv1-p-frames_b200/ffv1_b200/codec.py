@@ -326,10 +326,18 @@ class FFV1Decoder:
 
     def _decode_chunk(self, packets):
         n = len(packets)
-        fb = int(self.info.frame_bytes)
         bufs = [np.frombuffer(p, np.uint8) for p in packets]
         ptrs = (ctypes.c_void_p * n)(*[b.ctypes.data for b in bufs])
         sizes = (ctypes.c_int * n)(*[len(p) for p in packets])
+        if not self.info.frame_bytes:
+            # FFV1 version 0/1: the stream parameters arrive with the first keyframe; a probe call parses them
+            probe = np.empty(16, np.uint8)
+            r = lib().ffv1b200_dec_decode_host(self._h, n, ptrs, sizes, probe.ctypes.data, 0, None, None)
+            if r != ERR_BUFFER_TOO_SMALL:
+                _check(r)
+            _check(lib().ffv1b200_dec_info(self._h, ctypes.byref(self.info)))
+            self.pix_fmt = self.info.pix_fmt.decode()
+        fb = int(self.info.frame_bytes)
         out = np.empty(n * fb, np.uint8)
         keys = (ctypes.c_int * n)()
         dmg = (ctypes.c_uint64 * n)()

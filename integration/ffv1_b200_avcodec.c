@@ -256,10 +256,12 @@ static av_cold int b200_decode_init(AVCodecContext *avctx)
         return ret;
     }
     ffv1b200_dec_info(s->dec, &s->info);
-    avctx->pix_fmt = av_get_pix_fmt(s->info.pix_fmt);
-    avctx->bits_per_raw_sample = s->info.bits_per_raw_sample;
-    if (!(s->framebuf = av_malloc(s->info.frame_bytes)))
-        return AVERROR(ENOMEM);
+    if (s->info.frame_bytes) {                           /* version >= 2: everything is known from the extradata */
+        avctx->pix_fmt = av_get_pix_fmt(s->info.pix_fmt);
+        avctx->bits_per_raw_sample = s->info.bits_per_raw_sample;
+        if (!(s->framebuf = av_malloc(s->info.frame_bytes)))
+            return AVERROR(ENOMEM);
+    }
     return 0;
 }
 
@@ -271,6 +273,20 @@ static int b200_decode_frame(AVCodecContext *avctx, void *data, int *got_frame, 
     const uint8_t *src[4];
     int ls[4], key = 0, size = avpkt->size, ret;
     uint64_t damaged = 0;
+    if (!s->info.frame_bytes) {
+        /* version 0/1: parameters are carried by the first keyframe (ffv1dec.c:646-696); a probe call parses them */
+        uint8_t probe[16];
+        ret = ffv1b200_dec_decode_host(s->dec, 1, &pk, &size, probe, 0, NULL, NULL);
+        if (ret < 0 && ret != FFV1B200_ERR_BUFFER_TOO_SMALL) {
+            av_log(avctx, AV_LOG_ERROR, "ffv1_b200: %s\n", ffv1b200_last_error());
+            return ret;
+        }
+        ffv1b200_dec_info(s->dec, &s->info);
+        avctx->pix_fmt = av_get_pix_fmt(s->info.pix_fmt);
+        avctx->bits_per_raw_sample = s->info.bits_per_raw_sample;
+        if (!(s->framebuf = av_malloc(s->info.frame_bytes)))
+            return AVERROR(ENOMEM);
+    }
     if ((ret = ffv1b200_dec_decode_host(s->dec, 1, &pk, &size, s->framebuf, s->info.frame_bytes, &key, &damaged)) < 0) {
         av_log(avctx, AV_LOG_ERROR, "ffv1_b200: %s\n", ffv1b200_last_error());
         return ret;
