@@ -267,8 +267,28 @@ static int64_t mem_seek(void *opaque, int64_t off, int whence)
 }
 
 /* raw: nframes tightly packed frames in pix_fmt. Returns AVI size written into out, <0 on error. */
+static int64_t fate_avi_impl(AVCodec *codec, int batch, const uint8_t *raw, int nframes, int w, int h, const char *pix_fmt,
+                             int level, int slices, uint8_t *out, int64_t cap);
+
 int64_t ffv1ref_fate_avi(const uint8_t *raw, int nframes, int w, int h, const char *pix_fmt,
                          int level, int slices, uint8_t *out, int64_t cap)
+{
+    reg();
+    return fate_avi_impl(&ff_ffv1_encoder, 0, raw, nframes, w, h, pix_fmt, level, slices, out, cap);
+}
+
+/* the same FATE procedure with another registered encoder (the ffv1_b200 drop-in) */
+int64_t ffv1ref_fate_avi_named(const char *name, int batch, const uint8_t *raw, int nframes, int w, int h, const char *pix_fmt,
+                               int level, int slices, uint8_t *out, int64_t cap)
+{
+    reg();
+    AVCodec *codec = avcodec_find_encoder_by_name(name);
+    if (!codec) return -1;
+    return fate_avi_impl(codec, batch, raw, nframes, w, h, pix_fmt, level, slices, out, cap);
+}
+
+static int64_t fate_avi_impl(AVCodec *codec, int batch, const uint8_t *raw, int nframes, int w, int h, const char *pix_fmt,
+                             int level, int slices, uint8_t *out, int64_t cap)
 {
     static int fmt_registered;
     enum AVPixelFormat pf = av_get_pix_fmt(pix_fmt);
@@ -287,7 +307,7 @@ int64_t ffv1ref_fate_avi(const uint8_t *raw, int nframes, int w, int h, const ch
     oc->flags |= AVFMT_FLAG_BITEXACT;
     st = avformat_new_stream(oc, NULL);
 
-    enc = avcodec_alloc_context3(&ff_ffv1_encoder);
+    enc = avcodec_alloc_context3(codec);
     enc->width = w; enc->height = h; enc->pix_fmt = pf;
     enc->time_base = (AVRational){1, 25};
     enc->framerate = (AVRational){25, 1};
@@ -297,7 +317,8 @@ int64_t ffv1ref_fate_avi(const uint8_t *raw, int nframes, int w, int h, const ch
     enc->flags |= AV_CODEC_FLAG_BITEXACT;
     enc->sample_aspect_ratio = (AVRational){0, 1};
     if (oc->oformat->flags & AVFMT_GLOBALHEADER) enc->flags |= AV_CODEC_FLAG_GLOBAL_HEADER;
-    if ((ret = avcodec_open2(enc, &ff_ffv1_encoder, NULL)) < 0) return ret;
+    if (batch > 0) av_opt_set_int(enc->priv_data, "batch", batch, 0);
+    if ((ret = avcodec_open2(enc, codec, NULL)) < 0) return ret;
     /* ffmpeg.c init_output_stream: avcodec_parameters_from_context + time base / frame rate hints */
     avcodec_parameters_from_context(st->codecpar, enc);
     avcodec_copy_context(st->codec, enc);
@@ -329,6 +350,16 @@ int64_t ffv1ref_fate_avi(const uint8_t *raw, int nframes, int w, int h, const ch
             pkt.stream_index = 0;
             if ((ret = av_interleaved_write_frame(oc, &pkt)) < 0) return ret;
         }
+    }
+    for (;;) {                                       /* drain a delayed encoder (ffmpeg.c flush_encoders, 1698-1770) */
+        AVPacket pkt;
+        int got = 0;
+        av_init_packet(&pkt); pkt.data = NULL; pkt.size = 0;
+        if ((ret = avcodec_encode_video2(enc, &pkt, NULL, &got)) < 0) return ret;
+        if (!got) break;
+        av_packet_rescale_ts(&pkt, enc->time_base, st->time_base);
+        pkt.stream_index = 0;
+        if ((ret = av_interleaved_write_frame(oc, &pkt)) < 0) return ret;
     }
     av_write_trailer(oc);
     avio_flush(oc->pb);

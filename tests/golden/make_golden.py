@@ -32,3 +32,15 @@ out["s2_noisy1080_c2"] = run(1920, 1080, "yuv420p", dict(gop=16, level=3, coder=
 out["s2_noisy1080_c2"]["kind"] = "s2"
 json.dump(out, open(os.path.join(ROOT, "tests", "golden", "ref_packets.json"), "w"), indent=0, sort_keys=True)
 print("wrote", len(out), "cases")
+
+def fate_goldens(reference="/root/reference"):
+    """tests/golden/fate_vsynth.json: the md5 / size lines of the reference's own FATE goldens for this path
+    (tests/ref/vsynth/vsynth{1,2,3}-ffv1{,-v0,-v3-yuv420p}); test vectors only, used by tests/test_gpu_dropin_avcodec.py"""
+    import json, os
+    out = {}
+    for clip in ("vsynth1", "vsynth2", "vsynth3"):
+        for name in ("ffv1", "ffv1-v0", "ffv1-v3-yuv420p"):
+            lines = open(os.path.join(reference, "tests/ref/vsynth/%s-%s" % (clip, name))).read().split("\n")
+            out["%s-%s" % (clip, name)] = {"avi_md5": lines[0].split()[0], "avi_size": int(lines[1].split()[0]),
+                                           "decoded_md5": lines[2].split()[0]}
+    json.dump(out, open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "fate_vsynth.json"), "w"), indent=1, sort_keys=True)

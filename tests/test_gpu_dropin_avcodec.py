@@ -84,3 +84,32 @@ def test_decode_through_avcodec_api(lavc):
         assert r == pixfmt.frame_bytes(fmt, w, h) and name.value.decode() == fmt and bool(key.value) == pkts[i][1]
         assert np.array_equal(out[:r], np.ascontiguousarray(f).view(np.uint8).reshape(-1))
     lavc.ffv1ref_dec_close(hnd)
+
+FATE = [("ffv1", -1, 4), ("ffv1-v0", -1, 0), ("ffv1-v3-yuv420p", 3, 0)]       # tests/fate/vcodec.mak:113-118
+
+@pytest.mark.parametrize("clip", ["vsynth1", "vsynth3"])
+def test_fate_goldens_through_the_dropin(lavc, clip):
+    """FATE's enc_dec procedure (tests/fate-run.sh:171-193) with -c:v ffv1_b200: the reference's videogen clip, our encoder
+    behind the reference's libavcodec, the reference's AVI muxer -> the file must hash to the reference's own golden."""
+    import hashlib, json, subprocess, tempfile
+    gen = os.path.join(ROOT, "oracle", "_ref", "videogen")
+    if not os.path.exists(gen):
+        pytest.skip("oracle/_ref/videogen not built")
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "fate_vsynth.json")))
+    w, h = (352, 288) if clip == "vsynth1" else (34, 34)
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, clip + ".yuv")
+        subprocess.check_call([gen, path] + ([] if clip == "vsynth1" else ["34", "34"]))
+        raw = np.fromfile(path, np.uint8)
+    n = len(raw) // (w * h * 3 // 2)
+    assert n == 50
+    lavc.ffv1ref_fate_avi_named.restype = ctypes.c_int64
+    lavc.ffv1ref_fate_avi_named.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                            ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64]
+    for name, level, slices in FATE:
+        out = np.zeros(len(raw) + (4 << 20), np.uint8)
+        size = lavc.ffv1ref_fate_avi_named(b"ffv1_b200", 16, raw.ctypes.data, n, w, h, b"yuv420p", level, slices, out.ctypes.data, len(out))
+        g = gold["%s-%s" % (clip, name)]
+        assert size == g["avi_size"], (clip, name, size)
+        assert hashlib.md5(out[:size].tobytes()).hexdigest() == g["avi_md5"], (clip, name)
+        assert hashlib.md5(raw.tobytes()).hexdigest() == g["decoded_md5"]
