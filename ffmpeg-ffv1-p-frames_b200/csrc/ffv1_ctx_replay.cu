@@ -21,7 +21,7 @@ namespace ffv1 {
 
 constexpr int kHistThreads = 256;
 constexpr int kScatterThreads = 32 * kCtxTileLines;
-constexpr int kCtxThreads = 256;
+constexpr int kCtxThreads = 1024;
 constexpr int kMaxListCtx = 1024;
 
 __device__ __forceinline__ uint32_t cr_incl_scan(uint32_t v, int lane)
@@ -266,17 +266,18 @@ __device__ __forceinline__ void visit_step(uint16_t *addr, uint32_t val, uint32_
 }
 
 template <bool HIGH_E>
-__global__ void __launch_bounds__(kCtxThreads) k_replay_ctx(const EncDeviceTables T, const EncBatch B)
+__global__ void __launch_bounds__(kCtxThreads, 1) k_replay_ctx(const EncDeviceTables T, const EncBatch B)
 {
+    extern __shared__ __align__(16) unsigned char s_state_raw[];     // [ctx_count][32] the chain's model
     __shared__ uint8_t s_lut[512];
     __shared__ uint4 s_blk_all[kCtxThreads];
     __shared__ int s_next;
+    uint8_t *s_state = s_state_raw;
     const Layout &L = T.layout;
     const int tid = threadIdx.x, lane = tid & 31;
     uint4 *s_blk = s_blk_all + (tid & ~31);
     const uint32_t lut_base = (uint32_t)__cvta_generic_to_shared(s_lut);
     for (int i = tid; i < 512; i += kCtxThreads) s_lut[i] = T.trans_lut[i];
-    if (tid == 0) s_next = 0;
     if (B.status[0]) return;
     const int chain = blockIdx.x;
     const int pc = chain % L.npc, s = (chain / L.npc) % L.nslices, seg = chain / (L.npc * L.nslices);
@@ -286,14 +287,13 @@ __global__ void __launch_bounds__(kCtxThreads) k_replay_ctx(const EncDeviceTable
     const bool key = B.frame_key[f0] != 0;
     const bool hand_over = f1 == B.nframes;
     const size_t coff = ((size_t)s * L.npc + pc) * ((size_t)nctx * 32);
-    // contexts without symbols in this batch still hand their state to the next one
-    if (hand_over) {
+    // ---- the chain's model: 128 on keyframes (ffv1.c:177-202), else what the previous batch left
+    {
         const uint4 *cin4 = reinterpret_cast<const uint4 *>(B.carry_in + coff);
-        uint4 *cout4 = reinterpret_cast<uint4 *>(B.carry_out + coff);
+        uint4 *st4 = reinterpret_cast<uint4 *>(s_state);
         for (int i = tid; i < nctx * 2; i += kCtxThreads)
-            cout4[i] = key ? make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u) : cin4[i];
+            st4[i] = key ? make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u) : cin4[i];
     }
-    __syncthreads();
 
     const uint2 *chain_list = B.lists + (size_t)f0 * L.samples_per_frame + (size_t)(f1 - f0) * g.list_off[pc];
     const uint32_t *lstart = B.list_start + (size_t)chain * nctx;
@@ -302,17 +302,31 @@ __global__ void __launch_bounds__(kCtxThreads) k_replay_ctx(const EncDeviceTable
     uint16_t *dec_pc = B.dec + g.dec_off[pc];
     const int slot = slot_of_lane(lane);
     const uint32_t lanebit = 1u << lane, lt_mask = lanebit - 1u;
+    const int t0 = g.ct_first[pc];
 
-    for (;;) {
+    // Frame after frame: all warps of the CTA work on the same (chain, frame), so the decision region they scatter
+    // into (one frame of one slice-plane-context, < 1 MB) is completed while it is still in L2 -- with every list
+    // walked through all frames of the GOP at once, each 2..20-byte write was a read-modify-write in DRAM.
+    for (int f = f0; f < f1; f++) {
+      __syncthreads();                                              // model loaded / previous frame finished
+      if (tid == 0) s_next = 0;
+      __syncthreads();
+      // symbols of context c that precede frame f (f+1) inside the chain = scanned histogram of the chain's first tile
+      const uint32_t *before = B.ctx_hist + ((size_t)f * L.ctiles_per_frame + t0) * nctx;
+      const uint32_t *before_next = B.ctx_hist + ((size_t)(f + 1) * L.ctiles_per_frame + t0) * nctx;
+      for (;;) {
         int oi = 0;
         if (lane == 0) oi = atomicAdd(&s_next, 1);
         oi = __shfl_sync(0xFFFFFFFFu, oi, 0);
         if (oi >= nctx) break;
         const int c = order[oi];
-        const uint32_t n = lcount[c];
-        if (n == 0u) break;                                     // lists are ordered longest first
-        uint32_t st = key ? 128u : (uint32_t)B.carry_in[coff + (size_t)c * 32 + slot];
-        const uint2 *lp = chain_list + lstart[c];
+        const uint32_t ntot = lcount[c];
+        if (ntot == 0u) break;                                  // contexts are ordered by the length of their chain list
+        const uint32_t b0 = before[c], b1 = f + 1 < f1 ? before_next[c] : ntot;
+        const uint32_t n = b1 - b0;
+        if (n == 0u) continue;
+        uint32_t st = s_state[c * 32 + slot];
+        const uint2 *lp = chain_list + lstart[c] + b0;
         uint2 nx = lane < n ? lp[lane] : make_uint2(0u, 0u);
         for (uint32_t j0 = 0; j0 < n; j0 += 32u) {
             const uint32_t m = min(32u, n - j0);
@@ -328,6 +342,7 @@ __global__ void __launch_bounds__(kCtxThreads) k_replay_ctx(const EncDeviceTable
             const uint32_t rel = (uint32_t)(off - off0);
             const bool wide = __any_sync(0xFFFFFFFFu, lane < m && ((off - off0) >> 32) != 0ull);   // rare context, huge GOP
             uint16_t *o0 = dec_pc + off0;
+            asm volatile("" : "+l"(o0));                                    // keep the block base in one register pair
             // the block's (visit, bits, position) triples go through shared memory: one broadcast 16-byte load per symbol
             __syncwarp();
             s_blk[lane] = make_uint4(vis, bts, rel, 0u);
@@ -339,7 +354,8 @@ __global__ void __launch_bounds__(kCtxThreads) k_replay_ctx(const EncDeviceTable
                     const uint32_t idx = q.z + __popc(q.x & lt_mask);
                     const uint32_t bit = (q.y & lanebit) ? 0x100u : 0u;
                     // predicated (not branched): emit the decision and step the state only in the lanes the symbol visits
-                    visit_step(o0 + idx, st | bit, st, lut_base + bit + st, q.x & lanebit);
+                    visit_step(reinterpret_cast<uint16_t *>(reinterpret_cast<char *>(o0) + (size_t)idx * 2u), st | bit, st,
+                               lut_base + bit + st, q.x & lanebit);
                 }
             } else {
                 for (uint32_t k = 0; k < m; k++) {
@@ -373,7 +389,15 @@ __global__ void __launch_bounds__(kCtxThreads) k_replay_ctx(const EncDeviceTable
                 }
             }
         }
-        if (hand_over) B.carry_out[coff + (size_t)c * 32 + slot] = (uint8_t)st;
+        s_state[c * 32 + slot] = (uint8_t)st;
+      }
+    }
+    // ---- hand the model to the next batch when this segment runs to the end of the batch
+    __syncthreads();
+    if (hand_over) {
+        const uint4 *st4 = reinterpret_cast<const uint4 *>(s_state);
+        uint4 *cout4 = reinterpret_cast<uint4 *>(B.carry_out + coff);
+        for (int i = tid; i < nctx * 2; i += kCtxThreads) cout4[i] = st4[i];
     }
 }
 
@@ -399,8 +423,8 @@ void launch_ctx_replay(const EncDeviceTables &t, const EncBatch &b, cudaStream_t
     const int n = b.nframes * L.nslices * L.npc;
     k_dec_layout<<<(n + 127) / 128, 128, 0, s>>>(t, b);
     k_ctx_scatter<<<tiles, kScatterThreads, ctx_scatter_smem_bytes(L), s>>>(t, b);
-    if (L.coded_bits <= 10) k_replay_ctx<false><<<nchains, kCtxThreads, 0, s>>>(t, b);
-    else                    k_replay_ctx<true><<<nchains, kCtxThreads, 0, s>>>(t, b);
+    if (L.coded_bits <= 10) k_replay_ctx<false><<<nchains, kCtxThreads, L.ctx_count * 32, s>>>(t, b);
+    else                    k_replay_ctx<true><<<nchains, kCtxThreads, L.ctx_count * 32, s>>>(t, b);
 }
 
 } // namespace ffv1
