@@ -11,7 +11,8 @@
 //     which is what a byte extraction with PRMT (value << 8) yields for free;
 //   * each thread handles 8 consecutive samples held in registers and writes one 32-byte (256-bit) record vector.
 // Requirements checked on the host (else the generic kernel runs): 8- or 16-bit planar source, every source plane
-// 16-byte aligned with a 16-byte multiple linesize, every slice-plane starting at a multiple of 4 samples.
+// 16-byte aligned with a 16-byte multiple linesize, every slice-plane starting at a multiple of 4 samples and a
+// multiple of 8 samples wide.
 #include "ffv1_enc_kernels.cuh"
 #include <cuda.h>
 #include <cudaTypedefs.h>
@@ -49,6 +50,10 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase)
 {
     asm volatile(
@@ -72,6 +77,15 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
     uint32_t d;
     asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
     return d;
+}
+
+// 16-bit table read through a 32-bit shared-space address (+ compile-time offset): one LDS.S16, no address arithmetic
+template <int OFF>
+__device__ __forceinline__ int lds_s16(uint32_t saddr)
+{
+    short v;
+    asm("ld.shared.s16 %0, [%1+%2];" : "=h"(v) : "r"(saddr), "n"(OFF));
+    return (int)v;
 }
 
 struct FastItem {
@@ -177,10 +191,20 @@ k_pixel_fast(const EncDeviceTables T, const EncBatch B, const int maxchunks, con
     const int tid = threadIdx.x & (kFastGroup - 1), lane = tid & 31, warp = tid >> 5;
     const int group = threadIdx.x / kFastGroup;
     constexpr int kGroups = kFastThreads / kFastGroup;
-    unsigned char *tabAB = smem;
-    unsigned char *tabC = smem + kFastTabAB;
-    unsigned char *bufs = smem + kFastTabAB + (NIN == 5 ? kFastTabC : 0) + group * kFastBufs * G::kBufBytes;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kFastTabAB + (NIN == 5 ? kFastTabC : 0) + kGroups * kFastBufs * G::kBufBytes) + group * kFastBufs;
+    // Shared-memory map.  The (Q1,Q2 | Q0,Q3) table sits at a shared-space address that is a multiple of 64 KB, so that
+    // "(difference & 0xFF00) | lane offset | table base" is ONE LOP3 (no add): [group 0 buffers][table AB][table C]
+    // [group 1 buffers][mbarriers]
+    const uint32_t s0 = smem_u32(smem);
+    const uint32_t tab_s = (s0 + 0xFFFFu) & ~0xFFFFu;
+    if (tab_s - s0 < (uint32_t)(kFastBufs * G::kBufBytes)) __trap();         // the launch reserves 64 KB in front (see pixel_fast_smem_bytes)
+    unsigned char *tabAB = smem + (tab_s - s0);
+    unsigned char *tabC = tabAB + kFastTabAB;
+    unsigned char *after = tabC + (NIN == 5 ? kFastTabC : 0);
+    unsigned char *bufs = group == 0 ? smem : after;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(after + kFastBufs * G::kBufBytes) + group * 2 * kFastBufs;   // "full" barriers
+    uint64_t *empty = bars + kFastBufs;                                                                        // "empty" barriers
+    const uint32_t laneA = tab_s | ((uint32_t)(threadIdx.x & 31) * 4u);       // bits 8..15 are free for the table index
+    const uint32_t laneC = (tab_s + kFastTabAB) | ((uint32_t)(threadIdx.x & 31) * 4u);
 
     // ---- lane-replicated quantisation tables
     for (int i = threadIdx.x; i < 256 * 32; i += kFastThreads) {
@@ -192,7 +216,7 @@ k_pixel_fast(const EncDeviceTables T, const EncBatch B, const int maxchunks, con
         if (NIN == 5) *reinterpret_cast<uint32_t *>(tabC + e * 128 + l * 4) = (uint16_t)T.quant[1024 + e];
     }
     if (tid == 0) {
-        for (int i = 0; i < kFastBufs; i++) mbar_init(&bars[i], 1);
+        for (int i = 0; i < kFastBufs; i++) { mbar_init(&bars[i], 1); mbar_init(&empty[i], kFastGroup / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -200,7 +224,6 @@ k_pixel_fast(const EncDeviceTables T, const EncBatch B, const int maxchunks, con
     const int items_per_frame = L.tiles_per_frame * maxchunks;
     const long total = (long)items_per_frame * B.nframes;
     const int bits = L.coded_bits;
-    const uint32_t lane4 = (uint32_t)lane * 4u;
     const long step = (long)gridDim.x * kGroups;
 
     FastItem cur, pre;
@@ -215,12 +238,16 @@ k_pixel_fast(const EncDeviceTables T, const EncBatch B, const int maxchunks, con
                 else        fast_issue<BYTES>(T, B, pre, v, bufs + j * G::kBufBytes, &bars[j], lane);
             }
         }
+    // Producer / consumer ring without a group-wide barrier: a warp that has finished its units of an item moves on to
+    // the next item (already staged) at once; the issuing warp re-uses a buffer only after all 16 warps of the group
+    // have arrived on its "empty" barrier.
     int bi = 0, pi = kFastBufs - 1;           // buffer of the current item / of the item fetched now
-    uint32_t phase = 0;
-    for (; item < total; item += step) {
+    uint32_t phase = 0, ephase = 0;           // parity of full[bi] / of empty[pi]
+    for (int k = 0; item < total; item += step, k++) {
         unsigned char *buf = bufs + bi * G::kBufBytes;
         const long pitem = item + (kFastBufs - 1) * step;
         if (warp == 0 && pitem < total) {
+            if (k > 0) mbar_wait(&empty[pi], ephase);           // item k-1 (same buffer) has been consumed by every warp
             const bool v = fast_decode<BYTES>(T, pitem, items_per_frame, maxchunks, pre);
             if (TENSOR) fast_issue_tensor<BYTES>(T, maps, pre, v, bufs + pi * G::kBufBytes, &bars[pi], lane);
             else        fast_issue<BYTES>(T, B, pre, v, bufs + pi * G::kBufBytes, &bars[pi], lane);
@@ -309,32 +336,26 @@ k_pixel_fast(const EncDeviceTables T, const EncBatch B, const int maxchunks, con
 #undef S16
                 }
                 // slice-local right edge: RT of the last sample = its T
-                const bool lastu = cur.last_chunk && ux == upr - 1;
-                if ((cur.cw & (U - 1)) == 0) {                 // (uniform) the usual geometry: the row ends with a full unit
-                    if (lastu) Tt[U + 1] = Tt[U];
-                } else if (lastu) {
-                    const int il = (cur.cw - 1) & (U - 1);
-#pragma unroll
-                    for (int i = 0; i < U - 1; i++) if (il == i) Tt[i + 2] = Tt[i + 1];
-                }
+                // (pixel_fast_geometry_ok guarantees that rows end with a full unit)
+                if (cur.last_chunk && ux == upr - 1) Tt[U + 1] = Tt[U];
                 uint32_t out[U];
                 // Q1 term of sample i uses the difference LT-T = Tt[i]-Tt[i+1]; the same difference is the T-RT term
                 // (Q2) of sample i-1, so one address serves both tables (A holds Q1 low, Q2 high)
-                uint32_t aA = ((uint32_t)(Tt[0] - Tt[1]) & 0xFF00u) | lane4;
-                int q1 = *reinterpret_cast<const volatile int16_t *>(tabAB + aA);       // volatile: keep the two halves as two
-                int Lv = Lx, LLv = LLx;                                                  // LDS.S16 (LSU) instead of LDS + 2 PRMT (ALU)
+                uint32_t aA = ((uint32_t)(Tt[0] - Tt[1]) & 0xFF00u) | laneA;
+                int q1 = lds_s16<0>(aA);
+                int Lv = Lx, LLv = LLx;
 #pragma unroll
                 for (int i = 0; i < U; i++) {
                     const int LT = Tt[i], Tp = Tt[i + 1], RT = Tt[i + 2];
-                    aA = ((uint32_t)(Tp - RT) & 0xFF00u) | lane4;
-                    const int q2 = *reinterpret_cast<const volatile int16_t *>(tabAB + aA + 2);
-                    const uint32_t aB = ((uint32_t)(Lv - LT) & 0xFF00u) | lane4;
-                    int ctx = *reinterpret_cast<const int16_t *>(tabAB + aB + 128) + q1 + q2;
-                    q1 = *reinterpret_cast<const volatile int16_t *>(tabAB + aA);
+                    aA = ((uint32_t)(Tp - RT) & 0xFF00u) | laneA;
+                    const int q2 = lds_s16<2>(aA);
+                    const uint32_t aB = ((uint32_t)(Lv - LT) & 0xFF00u) | laneA;
+                    int ctx = lds_s16<128>(aB) + q1 + q2;
+                    q1 = lds_s16<0>(aA);
                     if (NIN == 5) {
-                        const uint32_t a3 = ((uint32_t)(LLv - Lv) & 0xFF00u) | lane4;
-                        const uint32_t a4 = (((uint32_t)(TT[i] - Tp) >> 1) & 0x7F80u) | lane4;
-                        ctx += *reinterpret_cast<const int16_t *>(tabAB + a3 + 130) + *reinterpret_cast<const int16_t *>(tabC + a4);
+                        const uint32_t a3 = ((uint32_t)(LLv - Lv) & 0xFF00u) | laneA;
+                        const uint32_t a4 = (((uint32_t)(TT[i] - Tp) >> 1) & 0x7F80u) | laneC;
+                        ctx += lds_s16<130>(a3) + lds_s16<0>(a4);
                     }
                     const int pred = max(min(Lv, Tp), min(max(Lv, Tp), Lv + Tp - LT));     // median (mathops.h:95-119)
                     int diff = X[i] - pred;                                                // residual * 256
@@ -357,8 +378,10 @@ k_pixel_fast(const EncDeviceTables T, const EncBatch B, const int maxchunks, con
                              : "memory");
             }
         }
-        // the group is done with this buffer: two items later the TMA unit may overwrite it
-        asm volatile("bar.sync %0, %1;" :: "r"(group + 1), "r"(kFastGroup) : "memory");
+        // this warp is done with the buffer
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[bi]);
+        if (k > 0 && pi == kFastBufs - 1) ephase ^= 1u;        // empty[] parity flips once per trip round the ring
         pi = bi;
         if (++bi == kFastBufs) { bi = 0; phase ^= 1u; }
     }
@@ -368,7 +391,8 @@ int pixel_fast_smem_bytes(const Layout &L)
 {
     const int bytes = L.src_kind == SRC_PLANAR16 ? 2 : 1;
     const int buf = bytes == 2 ? FastGeom<2>::kBufBytes : FastGeom<1>::kBufBytes;
-    return kFastTabAB + (L.ctx_inputs == 5 ? kFastTabC : 0) + (kFastThreads / kFastGroup) * kFastBufs * buf + 64 + 1024;
+    // 64 KB in front of the 64 KB-aligned table (holds group 0's buffers) + tables + group 1's buffers + mbarriers
+    return 65536 + kFastTabAB + (L.ctx_inputs == 5 ? kFastTabC : 0) + kFastBufs * buf + 256;
 }
 
 // static part of the eligibility test (geometry); pointer / linesize alignment is checked per call by the host
@@ -379,7 +403,7 @@ bool pixel_fast_geometry_ok(const Layout &L, const SliceGeom *slices, int nslice
         if (L.plane[p].pstep != (L.src_kind == SRC_PLANAR16 ? 2 : 1)) return false;          // ya8 interleaves two planes
     for (int s = 0; s < nslices; s++)
         for (int p = 0; p < L.nplanes; p++)
-            if (slices[s].px0[p] & 3) return false;
+            if ((slices[s].px0[p] & 3) || (slices[s].pw[p] & 7)) return false;      // 4-byte aligned starts, rows of whole 8-sample units
     return true;
 }
 
@@ -441,7 +465,7 @@ static void launch_t(const EncDeviceTables &t, const EncBatch &b, int maxchunks,
         const cuuint32_t estr[3] = {1u, 1u, 1u};
         if (strides[1] & 15) { tensor = false; break; }
         CUresult r = enc(&maps.m[sp], CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<uint8_t *>(frame0_planes[sp]), dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) tensor = false;
     }
