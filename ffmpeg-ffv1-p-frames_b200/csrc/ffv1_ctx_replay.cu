@@ -20,7 +20,7 @@
 namespace ffv1 {
 
 constexpr int kHistThreads = 256;
-constexpr int kScatterThreads = 32 * kCtxTileLines;
+constexpr int kScatterThreads = 128;                     // four tiles (one warp each) per CTA
 constexpr int kCtxThreads = 1024;
 constexpr int kMaxListCtx = 1024;
 
@@ -32,6 +32,19 @@ __device__ __forceinline__ uint32_t cr_incl_scan(uint32_t v, int lane)
         if (lane >= d) v += n;
     }
     return v;
+}
+
+// lanes (among `active`) holding the same 10-bit key as the caller: ten ballots (match.any is far slower here)
+__device__ __forceinline__ uint32_t same_key_lanes(uint32_t key, uint32_t active)
+{
+    uint32_t grp = active;
+#pragma unroll
+    for (int b = 0; b < 10; b++) {
+        const bool bit = (key >> b) & 1u;
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, bit);
+        grp &= bit ? m : ~m;
+    }
+    return grp;
 }
 
 __device__ __forceinline__ uint32_t decisions_of(int d)
@@ -87,10 +100,14 @@ __global__ void __launch_bounds__(256) k_ctx_scan(const EncDeviceTables T, const
         uint32_t run = 0;
         for (int f = f0; f < f1; f++) {
             uint32_t *h = B.ctx_hist + ((size_t)f * L.ctiles_per_frame + t0) * nctx + c;
-            for (int t = 0; t < nt; t++) {
-                const uint32_t v = h[(size_t)t * nctx];
-                h[(size_t)t * nctx] = run;
-                run += v;
+            // loads first, then the running sum and the stores: eight independent loads are in flight at a time
+            for (int tb = 0; tb < nt; tb += 8) {
+                uint32_t v[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) v[k] = tb + k < nt ? h[(size_t)(tb + k) * nctx] : 0u;
+#pragma unroll
+                for (int k = 0; k < 8; k++)
+                    if (tb + k < nt) { h[(size_t)(tb + k) * nctx] = run; run += v[k]; }
             }
         }
         s_total[c] = run;
@@ -139,18 +156,25 @@ __global__ void __launch_bounds__(128) k_dec_layout(const EncDeviceTables T, con
     uint32_t *run_cnt = B.run_cnt + (size_t)f * L.runs_per_frame + g.run_first;
     uint32_t pos = 0, run_start = 0, cur_run = T.lines[g.line_first + my_lines[0]].run;
     unsigned long long ndec = 0;
-    for (int i = 0; i < nl; i++) {
-        const int line = my_lines[i];
-        const uint32_t run = T.lines[g.line_first + line].run;
-        if (run != cur_run) {                                   // a run of this plane context ended: next one starts 16 B aligned
-            run_cnt[cur_run] = pos - run_start;
-            pos = (pos + 7u) & ~7u;
-            run_start = pos; cur_run = run;
+    for (int ib = 0; ib < nl; ib += 8) {
+        // the loads of eight lines are issued together; only the running position is sequential
+        int line[8]; uint32_t run[8], nd[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) line[k] = ib + k < nl ? my_lines[ib + k] : my_lines[nl - 1];
+#pragma unroll
+        for (int k = 0; k < 8; k++) { run[k] = T.lines[g.line_first + line[k]].run; nd[k] = line_pos[line[k]]; }
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            if (ib + k >= nl) break;
+            if (run[k] != cur_run) {                            // a run of this plane context ended: next one starts 16 B aligned
+                run_cnt[cur_run] = pos - run_start;
+                pos = (pos + 7u) & ~7u;
+                run_start = pos; cur_run = run[k];
+            }
+            line_pos[line[k]] = pos;
+            pos += nd[k];
+            ndec += nd[k];
         }
-        const uint32_t nd = line_pos[line];
-        line_pos[line] = pos;
-        pos += nd;
-        ndec += nd;
     }
     run_cnt[cur_run] = pos - run_start;
     atomicAdd(&B.status[3], ndec);
@@ -161,67 +185,60 @@ __global__ void __launch_bounds__(128) k_dec_layout(const EncDeviceTables T, con
 }
 
 // ------------------------------------------------------------------------------------------------ k_ctx_scatter
+// One warp per context tile; its lines are walked in coding order with one running list position per context in
+// shared memory (initialised from k_ctx_scan's tile bases), so the scatter is stable by construction: inside a
+// 32-sample group match.any ranks order the samples of a context, the leader advances the context's position.
 __global__ void __launch_bounds__(kScatterThreads) k_ctx_scatter(const EncDeviceTables T, const EncBatch B)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint32_t *s_off = reinterpret_cast<uint32_t *>(smem_raw);           // [kCtxTileLines][nctx]
     const Layout &L = T.layout;
     if (B.status[0]) return;
-    const CtxTile ct = T.ctiles[blockIdx.x];
+    const int nctx = L.ctx_count, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tile = blockIdx.x * (kScatterThreads / 32) + warp;
+    if (tile >= L.ctiles_per_frame) return;
+    uint32_t *s_off = reinterpret_cast<uint32_t *>(smem_raw) + warp * nctx;       // [nctx] next list position per context
+    const CtxTile ct = T.ctiles[tile];
     const int f = blockIdx.y;
     const SliceGeom &g = T.slices[ct.slice];
-    const int nctx = L.ctx_count, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
-    for (int i = tid; i < kCtxTileLines * nctx; i += kScatterThreads) s_off[i] = 0;
-    __syncthreads();
+    const int seg = B.frame_seg[f];
+    const int f0 = B.seg_first[seg], seglen = B.seg_first[seg + 1] - f0;
+    const int chain = (seg * L.nslices + ct.slice) * L.npc + ct.pc;
+    {
+        const uint32_t *tile_base = B.ctx_hist + ((size_t)f * L.ctiles_per_frame + tile) * nctx;
+        const uint32_t *lstart = B.list_start + (size_t)chain * nctx;
+        for (int c = lane; c < nctx; c += 32) s_off[c] = tile_base[c] + lstart[c];
+    }
+    __syncwarp();
     const uint32_t *rec_slice = B.rec + (size_t)f * L.rec_per_frame + g.rec_first;
     const int32_t *my_lines = T.pc_lines + g.pc_line_first[ct.pc] + ct.first;
-    int line = 0;
-    LineDesc ld;
-    ld.w = 0; ld.rec_off = 0;
-    if (warp < ct.nlines) { line = my_lines[warp]; ld = T.lines[g.line_first + line]; }
-    const uint32_t *recp = rec_slice + ld.rec_off;
-    uint32_t *my_off = s_off + warp * nctx;
-    // ---- phase 1: context histogram of every line (one warp per line, no atomics: the row belongs to the warp)
-    for (int x0 = 0; x0 < ld.w; x0 += 32) {
-        const bool act = x0 + lane < ld.w;
-        const uint32_t ctx = act ? recp[x0 + lane] >> 16 : 0u;
-        const uint32_t grp = __match_any_sync(0xFFFFFFFFu, act ? ctx : 0x10000u + lane);
-        if (act && (grp & lt_mask) == 0u) my_off[ctx] += __popc(grp);
-        __syncwarp();
-    }
-    __syncthreads();
-    // ---- phase 2: line histograms -> list positions (tile base from k_ctx_scan + lines above inside the tile)
-    {
-        const int seg = B.frame_seg[f];
-        const int f0 = B.seg_first[seg], seglen = B.seg_first[seg + 1] - f0;
-        const int chain = (seg * L.nslices + ct.slice) * L.npc + ct.pc;
-        const uint32_t *tile_base = B.ctx_hist + ((size_t)f * L.ctiles_per_frame + blockIdx.x) * nctx;
-        const uint32_t *lstart = B.list_start + (size_t)chain * nctx;
-        for (int c = tid; c < nctx; c += kScatterThreads) {
-            uint32_t base = tile_base[c] + lstart[c];
-            for (int l = 0; l < ct.nlines; l++) {
-                const uint32_t v = s_off[l * nctx + c];
-                s_off[l * nctx + c] = base;
-                base += v;
-            }
-        }
-        __syncthreads();
-        // ---- phase 3: stable scatter, coding order preserved inside every context
-        if (warp < ct.nlines) {
-            uint2 *list = B.lists + (size_t)f0 * L.samples_per_frame + (size_t)seglen * g.list_off[ct.pc];
-            uint32_t pos = B.line_pos[(size_t)f * L.lines_per_frame + g.line_first + line];
-            for (int x0 = 0; x0 < ld.w; x0 += 32) {
+    uint2 *list = B.lists + (size_t)f0 * L.samples_per_frame + (size_t)seglen * g.list_off[ct.pc];
+    const uint32_t *line_pos = B.line_pos + (size_t)f * L.lines_per_frame + g.line_first;
+    for (int l = 0; l < ct.nlines; l++) {
+        const int line = my_lines[l];
+        const LineDesc ld = T.lines[g.line_first + line];
+        const uint32_t *recp = rec_slice + ld.rec_off;
+        uint32_t pos = line_pos[line];
+        // 256 samples at a time: the eight loads of a chunk are in flight together (one load per 32-sample group
+        // exposed the full memory latency every ~150 instructions)
+        for (int xc = 0; xc < ld.w; xc += 256) {
+            uint32_t rr[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) rr[k] = xc + k * 32 + lane < ld.w ? recp[xc + k * 32 + lane] : 0u;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int x0 = xc + k * 32;
+                if (x0 >= ld.w) break;
                 const bool act = x0 + lane < ld.w;
-                const uint32_t r = act ? recp[x0 + lane] : 0u;
+                const uint32_t r = rr[k];
                 const uint32_t ctx = r >> 16;
                 const uint32_t nd = act ? decisions_of((int)(int16_t)(r & 0xFFFFu)) : 0u;
                 const uint32_t incl = cr_incl_scan(nd, lane);
-                const uint32_t grp = __match_any_sync(0xFFFFFFFFu, act ? ctx : 0x10000u + lane);
+                const uint32_t grp = same_key_lanes(ctx, __ballot_sync(0xFFFFFFFFu, act));       // contexts of this path are < 1024
                 const uint32_t rank = __popc(grp & lt_mask);
-                if (act) list[my_off[ctx] + rank] = make_uint2(pos + incl - nd, (r & 0xFFFFu) | ((uint32_t)f << 16));
+                if (act) list[s_off[ctx] + rank] = make_uint2(pos + incl - nd, (r & 0xFFFFu) | ((uint32_t)f << 16));
                 __syncwarp();
-                if (act && rank == 0u) my_off[ctx] += __popc(grp);
+                if (act && rank == 0u) s_off[ctx] += __popc(grp);
                 __syncwarp();
                 pos += __shfl_sync(0xFFFFFFFFu, incl, 31);
             }
@@ -406,7 +423,7 @@ bool ctx_replay_supported(const Layout &L)
     return !L.golomb && L.ctx_count <= kMaxListCtx;
 }
 
-int ctx_scatter_smem_bytes(const Layout &L) { return kCtxTileLines * L.ctx_count * 4; }
+int ctx_scatter_smem_bytes(const Layout &L) { return (kScatterThreads / 32) * L.ctx_count * 4; }
 
 cudaError_t configure_ctx_replay(const Layout &L)
 {
@@ -422,7 +439,8 @@ void launch_ctx_replay(const EncDeviceTables &t, const EncBatch &b, cudaStream_t
     k_ctx_scan<<<nchains, 256, 0, s>>>(t, b);
     const int n = b.nframes * L.nslices * L.npc;
     k_dec_layout<<<(n + 127) / 128, 128, 0, s>>>(t, b);
-    k_ctx_scatter<<<tiles, kScatterThreads, ctx_scatter_smem_bytes(L), s>>>(t, b);
+    dim3 stiles((L.ctiles_per_frame + kScatterThreads / 32 - 1) / (kScatterThreads / 32), b.nframes);
+    k_ctx_scatter<<<stiles, kScatterThreads, ctx_scatter_smem_bytes(L), s>>>(t, b);
     if (L.coded_bits <= 10) k_replay_ctx<false><<<nchains, kCtxThreads, L.ctx_count * 32, s>>>(t, b);
     else                    k_replay_ctx<true><<<nchains, kCtxThreads, L.ctx_count * 32, s>>>(t, b);
 }
