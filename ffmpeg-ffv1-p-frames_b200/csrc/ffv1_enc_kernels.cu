@@ -488,89 +488,135 @@ void launch_replay(const EncDeviceTables &t, const EncBatch &b, cudaStream_t s)
 
 // =================================================================================================
 // k_rangecode: one interval coder per (frame, slice); put_rac / renorm_encoder / ff_rac_terminate
-// (rangecoder.h:52-102, rangecoder.c:104-116).  The adaptive part already happened in k_replay, so a step is
+// (rangecoder.h:52-102, rangecoder.c:104-116).  The adaptive part already happened in the state replay, so a step is
 // range1 = range*p >> 8 plus the carry-propagating byte output.
 // =================================================================================================
-// Carry handling follows renorm_encoder (rangecoder.h:52-75) with one simplification that keeps the output identical:
-// instead of an "no outstanding byte yet" state, the coder starts with a dummy outstanding byte that is written to the
-// kScratchLead-1'th byte of the slice's scratch region and never read back (a carry into it is harmless), so the
-// payload starts at byte kScratchLead.  Bytes are shifted into a 32-bit word and stored four at a time.
+// Every lane of a warp runs its own coder, and the warp stays converged: the hot loop has no data-dependent branch
+// except two rare ones (a 0xFF byte waiting for its carry, the end of a run of decisions).
+//  * The decision stream of a lane is produced by a small generator (prefix | runs of its slice | closing decision) that
+//    runs four 16-byte vectors ahead of the coder, across run boundaries, so the coder never waits for a run switch.
+//  * A vector holds 8 decisions; entries behind the end of a run are replaced by 0x0000, which is an exact no-op for
+//    the coder (p = 0, bit = 0: range1 = 0, nothing moves, no renormalisation; real states are 1..255).
+//  * Carry handling follows renorm_encoder (rangecoder.h:52-75) with one simplification that keeps the output identical:
+//    instead of a "no outstanding byte yet" state the coder starts with a dummy outstanding byte that lands in byte
+//    kScratchLead-1 of the slice's scratch region and is never read back (a carry into it is harmless), so the payload
+//    starts at byte kScratchLead.  In the common case a renormalisation emits exactly one byte (outstanding byte +
+//    carry); bytes are shifted into a 32-bit word and stored four at a time.
 struct Rac {
     uint32_t low, range;
     uint32_t out_byte;   // outstanding byte (its final value depends on a carry that may still arrive)
     uint32_t out_count;  // 0xFF bytes behind it that a carry would turn into 0x00
-    uint32_t *buf;
+    uint32_t *wptr;      // next 32-bit word of the slice's scratch region
     uint32_t pos, cap, acc;
+    uint32_t room;       // 1 while a whole vector of decisions cannot overrun the scratch region (checked per vector)
 };
 
 __device__ __forceinline__ void rac_emit(Rac &c, uint32_t b)
 {
     c.acc = __funnelshift_r(c.acc, b, 8);                 // (acc >> 8) | (b << 24): little-endian word assembly
     c.pos++;
-    if ((c.pos & 3u) == 0u && c.pos <= c.cap) c.buf[(c.pos >> 2) - 1u] = c.acc;
+    if ((c.pos & 3u) == 0u) { if (c.pos <= c.cap) *c.wptr = c.acc; c.wptr++; }
 }
 
-__device__ __forceinline__ void rac_shift(Rac &c)
+// the uncommon renormalisations (renorm_encoder, rangecoder.h:52-75): a 0xFF byte that has to wait for its carry, or
+// the byte that resolves such a wait.  Out of line on purpose (all state by value, so it stays in registers): as a
+// predicated call the straight-line path of k_rangecode never has to jump over this code.
+struct RacOut { uint32_t out_byte, out_count, acc, pos; uint32_t *wptr; };
+
+__device__ __noinline__ RacOut rac_output_slow(uint32_t low, uint32_t wait, uint32_t out_byte, uint32_t out_count, uint32_t acc,
+                                               uint32_t pos, uint32_t cap, uint32_t *wptr)
 {
-    if (c.low <= 0xFF00u) {                               // common case: no carry, byte below 0xFF
-        rac_emit(c, c.out_byte);
-        if (c.out_count) { do rac_emit(c, 0xFFu); while (--c.out_count); }
-        c.out_byte = c.low >> 8;
-    } else if (c.low >= 0x10000u) {                       // carry
-        rac_emit(c, (c.out_byte + 1u) & 0xFFu);
-        if (c.out_count) { do rac_emit(c, 0x00u); while (--c.out_count); }
-        c.out_byte = (c.low >> 8) & 0xFFu;
-    } else {
-        c.out_count++;
+    RacOut o;
+    if (wait) { o.out_byte = out_byte; o.out_count = out_count + 1u; o.acc = acc; o.pos = pos; o.wptr = wptr; return o; }
+    Rac c;
+    c.out_byte = out_byte; c.out_count = out_count; c.acc = acc; c.pos = pos; c.cap = cap; c.wptr = wptr;
+    const uint32_t carry = low >> 16;
+    rac_emit(c, c.out_byte + carry);
+    const uint32_t fill = carry ? 0x00u : 0xFFu;
+#pragma unroll 1
+    do rac_emit(c, fill); while (--c.out_count);
+    o.out_byte = (low >> 8) & 0xFFu; o.out_count = 0u; o.acc = c.acc; o.pos = c.pos; o.wptr = c.wptr;
+    return o;
+}
+
+// Byte output of a renormalisation (sh = 1; `low` is the value before the shift).  The common case -- exactly one
+// byte, the outstanding byte plus the carry -- is predicated, not branched, so the 32 coders of a warp stay converged;
+// only a 0xFF byte waiting for its carry (about one renormalisation in 128) leaves the straight line.
+__device__ __forceinline__ void rac_output(Rac &c, uint32_t low, uint32_t sh)
+{
+    uint32_t slow, wait;
+    asm("{\n\t.reg .pred w, s;\n\t.reg .u32 t;\n\t"
+        "sub.u32 t, %3, 0xFF01;\n\t"
+        "setp.lt.u32 w, t, 0xFF;\n\t"                       // 0xFF00 < low < 0x10000: the byte is 0xFF, a carry may still flip it
+        "selp.u32 %1, 1, 0, w;\n\t"
+        "setp.ne.or.u32 w, %4, 0, w;\n\t"                   // ... or such bytes are still waiting
+        "setp.ne.and.u32 s, %2, 0, w;\n\t"
+        "selp.u32 %0, 1, 0, s;\n\t}"
+        : "=r"(slow), "=r"(wait) : "r"(sh), "r"(low), "r"(c.out_count));
+    if (__builtin_expect(slow != 0u, 0)) {
+        const RacOut o = rac_output_slow(low, wait, c.out_byte, c.out_count, c.acc, c.pos, c.cap, c.wptr);
+        c.out_byte = o.out_byte; c.out_count = o.out_count; c.acc = o.acc; c.pos = o.pos; c.wptr = o.wptr;
     }
-    c.low = (c.low & 0xFFu) << 8;
+    const uint32_t fast = sh & (slow ^ 1u);
+    asm volatile("{\n\t.reg .pred f, st;\n\t.reg .u32 t, b;\n\t"
+        "setp.ne.u32 f, %4, 0;\n\t"
+        "shr.u32 t, %5, 16;\n\t"
+        "add.u32 b, %1, t;\n\t"                             // outstanding byte + carry
+        "@f shf.r.wrap.b32 %0, %0, b, 8;\n\t"               // acc = acc >> 8 | byte << 24
+        "@f prmt.b32 %1, %5, 0, 0x4441;\n\t"                // outstanding byte = (low >> 8) & 0xFF
+        "@f add.u32 %2, %2, 1;\n\t"
+        "and.b32 t, %2, 3;\n\t"
+        "setp.eq.and.u32 st, t, 0, f;\n\t"
+        "setp.ne.and.u32 st, %6, 0, st;\n\t"
+        "@st st.global.u32 [%3], %0;\n\t"
+        "setp.eq.and.u32 st, t, 0, f;\n\t"
+        "@st add.u64 %3, %3, 4;\n\t}"
+        : "+r"(c.acc), "+r"(c.out_byte), "+r"(c.pos), "+l"(c.wptr) : "r"(fast), "r"(low), "r"(c.room) : "memory");
+}
+
+// put_rac (rangecoder.h:85-102) for one decision: p24 = probability state << 24, one = coded bit (any non-zero value)
+__device__ __forceinline__ void rac_code(Rac &c, uint32_t p24, uint32_t one)
+{
+    uint32_t low_before, sh;
+    asm("{\n\t.reg .pred one, sh;\n\t.reg .u32 r1, r0;\n\t"
+        "mul.hi.u32 r1, %1, %4;\n\t"                        // (range * p) >> 8
+        "sub.u32 r0, %1, r1;\n\t"
+        "setp.ne.u32 one, %5, 0;\n\t"
+        "selp.u32 %1, r1, r0, one;\n\t"
+        "@one add.u32 %0, %0, r0;\n\t"
+        "mov.u32 %2, %0;\n\t"
+        "setp.lt.u32 sh, %1, 0x100;\n\t"                    // p >= 1 and range >= 0x100 before: at most one shift
+        "selp.u32 %3, 1, 0, sh;\n\t"
+        "@sh shl.b32 %1, %1, 8;\n\t"
+        "@sh prmt.b32 %0, %0, 0, 0x4404;\n\t}"              // low = (low & 0xFF) << 8
+        : "+r"(c.low), "+r"(c.range), "=r"(low_before), "=r"(sh) : "r"(p24), "r"(one));
+    rac_output(c, low_before, sh);
+}
+
+__device__ __forceinline__ void rac_shift(Rac &c)         // forced renormalisation (termination only)
+{
+    const uint32_t low = c.low;
+    c.low = (low & 0xFFu) << 8;
     c.range <<= 8;
+    rac_output(c, low, 1u);
 }
 
-// put_rac (rangecoder.h:85-102) for the decision in bits [SH, SH+9) of `word`; the state update already happened in k_replay
-template <int SH>
-__device__ __forceinline__ void rac_code(Rac &c, uint32_t word)
+__device__ __forceinline__ void rac_code_word(Rac &c, uint32_t w)
 {
-    const uint32_t p = (word >> SH) & 0xFFu;
-    const uint32_t r1 = (c.range * p) >> 8;
-    const uint32_t r0 = c.range - r1;
-    if (word & (0x100u << SH)) { c.low += r0; c.range = r1; } else c.range = r0;
-    if (c.range < 0x100u) rac_shift(c);       // p >= 1 and range >= 0x100 before: at most one shift
+    rac_code(c, w << 24, w & 0x100u);
+    rac_code(c, __byte_perm(w, 0u, 0x2444), w & 0x1000000u);
 }
 
-__device__ __forceinline__ uint4 dec_load(const uint4 *src, uint32_t i, uint32_t nvec)
-{
-    return i < nvec ? __ldg(src + i) : make_uint4(0u, 0u, 0u, 0u);
-}
+// decision source of one coder: -1 = the slice's prefix (keyframe bit, slice header), 0..nruns-1 = sample runs,
+// nruns = the closing put_rac(state 129, 0) of ffv1enc.c:1331-1333
+struct RacGen {
+    const uint4 *ptr;
+    uint32_t rem;          // vectors left in the current source
+    uint32_t last_valid;   // decisions in its last vector (1..8)
+    int r;                 // current source
+    uint32_t cur0, cur1, cur2;
+};
 
-// n decisions starting at a 16-byte aligned address.  Four 16-byte vectors (32 decisions) stay in flight; the loop
-// body is deliberately NOT unrolled beyond one 32-bit word (2 decisions): the 32 lanes of a warp sit at different
-// points of their streams, so a compact body that stays in the instruction cache beats a long unrolled one.
-__device__ __forceinline__ void rac_code_run(Rac &c, const uint4 *src, uint32_t n)
-{
-    const uint32_t nwords = (n + 1u) >> 1, nvec = (nwords + 3u) >> 2;
-    uint4 v0 = dec_load(src, 0, nvec), v1 = dec_load(src, 1, nvec), v2 = dec_load(src, 2, nvec), v3 = dec_load(src, 3, nvec);
-    uint32_t done = 0;
-#pragma unroll 1
-    for (uint32_t i = 0; i < nvec; i++) {
-        uint4 v = v0;
-        v0 = v1; v1 = v2; v2 = v3;
-        v3 = dec_load(src, i + 4u, nvec);
-        const uint32_t wc = min(4u, nwords - 4u * i);
-#pragma unroll 1
-        for (uint32_t w = 0; w < wc; w++) {
-            const uint32_t word = v.x;
-            v.x = v.y; v.y = v.z; v.z = v.w;
-            rac_code<0>(c, word);
-            if (done + 1u < n) rac_code<16>(c, word);
-            done += 2u;
-        }
-    }
-}
-
-// Coders per warp.  The kernel is bound by instruction latency, not by issue slots: every lane that renormalises drags
-// the whole warp through the byte-output path, and a slice offers only one coder.  Using a few lanes per warp gives
-// several times more warps to hide that latency behind (and makes the renormalisation branch rarer per warp).
 constexpr int kRangeThreads = 32;
 
 __global__ void __launch_bounds__(kRangeThreads) k_rangecode(const EncDeviceTables T, const EncBatch B, const int lanes)
@@ -580,40 +626,81 @@ __global__ void __launch_bounds__(kRangeThreads) k_rangecode(const EncDeviceTabl
     const int idx = blockIdx.x * lanes + threadIdx.x;
     if (idx >= B.nframes * L.nslices) return;
     if (B.status[0]) return;
-    const int f = idx / L.nslices, s = idx - f * L.nslices;
+    // a warp holds the same slice of consecutive frames: their streams have similar lengths
+    const int s = idx / B.nframes, f = idx - s * B.nframes;
     const SliceGeom &g = T.slices[s];
     const int key = B.frame_key[f] ? 1 : 0;
+    const int nruns = g.nruns;
 
     Rac c;
     c.low = 0; c.range = 0xFF00u; c.out_byte = 0; c.out_count = 0;        // ff_init_range_encoder (+ dummy outstanding byte)
-    c.buf = reinterpret_cast<uint32_t *>(B.scratch + (size_t)f * L.scratch_per_frame + g.scratch_off);
-    c.pos = kScratchLead - 1; c.cap = g.scratch_cap; c.acc = 0;
+    c.wptr = reinterpret_cast<uint32_t *>(B.scratch + (size_t)f * L.scratch_per_frame + g.scratch_off);
+    c.pos = kScratchLead - 1; c.cap = g.scratch_cap; c.acc = 0; c.room = 1u;
 
     const uint16_t *dec_frame = B.dec + (size_t)f * L.dec_per_frame;
     const uint32_t *run_cnt = B.run_cnt + (size_t)f * L.runs_per_frame + g.run_first;
     const uint8_t *run_pc = T.run_pc + g.run_first;
-    uint32_t cur0 = 0u, cur1 = 0u, cur2 = 0u;
-    // source -1: the slice's prefix (keyframe bit, slice header); 0..nruns-1: sample runs; nruns: the closing
-    // put_rac(state 129, 0) of ffv1enc.c:1331-1333.  One loop so that the coder body exists once in the binary.
-#pragma unroll 1
-    for (int r = -1; r <= g.nruns; r++) {
-        const uint16_t *src;
-        uint32_t n;
-        if (r < 0) {
-            src = T.prefix + (size_t)(s * 2 + key) * kMaxPrefix;
-            n = (uint32_t)T.prefix_len[s * 2 + key];
-        } else if (r == g.nruns) {
-            src = T.prefix + (size_t)L.nslices * 2 * kMaxPrefix;          // one extra row holding the entry "129"
-            n = 1u;
-        } else {
-            const int pc = run_pc[r];
-            n = run_cnt[r];
-            const uint32_t at = pc == 0 ? cur0 : (pc == 1 ? cur1 : cur2);
-            src = dec_frame + g.dec_off[pc] + at;
-            const uint32_t nx = (at + n + 7u) & ~7u;
-            if (pc == 0) cur0 = nx; else if (pc == 1) cur1 = nx; else cur2 = nx;
+
+    RacGen gen;
+    gen.ptr = nullptr; gen.rem = 0; gen.last_valid = 0; gen.r = -2; gen.cur0 = gen.cur1 = gen.cur2 = 0u;
+
+    auto fetch = [&](uint4 &v) -> uint32_t {              // next vector of the lane's stream; returns decisions in it (0 = end)
+        if (gen.rem == 0u) {
+            while (gen.r < nruns) {                           // next non-empty source
+                const int r = ++gen.r;
+                const uint16_t *src;
+                uint32_t n;
+                if (r < 0) {
+                    src = T.prefix + (size_t)(s * 2 + key) * kMaxPrefix;
+                    n = (uint32_t)T.prefix_len[s * 2 + key];
+                } else if (r == nruns) {
+                    src = T.prefix + (size_t)L.nslices * 2 * kMaxPrefix;      // one extra row holding the entry "129"
+                    n = 1u;
+                } else {
+                    const int pc = run_pc[r];
+                    n = run_cnt[r];
+                    const uint32_t at = pc == 0 ? gen.cur0 : (pc == 1 ? gen.cur1 : gen.cur2);
+                    src = dec_frame + g.dec_off[pc] + at;
+                    const uint32_t nx = (at + n + 7u) & ~7u;
+                    if (pc == 0) gen.cur0 = nx; else if (pc == 1) gen.cur1 = nx; else gen.cur2 = nx;
+                }
+                if (n) {
+                    gen.ptr = reinterpret_cast<const uint4 *>(src);
+                    gen.rem = (n + 7u) >> 3;
+                    gen.last_valid = n - 8u * (gen.rem - 1u);
+                    break;
+                }
+            }
+            if (gen.rem == 0u) { v = make_uint4(0u, 0u, 0u, 0u); return 0u; }
         }
-        rac_code_run(c, reinterpret_cast<const uint4 *>(src), n);
+        v = __ldg(gen.ptr++);
+        return --gen.rem ? 8u : gen.last_valid;
+    };
+
+    uint4 q0, q1, q2, q3;
+    uint32_t vq = fetch(q0);
+    vq |= fetch(q1) << 4;
+    vq |= fetch(q2) << 8;
+    vq |= fetch(q3) << 12;
+#pragma unroll 1
+    for (;;) {
+        uint4 v = q0;
+        const uint32_t valid = vq & 0xFu;
+        if (valid == 0u) break;
+        q0 = q1; q1 = q2; q2 = q3;
+        vq = (vq >> 4) | (fetch(q3) << 12);
+        if (valid < 8u) {                                     // end of a run: what follows in the vector is not ours
+            const uint32_t k = valid;
+            if (k <= 6u) v.w = 0u; else if (k == 7u) v.w &= 0xFFFFu;
+            if (k <= 4u) v.z = 0u; else if (k == 5u) v.z &= 0xFFFFu;
+            if (k <= 2u) v.y = 0u; else if (k == 3u) v.y &= 0xFFFFu;
+            if (k == 1u) v.x &= 0xFFFFu;
+        }
+        c.room = c.pos + 16u <= c.cap ? 1u : 0u;
+        rac_code_word(c, v.x);
+        rac_code_word(c, v.y);
+        rac_code_word(c, v.z);
+        rac_code_word(c, v.w);
     }
     // ff_rac_terminate (rangecoder.c:104-116): two forced renormalisations
 #pragma unroll 1
@@ -622,10 +709,10 @@ __global__ void __launch_bounds__(kRangeThreads) k_rangecode(const EncDeviceTabl
         if (t == 0) c.low += 0xFFu;
         while (c.range < 0x100u) rac_shift(c);
     }
-    if ((c.pos & 3u) && c.pos + 4u <= c.cap) c.buf[c.pos >> 2] = c.acc >> (8u * (4u - (c.pos & 3u)));
+    if ((c.pos & 3u) && c.pos + 4u <= c.cap) *c.wptr = c.acc >> (8u * (4u - (c.pos & 3u)));
 
-    B.slice_bytes[idx] = c.pos - kScratchLead;
-    if (c.pos + 4u > c.cap) atomicMax(&B.status[1], (unsigned long long)c.pos + 4ull);
+    B.slice_bytes[f * L.nslices + s] = c.pos - kScratchLead;
+    if (c.pos + 24u > c.cap) atomicMax(&B.status[1], (unsigned long long)c.pos + 24ull);       // see Rac::room
 }
 
 void launch_rangecode(const EncDeviceTables &t, const EncBatch &b, cudaStream_t s)
@@ -634,9 +721,9 @@ void launch_rangecode(const EncDeviceTables &t, const EncBatch &b, cudaStream_t 
     static int forced = -1;
     if (forced < 0) { const char *v = getenv("FFV1B200_RANGE_LANES"); forced = v ? atoi(v) : 0; if (forced < 0 || forced > 32) forced = 0; }
     int lanes = forced;
-    if (!lanes) {                                  // aim at ~12 warps per SM
-        lanes = 2;
-        while (lanes < 32 && n / lanes > 148 * 12) lanes *= 2;
+    if (!lanes) {                                  // full warps once there are enough coders for ~4 warps per SM
+        lanes = 4;
+        while (lanes < 32 && n / lanes > 148 * 4) lanes *= 2;
     }
     k_rangecode<<<(n + lanes - 1) / lanes, kRangeThreads, 0, s>>>(t, b, lanes);
 }
