@@ -506,99 +506,100 @@ struct Rac {
     uint32_t low, range;
     uint32_t out_byte;   // outstanding byte (its final value depends on a carry that may still arrive)
     uint32_t out_count;  // 0xFF bytes behind it that a carry would turn into 0x00
-    uint32_t *wptr;      // next 32-bit word of the slice's scratch region
-    uint32_t pos, cap, acc;
-    uint32_t room;       // 1 while a whole vector of decisions cannot overrun the scratch region (checked per vector)
+    uint32_t pos;        // bytes produced (incl. the kScratchLead lead-in)
+    uint32_t fl;         // bytes already moved from the lane's ring to the scratch region (multiple of 16)
+    uint32_t ring;       // shared-memory address of the lane's 32-byte ring: byte i of the stream sits at ring + (i & 31)
+    uint32_t cap;
+    uint8_t *out;        // the slice's scratch region (256-byte aligned)
 };
 
-__device__ __forceinline__ void rac_emit(Rac &c, uint32_t b)
+__device__ __forceinline__ void rac_flush16(Rac &c)       // one finished 16-byte block: ring -> scratch region
 {
-    c.acc = __funnelshift_r(c.acc, b, 8);                 // (acc >> 8) | (b << 24): little-endian word assembly
-    c.pos++;
-    if ((c.pos & 3u) == 0u) { if (c.pos <= c.cap) *c.wptr = c.acc; c.wptr++; }
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(c.ring + (c.fl & 16u)));
+    if (c.fl + 16u <= c.cap) *reinterpret_cast<uint4 *>(c.out + c.fl) = v;
+    c.fl += 16u;
+}
+
+// the same, predicated (no branch: the lanes of a warp fill their rings at different times): moves a block once the
+// lane has 16 or more bytes waiting
+__device__ __forceinline__ void rac_flush16_if_full(Rac &c)
+{
+    const uint32_t full = (c.pos - c.fl >= 16u) ? 1u : 0u;
+    const uint32_t st = (full && c.fl + 16u <= c.cap) ? 1u : 0u;
+    asm volatile("{\n\t.reg .pred f, s;\n\t.reg .u32 a, b, c, d;\n\t"
+        "setp.ne.u32 f, %2, 0;\n\t"
+        "setp.ne.u32 s, %3, 0;\n\t"
+        "@f ld.shared.v4.u32 {a, b, c, d}, [%1];\n\t"
+        "@s st.global.v4.u32 [%0], {a, b, c, d};\n\t}"
+        :: "l"(c.out + c.fl), "r"(c.ring + (c.fl & 16u)), "r"(full), "r"(st) : "memory");
+    c.fl += full << 4;
 }
 
 // the uncommon renormalisations (renorm_encoder, rangecoder.h:52-75): a 0xFF byte that has to wait for its carry, or
 // the byte that resolves such a wait.  Out of line on purpose (all state by value, so it stays in registers): as a
-// predicated call the straight-line path of k_rangecode never has to jump over this code.
-struct RacOut { uint32_t out_byte, out_count, acc, pos; uint32_t *wptr; };
+// call, the straight-line path of k_rangecode does not have to jump over this code.
+struct RacOut { uint32_t out_byte, out_count, pos, fl; };
 
-__device__ __noinline__ RacOut rac_output_slow(uint32_t low, uint32_t wait, uint32_t out_byte, uint32_t out_count, uint32_t acc,
-                                               uint32_t pos, uint32_t cap, uint32_t *wptr)
+__device__ __noinline__ RacOut rac_output_slow(uint32_t low, uint32_t out_byte, uint32_t out_count, uint32_t pos, uint32_t fl,
+                                               uint32_t ring, uint32_t cap, uint8_t *out)
 {
     RacOut o;
-    if (wait) { o.out_byte = out_byte; o.out_count = out_count + 1u; o.acc = acc; o.pos = pos; o.wptr = wptr; return o; }
+    o.out_byte = out_byte; o.out_count = out_count + 1u; o.pos = pos; o.fl = fl;
+    if (low - 0xFF01u < 0xFFu) return o;                  // 0xFF00 < low < 0x10000: wait for the carry
     Rac c;
-    c.out_byte = out_byte; c.out_count = out_count; c.acc = acc; c.pos = pos; c.cap = cap; c.wptr = wptr;
+    c.pos = pos; c.fl = fl; c.ring = ring; c.cap = cap; c.out = out;
     const uint32_t carry = low >> 16;
-    rac_emit(c, c.out_byte + carry);
     const uint32_t fill = carry ? 0x00u : 0xFFu;
+    uint32_t b = out_byte + carry;
 #pragma unroll 1
-    do rac_emit(c, fill); while (--c.out_count);
-    o.out_byte = (low >> 8) & 0xFFu; o.out_count = 0u; o.acc = c.acc; o.pos = c.pos; o.wptr = c.wptr;
+    for (uint32_t i = 0; i <= out_count; i++) {
+        asm volatile("st.shared.u8 [%0], %1;" :: "r"(c.ring + (c.pos & 31u)), "r"(b) : "memory");
+        c.pos++;
+        if (c.pos - c.fl >= 16u) rac_flush16(c);
+        b = fill;
+    }
+    o.out_byte = (low >> 8) & 0xFFu; o.out_count = 0u; o.pos = c.pos; o.fl = c.fl;
     return o;
 }
 
-// Byte output of a renormalisation (sh = 1; `low` is the value before the shift).  The common case -- exactly one
-// byte, the outstanding byte plus the carry -- is predicated, not branched, so the 32 coders of a warp stay converged;
-// only a 0xFF byte waiting for its carry (about one renormalisation in 128) leaves the straight line.
-__device__ __forceinline__ void rac_output(Rac &c, uint32_t low, uint32_t sh)
-{
-    uint32_t slow, wait;
-    asm("{\n\t.reg .pred w, s;\n\t.reg .u32 t;\n\t"
-        "sub.u32 t, %3, 0xFF01;\n\t"
-        "setp.lt.u32 w, t, 0xFF;\n\t"                       // 0xFF00 < low < 0x10000: the byte is 0xFF, a carry may still flip it
-        "selp.u32 %1, 1, 0, w;\n\t"
-        "setp.ne.or.u32 w, %4, 0, w;\n\t"                   // ... or such bytes are still waiting
-        "setp.ne.and.u32 s, %2, 0, w;\n\t"
-        "selp.u32 %0, 1, 0, s;\n\t}"
-        : "=r"(slow), "=r"(wait) : "r"(sh), "r"(low), "r"(c.out_count));
-    if (__builtin_expect(slow != 0u, 0)) {
-        const RacOut o = rac_output_slow(low, wait, c.out_byte, c.out_count, c.acc, c.pos, c.cap, c.wptr);
-        c.out_byte = o.out_byte; c.out_count = o.out_count; c.acc = o.acc; c.pos = o.pos; c.wptr = o.wptr;
-    }
-    const uint32_t fast = sh & (slow ^ 1u);
-    asm volatile("{\n\t.reg .pred f, st;\n\t.reg .u32 t, b;\n\t"
-        "setp.ne.u32 f, %4, 0;\n\t"
-        "shr.u32 t, %5, 16;\n\t"
-        "add.u32 b, %1, t;\n\t"                             // outstanding byte + carry
-        "@f shf.r.wrap.b32 %0, %0, b, 8;\n\t"               // acc = acc >> 8 | byte << 24
-        "@f prmt.b32 %1, %5, 0, 0x4441;\n\t"                // outstanding byte = (low >> 8) & 0xFF
-        "@f add.u32 %2, %2, 1;\n\t"
-        "and.b32 t, %2, 3;\n\t"
-        "setp.eq.and.u32 st, t, 0, f;\n\t"
-        "setp.ne.and.u32 st, %6, 0, st;\n\t"
-        "@st st.global.u32 [%3], %0;\n\t"
-        "setp.eq.and.u32 st, t, 0, f;\n\t"
-        "@st add.u64 %3, %3, 4;\n\t}"
-        : "+r"(c.acc), "+r"(c.out_byte), "+r"(c.pos), "+l"(c.wptr) : "r"(fast), "r"(low), "r"(c.room) : "memory");
-}
-
-// put_rac (rangecoder.h:85-102) for one decision: p24 = probability state << 24, one = coded bit (any non-zero value)
+// put_rac (rangecoder.h:85-102) for one decision (p24 = probability state << 24, one = coded bit, any non-zero value)
+// and the byte output of its renormalisation.  The common case of the latter -- exactly one byte, the outstanding byte
+// plus the carry -- is predicated, not branched, so the 32 coders of a warp stay converged; only a 0xFF byte that has
+// to wait for its carry (about one renormalisation in 128) leaves the straight line.
 __device__ __forceinline__ void rac_code(Rac &c, uint32_t p24, uint32_t one)
 {
-    uint32_t low_before, sh;
-    asm("{\n\t.reg .pred one, sh;\n\t.reg .u32 r1, r0;\n\t"
-        "mul.hi.u32 r1, %1, %4;\n\t"                        // (range * p) >> 8
+    uint32_t low_before, slow;
+    asm volatile("{\n\t.reg .pred one, sh, w, s, f;\n\t.reg .u32 r1, r0, t, b, a;\n\t"
+        "mul.hi.u32 r1, %1, %7;\n\t"                        // (range * p) >> 8
         "sub.u32 r0, %1, r1;\n\t"
-        "setp.ne.u32 one, %5, 0;\n\t"
+        "setp.ne.u32 one, %8, 0;\n\t"
         "selp.u32 %1, r1, r0, one;\n\t"
         "@one add.u32 %0, %0, r0;\n\t"
-        "mov.u32 %2, %0;\n\t"
+        "mov.u32 %4, %0;\n\t"                               // low before the shift
         "setp.lt.u32 sh, %1, 0x100;\n\t"                    // p >= 1 and range >= 0x100 before: at most one shift
-        "selp.u32 %3, 1, 0, sh;\n\t"
         "@sh shl.b32 %1, %1, 8;\n\t"
-        "@sh prmt.b32 %0, %0, 0, 0x4404;\n\t}"              // low = (low & 0xFF) << 8
-        : "+r"(c.low), "+r"(c.range), "=r"(low_before), "=r"(sh) : "r"(p24), "r"(one));
-    rac_output(c, low_before, sh);
-}
-
-__device__ __forceinline__ void rac_shift(Rac &c)         // forced renormalisation (termination only)
-{
-    const uint32_t low = c.low;
-    c.low = (low & 0xFFu) << 8;
-    c.range <<= 8;
-    rac_output(c, low, 1u);
+        "@sh prmt.b32 %0, %0, 0, 0x4404;\n\t"               // low = (low & 0xFF) << 8
+        "sub.u32 t, %4, 0xFF01;\n\t"
+        "setp.lt.u32 w, t, 0xFF;\n\t"                       // the byte is 0xFF and a carry may still flip it ...
+        "setp.ne.or.u32 w, %6, 0, w;\n\t"                   // ... or such bytes are still waiting
+        "and.pred s, sh, w;\n\t"
+        "selp.u32 %5, 1, 0, s;\n\t"
+        "not.pred w, w;\n\t"
+        "and.pred f, sh, w;\n\t"
+        "shr.u32 t, %4, 16;\n\t"
+        "add.u32 b, %2, t;\n\t"                             // outstanding byte + carry
+        "and.b32 a, %3, 31;\n\t"
+        "or.b32 a, a, %9;\n\t"
+        "@f st.shared.u8 [a], b;\n\t"
+        "@f add.u32 %3, %3, 1;\n\t"
+        "@f prmt.b32 %2, %4, 0, 0x4441;\n\t}"               // outstanding byte = (low >> 8) & 0xFF
+        : "+r"(c.low), "+r"(c.range), "+r"(c.out_byte), "+r"(c.pos), "=r"(low_before), "=r"(slow)
+        : "r"(c.out_count), "r"(p24), "r"(one), "r"(c.ring) : "memory");
+    if (__builtin_expect(slow != 0u, 0)) {
+        const RacOut o = rac_output_slow(low_before, c.out_byte, c.out_count, c.pos, c.fl, c.ring, c.cap, c.out);
+        c.out_byte = o.out_byte; c.out_count = o.out_count; c.pos = o.pos; c.fl = o.fl;
+    }
 }
 
 __device__ __forceinline__ void rac_code_word(Rac &c, uint32_t w)
@@ -618,6 +619,8 @@ struct RacGen {
 };
 
 constexpr int kRangeThreads = 32;
+constexpr int kRangeChunk = 8;            // 16-byte decision vectors per chunk (one 128-byte line per lane)
+constexpr int kRangeDepth = 4;            // chunk slots per lane (power of two): kRangeDepth-1 chunks in flight
 
 __global__ void __launch_bounds__(kRangeThreads) k_rangecode(const EncDeviceTables T, const EncBatch B, const int lanes)
 {
@@ -632,19 +635,28 @@ __global__ void __launch_bounds__(kRangeThreads) k_rangecode(const EncDeviceTabl
     const int key = B.frame_key[f] ? 1 : 0;
     const int nruns = g.nruns;
 
+    __shared__ __align__(32) uint8_t s_ring[kRangeThreads * 32];
+    __shared__ __align__(16) uint4 s_vec[kRangeDepth * kRangeChunk * kRangeThreads];   // [chunk slot][vector][lane]
     Rac c;
     c.low = 0; c.range = 0xFF00u; c.out_byte = 0; c.out_count = 0;        // ff_init_range_encoder (+ dummy outstanding byte)
-    c.wptr = reinterpret_cast<uint32_t *>(B.scratch + (size_t)f * L.scratch_per_frame + g.scratch_off);
-    c.pos = kScratchLead - 1; c.cap = g.scratch_cap; c.acc = 0; c.room = 1u;
+    c.out = B.scratch + (size_t)f * L.scratch_per_frame + g.scratch_off;
+    c.pos = kScratchLead - 1; c.fl = 0; c.cap = g.scratch_cap;
+    c.ring = (uint32_t)__cvta_generic_to_shared(s_ring + threadIdx.x * 32);
 
     const uint16_t *dec_frame = B.dec + (size_t)f * L.dec_per_frame;
     const uint32_t *run_cnt = B.run_cnt + (size_t)f * L.runs_per_frame + g.run_first;
     const uint8_t *run_pc = T.run_pc + g.run_first;
 
+    const uint32_t vec_base = (uint32_t)__cvta_generic_to_shared(s_vec + threadIdx.x);
     RacGen gen;
     gen.ptr = nullptr; gen.rem = 0; gen.last_valid = 0; gen.r = -2; gen.cur0 = gen.cur1 = gen.cur2 = 0u;
 
-    auto fetch = [&](uint4 &v) -> uint32_t {              // next vector of the lane's stream; returns decisions in it (0 = end)
+    // Next chunk of the lane's stream: up to kRangeChunk consecutive 16-byte vectors of the current source, copied into
+    // chunk slot `slot` of the lane's shared-memory ring with cp.async (no register is tied to the data while it is in
+    // flight; the vectors of a chunk are requested back to back, so DRAM sees one 128-byte access per lane, not eight
+    // scattered 16-byte ones).  Returns nvec | decisions_in_last_vector << 4 (0 = the stream has ended).
+    auto fetch = [&](uint32_t slot) -> uint32_t {
+        uint32_t desc = 0u;
         if (gen.rem == 0u) {
             while (gen.r < nruns) {                           // next non-empty source
                 const int r = ++gen.r;
@@ -671,48 +683,69 @@ __global__ void __launch_bounds__(kRangeThreads) k_rangecode(const EncDeviceTabl
                     break;
                 }
             }
-            if (gen.rem == 0u) { v = make_uint4(0u, 0u, 0u, 0u); return 0u; }
         }
-        v = __ldg(gen.ptr++);
-        return --gen.rem ? 8u : gen.last_valid;
+        if (gen.rem) {
+            const uint32_t nv = min(gen.rem, (uint32_t)kRangeChunk);
+            const uint32_t dst = vec_base + slot * (kRangeChunk * kRangeThreads * 16u);
+#pragma unroll
+            for (uint32_t j = 0; j < (uint32_t)kRangeChunk; j++)
+                if (j < nv) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst + j * (kRangeThreads * 16u)), "l"(gen.ptr + j) : "memory");
+            gen.ptr += nv;
+            gen.rem -= nv;
+            desc = nv | (gen.rem ? 8u : gen.last_valid) << 4;
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        return desc;
     };
 
-    uint4 q0, q1, q2, q3;
-    uint32_t vq = fetch(q0);
-    vq |= fetch(q1) << 4;
-    vq |= fetch(q2) << 8;
-    vq |= fetch(q3) << 12;
+    // kRangeDepth chunks in flight per lane; dq holds their descriptors, 8 bits each, oldest in the low bits
+    uint32_t dq = 0u;
+#pragma unroll
+    for (int i = 0; i < kRangeDepth - 1; i++) dq |= fetch((uint32_t)i) << (8 * i);
+    uint32_t slot = 0u;
 #pragma unroll 1
     for (;;) {
-        uint4 v = q0;
-        const uint32_t valid = vq & 0xFu;
-        if (valid == 0u) break;
-        q0 = q1; q1 = q2; q2 = q3;
-        vq = (vq >> 4) | (fetch(q3) << 12);
-        if (valid < 8u) {                                     // end of a run: what follows in the vector is not ours
-            const uint32_t k = valid;
-            if (k <= 6u) v.w = 0u; else if (k == 7u) v.w &= 0xFFFFu;
-            if (k <= 4u) v.z = 0u; else if (k == 5u) v.z &= 0xFFFFu;
-            if (k <= 2u) v.y = 0u; else if (k == 3u) v.y &= 0xFFFFu;
-            if (k == 1u) v.x &= 0xFFFFu;
+        const uint32_t nv = dq & 0xFu, last_valid = (dq >> 4) & 0xFu;
+        if (nv == 0u) break;
+        dq = (dq >> 8) | fetch((slot + kRangeDepth - 1) & (kRangeDepth - 1)) << (8 * (kRangeDepth - 2));
+        asm volatile("cp.async.wait_group %0;" :: "n"(kRangeDepth - 1) : "memory");
+        uint32_t at = vec_base + slot * (kRangeChunk * kRangeThreads * 16u);
+        slot = (slot + 1u) & (kRangeDepth - 1);
+        uint4 v;
+        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(at) : "memory");
+#pragma unroll 1
+        for (uint32_t j = nv; j; j--) {
+            uint4 cur = v;
+            at += kRangeThreads * 16u;
+            // the next vector of the chunk is read while this one is coded (the chunk has landed as a whole)
+            if (j > 1u) asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(at) : "memory");
+            if (j == 1u && last_valid < 8u) {                     // end of a run: what follows in the vector is not ours
+                const uint32_t k = last_valid;
+                if (k <= 6u) cur.w = 0u; else if (k == 7u) cur.w &= 0xFFFFu;
+                if (k <= 4u) cur.z = 0u; else if (k == 5u) cur.z &= 0xFFFFu;
+                if (k <= 2u) cur.y = 0u; else if (k == 3u) cur.y &= 0xFFFFu;
+                if (k == 1u) cur.x &= 0xFFFFu;
+            }
+            rac_code_word(c, cur.x);
+            rac_code_word(c, cur.y);
+            rac_code_word(c, cur.z);
+            rac_code_word(c, cur.w);
+            rac_flush16_if_full(c);                               // at most 8 bytes per vector on the straight line
         }
-        c.room = c.pos + 16u <= c.cap ? 1u : 0u;
-        rac_code_word(c, v.x);
-        rac_code_word(c, v.y);
-        rac_code_word(c, v.z);
-        rac_code_word(c, v.w);
     }
-    // ff_rac_terminate (rangecoder.c:104-116): two forced renormalisations
+    // ff_rac_terminate (rangecoder.c:104-116): range = 0xFF, low += 0xFF, renormalise; range = 0xFF, renormalise.  A
+    // decision with p = 0, bit = 0 changes nothing, so forcing the range below 0x100 in front of one is exactly a
+    // forced renormalisation.
+    c.low += 0xFFu;
 #pragma unroll 1
     for (int t = 0; t < 2; t++) {
         c.range = 0xFFu;
-        if (t == 0) c.low += 0xFFu;
-        while (c.range < 0x100u) rac_shift(c);
+        rac_code(c, 0u, 0u);
     }
-    if ((c.pos & 3u) && c.pos + 4u <= c.cap) *c.wptr = c.acc >> (8u * (4u - (c.pos & 3u)));
+    while (c.fl < c.pos) rac_flush16(c);
 
     B.slice_bytes[f * L.nslices + s] = c.pos - kScratchLead;
-    if (c.pos + 24u > c.cap) atomicMax(&B.status[1], (unsigned long long)c.pos + 24ull);       // see Rac::room
+    if (((c.pos + 15u) & ~15u) > c.cap) atomicMax(&B.status[1], (unsigned long long)c.pos + 16ull);
 }
 
 void launch_rangecode(const EncDeviceTables &t, const EncBatch &b, cudaStream_t s)
@@ -721,9 +754,9 @@ void launch_rangecode(const EncDeviceTables &t, const EncBatch &b, cudaStream_t 
     static int forced = -1;
     if (forced < 0) { const char *v = getenv("FFV1B200_RANGE_LANES"); forced = v ? atoi(v) : 0; if (forced < 0 || forced > 32) forced = 0; }
     int lanes = forced;
-    if (!lanes) {                                  // full warps once there are enough coders for ~4 warps per SM
+    if (!lanes) {                                  // the coders are bound by latency: ~10 warps per SM before warps are filled up
         lanes = 4;
-        while (lanes < 32 && n / lanes > 148 * 4) lanes *= 2;
+        while (lanes < 32 && n / lanes > 148 * 12) lanes *= 2;
     }
     k_rangecode<<<(n + lanes - 1) / lanes, kRangeThreads, 0, s>>>(t, b, lanes);
 }
