@@ -16,6 +16,7 @@
 //                  binarisation (ffv1enc.c:185-231) with the context's 32-byte state in registers; writes p | bit<<8
 //                  at the recorded positions of the decision stream that k_rangecode consumes
 #include "ffv1_enc_kernels.cuh"
+#include <cstdlib>
 
 namespace ffv1 {
 
@@ -418,6 +419,184 @@ __global__ void __launch_bounds__(kCtxThreads, 1) k_replay_ctx(const EncDeviceTa
     }
 }
 
+// ------------------------------------------------------------------------------------------------ k_replay_grp
+// Same replay, but a warp works on TWO context lists at a time, 16 lanes each.  A symbol with exponent e <= EMAX only
+// touches the zero flag, e+1 exponent slots, e mantissa slots and one sign slot (ffv1enc.c:202-229), i.e. at most
+// 3*EMAX+3 of the 32 state slots; with EMAX = 4 (|residual| < 32) they fit 15 lanes:
+//     lane 0            slot 0                     "is zero"
+//     lanes 1..5        slots 1..5                 exponent, unary
+//     lanes 6..9        slots 25,24,23,22          mantissa bits 3..0 (the coding order walks them downwards)
+//     lanes 10..14      slots 11..15               sign, one slot per exponent
+// so the visiting order of a symbol is again increasing in lane index.  Larger residuals (rare on 8-bit content) are
+// replayed by one lane of the group against the shared-memory copy of the state row.  Halving the lanes per symbol
+// halves the instructions issued per symbol, which is what bounds this kernel; two CTAs of 512 threads share an SM so
+// that one chain's end-of-frame tail (its longest list) overlaps the other chain's work.
+template <int EMAX>
+__device__ __forceinline__ void symbol_masks_grp(int d, uint32_t &visit, uint32_t &bits, bool &slow)
+{
+    slow = false;
+    if (d == 0) { visit = 1u; bits = 1u; return; }
+    const uint32_t a = (uint32_t)abs(d);
+    const int e = 31 - __clz(a);
+    if (e > EMAX) { visit = 0u; bits = 0u; slow = true; return; }
+    const uint32_t ones_e = (1u << e) - 1u;
+    const uint32_t mant = e ? (__brev(a & ones_e) >> (32 - e)) : 0u;       // bit t <- bit e-1-t of |d|
+    visit = 1u | (((2u << e) - 1u) << 1) | (ones_e << (2 * EMAX + 2 - e)) | (1u << (2 * EMAX + 2 + e));
+    bits = (ones_e << 1) | (mant << (2 * EMAX + 2 - e)) | ((d < 0 ? 1u : 0u) << (2 * EMAX + 2 + e));
+}
+
+// put_symbol_inline (ffv1enc.c:185-231) decision by decision against a state row in shared memory (any magnitude)
+__device__ __noinline__ void replay_symbol_serial(uint8_t *row, const uint8_t *lut, uint16_t *o, int d)
+{
+    if (d == 0) { const uint32_t s = row[0]; o[0] = (uint16_t)(s | 0x100u); row[0] = lut[0x100u + s]; return; }
+    const uint32_t a = (uint32_t)abs(d);
+    const int ex = 31 - __clz(a);
+    const int nd = 2 * ex + 3;
+    for (int qi = 0; qi < nd; qi++) {
+        int sl; uint32_t bit;
+        if (qi == 0) { sl = 0; bit = 0u; }
+        else if (qi <= ex) { sl = 1 + min(qi - 1, 9); bit = 0x100u; }
+        else if (qi == ex + 1) { sl = 1 + min(ex, 9); bit = 0u; }
+        else if (qi <= 2 * ex + 1) { const int i = ex - 1 - (qi - ex - 2); sl = 22 + min(i, 9); bit = ((a >> i) & 1u) << 8; }
+        else { sl = 11 + min(ex, 10); bit = d < 0 ? 0x100u : 0u; }
+        const uint32_t s = row[sl];
+        o[qi] = (uint16_t)(s | bit);
+        row[sl] = lut[bit + s];
+    }
+}
+
+template <int EMAX, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_replay_grp(const EncDeviceTables T, const EncBatch B)
+{
+    constexpr int G = 16;
+    static_assert(3 * EMAX + 3 <= G, "roles must fit a group");
+    extern __shared__ __align__(16) unsigned char s_state_raw[];     // [ctx_count][32] the chain's model
+    __shared__ uint8_t s_lut[512];
+    __shared__ uint4 s_blk_all[THREADS];
+    __shared__ int s_next;
+    uint8_t *s_state = s_state_raw;
+    const Layout &L = T.layout;
+    const int tid = threadIdx.x, lane = tid & 31, g = lane & (G - 1);
+    const uint32_t gmask = 0xFFFFu << (lane & 16);                   // the lanes of my group
+    uint4 *s_blk = s_blk_all + (tid & ~(G - 1));                     // my group's block of G entries
+    const uint32_t lut_base = (uint32_t)__cvta_generic_to_shared(s_lut);
+    for (int i = tid; i < 512; i += THREADS) s_lut[i] = T.trans_lut[i];
+    if (B.status[0]) return;
+    const int chain = blockIdx.x;
+    const int pc = chain % L.npc, s = (chain / L.npc) % L.nslices, seg = chain / (L.npc * L.nslices);
+    const SliceGeom &sg = T.slices[s];
+    const int f0 = B.seg_first[seg], f1 = B.seg_first[seg + 1];
+    const int nctx = L.ctx_count;
+    const bool key = B.frame_key[f0] != 0;
+    const bool hand_over = f1 == B.nframes;
+    const size_t coff = ((size_t)s * L.npc + pc) * ((size_t)nctx * 32);
+    {
+        const uint4 *cin4 = reinterpret_cast<const uint4 *>(B.carry_in + coff);
+        uint4 *st4 = reinterpret_cast<uint4 *>(s_state);
+        for (int i = tid; i < nctx * 2; i += THREADS)
+            st4[i] = key ? make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u) : cin4[i];
+    }
+    const uint2 *chain_list = B.lists + (size_t)f0 * L.samples_per_frame + (size_t)(f1 - f0) * sg.list_off[pc];
+    const uint32_t *lstart = B.list_start + (size_t)chain * nctx;
+    const uint32_t *lcount = B.list_count + (size_t)chain * nctx;
+    const uint16_t *order = B.list_order + (size_t)chain * nctx;
+    uint16_t *dec_pc = B.dec + sg.dec_off[pc];
+    // role of the lane inside its group
+    const int slot = g == 0 ? 0 : (g <= EMAX + 1 ? g : (g <= 2 * EMAX + 1 ? 22 + (2 * EMAX + 1 - g) : (g <= 3 * EMAX + 2 ? 11 + g - (2 * EMAX + 2) : -1)));
+    const bool has_slot = slot >= 0;
+    const uint32_t lanebit = 1u << g, lt_mask = lanebit - 1u;
+    const int rot = (g - 8) & 31;                                    // rotr(bits, rot) puts my bit at bit 8
+    const int t0 = sg.ct_first[pc];
+
+    for (int f = f0; f < f1; f++) {
+        __syncthreads();                                             // model loaded / previous frame finished
+        if (tid == 0) s_next = 0;
+        __syncthreads();
+        const uint32_t *before = B.ctx_hist + ((size_t)f * L.ctiles_per_frame + t0) * nctx;
+        const uint32_t *before_next = B.ctx_hist + ((size_t)(f + 1) * L.ctiles_per_frame + t0) * nctx;
+        uint32_t n_left = 0u, st = 0u;
+        uint2 nx = make_uint2(0u, 0u);
+        int c = -1;
+        bool exhausted = false;                                      // no lists left in this frame for my group
+        const uint2 *lp = chain_list;
+        for (;;) {
+            // ---- groups that finished their list take the next one (longest first)
+            if (n_left == 0u && !exhausted) {
+                if (c >= 0 && has_slot) s_state[c * 32 + slot] = (uint8_t)st;
+                c = -1;
+                for (;;) {
+                    int oi = 0;
+                    if (g == 0) oi = atomicAdd(&s_next, 1);
+                    oi = __shfl_sync(gmask, oi, 0, G);
+                    if (oi >= nctx) { exhausted = true; break; }
+                    const int cc = order[oi];
+                    const uint32_t ntot = lcount[cc];
+                    if (ntot == 0u) { exhausted = true; break; }     // contexts are ordered by the length of their chain list
+                    const uint32_t b0 = before[cc], b1 = f + 1 < f1 ? before_next[cc] : ntot;
+                    if (b1 == b0) continue;
+                    c = cc; n_left = b1 - b0;
+                    lp = chain_list + lstart[cc] + b0;
+                    st = has_slot ? s_state[cc * 32 + slot] : 0u;
+                    nx = (uint32_t)g < n_left ? lp[g] : make_uint2(0u, 0u);
+                    break;
+                }
+            }
+            if (!__any_sync(0xFFFFFFFFu, n_left != 0u)) break;
+            // ---- a block of up to G symbols per group: masks and positions, one symbol per lane
+            const uint32_t m = min((uint32_t)G, n_left);
+            const uint2 en = (uint32_t)g < m ? nx : make_uint2(0u, 0u);
+            // the next block of the list is fetched while this one is replayed (the longest list of a frame is the
+            // critical path of the whole CTA: its loads must not be exposed)
+            if ((uint32_t)(G + g) < n_left) nx = lp[G + g];
+            const int d = (int)(int16_t)(en.y & 0xFFFFu);
+            uint32_t vis = 0u, bts = 0u;
+            bool slow = false;
+            if ((uint32_t)g < m) symbol_masks_grp<EMAX>(d, vis, bts, slow);
+            // a block never leaves its frame, so positions relative to its first symbol fit 32 bits
+            const unsigned long long off = (unsigned long long)(en.y >> 16) * L.dec_per_frame + en.x;
+            const unsigned long long off0 = __shfl_sync(0xFFFFFFFFu, off, lane & 16);
+            uint16_t *o0 = dec_pc + off0;
+            __syncwarp();
+            s_blk[g] = make_uint4(vis, bts, (uint32_t)(off - off0), (slow ? 0x80000000u : 0u) | (en.y & 0xFFFFu));
+            __syncwarp();
+            const uint32_t mm = max(m, __shfl_xor_sync(0xFFFFFFFFu, m, 16));
+            if (!__any_sync(0xFFFFFFFFu, slow)) {
+#pragma unroll 4
+                for (uint32_t k = 0; k < mm; k++) {
+                    const uint4 q = s_blk[k];
+                    const uint32_t idx = q.z + __popc(q.x & lt_mask);
+                    const uint32_t val = (__funnelshift_r(q.y, q.y, rot) & 0x100u) | st;
+                    visit_step(reinterpret_cast<uint16_t *>(reinterpret_cast<char *>(o0) + (size_t)idx * 2u), val, st,
+                               lut_base + val, q.x & lanebit);
+                }
+            } else {
+                for (uint32_t k = 0; k < mm; k++) {
+                    const uint4 q = s_blk[k];
+                    if (q.w >> 31) {                                 // uniform inside a group
+                        if (has_slot) s_state[c * 32 + slot] = (uint8_t)st;
+                        __syncwarp(gmask);
+                        if (g == 0) replay_symbol_serial(s_state + c * 32, s_lut, o0 + q.z, (int)(int16_t)(q.w & 0xFFFFu));
+                        __syncwarp(gmask);
+                        if (has_slot) st = s_state[c * 32 + slot];
+                    } else if (q.x & lanebit) {
+                        const uint32_t val = (__funnelshift_r(q.y, q.y, rot) & 0x100u) | st;
+                        o0[q.z + __popc(q.x & lt_mask)] = (uint16_t)val;
+                        st = lut_ld(lut_base + val);
+                    }
+                }
+            }
+            lp += m; n_left -= m;
+        }
+        if (c >= 0 && has_slot) s_state[c * 32 + slot] = (uint8_t)st;
+    }
+    __syncthreads();
+    if (hand_over) {
+        const uint4 *st4 = reinterpret_cast<const uint4 *>(s_state);
+        uint4 *cout4 = reinterpret_cast<uint4 *>(B.carry_out + coff);
+        for (int i = tid; i < nctx * 2; i += THREADS) cout4[i] = st4[i];
+    }
+}
+
 bool ctx_replay_supported(const Layout &L)
 {
     return !L.golomb && L.ctx_count <= kMaxListCtx;
@@ -441,7 +620,13 @@ void launch_ctx_replay(const EncDeviceTables &t, const EncBatch &b, cudaStream_t
     k_dec_layout<<<(n + 127) / 128, 128, 0, s>>>(t, b);
     dim3 stiles((L.ctiles_per_frame + kScatterThreads / 32 - 1) / (kScatterThreads / 32), b.nframes);
     k_ctx_scatter<<<stiles, kScatterThreads, ctx_scatter_smem_bytes(L), s>>>(t, b);
-    if (L.coded_bits <= 10) k_replay_ctx<false><<<nchains, kCtxThreads, L.ctx_count * 32, s>>>(t, b);
+    static int grp = -1;
+    if (grp < 0) { const char *v = getenv("FFV1B200_REPLAY_GROUPS"); grp = v ? atoi(v) : 2; }
+    // 8-bit content (residuals folded to <= 9 bits): two lists per warp; a frame's decision area must fit 32-bit offsets
+    const bool grp_ok = L.coded_bits <= 9 && L.dec_per_frame < 0x7FFFFFFFu;
+    if (grp == 1 && grp_ok) k_replay_grp<4, 1024><<<nchains, 1024, L.ctx_count * 32, s>>>(t, b);
+    else if (grp == 2 && grp_ok) k_replay_grp<4, 512><<<nchains, 512, L.ctx_count * 32, s>>>(t, b);
+    else if (L.coded_bits <= 10) k_replay_ctx<false><<<nchains, kCtxThreads, L.ctx_count * 32, s>>>(t, b);
     else                    k_replay_ctx<true><<<nchains, kCtxThreads, L.ctx_count * 32, s>>>(t, b);
 }
 
