@@ -21,6 +21,7 @@
 namespace ffv1 {
 
 constexpr int kHistThreads = 256;
+constexpr int kScanThreads = 1024;                       // one context per thread (<= kMaxListCtx)
 constexpr int kScatterThreads = 128;                     // four tiles (one warp each) per CTA
 constexpr int kCtxThreads = 1024;
 constexpr int kMaxListCtx = 1024;
@@ -85,7 +86,7 @@ __global__ void __launch_bounds__(kHistThreads) k_ctx_hist(const EncDeviceTables
 }
 
 // ------------------------------------------------------------------------------------------------ k_ctx_scan
-__global__ void __launch_bounds__(256) k_ctx_scan(const EncDeviceTables T, const EncBatch B)
+__global__ void __launch_bounds__(kScanThreads) k_ctx_scan(const EncDeviceTables T, const EncBatch B)
 {
     __shared__ uint32_t s_total[kMaxListCtx];
     __shared__ uint32_t s_start[kMaxListCtx];
@@ -97,7 +98,7 @@ __global__ void __launch_bounds__(256) k_ctx_scan(const EncDeviceTables T, const
     const int f0 = B.seg_first[seg], f1 = B.seg_first[seg + 1];
     const int nctx = L.ctx_count, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int t0 = g.ct_first[pc], nt = g.ct_count[pc];
-    for (int c = tid; c < nctx; c += 256) {
+    for (int c = tid; c < nctx; c += kScanThreads) {
         uint32_t run = 0;
         for (int f = f0; f < f1; f++) {
             uint32_t *h = B.ctx_hist + ((size_t)f * L.ctiles_per_frame + t0) * nctx + c;
@@ -114,21 +115,21 @@ __global__ void __launch_bounds__(256) k_ctx_scan(const EncDeviceTables T, const
         s_total[c] = run;
     }
     __syncthreads();
-    // exclusive scan over the contexts: 4 consecutive contexts per thread
+    // exclusive scan over the contexts: 4 consecutive contexts per thread (the first 256 threads)
     {
         uint32_t v[4], sum = 0;
 #pragma unroll
         for (int k = 0; k < 4; k++) { const int c = tid * 4 + k; v[k] = c < nctx ? s_total[c] : 0u; sum += v[k]; }
         const uint32_t incl = cr_incl_scan(sum, lane);
-        if (lane == 31) s_warp[warp] = incl;
+        if (lane == 31 && warp < 8) s_warp[warp] = incl;
         __syncthreads();
         uint32_t base = incl - sum;
-        for (int w = 0; w < warp; w++) base += s_warp[w];
+        for (int w = 0; w < min(warp, 8); w++) base += s_warp[w];
 #pragma unroll
         for (int k = 0; k < 4; k++) { const int c = tid * 4 + k; if (c < nctx) s_start[c] = base; base += v[k]; }
     }
     __syncthreads();
-    for (int c = tid; c < nctx; c += 256) {
+    for (int c = tid; c < nctx; c += kScanThreads) {
         B.list_start[(size_t)chain * nctx + c] = s_start[c];
         B.list_count[(size_t)chain * nctx + c] = s_total[c];
         // longest list first (ties: lower context first)
@@ -147,42 +148,47 @@ __global__ void __launch_bounds__(128) k_dec_layout(const EncDeviceTables T, con
 {
     const Layout &L = T.layout;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= B.nframes * L.nslices * L.npc) return;
-    const int pc = idx % L.npc, s = (idx / L.npc) % L.nslices, f = idx / (L.npc * L.nslices);
-    const SliceGeom &g = T.slices[s];
-    const int nl = g.pc_nlines[pc];
-    if (!nl) return;
-    const int32_t *my_lines = T.pc_lines + g.pc_line_first[pc];
-    uint32_t *line_pos = B.line_pos + (size_t)f * L.lines_per_frame + g.line_first;
-    uint32_t *run_cnt = B.run_cnt + (size_t)f * L.runs_per_frame + g.run_first;
-    uint32_t pos = 0, run_start = 0, cur_run = T.lines[g.line_first + my_lines[0]].run;
     unsigned long long ndec = 0;
-    for (int ib = 0; ib < nl; ib += 8) {
-        // the loads of eight lines are issued together; only the running position is sequential
-        int line[8]; uint32_t run[8], nd[8];
+    if (idx < B.nframes * L.nslices * L.npc) {
+        const int pc = idx % L.npc, s = (idx / L.npc) % L.nslices, f = idx / (L.npc * L.nslices);
+        const SliceGeom &g = T.slices[s];
+        const int nl = g.pc_nlines[pc];
+        if (nl) {
+            const int32_t *my_lines = T.pc_lines + g.pc_line_first[pc];
+            uint32_t *line_pos = B.line_pos + (size_t)f * L.lines_per_frame + g.line_first;
+            uint32_t *run_cnt = B.run_cnt + (size_t)f * L.runs_per_frame + g.run_first;
+            uint32_t pos = 0, run_start = 0, cur_run = T.lines[g.line_first + my_lines[0]].run;
+            for (int ib = 0; ib < nl; ib += 8) {
+                // the loads of eight lines are issued together; only the running position is sequential
+                int line[8]; uint32_t run[8], nd[8];
 #pragma unroll
-        for (int k = 0; k < 8; k++) line[k] = ib + k < nl ? my_lines[ib + k] : my_lines[nl - 1];
+                for (int k = 0; k < 8; k++) line[k] = ib + k < nl ? my_lines[ib + k] : my_lines[nl - 1];
 #pragma unroll
-        for (int k = 0; k < 8; k++) { run[k] = T.lines[g.line_first + line[k]].run; nd[k] = line_pos[line[k]]; }
+                for (int k = 0; k < 8; k++) { run[k] = T.lines[g.line_first + line[k]].run; nd[k] = line_pos[line[k]]; }
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-            if (ib + k >= nl) break;
-            if (run[k] != cur_run) {                            // a run of this plane context ended: next one starts 16 B aligned
-                run_cnt[cur_run] = pos - run_start;
-                pos = (pos + 7u) & ~7u;
-                run_start = pos; cur_run = run[k];
+                for (int k = 0; k < 8; k++) {
+                    if (ib + k >= nl) break;
+                    if (run[k] != cur_run) {                    // a run of this plane context ended: next one starts 16 B aligned
+                        run_cnt[cur_run] = pos - run_start;
+                        pos = (pos + 7u) & ~7u;
+                        run_start = pos; cur_run = run[k];
+                    }
+                    line_pos[line[k]] = pos;
+                    pos += nd[k];
+                    ndec += nd[k];
+                }
             }
-            line_pos[line[k]] = pos;
-            pos += nd[k];
-            ndec += nd[k];
+            run_cnt[cur_run] = pos - run_start;
+            if (pos + 8u > g.dec_cap[pc]) {
+                const unsigned long long ns = g.pc_samples[pc];
+                atomicMax(&B.status[0], ((unsigned long long)(pos + 8u) * 256ull + ns - 1) / ns + 1ull);
+            }
         }
     }
-    run_cnt[cur_run] = pos - run_start;
-    atomicAdd(&B.status[3], ndec);
-    if (pos + 8u > g.dec_cap[pc]) {
-        const unsigned long long ns = g.pc_samples[pc];
-        atomicMax(&B.status[0], ((unsigned long long)(pos + 8u) * 256ull + ns - 1) / ns + 1ull);
-    }
+    // one atomic per warp for the batch's decision count (tens of thousands of same-address atomics serialise)
+#pragma unroll
+    for (int d = 16; d; d >>= 1) ndec += __shfl_xor_sync(0xFFFFFFFFu, ndec, d);
+    if ((threadIdx.x & 31) == 0 && ndec) atomicAdd(&B.status[3], ndec);
 }
 
 // ------------------------------------------------------------------------------------------------ k_ctx_scatter
@@ -615,7 +621,7 @@ void launch_ctx_replay(const EncDeviceTables &t, const EncBatch &b, cudaStream_t
     const int nchains = b.nseg * L.nslices * L.npc;
     dim3 tiles(L.ctiles_per_frame, b.nframes);
     k_ctx_hist<<<tiles, kHistThreads, 0, s>>>(t, b);
-    k_ctx_scan<<<nchains, 256, 0, s>>>(t, b);
+    k_ctx_scan<<<nchains, kScanThreads, 0, s>>>(t, b);
     const int n = b.nframes * L.nslices * L.npc;
     k_dec_layout<<<(n + 127) / 128, 128, 0, s>>>(t, b);
     dim3 stiles((L.ctiles_per_frame + kScatterThreads / 32 - 1) / (kScatterThreads / 32), b.nframes);
