@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <vector>
 #include "ffv1_model.h"
 
 namespace ffv1 {
@@ -83,9 +84,32 @@ bool ctx_replay_supported(const Layout &L);
 cudaError_t configure_ctx_replay(const Layout &L);
 void launch_ctx_replay(const EncDeviceTables &t, const EncBatch &b, cudaStream_t s);
 // tuned per-pixel pass for planar sources (ffv1_pixel_fast.cu)
+// one work item of a frame: up to 32 rows x <= 512 bytes of one slice-plane (everything the kernel needs, precomputed)
+struct alignas(16) FastItemDesc {
+    int32_t  c0;          // tensor-map x coordinate (32-bit elements) staged at buffer column 0 (may be negative)
+    int32_t  c1;          // first source row that is fetched
+    uint32_t rec_off;     // first record of the item inside a frame's record area
+    uint32_t magic;       // ceil(2^20 / upr): unit index -> row without a division
+    uint16_t rec_stride;  // records between consecutive rows
+    uint16_t upr;         // 8-sample units per row
+    uint16_t nunits;      // upr * rows
+    uint16_t nunits_mod;  // nunits modulo the consumer threads of a group
+    uint16_t o0;          // byte offset of the item's first sample inside a staged row
+    uint16_t rowb;        // staged row pitch (bytes)
+    uint8_t  src_plane;
+    uint8_t  flags;       // 1 = first tile of the slice-plane (zero rows above), 2 = leftmost chunk, 4 = rightmost chunk
+    uint8_t  nrows;
+    uint8_t  pad;
+};
+static_assert(sizeof(FastItemDesc) == 32, "two 16-byte loads per item");
+struct FastPlan {
+    std::vector<FastItemDesc> items;
+    int32_t items_per_frame = 0, row_bytes[4] = {0, 0, 0, 0}, buf_bytes = 0, nbuf = 0, smem_bytes = 0;
+};
 bool pixel_fast_geometry_ok(const Layout &L, const SliceGeom *slices, int nslices);
-cudaError_t configure_pixel_fast(const Layout &L);
-void launch_pixel_fast(const EncDeviceTables &t, const EncBatch &b, int max_plane_width, int num_sms, cudaStream_t s,
-                       const uint8_t *const *frame0_planes, long long frame_stride, const SliceGeom *host_slices, int nslices);
+void build_pixel_fast_plan(const Tables &tab, FastPlan &plan);
+cudaError_t configure_pixel_fast(const FastPlan &plan);
+void launch_pixel_fast(const EncDeviceTables &t, const EncBatch &b, const FastPlan &plan, const FastItemDesc *d_items, int num_sms,
+                       cudaStream_t s, const uint8_t *const *frame0_planes, long long frame_stride);
 
 } // namespace ffv1

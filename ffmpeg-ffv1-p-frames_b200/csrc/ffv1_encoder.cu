@@ -59,6 +59,7 @@ struct FFV1B200Encoder {
     // static device tables
     DevBuf<SliceGeom> d_slices; DevBuf<LineDesc> d_lines; DevBuf<int32_t> d_pc_lines; DevBuf<TileDesc> d_tiles;
     DevBuf<CtxTile> d_ctiles;
+    FastPlan fast_plan; DevBuf<FastItemDesc> d_fast_items;
     DevBuf<int16_t> d_quant; DevBuf<uint8_t> d_lut, d_one_pow, d_run_pc; DevBuf<uint16_t> d_prefix; DevBuf<int32_t> d_prefix_len;
     DevBuf<uint8_t> d_gprefix; DevBuf<int32_t> d_gprefix_len;
     // shared intermediates
@@ -223,7 +224,7 @@ int enqueue_kernels(FFV1B200Encoder *e, Slot &sl, cudaStream_t s)
         for (int f = 1; f < nframes && fstride >= 0; f++)
             for (int i = 0; i < e->cfg.nb_src_planes; i++)
                 if ((long long)(sl.h_planes.p[f * 4 + i] - sl.h_planes.p[(f - 1) * 4 + i]) != fstride) { fstride = -1; break; }
-        launch_pixel_fast(t, b, e->max_plane_width, e->num_sms, s, sl.h_planes.p, fstride, e->tab.slices.data(), (int)e->tab.slices.size());
+        launch_pixel_fast(t, b, e->fast_plan, e->d_fast_items.p, e->num_sms, s, sl.h_planes.p, fstride);
     }
     else         launch_pixel(t, b, s);
     cudaEventRecord(sl.ev[1], s);
@@ -365,7 +366,11 @@ int ffv1b200_enc_open(FFV1B200Encoder **out, const FFV1B200EncParams *p)
     CU_TRY(configure_kernels(L));
     e->fast_pixel = pixel_fast_geometry_ok(L, e->tab.slices.data(), (int)e->tab.slices.size());
     if (const char *v = getenv("FFV1B200_PIXEL")) { if (!strcmp(v, "generic")) e->fast_pixel = false; }
-    if (e->fast_pixel) CU_TRY(configure_pixel_fast(L));
+    if (e->fast_pixel) {
+        build_pixel_fast_plan(e->tab, e->fast_plan);
+        CU_TRY(configure_pixel_fast(e->fast_plan));
+        CU_TRY(e->d_fast_items.upload(e->fast_plan.items.data(), e->fast_plan.items.size(), e->s_comp));
+    }
     e->ctx_replay = ctx_replay_supported(L);
     if (const char *v = getenv("FFV1B200_REPLAY")) { if (!strcmp(v, "warp")) e->ctx_replay = false; }
     if (e->ctx_replay) CU_TRY(configure_ctx_replay(L));

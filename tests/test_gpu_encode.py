@@ -121,3 +121,18 @@ def test_pipelined_submit_collect(B):
     with pytest.raises(B.FFV1Error):
         lib_pending = B.lib().ffv1b200_enc_collect(g._h, None, 0, None, None)
         raise B.FFV1Error(lib_pending, "no batch in flight") if lib_pending < 0 else AssertionError
+
+@pytest.mark.parametrize("cid", ["c2_gop_range_24sl", "c3_422p10_ctx1", "ctx1_8bit_range", "v1_10bit", "default_big_autov3"])
+def test_pixel_fast_row_copy_path(B, cid, monkeypatch):
+    """k_pixel_fast's fallback for device frames that are not equally spaced (one bulk copy per row instead of one
+    tensor-map request per item) must give the same packets"""
+    case = [c for c in CASES if c[0] == cid][0]
+    _, w, h, fmt, opts, kind, n = case
+    frames = make_frames(case)
+    o = O.Encoder(w, h, fmt, **opts)
+    monkeypatch.setenv("FFV1B200_PIXEL_ROWCOPY", "1")
+    g = B.FFV1Encoder(w, h, fmt, max_batch_frames=4, **gpu_opts(opts))
+    got = g.encode_batch(frames)
+    for i, f in enumerate(frames):
+        exp, key = o.encode(f)
+        assert got[i][0] == exp and got[i][1] == key, "packet %d differs" % i
