@@ -165,7 +165,7 @@ def cpu_baseline_leg(nframes=48):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=1024, help="frames per step per GPU (multiple of the GOP size)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])

@@ -60,6 +60,7 @@ struct FFV1B200Encoder {
     DevBuf<SliceGeom> d_slices; DevBuf<LineDesc> d_lines; DevBuf<int32_t> d_pc_lines; DevBuf<TileDesc> d_tiles;
     DevBuf<CtxTile> d_ctiles;
     FastPlan fast_plan; DevBuf<FastItemDesc> d_fast_items;
+    FusedPlan fused_plan; DevBuf<FusedSeg> d_fused_segs; DevBuf<FusedSlice> d_fused_slices;
     DevBuf<int16_t> d_quant; DevBuf<uint8_t> d_lut, d_one_pow, d_run_pc; DevBuf<uint16_t> d_prefix; DevBuf<int32_t> d_prefix_len;
     DevBuf<uint8_t> d_gprefix; DevBuf<int32_t> d_gprefix_len;
     // shared intermediates
@@ -71,7 +72,7 @@ struct FFV1B200Encoder {
     uint64_t submitted = 0, collected = 0;      // batch counters; slot of batch k = k % kSlots
     int carry_next = 0;                          // ring index holding the state after the last submitted batch
     double dec_per_sample = 5.0;
-    bool state_in_smem = true, fast_pixel = false, ctx_replay = false;
+    bool state_in_smem = true, fast_pixel = false, ctx_replay = false, fused_replay = false;
     int max_plane_width = 0, num_sms = 148;
     FFV1B200EncStats stats{};
     int last_slot = 0;
@@ -139,7 +140,7 @@ int alloc_buffers(FFV1B200Encoder *e)
     }
     const size_t g = e->cfg.gop_size > 0 ? e->cfg.gop_size : 1;
     const size_t nseg_max = (F + g - 1) / g + 1;
-    if (e->ctx_replay) {
+    if (e->ctx_replay && !e->fused_replay) {
         const size_t nchains = nseg_max * L.nslices * L.npc;
         CU_TRY(e->d_line_pos.alloc((size_t)L.lines_per_frame * F));
         CU_TRY(e->d_ctx_hist.alloc((size_t)L.ctiles_per_frame * L.ctx_count * F));
@@ -148,7 +149,7 @@ int alloc_buffers(FFV1B200Encoder *e)
         CU_TRY(e->d_list_order.alloc(nchains * L.ctx_count));
         CU_TRY(e->d_lists.alloc((size_t)L.samples_per_frame * F));
     }
-    if ((!e->state_in_smem && !e->ctx_replay) || L.golomb)
+    if ((!e->state_in_smem && !e->ctx_replay && !e->fused_replay) || L.golomb)
         CU_TRY(e->d_state_seg.alloc(state_bytes * nseg_max));            // one state set per GOP segment of a batch
     for (Slot &sl : e->slot) {
         CU_TRY(sl.d_planes.alloc(F * 4)); CU_TRY(sl.h_planes.alloc(F * 4));
@@ -228,14 +229,15 @@ int enqueue_kernels(FFV1B200Encoder *e, Slot &sl, cudaStream_t s)
     }
     else         launch_pixel(t, b, s);
     cudaEventRecord(sl.ev[1], s);
-    if (e->ctx_replay) launch_ctx_replay(t, b, s);
+    if (e->fused_replay) launch_fused_replay(t, b, e->fused_plan, e->d_fused_segs.p, e->d_fused_slices.p, s);
+    else if (e->ctx_replay) launch_ctx_replay(t, b, s);
     else if (!L.golomb) launch_replay(t, b, s);
     cudaEventRecord(sl.ev[2], s);
     if (!L.golomb) launch_rangecode(t, b, s); else launch_golomb(t, b, s);
     cudaEventRecord(sl.ev[3], s);
     launch_pack(t, b, s);
     cudaEventRecord(sl.ev[4], s);
-    e->stats.kernel_launches += L.golomb ? 4 : (e->ctx_replay ? 9 : 5);
+    e->stats.kernel_launches += L.golomb ? 4 : (e->fused_replay ? 5 : (e->ctx_replay ? 9 : 5));
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaMemcpyAsync(sl.h_status.p, sl.d_status.p, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost, s));
     CU_TRY(cudaMemcpyAsync(sl.h_pkt_size.p, sl.d_pkt_size.p, sizeof(uint32_t) * nframes, cudaMemcpyDeviceToHost, s));
@@ -374,6 +376,16 @@ int ffv1b200_enc_open(FFV1B200Encoder **out, const FFV1B200EncParams *p)
     e->ctx_replay = ctx_replay_supported(L);
     if (const char *v = getenv("FFV1B200_REPLAY")) { if (!strcmp(v, "warp")) e->ctx_replay = false; }
     if (e->ctx_replay) CU_TRY(configure_ctx_replay(L));
+    // experimental: the whole state replay in one kernel (FFV1B200_REPLAY=fused); bit-exact, but measured slower than the
+    // per-context list kernels on B200 (profiles/r01_replay_fused.txt), so it is not the default
+    build_fused_plan(e->tab, e->fused_plan);
+    e->fused_replay = false;
+    if (const char *v = getenv("FFV1B200_REPLAY")) { if (!strcmp(v, "fused")) e->fused_replay = e->fused_plan.ok; }
+    if (e->fused_replay) {
+        CU_TRY(configure_fused_replay(e->fused_plan));
+        CU_TRY(e->d_fused_segs.upload(e->fused_plan.segs.data(), e->fused_plan.segs.size(), e->s_comp));
+        CU_TRY(e->d_fused_slices.upload(e->fused_plan.slices.data(), e->fused_plan.slices.size(), e->s_comp));
+    }
     for (auto &g : e->tab.slices) for (int pl = 0; pl < L.nplanes; pl++) e->max_plane_width = std::max(e->max_plane_width, g.pw[pl]);
     CU_TRY(cudaDeviceGetAttribute(&e->num_sms, cudaDevAttrMultiProcessorCount, e->device));
 
