@@ -25,8 +25,9 @@ FRAME_BYTES = W * H * 3 // 2
 SAMPLES = W * H * 3 // 2
 ALGO_BYTES_PER_SAMPLE = 5          # 1 B read + 4 B (context,diff) record written
 # dram__bytes_read.sum + dram__bytes_write.sum of k_pixel_fast per frame, from the ncu --set full capture summarised in
-# profiles/r01_k_pixel_fast.txt (870.6 MB + 3128.2 MB for a 256-frame launch)
-TRAFFIC_BYTES_PER_FRAME = (870576896 + 3128153000) / 256
+# profiles/r01_k_pixel_fast.txt (6.015 GB + 12.686 GB for a 1024-frame launch; the reads include the two halo rows per
+# 32-row item, the 16-byte alignment blocks either side of a 320-byte row and DRAM's 64-byte access granularity)
+TRAFFIC_BYTES_PER_FRAME = (6014702000 + 12686427000) / 1024
 METRIC = "1080p yuv420p8 FFV1 level-3 GOP-16 encode throughput (bit-exact)"
 WORKLOAD = "1080p yuv420p8 synthetic noise clip, FFV1 level 3, GOP 16 (P-frames), coder=1, context=0, 24 slices, slicecrc"
 

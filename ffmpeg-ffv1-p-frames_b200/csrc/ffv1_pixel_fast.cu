@@ -249,8 +249,9 @@ __device__ __forceinline__ void fast_unit8_packed(const unsigned char *crow, con
         const int ctx = lds_s16<128>(aV) + q1 + lds_s16<2>(aH);
         if (n < 7) q1 = lds_s16<0>(aH);
         // context < 0: negate context and residual (ffv1enc.c:311-316); fold() to int8 and sign-extend to 16 bits in the PRMT
-        const int sgn = ctx >> 31;
-        const uint32_t sel = (uint32_t)(((n & 1) ? 0x54A2 : 0x5480) - 0x11 * sgn);
+        // the selector is built on the FMA pipe (IMAD.HI + IMAD): the ALU pipe is what bounds this kernel
+        const int sgn = __mulhi(ctx, 1);                                           // -1 / 0
+        const uint32_t sel = (uint32_t)(sgn * -0x11 + ((n & 1) ? 0x54A2 : 0x5480));
         out[n] = prmt(MG[n >> 1], (uint32_t)abs(ctx), sel);
     }
 }
@@ -534,6 +535,8 @@ static void launch_t(const EncDeviceTables &t, const EncBatch &b, const FastPlan
     PFN_cuTensorMapEncodeTiled_v12000 enc = tensor ? tensor_map_encoder() : nullptr;
     tensor = tensor && enc != nullptr;
     const Layout &L = t.layout;
+    CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+    if (const char *v = getenv("FFV1B200_TMA_L2")) { const int q = atoi(v); promo = q == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : (q == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : (q == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B)); }
     for (int p = 0; p < L.nplanes && tensor; p++) {
         const int sp = L.plane[p].src_plane;
         const int rows = (L.height + (1 << L.plane[p].vshift) - 1) >> L.plane[p].vshift;
@@ -543,7 +546,7 @@ static void launch_t(const EncDeviceTables &t, const EncBatch &b, const FastPlan
         const cuuint32_t estr[3] = {1u, 1u, 1u};
         if (strides[1] & 15) { tensor = false; break; }
         CUresult r = enc(&maps.m[sp], CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<uint8_t *>(frame0_planes[sp]), dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, promo,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) tensor = false;
     }
