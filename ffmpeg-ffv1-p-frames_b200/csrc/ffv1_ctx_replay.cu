@@ -17,6 +17,7 @@
 //                  at the recorded positions of the decision stream that k_rangecode consumes
 #include "ffv1_enc_kernels.cuh"
 #include <cstdlib>
+#include <cstring>
 
 namespace ffv1 {
 
@@ -253,6 +254,117 @@ __global__ void __launch_bounds__(kScatterThreads) k_ctx_scatter(const EncDevice
     }
 }
 
+// ------------------------------------------------------------------------------------------------ k_ctx_scatter_sm
+// Same result as k_ctx_scatter, but the tile is first sorted by context in SHARED memory (stable counting sort: one warp
+// per line, per-line context histograms, ballot ranks inside a 32-sample group) and then written to the per-context
+// lists as contiguous runs, one warp per run.  k_ctx_scatter's 8-byte stores land in ~20 different lists per
+// 32-sample group; with thousands of tiles in flight the half-written sectors do not survive in L2 until their
+// neighbours arrive, which costs 2x the DRAM traffic and stalls the warps on the store path.
+constexpr int kScatterSmThreads = 512;
+constexpr int kScatterSmMaxSamples = 5632;               // per tile (16 lines of <= 352 samples): 44 KB of entries
+
+__global__ void __launch_bounds__(kScatterSmThreads) k_ctx_scatter_sm(const EncDeviceTables T, const EncBatch B)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ uint32_t s_wtot[kScatterSmThreads / 32];
+    const Layout &L = T.layout;
+    if (B.status[0]) return;
+    const int nctx = L.ctx_count, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t *s_wh = reinterpret_cast<uint32_t *>(smem_raw);            // [8][nctx] per-line counts, two lines per word
+    uint32_t *s_goff = s_wh + 8 * nctx;                                 // [nctx] where the tile's run of a context goes in its list
+    uint16_t *s_start = reinterpret_cast<uint16_t *>(s_goff + nctx);    // [nctx] start of the run inside s_ent
+    uint16_t *s_cnt = s_start + ((nctx + 7) & ~7);                      // [nctx]
+    uint2 *s_ent = reinterpret_cast<uint2 *>(s_cnt + ((nctx + 7) & ~7));
+    const int tile = blockIdx.x, f = blockIdx.y;
+    const CtxTile ct = T.ctiles[tile];
+    const SliceGeom &g = T.slices[ct.slice];
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const int seg = B.frame_seg[f];
+    const int f0 = B.seg_first[seg], seglen = B.seg_first[seg + 1] - f0;
+    const int chain = (seg * L.nslices + ct.slice) * L.npc + ct.pc;
+    for (int i = tid; i < 8 * nctx; i += kScatterSmThreads) s_wh[i] = 0u;
+    {
+        const uint32_t *tile_base = B.ctx_hist + ((size_t)f * L.ctiles_per_frame + tile) * nctx;
+        const uint32_t *lstart = B.list_start + (size_t)chain * nctx;
+        for (int c = tid; c < nctx; c += kScatterSmThreads) s_goff[c] = tile_base[c] + lstart[c];
+    }
+    __syncthreads();
+    const uint32_t *rec_slice = B.rec + (size_t)f * L.rec_per_frame + g.rec_first;
+    const int32_t *my_lines = T.pc_lines + g.pc_line_first[ct.pc] + ct.first;
+    const uint32_t *recp = nullptr;
+    int w = 0;
+    uint32_t pos = 0;
+    if (warp < ct.nlines) {
+        const int line = my_lines[warp];
+        const LineDesc ld = T.lines[g.line_first + line];
+        recp = rec_slice + ld.rec_off;
+        w = ld.w;
+        pos = B.line_pos[(size_t)f * L.lines_per_frame + g.line_first + line];
+        uint32_t *wh = s_wh + (warp >> 1) * nctx;
+        const uint32_t one = (warp & 1) ? 0x10000u : 1u;
+        for (int x = lane; x < w; x += 32) atomicAdd(&wh[recp[x] >> 16], one);
+    }
+    __syncthreads();
+    // per context (two per thread): counts of the 16 lines -> exclusive offsets in place, total; block scan of the totals
+    uint32_t cc[2] = {0u, 0u};
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+        const int c = 2 * tid + j;
+        if (c < nctx) {
+            uint32_t run = 0;
+#pragma unroll
+            for (int h = 0; h < 8; h++) {
+                const uint32_t v = s_wh[h * nctx + c];
+                const uint32_t lo = v & 0xFFFFu, hi = v >> 16;
+                s_wh[h * nctx + c] = run | ((run + lo) << 16);
+                run += lo + hi;
+            }
+            s_cnt[c] = (uint16_t)run;
+            cc[j] = run;
+        }
+    }
+    const uint32_t pair = cc[0] + cc[1];
+    const uint32_t incl = cr_incl_scan(pair, lane);
+    if (lane == 31) s_wtot[warp] = incl;
+    __syncthreads();
+    {
+        uint32_t base = incl - pair;
+        for (int ww = 0; ww < warp; ww++) base += s_wtot[ww];
+        if (2 * tid < nctx) s_start[2 * tid] = (uint16_t)base;
+        if (2 * tid + 1 < nctx) s_start[2 * tid + 1] = (uint16_t)(base + cc[0]);
+    }
+    __syncthreads();
+    // stable placement: {position of the symbol's first decision, residual | frame << 16}
+    if (warp < ct.nlines) {
+        uint32_t *wh = s_wh + (warp >> 1) * nctx;
+        const int sh = (warp & 1) * 16;
+        for (int x0 = 0; x0 < w; x0 += 32) {
+            const bool act = x0 + lane < w;
+            const uint32_t r = act ? recp[x0 + lane] : 0u;
+            const uint32_t ctx = r >> 16;
+            const uint32_t nd = act ? decisions_of((int)(int16_t)(r & 0xFFFFu)) : 0u;
+            const uint32_t in = cr_incl_scan(nd, lane);
+            const uint32_t grp = __match_any_sync(0xFFFFFFFFu, act ? ctx : 0xFFFFFFFFu);
+            const uint32_t rank = __popc(grp & lt_mask);
+            uint32_t off = 0u;
+            if (act && rank == 0u) off = (atomicAdd(&wh[ctx], (uint32_t)__popc(grp) << sh) >> sh) & 0xFFFFu;
+            off = __shfl_sync(0xFFFFFFFFu, off, (__ffs(grp) - 1) & 31);
+            if (act) s_ent[(uint32_t)s_start[ctx] + off + rank] = make_uint2(pos + in - nd, (r & 0xFFFFu) | ((uint32_t)f << 16));
+            pos += __shfl_sync(0xFFFFFFFFu, in, 31);
+        }
+    }
+    __syncthreads();
+    // runs -> lists: one warp per context, 8 bytes per lane, contiguous
+    uint2 *list = B.lists + (size_t)f0 * L.samples_per_frame + (size_t)seglen * g.list_off[ct.pc];
+    for (int c = warp; c < nctx; c += kScatterSmThreads / 32) {
+        const uint32_t n = s_cnt[c];
+        if (n == 0u) continue;
+        uint2 *dst = list + s_goff[c];
+        const uint2 *src = s_ent + s_start[c];
+        for (uint32_t i = lane; i < n; i += 32) dst[i] = src[i];
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ k_replay_ctx
 // Lane <-> state slot permutation.  put_symbol_inline visits the slots of a symbol in the order
 //   0 | 1..e+1 | 22+e-1 .. 22 | 11+e                                  (ffv1enc.c:202-229, e <= 9)
@@ -472,7 +584,7 @@ __device__ __noinline__ void replay_symbol_serial(uint8_t *row, const uint8_t *l
 }
 
 template <int EMAX, int THREADS>
-__global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_replay_grp(const EncDeviceTables T, const EncBatch B)
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_replay_grp(const EncDeviceTables T, const EncBatch B, const int window)
 {
     constexpr int G = 16;
     static_assert(3 * EMAX + 3 <= G, "roles must fit a group");
@@ -514,12 +626,19 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_replay_grp(const En
     const int rot = (g - 8) & 31;                                    // rotr(bits, rot) puts my bit at bit 8
     const int t0 = sg.ct_first[pc];
 
-    for (int f = f0; f < f1; f++) {
-        __syncthreads();                                             // model loaded / previous frame finished
+    // Window after window (`window` context tiles of a frame): all warps of the CTA work on the same stretch of the
+    // (frame, slice, plane context) decision region, which is then completed while it is still in L2 (with whole frames
+    // per round, 296 resident CTAs x 0.8 MB of half-written sectors thrashed the 126 MB L2: 3x DRAM traffic).
+    const int nt = sg.ct_count[pc];
+    for (int f = f0; f < f1; f++)
+    for (int tw = 0; tw < nt; tw += window) {
+        __syncthreads();                                             // model loaded / previous window finished
         if (tid == 0) s_next = 0;
         __syncthreads();
-        const uint32_t *before = B.ctx_hist + ((size_t)f * L.ctiles_per_frame + t0) * nctx;
-        const uint32_t *before_next = B.ctx_hist + ((size_t)(f + 1) * L.ctiles_per_frame + t0) * nctx;
+        const bool last_win = tw + window >= nt;
+        const uint32_t *before = B.ctx_hist + ((size_t)f * L.ctiles_per_frame + t0 + tw) * nctx;
+        const uint32_t *before_next = last_win ? B.ctx_hist + ((size_t)(f + 1) * L.ctiles_per_frame + t0) * nctx
+                                               : B.ctx_hist + ((size_t)f * L.ctiles_per_frame + t0 + tw + window) * nctx;
         uint32_t n_left = 0u, st = 0u;
         uint2 nx = make_uint2(0u, 0u);
         int c = -1;
@@ -538,7 +657,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_replay_grp(const En
                     const int cc = order[oi];
                     const uint32_t ntot = lcount[cc];
                     if (ntot == 0u) { exhausted = true; break; }     // contexts are ordered by the length of their chain list
-                    const uint32_t b0 = before[cc], b1 = f + 1 < f1 ? before_next[cc] : ntot;
+                    const uint32_t b0 = before[cc], b1 = (!last_win || f + 1 < f1) ? before_next[cc] : ntot;
                     if (b1 == b0) continue;
                     c = cc; n_left = b1 - b0;
                     lp = chain_list + lstart[cc] + b0;
@@ -609,13 +728,16 @@ bool ctx_replay_supported(const Layout &L)
 }
 
 int ctx_scatter_smem_bytes(const Layout &L) { return (kScatterThreads / 32) * L.ctx_count * 4; }
+int ctx_scatter_sm_smem_bytes(const Layout &L) { return 9 * L.ctx_count * 4 + 2 * ((L.ctx_count + 7) & ~7) * 2 + kScatterSmMaxSamples * 8; }
 
 cudaError_t configure_ctx_replay(const Layout &L)
 {
+    cudaError_t e = cudaFuncSetAttribute(k_ctx_scatter_sm, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx_scatter_sm_smem_bytes(L));
+    if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(k_ctx_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx_scatter_smem_bytes(L));
 }
 
-void launch_ctx_replay(const EncDeviceTables &t, const EncBatch &b, cudaStream_t s)
+void launch_ctx_replay(const EncDeviceTables &t, const EncBatch &b, int max_tile_samples, cudaStream_t s)
 {
     const Layout &L = t.layout;
     const int nchains = b.nseg * L.nslices * L.npc;
@@ -624,14 +746,23 @@ void launch_ctx_replay(const EncDeviceTables &t, const EncBatch &b, cudaStream_t
     k_ctx_scan<<<nchains, kScanThreads, 0, s>>>(t, b);
     const int n = b.nframes * L.nslices * L.npc;
     k_dec_layout<<<(n + 127) / 128, 128, 0, s>>>(t, b);
-    dim3 stiles((L.ctiles_per_frame + kScatterThreads / 32 - 1) / (kScatterThreads / 32), b.nframes);
-    k_ctx_scatter<<<stiles, kScatterThreads, ctx_scatter_smem_bytes(L), s>>>(t, b);
+    // tiles that fit the shared-memory sort (slices up to 352 samples wide) take the staged scatter
+    static int staged = -1;
+    if (staged < 0) { const char *v = getenv("FFV1B200_SCATTER"); staged = (v && !strcmp(v, "direct")) ? 0 : 1; }
+    if (staged && max_tile_samples <= kScatterSmMaxSamples) {
+        k_ctx_scatter_sm<<<tiles, kScatterSmThreads, ctx_scatter_sm_smem_bytes(L), s>>>(t, b);
+    } else {
+        dim3 stiles((L.ctiles_per_frame + kScatterThreads / 32 - 1) / (kScatterThreads / 32), b.nframes);
+        k_ctx_scatter<<<stiles, kScatterThreads, ctx_scatter_smem_bytes(L), s>>>(t, b);
+    }
     static int grp = -1;
     if (grp < 0) { const char *v = getenv("FFV1B200_REPLAY_GROUPS"); grp = v ? atoi(v) : 2; }
     // 8-bit content (residuals folded to <= 9 bits): two lists per warp; a frame's decision area must fit 32-bit offsets
     const bool grp_ok = L.coded_bits <= 9 && L.dec_per_frame < 0x7FFFFFFFu;
-    if (grp == 1 && grp_ok) k_replay_grp<4, 1024><<<nchains, 1024, L.ctx_count * 32, s>>>(t, b);
-    else if (grp == 2 && grp_ok) k_replay_grp<4, 512><<<nchains, 512, L.ctx_count * 32, s>>>(t, b);
+    static int window = -1;
+    if (window < 0) { const char *v = getenv("FFV1B200_REPLAY_WINDOW"); window = v ? atoi(v) : 8; if (window < 1) window = 1 << 20; }
+    if (grp == 1 && grp_ok) k_replay_grp<4, 1024><<<nchains, 1024, L.ctx_count * 32, s>>>(t, b, window);
+    else if (grp == 2 && grp_ok) k_replay_grp<4, 512><<<nchains, 512, L.ctx_count * 32, s>>>(t, b, window);
     else if (L.coded_bits <= 10) k_replay_ctx<false><<<nchains, kCtxThreads, L.ctx_count * 32, s>>>(t, b);
     else                    k_replay_ctx<true><<<nchains, kCtxThreads, L.ctx_count * 32, s>>>(t, b);
 }

@@ -73,7 +73,7 @@ struct FFV1B200Encoder {
     int carry_next = 0;                          // ring index holding the state after the last submitted batch
     double dec_per_sample = 5.0;
     bool state_in_smem = true, fast_pixel = false, ctx_replay = false, fused_replay = false;
-    int max_plane_width = 0, num_sms = 148;
+    int max_plane_width = 0, num_sms = 148, max_ctile_samples = 0;
     FFV1B200EncStats stats{};
     int last_slot = 0;
 };
@@ -230,7 +230,7 @@ int enqueue_kernels(FFV1B200Encoder *e, Slot &sl, cudaStream_t s)
     else         launch_pixel(t, b, s);
     cudaEventRecord(sl.ev[1], s);
     if (e->fused_replay) launch_fused_replay(t, b, e->fused_plan, e->d_fused_segs.p, e->d_fused_slices.p, s);
-    else if (e->ctx_replay) launch_ctx_replay(t, b, s);
+    else if (e->ctx_replay) launch_ctx_replay(t, b, e->max_ctile_samples, s);
     else if (!L.golomb) launch_replay(t, b, s);
     cudaEventRecord(sl.ev[2], s);
     if (!L.golomb) launch_rangecode(t, b, s); else launch_golomb(t, b, s);
@@ -387,6 +387,12 @@ int ffv1b200_enc_open(FFV1B200Encoder **out, const FFV1B200EncParams *p)
         CU_TRY(e->d_fused_slices.upload(e->fused_plan.slices.data(), e->fused_plan.slices.size(), e->s_comp));
     }
     for (auto &g : e->tab.slices) for (int pl = 0; pl < L.nplanes; pl++) e->max_plane_width = std::max(e->max_plane_width, g.pw[pl]);
+    for (const CtxTile &ct : e->tab.ctiles) {
+        const SliceGeom &g = e->tab.slices[ct.slice];
+        int ns = 0;
+        for (int i = 0; i < ct.nlines; i++) ns += e->tab.lines[g.line_first + e->tab.pc_lines[g.pc_line_first[ct.pc] + ct.first + i]].w;
+        e->max_ctile_samples = std::max(e->max_ctile_samples, ns);
+    }
     CU_TRY(cudaDeviceGetAttribute(&e->num_sms, cudaDevAttrMultiProcessorCount, e->device));
 
     cudaStream_t s = e->s_comp;
