@@ -642,6 +642,33 @@ int ffv1b200_enc_encode_device(FFV1B200Encoder *e, int nframes, const void *cons
     return nframes;
 }
 
+int ffv1b200_enc_encode_cuda(FFV1B200Encoder *e, int nframes, const void *const *d_planes, const int *linesizes,
+                             uint8_t *out, size_t out_cap, FFV1B200Packet *pkts, size_t *needed)
+{
+    if (!e || !out || !pkts) return fail(FFV1B200_ERR_EINVAL, "null argument");
+    if (e->submitted != e->collected) return fail(FFV1B200_ERR_EINVAL, "collect the batches in flight first");
+    CU_TRY(cudaSetDevice(e->device));
+    Slot &sl = e->slot[e->submitted % kSlots];
+    if (!sl.d_out.p) CU_TRY(sl.d_out.alloc((size_t)e->max_batch * ((size_t)e->cfg.frame_bytes() / 2 + 65536)));
+    size_t total = 0;
+    int r;
+    for (;;) {                                                  // the packets are assembled in the slot's own device buffer
+        r = ffv1b200_enc_encode_device(e, nframes, d_planes, linesizes, sl.d_out.p, sl.d_out.n, pkts, &total, nullptr);
+        if (r != FFV1B200_ERR_BUFFER_TOO_SMALL) break;
+        CU_TRY(sl.d_out.alloc(total + 4096));
+    }
+    if (r < 0) return r;
+    if (needed) *needed = total;
+    if (total > out_cap) {
+        // the batch is coded (the model state has moved on): the caller sized `out` from FFV1B200EncInfo.frame_bytes
+        return fail(FFV1B200_ERR_BUFFER_TOO_SMALL, "output buffer too small: need " + std::to_string(total) + " bytes");
+    }
+    CU_TRY(cudaMemcpyAsync(out, sl.d_out.p, total, cudaMemcpyDeviceToHost, e->s_out));
+    CU_TRY(cudaStreamSynchronize(e->s_out));
+    e->stats.d2h_bytes += (int64_t)total;
+    return r;
+}
+
 int ffv1b200_enc_stats(const FFV1B200Encoder *e, FFV1B200EncStats *s)
 {
     if (!e || !s) return FFV1B200_ERR_EINVAL;

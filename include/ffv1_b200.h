@@ -144,6 +144,13 @@ int  ffv1b200_enc_encode_device(FFV1B200Encoder *enc, int nframes,
                                 void *d_out, size_t d_out_cap, FFV1B200Packet *pkts, size_t *needed,
                                 void *stream);
 
+/* AV_PIX_FMT_CUDA frames in, packets out to HOST memory: what an AVCodec.encode2 needs when avctx->pix_fmt is
+ * AV_PIX_FMT_CUDA (frame->data[i] = CUdeviceptr, sw_format from avctx->hw_frames_ctx; nvenc's use of the same frames:
+ * libavcodec/nvenc.c:1162-1170).  Same packets as ffv1b200_enc_encode_host on the same pixels. */
+int  ffv1b200_enc_encode_cuda(FFV1B200Encoder *enc, int nframes,
+                              const void *const *d_planes, const int *linesizes,
+                              uint8_t *out, size_t out_cap, FFV1B200Packet *pkts, size_t *needed);
+
 int  ffv1b200_enc_stats(const FFV1B200Encoder *enc, FFV1B200EncStats *stats);
 
 /* Test hook: run only the per-pixel pass on frames already uploaded by the last encode call and copy the

@@ -21,6 +21,7 @@
 #include "libavutil/imgutils.h"
 #include "libavutil/mem.h"
 #include "libavutil/log.h"
+#include "libavutil/hwcontext.h"
 #include "../include/ffv1_b200.h"
 
 /* ------------------------------------------------------------------------------------------------ encoder */
@@ -28,6 +29,7 @@ typedef struct B200EncContext {
     const AVClass *class;              /* must be first (AVOptions) */
     int ec, ac, context_model;         /* same names / meaning as FFV1Context.ec/.ac/.context_model */
     int batch, device;
+    int cuda_frames;                   /* avctx->pix_fmt == AV_PIX_FMT_CUDA: frame->data[] are device pointers */
     FFV1B200Encoder *enc;
     AVFrame **queue;                   /* frames waiting for a full batch (references) */
     int nqueued;
@@ -54,7 +56,10 @@ static int b200_run_batch(AVCodecContext *avctx)
             linesizes[4 * i + p] = s->queue[i]->linesize[p];
         }
     for (;;) {
-        ret = ffv1b200_enc_encode_host(s->enc, s->nqueued, planes, linesizes, s->outbuf, s->outcap, s->pkts, &needed);
+        if (s->cuda_frames)
+            ret = ffv1b200_enc_encode_cuda(s->enc, s->nqueued, (const void *const *)planes, linesizes, s->outbuf, s->outcap, s->pkts, &needed);
+        else
+            ret = ffv1b200_enc_encode_host(s->enc, s->nqueued, planes, linesizes, s->outbuf, s->outcap, s->pkts, &needed);
         if (ret != FFV1B200_ERR_BUFFER_TOO_SMALL)
             break;
         av_freep(&s->outbuf);
@@ -84,13 +89,22 @@ static av_cold int b200_encode_init(AVCodecContext *avctx)
     const uint8_t *ed;
     int edsize, ret;
 
+    enum AVPixelFormat sw_fmt = avctx->pix_fmt;
     if (avctx->pix_fmt == AV_PIX_FMT_CUDA) {
-        av_log(avctx, AV_LOG_ERROR, "AV_PIX_FMT_CUDA input: build with FFV1B200_HWFRAMES (see INTEGRATION.md)\n");
-        return AVERROR(ENOSYS);
+        /* frames live in device memory (hwcontext_cuda.h:31-40); the software format comes from the frames context,
+         * as in nvenc.c:412-421 */
+        AVHWFramesContext *fc;
+        if (!avctx->hw_frames_ctx) {
+            av_log(avctx, AV_LOG_ERROR, "AV_PIX_FMT_CUDA input needs avctx->hw_frames_ctx\n");
+            return AVERROR(EINVAL);
+        }
+        fc = (AVHWFramesContext *)avctx->hw_frames_ctx->data;
+        sw_fmt = fc->sw_format;
+        s->cuda_frames = 1;
     }
     memset(&p, 0, sizeof(p));
     p.width = avctx->width; p.height = avctx->height;
-    p.pix_fmt = av_get_pix_fmt_name(avctx->pix_fmt);
+    p.pix_fmt = av_get_pix_fmt_name(sw_fmt);
     p.gop_size = avctx->gop_size;
     p.level = avctx->level;
     p.slices = avctx->slices;
@@ -230,6 +244,7 @@ AVCodec ff_ffv1_b200_encoder = {
         AV_PIX_FMT_YUVA444P9, AV_PIX_FMT_YUVA422P9, AV_PIX_FMT_YUVA420P9,
         AV_PIX_FMT_GRAY16,    AV_PIX_FMT_GRAY8,     AV_PIX_FMT_GBRP9,     AV_PIX_FMT_GBRP10,
         AV_PIX_FMT_GBRP12,    AV_PIX_FMT_GBRP14,    AV_PIX_FMT_YA8,
+        AV_PIX_FMT_CUDA,      /* device-resident frames of any of the above (sw_format in avctx->hw_frames_ctx) */
         AV_PIX_FMT_NONE
     },
     .priv_class     = &b200_enc_class,

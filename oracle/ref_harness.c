@@ -143,6 +143,60 @@ int ffv1ref_enc_frame(void *h, uint8_t *const planes[4], const int linesize[4], 
     return ret;
 }
 
+/* ---- AV_PIX_FMT_CUDA input (drop-in test of the shim's device-frame path).  The reference tree is built without
+ * CONFIG_CUDA here, so the frames context is filled in by hand: a codec only reads sw_format / width / height from it
+ * (nvenc.c:412-421), and the AVFrames carry caller-owned device pointers behind a dummy refcounted buffer. */
+#include "libavutil/hwcontext.h"
+void *ffv1ref_enc_open_named_cuda(const char *name, int w, int h, const char *sw_pix_fmt, int gop, int level, int coder, int context,
+                                  int slices, int slicecrc, int batch)
+{
+    reg();
+    AVCodec *codec = avcodec_find_encoder_by_name(name);
+    enum AVPixelFormat sw = av_get_pix_fmt(sw_pix_fmt);
+    if (!codec || sw == AV_PIX_FMT_NONE) return NULL;
+    RefEnc *e = calloc(1, sizeof(*e));
+    AVHWFramesContext *fc = av_mallocz(sizeof(*fc));
+    e->ctx = avcodec_alloc_context3(codec);
+    e->ctx->width = w; e->ctx->height = h; e->ctx->pix_fmt = AV_PIX_FMT_CUDA;
+    fc->format = AV_PIX_FMT_CUDA; fc->sw_format = sw; fc->width = w; fc->height = h;
+    e->ctx->hw_frames_ctx = av_buffer_create((uint8_t *)fc, sizeof(*fc), NULL, NULL, 0);
+    e->ctx->time_base = (AVRational){1, 25};
+    e->ctx->gop_size = gop; e->ctx->level = level; e->ctx->slices = slices;
+    e->ctx->flags |= AV_CODEC_FLAG_BITEXACT;
+    e->ctx->thread_count = 1;
+    av_opt_set_int(e->ctx->priv_data, "coder", coder, 0);
+    av_opt_set_int(e->ctx->priv_data, "context", context, 0);
+    av_opt_set_int(e->ctx->priv_data, "slicecrc", slicecrc, 0);
+    if (batch > 0) av_opt_set_int(e->ctx->priv_data, "batch", batch, 0);
+    if (avcodec_open2(e->ctx, codec, NULL) < 0) { avcodec_free_context(&e->ctx); free(e); return NULL; }
+    e->frame = av_frame_alloc();
+    return e;
+}
+
+/* planes[] are DEVICE pointers that stay valid until the packet of this frame has been returned */
+int ffv1ref_enc_frame_cuda(void *h, uint8_t *const planes[4], const int linesize[4], uint8_t *dst, int cap, int *key)
+{
+    RefEnc *e = h;
+    AVPacket pkt;
+    int got = 0, ret, i;
+    av_init_packet(&pkt); pkt.data = NULL; pkt.size = 0;
+    av_frame_unref(e->frame);
+    e->frame->format = AV_PIX_FMT_CUDA; e->frame->width = e->ctx->width; e->frame->height = e->ctx->height;
+    e->frame->buf[0] = av_buffer_alloc(1);                 /* refcounted: av_frame_clone() must not copy pixels */
+    for (i = 0; i < 4; i++) { e->frame->data[i] = planes[i]; e->frame->linesize[i] = planes[i] ? linesize[i] : 0; }
+    e->frame->pts = e->pts++;
+    e->frame->sample_aspect_ratio = (AVRational){0, 1};
+    ret = avcodec_encode_video2(e->ctx, &pkt, e->frame, &got);
+    if (ret < 0) return ret;
+    if (!got) return 0;
+    if (pkt.size > cap) { av_packet_unref(&pkt); return -2; }
+    memcpy(dst, pkt.data, pkt.size);
+    ret = pkt.size;
+    if (key) *key = !!(pkt.flags & AV_PKT_FLAG_KEY);
+    av_packet_unref(&pkt);
+    return ret;
+}
+
 void ffv1ref_enc_close(void *h)
 {
     RefEnc *e = h;

@@ -85,6 +85,54 @@ def test_decode_through_avcodec_api(lavc):
         assert np.array_equal(out[:r], np.ascontiguousarray(f).view(np.uint8).reshape(-1))
     lavc.ffv1ref_dec_close(hnd)
 
+@pytest.mark.parametrize("cid", ["c2_gop_range_24sl", "fate_ffv1_golomb", "c3_422p10_ctx1"])
+def test_cuda_frames_through_avcodec_api(lavc, cid):
+    """avctx->pix_fmt = AV_PIX_FMT_CUDA: AVFrames whose data[] are device pointers (sw_format from hw_frames_ctx) must give
+    the packets the reference encoder produces from the same pixels in system memory"""
+    import torch
+    case = [c for c in CASES if c[0] == cid][0]
+    _, w, h, fmt, opts, kind, n = case
+    ref_ed, ref_pkts = encode_named(lavc, "ffv1", case, 0)
+    o = dict(gop=12, level=-1, coder=0, context=0, slices=0, slicecrc=-1); o.update(opts)
+    lavc.ffv1ref_enc_open_named_cuda.restype = ctypes.c_void_p
+    lavc.ffv1ref_enc_open_named_cuda.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_char_p] + [ctypes.c_int] * 7
+    lavc.ffv1ref_enc_frame_cuda.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int),
+                                            ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
+    hnd = lavc.ffv1ref_enc_open_named_cuda(b"ffv1_b200", w, h, fmt.encode(), o["gop"], o["level"], o["coder"], o["context"],
+                                           o["slices"], o["slicecrc"], 4)
+    assert hnd, "avcodec_open2(ffv1_b200, AV_PIX_FMT_CUDA) failed"
+    ed = ctypes.create_string_buffer(1 << 16)
+    ned = lavc.ffv1ref_enc_extradata(hnd, ed, 1 << 16)
+    assert ed.raw[:ned] == ref_ed
+    cap = 65536 + pixfmt.frame_bytes(fmt, w, h) * 4
+    buf = ctypes.create_string_buffer(cap); key = ctypes.c_int()
+    keep, pkts = [], []
+    for f in make_frames(case):
+        planes = split_planes(np.ascontiguousarray(f).view(np.uint8).reshape(-1), fmt, w, h)
+        ptrs, strides = (ctypes.c_void_p * 4)(), (ctypes.c_int * 4)()
+        for i, pl in enumerate(planes):
+            rows, rb = pl.shape[0], pl.shape[1] * pl.itemsize if pl.ndim == 2 else pl.shape[1] * pl.shape[2] * pl.itemsize
+            pitch = (rb + 255) & ~255                                       # device frames with a pitch, like cuMemAllocPitch
+            d = torch.zeros((rows, pitch), dtype=torch.uint8, device="cuda")
+            d[:, :rb] = torch.from_numpy(np.ascontiguousarray(pl).view(np.uint8).reshape(rows, rb)).cuda()
+            keep.append(d)
+            ptrs[i] = d.data_ptr(); strides[i] = pitch
+        torch.cuda.synchronize()
+        r = lavc.ffv1ref_enc_frame_cuda(hnd, ptrs, strides, buf, cap, ctypes.byref(key))
+        assert r >= 0
+        if r:
+            pkts.append((buf.raw[:r], bool(key.value)))
+    while True:
+        r = lavc.ffv1ref_enc_frame(hnd, None, None, 0, 1, 0, 0, buf, cap, ctypes.byref(key))
+        assert r >= 0
+        if not r:
+            break
+        pkts.append((buf.raw[:r], bool(key.value)))
+    lavc.ffv1ref_enc_close(hnd)
+    assert len(pkts) == len(ref_pkts)
+    for i, (a, b) in enumerate(zip(pkts, ref_pkts)):
+        assert a == b, "packet %d differs from the reference encoder's" % i
+
 FATE = [("ffv1", -1, 4), ("ffv1-v0", -1, 0), ("ffv1-v3-yuv420p", 3, 0)]       # tests/fate/vcodec.mak:113-118
 
 @pytest.mark.parametrize("clip", ["vsynth1", "vsynth3"])

@@ -1,0 +1,35 @@
+#!/usr/bin/env python3
+"""Decode throughput of the CUDA decoder on the bench workload (1080p yuv420p8, GOP 16, 24 slices, range coder):
+encodes N synthetic frames with the CUDA encoder, then times ffv1b200_dec_decode_host over the packets (host packets in,
+host frames out, copies included) and checks the round trip.  usage: bench_decode.py [nframes] [batch]"""
+import json, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "ffmpeg-ffv1-p-frames_b200"))
+import numpy as np
+import ffv1_b200
+from oracle import synth
+
+def main():
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+    batch = int(sys.argv[2]) if len(sys.argv) > 2 else n
+    W, H, FMT = 1920, 1080, "yuv420p"
+    g = synth.Noisy(W, H, FMT, 1234)
+    base = [g.next() for _ in range(16)]
+    frames = [base[i % 16] for i in range(n)]
+    enc = ffv1_b200.FFV1Encoder(W, H, FMT, g=16, level=3, coder=1, context=0, slices=24, max_batch_frames=min(n, 256))
+    pkts = [bytes(p) for p, _ in enc.encode_batch(frames)]
+    extradata = enc.extradata
+    enc.close()
+    dec = ffv1_b200.FFV1Decoder(W, H, extradata, max_batch_frames=batch)
+    out = dec.decode_batch(pkts)            # warm-up (+ correctness)
+    for i in (0, 1, n // 2, n - 1):
+        assert np.array_equal(out[i][0], frames[i]), "frame %d does not round-trip" % i
+    t0 = time.perf_counter()
+    out = dec.decode_batch(pkts)
+    dt = time.perf_counter() - t0
+    s = dec.stats()
+    print(json.dumps({"decode_fps": n / dt, "frames": n, "batch": batch, "seconds": dt,
+                      "stats": {k: getattr(s, k) for k, _ in s._fields_}}))
+
+if __name__ == "__main__":
+    main()
