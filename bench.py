@@ -173,6 +173,7 @@ def main():
     ap.add_argument("--ref-frames", type=int, default=32, help="--impl reference: frames per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-decode", action="store_true", help="skip the decoder leg (extra key \"decode\", N=1 only)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -308,6 +309,15 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_leg()
+        if world == 1 and not args.no_decode:
+            try:                                     # decoder of the same stream (extra information, not the metric)
+                sys.path.insert(0, os.path.join(ROOT, "tools"))
+                import bench_decode
+                del frames_dev, out_dev
+                torch.cuda.empty_cache()
+                line["decode"] = bench_decode.run(512, 512)
+            except Exception as ex:
+                line["decode"] = {"value": None, "note": repr(ex)}
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

@@ -762,7 +762,13 @@ void launch_ctx_replay(const EncDeviceTables &t, const EncBatch &b, int max_tile
     static int window = -1;
     if (window < 0) { const char *v = getenv("FFV1B200_REPLAY_WINDOW"); window = v ? atoi(v) : 8; if (window < 1) window = 1 << 20; }
     if (grp == 1 && grp_ok) k_replay_grp<4, 1024><<<nchains, 1024, L.ctx_count * 32, s>>>(t, b, window);
-    else if (grp == 2 && grp_ok) k_replay_grp<4, 512><<<nchains, 512, L.ctx_count * 32, s>>>(t, b, window);
+    else if (grp == 2 && grp_ok) {
+        static int threads = -1;
+        if (threads < 0) { const char *v = getenv("FFV1B200_REPLAY_THREADS"); threads = v ? atoi(v) : 512; }
+        if (threads == 128)      k_replay_grp<4, 128><<<nchains, 128, L.ctx_count * 32, s>>>(t, b, window);
+        else if (threads == 256) k_replay_grp<4, 256><<<nchains, 256, L.ctx_count * 32, s>>>(t, b, window);
+        else                     k_replay_grp<4, 512><<<nchains, 512, L.ctx_count * 32, s>>>(t, b, window);
+    }
     else if (L.coded_bits <= 10) k_replay_ctx<false><<<nchains, kCtxThreads, L.ctx_count * 32, s>>>(t, b);
     else                    k_replay_ctx<true><<<nchains, kCtxThreads, L.ctx_count * 32, s>>>(t, b);
 }

@@ -273,16 +273,23 @@ __device__ void dec_line(SliceRd &sr, uint8_t *model, const int16_t *q, const ui
 
 constexpr int kDecSmemQuant = 2 * 5 * 256;
 
-__global__ void __launch_bounds__(32) k_decode(const DecDeviceTables T, const DecBatch B)
+constexpr int kDecWarps = 2;               // chains per CTA (they share the quantisation / transition tables)
+
+__global__ void __launch_bounds__(32 * kDecWarps) k_decode(const DecDeviceTables T, const DecBatch B)
 {
+    extern __shared__ __align__(16) unsigned char s_dyn[];      // per warp: [model of the current plane context][line ring]
     __shared__ int16_t s_quant[kDecSmemQuant];
     __shared__ uint8_t s_lut[512];
-    const int lane = threadIdx.x;
-    for (int i = lane; i < kDecSmemQuant; i += 32) s_quant[i] = T.quant[i];
-    for (int i = lane; i < 512; i += 32) s_lut[i] = T.lut[i];
-    __syncwarp();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < kDecSmemQuant; i += 32 * kDecWarps) s_quant[i] = T.quant[i];
+    for (int i = threadIdx.x; i < 512; i += 32 * kDecWarps) s_lut[i] = T.lut[i];
+    __syncthreads();
 
-    const int chain = blockIdx.x;
+    const int chain = blockIdx.x * kDecWarps + warp;
+    if (chain >= B.nseg * T.max_slices) return;
+    const int per_warp = T.smem_model + T.smem_ring_w * 3 * 2;
+    uint8_t *s_model = s_dyn + (size_t)warp * per_warp;
+    int16_t *s_ring = reinterpret_cast<int16_t *>(s_model + T.smem_model);
     const int seg = chain / T.max_slices, si = chain - seg * T.max_slices;
     const int f0 = B.seg_first[seg], f1 = B.seg_first[seg + 1];
     uint8_t *models = B.state + ((size_t)B.seg_set[seg] * T.max_slices + si) * 3 * T.state_stride;
@@ -291,6 +298,7 @@ __global__ void __launch_bounds__(32) k_decode(const DecDeviceTables T, const De
     const int bits = T.coded_bits;
     const int nplanes = T.colorspace ? 3 + T.transparency : (T.ya8 ? 2 : 1 + 2 * T.chroma_planes + T.transparency);
 
+    int sm_pc = -1, sm_nb = 0;             // plane context whose model is in shared memory, its size in 16-byte units
     for (int f = f0; f < f1; f++) {
         if (si >= B.slice_count[f]) continue;
         const int fs = f * T.max_slices + si;
@@ -389,14 +397,31 @@ __global__ void __launch_bounds__(32) k_decode(const DecDeviceTables T, const De
                 const int px0 = sx >> hs, py0 = sy >> vs;
                 const int16_t *q = s_quant + qti[pc < T.plane_count ? pc : 0] * 5 * 256;
                 uint8_t *model = models + (size_t)pc * T.state_stride;
-                int16_t *rows = ring;                                                    // plane slot 0: three rows
-                for (int i = lane - kDecRingPad; i < 3 * T.ring_w - kDecRingPad; i += 32) rows[i] = 0;
+                // the plane context's model moves to shared memory while its planes are decoded (U and V share one)
+                if (T.smem_model) {
+                    if (pc != sm_pc) {
+                        const int nb = (T.ctx_count[qti[pc < T.plane_count ? pc : 0]] * (golomb ? 8 : 32) + 15) >> 4;
+                        if (sm_pc >= 0) {
+                            uint4 *dst = reinterpret_cast<uint4 *>(models + (size_t)sm_pc * T.state_stride);
+                            for (int i = lane; i < sm_nb; i += 32) dst[i] = reinterpret_cast<const uint4 *>(s_model)[i];
+                        }
+                        __syncwarp();
+                        const uint4 *src = reinterpret_cast<const uint4 *>(model);
+                        for (int i = lane; i < nb; i += 32) reinterpret_cast<uint4 *>(s_model)[i] = src[i];
+                        sm_pc = pc; sm_nb = nb;
+                    }
+                    model = s_model;
+                }
+                const bool ring_sm = T.smem_ring_w && w + 2 * kDecRingPad <= T.smem_ring_w;
+                const int rw = ring_sm ? T.smem_ring_w : T.ring_w;
+                int16_t *rows = ring_sm ? s_ring + kDecRingPad : ring;                    // plane slot 0: three rows
+                for (int i = lane - kDecRingPad; i < 3 * rw - kDecRingPad; i += 32) rows[i] = 0;
                 __syncwarp();
                 if (lane == 0) sr.run_index = 0;
                 for (int y = 0; y < h; y++) {
-                    int16_t *cur = rows + (y % 3) * T.ring_w;
-                    int16_t *top = rows + ((y + 2) % 3) * T.ring_w;
-                    int16_t *top2 = rows + ((y + 1) % 3) * T.ring_w;
+                    int16_t *cur = rows + (y % 3) * rw;
+                    int16_t *top = rows + ((y + 2) % 3) * rw;
+                    int16_t *top2 = rows + ((y + 1) % 3) * rw;
                     if (lane == 0) {
                         cur[-1] = top[0];                 // ffv1dec.c:199-200
                         top[w] = top[w - 1];
@@ -413,6 +438,14 @@ __global__ void __launch_bounds__(32) k_decode(const DecDeviceTables T, const De
                     }
                     __syncwarp();
                 }
+            }
+            // the model goes back to global memory at the end of the slice (the keyframe reset and a different slice
+            // geometry in the next frame work on the global copy)
+            if (sm_pc >= 0) {
+                uint4 *dst = reinterpret_cast<uint4 *>(models + (size_t)sm_pc * T.state_stride);
+                for (int i = lane; i < sm_nb; i += 32) dst[i] = reinterpret_cast<const uint4 *>(s_model)[i];
+                sm_pc = -1;
+                __syncwarp();
             }
         } else {
             // ---- decode_rgb_frame (ffv1dec.c:226-280): planes interleaved per row, shared run_index
@@ -472,7 +505,11 @@ __global__ void __launch_bounds__(32) k_decode(const DecDeviceTables T, const De
 
 void launch_decode(const DecDeviceTables &t, const DecBatch &b, cudaStream_t s)
 {
-    k_decode<<<b.nseg * t.max_slices, 32, 0, s>>>(t, b);
+    const int chains = b.nseg * t.max_slices;
+    const int smem = kDecWarps * (t.smem_model + t.smem_ring_w * 3 * 2);
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(k_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (24 * 1024 + 8 * 1024)); attr = true; }
+    k_decode<<<(chains + kDecWarps - 1) / kDecWarps, 32 * kDecWarps, smem, s>>>(t, b);
 }
 
 // ------------------------------------------------------------------------------------------------ concealment

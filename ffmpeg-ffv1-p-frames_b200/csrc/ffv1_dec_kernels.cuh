@@ -19,6 +19,8 @@ struct DecDeviceTables {
     const uint8_t *lut;                 // [512] zero_state | one_state the slice coders run with
     int64_t state_stride;               // bytes of one (slice, plane context) model
     int32_t ring_w;                     // int16 elements per ring row
+    int32_t smem_model;                 // bytes of shared memory per chain for the current plane context's model (0 = keep it in global memory)
+    int32_t smem_ring_w;                // int16 elements per shared-memory ring row (0 = ring in global memory)
 };
 
 struct DecBatch {

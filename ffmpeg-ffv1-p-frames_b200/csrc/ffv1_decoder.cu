@@ -66,6 +66,15 @@ static int configure(FFV1B200Decoder *d)
     t.state_stride = (int64_t)maxctx * 32;                    // golomb models need 8 bytes per context: fits as well
     // a slice header may announce any rectangle of the grid: rows are sized for the frame width
     t.ring_w = ((c.width + 2 * kDecRingPad + 31) / 32) * 32;
+    // planar YUV: the model of the plane context being decoded (<= 24 KB: small context model, or Golomb-Rice states)
+    // and the three-row line ring of a regular slice live in shared memory
+    {
+        const int64_t model = (int64_t)maxctx * (c.ac == AC_GOLOMB ? 8 : 32);
+        t.smem_model = (!c.colorspace && model <= 24 * 1024) ? (int32_t)((model + 15) & ~15) : 0;
+        const int sw = (c.width + c.num_h_slices - 1) / c.num_h_slices + 1;
+        const int rw = ((sw + 2 * kDecRingPad + 31) / 32) * 32;
+        t.smem_ring_w = (!c.colorspace && rw * 3 * 2 <= 8 * 1024) ? rw : 0;
+    }
 
     CU_TRY(d->d_quant.upload(&c.quant_tables[0][0][0], 2 * 5 * 256, d->stream));
     uint8_t lut[512];
