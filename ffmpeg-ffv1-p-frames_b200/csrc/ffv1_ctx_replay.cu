@@ -267,6 +267,7 @@ __global__ void __launch_bounds__(kScatterSmThreads) k_ctx_scatter_sm(const EncD
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint32_t s_wtot[kScatterSmThreads / 32];
+    __shared__ int s_nne;                                               // contexts that occur in the tile
     const Layout &L = T.layout;
     if (B.status[0]) return;
     const int nctx = L.ctx_count, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -274,7 +275,8 @@ __global__ void __launch_bounds__(kScatterSmThreads) k_ctx_scatter_sm(const EncD
     uint32_t *s_goff = s_wh + 8 * nctx;                                 // [nctx] where the tile's run of a context goes in its list
     uint16_t *s_start = reinterpret_cast<uint16_t *>(s_goff + nctx);    // [nctx] start of the run inside s_ent
     uint16_t *s_cnt = s_start + ((nctx + 7) & ~7);                      // [nctx]
-    uint2 *s_ent = reinterpret_cast<uint2 *>(s_cnt + ((nctx + 7) & ~7));
+    uint16_t *s_ne = s_cnt + ((nctx + 7) & ~7);                         // [nctx] the contexts that occur in the tile
+    uint2 *s_ent = reinterpret_cast<uint2 *>(s_ne + ((nctx + 7) & ~7));
     const int tile = blockIdx.x, f = blockIdx.y;
     const CtxTile ct = T.ctiles[tile];
     const SliceGeom &g = T.slices[ct.slice];
@@ -283,6 +285,7 @@ __global__ void __launch_bounds__(kScatterSmThreads) k_ctx_scatter_sm(const EncD
     const int f0 = B.seg_first[seg], seglen = B.seg_first[seg + 1] - f0;
     const int chain = (seg * L.nslices + ct.slice) * L.npc + ct.pc;
     for (int i = tid; i < 8 * nctx; i += kScatterSmThreads) s_wh[i] = 0u;
+    if (tid == 0) s_nne = 0;
     {
         const uint32_t *tile_base = B.ctx_hist + ((size_t)f * L.ctiles_per_frame + tile) * nctx;
         const uint32_t *lstart = B.list_start + (size_t)chain * nctx;
@@ -332,6 +335,8 @@ __global__ void __launch_bounds__(kScatterSmThreads) k_ctx_scatter_sm(const EncD
         for (int ww = 0; ww < warp; ww++) base += s_wtot[ww];
         if (2 * tid < nctx) s_start[2 * tid] = (uint16_t)base;
         if (2 * tid + 1 < nctx) s_start[2 * tid + 1] = (uint16_t)(base + cc[0]);
+        if (cc[0]) s_ne[atomicAdd(&s_nne, 1)] = (uint16_t)(2 * tid);
+        if (cc[1]) s_ne[atomicAdd(&s_nne, 1)] = (uint16_t)(2 * tid + 1);
     }
     __syncthreads();
     // stable placement: {position of the symbol's first decision, residual | frame << 16}
@@ -356,9 +361,10 @@ __global__ void __launch_bounds__(kScatterSmThreads) k_ctx_scatter_sm(const EncD
     __syncthreads();
     // runs -> lists: one warp per context, 8 bytes per lane, contiguous
     uint2 *list = B.lists + (size_t)f0 * L.samples_per_frame + (size_t)seglen * g.list_off[ct.pc];
-    for (int c = warp; c < nctx; c += kScatterSmThreads / 32) {
+    const int nne = s_nne;
+    for (int i = warp; i < nne; i += kScatterSmThreads / 32) {
+        const int c = s_ne[i];
         const uint32_t n = s_cnt[c];
-        if (n == 0u) continue;
         uint2 *dst = list + s_goff[c];
         const uint2 *src = s_ent + s_start[c];
         for (uint32_t i = lane; i < n; i += 32) dst[i] = src[i];
@@ -728,7 +734,7 @@ bool ctx_replay_supported(const Layout &L)
 }
 
 int ctx_scatter_smem_bytes(const Layout &L) { return (kScatterThreads / 32) * L.ctx_count * 4; }
-int ctx_scatter_sm_smem_bytes(const Layout &L) { return 9 * L.ctx_count * 4 + 2 * ((L.ctx_count + 7) & ~7) * 2 + kScatterSmMaxSamples * 8; }
+int ctx_scatter_sm_smem_bytes(const Layout &L) { return 9 * L.ctx_count * 4 + 3 * ((L.ctx_count + 7) & ~7) * 2 + kScatterSmMaxSamples * 8; }
 
 cudaError_t configure_ctx_replay(const Layout &L)
 {
