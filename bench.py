@@ -193,7 +193,7 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
-        os.environ["NCCL_DEBUG"] = "WARN"      # stdout carries exactly one JSON line (NCCL_DEBUG=VERSION would add a banner)
+        os.environ.pop("NCCL_DEBUG", None)     # WARN / VERSION / INFO all print a banner; stdout is also redirected below
         dist.init_process_group("nccl", device_id=dev)
 
     B = max(GOP, args.batch // GOP * GOP)
@@ -329,4 +329,19 @@ def ctypes_ptr(v):
 
 
 if __name__ == "__main__":
-    main()
+    # stdout carries exactly ONE JSON line: everything libraries write to fd 1 meanwhile (NCCL banners, ...) goes to stderr
+    sys.stdout.flush()
+    _saved = os.dup(1)
+    os.dup2(2, 1)
+    _real_print = print
+    _lines = []
+    def print(*a, **k):                      # noqa: A001 -- the JSON line is held back until fd 1 is restored
+        _lines.append(" ".join(str(x) for x in a))
+    try:
+        main()
+    finally:
+        sys.stdout.flush()
+        os.dup2(_saved, 1)
+        os.close(_saved)
+        for ln in _lines:
+            _real_print(ln, flush=True)
