@@ -634,7 +634,8 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_replay_grp(const En
 
     // Window after window (`window` context tiles of a frame): all warps of the CTA work on the same stretch of the
     // (frame, slice, plane context) decision region, which is then completed while it is still in L2 (with whole frames
-    // per round, 296 resident CTAs x 0.8 MB of half-written sectors thrashed the 126 MB L2: 3x DRAM traffic).
+    // per round, 296 resident CTAs x 0.8 MB of half-written sectors thrashed the 126 MB L2: 3x DRAM traffic).  Measured
+    // optimum on B200: 256-thread CTAs (4 per SM) x 3 tiles; the time follows (resident CTAs x window), i.e. the L2 footprint.
     const int nt = sg.ct_count[pc];
     for (int f = f0; f < f1; f++)
     for (int tw = 0; tw < nt; tw += window) {
@@ -766,11 +767,11 @@ void launch_ctx_replay(const EncDeviceTables &t, const EncBatch &b, int max_tile
     // 8-bit content (residuals folded to <= 9 bits): two lists per warp; a frame's decision area must fit 32-bit offsets
     const bool grp_ok = L.coded_bits <= 9 && L.dec_per_frame < 0x7FFFFFFFu;
     static int window = -1;
-    if (window < 0) { const char *v = getenv("FFV1B200_REPLAY_WINDOW"); window = v ? atoi(v) : 8; if (window < 1) window = 1 << 20; }
+    if (window < 0) { const char *v = getenv("FFV1B200_REPLAY_WINDOW"); window = v ? atoi(v) : 3; if (window < 1) window = 1 << 20; }
     if (grp == 1 && grp_ok) k_replay_grp<4, 1024><<<nchains, 1024, L.ctx_count * 32, s>>>(t, b, window);
     else if (grp == 2 && grp_ok) {
         static int threads = -1;
-        if (threads < 0) { const char *v = getenv("FFV1B200_REPLAY_THREADS"); threads = v ? atoi(v) : 512; }
+        if (threads < 0) { const char *v = getenv("FFV1B200_REPLAY_THREADS"); threads = v ? atoi(v) : 256; }
         if (threads == 128)      k_replay_grp<4, 128><<<nchains, 128, L.ctx_count * 32, s>>>(t, b, window);
         else if (threads == 256) k_replay_grp<4, 256><<<nchains, 256, L.ctx_count * 32, s>>>(t, b, window);
         else                     k_replay_grp<4, 512><<<nchains, 512, L.ctx_count * 32, s>>>(t, b, window);

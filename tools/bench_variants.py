@@ -1,0 +1,14 @@
+import sys, time, os
+sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/ffmpeg-ffv1-p-frames_b200")
+import numpy as np, ffv1_b200
+from oracle import synth
+W,H,FMT=1920,1080,"yuv420p"
+g=synth.Noisy(W,H,FMT,1234); base=[g.next() for _ in range(16)]
+n=256; frames=[base[i%16] for i in range(n)]
+for coder, ctx in ((0,0),(1,1)):
+    enc=ffv1_b200.FFV1Encoder(W,H,FMT,g=16,level=3,coder=coder,context=ctx,slices=24,max_batch_frames=n)
+    enc.encode_batch(frames)
+    t0=time.perf_counter(); p=enc.encode_batch(frames); dt=time.perf_counter()-t0
+    s=enc.stats(); st={k:getattr(s,k) for k,_ in s._fields_}
+    print("coder",coder,"context",ctx,"fps %.1f"%(n/dt), {k:round(v,1) for k,v in st.items() if k.startswith("ms_")}, "bytes/frame", sum(len(x[0]) for x in p)//n)
+    enc.close()
