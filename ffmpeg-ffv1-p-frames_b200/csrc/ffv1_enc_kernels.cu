@@ -506,6 +506,7 @@ struct Rac {
     uint32_t low, range;
     uint32_t out_byte;   // outstanding byte (its final value depends on a carry that may still arrive)
     uint32_t out_count;  // 0xFF bytes behind it that a carry would turn into 0x00
+    uint32_t thr;        // 0xFE, or 0xFFFFFFFF while out_count != 0 (see rac_code)
     uint32_t pos;        // bytes produced (incl. the kScratchLead lead-in)
     uint32_t fl;         // bytes already moved from the lane's ring to the scratch region (multiple of 16)
     uint32_t ring;       // shared-memory address of the lane's 32-byte ring: byte i of the stream sits at ring + (i & 31)
@@ -569,36 +570,33 @@ __device__ __noinline__ RacOut rac_output_slow(uint32_t low, uint32_t out_byte, 
 // to wait for its carry (about one renormalisation in 128) leaves the straight line.
 __device__ __forceinline__ void rac_code(Rac &c, uint32_t p24, uint32_t one)
 {
-    uint32_t low_before, slow;
-    asm volatile("{\n\t.reg .pred one, sh, w, s, f;\n\t.reg .u32 r1, r0, t, b, a;\n\t"
+    uint32_t t, slow;
+    // 17 instructions: the "wait" test (byte 0xFF with no carry yet, or 0xFF bytes already waiting) is one two-output
+    // setp against c.thr (0xFE, or 0xFFFFFFFF while bytes wait), everything that reads `low` comes before its shift
+    asm volatile("{\n\t.reg .pred one, sh, s, f;\n\t.reg .u32 r1, r0, cy, b, a;\n\t"
         "mul.hi.u32 r1, %1, %7;\n\t"                        // (range * p) >> 8
         "sub.u32 r0, %1, r1;\n\t"
         "setp.ne.u32 one, %8, 0;\n\t"
         "selp.u32 %1, r1, r0, one;\n\t"
         "@one add.u32 %0, %0, r0;\n\t"
-        "mov.u32 %4, %0;\n\t"                               // low before the shift
         "setp.lt.u32 sh, %1, 0x100;\n\t"                    // p >= 1 and range >= 0x100 before: at most one shift
-        "@sh shl.b32 %1, %1, 8;\n\t"
-        "@sh prmt.b32 %0, %0, 0, 0x4404;\n\t"               // low = (low & 0xFF) << 8
-        "sub.u32 t, %4, 0xFF01;\n\t"
-        "setp.lt.u32 w, t, 0xFF;\n\t"                       // the byte is 0xFF and a carry may still flip it ...
-        "setp.ne.or.u32 w, %6, 0, w;\n\t"                   // ... or such bytes are still waiting
-        "and.pred s, sh, w;\n\t"
+        "sub.u32 %4, %0, 0xFF01;\n\t"                       // 0xFF01 <= low <= 0xFFFF: the byte is 0xFF and a carry may still flip it
+        "setp.le.and.u32 s|f, %4, %6, sh;\n\t"              // s: leave the straight line; f: emit outstanding byte + carry
         "selp.u32 %5, 1, 0, s;\n\t"
-        "not.pred w, w;\n\t"
-        "and.pred f, sh, w;\n\t"
-        "shr.u32 t, %4, 16;\n\t"
-        "add.u32 b, %2, t;\n\t"                             // outstanding byte + carry
-        "and.b32 a, %3, 31;\n\t"
-        "or.b32 a, a, %9;\n\t"
+        "shr.u32 cy, %0, 16;\n\t"
+        "add.u32 b, %2, cy;\n\t"                            // outstanding byte + carry
+        "lop3.b32 a, %3, 31, %9, 0xEA;\n\t"                 // ring | (pos & 31)
         "@f st.shared.u8 [a], b;\n\t"
         "@f add.u32 %3, %3, 1;\n\t"
-        "@f prmt.b32 %2, %4, 0, 0x4441;\n\t}"               // outstanding byte = (low >> 8) & 0xFF
-        : "+r"(c.low), "+r"(c.range), "+r"(c.out_byte), "+r"(c.pos), "=r"(low_before), "=r"(slow)
-        : "r"(c.out_count), "r"(p24), "r"(one), "r"(c.ring) : "memory");
+        "@f prmt.b32 %2, %0, 0, 0x4441;\n\t"                // outstanding byte = (low >> 8) & 0xFF
+        "@sh shl.b32 %1, %1, 8;\n\t"
+        "@sh prmt.b32 %0, %0, 0, 0x4404;\n\t}"              // low = (low & 0xFF) << 8
+        : "+r"(c.low), "+r"(c.range), "+r"(c.out_byte), "+r"(c.pos), "=r"(t), "=r"(slow)
+        : "r"(c.thr), "r"(p24), "r"(one), "r"(c.ring) : "memory");
     if (__builtin_expect(slow != 0u, 0)) {
-        const RacOut o = rac_output_slow(low_before, c.out_byte, c.out_count, c.pos, c.fl, c.ring, c.cap, c.out);
+        const RacOut o = rac_output_slow(t + 0xFF01u, c.out_byte, c.out_count, c.pos, c.fl, c.ring, c.cap, c.out);
         c.out_byte = o.out_byte; c.out_count = o.out_count; c.pos = o.pos; c.fl = o.fl;
+        c.thr = o.out_count ? 0xFFFFFFFFu : 0xFEu;
     }
 }
 
@@ -638,7 +636,7 @@ __global__ void __launch_bounds__(kRangeThreads) k_rangecode(const EncDeviceTabl
     __shared__ __align__(32) uint8_t s_ring[kRangeThreads * 32];
     __shared__ __align__(16) uint4 s_vec[kRangeDepth * kRangeChunk * kRangeThreads];   // [chunk slot][vector][lane]
     Rac c;
-    c.low = 0; c.range = 0xFF00u; c.out_byte = 0; c.out_count = 0;        // ff_init_range_encoder (+ dummy outstanding byte)
+    c.low = 0; c.range = 0xFF00u; c.out_byte = 0; c.out_count = 0; c.thr = 0xFEu;   // ff_init_range_encoder (+ dummy outstanding byte)
     c.out = B.scratch + (size_t)f * L.scratch_per_frame + g.scratch_off;
     c.pos = kScratchLead - 1; c.fl = 0; c.cap = g.scratch_cap;
     c.ring = (uint32_t)__cvta_generic_to_shared(s_ring + threadIdx.x * 32);
