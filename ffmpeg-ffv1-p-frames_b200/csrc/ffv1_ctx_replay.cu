@@ -611,6 +611,11 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_replay_grp(const En
     const SliceGeom &sg = T.slices[s];
     const int f0 = B.seg_first[seg], f1 = B.seg_first[seg + 1];
     const int nctx = L.ctx_count;
+    // list bookkeeping of the chain / of the current window in shared memory: taking the next list costs no global load
+    uint32_t *s_lstart = reinterpret_cast<uint32_t *>(s_state_raw + (size_t)nctx * 32);     // [nctx] start of every list
+    uint32_t *s_b0 = s_lstart + nctx, *s_b1 = s_b0 + nctx;                                // [nctx] the window's part of every list
+    uint16_t *s_order = reinterpret_cast<uint16_t *>(s_b1 + nctx);                          // [nctx] contexts, longest list first
+    __shared__ int s_nlists;
     const bool key = B.frame_key[f0] != 0;
     const bool hand_over = f1 == B.nframes;
     const size_t coff = ((size_t)s * L.npc + pc) * ((size_t)nctx * 32);
@@ -625,6 +630,14 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_replay_grp(const En
     const uint32_t *lcount = B.list_count + (size_t)chain * nctx;
     const uint16_t *order = B.list_order + (size_t)chain * nctx;
     uint16_t *dec_pc = B.dec + sg.dec_off[pc];
+    if (tid == 0) s_nlists = 0;
+    __syncthreads();
+    for (int i = tid; i < nctx; i += THREADS) {
+        s_lstart[i] = lstart[i];
+        const uint16_t c = order[i];
+        s_order[i] = c;
+        if (lcount[c]) atomicMax(&s_nlists, i + 1);           // the order is by list length: the non-empty lists come first
+    }
     // role of the lane inside its group
     const int slot = g == 0 ? 0 : (g <= EMAX + 1 ? g : (g <= 2 * EMAX + 1 ? 22 + (2 * EMAX + 1 - g) : (g <= 3 * EMAX + 2 ? 11 + g - (2 * EMAX + 2) : -1)));
     const bool has_slot = slot >= 0;
@@ -641,11 +654,16 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_replay_grp(const En
     for (int tw = 0; tw < nt; tw += window) {
         __syncthreads();                                             // model loaded / previous window finished
         if (tid == 0) s_next = 0;
-        __syncthreads();
         const bool last_win = tw + window >= nt;
-        const uint32_t *before = B.ctx_hist + ((size_t)f * L.ctiles_per_frame + t0 + tw) * nctx;
-        const uint32_t *before_next = last_win ? B.ctx_hist + ((size_t)(f + 1) * L.ctiles_per_frame + t0) * nctx
-                                               : B.ctx_hist + ((size_t)f * L.ctiles_per_frame + t0 + tw + window) * nctx;
+        {
+            const uint32_t *bf = B.ctx_hist + ((size_t)f * L.ctiles_per_frame + t0 + tw) * nctx;
+            const uint32_t *bn = last_win ? B.ctx_hist + ((size_t)(f + 1) * L.ctiles_per_frame + t0) * nctx
+                                          : B.ctx_hist + ((size_t)f * L.ctiles_per_frame + t0 + tw + window) * nctx;
+            const bool use_bn = !last_win || f + 1 < f1;
+            for (int i = tid; i < nctx; i += THREADS) { s_b0[i] = bf[i]; s_b1[i] = use_bn ? bn[i] : lcount[i]; }
+        }
+        __syncthreads();
+
         uint32_t n_left = 0u, st = 0u;
         uint2 nx = make_uint2(0u, 0u);
         int c = -1;
@@ -660,14 +678,12 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_replay_grp(const En
                     int oi = 0;
                     if (g == 0) oi = atomicAdd(&s_next, 1);
                     oi = __shfl_sync(gmask, oi, 0, G);
-                    if (oi >= nctx) { exhausted = true; break; }
-                    const int cc = order[oi];
-                    const uint32_t ntot = lcount[cc];
-                    if (ntot == 0u) { exhausted = true; break; }     // contexts are ordered by the length of their chain list
-                    const uint32_t b0 = before[cc], b1 = (!last_win || f + 1 < f1) ? before_next[cc] : ntot;
+                    if (oi >= s_nlists) { exhausted = true; break; }
+                    const int cc = s_order[oi];
+                    const uint32_t b0 = s_b0[cc], b1 = s_b1[cc];
                     if (b1 == b0) continue;
                     c = cc; n_left = b1 - b0;
-                    lp = chain_list + lstart[cc] + b0;
+                    lp = chain_list + s_lstart[cc] + b0;
                     st = has_slot ? s_state[cc * 32 + slot] : 0u;
                     nx = (uint32_t)g < n_left ? lp[g] : make_uint2(0u, 0u);
                     break;
@@ -729,6 +745,8 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_replay_grp(const En
     }
 }
 
+static int replay_grp_smem(const Layout &L) { return L.ctx_count * (32 + 12 + 2) + 16; }
+
 bool ctx_replay_supported(const Layout &L)
 {
     return !L.golomb && L.ctx_count <= kMaxListCtx;
@@ -768,13 +786,13 @@ void launch_ctx_replay(const EncDeviceTables &t, const EncBatch &b, int max_tile
     const bool grp_ok = L.coded_bits <= 9 && L.dec_per_frame < 0x7FFFFFFFu;
     static int window = -1;
     if (window < 0) { const char *v = getenv("FFV1B200_REPLAY_WINDOW"); window = v ? atoi(v) : 3; if (window < 1) window = 1 << 20; }
-    if (grp == 1 && grp_ok) k_replay_grp<4, 1024><<<nchains, 1024, L.ctx_count * 32, s>>>(t, b, window);
+    if (grp == 1 && grp_ok) k_replay_grp<4, 1024><<<nchains, 1024, replay_grp_smem(L), s>>>(t, b, window);
     else if (grp == 2 && grp_ok) {
         static int threads = -1;
         if (threads < 0) { const char *v = getenv("FFV1B200_REPLAY_THREADS"); threads = v ? atoi(v) : 256; }
-        if (threads == 128)      k_replay_grp<4, 128><<<nchains, 128, L.ctx_count * 32, s>>>(t, b, window);
-        else if (threads == 256) k_replay_grp<4, 256><<<nchains, 256, L.ctx_count * 32, s>>>(t, b, window);
-        else                     k_replay_grp<4, 512><<<nchains, 512, L.ctx_count * 32, s>>>(t, b, window);
+        if (threads == 128)      k_replay_grp<4, 128><<<nchains, 128, replay_grp_smem(L), s>>>(t, b, window);
+        else if (threads == 256) k_replay_grp<4, 256><<<nchains, 256, replay_grp_smem(L), s>>>(t, b, window);
+        else                     k_replay_grp<4, 512><<<nchains, 512, replay_grp_smem(L), s>>>(t, b, window);
     }
     else if (L.coded_bits <= 10) k_replay_ctx<false><<<nchains, kCtxThreads, L.ctx_count * 32, s>>>(t, b);
     else                    k_replay_ctx<true><<<nchains, kCtxThreads, L.ctx_count * 32, s>>>(t, b);
