@@ -103,13 +103,13 @@ __global__ void __launch_bounds__(kScanThreads) k_ctx_scan(const EncDeviceTables
         uint32_t run = 0;
         for (int f = f0; f < f1; f++) {
             uint32_t *h = B.ctx_hist + ((size_t)f * L.ctiles_per_frame + t0) * nctx + c;
-            // loads first, then the running sum and the stores: eight independent loads are in flight at a time
-            for (int tb = 0; tb < nt; tb += 8) {
-                uint32_t v[8];
+            // loads first, then the running sum and the stores: sixteen independent loads are in flight at a time
+            for (int tb = 0; tb < nt; tb += 16) {
+                uint32_t v[16];
 #pragma unroll
-                for (int k = 0; k < 8; k++) v[k] = tb + k < nt ? h[(size_t)(tb + k) * nctx] : 0u;
+                for (int k = 0; k < 16; k++) v[k] = tb + k < nt ? h[(size_t)(tb + k) * nctx] : 0u;
 #pragma unroll
-                for (int k = 0; k < 8; k++)
+                for (int k = 0; k < 16; k++)
                     if (tb + k < nt) { h[(size_t)(tb + k) * nctx] = run; run += v[k]; }
             }
         }
