@@ -820,7 +820,7 @@ __device__ __forceinline__ void vlc_put(BitW &w, VlcEnc *sp, int v, int bits)
     *sp = s;
 }
 
-__global__ void __launch_bounds__(32) k_golomb(const EncDeviceTables T, const EncBatch B)
+__global__ void __launch_bounds__(32) k_golomb(const EncDeviceTables T, const EncBatch B, const int sm_state)
 {
     const Layout &L = T.layout;
     const int lane = threadIdx.x;
@@ -828,8 +828,10 @@ __global__ void __launch_bounds__(32) k_golomb(const EncDeviceTables T, const En
     const int seg = chain / L.nslices, s = chain - seg * L.nslices;
     const SliceGeom &g = T.slices[s];
     const int f0 = B.seg_first[seg], f1 = B.seg_first[seg + 1];
-    const size_t pc_bytes = (size_t)L.ctx_count * 32;                     // same footprint as a range-coder model
-    uint8_t *st = B.state_seg + (size_t)chain * L.npc * pc_bytes;
+    extern __shared__ __align__(8) unsigned char s_vlc[];                 // the chain's VlcStates when they fit (small context model)
+    const size_t pc_bytes = (size_t)L.ctx_count * 32;                     // footprint of a plane context in the carry / state areas
+    uint8_t *st = sm_state ? s_vlc : B.state_seg + (size_t)chain * L.npc * pc_bytes;
+    const size_t st_pc = sm_state ? (size_t)L.ctx_count : pc_bytes / 8;   // uint2 entries between the plane contexts of `st`
     const size_t coff = (size_t)s * L.npc * pc_bytes;
     {
         const bool key = B.frame_key[f0];
@@ -838,7 +840,7 @@ __global__ void __launch_bounds__(32) k_golomb(const EncDeviceTables T, const En
         // VlcState {drift 0, error_sum 4, bias 0, count 1} (ffv1.c:194-199)
         for (int pc = 0; pc < L.npc; pc++)
             for (int i = lane; i < L.ctx_count; i += 32)
-                st8[pc * (pc_bytes / 8) + i] = key ? make_uint2(0x00040000u, 0x00000100u) : in8[pc * (pc_bytes / 8) + i];
+                st8[pc * st_pc + i] = key ? make_uint2(0x00040000u, 0x00000100u) : in8[pc * (pc_bytes / 8) + i];
         __syncwarp();
     }
     const int bits = L.coded_bits;
@@ -848,7 +850,8 @@ __global__ void __launch_bounds__(32) k_golomb(const EncDeviceTables T, const En
         const int npre = T.gprefix_len[s * 2 + key];
         const uint8_t *pre = T.gprefix + (size_t)(s * 2 + key) * kMaxGolombPrefix;
         for (int i = lane; i < npre; i += 32) out[i] = pre[i];
-        if (lane == 0) {
+        // every lane walks the lines (32 records per coalesced load, handed to lane 0 through shuffles); lane 0 codes
+        {
             BitW w;
             w.buf = out; w.pos = (uint32_t)npre; w.cap = g.scratch_cap - kScratchLead; w.acc = 0; w.nbits = 0;
             const uint32_t *rec_slice = B.rec + (size_t)f * L.rec_per_frame + g.rec_first;
@@ -856,31 +859,38 @@ __global__ void __launch_bounds__(32) k_golomb(const EncDeviceTables T, const En
             for (int li = 0; li < g.nlines; li++) {
                 const LineDesc ld = T.lines[g.line_first + li];
                 if (!L.rgb && ld.y == 0) run_index = 0;                   // encode_plane starts a new plane (ffv1enc.c:379)
-                VlcEnc *vs = reinterpret_cast<VlcEnc *>(st + (size_t)ld.pc * pc_bytes);
+                VlcEnc *vs = reinterpret_cast<VlcEnc *>(st + (size_t)ld.pc * (sm_state ? (size_t)L.ctx_count * 8 : pc_bytes));
                 const uint32_t *recp = rec_slice + ld.rec_off;
                 int run_count = 0, run_mode = 0;
-                for (int x = 0; x < ld.w; x++) {
-                    const uint32_t r = recp[x];
-                    const int ctx = (int)(r >> 16);
-                    int diff = (int)(int16_t)(r & 0xFFFFu);
-                    if (ctx == 0) run_mode = 1;
-                    if (run_mode) {
-                        if (diff) {
-                            while (run_count >= 1 << c_enc_log2_run[run_index]) {
-                                run_count -= 1 << c_enc_log2_run[run_index];
-                                run_index++;
-                                bw_put(w, 1, 1u);
-                            }
-                            bw_put(w, 1 + c_enc_log2_run[run_index], (uint32_t)run_count);
-                            if (run_index) run_index--;
-                            run_count = 0; run_mode = 0;
-                            if (diff > 0) diff--;
-                        } else
-                            run_count++;
+                uint32_t nx = lane < ld.w ? recp[lane] : 0u;
+                for (int x0 = 0; x0 < ld.w; x0 += 32) {
+                    const uint32_t rr = nx;
+                    if (x0 + 32 + lane < ld.w) nx = recp[x0 + 32 + lane];  // next group in flight while this one is coded
+                    const int n = min(32, (int)ld.w - x0);
+                    for (int kk = 0; kk < n; kk++) {
+                        const uint32_t r = __shfl_sync(0xFFFFFFFFu, rr, kk);
+                        if (lane != 0) continue;
+                        const int ctx = (int)(r >> 16);
+                        int diff = (int)(int16_t)(r & 0xFFFFu);
+                        if (ctx == 0) run_mode = 1;
+                        if (run_mode) {
+                            if (diff) {
+                                while (run_count >= 1 << c_enc_log2_run[run_index]) {
+                                    run_count -= 1 << c_enc_log2_run[run_index];
+                                    run_index++;
+                                    bw_put(w, 1, 1u);
+                                }
+                                bw_put(w, 1 + c_enc_log2_run[run_index], (uint32_t)run_count);
+                                if (run_index) run_index--;
+                                run_count = 0; run_mode = 0;
+                                if (diff > 0) diff--;
+                            } else
+                                run_count++;
+                        }
+                        if (!run_mode) vlc_put(w, vs + ctx, diff, bits);
                     }
-                    if (!run_mode) vlc_put(w, vs + ctx, diff, bits);
                 }
-                if (run_mode) {                                            // end-of-line run flush (ffv1enc.c:358-367)
+                if (lane == 0 && run_mode) {                               // end-of-line run flush (ffv1enc.c:358-367)
                     while (run_count >= 1 << c_enc_log2_run[run_index]) {
                         run_count -= 1 << c_enc_log2_run[run_index];
                         run_index++;
@@ -889,9 +899,11 @@ __global__ void __launch_bounds__(32) k_golomb(const EncDeviceTables T, const En
                     if (run_count) bw_put(w, 1, 1u);
                 }
             }
-            if (w.nbits) bw_put(w, 8 - w.nbits, 0u);                      // flush_put_bits: zero padding to a byte
-            B.slice_bytes[f * L.nslices + s] = w.pos;
-            if (w.pos > w.cap) atomicMax(&B.status[1], (unsigned long long)w.pos);
+            if (lane == 0) {
+                if (w.nbits) bw_put(w, 8 - w.nbits, 0u);                  // flush_put_bits: zero padding to a byte
+                B.slice_bytes[f * L.nslices + s] = w.pos;
+                if (w.pos > w.cap) atomicMax(&B.status[1], (unsigned long long)w.pos);
+            }
         }
         __syncwarp();
     }
@@ -899,13 +911,16 @@ __global__ void __launch_bounds__(32) k_golomb(const EncDeviceTables T, const En
         const uint2 *st8 = reinterpret_cast<const uint2 *>(st);
         uint2 *out8 = reinterpret_cast<uint2 *>(B.carry_out + coff);
         for (int pc = 0; pc < L.npc; pc++)
-            for (int i = lane; i < L.ctx_count; i += 32) out8[pc * (pc_bytes / 8) + i] = st8[pc * (pc_bytes / 8) + i];
+            for (int i = lane; i < L.ctx_count; i += 32) out8[pc * (pc_bytes / 8) + i] = st8[pc * st_pc + i];
     }
 }
 
 void launch_golomb(const EncDeviceTables &t, const EncBatch &b, cudaStream_t s)
 {
-    k_golomb<<<b.nseg * t.layout.nslices, 32, 0, s>>>(t, b);
+    // VlcStates of the chain (8 bytes per context and plane context) in shared memory when they fit
+    const size_t bytes = (size_t)t.layout.npc * t.layout.ctx_count * 8;
+    const int sm_state = bytes <= 40 * 1024;
+    k_golomb<<<b.nseg * t.layout.nslices, 32, sm_state ? bytes : 0, s>>>(t, b, sm_state);
 }
 
 // =================================================================================================
