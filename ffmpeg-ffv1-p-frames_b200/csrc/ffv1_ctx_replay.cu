@@ -598,6 +598,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_replay_grp(const En
     __shared__ uint8_t s_lut[512];
     __shared__ uint4 s_blk_all[THREADS];
     __shared__ int s_next;
+    __shared__ uint2 s_mask[64];                                     // (visit, bits) of the residuals -32..31 (visit 0: serial path)
     uint8_t *s_state = s_state_raw;
     const Layout &L = T.layout;
     const int tid = threadIdx.x, lane = tid & 31, g = lane & (G - 1);
@@ -605,6 +606,11 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_replay_grp(const En
     uint4 *s_blk = s_blk_all + (tid & ~(G - 1));                     // my group's block of G entries
     const uint32_t lut_base = (uint32_t)__cvta_generic_to_shared(s_lut);
     for (int i = tid; i < 512; i += THREADS) s_lut[i] = T.trans_lut[i];
+    if (tid < 64) {
+        uint32_t v = 0u, bt = 0u; bool sl = false;
+        symbol_masks_grp<EMAX>(tid - 32, v, bt, sl);
+        s_mask[tid] = make_uint2(sl ? 0u : v, bt);
+    }
     if (B.status[0]) return;
     const int chain = blockIdx.x;
     const int pc = chain % L.npc, s = (chain / L.npc) % L.nslices, seg = chain / (L.npc * L.nslices);
@@ -652,6 +658,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_replay_grp(const En
     const int nt = sg.ct_count[pc];
     for (int f = f0; f < f1; f++)
     for (int tw = 0; tw < nt; tw += window) {
+        uint16_t *dec_f = dec_pc + (size_t)f * L.dec_per_frame;
         __syncthreads();                                             // model loaded / previous window finished
         if (tid == 0) s_next = 0;
         const bool last_win = tw + window >= nt;
@@ -699,13 +706,17 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_replay_grp(const En
             const int d = (int)(int16_t)(en.y & 0xFFFFu);
             uint32_t vis = 0u, bts = 0u;
             bool slow = false;
-            if ((uint32_t)g < m) symbol_masks_grp<EMAX>(d, vis, bts, slow);
-            // a block never leaves its frame, so positions relative to its first symbol fit 32 bits
-            const unsigned long long off = (unsigned long long)(en.y >> 16) * L.dec_per_frame + en.x;
-            const unsigned long long off0 = __shfl_sync(0xFFFFFFFFu, off, lane & 16);
-            uint16_t *o0 = dec_pc + off0;
+            if ((uint32_t)g < m) {                                   // masks from the table; anything else takes the serial path
+                const uint32_t di = (uint32_t)(d + 32);
+                const uint2 mk = s_mask[di & 63u];
+                slow = di >= 64u || mk.x == 0u;
+                if (!slow) { vis = mk.x; bts = mk.y; }
+            }
+            // every entry of the window lies in frame f: positions relative to the block's first symbol, 32-bit arithmetic
+            const uint32_t off0 = __shfl_sync(0xFFFFFFFFu, en.x, lane & 16);
+            uint16_t *o0 = dec_f + off0;
             __syncwarp();
-            s_blk[g] = make_uint4(vis, bts, (uint32_t)(off - off0), (slow ? 0x80000000u : 0u) | (en.y & 0xFFFFu));
+            s_blk[g] = make_uint4(vis, bts, en.x - off0, (slow ? 0x80000000u : 0u) | (en.y & 0xFFFFu));
             __syncwarp();
             const uint32_t mm = max(m, __shfl_xor_sync(0xFFFFFFFFu, m, 16));
             if (!__any_sync(0xFFFFFFFFu, slow)) {
