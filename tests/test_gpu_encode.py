@@ -150,3 +150,27 @@ def test_fused_replay_kernel(B, cid, monkeypatch):
     for i, f in enumerate(frames):
         exp, key = o.encode(f)
         assert got[i][0] == exp and got[i][1] == key, "packet %d differs" % i
+
+FULL = [   # BASELINE.json configs[2] and [3] at full size, with the options the reference actually accepts
+    ("c3_full_1080p_422p10_ctx1", 1920, 1080, "yuv422p10le", dict(gop=16, level=3, coder=0, context=1), 1235),
+    ("c4_full_2160p_gbrp14_30sl", 3840, 2160, "gbrp14le",    dict(gop=16, level=3, coder=2, context=0, slices=30), 1236),
+]
+
+@pytest.mark.parametrize("case", FULL, ids=[c[0] for c in FULL])
+def test_full_size_configs(B, case):
+    """full-size frames: packets byte-identical to the oracle, and the CUDA decoder gives the source back"""
+    from oracle import synth
+    cid, w, h, fmt, opts, seed = case
+    gen = synth.Noisy(w, h, fmt, seed)
+    frames = [gen.next() for _ in range(3)]              # keyframe + two state-carry-over frames
+    o = O.Encoder(w, h, fmt, **opts)
+    g = B.FFV1Encoder(w, h, fmt, max_batch_frames=3, **gpu_opts(opts))
+    assert g.extradata == o.extradata
+    got = g.encode_batch(frames)
+    for i, f in enumerate(frames):
+        exp, key = o.encode(f)
+        assert got[i][1] == key and len(got[i][0]) == len(exp) and got[i][0] == exp, "packet %d differs" % i
+    d = B.FFV1Decoder(w, h, g.extradata, max_batch_frames=3)
+    out = d.decode_batch([p for p, _ in got])
+    for i, f in enumerate(frames):
+        assert np.array_equal(out[i][0], np.ascontiguousarray(f).view(np.uint8).reshape(-1)), "decoded frame %d differs" % i
