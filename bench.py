@@ -172,9 +172,16 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--ref-frames", type=int, default=32, help="--impl reference: frames per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--coder", type=int, default=None, help="variant runs only: 0 = Golomb-Rice, -2 = default state table (the metric is coder=1)")
+    ap.add_argument("--context", type=int, default=None, help="variant runs only: 1 = large context model")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-decode", action="store_true", help="skip the decoder leg (extra key \"decode\", N=1 only)")
     args = ap.parse_args()
+    global WORKLOAD
+    if args.coder is not None or args.context is not None:
+        if args.coder is not None: OPTS["coder"] = args.coder
+        if args.context is not None: OPTS["context"] = args.context
+        WORKLOAD = WORKLOAD.replace("coder=1, context=0", "VARIANT coder=%d, context=%d" % (OPTS["coder"], OPTS["context"]))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -55,7 +55,23 @@ __device__ __forceinline__ uint32_t decisions_of(int d)
     return d ? (uint32_t)(2 * (31 - __clz((uint32_t)abs(d))) + 3) : 1u;       // put_symbol_inline: 1 or 2e+3
 }
 
+// Golomb-Rice mode (ffv1enc.c:327-357): which of the 32 samples of a group are coded in run mode.  Run mode starts at a
+// sample whose context is 0 and lasts up to and including the next non-zero residual:
+//     M(i) = ctx(i)==0 || (M(i-1) && diff(i-1)==0)
+// i.e. a carry chain with generate = zero & ctx0 and propagate = zero & ~ctx0, evaluated by one 64-bit addition.
+// `carry` = the run continues into the next group of the line.  Samples with M && diff==0 are absorbed into the run
+// (no VLC code, no state update); samples with M && diff!=0 end it and code diff-1 for positive residuals.
+__device__ __forceinline__ uint32_t gr_run_members(uint32_t ctx0, uint32_t zero, uint32_t &carry)
+{
+    const uint32_t a = zero, b = zero & ctx0;
+    const unsigned long long sum = (unsigned long long)a + b + carry;
+    const uint32_t c = (uint32_t)sum ^ a ^ b;                 // carry INTO every bit = "a run reaches this sample"
+    carry = (uint32_t)(sum >> 32);
+    return ctx0 | c;
+}
+
 // ------------------------------------------------------------------------------------------------ k_ctx_hist
+template <bool GOLOMB>
 __global__ void __launch_bounds__(kHistThreads) k_ctx_hist(const EncDeviceTables T, const EncBatch B)
 {
     __shared__ uint32_t s_hist[kMaxListCtx];
@@ -73,6 +89,18 @@ __global__ void __launch_bounds__(kHistThreads) k_ctx_hist(const EncDeviceTables
         const LineDesc ld = T.lines[g.line_first + line];
         const uint32_t *recp = rec_slice + ld.rec_off;
         uint32_t nd = 0;
+        if (GOLOMB) {
+            // only the samples that get a VLC code count (run mode absorbs zero residuals); groups of a line in order
+            uint32_t carry = 0u;
+            for (int x0 = 0; x0 < ld.w; x0 += 32) {
+                const bool act = x0 + lane < ld.w;
+                const uint32_t r = act ? recp[x0 + lane] : 0xFFFF0001u;
+                const uint32_t zero = __ballot_sync(0xFFFFFFFFu, act && (r & 0xFFFFu) == 0u);
+                const uint32_t ctx0 = __ballot_sync(0xFFFFFFFFu, act && (r >> 16) == 0u);
+                const uint32_t mem = gr_run_members(ctx0, zero, carry);
+                if (act && !((mem & zero) >> lane & 1u)) atomicAdd(&s_hist[r >> 16], 1u);
+            }
+        } else
         for (int x = lane; x < ld.w; x += 32) {
             const uint32_t r = recp[x];
             nd += decisions_of((int)(int16_t)(r & 0xFFFFu));
@@ -263,6 +291,7 @@ __global__ void __launch_bounds__(kScatterThreads) k_ctx_scatter(const EncDevice
 constexpr int kScatterSmThreads = 512;
 constexpr int kScatterSmMaxSamples = 5632;               // per tile (16 lines of <= 352 samples): 44 KB of entries
 
+template <bool GOLOMB>
 __global__ void __launch_bounds__(kScatterSmThreads) k_ctx_scatter_sm(const EncDeviceTables T, const EncBatch B)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -302,9 +331,20 @@ __global__ void __launch_bounds__(kScatterSmThreads) k_ctx_scatter_sm(const EncD
         const LineDesc ld = T.lines[g.line_first + line];
         recp = rec_slice + ld.rec_off;
         w = ld.w;
-        pos = B.line_pos[(size_t)f * L.lines_per_frame + g.line_first + line];
+        pos = GOLOMB ? 0u : B.line_pos[(size_t)f * L.lines_per_frame + g.line_first + line];
         uint32_t *wh = s_wh + (warp >> 1) * nctx;
         const uint32_t one = (warp & 1) ? 0x10000u : 1u;
+        if (GOLOMB) {
+            uint32_t carry = 0u;
+            for (int x0 = 0; x0 < w; x0 += 32) {
+                const bool act = x0 + lane < w;
+                const uint32_t r = act ? recp[x0 + lane] : 0xFFFF0001u;
+                const uint32_t zero = __ballot_sync(0xFFFFFFFFu, act && (r & 0xFFFFu) == 0u);
+                const uint32_t ctx0 = __ballot_sync(0xFFFFFFFFu, act && (r >> 16) == 0u);
+                const uint32_t mem = gr_run_members(ctx0, zero, carry);
+                if (act && !((mem & zero) >> lane & 1u)) atomicAdd(&wh[r >> 16], one);
+            }
+        } else
         for (int x = lane; x < w; x += 32) atomicAdd(&wh[recp[x] >> 16], one);
     }
     __syncthreads();
@@ -343,19 +383,31 @@ __global__ void __launch_bounds__(kScatterSmThreads) k_ctx_scatter_sm(const EncD
     if (warp < ct.nlines) {
         uint32_t *wh = s_wh + (warp >> 1) * nctx;
         const int sh = (warp & 1) * 16;
+        uint32_t gcarry = 0u;
+        const uint32_t rec_line = (uint32_t)(recp - rec_slice);         // Golomb-Rice mode: entries carry the record index
         for (int x0 = 0; x0 < w; x0 += 32) {
-            const bool act = x0 + lane < w;
-            const uint32_t r = act ? recp[x0 + lane] : 0u;
+            bool act = x0 + lane < w;
+            uint32_t r = act ? recp[x0 + lane] : (GOLOMB ? 0xFFFF0001u : 0u);
+            if (GOLOMB) {
+                const uint32_t zero = __ballot_sync(0xFFFFFFFFu, act && (r & 0xFFFFu) == 0u);
+                const uint32_t ctx0 = __ballot_sync(0xFFFFFFFFu, act && (r >> 16) == 0u);
+                const uint32_t mem = gr_run_members(ctx0, zero, gcarry);
+                const bool inrun = (mem >> lane) & 1u;
+                const int d = (int)(int16_t)(r & 0xFFFFu);
+                if (inrun && d == 0) act = false;                         // absorbed into the run: no code, no list entry
+                else if (inrun && d > 0) r = (r & 0xFFFF0000u) | (uint32_t)(d - 1);   // the residual that ends a run (ffv1enc.c:345-346)
+            }
             const uint32_t ctx = r >> 16;
-            const uint32_t nd = act ? decisions_of((int)(int16_t)(r & 0xFFFFu)) : 0u;
-            const uint32_t in = cr_incl_scan(nd, lane);
+            const uint32_t nd = (act && !GOLOMB) ? decisions_of((int)(int16_t)(r & 0xFFFFu)) : 0u;
+            const uint32_t in = GOLOMB ? 0u : cr_incl_scan(nd, lane);
             const uint32_t grp = __match_any_sync(0xFFFFFFFFu, act ? ctx : 0xFFFFFFFFu);
             const uint32_t rank = __popc(grp & lt_mask);
             uint32_t off = 0u;
             if (act && rank == 0u) off = (atomicAdd(&wh[ctx], (uint32_t)__popc(grp) << sh) >> sh) & 0xFFFFu;
             off = __shfl_sync(0xFFFFFFFFu, off, (__ffs(grp) - 1) & 31);
-            if (act) s_ent[(uint32_t)s_start[ctx] + off + rank] = make_uint2(pos + in - nd, (r & 0xFFFFu) | ((uint32_t)f << 16));
-            pos += __shfl_sync(0xFFFFFFFFu, in, 31);
+            if (act) s_ent[(uint32_t)s_start[ctx] + off + rank] = make_uint2(GOLOMB ? rec_line + (uint32_t)(x0 + lane) : pos + in - nd,
+                                                                            (r & 0xFFFFu) | ((uint32_t)f << 16));
+            if (!GOLOMB) pos += __shfl_sync(0xFFFFFFFFu, in, 31);
         }
     }
     __syncthreads();
@@ -763,14 +815,35 @@ bool ctx_replay_supported(const Layout &L)
     return !L.golomb && L.ctx_count <= kMaxListCtx;
 }
 
+bool ctx_lists_configurable(const Layout &L) { return L.ctx_count <= kMaxListCtx; }
+
 int ctx_scatter_smem_bytes(const Layout &L) { return (kScatterThreads / 32) * L.ctx_count * 4; }
 int ctx_scatter_sm_smem_bytes(const Layout &L) { return 9 * L.ctx_count * 4 + 3 * ((L.ctx_count + 7) & ~7) * 2 + kScatterSmMaxSamples * 8; }
 
 cudaError_t configure_ctx_replay(const Layout &L)
 {
-    cudaError_t e = cudaFuncSetAttribute(k_ctx_scatter_sm, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx_scatter_sm_smem_bytes(L));
+    cudaError_t e = cudaFuncSetAttribute(k_ctx_scatter_sm<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx_scatter_sm_smem_bytes(L));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_ctx_scatter_sm<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx_scatter_sm_smem_bytes(L));
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(k_ctx_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx_scatter_smem_bytes(L));
+}
+
+// Golomb-Rice mode: per-context lists of the samples that get a VLC code ({record index, residual | frame << 16})
+bool golomb_lists_supported(const Layout &L, int max_tile_samples)
+{
+    return L.golomb && L.ctx_count <= kMaxListCtx && max_tile_samples <= kScatterSmMaxSamples &&
+           (unsigned long long)L.rec_per_frame * 2ull <= L.dec_per_frame;
+}
+
+void launch_golomb_lists(const EncDeviceTables &t, const EncBatch &b, cudaStream_t s)
+{
+    const Layout &L = t.layout;
+    const int nchains = b.nseg * L.nslices * L.npc;
+    dim3 tiles(L.ctiles_per_frame, b.nframes);
+    k_ctx_hist<true><<<tiles, kHistThreads, 0, s>>>(t, b);
+    k_ctx_scan<<<nchains, kScanThreads, 0, s>>>(t, b);
+    k_ctx_scatter_sm<true><<<tiles, kScatterSmThreads, ctx_scatter_sm_smem_bytes(L), s>>>(t, b);
 }
 
 void launch_ctx_replay(const EncDeviceTables &t, const EncBatch &b, int max_tile_samples, cudaStream_t s)
@@ -778,7 +851,7 @@ void launch_ctx_replay(const EncDeviceTables &t, const EncBatch &b, int max_tile
     const Layout &L = t.layout;
     const int nchains = b.nseg * L.nslices * L.npc;
     dim3 tiles(L.ctiles_per_frame, b.nframes);
-    k_ctx_hist<<<tiles, kHistThreads, 0, s>>>(t, b);
+    k_ctx_hist<false><<<tiles, kHistThreads, 0, s>>>(t, b);
     k_ctx_scan<<<nchains, kScanThreads, 0, s>>>(t, b);
     const int n = b.nframes * L.nslices * L.npc;
     k_dec_layout<<<(n + 127) / 128, 128, 0, s>>>(t, b);
@@ -786,7 +859,7 @@ void launch_ctx_replay(const EncDeviceTables &t, const EncBatch &b, int max_tile
     static int staged = -1;
     if (staged < 0) { const char *v = getenv("FFV1B200_SCATTER"); staged = (v && !strcmp(v, "direct")) ? 0 : 1; }
     if (staged && max_tile_samples <= kScatterSmMaxSamples) {
-        k_ctx_scatter_sm<<<tiles, kScatterSmThreads, ctx_scatter_sm_smem_bytes(L), s>>>(t, b);
+        k_ctx_scatter_sm<false><<<tiles, kScatterSmThreads, ctx_scatter_sm_smem_bytes(L), s>>>(t, b);
     } else {
         dim3 stiles((L.ctiles_per_frame + kScatterThreads / 32 - 1) / (kScatterThreads / 32), b.nframes);
         k_ctx_scatter<<<stiles, kScatterThreads, ctx_scatter_smem_bytes(L), s>>>(t, b);

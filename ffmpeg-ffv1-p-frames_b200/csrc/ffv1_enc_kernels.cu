@@ -915,6 +915,149 @@ __global__ void __launch_bounds__(32) k_golomb(const EncDeviceTables T, const En
     }
 }
 
+// =================================================================================================
+// Golomb-Rice mode, decomposed (small context model): the adaptive part -- which Rice parameter k and which sign
+// flip a sample gets, put_vlc_symbol / update_vlc_state (ffv1enc.c:240-269, ffv1.h:192-224) -- depends only on the
+// samples coded in the same context, so it is replayed per context list like the range coder's states
+// (ffv1_ctx_replay.cu builds the lists: hist / scan / scatter in Golomb mode); what is left for the sequential walk of
+// a slice is the run mode and the bit writer, and that walk no longer chains the frames of a GOP.
+//   k_gr_replay   one lane per (chain, context) list: VlcState in registers -> code word (value | length << 26) of
+//                 every coded sample, stored at the sample's record index in the code array (the decision buffer)
+//   k_gr_pack     one warp per (frame, slice): run mode (ffv1enc.c:327-367) + MSB-first bit writer over the code words
+// =================================================================================================
+constexpr int kGrReplayWarps = 4;
+
+__global__ void __launch_bounds__(32 * kGrReplayWarps) k_gr_replay(const EncDeviceTables T, const EncBatch B)
+{
+    const Layout &L = T.layout;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int chain = blockIdx.x;
+    const int pc = chain % L.npc, s = (chain / L.npc) % L.nslices, seg = chain / (L.npc * L.nslices);
+    const SliceGeom &g = T.slices[s];
+    const int f0 = B.seg_first[seg], f1 = B.seg_first[seg + 1];
+    const int nctx = L.ctx_count;
+    const int oi = (blockIdx.y * kGrReplayWarps + warp) * 32 + lane;       // lists in order of decreasing length
+    if (oi >= nctx) return;
+    const int c = B.list_order[(size_t)chain * nctx + oi];
+    uint32_t n = B.list_count[(size_t)chain * nctx + c];
+    const uint2 *lp = B.lists + (size_t)f0 * L.samples_per_frame + (size_t)(f1 - f0) * g.list_off[pc] + B.list_start[(size_t)chain * nctx + c];
+    // VlcState of (slice, plane context, context): {drift 0, error_sum 4, bias 0, count 1} on keyframes (ffv1.c:194-199)
+    const size_t pc_bytes = (size_t)nctx * 32;
+    const size_t sidx = ((size_t)s * L.npc + pc) * (pc_bytes / 8) + c;
+    int drift = 0, esum = 4, bias = 0, count = 1;
+    if (!B.frame_key[f0]) {
+        const uint2 v = reinterpret_cast<const uint2 *>(B.carry_in)[sidx];
+        drift = (int)(int16_t)(v.x & 0xFFFFu); esum = (int)(v.x >> 16); bias = (int)(int8_t)(v.y & 0xFFu); count = (int)((v.y >> 8) & 0xFFu);
+    }
+    uint32_t *code = reinterpret_cast<uint32_t *>(B.dec) + g.rec_first;
+    const size_t code_frame = L.dec_per_frame / 2;                          // 32-bit words per frame in the code array
+    const int bits = L.coded_bits;
+    for (uint32_t i = 0; i < n; i++) {
+        const uint2 en = lp[i];
+        int v = (int)(int16_t)(en.y & 0xFFFFu);
+        // put_vlc_symbol + set_sr_golomb
+        v = ((v - bias) << (32 - bits)) >> (32 - bits);                     // fold
+        int k = 0;
+        for (int q = count; q < esum; q += q) k++;
+        const int cd = v ^ ((2 * drift + count) >> 31);
+        int m = -2 * cd - 1;
+        m ^= m >> 31;
+        const int e = m >> k;
+        uint32_t len, val;
+        if (e < 12) { len = (uint32_t)(e + k + 1); val = (1u << k) + ((uint32_t)m & ((1u << k) - 1u)); }
+        else        { len = (uint32_t)(12 + bits); val = (uint32_t)(m - 11); }
+        code[(size_t)(en.y >> 16) * code_frame + en.x] = val | (len << 26);
+        // update_vlc_state
+        esum += abs(v);
+        drift += v;
+        if (count == 128) { count >>= 1; drift >>= 1; esum >>= 1; }
+        count++;
+        if (drift <= -count) {
+            if (bias > -128) bias--;
+            drift += count;
+            if (drift <= -count) drift = -count + 1;
+        } else if (drift > 0) {
+            if (bias < 127) bias++;
+            drift -= count;
+            if (drift > 0) drift = 0;
+        }
+    }
+    if (f1 == B.nframes)
+        reinterpret_cast<uint2 *>(B.carry_out)[sidx] = make_uint2(((uint32_t)drift & 0xFFFFu) | ((uint32_t)esum << 16),
+                                                                   ((uint32_t)bias & 0xFFu) | ((uint32_t)count << 8));
+}
+
+__global__ void __launch_bounds__(32) k_gr_pack(const EncDeviceTables T, const EncBatch B)
+{
+    const Layout &L = T.layout;
+    const int lane = threadIdx.x;
+    const int f = blockIdx.x / L.nslices, s = blockIdx.x - f * L.nslices;
+    const SliceGeom &g = T.slices[s];
+    const int key = B.frame_key[f] ? 1 : 0;
+    uint8_t *out = B.scratch + (size_t)f * L.scratch_per_frame + g.scratch_off + kScratchLead;
+    const int npre = T.gprefix_len[s * 2 + key];
+    const uint8_t *pre = T.gprefix + (size_t)(s * 2 + key) * kMaxGolombPrefix;
+    for (int i = lane; i < npre; i += 32) out[i] = pre[i];
+    BitW w;
+    w.buf = out; w.pos = (uint32_t)npre; w.cap = g.scratch_cap - kScratchLead; w.acc = 0; w.nbits = 0;
+    const uint32_t *rec_slice = B.rec + (size_t)f * L.rec_per_frame + g.rec_first;
+    const uint32_t *code_slice = reinterpret_cast<const uint32_t *>(B.dec) + (size_t)f * (L.dec_per_frame / 2) + g.rec_first;
+    int run_index = 0;
+    for (int li = 0; li < g.nlines; li++) {
+        const LineDesc ld = T.lines[g.line_first + li];
+        if (!L.rgb && ld.y == 0) run_index = 0;                           // encode_plane starts a new plane (ffv1enc.c:379)
+        const uint32_t *recp = rec_slice + ld.rec_off, *codep = code_slice + ld.rec_off;
+        int run_count = 0, run_mode = 0;
+        uint32_t nr = lane < ld.w ? recp[lane] : 0u, nc = lane < ld.w ? codep[lane] : 0u;
+        for (int x0 = 0; x0 < ld.w; x0 += 32) {
+            const uint32_t rr = nr, cc = nc;
+            if (x0 + 32 + lane < ld.w) { nr = recp[x0 + 32 + lane]; nc = codep[x0 + 32 + lane]; }
+            const int n = min(32, (int)ld.w - x0);
+            for (int kk = 0; kk < n; kk++) {
+                const uint32_t r = __shfl_sync(0xFFFFFFFFu, rr, kk), cw = __shfl_sync(0xFFFFFFFFu, cc, kk);
+                if (lane != 0) continue;
+                const bool nz = (r & 0xFFFFu) != 0u;
+                if ((r >> 16) == 0u) run_mode = 1;
+                if (run_mode) {
+                    if (nz) {
+                        while (run_count >= 1 << c_enc_log2_run[run_index]) {
+                            run_count -= 1 << c_enc_log2_run[run_index];
+                            run_index++;
+                            bw_put(w, 1, 1u);
+                        }
+                        bw_put(w, 1 + c_enc_log2_run[run_index], (uint32_t)run_count);
+                        if (run_index) run_index--;
+                        run_count = 0; run_mode = 0;
+                    } else
+                        run_count++;
+                }
+                if (!run_mode) bw_put(w, (int)(cw >> 26), cw & 0x3FFFFFFu);
+            }
+        }
+        if (lane == 0 && run_mode) {                                       // end-of-line run flush (ffv1enc.c:358-367)
+            while (run_count >= 1 << c_enc_log2_run[run_index]) {
+                run_count -= 1 << c_enc_log2_run[run_index];
+                run_index++;
+                bw_put(w, 1, 1u);
+            }
+            if (run_count) bw_put(w, 1, 1u);
+        }
+    }
+    if (lane == 0) {
+        if (w.nbits) bw_put(w, 8 - w.nbits, 0u);                          // flush_put_bits: zero padding to a byte
+        B.slice_bytes[f * L.nslices + s] = w.pos;
+        if (w.pos > w.cap) atomicMax(&B.status[1], (unsigned long long)w.pos);
+    }
+}
+
+void launch_golomb_coder(const EncDeviceTables &t, const EncBatch &b, cudaStream_t s)
+{
+    const Layout &L = t.layout;
+    dim3 grid(b.nseg * L.nslices * L.npc, (L.ctx_count + 32 * kGrReplayWarps - 1) / (32 * kGrReplayWarps));
+    k_gr_replay<<<grid, 32 * kGrReplayWarps, 0, s>>>(t, b);
+    k_gr_pack<<<b.nframes * L.nslices, 32, 0, s>>>(t, b);
+}
+
 void launch_golomb(const EncDeviceTables &t, const EncBatch &b, cudaStream_t s)
 {
     // VlcStates of the chain (8 bytes per context and plane context) in shared memory when they fit

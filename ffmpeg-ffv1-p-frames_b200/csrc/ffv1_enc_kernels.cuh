@@ -77,6 +77,11 @@ int  replay_smem_bytes(const Layout &L);
 void launch_replay(const EncDeviceTables &t, const EncBatch &b, cudaStream_t s);
 void launch_rangecode(const EncDeviceTables &t, const EncBatch &b, cudaStream_t s);
 void launch_golomb(const EncDeviceTables &t, const EncBatch &b, cudaStream_t s);
+// Golomb-Rice mode decomposed by context (small context model): lists (ffv1_ctx_replay.cu), then VlcState replay + bit writer
+bool golomb_lists_supported(const Layout &L, int max_tile_samples);
+bool ctx_lists_configurable(const Layout &L);
+void launch_golomb_lists(const EncDeviceTables &t, const EncBatch &b, cudaStream_t s);
+void launch_golomb_coder(const EncDeviceTables &t, const EncBatch &b, cudaStream_t s);
 void launch_pack(const EncDeviceTables &t, const EncBatch &b, cudaStream_t s);
 cudaError_t configure_kernels(const Layout &L);
 // context-decomposed state replay (ffv1_ctx_replay.cu)

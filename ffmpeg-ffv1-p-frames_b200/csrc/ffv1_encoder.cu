@@ -72,7 +72,7 @@ struct FFV1B200Encoder {
     uint64_t submitted = 0, collected = 0;      // batch counters; slot of batch k = k % kSlots
     int carry_next = 0;                          // ring index holding the state after the last submitted batch
     double dec_per_sample = 5.0;
-    bool state_in_smem = true, fast_pixel = false, ctx_replay = false, fused_replay = false;
+    bool state_in_smem = true, fast_pixel = false, ctx_replay = false, fused_replay = false, golomb_lists = false;
     int max_plane_width = 0, num_sms = 148, max_ctile_samples = 0;
     FFV1B200EncStats stats{};
     int last_slot = 0;
@@ -132,7 +132,7 @@ int alloc_buffers(FFV1B200Encoder *e)
     CU_TRY(e->d_run_cnt.alloc((size_t)L.runs_per_frame * F));
     CU_TRY(e->d_slice_bytes.alloc((size_t)L.nslices * F));
     CU_TRY(e->d_scratch.alloc((size_t)L.scratch_per_frame * F));
-    if (!L.golomb) CU_TRY(e->d_dec.alloc((size_t)L.dec_per_frame * F + 64));
+    if (!L.golomb || e->golomb_lists) CU_TRY(e->d_dec.alloc((size_t)L.dec_per_frame * F + 64));   // Golomb lists: the code words
     const size_t state_bytes = (size_t)L.nslices * L.npc * L.ctx_count * 32;
     for (int k = 0; k < kCarry; k++) {
         CU_TRY(e->d_carry[k].alloc(state_bytes));
@@ -140,7 +140,7 @@ int alloc_buffers(FFV1B200Encoder *e)
     }
     const size_t g = e->cfg.gop_size > 0 ? e->cfg.gop_size : 1;
     const size_t nseg_max = (F + g - 1) / g + 1;
-    if (e->ctx_replay && !e->fused_replay) {
+    if ((e->ctx_replay && !e->fused_replay) || e->golomb_lists) {
         const size_t nchains = nseg_max * L.nslices * L.npc;
         CU_TRY(e->d_line_pos.alloc((size_t)L.lines_per_frame * F));
         CU_TRY(e->d_ctx_hist.alloc((size_t)L.ctiles_per_frame * L.ctx_count * F));
@@ -149,7 +149,7 @@ int alloc_buffers(FFV1B200Encoder *e)
         CU_TRY(e->d_list_order.alloc(nchains * L.ctx_count));
         CU_TRY(e->d_lists.alloc((size_t)L.samples_per_frame * F));
     }
-    if ((!e->state_in_smem && !e->ctx_replay && !e->fused_replay) || L.golomb)
+    if ((!e->state_in_smem && !e->ctx_replay && !e->fused_replay) || (L.golomb && !e->golomb_lists))
         CU_TRY(e->d_state_seg.alloc(state_bytes * nseg_max));            // one state set per GOP segment of a batch
     for (Slot &sl : e->slot) {
         CU_TRY(sl.d_planes.alloc(F * 4)); CU_TRY(sl.h_planes.alloc(F * 4));
@@ -233,11 +233,13 @@ int enqueue_kernels(FFV1B200Encoder *e, Slot &sl, cudaStream_t s)
     else if (e->ctx_replay) launch_ctx_replay(t, b, e->max_ctile_samples, s);
     else if (!L.golomb) launch_replay(t, b, s);
     cudaEventRecord(sl.ev[2], s);
-    if (!L.golomb) launch_rangecode(t, b, s); else launch_golomb(t, b, s);
+    if (!L.golomb) launch_rangecode(t, b, s);
+    else if (e->golomb_lists) { launch_golomb_lists(t, b, s); launch_golomb_coder(t, b, s); }
+    else launch_golomb(t, b, s);
     cudaEventRecord(sl.ev[3], s);
     launch_pack(t, b, s);
     cudaEventRecord(sl.ev[4], s);
-    e->stats.kernel_launches += L.golomb ? 4 : (e->fused_replay ? 5 : (e->ctx_replay ? 9 : 5));
+    e->stats.kernel_launches += L.golomb ? (e->golomb_lists ? 8 : 4) : (e->fused_replay ? 5 : (e->ctx_replay ? 9 : 5));
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaMemcpyAsync(sl.h_status.p, sl.d_status.p, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost, s));
     CU_TRY(cudaMemcpyAsync(sl.h_pkt_size.p, sl.d_pkt_size.p, sizeof(uint32_t) * nframes, cudaMemcpyDeviceToHost, s));
@@ -393,6 +395,10 @@ int ffv1b200_enc_open(FFV1B200Encoder **out, const FFV1B200EncParams *p)
         for (int i = 0; i < ct.nlines; i++) ns += e->tab.lines[g.line_first + e->tab.pc_lines[g.pc_line_first[ct.pc] + ct.first + i]].w;
         e->max_ctile_samples = std::max(e->max_ctile_samples, ns);
     }
+    // Golomb-Rice mode decomposed by context (FFV1B200_GOLOMB=serial keeps the one-coder-per-chain kernel)
+    e->golomb_lists = golomb_lists_supported(L, e->max_ctile_samples);
+    if (const char *v = getenv("FFV1B200_GOLOMB")) { if (!strcmp(v, "serial")) e->golomb_lists = false; }
+    if (e->golomb_lists) CU_TRY(configure_ctx_replay(L));
     CU_TRY(cudaDeviceGetAttribute(&e->num_sms, cudaDevAttrMultiProcessorCount, e->device));
 
     cudaStream_t s = e->s_comp;
