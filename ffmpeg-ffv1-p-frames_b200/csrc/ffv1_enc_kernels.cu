@@ -925,66 +925,120 @@ __global__ void __launch_bounds__(32) k_golomb(const EncDeviceTables T, const En
 //                 every coded sample, stored at the sample's record index in the code array (the decision buffer)
 //   k_gr_pack     one warp per (frame, slice): run mode (ffv1enc.c:327-367) + MSB-first bit writer over the code words
 // =================================================================================================
-constexpr int kGrReplayWarps = 4;
+constexpr int kGrThreads = 256;           // lanes of a chain's CTA: one (or a few) context lists per lane for the whole chain
+constexpr int kGrSlots = 4;               // context lists per lane (ctx_count <= 1024)
 
-__global__ void __launch_bounds__(32 * kGrReplayWarps) k_gr_replay(const EncDeviceTables T, const EncBatch B)
+// One CTA per (GOP segment, slice, plane context) chain; lane <-> context list(s), VlcState in registers for the whole
+// chain.  The CTA walks the chain window by window (`window` context tiles of a frame, bounds from k_ctx_scan's tile
+// bases staged in shared memory) so that the code words it scatters into the code array land in a stretch that is
+// completed while it is still in L2 -- with every lane running through its whole list at its own pace each 4-byte
+// store was a read-modify-write of a DRAM sector.
+__global__ void __launch_bounds__(kGrThreads, 4) k_gr_replay(const EncDeviceTables T, const EncBatch B, const int window)
 {
+    extern __shared__ __align__(16) uint32_t s_gr[];                        // [2][nctx] the window's part of every list
     const Layout &L = T.layout;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tid = threadIdx.x;
     const int chain = blockIdx.x;
     const int pc = chain % L.npc, s = (chain / L.npc) % L.nslices, seg = chain / (L.npc * L.nslices);
     const SliceGeom &g = T.slices[s];
     const int f0 = B.seg_first[seg], f1 = B.seg_first[seg + 1];
     const int nctx = L.ctx_count;
-    const int oi = (blockIdx.y * kGrReplayWarps + warp) * 32 + lane;       // lists in order of decreasing length
-    if (oi >= nctx) return;
-    const int c = B.list_order[(size_t)chain * nctx + oi];
-    uint32_t n = B.list_count[(size_t)chain * nctx + c];
-    const uint2 *lp = B.lists + (size_t)f0 * L.samples_per_frame + (size_t)(f1 - f0) * g.list_off[pc] + B.list_start[(size_t)chain * nctx + c];
-    // VlcState of (slice, plane context, context): {drift 0, error_sum 4, bias 0, count 1} on keyframes (ffv1.c:194-199)
+    uint32_t *s_b0 = s_gr, *s_b1 = s_gr + nctx;
+    const uint32_t *lcount = B.list_count + (size_t)chain * nctx;
+    const uint2 *chain_list = B.lists + (size_t)f0 * L.samples_per_frame + (size_t)(f1 - f0) * g.list_off[pc];
     const size_t pc_bytes = (size_t)nctx * 32;
-    const size_t sidx = ((size_t)s * L.npc + pc) * (pc_bytes / 8) + c;
-    int drift = 0, esum = 4, bias = 0, count = 1;
-    if (!B.frame_key[f0]) {
-        const uint2 v = reinterpret_cast<const uint2 *>(B.carry_in)[sidx];
-        drift = (int)(int16_t)(v.x & 0xFFFFu); esum = (int)(v.x >> 16); bias = (int)(int8_t)(v.y & 0xFFu); count = (int)((v.y >> 8) & 0xFFu);
-    }
-    uint32_t *code = reinterpret_cast<uint32_t *>(B.dec) + g.rec_first;
-    const size_t code_frame = L.dec_per_frame / 2;                          // 32-bit words per frame in the code array
+    const size_t sbase = ((size_t)s * L.npc + pc) * (pc_bytes / 8);
+    const bool key = B.frame_key[f0] != 0;
     const int bits = L.coded_bits;
-    for (uint32_t i = 0; i < n; i++) {
-        const uint2 en = lp[i];
-        int v = (int)(int16_t)(en.y & 0xFFFFu);
-        // put_vlc_symbol + set_sr_golomb
-        v = ((v - bias) << (32 - bits)) >> (32 - bits);                     // fold
-        int k = 0;
-        for (int q = count; q < esum; q += q) k++;
-        const int cd = v ^ ((2 * drift + count) >> 31);
-        int m = -2 * cd - 1;
-        m ^= m >> 31;
-        const int e = m >> k;
-        uint32_t len, val;
-        if (e < 12) { len = (uint32_t)(e + k + 1); val = (1u << k) + ((uint32_t)m & ((1u << k) - 1u)); }
-        else        { len = (uint32_t)(12 + bits); val = (uint32_t)(m - 11); }
-        code[(size_t)(en.y >> 16) * code_frame + en.x] = val | (len << 26);
-        // update_vlc_state
-        esum += abs(v);
-        drift += v;
-        if (count == 128) { count >>= 1; drift >>= 1; esum >>= 1; }
-        count++;
-        if (drift <= -count) {
-            if (bias > -128) bias--;
-            drift += count;
-            if (drift <= -count) drift = -count + 1;
-        } else if (drift > 0) {
-            if (bias < 127) bias++;
-            drift -= count;
-            if (drift > 0) drift = 0;
+    // my lists: contexts order[tid], order[tid + 256], ... (the order is by decreasing list length)
+    int ctx[kGrSlots], drift[kGrSlots], esum[kGrSlots], bias[kGrSlots], count[kGrSlots];
+    uint32_t lstart[kGrSlots];
+#pragma unroll
+    for (int j = 0; j < kGrSlots; j++) {
+        const int oi = tid + j * kGrThreads;
+        ctx[j] = -1; drift[j] = 0; esum[j] = 4; bias[j] = 0; count[j] = 1; lstart[j] = 0u;   // {0,4,0,1} on keyframes (ffv1.c:194-199)
+        if (oi < nctx) {
+            const int c = B.list_order[(size_t)chain * nctx + oi];
+            ctx[j] = c;
+            lstart[j] = B.list_start[(size_t)chain * nctx + c];
+            if (!key) {
+                const uint2 v = reinterpret_cast<const uint2 *>(B.carry_in)[sbase + c];
+                drift[j] = (int)(int16_t)(v.x & 0xFFFFu); esum[j] = (int)(v.x >> 16);
+                bias[j] = (int)(int8_t)(v.y & 0xFFu); count[j] = (int)((v.y >> 8) & 0xFFu);
+            }
         }
     }
-    if (f1 == B.nframes)
-        reinterpret_cast<uint2 *>(B.carry_out)[sidx] = make_uint2(((uint32_t)drift & 0xFFFFu) | ((uint32_t)esum << 16),
-                                                                   ((uint32_t)bias & 0xFFu) | ((uint32_t)count << 8));
+    const size_t code_frame = L.dec_per_frame / 2;                          // 32-bit words per frame in the code array
+    const int t0 = g.ct_first[pc], nt = g.ct_count[pc];
+    for (int f = f0; f < f1; f++) {
+        uint32_t *code = reinterpret_cast<uint32_t *>(B.dec) + (size_t)f * code_frame + g.rec_first;
+        for (int tw = 0; tw < nt; tw += window) {
+            __syncthreads();                                                // everybody is done with the previous window's bounds
+            const bool last_win = tw + window >= nt;
+            const uint32_t *bf = B.ctx_hist + ((size_t)f * L.ctiles_per_frame + t0 + tw) * nctx;
+            const uint32_t *bn = last_win ? B.ctx_hist + ((size_t)(f + 1) * L.ctiles_per_frame + t0) * nctx
+                                          : B.ctx_hist + ((size_t)f * L.ctiles_per_frame + t0 + tw + window) * nctx;
+            const bool use_bn = !last_win || f + 1 < f1;
+            for (int i = tid; i < nctx; i += kGrThreads) { s_b0[i] = bf[i]; s_b1[i] = use_bn ? bn[i] : lcount[i]; }
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < kGrSlots; j++) {
+                if (ctx[j] < 0) continue;
+                const uint32_t b0 = s_b0[ctx[j]], b1 = s_b1[ctx[j]];
+                const uint2 *lp = chain_list + lstart[j];
+                // four entries per round, the next round's loads in flight while this one is coded: with ~2000 lists
+                // streaming per SM the lines do not survive in L1, so every load is an L2 (or DRAM) round trip
+                uint2 nxt[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) nxt[q] = b0 + q < b1 ? lp[b0 + q] : make_uint2(0u, 0u);
+                for (uint32_t i = b0; i < b1; i += 4u) {
+                    uint2 cur[4];
+#pragma unroll
+                    for (int q = 0; q < 4; q++) { cur[q] = nxt[q]; if (i + 4u + q < b1) nxt[q] = lp[i + 4u + q]; }
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        if (i + q >= b1) break;
+                        const uint2 en = cur[q];
+                        int v = (int)(int16_t)(en.y & 0xFFFFu);
+                        // put_vlc_symbol + set_sr_golomb (ffv1enc.c:240-269, golomb.h:554-563), branch-free: the lanes of a
+                        // warp run different lists, and the longest list of the chain is the critical path of the CTA
+                        const int cn = count[j], es = esum[j];
+                        v = ((v - bias[j]) << (32 - bits)) >> (32 - bits);      // fold
+                        // k = smallest k with (count << k) >= error_sum: floor-log2 difference, plus one if that falls short
+                        const int t = max(__clz(cn) - __clz(es), 0);
+                        const int k = es > cn ? t + (((uint32_t)cn << t) < (uint32_t)es ? 1 : 0) : 0;
+                        const int cd = v ^ ((2 * drift[j] + cn) >> 31);
+                        int m = -2 * cd - 1;
+                        m ^= m >> 31;
+                        const int e = m >> k;
+                        const bool esc = e >= 12;
+                        const uint32_t len = esc ? (uint32_t)(12 + bits) : (uint32_t)(e + k + 1);
+                        const uint32_t val = esc ? (uint32_t)(m - 11) : (1u << k) + ((uint32_t)m & ((1u << k) - 1u));
+                        code[en.x] = val | (len << 26);
+                        // update_vlc_state (ffv1.h:192-224)
+                        int d2 = drift[j] + v, e2 = es + abs(v), c2 = cn;
+                        const int half = cn == 128 ? 1 : 0;
+                        c2 >>= half; d2 >>= half; e2 >>= half;
+                        c2++;
+                        const bool neg = d2 <= -c2, pos = d2 > 0;
+                        int b2 = bias[j] + (pos ? 1 : 0) - (neg ? 1 : 0);
+                        b2 = max(-128, min(127, b2));
+                        d2 += neg ? c2 : (pos ? -c2 : 0);
+                        if (neg) d2 = max(d2, -c2 + 1);
+                        if (pos) d2 = min(d2, 0);
+                        drift[j] = d2; esum[j] = e2; count[j] = c2; bias[j] = b2;
+                    }
+                }
+            }
+        }
+    }
+    if (f1 == B.nframes) {
+#pragma unroll
+        for (int j = 0; j < kGrSlots; j++)
+            if (ctx[j] >= 0)
+                reinterpret_cast<uint2 *>(B.carry_out)[sbase + ctx[j]] = make_uint2(((uint32_t)drift[j] & 0xFFFFu) | ((uint32_t)esum[j] << 16),
+                                                                                    ((uint32_t)bias[j] & 0xFFu) | ((uint32_t)count[j] << 8));
+    }
 }
 
 __global__ void __launch_bounds__(32) k_gr_pack(const EncDeviceTables T, const EncBatch B)
@@ -1053,8 +1107,9 @@ __global__ void __launch_bounds__(32) k_gr_pack(const EncDeviceTables T, const E
 void launch_golomb_coder(const EncDeviceTables &t, const EncBatch &b, cudaStream_t s)
 {
     const Layout &L = t.layout;
-    dim3 grid(b.nseg * L.nslices * L.npc, (L.ctx_count + 32 * kGrReplayWarps - 1) / (32 * kGrReplayWarps));
-    k_gr_replay<<<grid, 32 * kGrReplayWarps, 0, s>>>(t, b);
+    static int window = -1;
+    if (window < 0) { const char *v = getenv("FFV1B200_GOLOMB_WINDOW"); window = v ? atoi(v) : 3; if (window < 1) window = 1 << 20; }
+    k_gr_replay<<<b.nseg * L.nslices * L.npc, kGrThreads, 2 * L.ctx_count * sizeof(uint32_t), s>>>(t, b, window);
     k_gr_pack<<<b.nframes * L.nslices, 32, 0, s>>>(t, b);
 }
 
