@@ -1041,66 +1041,160 @@ __global__ void __launch_bounds__(kGrThreads, 4) k_gr_replay(const EncDeviceTabl
     }
 }
 
-__global__ void __launch_bounds__(32) k_gr_pack(const EncDeviceTables T, const EncBatch B)
+constexpr int kGrPackWarps = 4;            // (frame, slice) units per CTA
+constexpr int kGrPackWin = 96;             // 32-bit words of the per-warp bit window (a group appends at most ~75)
+
+// put_bits (put_bits.h:152-195) into the warp's shared-memory window: `len` bits of `val` at bit position p counted
+// from the start of the slice's scratch payload; wbase = index of the window's first word.  MSB-first.
+__device__ __forceinline__ void gr_window_or(uint32_t *win, uint32_t wbase, uint32_t p, uint32_t len, uint32_t val, bool atomic)
 {
+    const uint32_t sh = p & 31u, wi = (p >> 5) - wbase;
+    const unsigned long long v64 = (unsigned long long)val << (64u - len - sh);     // len + sh <= 57
+    const uint32_t hi = (uint32_t)(v64 >> 32), lo = (uint32_t)v64;
+    if (atomic) { atomicOr(&win[wi], hi); if (lo) atomicOr(&win[wi + 1], lo); }
+    else        { win[wi] |= hi; win[wi + 1] |= lo; }
+}
+
+// One warp per (frame, slice).  Groups of 32 samples without a run-mode sample (the normal case on natural content) are
+// packed by all lanes at once: exclusive scan of the code lengths, every lane ORs its code word into the window, the
+// completed words go out as big-endian 32-bit stores.  Groups that touch run mode (ffv1enc.c:327-367) are walked by
+// lane 0 through the same window.
+__global__ void __launch_bounds__(32 * kGrPackWarps) k_gr_pack(const EncDeviceTables T, const EncBatch B)
+{
+    __shared__ uint32_t s_win[kGrPackWarps][kGrPackWin];
     const Layout &L = T.layout;
-    const int lane = threadIdx.x;
-    const int f = blockIdx.x / L.nslices, s = blockIdx.x - f * L.nslices;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int unit = blockIdx.x * kGrPackWarps + warp;
+    if (unit >= B.nframes * L.nslices) return;
+    const int f = unit / L.nslices, s = unit - f * L.nslices;
     const SliceGeom &g = T.slices[s];
     const int key = B.frame_key[f] ? 1 : 0;
-    uint8_t *out = B.scratch + (size_t)f * L.scratch_per_frame + g.scratch_off + kScratchLead;
+    uint8_t *out = B.scratch + (size_t)f * L.scratch_per_frame + g.scratch_off + kScratchLead;     // 4-byte aligned
+    uint32_t *out32 = reinterpret_cast<uint32_t *>(out);
+    const uint32_t cap = g.scratch_cap - kScratchLead;
     const int npre = T.gprefix_len[s * 2 + key];
     const uint8_t *pre = T.gprefix + (size_t)(s * 2 + key) * kMaxGolombPrefix;
-    for (int i = lane; i < npre; i += 32) out[i] = pre[i];
-    BitW w;
-    w.buf = out; w.pos = (uint32_t)npre; w.cap = g.scratch_cap - kScratchLead; w.acc = 0; w.nbits = 0;
+    for (int i = lane; i < (npre & ~3); i += 32) if ((uint32_t)i < cap) out[i] = pre[i];             // whole words of the prefix
+    uint32_t *win = s_win[warp];
+    for (int i = lane; i < kGrPackWin; i += 32) win[i] = 0u;
+    __syncwarp();
+    if (lane < (npre & 3)) atomicOr(&win[0], (uint32_t)pre[(npre & ~3) + lane] << (24 - 8 * lane)); // its last, partial word
+    __syncwarp();
+    uint32_t P = (uint32_t)npre * 8u;                                      // bits written (warp-uniform)
+    uint32_t wbase = P >> 5;
     const uint32_t *rec_slice = B.rec + (size_t)f * L.rec_per_frame + g.rec_first;
     const uint32_t *code_slice = reinterpret_cast<const uint32_t *>(B.dec) + (size_t)f * (L.dec_per_frame / 2) + g.rec_first;
-    int run_index = 0;
+    int run_index = 0;                                                     // lane 0
     for (int li = 0; li < g.nlines; li++) {
         const LineDesc ld = T.lines[g.line_first + li];
         if (!L.rgb && ld.y == 0) run_index = 0;                           // encode_plane starts a new plane (ffv1enc.c:379)
         const uint32_t *recp = rec_slice + ld.rec_off, *codep = code_slice + ld.rec_off;
-        int run_count = 0, run_mode = 0;
-        uint32_t nr = lane < ld.w ? recp[lane] : 0u, nc = lane < ld.w ? codep[lane] : 0u;
+        int run_count = 0;                                                 // lane 0; run mode at a group start = carry
+        uint32_t carry = 0u, run_open = 0u;
+        uint32_t nr = lane < ld.w ? recp[lane] : 0xFFFF0001u, nc = lane < ld.w ? codep[lane] : 0u;
         for (int x0 = 0; x0 < ld.w; x0 += 32) {
+            const bool act = x0 + lane < ld.w;
             const uint32_t rr = nr, cc = nc;
+            nr = 0xFFFF0001u;
             if (x0 + 32 + lane < ld.w) { nr = recp[x0 + 32 + lane]; nc = codep[x0 + 32 + lane]; }
-            const int n = min(32, (int)ld.w - x0);
-            for (int kk = 0; kk < n; kk++) {
-                const uint32_t r = __shfl_sync(0xFFFFFFFFu, rr, kk), cw = __shfl_sync(0xFFFFFFFFu, cc, kk);
-                if (lane != 0) continue;
-                const bool nz = (r & 0xFFFFu) != 0u;
-                if ((r >> 16) == 0u) run_mode = 1;
-                if (run_mode) {
-                    if (nz) {
-                        while (run_count >= 1 << c_enc_log2_run[run_index]) {
-                            run_count -= 1 << c_enc_log2_run[run_index];
-                            run_index++;
-                            bw_put(w, 1, 1u);
-                        }
-                        bw_put(w, 1 + c_enc_log2_run[run_index], (uint32_t)run_count);
-                        if (run_index) run_index--;
-                        run_count = 0; run_mode = 0;
-                    } else
-                        run_count++;
+            const uint32_t zero = __ballot_sync(0xFFFFFFFFu, act && (rr & 0xFFFFu) == 0u);
+            const uint32_t ctx0 = __ballot_sync(0xFFFFFFFFu, act && (rr >> 16) == 0u);
+            const uint32_t cin = carry;
+            // same carry chain as in the list builder (gr_run_members, ffv1_ctx_replay.cu)
+            const unsigned long long sum = (unsigned long long)zero + (zero & ctx0) + cin;
+            const uint32_t mem = ctx0 | ((uint32_t)sum ^ zero ^ (zero & ctx0));
+            carry = (uint32_t)(sum >> 32);
+            run_open = ((mem & zero) >> (min(32, (int)ld.w - x0) - 1)) & 1u;   // the line's last sample so far is inside a run
+            uint32_t total;
+            if ((mem | cin) == 0u) {
+                // ---- no run mode in this group: all lanes at once
+                const uint32_t len = act ? cc >> 26 : 0u;
+                uint32_t incl = len;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const uint32_t n = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += n; }
+                total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+                if (len) gr_window_or(win, wbase, P + incl - len, len, cc & 0x3FFFFFFu, true);
+            } else {
+                // ---- lane 0 walks the group: run mode + codes
+                uint32_t p = P;
+                const int n = min(32, (int)ld.w - x0);
+                for (int kk = 0; kk < n; kk++) {
+                    const uint32_t r = __shfl_sync(0xFFFFFFFFu, rr, kk), cw = __shfl_sync(0xFFFFFFFFu, cc, kk);
+                    if (lane != 0) continue;
+                    const bool nz = (r & 0xFFFFu) != 0u;
+                    int run_mode = (int)((mem >> kk) & 1u);              // M(kk): this sample is coded in run mode
+                    if (run_mode) {
+                        if (nz) {
+                            while (run_count >= 1 << c_enc_log2_run[run_index]) {
+                                run_count -= 1 << c_enc_log2_run[run_index];
+                                run_index++;
+                                gr_window_or(win, wbase, p, 1u, 1u, false); p += 1u;
+                            }
+                            const uint32_t ln = 1u + c_enc_log2_run[run_index];
+                            gr_window_or(win, wbase, p, ln, (uint32_t)run_count, false); p += ln;
+                            if (run_index) run_index--;
+                            run_count = 0; run_mode = 0;
+                        } else
+                            run_count++;
+                    }
+                    if (!run_mode) { const uint32_t ln = cw >> 26; gr_window_or(win, wbase, p, ln, cw & 0x3FFFFFFu, false); p += ln; }
                 }
-                if (!run_mode) bw_put(w, (int)(cw >> 26), cw & 0x3FFFFFFu);
+                total = __shfl_sync(0xFFFFFFFFu, p, 0) - P;
+            }
+            P += total;
+            __syncwarp();
+            // ---- completed words -> scratch (big-endian), the partial one moves to the front of the window
+            const uint32_t nfull = (P >> 5) - wbase;
+            uint32_t keep = 0u;
+            if (nfull) {
+                for (uint32_t i = lane; i < nfull; i += 32)
+                    if ((wbase + i) * 4u + 4u <= cap) out32[wbase + i] = __byte_perm(win[i], 0u, 0x0123);
+                keep = win[nfull];
+                __syncwarp();
+                for (uint32_t i = lane; i <= nfull + 1u && i < (uint32_t)kGrPackWin; i += 32) win[i] = 0u;
+                __syncwarp();
+                if (lane == 0) win[0] = keep;
+                wbase += nfull;
+                __syncwarp();
             }
         }
-        if (lane == 0 && run_mode) {                                       // end-of-line run flush (ffv1enc.c:358-367)
-            while (run_count >= 1 << c_enc_log2_run[run_index]) {
-                run_count -= 1 << c_enc_log2_run[run_index];
-                run_index++;
-                bw_put(w, 1, 1u);
+        // end-of-line run flush (ffv1enc.c:358-367): lane 0, a handful of bits
+        if (run_open) {
+            uint32_t p = P;
+            if (lane == 0) {
+                while (run_count >= 1 << c_enc_log2_run[run_index]) {
+                    run_count -= 1 << c_enc_log2_run[run_index];
+                    run_index++;
+                    gr_window_or(win, wbase, p, 1u, 1u, false); p += 1u;
+                }
+                if (run_count) { gr_window_or(win, wbase, p, 1u, 1u, false); p += 1u; }
             }
-            if (run_count) bw_put(w, 1, 1u);
+            P = __shfl_sync(0xFFFFFFFFu, p, 0);
+            __syncwarp();
+            const uint32_t nfull = (P >> 5) - wbase;
+            if (nfull) {
+                for (uint32_t i = lane; i < nfull; i += 32)
+                    if ((wbase + i) * 4u + 4u <= cap) out32[wbase + i] = __byte_perm(win[i], 0u, 0x0123);
+                const uint32_t keep = win[nfull];
+                __syncwarp();
+                for (uint32_t i = lane; i <= nfull + 1u && i < (uint32_t)kGrPackWin; i += 32) win[i] = 0u;
+                __syncwarp();
+                if (lane == 0) win[0] = keep;
+                wbase += nfull;
+                __syncwarp();
+            }
         }
     }
+    // flush_put_bits: zero padding to a byte; the last, partial word goes out byte by byte
+    const uint32_t nbytes = (P + 7u) >> 3;
+    {
+        const uint32_t first = wbase * 4u;
+        const uint32_t wv = win[0];
+        if (lane < 4 && first + lane < nbytes && first + lane < cap) out[first + lane] = (uint8_t)(wv >> (24 - 8 * lane));
+    }
     if (lane == 0) {
-        if (w.nbits) bw_put(w, 8 - w.nbits, 0u);                          // flush_put_bits: zero padding to a byte
-        B.slice_bytes[f * L.nslices + s] = w.pos;
-        if (w.pos > w.cap) atomicMax(&B.status[1], (unsigned long long)w.pos);
+        B.slice_bytes[f * L.nslices + s] = nbytes;
+        if (nbytes > cap) atomicMax(&B.status[1], (unsigned long long)nbytes);
     }
 }
 
@@ -1110,7 +1204,7 @@ void launch_golomb_coder(const EncDeviceTables &t, const EncBatch &b, cudaStream
     static int window = -1;
     if (window < 0) { const char *v = getenv("FFV1B200_GOLOMB_WINDOW"); window = v ? atoi(v) : 3; if (window < 1) window = 1 << 20; }
     k_gr_replay<<<b.nseg * L.nslices * L.npc, kGrThreads, 2 * L.ctx_count * sizeof(uint32_t), s>>>(t, b, window);
-    k_gr_pack<<<b.nframes * L.nslices, 32, 0, s>>>(t, b);
+    k_gr_pack<<<(b.nframes * L.nslices + kGrPackWarps - 1) / kGrPackWarps, 32 * kGrPackWarps, 0, s>>>(t, b);
 }
 
 void launch_golomb(const EncDeviceTables &t, const EncBatch &b, cudaStream_t s)
