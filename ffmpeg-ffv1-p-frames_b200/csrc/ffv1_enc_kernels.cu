@@ -1084,7 +1084,7 @@ __global__ void __launch_bounds__(32 * kGrPackWarps) k_gr_pack(const EncDeviceTa
     uint32_t wbase = P >> 5;
     const uint32_t *rec_slice = B.rec + (size_t)f * L.rec_per_frame + g.rec_first;
     const uint32_t *code_slice = reinterpret_cast<const uint32_t *>(B.dec) + (size_t)f * (L.dec_per_frame / 2) + g.rec_first;
-    int run_index = 0;                                                     // lane 0
+    int run_index = 0;                                                     // warp-uniform (lane 0 changes it on the serial paths)
     for (int li = 0; li < g.nlines; li++) {
         const LineDesc ld = T.lines[g.line_first + li];
         if (!L.rgb && ld.y == 0) run_index = 0;                           // encode_plane starts a new plane (ffv1enc.c:379)
@@ -1106,9 +1106,14 @@ __global__ void __launch_bounds__(32 * kGrPackWarps) k_gr_pack(const EncDeviceTa
             carry = (uint32_t)(sum >> 32);
             run_open = ((mem & zero) >> (min(32, (int)ld.w - x0) - 1)) & 1u;   // the line's last sample so far is inside a run
             uint32_t total;
-            if ((mem | cin) == 0u) {
-                // ---- no run mode in this group: all lanes at once
-                const uint32_t len = act ? cc >> 26 : 0u;
+            if (((mem & zero) | cin) == 0u) {
+                // ---- no sample is absorbed into a run: all lanes at once.  A run-mode sample of such a group ends a run of
+                //      length 0 at once: 1 + log2_run[run_index] zero bits in front of its code, then run_index-- (ffv1enc.c:
+                //      338-346), so its run_index is the group's minus the run-mode samples before it
+                const int ri = max(run_index - (int)__popc(mem & ((1u << lane) - 1u)), 0);
+                const uint32_t inrun = (mem >> lane) & 1u;
+                const uint32_t len = act ? (cc >> 26) + (inrun ? 1u + c_enc_log2_run[ri] : 0u) : 0u;
+                run_index = max(run_index - (int)__popc(mem), 0);
                 uint32_t incl = len;
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) { const uint32_t n = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += n; }
@@ -1140,6 +1145,7 @@ __global__ void __launch_bounds__(32 * kGrPackWarps) k_gr_pack(const EncDeviceTa
                     if (!run_mode) { const uint32_t ln = cw >> 26; gr_window_or(win, wbase, p, ln, cw & 0x3FFFFFFu, false); p += ln; }
                 }
                 total = __shfl_sync(0xFFFFFFFFu, p, 0) - P;
+                run_index = __shfl_sync(0xFFFFFFFFu, run_index, 0);
             }
             P += total;
             __syncwarp();
@@ -1170,6 +1176,7 @@ __global__ void __launch_bounds__(32 * kGrPackWarps) k_gr_pack(const EncDeviceTa
                 if (run_count) { gr_window_or(win, wbase, p, 1u, 1u, false); p += 1u; }
             }
             P = __shfl_sync(0xFFFFFFFFu, p, 0);
+            run_index = __shfl_sync(0xFFFFFFFFu, run_index, 0);
             __syncwarp();
             const uint32_t nfull = (P >> 5) - wbase;
             if (nfull) {
