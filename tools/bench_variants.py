@@ -1,5 +1,8 @@
+"""Encode throughput of the non-headline variants on the bench clip (256-frame batches, host path): Golomb-Rice with the
+small context model and the range coder with the large context model.  usage: bench_variants.py"""
 import sys, time, os
-sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/ffmpeg-ffv1-p-frames_b200")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "ffmpeg-ffv1-p-frames_b200"))
 import numpy as np, ffv1_b200
 from oracle import synth
 W,H,FMT=1920,1080,"yuv420p"
