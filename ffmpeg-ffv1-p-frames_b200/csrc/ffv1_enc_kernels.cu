@@ -925,15 +925,15 @@ __global__ void __launch_bounds__(32) k_golomb(const EncDeviceTables T, const En
 //                 every coded sample, stored at the sample's record index in the code array (the decision buffer)
 //   k_gr_pack     one warp per (frame, slice): run mode (ffv1enc.c:327-367) + MSB-first bit writer over the code words
 // =================================================================================================
-constexpr int kGrThreads = 256;           // lanes of a chain's CTA: one (or a few) context lists per lane for the whole chain
-constexpr int kGrSlots = 4;               // context lists per lane (ctx_count <= 1024)
+constexpr int kGrThreads = 128;           // lanes of a chain's CTA: one (or a few) context lists per lane for the whole chain
+constexpr int kGrSlots = 8;               // context lists per lane (ctx_count <= 1024)
 
 // One CTA per (GOP segment, slice, plane context) chain; lane <-> context list(s), VlcState in registers for the whole
 // chain.  The CTA walks the chain window by window (`window` context tiles of a frame, bounds from k_ctx_scan's tile
 // bases staged in shared memory) so that the code words it scatters into the code array land in a stretch that is
 // completed while it is still in L2 -- with every lane running through its whole list at its own pace each 4-byte
 // store was a read-modify-write of a DRAM sector.
-__global__ void __launch_bounds__(kGrThreads, 4) k_gr_replay(const EncDeviceTables T, const EncBatch B, const int window)
+__global__ void __launch_bounds__(kGrThreads, 8) k_gr_replay(const EncDeviceTables T, const EncBatch B, const int window)
 {
     extern __shared__ __align__(16) uint32_t s_gr[];                        // [2][nctx] the window's part of every list
     const Layout &L = T.layout;
