@@ -95,22 +95,19 @@ __device__ __forceinline__ void rd_init(RDec &c, const uint8_t *buf, uint32_t si
     c.ptr = buf + 2;
 }
 
-__device__ __forceinline__ int rd_get(RDec &c, uint8_t *state, const uint8_t *lut)
+__device__ __forceinline__ int rd_get(RDec &c, uint8_t *state, const uint16_t *lut)
 {
-    // get_rac + refill (rangecoder.h:104-145)
+    // get_rac + refill (rangecoder.h:104-145).  lut[s] = zero_state[s] | one_state[s] << 8: both successors of the
+    // state are fetched while the interval is split, the decoded bit only selects one (the dependent chain
+    // state -> bit -> table -> state is what a slice decoder's speed hangs on)
     const uint32_t s = *state;
+    const uint32_t zz = lut[s];
     const uint32_t range1 = (c.range * s) >> 8;
-    int bit;
-    c.range -= range1;
-    if (c.low < c.range) {
-        *state = lut[s];
-        bit = 0;
-    } else {
-        c.low -= c.range;
-        *state = lut[256 + s];
-        c.range = range1;
-        bit = 1;
-    }
+    const uint32_t r0 = c.range - range1;
+    const int bit = c.low >= r0;
+    c.low -= bit ? r0 : 0u;
+    c.range = bit ? range1 : r0;
+    *state = (uint8_t)(bit ? zz >> 8 : zz);
     if (c.range < 0x100u) {
         c.range <<= 8;
         c.low <<= 8;
@@ -120,7 +117,7 @@ __device__ __forceinline__ int rd_get(RDec &c, uint8_t *state, const uint8_t *lu
     return bit;
 }
 
-__device__ int rd_symbol(RDec &c, uint8_t *state, const uint8_t *lut, bool is_signed, int &err)
+__device__ int rd_symbol(RDec &c, uint8_t *state, const uint16_t *lut, bool is_signed, int &err)
 {
     // get_symbol_inline (ffv1dec.c:42-63)
     if (rd_get(c, state, lut)) return 0;
@@ -223,7 +220,7 @@ struct SliceRd {
 };
 
 // one line of one plane into the ring (ffv1dec.c:100-181).  cur/top/top2 point at x = 0 of the ring rows.
-__device__ void dec_line(SliceRd &sr, uint8_t *model, const int16_t *q, const uint8_t *lut, int16_t *cur, const int16_t *top,
+__device__ void dec_line(SliceRd &sr, uint8_t *model, const int16_t *q, const uint16_t *lut, int16_t *cur, const int16_t *top,
                          const int16_t *top2, int w, int bits)
 {
     const bool five = q[3 * 256 + 127] != 0;
@@ -279,10 +276,10 @@ __global__ void __launch_bounds__(32 * kDecWarps) k_decode(const DecDeviceTables
 {
     extern __shared__ __align__(16) unsigned char s_dyn[];      // per warp: [model of the current plane context][line ring]
     __shared__ int16_t s_quant[kDecSmemQuant];
-    __shared__ uint8_t s_lut[512];
+    __shared__ uint16_t s_lut[256];                              // zero_state | one_state << 8
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < kDecSmemQuant; i += 32 * kDecWarps) s_quant[i] = T.quant[i];
-    for (int i = threadIdx.x; i < 512; i += 32 * kDecWarps) s_lut[i] = T.lut[i];
+    for (int i = threadIdx.x; i < 256; i += 32 * kDecWarps) s_lut[i] = (uint16_t)(T.lut[i] | (T.lut[256 + i] << 8));
     __syncthreads();
 
     const int chain = blockIdx.x * kDecWarps + warp;
