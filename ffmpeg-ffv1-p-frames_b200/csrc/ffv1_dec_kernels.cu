@@ -10,6 +10,8 @@
 //               into an int16 line ring (the reference's sample_buffer); after every line the whole warp converts
 //               the line (inverse RCT for RGB) and writes it to the output frame with coalesced stores.
 //   k_conceal   damaged slices are replaced by the co-located pixels of the previous frame (ffv1dec.c:998-1021).
+#include <cstdio>
+#include <cstdlib>
 #include "ffv1_dec_kernels.cuh"
 
 namespace ffv1 {
@@ -268,11 +270,208 @@ __device__ void dec_line(SliceRd &sr, uint8_t *model, const int16_t *q, const ui
     }
 }
 
+// ---- range-coder sample loop with the coder's working set in registers (same arithmetic as rd_get / rd_symbol).
+// What a slice decoder's speed hangs on is the dependent chain state -> interval split -> bit -> next state -> ... of one
+// lane.  Here only the interval arithmetic stays on that chain:
+//  * the 32 state bytes of the sample's context come in with two 128-bit loads; a symbol touches every byte at most once
+//    while its exponent is < 9 (bytes 1+e, 22+i, 11+e are distinct), so the decisions read them from registers and the
+//    successor states leave with byte stores that nothing waits for (larger exponents continue on the memory copy);
+//  * the successor pair lut[s] is fetched before the decision, the decoded bit only selects;
+//  * the bitstream comes through a 32-bit register window refilled from an aligned word loaded four renormalisations
+//    ahead;
+//  * the part of the next sample's context that does not depend on the sample being decoded (Q1, Q2, Q4) is looked up
+//    one sample ahead.
+struct FastRc {
+    uint32_t low, range;
+    uint32_t win, cnt;       // `cnt` unread bytes in the top of `win`
+    uint32_t nxt;            // the aligned word at p (big endian, bytes past the end zero)
+    const uint8_t *p, *end;
+};
+
+__device__ __forceinline__ uint32_t be32_masked(const uint8_t *p, const uint8_t *end)
+{
+    if (p >= end) return 0u;
+    uint32_t w = __byte_perm(*reinterpret_cast<const uint32_t *>(p), 0u, 0x0123);
+    const long left = end - p;
+    if (left < 4) w &= 0xFFFFFFFFu << (8 * (4 - (int)left));
+    return w;
+}
+
+__device__ __forceinline__ void fr_open(FastRc &c, const RDec &rc)
+{
+    const uint32_t m = (uint32_t)(reinterpret_cast<uintptr_t>(rc.ptr) & 3u);
+    const uint8_t *p0 = rc.ptr - m;                      // packets start 16-byte aligned in the staging buffer
+    c.low = rc.low; c.range = rc.range; c.end = rc.end;
+    c.win = be32_masked(p0, rc.end) << (8 * m);
+    c.cnt = 4 - m;
+    c.p = p0 + 4;
+    c.nxt = be32_masked(c.p, rc.end);
+}
+
+__device__ __forceinline__ void fr_close(const FastRc &c, RDec &rc)
+{
+    rc.low = c.low; rc.range = c.range; rc.ptr = c.p - c.cnt;
+}
+
+// the table reads are spelled as shared-memory loads from a 32-bit address (the tables never change while the kernel
+// runs, so the loads are pure)
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr)
+{
+    uint16_t v;
+    asm("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ int lds_s16(uint32_t addr)
+{
+    short v;
+    asm("ld.shared.s16 %0, [%1];" : "=h"(v) : "r"(addr));
+    return v;
+}
+
+__device__ __forceinline__ uint32_t fr_bit(FastRc &c, uint32_t s)
+{
+    const uint32_t range1 = (c.range * s) >> 8;
+    const uint32_t r0 = c.range - range1;
+    const bool bit = c.low >= r0;
+    if (bit) c.low -= r0;
+    c.range = bit ? range1 : r0;
+    if (c.range < 0x100u) {
+        c.range <<= 8;
+        c.low = (c.low << 8) | (c.win >> 24);
+        c.win <<= 8;
+        if (--c.cnt == 0) {
+            c.win = c.nxt; c.cnt = 4; c.p += 4;
+            c.nxt = be32_masked(c.p, c.end);
+        }
+    }
+    return bit;
+}
+
+__device__ __forceinline__ uint32_t fr_mem(FastRc &c, uint8_t *state, const uint16_t *lut)
+{
+    const uint32_t s = *state;
+    const uint32_t zz = lut[s];
+    const uint32_t bit = fr_bit(c, s);
+    *state = (uint8_t)(bit ? zz >> 8 : zz);
+    return bit;
+}
+
+#define FR_DECIDE(sv, rowptr)                                                            \
+    do {                                                                                 \
+        s = (sv);                                                                        \
+        zz = lds_u16(lut_sa + 2u * s);                                                   \
+        bit = fr_bit(c, s);                                                             \
+        *(rowptr) = (uint8_t)(bit ? zz >> 8 : zz);                                       \
+    } while (0)
+
+__device__ __forceinline__ int fr_symbol(FastRc &c, uint8_t *row, const uint16_t *lut, uint32_t lut_sa, int &err)
+{
+    const uint4 ra = *reinterpret_cast<const uint4 *>(row), rb = *reinterpret_cast<const uint4 *>(row + 16);
+    const uint32_t w[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+    uint32_t s, zz, bit;
+    FR_DECIDE(__byte_perm(w[0], 0u, 0x4440), row);
+    if (bit) return 0;
+    int e = 0;
+    bool open = true;
+#pragma unroll
+    for (int k = 0; k < 9; k++) {
+        FR_DECIDE(__byte_perm(w[(1 + k) >> 2], 0u, 0x4440 + ((1 + k) & 3)), row + 1 + k);
+        if (!bit) { open = false; break; }
+        e = k + 1;
+    }
+    if (open) {
+        while (fr_mem(c, row + 1 + min(e, 9), lut)) {
+            if (++e > 31) { err = 1; return 0; }
+        }
+        int a = 1;
+        for (int i = e - 1; i >= 0; i--) a += a + (int)fr_mem(c, row + 22 + min(i, 9), lut);
+        return fr_mem(c, row + 11 + min(e, 10), lut) ? -a : a;
+    }
+    const uint32_t sgw = e == 0 ? w[2] >> 24 : (e <= 4 ? w[3] : w[4]) >> (8 * ((e - 1) & 3));
+    unsigned long long mq = ((unsigned long long)__funnelshift_r(w[6], w[7], 16) << 32) | __funnelshift_r(w[5], w[6], 16);
+    mq <<= (8 * (8 - e)) & 63;
+    int a = 1;
+    for (int i = e - 1; i >= 0; i--) {
+        const uint32_t sv = (uint32_t)(mq >> 56);
+        mq <<= 8;
+        FR_DECIDE(sv, row + 22 + i);
+        a += a + (int)bit;
+    }
+    FR_DECIDE(sgw & 0xFFu, row + 11 + e);
+    return bit ? -a : a;
+}
+
+// decode_line for the range coder (ffv1dec.c:100-181 with ac != AC_GOLOMB_RICE)
+template <bool FIVE>
+__device__ __forceinline__ void dec_line_rc(SliceRd &sr, uint8_t *model, const int16_t *q, const uint16_t *lut, int16_t *cur,
+                                            const int16_t *top, const int16_t *top2, int w, int bits)
+{
+    FastRc c;
+    fr_open(c, sr.rc);
+    const int mask = (1 << bits) - 1;
+    int err = 0;
+    const uint32_t lut_sa = (uint32_t)__cvta_generic_to_shared(lut);
+    int L = cur[-1], LL = cur[-2], LT = top[-1], Tp = top[0], RT = top[1];
+    int qn = q[256 + ((LT - Tp) & 0xFF)] + q[512 + ((Tp - RT) & 0xFF)];
+    if (FIVE) qn += q[1024 + ((top2[0] - Tp) & 0xFF)];
+    for (int x = 0; x < w; x++) {
+        int ctx = q[(L - LT) & 0xFF] + qn;
+        if (FIVE) ctx += q[768 + ((LL - L) & 0xFF)];
+        const int RT2 = top[x + 2];                       // inside the row's padding at the right edge, not used there
+        qn = q[256 + ((Tp - RT) & 0xFF)] + q[512 + ((RT - RT2) & 0xFF)];
+        if (FIVE) qn += q[1024 + ((top2[x + 1] - RT) & 0xFF)];
+        const int pred = median3(L, Tp, L + Tp - LT);
+        const bool neg = ctx < 0;
+        int diff = fr_symbol(c, model + (size_t)abs(ctx) * 32, lut, lut_sa, err);
+        if (neg) diff = -diff;
+        const int v = (int)(int16_t)((pred + diff) & mask);                             // ffv1dec.c:178, int16 line buffer
+        cur[x] = (int16_t)v;
+        LL = L; L = v; LT = Tp; Tp = RT; RT = RT2;
+    }
+    sr.err |= err;
+    fr_close(c, sr.rc);
+}
+
+// ---- the common case (planar, range coder, three-table context, model and lines in shared memory): what one lane has to
+// do per sample is cut down to what depends on the sample decoded just before.  The warp prepares every line in parallel:
+// per x a record {T = top[x], q12 = Q1[LT-T] + Q2[T-RT]} from the finished line above; the serial lane reads one record,
+// adds Q0[L-LT], decodes, and stores the sample into the record; the warp then writes the line out and turns `cur` into
+// the next line's `top`.
+struct __align__(8) LineRec { int16_t top, q12, cur, pad; };
+
+__device__ __forceinline__ void dec_line_rec(SliceRd &sr, uint8_t *model, const int16_t *q, const uint16_t *lut, LineRec *rec,
+                                             int w, int bits, int topm1)
+{
+    FastRc c;
+    fr_open(c, sr.rc);
+    const int mask = (1 << bits) - 1;
+    int err = 0;
+    const uint32_t lut_sa = (uint32_t)__cvta_generic_to_shared(lut), q_sa = (uint32_t)__cvta_generic_to_shared(q);
+    int L = rec[0].top, LT = topm1;                      // sample[1][-1] = sample[0][0] (ffv1dec.c:199)
+    LineRec *r = rec, *const rend = rec + w;
+    do {
+        const int Tp = r->top, q12 = r->q12;
+        const int d = L - LT;
+        const int ctx = lds_s16(q_sa + 2u * (uint32_t)(d & 0xFF)) + q12;
+        const int pred = median3(L, Tp, d + Tp);
+        int diff = fr_symbol(c, model + (size_t)abs(ctx) * 32, lut, lut_sa, err);
+        if (ctx < 0) diff = -diff;
+        L = (int)(int16_t)((pred + diff) & mask);
+        r->cur = (int16_t)L;
+        LT = Tp;
+        r++;
+    } while (r != rend);
+    sr.err |= err;
+    fr_close(c, sr.rc);
+}
+
 constexpr int kDecSmemQuant = 2 * 5 * 256;
 
 constexpr int kDecWarps = 2;               // chains per CTA (they share the quantisation / transition tables)
 
-__global__ void __launch_bounds__(32 * kDecWarps) k_decode(const DecDeviceTables T, const DecBatch B)
+// MINB = resident CTAs per SM the register allocation aims at (8: no spills; 12: for batches with more chains than 8 CTAs hold)
+template <int MINB>
+__global__ void __launch_bounds__(32 * kDecWarps, MINB) k_decode(const DecDeviceTables T, const DecBatch B)
 {
     extern __shared__ __align__(16) unsigned char s_dyn[];      // per warp: [model of the current plane context][line ring]
     __shared__ int16_t s_quant[kDecSmemQuant];
@@ -284,7 +483,7 @@ __global__ void __launch_bounds__(32 * kDecWarps) k_decode(const DecDeviceTables
 
     const int chain = blockIdx.x * kDecWarps + warp;
     if (chain >= B.nseg * T.max_slices) return;
-    const int per_warp = T.smem_model + T.smem_ring_w * 3 * 2;
+    const int per_warp = T.smem_model + T.smem_ring_w * kDecSmemRingBytes;
     uint8_t *s_model = s_dyn + (size_t)warp * per_warp;
     int16_t *s_ring = reinterpret_cast<int16_t *>(s_model + T.smem_model);
     const int seg = chain / T.max_slices, si = chain - seg * T.max_slices;
@@ -296,6 +495,10 @@ __global__ void __launch_bounds__(32 * kDecWarps) k_decode(const DecDeviceTables
     const int nplanes = T.colorspace ? 3 + T.transparency : (T.ya8 ? 2 : 1 + 2 * T.chroma_planes + T.transparency);
 
     int sm_pc = -1, sm_nb = 0;             // plane context whose model is in shared memory, its size in 16-byte units
+#ifdef FFV1_DEC_PROBE
+    long long probe_serial = 0, probe_samples = 0;
+    const long long probe_t0 = clock64();
+#endif
     for (int f = f0; f < f1; f++) {
         if (si >= B.slice_count[f]) continue;
         const int fs = f * T.max_slices + si;
@@ -395,9 +598,12 @@ __global__ void __launch_bounds__(32 * kDecWarps) k_decode(const DecDeviceTables
                 const int16_t *q = s_quant + qti[pc < T.plane_count ? pc : 0] * 5 * 256;
                 uint8_t *model = models + (size_t)pc * T.state_stride;
                 // the plane context's model moves to shared memory while its planes are decoded (U and V share one)
-                if (T.smem_model) {
+                // (the slice header picks the quantisation table set per plane: only a set whose model fits is moved)
+                const int model_nb = (T.ctx_count[qti[pc < T.plane_count ? pc : 0]] * (golomb ? 8 : 32) + 15) >> 4;
+                const bool model_sm = T.smem_model && model_nb * 16 <= T.smem_model;
+                if (model_sm) {
                     if (pc != sm_pc) {
-                        const int nb = (T.ctx_count[qti[pc < T.plane_count ? pc : 0]] * (golomb ? 8 : 32) + 15) >> 4;
+                        const int nb = model_nb;
                         if (sm_pc >= 0) {
                             uint4 *dst = reinterpret_cast<uint4 *>(models + (size_t)sm_pc * T.state_stride);
                             for (int i = lane; i < sm_nb; i += 32) dst[i] = reinterpret_cast<const uint4 *>(s_model)[i];
@@ -411,6 +617,50 @@ __global__ void __launch_bounds__(32 * kDecWarps) k_decode(const DecDeviceTables
                 }
                 const bool ring_sm = T.smem_ring_w && w + 2 * kDecRingPad <= T.smem_ring_w;
                 const int rw = ring_sm ? T.smem_ring_w : T.ring_w;
+                if (!golomb && ring_sm && !q[3 * 256 + 127]) {
+                    LineRec *rec = reinterpret_cast<LineRec *>(s_ring);
+                    for (int x = lane; x < w; x += 32) rec[x] = LineRec{0, 0, 0, 0};
+                    __syncwarp();
+                    int topm1 = 0;                                                       // top[-1] of the line being decoded
+                    for (int y = 0; y < h; y++) {
+                        const int cm1 = rec[0].top;
+                        for (int x = lane; x < w; x += 32) {
+                            const int Tp = rec[x].top, LTv = x ? rec[x - 1].top : topm1, RTv = x + 1 < w ? rec[x + 1].top : Tp;
+                            rec[x].q12 = (int16_t)(q[256 + ((LTv - Tp) & 0xFF)] + q[512 + ((Tp - RTv) & 0xFF)]);
+                        }
+                        __syncwarp();
+#ifdef FFV1_DEC_PROBE
+                        const long long pt0 = clock64();
+#endif
+                        if (lane == 0) {
+                            if (model_sm) dec_line_rec(sr, s_model, q, s_lut, rec, w, bits, topm1);
+                            else dec_line_rec(sr, model, q, s_lut, rec, w, bits, topm1);
+                        }
+#ifdef FFV1_DEC_PROBE
+                        probe_serial += clock64() - pt0; probe_samples += w;
+#endif
+                        topm1 = cm1;                                                     // the next line's top[-1] is this line's cur[-1]
+                        __syncwarp();
+                        uint8_t *dst = frame + T.plane_off[src] + (size_t)(py0 + y) * T.plane_pitch[src];
+                        if (T.bits <= 8) {
+                            for (int x = lane; x < w; x += 32) {
+                                const int16_t v = rec[x].cur;
+                                dst[(px0 + x) * pstep + poff] = (uint8_t)v;
+                                rec[x].top = v;
+                            }
+                        } else {
+                            const int shl = T.packed_at_lsb ? 0 : 16 - T.bits;          // ffv1dec.c:211-219
+                            uint16_t *d16 = reinterpret_cast<uint16_t *>(dst) + px0;
+                            for (int x = lane; x < w; x += 32) {
+                                const int16_t v = rec[x].cur;
+                                d16[x] = (uint16_t)((uint16_t)v << shl);
+                                rec[x].top = v;
+                            }
+                        }
+                        __syncwarp();
+                    }
+                    continue;
+                }
                 int16_t *rows = ring_sm ? s_ring + kDecRingPad : ring;                    // plane slot 0: three rows
                 for (int i = lane - kDecRingPad; i < 3 * rw - kDecRingPad; i += 32) rows[i] = 0;
                 __syncwarp();
@@ -422,7 +672,19 @@ __global__ void __launch_bounds__(32 * kDecWarps) k_decode(const DecDeviceTables
                     if (lane == 0) {
                         cur[-1] = top[0];                 // ffv1dec.c:199-200
                         top[w] = top[w - 1];
-                        dec_line(sr, model, q, s_lut, cur, top, top2, w, bits);
+                        if (golomb)
+                            dec_line(sr, model, q, s_lut, cur, top, top2, w, bits);
+                        else if (model_sm && ring_sm) {
+                            // the common case, spelled out on the shared-memory arrays so that the loads are LDS
+                            int16_t *r0 = s_ring + kDecRingPad;
+                            int16_t *c1 = r0 + (y % 3) * T.smem_ring_w;
+                            const int16_t *t1 = r0 + ((y + 2) % 3) * T.smem_ring_w, *t2 = r0 + ((y + 1) % 3) * T.smem_ring_w;
+                            if (q[3 * 256 + 127]) dec_line_rc<true>(sr, s_model, q, s_lut, c1, t1, t2, w, bits);
+                            else dec_line_rc<false>(sr, s_model, q, s_lut, c1, t1, t2, w, bits);
+                        } else if (q[3 * 256 + 127])
+                            dec_line_rc<true>(sr, model, q, s_lut, cur, top, top2, w, bits);
+                        else
+                            dec_line_rc<false>(sr, model, q, s_lut, cur, top, top2, w, bits);
                     }
                     __syncwarp();
                     uint8_t *dst = frame + T.plane_off[src] + (size_t)(py0 + y) * T.plane_pitch[src];
@@ -460,8 +722,11 @@ __global__ void __launch_bounds__(32 * kDecWarps) k_decode(const DecDeviceTables
                         const int pc = (p + 1) / 2;
                         cur[-1] = top[0];
                         top[sw] = top[sw - 1];
-                        dec_line(sr, models + (size_t)pc * T.state_stride, s_quant + qti[pc < T.plane_count ? pc : 0] * 5 * 256, s_lut,
-                                 cur, top, top2, sw, bits);
+                        uint8_t *model = models + (size_t)pc * T.state_stride;
+                        const int16_t *q = s_quant + qti[pc < T.plane_count ? pc : 0] * 5 * 256;
+                        if (golomb) dec_line(sr, model, q, s_lut, cur, top, top2, sw, bits);
+                        else if (q[3 * 256 + 127]) dec_line_rc<true>(sr, model, q, s_lut, cur, top, top2, sw, bits);
+                        else dec_line_rc<false>(sr, model, q, s_lut, cur, top, top2, sw, bits);
                     }
                 }
                 __syncwarp();
@@ -498,15 +763,48 @@ __global__ void __launch_bounds__(32 * kDecWarps) k_decode(const DecDeviceTables
         }
         __syncwarp();
     }
+#ifdef FFV1_DEC_PROBE
+    if (lane == 0 && (chain == 0 || chain == 101))
+        printf("chain %d: %lld samples, serial %lld cycles (%.1f per sample), total %lld cycles\n", chain, probe_samples, probe_serial,
+               (double)probe_serial / (double)max(probe_samples, 1ll), clock64() - probe_t0);
+#endif
 }
 
-void launch_decode(const DecDeviceTables &t, const DecBatch &b, cudaStream_t s)
+void launch_decode(const DecDeviceTables &t_in, const DecBatch &b, cudaStream_t s)
 {
+    DecDeviceTables t = t_in;
+    {
+        const char *e = getenv("FFV1B200_DEC_SMEM");
+        if (e && atoi(e) == 0) t.smem_model = 0;
+    }
     const int chains = b.nseg * t.max_slices;
-    const int smem = kDecWarps * (t.smem_model + t.smem_ring_w * 3 * 2);
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(k_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (24 * 1024 + 8 * 1024)); attr = true; }
-    k_decode<<<(chains + kDecWarps - 1) / kDecWarps, 32 * kDecWarps, smem, s>>>(t, b);
+    // Models in shared memory cap the chains an SM holds (a 21 KB model per chain); a batch with more chains than that
+    // runs faster with the models in global memory and twice the warps per scheduler to hide its latency.
+    static int nsm = -1;
+    if (nsm < 0) {
+        cudaFuncSetAttribute(k_decode<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDecWarps * (24 * 1024 + 11 * 1024));
+        cudaFuncSetAttribute(k_decode<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDecWarps * (24 * 1024 + 11 * 1024));
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    }
+    if (t.smem_model) {
+        int nb = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_decode<8>, 32 * kDecWarps, kDecWarps * (t.smem_model + t.smem_ring_w * kDecSmemRingBytes));
+        if (chains > nb * nsm * kDecWarps) t.smem_model = 0;
+    }
+    const int smem = kDecWarps * (t.smem_model + t.smem_ring_w * kDecSmemRingBytes);
+    const int grid = (chains + kDecWarps - 1) / kDecWarps;
+    // more chains than the spill-free register allocation keeps resident, but few enough for the 80-register one to
+    // hold in a single wave: take that one (2048 frames of 1080p: 1421 instead of 1239 frames/s)
+    int nb8 = 0, nb12 = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb8, k_decode<8>, 32 * kDecWarps, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb12, k_decode<12>, 32 * kDecWarps, smem);
+    const char *ev = getenv("FFV1B200_DEC_MINB");
+    const bool dense = ev ? atoi(ev) > 8 : (grid > nb8 * nsm && grid <= nb12 * nsm);
+    if (getenv("FFV1B200_DEBUG")) fprintf(stderr, "k_decode<%d>: grid %d, %d B dynamic smem\n", dense ? 12 : 8, grid, smem);
+    if (dense) k_decode<12><<<grid, 32 * kDecWarps, smem, s>>>(t, b);
+    else k_decode<8><<<grid, 32 * kDecWarps, smem, s>>>(t, b);
 }
 
 // ------------------------------------------------------------------------------------------------ concealment

@@ -5,6 +5,7 @@
 
 namespace ffv1 {
 
+constexpr int kDecSmemRingBytes = 8;     // shared-memory bytes per ring sample: three int16 rows, or one 8-byte line record
 constexpr int kDecRingPad = 8;          // int16 elements kept left of x = 0 in a ring row (positions -1, -2 are used)
 
 struct DecDeviceTables {

@@ -69,11 +69,17 @@ static int configure(FFV1B200Decoder *d)
     // planar YUV: the model of the plane context being decoded (<= 24 KB: small context model, or Golomb-Rice states)
     // and the three-row line ring of a regular slice live in shared memory
     {
-        const int64_t model = (int64_t)maxctx * (c.ac == AC_GOLOMB ? 8 : 32);
-        t.smem_model = (!c.colorspace && model <= 24 * 1024) ? (int32_t)((model + 15) & ~15) : 0;
+        // version 3 carries both quantisation table sets and every slice header picks one per plane: room for the
+        // largest set that fits (a plane coded with a larger one keeps its model in global memory)
+        int64_t model = 0;
+        for (int i = 0; i < 2; i++) {
+            const int64_t m = (int64_t)c.context_count[i] * (c.ac == AC_GOLOMB ? 8 : 32);
+            if (m <= 24 * 1024 && m > model) model = m;
+        }
+        t.smem_model = (!c.colorspace && model > 0) ? (int32_t)((model + 15) & ~15) : 0;
         const int sw = (c.width + c.num_h_slices - 1) / c.num_h_slices + 1;
         const int rw = ((sw + 2 * kDecRingPad + 31) / 32) * 32;
-        t.smem_ring_w = (!c.colorspace && rw * 3 * 2 <= 8 * 1024) ? rw : 0;
+        t.smem_ring_w = (!c.colorspace && rw * kDecSmemRingBytes <= 11 * 1024) ? rw : 0;
     }
 
     CU_TRY(d->d_quant.upload(&c.quant_tables[0][0][0], 2 * 5 * 256, d->stream));
