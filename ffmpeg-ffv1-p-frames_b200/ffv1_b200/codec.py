@@ -317,14 +317,17 @@ class FFV1Decoder:
         self.width, self.height = width, height
         self.max_batch = max_batch_frames
 
-    def decode_batch(self, packets):
-        """packets: list of bytes. Returns [(uint8 frame array, key_frame, damaged_slice_mask)]."""
-        out = []
+    def decode_batch(self, packets, out=None):
+        """packets: list of bytes. Returns [(uint8 frame array, key_frame, damaged_slice_mask)].
+        out: optional uint8 array (e.g. pinned host memory) of len(packets) * frame_bytes the frames are written to."""
+        res = []
+        fb = int(self.info.frame_bytes)
         for i in range(0, len(packets), self.max_batch):
-            out += self._decode_chunk(packets[i:i + self.max_batch])
-        return out
+            o = out[i * fb:(i + self.max_batch) * fb] if (out is not None and fb) else None
+            res += self._decode_chunk(packets[i:i + self.max_batch], o)
+        return res
 
-    def _decode_chunk(self, packets):
+    def _decode_chunk(self, packets, out=None):
         n = len(packets)
         bufs = [np.frombuffer(p, np.uint8) for p in packets]
         ptrs = (ctypes.c_void_p * n)(*[b.ctypes.data for b in bufs])
@@ -338,7 +341,10 @@ class FFV1Decoder:
             _check(lib().ffv1b200_dec_info(self._h, ctypes.byref(self.info)))
             self.pix_fmt = self.info.pix_fmt.decode()
         fb = int(self.info.frame_bytes)
-        out = np.empty(n * fb, np.uint8)
+        if out is None:
+            out = np.empty(n * fb, np.uint8)
+        elif out.nbytes < n * fb or out.dtype != np.uint8:
+            raise FFV1Error(ERR_BUFFER_TOO_SMALL, "output array too small")
         keys = (ctypes.c_int * n)()
         dmg = (ctypes.c_uint64 * n)()
         _check(lib().ffv1b200_dec_decode_host(self._h, n, ptrs, sizes, out.ctypes.data, out.nbytes, keys, dmg))

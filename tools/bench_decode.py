@@ -23,17 +23,27 @@ def run(n=256, batch=None):
     out = dec.decode_batch(pkts)            # warm-up (+ correctness)
     for i in (0, 1, n // 2, n - 1):
         assert np.array_equal(out[i][0], frames[i]), "frame %d does not round-trip" % i
+    host_out, pinned = None, False
+    try:                                    # frames land in pinned host memory, like the frames of the encoder's e2e leg
+        import torch
+        host_out = torch.empty(n * ffv1_b200.frame_bytes(FMT, W, H), dtype=torch.uint8, pin_memory=True).numpy()
+        pinned = True
+    except Exception:
+        pass
     t0 = time.perf_counter()
-    out = dec.decode_batch(pkts)
+    out = dec.decode_batch(pkts, out=host_out)
     dt = time.perf_counter() - t0
+    for i in (0, n - 1):
+        assert np.array_equal(out[i][0], frames[i]), "frame %d does not round-trip" % i
     s = dec.stats()
     st = {k: getattr(s, k) for k, _ in s._fields_}
     dec.close()
     # two decode_batch calls were made (warm-up + timed): the kernel time in the statistics covers both
     return {"value": n / dt, "unit": "frames/s", "frames": n, "batch": batch, "round_trip": "bit-exact",
             "kernel_fps": 2 * n / (st["ms_decode_kernel"] * 1e-3) if st.get("ms_decode_kernel") else None,
-            "note": "ffv1b200_dec_decode_host: host packets in, host frames out (pageable numpy buffers), copies included; "
-                    "k_decode = one warp per (GOP, slice) chain, serial inside a slice like decode_line"}
+            "note": "ffv1b200_dec_decode_host: host packets in, host frames out (%s), copies included; "
+                    "k_decode = one warp per (GOP, slice) chain, serial inside a slice like decode_line"
+                    % ("pinned host memory" if pinned else "pageable numpy buffers")}
 
 if __name__ == "__main__":
     print(json.dumps(run(int(sys.argv[1]) if len(sys.argv) > 1 else 256, int(sys.argv[2]) if len(sys.argv) > 2 else None)))
