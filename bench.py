@@ -322,7 +322,7 @@ def main():
                 import bench_decode
                 del frames_dev, out_dev
                 torch.cuda.empty_cache()
-                line["decode"] = bench_decode.run(512, 512)
+                line["decode"] = bench_decode.run(512, 512, 1, 0 if args.no_cpu_baseline else 33)
             except Exception as ex:
                 line["decode"] = {"value": None, "note": repr(ex)}
         print(json.dumps(line))
