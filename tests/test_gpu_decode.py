@@ -97,3 +97,23 @@ def test_non_keyframe_first_is_refused(B):
     with pytest.raises(B.FFV1Error) as e:
         d.decode(pkts[1])
     assert e.value.code == -1094995529      # AVERROR_INVALIDDATA (ffv1dec.c:930-935)
+
+@pytest.mark.parametrize("env", [{"FFV1B200_DEC_SMEM": "0"}, {"FFV1B200_DEC_MINB": "12"},
+                                 {"FFV1B200_DEC_SMEM": "0", "FFV1B200_DEC_MINB": "12"}],
+                         ids=["models_global", "dense_regs", "models_global_dense_regs"])
+def test_large_batch_kernel_variants(B, env, monkeypatch):
+    """launch_decode switches model placement (shared -> global memory) and the register allocation with the number of
+    chains in the batch; the variants only big batches reach are forced here and must decode the same bytes"""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    for cid in ("c2_gop_range_24sl", "c1_cif_intra", "c3_422p10_ctx1", "fate_ffv1_golomb", "fate_v3_444p16", "yuva420p", "gray16", "v0_range"):
+        sel = [c for c in CASES if c[0] == cid]
+        if not sel:
+            continue
+        case = sel[0]
+        _, w, h, fmt, opts, kind, n = case
+        frames, extradata, pkts, ref = oracle_stream(case)
+        got = B.FFV1Decoder(w, h, extradata, max_batch_frames=len(pkts)).decode_batch(pkts)
+        for i in range(len(pkts)):
+            assert got[i][2] == 0
+            assert np.array_equal(got[i][0], ref[i][0]), "%s: frame %d differs (%s)" % (cid, i, env)
