@@ -271,8 +271,8 @@ __device__ void dec_line(SliceRd &sr, uint8_t *model, const int16_t *q, const ui
 }
 
 // ---- range-coder sample loop with the coder's working set in registers (same arithmetic as rd_get / rd_symbol).
-// What a slice decoder's speed hangs on is the dependent chain state -> interval split -> bit -> next state -> ... of one
-// lane.  Here only the interval arithmetic stays on that chain:
+// A chain's speed is the number of instructions its one serial lane issues per sample (a lone warp pays ~4.5 cycles per
+// issued instruction, profiles/r01_k_decode_probe.txt), so the reader is built to issue few:
 //  * the 32 state bytes of the sample's context come in with two 128-bit loads; a symbol touches every byte at most once
 //    while its exponent is < 9 (bytes 1+e, 22+i, 11+e are distinct), so the decisions read them from registers and the
 //    successor states leave with byte stores that nothing waits for (larger exponents continue on the memory copy);
