@@ -410,7 +410,8 @@ __device__ __forceinline__ void dec_line_rc(SliceRd &sr, uint8_t *model, const i
     fr_open(c, sr.rc);
     const int mask = (1 << bits) - 1;
     int err = 0;
-    const uint32_t lut_sa = (uint32_t)__cvta_generic_to_shared(lut);
+    uint32_t lut_sa = (uint32_t)__cvta_generic_to_shared(lut);
+    asm volatile("" : "+r"(lut_sa));
     int L = cur[-1], LL = cur[-2], LT = top[-1], Tp = top[0], RT = top[1];
     int qn = q[256 + ((LT - Tp) & 0xFF)] + q[512 + ((Tp - RT) & 0xFF)];
     if (FIVE) qn += q[1024 + ((top2[0] - Tp) & 0xFF)];
@@ -446,7 +447,8 @@ __device__ __forceinline__ void dec_line_rec(SliceRd &sr, uint8_t *model, const 
     fr_open(c, sr.rc);
     const int mask = (1 << bits) - 1;
     int err = 0;
-    const uint32_t lut_sa = (uint32_t)__cvta_generic_to_shared(lut), q_sa = (uint32_t)__cvta_generic_to_shared(q);
+    uint32_t lut_sa = (uint32_t)__cvta_generic_to_shared(lut), q_sa = (uint32_t)__cvta_generic_to_shared(q);
+    asm volatile("" : "+r"(lut_sa), "+r"(q_sa));         // keep them in registers (otherwise re-derived from %cluster_ctarank per sample)
     int L = rec[0].top, LT = topm1;                      // sample[1][-1] = sample[0][0] (ffv1dec.c:199)
     LineRec *r = rec, *const rend = rec + w;
     do {
