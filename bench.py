@@ -168,7 +168,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=1024, help="frames per step per GPU (multiple of the GOP size)")
+    ap.add_argument("--batch", type=int, default=2048, help="frames per step per GPU (multiple of the GOP size)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--ref-frames", type=int, default=32, help="--impl reference: frames per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")

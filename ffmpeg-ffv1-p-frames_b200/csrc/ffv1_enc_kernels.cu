@@ -620,8 +620,10 @@ constexpr int kRangeThreads = 32;
 constexpr int kRangeChunk = 8;            // 16-byte decision vectors per chunk (one 128-byte line per lane)
 constexpr int kRangeDepth = 4;            // chunk slots per lane (power of two): kRangeDepth-1 chunks in flight
 
-__global__ void __launch_bounds__(kRangeThreads) k_rangecode(const EncDeviceTables T, const EncBatch B, const int lanes)
+template <int LANES>        // coders per warp known at compile time (16: the common case, immediate strides) or 0 = `lanes_rt`
+__global__ void __launch_bounds__(kRangeThreads) k_rangecode(const EncDeviceTables T, const EncBatch B, const int lanes_rt)
 {
+    const int lanes = LANES ? LANES : lanes_rt;
     const Layout &L = T.layout;
     if ((int)threadIdx.x >= lanes) return;
     const int idx = blockIdx.x * lanes + threadIdx.x;
@@ -633,8 +635,11 @@ __global__ void __launch_bounds__(kRangeThreads) k_rangecode(const EncDeviceTabl
     const int key = B.frame_key[f] ? 1 : 0;
     const int nruns = g.nruns;
 
-    __shared__ __align__(32) uint8_t s_ring[kRangeThreads * 32];
-    __shared__ __align__(16) uint4 s_vec[kRangeDepth * kRangeChunk * kRangeThreads];   // [chunk slot][vector][lane]
+    // sized by the lanes in use (544 bytes per coder), so that half-filled warps do not halve the warps an SM holds
+    extern __shared__ __align__(32) uint8_t s_range_dyn[];
+    uint4 *s_vec = reinterpret_cast<uint4 *>(s_range_dyn);                              // [chunk slot][vector][lane]
+    uint8_t *s_ring = s_range_dyn + (size_t)kRangeDepth * kRangeChunk * lanes * 16;      // [lane][32]
+    const uint32_t vstride = (uint32_t)lanes * 16u, cstride = (uint32_t)kRangeChunk * vstride;
     Rac c;
     c.low = 0; c.range = 0xFF00u; c.out_byte = 0; c.out_count = 0; c.thr = 0xFEu;   // ff_init_range_encoder (+ dummy outstanding byte)
     c.out = B.scratch + (size_t)f * L.scratch_per_frame + g.scratch_off;
@@ -684,10 +689,10 @@ __global__ void __launch_bounds__(kRangeThreads) k_rangecode(const EncDeviceTabl
         }
         if (gen.rem) {
             const uint32_t nv = min(gen.rem, (uint32_t)kRangeChunk);
-            const uint32_t dst = vec_base + slot * (kRangeChunk * kRangeThreads * 16u);
+            const uint32_t dst = vec_base + slot * cstride;
 #pragma unroll
             for (uint32_t j = 0; j < (uint32_t)kRangeChunk; j++)
-                if (j < nv) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst + j * (kRangeThreads * 16u)), "l"(gen.ptr + j) : "memory");
+                if (j < nv) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst + j * vstride), "l"(gen.ptr + j) : "memory");
             gen.ptr += nv;
             gen.rem -= nv;
             desc = nv | (gen.rem ? 8u : gen.last_valid) << 4;
@@ -707,14 +712,14 @@ __global__ void __launch_bounds__(kRangeThreads) k_rangecode(const EncDeviceTabl
         if (nv == 0u) break;
         dq = (dq >> 8) | fetch((slot + kRangeDepth - 1) & (kRangeDepth - 1)) << (8 * (kRangeDepth - 2));
         asm volatile("cp.async.wait_group %0;" :: "n"(kRangeDepth - 1) : "memory");
-        uint32_t at = vec_base + slot * (kRangeChunk * kRangeThreads * 16u);
+        uint32_t at = vec_base + slot * cstride;
         slot = (slot + 1u) & (kRangeDepth - 1);
         uint4 v;
         asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(at) : "memory");
 #pragma unroll 1
         for (uint32_t j = nv; j; j--) {
             uint4 cur = v;
-            at += kRangeThreads * 16u;
+            at += vstride;
             // the next vector of the chunk is read while this one is coded (the chunk has landed as a whole)
             if (j > 1u) asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(at) : "memory");
             if (j == 1u && last_valid < 8u) {                     // end of a run: what follows in the vector is not ours
@@ -754,9 +759,19 @@ void launch_rangecode(const EncDeviceTables &t, const EncBatch &b, cudaStream_t 
     int lanes = forced;
     if (!lanes) {                                  // the coders are bound by latency: ~10 warps per SM before warps are filled up
         lanes = 4;
-        while (lanes < 32 && n / lanes > 148 * 12) lanes *= 2;
+        while (lanes < 16 && n / lanes > 148 * 12) lanes *= 2;
+        if (n / lanes > 148 * 26) lanes = 32;      // 16 coders per warp (the measured optimum) as long as the warps stay resident
     }
-    k_rangecode<<<(n + lanes - 1) / lanes, kRangeThreads, 0, s>>>(t, b, lanes);
+    static bool attr = false;
+    if (!attr) {                                    // 26 resident warps of 8.7 KB need the large shared-memory carveout
+        cudaFuncSetAttribute(k_rangecode<16>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(k_rangecode<0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        attr = true;
+    }
+    const int smem = lanes * (32 + kRangeDepth * kRangeChunk * 16);
+    if (getenv("FFV1B200_DEBUG")) fprintf(stderr, "k_rangecode: %d coders, %d lanes\n", n, lanes);
+    if (lanes == 16) k_rangecode<16><<<(n + lanes - 1) / lanes, kRangeThreads, smem, s>>>(t, b, lanes);
+    else k_rangecode<0><<<(n + lanes - 1) / lanes, kRangeThreads, smem, s>>>(t, b, lanes);
 }
 
 // =================================================================================================
