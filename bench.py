@@ -5,14 +5,20 @@ HBM GB/s").
   python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B]        our arm (CUDA kernels via the C ABI)
   python bench.py --impl reference ...                                     the reference's own CPU encoder (oracle/_ref)
   torchrun --nproc-per-node N ... bench.py --gpus N ...                    one rank per GPU, GOP-aligned frame ranges
+  python bench.py --frames-total 2400 [--gpus N]                           BASELINE configs[4]: a fixed 2400-frame job,
+                                                                           GOP-partitioned over the GPUs, encode + decode
 
-Workload (BASELINE.json configs[1]): 1920x1080 yuv420p 8-bit synthetic "camera noise" clip, FFV1 level 3, GOP 16
-(state-carry-over non-keyframes = the reference's P-frames), coder=1 (range coder, custom table), context=0,
-24 slices, slice CRCs.  A step = one batch of B frames per GPU through the whole encode path (per-pixel pass, state
-replay, range coder, packet assembly).  value = frames/s with frames resident in HBM; e2e = the same through the
-host-buffer C-ABI call (pinned host frames in, packets out to host memory, copies inside the timed region).
+Workload (BASELINE.json configs[1]): 1920x1080 yuv420p 8-bit synthetic "camera noise" clip S2 (32 frames,
+numpy seed 1234, tiled in time; with GOP 16 every 32-frame period codes to the same packets), FFV1 level 3, GOP 16
+(state-carry-over non-keyframes = the reference's P-frames), coder=1 (range coder, custom table), context=0, 24 slices,
+slice CRCs.  BOTH arms encode these bytes.  A step = one batch of B frames per GPU through the whole encode path
+(per-pixel pass, state replay, range coder, packet assembly).  value = frames/s with frames resident in HBM; e2e = the
+same through the host-buffer C-ABI calls (pinned host frames in, packets out to host memory, copies inside the timed
+region).  After the timed loops the packets of the LAST batch of each leg are compared (size + MD5) with the reference
+build's own packets (tests/golden/ref_packets.json, written by tests/golden/make_golden.py from oracle/_ref): the line
+carries "parity_checked".
 """
-import argparse, json, os, statistics, subprocess, sys, threading, time
+import argparse, ctypes, hashlib, json, os, statistics, subprocess, sys, threading, time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -21,6 +27,7 @@ sys.path.insert(0, os.path.join(ROOT, "ffmpeg-ffv1-p-frames_b200"))
 W, H, FMT = 1920, 1080, "yuv420p"
 OPTS = dict(level=3, coder=1, context=0, slices=24)
 GOP = 16
+CLIP = 32                          # frames of the S2 clip (two GOPs); frame i of any stream = clip frame i % 32
 FRAME_BYTES = W * H * 3 // 2
 SAMPLES = W * H * 3 // 2
 ALGO_BYTES_PER_SAMPLE = 5          # 1 B read + 4 B (context,diff) record written
@@ -30,6 +37,16 @@ ALGO_BYTES_PER_SAMPLE = 5          # 1 B read + 4 B (context,diff) record writte
 TRAFFIC_BYTES_PER_FRAME = (6014702000 + 12686427000) / 1024
 METRIC = "1080p yuv420p8 FFV1 level-3 GOP-16 encode throughput (bit-exact)"
 WORKLOAD = "1080p yuv420p8 synthetic noise clip, FFV1 level 3, GOP 16 (P-frames), coder=1, context=0, 24 slices, slicecrc"
+GOLDEN = os.path.join(ROOT, "tests", "golden", "ref_packets.json")
+
+
+def config_dict():
+    """identical for both arms: it names the workload, nothing about how an arm runs it"""
+    return {"workload": WORKLOAD,
+            "clip": "S2 noisy1080 (SURVEY.md 8(d)): numpy default_rng(1234), %d frames, tiled in time" % CLIP,
+            "l2_policy": "a step's input (>= 99.5 MB per 32 frames, 6.4 GB at the default batch) and intermediates are far "
+                         "larger than the 126 MB L2: no flush needed",
+            "parallelism": "GOP-aligned frame ranges per GPU, no collective"}
 
 
 def measured_peak():
@@ -38,6 +55,41 @@ def measured_peak():
             return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def s2_clip(nframes=CLIP, seed=1234):
+    """S2 'noisy1080' exactly as SURVEY.md 8(d) states it (draw order Y, U, V per frame); [nframes, FRAME_BYTES] uint8"""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:H, 0:W]
+    cx, cy = xx[::2, ::2], yy[::2, ::2]
+    out = np.empty((nframes, FRAME_BYTES), np.uint8)
+    for n in range(nframes):
+        Y = np.clip(((0.1 * xx + 0.07 * yy + 1.5 * n) % 256) + rng.normal(0, 2, (H, W)), 0, 255).astype(np.uint8)
+        U = np.clip(128 + 20 * np.sin((cx + 3 * n) / 97) + rng.normal(0, 1.5, cx.shape), 0, 255).astype(np.uint8)
+        V = np.clip(128 + 20 * np.cos((cy + 2 * n) / 71) + rng.normal(0, 1.5, cy.shape), 0, 255).astype(np.uint8)
+        out[n, :W * H] = Y.ravel()
+        out[n, W * H:W * H + W * H // 4] = U.ravel()
+        out[n, W * H + W * H // 4:] = V.ravel()
+    return out
+
+
+def golden():
+    with open(GOLDEN) as fh:
+        return json.load(fh)["s2_noisy1080_c2"]
+
+
+def check_packets(gold, clip_ok, get_packet, indices, first_frame=0):
+    """size, MD5 and key flag of the given packets against the reference build's (frame i <-> golden packet i % 32)"""
+    if not clip_ok or OPTS != dict(level=3, coder=1, context=0, slices=24):
+        return None
+    for i in indices:
+        data, key = get_packet(i)
+        exp = gold["packets"][(first_frame + i) % CLIP]
+        got = [len(data), hashlib.md5(data).hexdigest(), int(key)]
+        if got != exp:
+            raise SystemExit("PARITY FAILURE: packet %d is %r, the reference encoder gives %r" % (i, got, exp))
+    return len(indices)
 
 
 class ClockSampler:
@@ -82,100 +134,74 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def synth_frames_torch(torch, nframes, device, seed):
-    """S2 'noisy1080'-style frames (ramps + gaussian noise) generated on the GPU, tightly packed yuv420p"""
-    g = torch.Generator(device=device)
-    g.manual_seed(seed)
-    out = torch.empty((nframes, FRAME_BYTES), dtype=torch.uint8, device=device)
-    yy, xx = torch.meshgrid(torch.arange(H, device=device, dtype=torch.float32), torch.arange(W, device=device, dtype=torch.float32), indexing="ij")
-    cx, cy = xx[::2, ::2], yy[::2, ::2]
-    for n in range(nframes):
-        Y = ((0.1 * xx + 0.07 * yy + 1.5 * n) % 256) + 2.0 * torch.randn((H, W), device=device, generator=g)
-        U = 128 + 20 * torch.sin((cx + 3 * n) / 97) + 1.5 * torch.randn(cx.shape, device=device, generator=g)
-        V = 128 + 20 * torch.cos((cy + 2 * n) / 71) + 1.5 * torch.randn(cy.shape, device=device, generator=g)
-        out[n, :W * H] = Y.clamp(0, 255).to(torch.uint8).reshape(-1)
-        out[n, W * H:W * H + W * H // 4] = U.clamp(0, 255).to(torch.uint8).reshape(-1)
-        out[n, W * H + W * H // 4:] = V.clamp(0, 255).to(torch.uint8).reshape(-1)
-    return out
-
-
-def synth_frames_numpy(nframes, seed=1234):
-    from oracle import synth
-    g = synth.Noisy(W, H, FMT, seed)
-    return [g.next() for _ in range(nframes)]
+# ------------------------------------------------------------------------------------------------ reference arm
+def time_reference(nframes_per_step, steps, warmup):
+    """the UNMODIFIED reference encoder (oracle/_ref, compiled from /root/reference by oracle/Makefile) on the S2 clip,
+    slice-threaded on the host cores (pthread_slice.c); the oracle C port only if that library did not travel"""
+    from oracle import ffv1_ref
+    clip = s2_clip(min(nframes_per_step, CLIP))
+    frames = [clip[i % len(clip)] for i in range(nframes_per_step)]
+    if ffv1_ref.available():
+        kind, threads = "reference", min(os.cpu_count() or 1, 24)
+        enc = ffv1_ref.Encoder(W, H, FMT, gop=GOP, threads=threads, **OPTS)
+        what = "unmodified ffv1enc.c (oracle/_ref), %d slice threads" % threads
+    else:
+        from oracle import ffv1_oracle
+        kind, threads = "port", 1
+        enc = ffv1_oracle.Encoder(W, H, FMT, gop=GOP, **OPTS)
+        what = "oracle C port, 1 thread (oracle/_ref did not travel)"
+    gold = golden()
+    clip_ok = hashlib.md5(clip.tobytes()).hexdigest() == gold["input_md5"] if len(clip) == CLIP else False
+    for _ in range(warmup):
+        for f in frames:
+            enc.encode(f)
+    pk = []
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        pk = [enc.encode(f) for f in frames]
+    dt = time.perf_counter() - t0
+    # (frames per step is a multiple of the GOP size, so every step starts on a keyframe like the golden stream)
+    parity = check_packets(gold, clip_ok and nframes_per_step % GOP == 0, lambda i: pk[i], range(min(len(pk), CLIP)))
+    fps = nframes_per_step * steps / dt
+    return fps, dt, {"value": fps, "unit": "frames/s", "cores": threads, "kind": kind,
+                     "sample": "%d frames/step x %d steps of the same clip, %s" % (nframes_per_step, steps, what),
+                     "parity_checked": bool(parity)}
 
 
 def run_reference(args, rank, world):
-    """The reference's own CPU encoder (unmodified sources compiled into oracle/_ref), slice-threaded on the host cores."""
     if rank != 0:
         return
-    from oracle import ffv1_ref
-    if not ffv1_ref.available():
-        from oracle import ffv1_oracle
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libffv1ref.so missing (build needs /root/reference)"}))
-        return
-    threads = min(os.cpu_count() or 1, 24)
-    per_step = args.ref_frames
-    frames = synth_frames_numpy(per_step)
-    enc = ffv1_ref.Encoder(W, H, FMT, gop=GOP, threads=threads, **OPTS)
-    nbytes = 0
-    for _ in range(args.warmup):
-        for f in frames:
-            enc.encode(f)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        for f in frames:
-            nbytes += len(enc.encode(f)[0])
-    dt = time.perf_counter() - t0
-    fps = per_step * args.steps / dt
+    per_step = max(GOP, args.ref_frames // GOP * GOP)
+    fps, dt, cb = time_reference(per_step, args.steps, args.warmup)
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1000 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frames_per_step": per_step, "host_threads": threads},
-            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "reference",
-                             "sample": "%d frames/step x %d steps, slice threads (pthread_slice.c), unmodified ffv1enc.c" % (per_step, args.steps)},
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config_dict(),
+            "run": {"frames_per_step": per_step, "host_threads": cb["cores"],
+                    "note": "ONE process with up to 24 slice threads whatever --gpus says (slice threading is all the "
+                            "reference offers inside one encoder; 24 slices cap it): at N GPUs the ratio compares N GPUs "
+                            "with these threads"},
+            "cpu_baseline": cb, "parity_checked": cb["parity_checked"],
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
-def cpu_baseline_leg(nframes=48):
-    """reference CPU encoder on a bounded sample of the same workload (rank 0, N=1 only)"""
-    try:
-        from oracle import ffv1_ref
-        kind = "reference"
-        if ffv1_ref.available():
-            threads = min(os.cpu_count() or 1, 24)
-            enc = ffv1_ref.Encoder(W, H, FMT, gop=GOP, threads=threads, **OPTS)
-        else:
-            from oracle import ffv1_oracle
-            kind, threads = "port", 1
-            nframes = 16
-            enc = ffv1_oracle.Encoder(W, H, FMT, gop=GOP, **OPTS)
-        frames = synth_frames_numpy(nframes)
-        enc.encode(frames[0])      # warm the page cache / thread pool; GOP position restarts below anyway
-        t0 = time.perf_counter()
-        for f in frames:
-            enc.encode(f)
-        dt = time.perf_counter() - t0
-        return {"value": nframes / dt, "unit": "frames/s", "cores": threads, "kind": kind,
-                "sample": "%d frames of the same workload, %s, %d host thread(s)" % (nframes, "oracle/_ref slice-threaded" if kind == "reference" else "oracle C port", threads)}
-    except Exception as ex:      # the baseline must never take the GPU number down
-        return {"value": None, "unit": "frames/s", "cores": 0, "kind": "unavailable", "sample": repr(ex)}
-
-
+# ------------------------------------------------------------------------------------------------ our arm
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=2048, help="frames per step per GPU (multiple of the GOP size)")
+    ap.add_argument("--batch", type=int, default=2048, help="frames per step per GPU (multiple of 32)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--ref-frames", type=int, default=32, help="--impl reference: frames per step")
+    ap.add_argument("--frames-total", type=int, default=0, help="BASELINE configs[4]: a fixed job of this many frames split "
+                    "into GOP-aligned ranges over the GPUs (strong scaling), encode and decode")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--coder", type=int, default=None, help="variant runs only: 0 = Golomb-Rice, -2 = default state table (the metric is coder=1)")
     ap.add_argument("--context", type=int, default=None, help="variant runs only: 1 = large context model")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-decode", action="store_true", help="skip the decoder leg (extra key \"decode\", N=1 only)")
+    ap.add_argument("--no-avcodec", action="store_true", help="skip the leg through the AVCodec shim (extra key \"e2e_avcodec\")")
     args = ap.parse_args()
     global WORKLOAD
     if args.coder is not None or args.context is not None:
@@ -197,18 +223,47 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the FFV1 path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # the rank's thread and its pinned staging buffers go to the NUMA node the GPU hangs off (before anything is pinned)
+    numa_node = ffv1_b200.bind_thread_to_device(local_rank)
     dist = None
     if world > 1:
         import torch.distributed as dist
-        os.environ.pop("NCCL_DEBUG", None)     # WARN / VERSION / INFO all print a banner; stdout is also redirected below
         dist.init_process_group("nccl", device_id=dev)
 
-    B = max(GOP, args.batch // GOP * GOP)
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    gold = golden()
+    clip = s2_clip()
+    clip_ok = hashlib.md5(clip.tobytes()).hexdigest() == gold["input_md5"]
+    clip_dev = torch.from_numpy(clip).to(dev)
+
+    if args.frames_total:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_job
+        line = bench_job.run(args, rank, local_rank, world, dev, dist, barrier, max_over_ranks, clip, clip_dev, clip_ok, gold,
+                             config_dict(), METRIC, OPTS, numa_node, ClockSampler)
+        if line is not None:
+            print(json.dumps(line))
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    B = max(CLIP, args.batch // CLIP * CLIP)
     steps_total = args.warmup + args.steps
-    # GOP-aligned frame ranges: rank r codes pictures [r*steps_total*B, ...) -- no data is exchanged between ranks
+    # GOP-aligned frame ranges: rank r codes pictures [r*2*steps_total*B, ...) -- no data is exchanged between ranks
     enc = ffv1_b200.FFV1Encoder(W, H, FMT, g=GOP, device=local_rank, max_batch_frames=B,
                                 first_picture_number=rank * 2 * steps_total * B, **OPTS)
-    frames_dev = synth_frames_torch(torch, B, dev, 1234 + rank)
+    frames_dev = clip_dev[torch.arange(B, device=dev) % CLIP].contiguous()          # [B, FRAME_BYTES]
     out_cap = B * (FRAME_BYTES // 2 + 65536)
     out_dev = torch.empty(out_cap, dtype=torch.uint8, device=dev)
     base = frames_dev.data_ptr()
@@ -217,16 +272,10 @@ def main():
         p0 = base + f * FRAME_BYTES
         planes += [p0, p0 + W * H, p0 + W * H + W * H // 4, 0]
         ls += [W, W // 2, W // 2, 0]
-    import ctypes
     planes = (ctypes.c_void_p * (4 * B))(*planes)
     ls = (ctypes.c_int * (4 * B))(*ls)
     stream = torch.cuda.Stream(device=dev)
-    sh = ctypes_ptr(stream.cuda_stream)
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
+    sh = ctypes.c_void_p(stream.cuda_stream)
 
     # ---------------- device-resident throughput ("value")
     for _ in range(args.warmup):
@@ -247,10 +296,16 @@ def main():
     st1 = {k: getattr(s1, k) for k, _ in s1._fields_}
     d = {k: st1[k] - st0[k] for k in st1}
     pkt_bytes_step = sum(p.size for p in pk)
+    # parity of the timed path: the first and the last 32 packets of the last timed batch against the reference's own
+    tail = list(range(CLIP)) + list(range(B - CLIP, B))
+    def dev_packet(i):
+        return out_dev[pk[i].offset:pk[i].offset + pk[i].size].cpu().numpy().tobytes(), pk[i].flags & 1
+    parity_value = check_packets(gold, clip_ok, dev_packet, tail)
 
     # ---------------- end to end through the host-buffer C-ABI calls ("e2e"): pinned host frames in, packets out to
-    #                  pinned host memory; submit/collect keeps two batches in flight (copies overlap kernels)
-    e2e = None
+    #                  pinned host memory; submit / collect_async keep two batches in flight: the frames of batch k+2 go
+    #                  to the device while batch k+1 is coded and the packets of batch k go to the host
+    e2e, parity_e2e = None, None
     if not args.no_e2e:
         host_in = torch.empty((B, FRAME_BYTES), dtype=torch.uint8, pin_memory=True)
         host_in.copy_(frames_dev)
@@ -260,34 +315,53 @@ def main():
         torch.cuda.empty_cache()
         enc2 = ffv1_b200.FFV1Encoder(W, H, FMT, g=GOP, device=local_rank, max_batch_frames=B,
                                      first_picture_number=(rank * 2 + 1) * steps_total * B, **OPTS)
-        host_out = torch.empty(out_cap, dtype=torch.uint8, pin_memory=True).numpy()
+        host_out = [torch.empty(out_cap, dtype=torch.uint8, pin_memory=True).numpy() for _ in range(2)]
         table = enc2.prepare(host_frames)
-        for _ in range(min(args.warmup, 2)):
+        for i in range(min(args.warmup, 2)):
             enc2.submit(table)
-            enc2.collect(out=host_out, copy=False)
+            enc2.collect(out=host_out[i & 1], copy=False)
         barrier()
         t0 = time.perf_counter()
         enc2.submit(table)
-        for _ in range(args.steps - 1):
+        for i in range(args.steps - 1):
             enc2.submit(table)
-            pk2 = enc2.collect(out=host_out, copy=False)
-        pk2 = enc2.collect(out=host_out, copy=False)
+            pk2 = enc2.collect(out=host_out[i & 1], copy=False, wait_bytes=False)
+        last = host_out[(args.steps - 1) & 1]
+        pk2 = enc2.collect(out=last, copy=False)
         torch.cuda.synchronize(dev)
-        dt = time.perf_counter() - t0
-        if dist is not None:
-            t = torch.tensor([dt], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
+        dt = max_over_ranks(time.perf_counter() - t0)
+        parity_e2e = check_packets(gold, clip_ok, lambda i: (last[pk2[i].offset:pk2[i].offset + pk2[i].size].tobytes(), pk2[i].flags & 1), tail)
+        d2h_step = int(sum(p.size for p in pk2)) + 12 * B + 72
         e2e = {"value": world * B * args.steps / dt, "unit": "frames/s", "h2d_bytes_per_step": B * FRAME_BYTES,
-               "d2h_bytes_per_step": int(sum(p.size for p in pk2)) + 12 * B + 72,
-               "note": "ffv1b200_enc_submit_host/_collect: pinned host frames -> packets in pinned host memory, two batches "
-                       "in flight, wall clock over all steps incl. every copy, max over ranks"}
+               "d2h_bytes_per_step": d2h_step, "numa_node": numa_node,
+               "note": "ffv1b200_enc_submit_host / _collect_async: pinned host frames -> packets in pinned host memory, two "
+                       "batches in flight (H2D of batch k+2, kernels of k+1 and D2H of k overlap), wall clock over all steps "
+                       "incl. every copy, max over ranks"}
         del enc2
+        # ---- the copies alone (same pinned buffers, same sizes, no kernel): the ceiling the link sets for e2e
+        cin, cout = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        npk = int(sum(p.size for p in pk2))
+        ho = torch.from_numpy(host_out[0])
+        def copies(n):
+            for _ in range(n):
+                with torch.cuda.stream(cin):
+                    frames_dev.copy_(host_in, non_blocking=True)
+                with torch.cuda.stream(cout):
+                    ho[:npk].copy_(out_dev[:npk], non_blocking=True)
+            torch.cuda.synchronize(dev)
+        copies(1)
+        barrier()
+        t0 = time.perf_counter()
+        copies(max(2, args.steps // 2))
+        dtc = max_over_ranks(time.perf_counter() - t0)
+        cfps = world * B * max(2, args.steps // 2) / dtc
+        e2e["copy_only"] = {"value": cfps, "unit": "frames/s", "frac": e2e["value"] / cfps,
+                            "gb_per_s_per_gpu": {"h2d": B * FRAME_BYTES * max(2, args.steps // 2) / dtc / 1e9,
+                                                 "d2h": npk * max(2, args.steps // 2) / dtc / 1e9},
+                            "note": "the same H2D and D2H copies, concurrently on two streams, no kernels; frac = e2e / this"}
+        del host_in, host_frames, table
 
-    if dist is not None:
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    ms = max_over_ranks(ms)
     clocks = sampler.stop() if sampler else None
 
     if rank == 0:
@@ -298,10 +372,13 @@ def main():
         line = {
             "metric": METRIC, "value": world * B * args.steps / (ms * 1e-3), "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": B, "input_bytes_per_step_per_gpu": B * FRAME_BYTES,
-                       "l2_policy": "input (%.0f MB) and intermediate streams are far larger than the 126 MB L2" % (B * FRAME_BYTES / 1e6),
-                       "parallelism": "GOP-aligned frame ranges per GPU, no collective", "packet_bytes_per_frame": pkt_bytes_step / B},
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config_dict(),
+            "run": {"frames_per_step_per_gpu": B, "input_bytes_per_step_per_gpu": B * FRAME_BYTES,
+                    "packet_bytes_per_frame": pkt_bytes_step / B},
+            "parity_checked": bool(parity_value) and (args.no_e2e or bool(parity_e2e)),
+            "parity": {"against": "reference build's packets (tests/golden/ref_packets.json: size, MD5, key flag)",
+                       "value_leg_packets": parity_value, "e2e_leg_packets": parity_e2e,
+                       "which": "first and last 32 packets of the last timed batch of each leg", "input_md5_ok": clip_ok},
             "roofline": {"kernel": "k_pixel_fast (prediction/context/residual pass)", "bound": "hbm", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": TRAFFIC_BYTES_PER_FRAME * B,
                          "traffic_source": "ncu dram__bytes_read+write per launch, profiles/r01_k_pixel_fast.txt, scaled to this batch",
@@ -314,25 +391,31 @@ def main():
             "gpu_launches": d["kernel_launches"], "retries": d["retries"],
             "clocks": clocks, "e2e": e2e,
         }
+        del frames_dev, out_dev
+        torch.cuda.empty_cache()
+        if world == 1 and not args.no_avcodec and not args.no_e2e:
+            try:                                     # the same encode through the AVCodec shim and the reference's libavcodec
+                sys.path.insert(0, os.path.join(ROOT, "tools"))
+                import bench_avcodec
+                line["e2e_avcodec"] = bench_avcodec.run(clip, gold if clip_ok else None, batch=B, opts=OPTS, gop=GOP,
+                                                        ref_frames=0 if args.no_cpu_baseline else 64)
+            except Exception as ex:
+                line["e2e_avcodec"] = {"value": None, "note": repr(ex)}
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline_leg()
+            try:
+                line["cpu_baseline"] = time_reference(32, 6, 1)[2]
+            except Exception as ex:      # the baseline must never take the GPU number down
+                line["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": 0, "kind": "unavailable", "sample": repr(ex)}
         if world == 1 and not args.no_decode:
             try:                                     # decoder of the same stream (extra information, not the metric)
                 sys.path.insert(0, os.path.join(ROOT, "tools"))
                 import bench_decode
-                del frames_dev, out_dev
-                torch.cuda.empty_cache()
                 line["decode"] = bench_decode.run(512, 512, 1, 0 if args.no_cpu_baseline else 33)
             except Exception as ex:
                 line["decode"] = {"value": None, "note": repr(ex)}
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
-
-
-def ctypes_ptr(v):
-    import ctypes
-    return ctypes.c_void_p(v)
 
 
 if __name__ == "__main__":

@@ -3,6 +3,12 @@
 #include "ffv1_internal.h"
 #include <cuda_runtime.h>
 #include <string>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <sched.h>
+#include <unistd.h>
+#include <sys/syscall.h>
 
 namespace ffv1 {
 static thread_local std::string g_last_error;
@@ -49,6 +55,55 @@ int ffv1b200_device_count(void)
         return FFV1B200_ERR_EXTERNAL;
     }
     return n;
+}
+
+// Host side of the copy path: the staging buffers of a GPU should live on the NUMA node its PCIe root port hangs off, and
+// the thread that fills / submits them should run there.  Reads the node from sysfs, pins the calling thread to the
+// node's CPUs and makes the node the preferred one for the thread's future allocations (pinned buffers included: they
+// are placed when they are allocated).  Returns the node, or FFV1B200_ERR_ENOSYS when the topology is not visible
+// (single-node machines, containers without sysfs): nothing is changed then.
+int ffv1b200_bind_thread_to_device(int device)
+{
+    char bdf[32] = {0};
+    if (cudaDeviceGetPCIBusId(bdf, sizeof(bdf), device) != cudaSuccess) {
+        cudaGetLastError();
+        ffv1::set_last_error("no such CUDA device");
+        return FFV1B200_ERR_EINVAL;
+    }
+    for (char *q = bdf; *q; q++) if (*q >= 'A' && *q <= 'F') *q += 'a' - 'A';
+    char path[128];
+    snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bdf);
+    int node = -1;
+    if (FILE *fh = fopen(path, "r")) { if (fscanf(fh, "%d", &node) != 1) node = -1; fclose(fh); }
+    if (node < 0) { ffv1::set_last_error(std::string("NUMA node of ") + bdf + " not visible"); return FFV1B200_ERR_ENOSYS; }
+    snprintf(path, sizeof(path), "/sys/devices/system/node/node%d/cpulist", node);
+    FILE *fh = fopen(path, "r");
+    if (!fh) { ffv1::set_last_error(std::string(path) + " not readable"); return FFV1B200_ERR_ENOSYS; }
+    char list[4096] = {0};
+    const bool got = fgets(list, sizeof(list), fh) != nullptr;
+    fclose(fh);
+    cpu_set_t allowed, want;
+    CPU_ZERO(&want);
+    if (!got || sched_getaffinity(0, sizeof(allowed), &allowed) != 0) return FFV1B200_ERR_ENOSYS;
+    int ncpu = 0;
+    for (char *q = list; *q && *q != '\n';) {                       // "0-31,64-95"
+        char *end;
+        long a = strtol(q, &end, 10), b = a;
+        if (end == q) break;
+        if (*end == '-') { q = end + 1; b = strtol(q, &end, 10); }
+        for (long c = a; c <= b && c < CPU_SETSIZE; c++) if (CPU_ISSET(c, &allowed)) { CPU_SET(c, &want); ncpu++; }
+        q = *end == ',' ? end + 1 : end;
+    }
+    if (!ncpu) { ffv1::set_last_error("no allowed CPU on the device's NUMA node"); return FFV1B200_ERR_ENOSYS; }
+    if (sched_setaffinity(0, sizeof(want), &want) != 0) return FFV1B200_ERR_ENOSYS;
+#ifdef SYS_set_mempolicy
+    if (node < 1024) {
+        unsigned long mask[16] = {0};
+        mask[node / (8 * sizeof(unsigned long))] |= 1ul << (node % (8 * sizeof(unsigned long)));
+        syscall(SYS_set_mempolicy, 1 /* MPOL_PREFERRED */, mask, 1024ul + 1ul);     // best effort (may be filtered in containers)
+    }
+#endif
+    return node;
 }
 
 } // extern "C"

@@ -856,24 +856,24 @@ void launch_ctx_replay(const EncDeviceTables &t, const EncBatch &b, int max_tile
     const int n = b.nframes * L.nslices * L.npc;
     k_dec_layout<<<(n + 127) / 128, 128, 0, s>>>(t, b);
     // tiles that fit the shared-memory sort (slices up to 352 samples wide) take the staged scatter
-    static int staged = -1;
-    if (staged < 0) { const char *v = getenv("FFV1B200_SCATTER"); staged = (v && !strcmp(v, "direct")) ? 0 : 1; }
+    int staged = 1;
+    if (const char *v = getenv("FFV1B200_SCATTER")) staged = strcmp(v, "direct") ? 1 : 0;
     if (staged && max_tile_samples <= kScatterSmMaxSamples) {
         k_ctx_scatter_sm<false><<<tiles, kScatterSmThreads, ctx_scatter_sm_smem_bytes(L), s>>>(t, b);
     } else {
         dim3 stiles((L.ctiles_per_frame + kScatterThreads / 32 - 1) / (kScatterThreads / 32), b.nframes);
         k_ctx_scatter<<<stiles, kScatterThreads, ctx_scatter_smem_bytes(L), s>>>(t, b);
     }
-    static int grp = -1;
-    if (grp < 0) { const char *v = getenv("FFV1B200_REPLAY_GROUPS"); grp = v ? atoi(v) : 2; }
+    int grp = 2;
+    if (const char *v = getenv("FFV1B200_REPLAY_GROUPS")) grp = atoi(v);
     // 8-bit content (residuals folded to <= 9 bits): two lists per warp; a frame's decision area must fit 32-bit offsets
     const bool grp_ok = L.coded_bits <= 9 && L.dec_per_frame < 0x7FFFFFFFu;
-    static int window = -1;
-    if (window < 0) { const char *v = getenv("FFV1B200_REPLAY_WINDOW"); window = v ? atoi(v) : 3; if (window < 1) window = 1 << 20; }
+    int window = 3;
+    if (const char *v = getenv("FFV1B200_REPLAY_WINDOW")) { window = atoi(v); if (window < 1) window = 1 << 20; }
     if (grp == 1 && grp_ok) k_replay_grp<4, 1024><<<nchains, 1024, replay_grp_smem(L), s>>>(t, b, window);
     else if (grp == 2 && grp_ok) {
-        static int threads = -1;
-        if (threads < 0) { const char *v = getenv("FFV1B200_REPLAY_THREADS"); threads = v ? atoi(v) : 256; }
+        int threads = 256;
+        if (const char *v = getenv("FFV1B200_REPLAY_THREADS")) threads = atoi(v);
         if (threads == 128)      k_replay_grp<4, 128><<<nchains, 128, replay_grp_smem(L), s>>>(t, b, window);
         else if (threads == 256) k_replay_grp<4, 256><<<nchains, 256, replay_grp_smem(L), s>>>(t, b, window);
         else                     k_replay_grp<4, 512><<<nchains, 512, replay_grp_smem(L), s>>>(t, b, window);

@@ -218,7 +218,7 @@ int ffv1b200_dec_decode_host(FFV1B200Decoder *d, int n, const uint8_t *const *pk
         if (key) {
             const uint8_t *q = pk + size;
             int cnt = 0;
-            for (; cnt < kMaxSlices && 3 < q - pk; cnt++) {
+            for (; cnt < kMaxSlices && trailer <= q - pk; cnt++) {      // (the reference tests 3 < q - pk and may read before the packet)
                 const long sz = ((long)q[-trailer] << 16) | ((long)q[-trailer + 1] << 8) | q[-trailer + 2];
                 if (sz + trailer > q - pk) break;
                 q -= sz + trailer;

@@ -754,8 +754,9 @@ __global__ void __launch_bounds__(kRangeThreads) k_rangecode(const EncDeviceTabl
 void launch_rangecode(const EncDeviceTables &t, const EncBatch &b, cudaStream_t s)
 {
     const int n = b.nframes * t.layout.nslices;
-    static int forced = -1;
-    if (forced < 0) { const char *v = getenv("FFV1B200_RANGE_LANES"); forced = v ? atoi(v) : 0; if (forced < 0 || forced > 32) forced = 0; }
+    // FFV1B200_RANGE_LANES forces the coders per warp (read at every launch: the parity tests walk through all variants)
+    int forced = 0;
+    if (const char *v = getenv("FFV1B200_RANGE_LANES")) { forced = atoi(v); if (forced < 1 || forced > 32 || (forced & (forced - 1))) forced = 0; }
     int lanes = forced;
     if (!lanes) {                                  // the coders are bound by latency: ~10 warps per SM before warps are filled up
         lanes = 4;
@@ -1223,8 +1224,8 @@ __global__ void __launch_bounds__(32 * kGrPackWarps) k_gr_pack(const EncDeviceTa
 void launch_golomb_coder(const EncDeviceTables &t, const EncBatch &b, cudaStream_t s)
 {
     const Layout &L = t.layout;
-    static int window = -1;
-    if (window < 0) { const char *v = getenv("FFV1B200_GOLOMB_WINDOW"); window = v ? atoi(v) : 3; if (window < 1) window = 1 << 20; }
+    int window = 3;
+    if (const char *v = getenv("FFV1B200_GOLOMB_WINDOW")) { window = atoi(v); if (window < 1) window = 1 << 20; }
     k_gr_replay<<<b.nseg * L.nslices * L.npc, kGrThreads, 2 * L.ctx_count * sizeof(uint32_t), s>>>(t, b, window);
     k_gr_pack<<<(b.nframes * L.nslices + kGrPackWarps - 1) / kGrPackWarps, 32 * kGrPackWarps, 0, s>>>(t, b);
 }

@@ -35,7 +35,15 @@ struct Slot {
     DevBuf<unsigned long long> d_status; PinnedBuf<unsigned long long> h_status;
     DevBuf<uint32_t> d_pkt_size; PinnedBuf<uint32_t> h_pkt_size;
     DevBuf<uint64_t> d_pkt_off; PinnedBuf<uint64_t> h_pkt_off;
-    cudaEvent_t ev_h2d = nullptr, ev_small = nullptr, ev[6] = {nullptr};
+    // what every slice codes before its first sample (keyframe bit, slice header) depends on the frame properties the
+    // batch was submitted with (ffv1enc.c:1044-1049): each slot keeps its own copy, so a batch in flight -- or re-run by
+    // recover() -- is never coded with the properties of a later one
+    DevBuf<uint16_t> d_prefix; DevBuf<int32_t> d_prefix_len;
+    DevBuf<uint8_t> d_gprefix; DevBuf<int32_t> d_gprefix_len;
+    FFV1B200FrameProps props{0, 1, 3};
+    bool prefix_valid = false;
+    cudaEvent_t ev_h2d = nullptr, ev_small = nullptr, ev_d2h = nullptr, ev[6] = {nullptr};
+    bool d2h_pending = false;        // a packet copy from this slot's output area may still be running on the copy-out stream
     int nframes = 0, nseg = 0, carry_in = 0;
     int64_t first_pn = 0;
     int ls[4] = {0, 0, 0, 0};
@@ -52,8 +60,7 @@ struct FFV1B200Encoder {
     std::vector<uint8_t> extradata;
     int device = 0, max_batch = 64;
     int64_t picture_number = 0;      // of the next frame to be SUBMITTED
-    FFV1B200FrameProps props{0, 1, 3};
-    bool prefix_dirty = true;
+    FFV1B200FrameProps props{0, 1, 3};          // of the frames submitted next
     cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
 
     // static device tables
@@ -61,8 +68,7 @@ struct FFV1B200Encoder {
     DevBuf<CtxTile> d_ctiles;
     FastPlan fast_plan; DevBuf<FastItemDesc> d_fast_items;
     FusedPlan fused_plan; DevBuf<FusedSeg> d_fused_segs; DevBuf<FusedSlice> d_fused_slices;
-    DevBuf<int16_t> d_quant; DevBuf<uint8_t> d_lut, d_one_pow, d_run_pc; DevBuf<uint16_t> d_prefix; DevBuf<int32_t> d_prefix_len;
-    DevBuf<uint8_t> d_gprefix; DevBuf<int32_t> d_gprefix_len;
+    DevBuf<int16_t> d_quant; DevBuf<uint8_t> d_lut, d_one_pow, d_run_pc;
     // shared intermediates
     DevBuf<uint32_t> d_rec, d_run_cnt, d_slice_bytes, d_line_pos, d_ctx_hist, d_list_start, d_list_count;
     DevBuf<uint16_t> d_dec, d_list_order;
@@ -84,42 +90,42 @@ int fail(int code, const std::string &msg) { set_last_error(msg); return code; }
 
 #define CU_TRY(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) return fail(FFV1B200_ERR_EXTERNAL, std::string(#expr) + ": " + cudaGetErrorString(e_)); } while (0)
 
-int upload_prefixes(FFV1B200Encoder *e)
+// the slot's header tables for the frame properties its batch is submitted with (stream-ordered on the stream the batch's
+// kernels run on; the sources are pageable, so the copies are staged before the calls return)
+int upload_prefixes(FFV1B200Encoder *e, Slot &sl, cudaStream_t s)
 {
+    const FFV1B200FrameProps &pr = e->props;
+    if (sl.prefix_valid && sl.props.sar_num == pr.sar_num && sl.props.sar_den == pr.sar_den && sl.props.picture_structure == pr.picture_structure)
+        return 0;
     const int ns = e->cfg.slice_count();
-    cudaStream_t s = e->s_comp;
     if (e->tab.layout.golomb) {
         std::vector<uint8_t> gp((size_t)ns * 2 * kMaxGolombPrefix, 0);
         std::vector<int32_t> gl((size_t)ns * 2, 0);
-        for (int sl = 0; sl < ns; sl++)
+        for (int sx = 0; sx < ns; sx++)
             for (int key = 0; key < 2; key++) {
-                std::vector<uint8_t> b = slice_prefix_bytes(e->cfg, sl, key != 0, e->props.sar_num, e->props.sar_den, e->props.picture_structure);
+                std::vector<uint8_t> b = slice_prefix_bytes(e->cfg, sx, key != 0, pr.sar_num, pr.sar_den, pr.picture_structure);
                 if ((int)b.size() > kMaxGolombPrefix) return fail(FFV1B200_ERR_EINVAL, "slice header too long");
-                std::copy(b.begin(), b.end(), gp.begin() + (size_t)(sl * 2 + key) * kMaxGolombPrefix);
-                gl[sl * 2 + key] = (int32_t)b.size();
+                std::copy(b.begin(), b.end(), gp.begin() + (size_t)(sx * 2 + key) * kMaxGolombPrefix);
+                gl[sx * 2 + key] = (int32_t)b.size();
             }
-        CU_TRY(cudaStreamSynchronize(s));                 // earlier batches may still read the old tables
-        CU_TRY(e->d_gprefix.upload(gp.data(), gp.size(), s));
-        CU_TRY(e->d_gprefix_len.upload(gl.data(), gl.size(), s));
-        CU_TRY(cudaStreamSynchronize(s));
-        e->prefix_dirty = false;
-        return 0;
+        CU_TRY(sl.d_gprefix.upload(gp.data(), gp.size(), s));
+        CU_TRY(sl.d_gprefix_len.upload(gl.data(), gl.size(), s));
+    } else {
+        std::vector<uint16_t> pre((size_t)(ns * 2 + 1) * kMaxPrefix, 0);
+        pre[(size_t)ns * 2 * kMaxPrefix] = 129;                              // the decision that closes every slice (state 129, bit 0)
+        std::vector<int32_t> len((size_t)ns * 2, 0);
+        for (int sx = 0; sx < ns; sx++)
+            for (int key = 0; key < 2; key++) {
+                std::vector<uint16_t> d = slice_prefix_decisions(e->cfg, sx, key != 0, pr.sar_num, pr.sar_den, pr.picture_structure);
+                if ((int)d.size() > kMaxPrefix) return fail(FFV1B200_ERR_EINVAL, "slice header too long");
+                std::copy(d.begin(), d.end(), pre.begin() + (size_t)(sx * 2 + key) * kMaxPrefix);
+                len[sx * 2 + key] = (int32_t)d.size();
+            }
+        CU_TRY(sl.d_prefix.upload(pre.data(), pre.size(), s));
+        CU_TRY(sl.d_prefix_len.upload(len.data(), len.size(), s));
     }
-    std::vector<uint16_t> pre((size_t)(ns * 2 + 1) * kMaxPrefix, 0);
-    pre[(size_t)ns * 2 * kMaxPrefix] = 129;                              // the decision that closes every slice (state 129, bit 0)
-    std::vector<int32_t> len((size_t)ns * 2, 0);
-    for (int sl = 0; sl < ns; sl++)
-        for (int key = 0; key < 2; key++) {
-            std::vector<uint16_t> d = slice_prefix_decisions(e->cfg, sl, key != 0, e->props.sar_num, e->props.sar_den, e->props.picture_structure);
-            if ((int)d.size() > kMaxPrefix) return fail(FFV1B200_ERR_EINVAL, "slice header too long");
-            std::copy(d.begin(), d.end(), pre.begin() + (size_t)(sl * 2 + key) * kMaxPrefix);
-            len[sl * 2 + key] = (int32_t)d.size();
-        }
-    CU_TRY(cudaStreamSynchronize(s));
-    CU_TRY(e->d_prefix.upload(pre.data(), pre.size(), s));
-    CU_TRY(e->d_prefix_len.upload(len.data(), len.size(), s));
-    CU_TRY(cudaStreamSynchronize(s));
-    e->prefix_dirty = false;
+    sl.props = pr;
+    sl.prefix_valid = true;
     return 0;
 }
 
@@ -160,19 +166,20 @@ int alloc_buffers(FFV1B200Encoder *e)
         CU_TRY(sl.d_pkt_size.alloc(F)); CU_TRY(sl.h_pkt_size.alloc(F));
         CU_TRY(sl.d_pkt_off.alloc(F + 1)); CU_TRY(sl.h_pkt_off.alloc(F + 1));
         CU_TRY(cudaEventCreate(&sl.ev_h2d)); CU_TRY(cudaEventCreate(&sl.ev_small));
+        CU_TRY(cudaEventCreateWithFlags(&sl.ev_d2h, cudaEventDisableTiming));
         for (auto &ev : sl.ev) CU_TRY(cudaEventCreate(&ev));
     }
     return 0;
 }
 
-EncDeviceTables device_tables(FFV1B200Encoder *e)
+EncDeviceTables device_tables(FFV1B200Encoder *e, const Slot &sl)
 {
     EncDeviceTables t;
     t.layout = e->tab.layout;
     t.slices = e->d_slices.p; t.lines = e->d_lines.p; t.pc_lines = e->d_pc_lines.p; t.tiles = e->d_tiles.p;
     t.ctiles = e->d_ctiles.p;
     t.quant = e->d_quant.p; t.trans_lut = e->d_lut.p; t.one_pow = e->d_one_pow.p; t.run_pc = e->d_run_pc.p;
-    t.gprefix = e->d_gprefix.p; t.gprefix_len = e->d_gprefix_len.p; t.prefix = e->d_prefix.p; t.prefix_len = e->d_prefix_len.p;
+    t.gprefix = sl.d_gprefix.p; t.gprefix_len = sl.d_gprefix_len.p; t.prefix = sl.d_prefix.p; t.prefix_len = sl.d_prefix_len.p;
     t.ec = e->cfg.ec; t.version = e->cfg.version; t.state_in_smem = e->state_in_smem ? 1 : 0;
     return t;
 }
@@ -202,7 +209,9 @@ int enqueue_kernels(FFV1B200Encoder *e, Slot &sl, cudaStream_t s)
     CU_TRY(cudaMemcpyAsync(sl.d_frame_seg.p, sl.h_frame_seg.p, sizeof(int32_t) * nframes, cudaMemcpyHostToDevice, s));
     CU_TRY(cudaMemsetAsync(sl.d_status.p, 0, sizeof(unsigned long long) * 8, s));
 
-    EncDeviceTables t = device_tables(e);
+    // the packet area of this slot may still be on its way to the host (ffv1b200_enc_collect_async)
+    if (sl.d2h_pending) CU_TRY(cudaStreamWaitEvent(s, sl.ev_d2h, 0));
+    EncDeviceTables t = device_tables(e, sl);
     EncBatch b{};
     b.nframes = nframes; b.nseg = sl.nseg;
     b.planes = sl.d_planes.p;
@@ -337,6 +346,17 @@ bool pixel_fast_ok(const FFV1B200Encoder *e, const Slot &sl)
     return fast;
 }
 
+// waits until no packet copy of an earlier ffv1b200_enc_collect_async is running any more
+int finish_output(FFV1B200Encoder *e)
+{
+    for (Slot &sl : e->slot)
+        if (sl.d2h_pending) {
+            CU_TRY(cudaEventSynchronize(sl.ev_d2h));
+            sl.d2h_pending = false;
+        }
+    return 0;
+}
+
 } // namespace
 
 extern "C" {
@@ -363,7 +383,10 @@ int ffv1b200_enc_open(FFV1B200Encoder **out, const FFV1B200EncParams *p)
     CU_TRY(cudaStreamCreateWithFlags(&e->s_out, cudaStreamNonBlocking));
 
     e->extradata = write_extradata(e->cfg);
+    // test hook: start with decision regions that are too small, so that the overflow -> grow -> re-run path is taken
+    if (const char *v = getenv("FFV1B200_DEC_PER_SAMPLE")) { const double q = atof(v); if (q >= 0.25 && q <= 64.0) e->dec_per_sample = q; }
     build_tables(e->cfg, e->tab);
+    if (e->dec_per_sample != 5.0) layout_decisions(e->tab, e->dec_per_sample);
     const Layout &L = e->tab.layout;
     e->state_in_smem = replay_smem_bytes(L) <= 227 * 1024;
     if (const char *v = getenv("FFV1B200_REPLAY_STATE")) { if (!strcmp(v, "global")) e->state_in_smem = false; }
@@ -417,8 +440,6 @@ int ffv1b200_enc_open(FFV1B200Encoder **out, const FFV1B200EncParams *p)
         for (int q = 0; q < 256; q++) one_pow[k * 256 + q] = lut[256 + one_pow[(k - 1) * 256 + q]];
     CU_TRY(e->d_one_pow.upload(one_pow.data(), one_pow.size(), s));
     CU_TRY(e->d_run_pc.upload(e->tab.run_pc.data(), e->tab.run_pc.size(), s));
-    CU_TRY(e->d_prefix.alloc((size_t)(L.nslices * 2 + 1) * kMaxPrefix));
-    CU_TRY(e->d_prefix_len.alloc((size_t)L.nslices * 2));
     r = alloc_buffers(e.get());
     if (r < 0) return r;
     CU_TRY(cudaStreamSynchronize(s));
@@ -430,10 +451,12 @@ void ffv1b200_enc_close(FFV1B200Encoder *e)
 {
     if (!e) return;
     cudaSetDevice(e->device);
+    finish_output(e);
     for (cudaStream_t s : {e->s_in, e->s_comp, e->s_out}) if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
     for (Slot &sl : e->slot) {
         if (sl.ev_h2d) cudaEventDestroy(sl.ev_h2d);
         if (sl.ev_small) cudaEventDestroy(sl.ev_small);
+        if (sl.ev_d2h) cudaEventDestroy(sl.ev_d2h);
         for (auto &ev : sl.ev) if (ev) cudaEventDestroy(ev);
     }
     delete e;
@@ -466,10 +489,7 @@ int ffv1b200_enc_info(const FFV1B200Encoder *e, FFV1B200EncInfo *i)
 void ffv1b200_enc_set_frame_props(FFV1B200Encoder *e, const FFV1B200FrameProps *p)
 {
     if (!e || !p) return;
-    if (p->sar_num != e->props.sar_num || p->sar_den != e->props.sar_den || p->picture_structure != e->props.picture_structure) {
-        e->props = *p;
-        e->prefix_dirty = true;
-    }
+    e->props = *p;               // applies to the batches submitted from now on; batches in flight keep theirs
 }
 
 int ffv1b200_enc_submit_host(FFV1B200Encoder *e, int nframes, const uint8_t *const *planes, const int *linesizes)
@@ -478,8 +498,8 @@ int ffv1b200_enc_submit_host(FFV1B200Encoder *e, int nframes, const uint8_t *con
     if (nframes < 1 || nframes > e->max_batch) return fail(FFV1B200_ERR_EINVAL, "nframes outside 1..max_batch_frames");
     if (e->submitted - e->collected >= (uint64_t)kSlots) return fail(FFV1B200_ERR_EINVAL, "two batches are already in flight: collect one first");
     CU_TRY(cudaSetDevice(e->device));
-    if (e->prefix_dirty) { int r = upload_prefixes(e); if (r < 0) return r; }
     Slot &sl = e->slot[e->submitted % kSlots];
+    { int r = upload_prefixes(e, sl, e->s_comp); if (r < 0) return r; }
     const Config &c = e->cfg;
     const int np = c.nb_src_planes;
 
@@ -560,11 +580,19 @@ int ffv1b200_enc_submit_host(FFV1B200Encoder *e, int nframes, const uint8_t *con
     return nframes;
 }
 
-int ffv1b200_enc_collect(FFV1B200Encoder *e, uint8_t *out, size_t out_cap, FFV1B200Packet *pkts, size_t *needed)
+int ffv1b200_enc_sync_output(FFV1B200Encoder *e)
+{
+    if (!e) return fail(FFV1B200_ERR_EINVAL, "null argument");
+    CU_TRY(cudaSetDevice(e->device));
+    return finish_output(e);
+}
+
+int ffv1b200_enc_collect_async(FFV1B200Encoder *e, uint8_t *out, size_t out_cap, FFV1B200Packet *pkts, size_t *needed)
 {
     if (!e || !out || !pkts) return fail(FFV1B200_ERR_EINVAL, "null argument");
     if (e->collected == e->submitted) return fail(FFV1B200_ERR_EINVAL, "no batch in flight");
     CU_TRY(cudaSetDevice(e->device));
+    { int r = finish_output(e); if (r < 0) return r; }          // the previous batch's bytes are complete from here on
     Slot &sl = e->slot[e->collected % kSlots];
     CU_TRY(cudaEventSynchronize(sl.ev_small));
     if (sl.h_status.p[0] | sl.h_status.p[1] | sl.h_status.p[2]) {
@@ -577,8 +605,11 @@ int ffv1b200_enc_collect(FFV1B200Encoder *e, uint8_t *out, size_t out_cap, FFV1B
         set_last_error("output buffer too small: need " + std::to_string(total) + " bytes");
         return FFV1B200_ERR_BUFFER_TOO_SMALL;                   // the batch stays collectable
     }
+    // the copy runs on its own stream: the caller can submit the next batch (whose host->device copies use the other
+    // direction of the link) while the packets are still on their way
     CU_TRY(cudaMemcpyAsync(out, sl.out, total, cudaMemcpyDeviceToHost, e->s_out));
-    CU_TRY(cudaStreamSynchronize(e->s_out));
+    CU_TRY(cudaEventRecord(sl.ev_d2h, e->s_out));
+    sl.d2h_pending = true;
     e->stats.d2h_bytes += (int64_t)total;
     account(e, sl);
     fill_packets(sl, pkts);
@@ -586,6 +617,14 @@ int ffv1b200_enc_collect(FFV1B200Encoder *e, uint8_t *out, size_t out_cap, FFV1B
     e->last_slot = (int)(e->collected % kSlots);
     e->collected++;
     return sl.nframes;
+}
+
+int ffv1b200_enc_collect(FFV1B200Encoder *e, uint8_t *out, size_t out_cap, FFV1B200Packet *pkts, size_t *needed)
+{
+    const int r = ffv1b200_enc_collect_async(e, out, out_cap, pkts, needed);
+    if (r < 0) return r;
+    const int q = finish_output(e);
+    return q < 0 ? q : r;
 }
 
 int ffv1b200_enc_pending(const FFV1B200Encoder *e)
@@ -612,9 +651,9 @@ int ffv1b200_enc_encode_device(FFV1B200Encoder *e, int nframes, const void *cons
     if (nframes < 1 || nframes > e->max_batch) return fail(FFV1B200_ERR_EINVAL, "nframes outside 1..max_batch_frames");
     if (e->submitted != e->collected) return fail(FFV1B200_ERR_EINVAL, "collect the batches in flight first");
     CU_TRY(cudaSetDevice(e->device));
-    if (e->prefix_dirty) { int r = upload_prefixes(e); if (r < 0) return r; }
     cudaStream_t s = stream ? (cudaStream_t)stream : e->s_comp;
     Slot &sl = e->slot[e->submitted % kSlots];
+    { int r = upload_prefixes(e, sl, s); if (r < 0) return r; }
     for (int i = 0; i < 4; i++) sl.ls[i] = linesizes[i];
     for (int f = 0; f < nframes; f++)
         for (int i = 0; i < 4; i++) {

@@ -77,6 +77,9 @@ def lib():
                                                ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(Packet), ctypes.POINTER(ctypes.c_size_t)]
         L.ffv1b200_enc_submit_host.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int)]
         L.ffv1b200_enc_collect.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(Packet), ctypes.POINTER(ctypes.c_size_t)]
+        L.ffv1b200_enc_collect_async.argtypes = L.ffv1b200_enc_collect.argtypes
+        L.ffv1b200_enc_sync_output.argtypes = [ctypes.c_void_p]
+        L.ffv1b200_bind_thread_to_device.argtypes = [ctypes.c_int]
         L.ffv1b200_enc_pending.argtypes = [ctypes.c_void_p]
         L.ffv1b200_enc_encode_device.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int),
                                                  ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(Packet), ctypes.POINTER(ctypes.c_size_t),
@@ -103,6 +106,11 @@ def _check(r):
 
 def device_count():
     return _check(lib().ffv1b200_device_count())
+
+def bind_thread_to_device(device):
+    """Pins the calling thread (and its future allocations) to the NUMA node of the GPU; returns the node or None."""
+    r = lib().ffv1b200_bind_thread_to_device(device)
+    return r if r >= 0 else None
 
 # --- tightly packed frame geometry (what av_image_copy_to_buffer(align=1) produces) -------------------
 def plane_shapes(pix_fmt, w, h):
@@ -228,8 +236,13 @@ class FFV1Encoder:
         self._inflight = getattr(self, "_inflight", [])
         self._inflight.append((keep, n))
 
-    def collect(self, out=None, copy=True):
-        """Wait for the oldest submitted batch. Returns [(bytes, key)] (or the Packet array when copy=False)."""
+    def collect(self, out=None, copy=True, wait_bytes=True):
+        """Wait for the oldest submitted batch. Returns [(bytes, key)] (or the Packet array when copy=False).
+        wait_bytes=False (needs out= and copy=False): return once the packets' device->host copy is queued; the bytes are
+        complete after the next collect() / sync_output()."""
+        if not wait_bytes and (out is None or copy):
+            raise ValueError("wait_bytes=False needs a caller-owned out array and copy=False")
+        fn = lib().ffv1b200_enc_collect if wait_bytes else lib().ffv1b200_enc_collect_async
         keep, n = self._inflight.pop(0)
         fb = int(self.info.frame_bytes)
         cap = n * (fb + fb // 4 + 65536) if out is None else out.nbytes
@@ -237,7 +250,7 @@ class FFV1Encoder:
         needed = ctypes.c_size_t()
         while True:
             buf = self._out_buffer(cap) if out is None else out
-            r = lib().ffv1b200_enc_collect(self._h, buf.ctypes.data, cap, pk, ctypes.byref(needed))
+            r = fn(self._h, buf.ctypes.data, cap, pk, ctypes.byref(needed))
             if r == ERR_BUFFER_TOO_SMALL and out is None:
                 cap = int(needed.value) + 4096
                 continue
@@ -246,6 +259,9 @@ class FFV1Encoder:
         if not copy:
             return pk
         return [(buf[pk[i].offset:pk[i].offset + pk[i].size].tobytes(), bool(pk[i].flags & 1)) for i in range(n)]
+
+    def sync_output(self):
+        _check(lib().ffv1b200_enc_sync_output(self._h))
 
     def pending(self):
         return _check(lib().ffv1b200_enc_pending(self._h))

@@ -97,6 +97,11 @@ const char *ffv1b200_strerror(int err);
 const char *ffv1b200_last_error(void);
 /* Number of usable CUDA devices with an sm_100 kernel image, or a negative error (never a CPU fallback). */
 int ffv1b200_device_count(void);
+/* Pins the calling thread to the CPUs of the NUMA node the device's PCIe link hangs off and prefers that node for the
+ * thread's allocations (call it before allocating the pinned frame / packet buffers a device is fed from).  Returns the
+ * node, or FFV1B200_ERR_ENOSYS when the topology is not visible (nothing is changed then).  Host-side plumbing of the
+ * copy path the reference does not have (its frames never leave system memory). */
+int ffv1b200_bind_thread_to_device(int device);
 
 /* ------------------------------------------------------------------ encoder */
 
@@ -135,6 +140,14 @@ int  ffv1b200_enc_encode_host(FFV1B200Encoder *enc, int nframes,
 int  ffv1b200_enc_submit_host(FFV1B200Encoder *enc, int nframes, const uint8_t *const *planes, const int *linesizes);
 int  ffv1b200_enc_collect(FFV1B200Encoder *enc, uint8_t *out, size_t out_cap, FFV1B200Packet *pkts, size_t *needed);
 int  ffv1b200_enc_pending(const FFV1B200Encoder *enc);      /* batches submitted and not yet collected (0..2) */
+/* collect without waiting for the packet BYTES: returns as soon as the batch is coded and its device->host copy has been
+ * queued; pkts[] (offsets, sizes, flags) is valid on return, the bytes in `out` are complete once the next
+ * ffv1b200_enc_collect* / ffv1b200_enc_sync_output / ffv1b200_enc_close call has returned.  With
+ *     submit(k+1); collect_async(k); submit(k+2); collect_async(k+1); ...
+ * the packets of batch k travel to the host while the frames of batch k+2 travel to the device (the link is full
+ * duplex) and batch k+1 is being coded. */
+int  ffv1b200_enc_collect_async(FFV1B200Encoder *enc, uint8_t *out, size_t out_cap, FFV1B200Packet *pkts, size_t *needed);
+int  ffv1b200_enc_sync_output(FFV1B200Encoder *enc);
 
 /* Same, for frames already resident in DEVICE memory (AV_PIX_FMT_CUDA AVFrames: data[i] are CUdeviceptr,
  * hwcontext_cuda.h:31-40).  Packets are produced in device memory (d_out, d_out_cap bytes); sizes/offsets are

@@ -41,6 +41,97 @@ def test_packets_match_oracle(B, case):
         if md5(b"".join(x.tobytes() for x in frames)) == gold["input_md5"]:
             assert [len(got[i][0]), md5(got[i][0])] == gold["packets"][i][:2]   # the reference build's own output
 
+# k_rangecode variants: launch_rangecode picks the coders per warp from the batch size (4, 8, 16 = the k_rangecode<16>
+# instantiation the 2048-frame bench runs, 32); each has its own shared-memory strides and ring offsets
+LANE_CASES = [c for c in CASES if c[0] in ("c1_cif_intra", "c2_gop_range_24sl", "c4_gbrp14_30sl", "range_def", "nocrc",
+                                           "yuva420p", "tiny_1slice", "v0_range", "range_flat")]
+
+@pytest.mark.parametrize("lanes", [1, 2, 8, 16, 32])
+@pytest.mark.parametrize("case", LANE_CASES, ids=[c[0] for c in LANE_CASES])
+def test_rangecode_lane_variants(B, case, lanes, monkeypatch):
+    cid, w, h, fmt, opts, kind, n = case
+    frames = make_frames(case)
+    o = O.Encoder(w, h, fmt, **opts)
+    monkeypatch.setenv("FFV1B200_RANGE_LANES", str(lanes))
+    g = B.FFV1Encoder(w, h, fmt, max_batch_frames=len(frames), **gpu_opts(opts))
+    got = g.encode_batch(frames)
+    for i, f in enumerate(frames):
+        exp, key = o.encode(f)
+        assert got[i][1] == key and got[i][0] == exp, "packet %d differs with %d coders per warp" % (i, lanes)
+
+def _s2_clip():
+    from oracle import synth
+    g0 = GOLD["s2_noisy1080_c2"]
+    gen = synth.Noisy(1920, 1080, "yuv420p", 1234)
+    frames = [gen.next() for _ in range(32)]
+    if md5(b"".join(f.tobytes() for f in frames)) != g0["input_md5"]:
+        pytest.skip("synthetic input differs from the fixture's")
+    return g0, frames
+
+@pytest.mark.parametrize("nframes,dec_per_sample", [(640, None), (96, "2.5")], ids=["640_frames_auto_lanes", "recover_small_regions"])
+def test_large_batch_against_reference_md5s(B, nframes, dec_per_sample, monkeypatch):
+    """The configuration bench.py times: one big batch of BASELINE configs[1] frames.  640 frames x 24 slices = 15360
+    coders makes launch_rangecode choose k_rangecode<16> by itself, k_replay_grp walks windows over 40 GOP segments per
+    slice, and (second case) decision regions sized for 2.5 entries per sample overflow on this clip (4.25 needed), so
+    the batch goes through recover().  The 32 golden frames are tiled; with GOP 16 packet k == golden packet k % 32
+    (the reference build's own sizes and MD5s)."""
+    g0, frames = _s2_clip()
+    if dec_per_sample:
+        monkeypatch.setenv("FFV1B200_DEC_PER_SAMPLE", dec_per_sample)
+    monkeypatch.delenv("FFV1B200_RANGE_LANES", raising=False)
+    enc = B.FFV1Encoder(1920, 1080, "yuv420p", g=16, level=3, coder=1, context=0, slices=24, max_batch_frames=nframes)
+    assert md5(enc.extradata) == g0["extradata_md5"]
+    tiled = [frames[i % 32] for i in range(nframes)]
+    table = enc.prepare(tiled)
+    enc.submit(table)
+    cap = nframes * (1920 * 1080 * 3 // 2)
+    out = np.empty(cap, np.uint8)
+    pk = enc.collect(out=out, copy=False)
+    st = enc.stats()
+    assert (st.retries > 0) == bool(dec_per_sample), "recover() %s" % ("was not exercised" if dec_per_sample else "ran unexpectedly")
+    for i in range(nframes):
+        b = out[pk[i].offset:pk[i].offset + pk[i].size]
+        assert [int(pk[i].size), md5(b), int(pk[i].flags & 1)] == g0["packets"][i % 32], "packet %d" % i
+
+SAR_CASES = [c for c in CASES if c[0] in ("c2_gop_range_24sl", "fate_ffv1_golomb", "c4_gbrp14_30sl", "v0_range")]
+
+@pytest.mark.parametrize("case", SAR_CASES, ids=[c[0] for c in SAR_CASES])
+def test_sar_and_field_order_in_slice_headers(B, case):
+    """sample_aspect_ratio and interlaced/top_field_first are coded into every slice header (ffv1enc.c:1044-1049):
+    batches with SAR 1:1, 4:3, TFF and BFF frames must match the oracle and -- where it is built -- the reference encoder.
+    The properties change between batches, including while an earlier batch is still in flight."""
+    cid, w, h, fmt, opts, kind, n = case
+    frames = make_frames(case)
+    props = [((1, 1), 3), ((4, 3), 1), ((16, 11), 2), ((0, 1), 3)]          # (sar, picture_structure) per batch
+    o = O.Encoder(w, h, fmt, **opts)
+    try:
+        from oracle import ffv1_ref
+        r = ffv1_ref.Encoder(w, h, fmt, **opts) if ffv1_ref.available() else None
+    except Exception:
+        r = None
+    g = B.FFV1Encoder(w, h, fmt, max_batch_frames=2, **gpu_opts(opts))
+    exp, got, k = [], [], 0
+    chunks = [frames[i:i + 2] for i in range(0, len(frames), 2)]
+    for ci, ch in enumerate(chunks):
+        sar, ps = props[ci % len(props)]
+        for f in ch:
+            e = o.encode(f, sar=sar, picture_structure=ps)
+            if r is not None:
+                assert r.encode(f, sar=sar, interlaced=int(ps != 3), tff=int(ps == 1)) == e, "oracle vs reference build, frame %d" % k
+            exp.append(e); k += 1
+        g.set_frame_props(sar=sar, picture_structure=ps)
+        g.submit(ch)                                      # up to two batches in flight, each with its own properties
+        if g.pending() == 2:
+            got += g.collect()
+    while g.pending():
+        got += g.collect()
+    assert len(got) == len(exp)
+    for i in range(len(exp)):
+        assert got[i] == exp[i], "packet %d (batch %d) differs" % (i, i // 2)
+    if opts.get("level", -1) not in (0, 1):              # versions 0/1 have no slice header
+        plain = O.Encoder(w, h, fmt, **opts).encode(frames[0])[0]
+        assert plain != exp[0][0], "the properties must change the packet bytes (else the test checks nothing)"
+
 @pytest.mark.parametrize("case", [c for c in CASES if c[0] in ("c2_gop_range_24sl", "c3_422p10_ctx1", "c4_gbrp14_30sl",
                                                               "bgra_range_ctx1", "yuv410p_odd", "fate_v3_444p16", "ya8")],
                          ids=lambda c: c[0])
