@@ -9,6 +9,9 @@
 #include <sched.h>
 #include <unistd.h>
 #include <sys/syscall.h>
+#include <sys/mman.h>
+#include <map>
+#include <mutex>
 
 namespace ffv1 {
 static thread_local std::string g_last_error;
@@ -57,6 +60,71 @@ int ffv1b200_device_count(void)
     return n;
 }
 
+static int numa_node_of_device(int device, char *bdf_out)
+{
+    char bdf[32] = {0};
+    if (cudaDeviceGetPCIBusId(bdf, sizeof(bdf), device) != cudaSuccess) { cudaGetLastError(); return -2; }
+    for (char *q = bdf; *q; q++) if (*q >= 'A' && *q <= 'F') *q += 'a' - 'A';
+    if (bdf_out) memcpy(bdf_out, bdf, sizeof(bdf));
+    char path[128];
+    snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bdf);
+    int node = -1;
+    if (FILE *fh = fopen(path, "r")) { if (fscanf(fh, "%d", &node) != 1) node = -1; fclose(fh); }
+    return node;
+}
+
+// Pinned host memory for frame / packet staging, placed on the device's NUMA node when the topology is visible (the
+// pages are bound before they are first touched, then registered with CUDA), without touching the caller's affinity.
+static std::mutex g_host_mu;
+static std::map<void *, size_t> g_host_allocs;
+
+void *ffv1b200_host_alloc(size_t bytes, int device)
+{
+    if (!bytes) bytes = 1;
+    const size_t page = (size_t)sysconf(_SC_PAGESIZE);
+    bytes = (bytes + page - 1) / page * page;
+    void *p = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    if (p == MAP_FAILED) { ffv1::set_last_error("mmap failed"); return nullptr; }
+#ifdef SYS_mbind
+    const int node = numa_node_of_device(device, nullptr);
+    if (node >= 0 && node < 1024) {
+        unsigned long mask[16] = {0};
+        mask[node / (8 * sizeof(unsigned long))] |= 1ul << (node % (8 * sizeof(unsigned long)));
+        syscall(SYS_mbind, p, bytes, 1 /* MPOL_PREFERRED */, mask, 1024ul + 1ul, 0u);      // best effort
+    }
+#endif
+    int cur = -1;
+    cudaGetDevice(&cur);
+    if (device >= 0 && cur != device) cudaSetDevice(device);
+    cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable);
+    if (device >= 0 && cur >= 0 && cur != device) cudaSetDevice(cur);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        munmap(p, bytes);
+        ffv1::set_last_error(std::string("cudaHostRegister: ") + cudaGetErrorString(e));
+        return nullptr;
+    }
+    std::lock_guard<std::mutex> g(g_host_mu);
+    g_host_allocs[p] = bytes;
+    return p;
+}
+
+void ffv1b200_host_free(void *p)
+{
+    if (!p) return;
+    size_t bytes = 0;
+    {
+        std::lock_guard<std::mutex> g(g_host_mu);
+        auto it = g_host_allocs.find(p);
+        if (it == g_host_allocs.end()) return;
+        bytes = it->second;
+        g_host_allocs.erase(it);
+    }
+    cudaHostUnregister(p);
+    cudaGetLastError();
+    munmap(p, bytes);
+}
+
 // Host side of the copy path: the staging buffers of a GPU should live on the NUMA node its PCIe root port hangs off, and
 // the thread that fills / submits them should run there.  Reads the node from sysfs, pins the calling thread to the
 // node's CPUs and makes the node the preferred one for the thread's future allocations (pinned buffers included: they
@@ -65,16 +133,9 @@ int ffv1b200_device_count(void)
 int ffv1b200_bind_thread_to_device(int device)
 {
     char bdf[32] = {0};
-    if (cudaDeviceGetPCIBusId(bdf, sizeof(bdf), device) != cudaSuccess) {
-        cudaGetLastError();
-        ffv1::set_last_error("no such CUDA device");
-        return FFV1B200_ERR_EINVAL;
-    }
-    for (char *q = bdf; *q; q++) if (*q >= 'A' && *q <= 'F') *q += 'a' - 'A';
     char path[128];
-    snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bdf);
-    int node = -1;
-    if (FILE *fh = fopen(path, "r")) { if (fscanf(fh, "%d", &node) != 1) node = -1; fclose(fh); }
+    const int node = numa_node_of_device(device, bdf);
+    if (node == -2) { ffv1::set_last_error("no such CUDA device"); return FFV1B200_ERR_EINVAL; }
     if (node < 0) { ffv1::set_last_error(std::string("NUMA node of ") + bdf + " not visible"); return FFV1B200_ERR_ENOSYS; }
     snprintf(path, sizeof(path), "/sys/devices/system/node/node%d/cpulist", node);
     FILE *fh = fopen(path, "r");

@@ -82,6 +82,7 @@ struct FFV1B200Encoder {
     int max_plane_width = 0, num_sms = 148, max_ctile_samples = 0;
     FFV1B200EncStats stats{};
     int last_slot = 0;
+    int cuda_pending = 0;            // frames of a batch that ffv1b200_enc_encode_cuda has coded but could not hand out
 };
 
 namespace {
@@ -693,21 +694,33 @@ int ffv1b200_enc_encode_cuda(FFV1B200Encoder *e, int nframes, const void *const 
     if (!e || !out || !pkts) return fail(FFV1B200_ERR_EINVAL, "null argument");
     if (e->submitted != e->collected) return fail(FFV1B200_ERR_EINVAL, "collect the batches in flight first");
     CU_TRY(cudaSetDevice(e->device));
-    Slot &sl = e->slot[e->submitted % kSlots];
-    if (!sl.d_out.p) CU_TRY(sl.d_out.alloc((size_t)e->max_batch * ((size_t)e->cfg.frame_bytes() / 2 + 65536)));
+    { int q = finish_output(e); if (q < 0) return q; }
     size_t total = 0;
     int r;
-    for (;;) {                                                  // the packets are assembled in the slot's own device buffer
-        r = ffv1b200_enc_encode_device(e, nframes, d_planes, linesizes, sl.d_out.p, sl.d_out.n, pkts, &total, nullptr);
-        if (r != FFV1B200_ERR_BUFFER_TOO_SMALL) break;
-        CU_TRY(sl.d_out.alloc(total + 4096));
+    if (e->cuda_pending) {
+        // the previous call coded this batch but the caller's buffer was too small: only the hand-out is repeated
+        if (nframes != e->cuda_pending) return fail(FFV1B200_ERR_EINVAL, "repeat the call that returned BUFFER_TOO_SMALL first");
+        Slot &sl = e->slot[e->last_slot];
+        total = (size_t)sl.h_pkt_off.p[sl.nframes];
+        fill_packets(sl, pkts);
+        r = nframes;
+    } else {
+        Slot &sl = e->slot[e->submitted % kSlots];
+        if (!sl.d_out.p) CU_TRY(sl.d_out.alloc((size_t)e->max_batch * ((size_t)e->cfg.frame_bytes() / 2 + 65536)));
+        for (;;) {                                              // the packets are assembled in the slot's own device buffer
+            r = ffv1b200_enc_encode_device(e, nframes, d_planes, linesizes, sl.d_out.p, sl.d_out.n, pkts, &total, nullptr);
+            if (r != FFV1B200_ERR_BUFFER_TOO_SMALL) break;
+            CU_TRY(sl.d_out.alloc(total + 4096));
+        }
+        if (r < 0) return r;
     }
-    if (r < 0) return r;
+    Slot &sl = e->slot[e->last_slot];
     if (needed) *needed = total;
     if (total > out_cap) {
-        // the batch is coded (the model state has moved on): the caller sized `out` from FFV1B200EncInfo.frame_bytes
+        e->cuda_pending = nframes;                              // coded; the same call with a larger buffer hands it out
         return fail(FFV1B200_ERR_BUFFER_TOO_SMALL, "output buffer too small: need " + std::to_string(total) + " bytes");
     }
+    e->cuda_pending = 0;
     CU_TRY(cudaMemcpyAsync(out, sl.d_out.p, total, cudaMemcpyDeviceToHost, e->s_out));
     CU_TRY(cudaStreamSynchronize(e->s_out));
     e->stats.d2h_bytes += (int64_t)total;

@@ -102,6 +102,11 @@ int ffv1b200_device_count(void);
  * node, or FFV1B200_ERR_ENOSYS when the topology is not visible (nothing is changed then).  Host-side plumbing of the
  * copy path the reference does not have (its frames never leave system memory). */
 int ffv1b200_bind_thread_to_device(int device);
+/* Pinned (page-locked) host memory for frames / packets that a device is fed from or writes to, placed on the device's
+ * NUMA node where the topology is visible; NULL on failure.  Any host memory works with the *_host calls -- pinned memory
+ * lets their copies run asynchronously at full link speed. */
+void *ffv1b200_host_alloc(size_t bytes, int device);
+void  ffv1b200_host_free(void *p);
 
 /* ------------------------------------------------------------------ encoder */
 
@@ -159,7 +164,9 @@ int  ffv1b200_enc_encode_device(FFV1B200Encoder *enc, int nframes,
 
 /* AV_PIX_FMT_CUDA frames in, packets out to HOST memory: what an AVCodec.encode2 needs when avctx->pix_fmt is
  * AV_PIX_FMT_CUDA (frame->data[i] = CUdeviceptr, sw_format from avctx->hw_frames_ctx; nvenc's use of the same frames:
- * libavcodec/nvenc.c:1162-1170).  Same packets as ffv1b200_enc_encode_host on the same pixels. */
+ * libavcodec/nvenc.c:1162-1170).  Same packets as ffv1b200_enc_encode_host on the same pixels.
+ * FFV1B200_ERR_BUFFER_TOO_SMALL (*needed = size): the batch IS coded; repeat the call with the same nframes and a larger
+ * buffer to receive it (nothing is coded twice). */
 int  ffv1b200_enc_encode_cuda(FFV1B200Encoder *enc, int nframes,
                               const void *const *d_planes, const int *linesizes,
                               uint8_t *out, size_t out_cap, FFV1B200Packet *pkts, size_t *needed);

@@ -228,6 +228,17 @@ void *ffv1ref_dec_open_named(const char *name, int w, int h, const uint8_t *extr
     return dec_open_impl(codec, w, h, extradata, extradata_size, 1, 0);
 }
 
+/* private options of the named decoder ("batch=8:gpu=0") applied before avcodec_open2 */
+static const char *g_dec_extra_opts;
+void *ffv1ref_dec_open_named_opts(const char *name, int w, int h, const uint8_t *extradata, int extradata_size, const char *extra_opts)
+{
+    void *r;
+    g_dec_extra_opts = extra_opts;
+    r = ffv1ref_dec_open_named(name, w, h, extradata, extradata_size);
+    g_dec_extra_opts = NULL;
+    return r;
+}
+
 static void *dec_open_impl(AVCodec *codec, int w, int h, const uint8_t *extradata, int extradata_size, int threads, int frame_threads)
 {
     RefDec *d = calloc(1, sizeof(*d));
@@ -241,7 +252,8 @@ static void *dec_open_impl(AVCodec *codec, int w, int h, const uint8_t *extradat
     d->ctx->flags |= AV_CODEC_FLAG_BITEXACT;
     d->ctx->thread_count = threads > 1 ? threads : 1;
     if (threads > 1) d->ctx->thread_type = frame_threads ? FF_THREAD_FRAME : FF_THREAD_SLICE;
-    if (avcodec_open2(d->ctx, codec, NULL) < 0) {
+    if ((g_dec_extra_opts && *g_dec_extra_opts && av_set_options_string(d->ctx->priv_data, g_dec_extra_opts, "=", ":") < 0) ||
+        avcodec_open2(d->ctx, codec, NULL) < 0) {
         avcodec_free_context(&d->ctx); free(d); return NULL;
     }
     d->frame = av_frame_alloc();
@@ -280,6 +292,133 @@ void ffv1ref_dec_close(void *h)
     avcodec_close(d->ctx);
     avcodec_free_context(&d->ctx);
     free(d);
+}
+
+/* ---- throughput of an encoder through the public API (bench.py "e2e_avcodec"): `nframes` frames, taken round-robin from
+ * `clip` (nclip tightly packed frames in pageable memory, wrapped as refcounted AVFrames WITHOUT copying, the way ffmpeg.c
+ * hands rawvideo frames on), go through avcodec_encode_video2 of the named codec; the packets are dropped except the last
+ * `nkeep`, which are copied to `keep` (sizes in keep_size, key flags in keep_key) for the caller's parity check.  Returns
+ * the seconds from the first frame to the last drained packet (open/close excluded), < 0 on error. */
+#include <time.h>
+static void noop_free(void *opaque, uint8_t *data) { (void)opaque; (void)data; }
+double ffv1ref_bench_encode(const char *name, int w, int h, const char *pix_fmt, int gop, int level, int coder, int context,
+                            int slices, int slicecrc, int threads, const char *extra_opts,
+                            const uint8_t *clip, int nclip, int nframes,
+                            uint8_t *keep, int64_t keep_cap, int nkeep, int *keep_size, int *keep_key, int64_t *total_bytes)
+{
+    reg();
+    AVCodec *codec = avcodec_find_encoder_by_name(name);
+    if (!codec) return -1;
+    RefEnc *e = enc_open_impl(codec, w, h, pix_fmt, gop, level, coder, context, slices, slicecrc, threads, 0, 0);
+    /* (private options of the codec under test, "key=value:key=value", are applied before avcodec_open2 by reopening) */
+    if (!e) return -2;
+    if (extra_opts && *extra_opts) {
+        avcodec_close(e->ctx); avcodec_free_context(&e->ctx); av_frame_free(&e->frame); free(e);
+        enum AVPixelFormat pf = av_get_pix_fmt(pix_fmt);
+        e = calloc(1, sizeof(*e));
+        e->ctx = avcodec_alloc_context3(codec);
+        e->ctx->width = w; e->ctx->height = h; e->ctx->pix_fmt = pf; e->ctx->time_base = (AVRational){1, 25};
+        e->ctx->gop_size = gop; e->ctx->level = level; e->ctx->slices = slices; e->ctx->flags |= AV_CODEC_FLAG_BITEXACT;
+        if (threads > 1) { e->ctx->thread_count = threads; e->ctx->thread_type = FF_THREAD_SLICE; } else e->ctx->thread_count = 1;
+        av_opt_set_int(e->ctx->priv_data, "coder", coder, 0);
+        av_opt_set_int(e->ctx->priv_data, "context", context, 0);
+        av_opt_set_int(e->ctx->priv_data, "slicecrc", slicecrc, 0);
+        if (av_set_options_string(e->ctx->priv_data, extra_opts, "=", ":") < 0 || avcodec_open2(e->ctx, codec, NULL) < 0) {
+            avcodec_free_context(&e->ctx); free(e); return -3;
+        }
+        e->frame = av_frame_alloc();
+    }
+    const enum AVPixelFormat pf = e->ctx->pix_fmt;
+    const int fb = av_image_get_buffer_size(pf, w, h, 1);
+    int64_t bytes = 0, kept = 0;
+    int npk = 0, i, ret = 0, got;
+    struct timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    for (i = 0; ; i++) {
+        AVPacket pkt;
+        AVFrame *f = NULL;
+        av_init_packet(&pkt); pkt.data = NULL; pkt.size = 0;
+        if (i < nframes) {
+            f = e->frame;
+            av_frame_unref(f);
+            f->format = pf; f->width = w; f->height = h;
+            av_image_fill_arrays(f->data, f->linesize, clip + (size_t)(i % nclip) * fb, pf, w, h, 1);
+            f->buf[0] = av_buffer_create((uint8_t *)clip + (size_t)(i % nclip) * fb, fb, noop_free, NULL, AV_BUFFER_FLAG_READONLY);
+            f->pts = i;
+            f->sample_aspect_ratio = (AVRational){0, 1};
+        }
+        ret = avcodec_encode_video2(e->ctx, &pkt, f, &got);
+        if (ret < 0) break;
+        if (got) {
+            if (npk >= nframes - nkeep && kept + pkt.size <= keep_cap) {
+                const int k = npk - (nframes - nkeep);
+                memcpy(keep + kept, pkt.data, pkt.size);
+                keep_size[k] = pkt.size; keep_key[k] = !!(pkt.flags & AV_PKT_FLAG_KEY);
+                kept += pkt.size;
+            }
+            bytes += pkt.size; npk++;
+            av_packet_unref(&pkt);
+        } else if (i >= nframes) break;                      /* drained */
+    }
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    if (total_bytes) *total_bytes = bytes;
+    ffv1ref_enc_close(e);
+    if (ret < 0) return ret;
+    if (npk != nframes) return -4;
+    return (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
+}
+
+/* same for a decoder: npk packets (pkt[i], size[i]) through avcodec_decode_video2, pictures dropped except the last, which
+ * is copied tightly packed to `last` (cap bytes).  Returns seconds, < 0 on error; *nframes_out = pictures received. */
+double ffv1ref_bench_decode(const char *name, int w, int h, const uint8_t *extradata, int extradata_size, int threads,
+                            int frame_threads, const char *extra_opts, const uint8_t *const *pkt, const int *size, int npk,
+                            uint8_t *last, int cap, int *nframes_out)
+{
+    reg();
+    AVCodec *codec = avcodec_find_decoder_by_name(name);
+    if (!codec) return -1;
+    RefDec *d = calloc(1, sizeof(*d));
+    d->ctx = avcodec_alloc_context3(codec);
+    d->ctx->width = w; d->ctx->height = h;
+    if (extradata_size > 0) {
+        d->ctx->extradata = av_mallocz(extradata_size + AV_INPUT_BUFFER_PADDING_SIZE);
+        memcpy(d->ctx->extradata, extradata, extradata_size);
+        d->ctx->extradata_size = extradata_size;
+    }
+    d->ctx->flags |= AV_CODEC_FLAG_BITEXACT;
+    d->ctx->thread_count = threads > 1 ? threads : 1;
+    if (threads > 1) d->ctx->thread_type = frame_threads ? FF_THREAD_FRAME : FF_THREAD_SLICE;
+    if ((extra_opts && *extra_opts && av_set_options_string(d->ctx->priv_data, extra_opts, "=", ":") < 0) ||
+        avcodec_open2(d->ctx, codec, NULL) < 0) { avcodec_free_context(&d->ctx); free(d); return -3; }
+    d->frame = av_frame_alloc();
+    /* packets with the padding lavc asks for, prepared outside the timed region */
+    int maxsz = 0, i, ret = 0, got, nout = 0;
+    for (i = 0; i < npk; i++) if (size[i] > maxsz) maxsz = size[i];
+    uint8_t **padded = calloc(npk, sizeof(*padded));
+    for (i = 0; i < npk; i++) { padded[i] = av_mallocz(size[i] + AV_INPUT_BUFFER_PADDING_SIZE); memcpy(padded[i], pkt[i], size[i]); }
+    struct timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    for (i = 0; ; i++) {
+        AVPacket p;
+        av_init_packet(&p);
+        p.data = i < npk ? padded[i] : NULL; p.size = i < npk ? size[i] : 0; p.pts = p.dts = i;
+        ret = avcodec_decode_video2(d->ctx, d->frame, &got, &p);
+        if (ret < 0) break;
+        if (got) {
+            nout++;
+            if (nout == npk && last)
+                av_image_copy_to_buffer(last, cap, (const uint8_t *const *)d->frame->data, d->frame->linesize,
+                                        d->frame->format, d->frame->width, d->frame->height, 1);
+            av_frame_unref(d->frame);
+        } else if (i >= npk) break;
+    }
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    for (i = 0; i < npk; i++) av_free(padded[i]);
+    free(padded);
+    if (nframes_out) *nframes_out = nout;
+    ffv1ref_dec_close(d);
+    if (ret < 0) return ret;
+    return (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
 }
 
 /* CRC helper so tests can pin libavutil's AV_CRC_32_IEEE convention (crc.c:357-380). */

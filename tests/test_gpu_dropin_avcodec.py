@@ -30,7 +30,8 @@ def lavc():
     L.ffv1ref_dec_open_named.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
     return L
 
-def encode_named(L, name, case, batch):
+def encode_named(L, name, case, batch, props=None):
+    """props: optional function frame index -> (sar_num, sar_den, interlaced, top_field_first)"""
     cid, w, h, fmt, opts, kind, n = case
     o = dict(gop=12, level=-1, coder=0, context=0, slices=0, slicecrc=-1); o.update(opts)
     hnd = L.ffv1ref_enc_open_named(name.encode(), w, h, fmt.encode(), o["gop"], o["level"], o["coder"], o["context"],
@@ -42,10 +43,11 @@ def encode_named(L, name, case, batch):
     buf = ctypes.create_string_buffer(cap)
     key = ctypes.c_int()
     pkts = []
-    for f in make_frames(case):
+    for fi, f in enumerate(make_frames(case)):
         planes = split_planes(np.ascontiguousarray(f).view(np.uint8).reshape(-1), fmt, w, h)
         ptrs, strides = _plane_args(planes)
-        r = L.ffv1ref_enc_frame(hnd, ptrs, strides, 0, 1, 0, 0, buf, cap, ctypes.byref(key))
+        sn, sd, il, tff = props(fi) if props else (0, 1, 0, 0)
+        r = L.ffv1ref_enc_frame(hnd, ptrs, strides, sn, sd, il, tff, buf, cap, ctypes.byref(key))
         assert r >= 0
         if r:
             pkts.append((buf.raw[:r], bool(key.value)))
@@ -70,6 +72,69 @@ def test_same_packets_through_avcodec_api(lavc, case):
     for i, (a, b) in enumerate(zip(our_pkts, ref_pkts)):
         assert a[1] == b[1], "AV_PKT_FLAG_KEY of packet %d" % i
         assert a[0] == b[0], "packet %d differs from the reference encoder's" % i
+
+PROPS = [(1, 1, 0, 0), (1, 1, 0, 0), (4, 3, 1, 1), (4, 3, 1, 1), (4, 3, 1, 0), (0, 1, 0, 0), (16, 11, 0, 0), (16, 11, 1, 1)]
+
+@pytest.mark.parametrize("cid,batch", [("fate_ffv1_golomb", 5), ("fate_ffv1_golomb", 3), ("c2_gop_range_24sl", 4), ("c2_gop_range_24sl", 2),
+                                       ("c4_gbrp14_30sl", 2)])
+def test_sar_and_field_order_change_mid_stream(lavc, cid, batch):
+    """AVFrame.sample_aspect_ratio / interlaced_frame / top_field_first change while frames are queued and while packets of
+    earlier batches are still being handed out (ffv1enc.c:1044-1049 codes them per frame): same packets as the reference"""
+    case = [c for c in CASES if c[0] == cid][0]
+    pr = lambda i: PROPS[i % len(PROPS)]
+    ref_ed, ref_pkts = encode_named(lavc, "ffv1", case, 0, pr)
+    our_ed, our_pkts = encode_named(lavc, "ffv1_b200", case, batch, pr)
+    plain = encode_named(lavc, "ffv1", case, 0)[1]
+    assert plain[0][0] != ref_pkts[0][0], "the properties must change the bytes"
+    assert our_ed == ref_ed and len(our_pkts) == len(ref_pkts) == case[6]
+    for i, (a, b) in enumerate(zip(our_pkts, ref_pkts)):
+        assert a == b, "packet %d differs from the reference encoder's" % i
+
+@pytest.mark.parametrize("batch", [1, 4, 64])
+def test_batched_decode_through_avcodec_api(lavc, batch):
+    """the decoder's "batch" option: pictures come out batch-1 calls late and the rest on the drain (AV_CODEC_CAP_DELAY)"""
+    case = [c for c in CASES if c[0] == "fate_ffv1_golomb"][0]
+    cid, w, h, fmt, opts, kind, n = case
+    ed, pkts = encode_named(lavc, "ffv1", case, 0)
+    lavc.ffv1ref_dec_open_named_opts.restype = ctypes.c_void_p
+    lavc.ffv1ref_dec_open_named_opts.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_char_p]
+    hnd = lavc.ffv1ref_dec_open_named_opts(b"ffv1_b200", w, h, ed, len(ed), ("batch=%d" % batch).encode())
+    assert hnd
+    cap = w * h * 8 + 64
+    out = np.zeros(cap, np.uint8); name = ctypes.create_string_buffer(32); key = ctypes.c_int()
+    frames = [np.ascontiguousarray(f).view(np.uint8).reshape(-1) for f in make_frames(case)]
+    got = []
+    for i in range(n):
+        r = lavc.ffv1ref_dec_packet(hnd, pkts[i][0], len(pkts[i][0]), out.ctypes.data, cap, name, ctypes.byref(key))
+        assert r >= 0
+        if r:
+            got.append((out[:r].copy(), bool(key.value)))
+    assert len(got) == (n - (batch - 1) if n >= batch else 0)
+    while True:
+        r = lavc.ffv1ref_dec_packet(hnd, b"", 0, out.ctypes.data, cap, name, ctypes.byref(key))
+        assert r >= 0
+        if not r:
+            break
+        got.append((out[:r].copy(), bool(key.value)))
+    lavc.ffv1ref_dec_close(hnd)
+    assert len(got) == n
+    for i in range(n):
+        assert got[i][1] == pkts[i][1] and np.array_equal(got[i][0], frames[i]), "picture %d" % i
+
+def test_bench_harness_loop_gives_the_same_packets(lavc):
+    """tools/bench_avcodec.py's loop (zero-copy AVFrames, worker-thread staging, pipelined batches): packets of -c:v ffv1_b200
+    == packets of -c:v ffv1 on a tiled clip, including batches that end inside a GOP"""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import bench_avcodec as A
+    case = [c for c in CASES if c[0] == "c2_gop_range_24sl"][0]
+    cid, w, h, fmt, opts, kind, n = case
+    clip = np.stack([np.ascontiguousarray(f).view(np.uint8).reshape(-1) for f in make_frames(case)])
+    o = dict(opts); gop = o.pop("gop")
+    _, nb_ref, ref = A.encode("ffv1", clip, w, h, fmt, 50, gop, o, nkeep=50)
+    for extra in ("batch=7:copy_threads=3", "batch=16:copy_threads=0", "batch=64:copy_threads=8"):
+        _, nb, got = A.encode("ffv1_b200", clip, w, h, fmt, 50, gop, o, extra=extra, nkeep=50)
+        assert nb == nb_ref and got == ref, extra
 
 def test_decode_through_avcodec_api(lavc):
     case = [c for c in CASES if c[0] == "c2_gop_range_24sl"][0]
