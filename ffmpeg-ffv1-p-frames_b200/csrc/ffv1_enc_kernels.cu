@@ -489,121 +489,91 @@ void launch_replay(const EncDeviceTables &t, const EncBatch &b, cudaStream_t s)
 // =================================================================================================
 // k_rangecode: one interval coder per (frame, slice); put_rac / renorm_encoder / ff_rac_terminate
 // (rangecoder.h:52-102, rangecoder.c:104-116).  The adaptive part already happened in the state replay, so a step is
-// range1 = range*p >> 8 plus the carry-propagating byte output.
+// range1 = range*p >> 8, the interval update and the renormalisation.
 // =================================================================================================
-// Every lane of a warp runs its own coder, and the warp stays converged: the hot loop has no data-dependent branch
-// except two rare ones (a 0xFF byte waiting for its carry, the end of a run of decisions).
+// Every lane of a warp runs its own coder and the warp NEVER diverges inside the decision loop:
+//  * Carry-free output.  renorm_encoder delays bytes (outstanding_byte / outstanding_count) because a later carry may
+//    still increment them.  Here a renormalisation emits the 9-bit value low >> 8 (byte + carry bit 16 of low) as a
+//    16-bit entry and moves on; the carries are added up afterwards, in parallel, by the packet-assembly kernel
+//    (byte k = (v[k] + carry out of v[k+1..]) & 0xFF, a carry-lookahead over generate = v >> 8 and propagate =
+//    (v & 0xFF) == 0xFF; see pack_resolved_be).  The bytes are the reference's: its delayed writes perform exactly this
+//    addition, and the entry of the last renormalisation (what would stay in outstanding_byte for ever) is dropped
+//    like ff_rac_terminate drops it.  No "0xFF byte waits for its carry" path is left: a decision is 12 straight-line
+//    instructions, split between the FMA pipe (mul.hi, subtract, add, shifts as mad) and the ALU pipe (select,
+//    compares, permutes) -- each pipe takes a warp instruction every other cycle, so the mix is what sets the speed.
 //  * The decision stream of a lane is produced by a small generator (prefix | runs of its slice | closing decision) that
-//    runs four 16-byte vectors ahead of the coder, across run boundaries, so the coder never waits for a run switch.
+//    runs chunks of eight 16-byte vectors ahead of the coder through cp.async, across run boundaries.
 //  * A vector holds 8 decisions; entries behind the end of a run are replaced by 0x0000, which is an exact no-op for
 //    the coder (p = 0, bit = 0: range1 = 0, nothing moves, no renormalisation; real states are 1..255).
-//  * Carry handling follows renorm_encoder (rangecoder.h:52-75) with one simplification that keeps the output identical:
-//    instead of a "no outstanding byte yet" state the coder starts with a dummy outstanding byte that lands in byte
-//    kScratchLead-1 of the slice's scratch region and is never read back (a carry into it is harmless), so the payload
-//    starts at byte kScratchLead.  In the common case a renormalisation emits exactly one byte (outstanding byte +
-//    carry); bytes are shifted into a 32-bit word and stored four at a time.
+//  * Output entries go through a per-lane ring in shared memory laid out [row][lane] (a lane always hits its own bank:
+//    no conflicts whatever the lanes' positions) and leave as 16-byte stores of 8 entries.
+constexpr int kRingRows = 32;             // entries per lane
+constexpr uint32_t kRowUnit = 1u << 27;   // ring positions are kept as row << 27: they wrap around the 32 rows by themselves
+
 struct Rac {
     uint32_t low, range;
-    uint32_t out_byte;   // outstanding byte (its final value depends on a carry that may still arrive)
-    uint32_t out_count;  // 0xFF bytes behind it that a carry would turn into 0x00
-    uint32_t thr;        // 0xFE, or 0xFFFFFFFF while out_count != 0 (see rac_code)
-    uint32_t pos;        // bytes produced (incl. the kScratchLead lead-in)
-    uint32_t fl;         // bytes already moved from the lane's ring to the scratch region (multiple of 16)
-    uint32_t ring;       // shared-memory address of the lane's 32-byte ring: byte i of the stream sits at ring + (i & 31)
-    uint32_t cap;
-    uint8_t *out;        // the slice's scratch region (256-byte aligned)
+    uint32_t posx;       // (entries produced mod 32) << 27
+    uint32_t flx;        // (entries moved from the ring to the scratch region mod 32) << 27; whole groups of 8
+    uint32_t nfl;        // entries moved to the scratch region
+    uint32_t ring;       // shared-memory address of the lane's column of the ring
+    uint32_t cap;        // entries the slice's scratch region holds
+    uint16_t *out;       // the slice's scratch region (256-byte aligned), 16-bit entries
 };
 
-__device__ __forceinline__ void rac_flush16(Rac &c)       // one finished 16-byte block: ring -> scratch region
-{
-    uint4 v;
-    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(c.ring + (c.fl & 16u)));
-    if (c.fl + 16u <= c.cap) *reinterpret_cast<uint4 *>(c.out + c.fl) = v;
-    c.fl += 16u;
-}
-
-// the same, predicated (no branch: the lanes of a warp fill their rings at different times): moves a block once the
-// lane has 16 or more bytes waiting
-__device__ __forceinline__ void rac_flush16_if_full(Rac &c)
-{
-    const uint32_t full = (c.pos - c.fl >= 16u) ? 1u : 0u;
-    const uint32_t st = (full && c.fl + 16u <= c.cap) ? 1u : 0u;
-    asm volatile("{\n\t.reg .pred f, s;\n\t.reg .u32 a, b, c, d;\n\t"
-        "setp.ne.u32 f, %2, 0;\n\t"
-        "setp.ne.u32 s, %3, 0;\n\t"
-        "@f ld.shared.v4.u32 {a, b, c, d}, [%1];\n\t"
-        "@s st.global.v4.u32 [%0], {a, b, c, d};\n\t}"
-        :: "l"(c.out + c.fl), "r"(c.ring + (c.fl & 16u)), "r"(full), "r"(st) : "memory");
-    c.fl += full << 4;
-}
-
-// the uncommon renormalisations (renorm_encoder, rangecoder.h:52-75): a 0xFF byte that has to wait for its carry, or
-// the byte that resolves such a wait.  Out of line on purpose (all state by value, so it stays in registers): as a
-// call, the straight-line path of k_rangecode does not have to jump over this code.
-struct RacOut { uint32_t out_byte, out_count, pos, fl; };
-
-__device__ __noinline__ RacOut rac_output_slow(uint32_t low, uint32_t out_byte, uint32_t out_count, uint32_t pos, uint32_t fl,
-                                               uint32_t ring, uint32_t cap, uint8_t *out)
-{
-    RacOut o;
-    o.out_byte = out_byte; o.out_count = out_count + 1u; o.pos = pos; o.fl = fl;
-    if (low - 0xFF01u < 0xFFu) return o;                  // 0xFF00 < low < 0x10000: wait for the carry
-    Rac c;
-    c.pos = pos; c.fl = fl; c.ring = ring; c.cap = cap; c.out = out;
-    const uint32_t carry = low >> 16;
-    const uint32_t fill = carry ? 0x00u : 0xFFu;
-    uint32_t b = out_byte + carry;
-#pragma unroll 1
-    for (uint32_t i = 0; i <= out_count; i++) {
-        asm volatile("st.shared.u8 [%0], %1;" :: "r"(c.ring + (c.pos & 31u)), "r"(b) : "memory");
-        c.pos++;
-        if (c.pos - c.fl >= 16u) rac_flush16(c);
-        b = fill;
-    }
-    o.out_byte = (low >> 8) & 0xFFu; o.out_count = 0u; o.pos = c.pos; o.fl = c.fl;
-    return o;
-}
-
 // put_rac (rangecoder.h:85-102) for one decision (p24 = probability state << 24, one = coded bit, any non-zero value)
-// and the byte output of its renormalisation.  The common case of the latter -- exactly one byte, the outstanding byte
-// plus the carry -- is predicated, not branched, so the 32 coders of a warp stay converged; only a 0xFF byte that has
-// to wait for its carry (about one renormalisation in 128) leaves the straight line.
-__device__ __forceinline__ void rac_code(Rac &c, uint32_t p24, uint32_t one)
+// and its renormalisation.  p >= 1 and range >= 0x100 before: at most one shift.  What is stored is low >> 8 (9
+// significant bits) from a register of its own: `low` is rewritten right behind the store.  rowmul = bytes between two rows of the ring * 32: the address of
+// row (posx >> 27) is ring + ((posx * rowmul) >> 32), one mad.hi on the FMA pipe.
+template <uint32_t ROWMUL>
+__device__ __forceinline__ void rac_code(Rac &c, uint32_t p24, uint32_t one, uint32_t rowmul_rt)
 {
-    uint32_t t, slow;
-    // 17 instructions: the "wait" test (byte 0xFF with no carry yet, or 0xFF bytes already waiting) is one two-output
-    // setp against c.thr (0xFE, or 0xFFFFFFFF while bytes wait), everything that reads `low` comes before its shift
-    asm volatile("{\n\t.reg .pred one, sh, s, f;\n\t.reg .u32 r1, r0, cy, b, a;\n\t"
-        "mul.hi.u32 r1, %1, %7;\n\t"                        // (range * p) >> 8
-        "sub.u32 r0, %1, r1;\n\t"
-        "setp.ne.u32 one, %8, 0;\n\t"
+    const uint32_t rowmul = ROWMUL ? ROWMUL : rowmul_rt;
+    asm volatile("{\n\t.reg .pred one, sh;\n\t.reg .u32 r1, r0, a, b;\n\t"
+        "mul.hi.u32 r1, %1, %3;\n\t"                        // (range * p) >> 8
+        "mad.lo.u32 r0, r1, 0xFFFFFFFF, %1;\n\t"            // range - range1
+        "setp.ne.u32 one, %4, 0;\n\t"
         "selp.u32 %1, r1, r0, one;\n\t"
-        "@one add.u32 %0, %0, r0;\n\t"
-        "setp.lt.u32 sh, %1, 0x100;\n\t"                    // p >= 1 and range >= 0x100 before: at most one shift
-        "sub.u32 %4, %0, 0xFF01;\n\t"                       // 0xFF01 <= low <= 0xFFFF: the byte is 0xFF and a carry may still flip it
-        "setp.le.and.u32 s|f, %4, %6, sh;\n\t"              // s: leave the straight line; f: emit outstanding byte + carry
-        "selp.u32 %5, 1, 0, s;\n\t"
-        "shr.u32 cy, %0, 16;\n\t"
-        "add.u32 b, %2, cy;\n\t"                            // outstanding byte + carry
-        "lop3.b32 a, %3, 31, %9, 0xEA;\n\t"                 // ring | (pos & 31)
-        "@f st.shared.u8 [a], b;\n\t"
-        "@f add.u32 %3, %3, 1;\n\t"
-        "@f prmt.b32 %2, %0, 0, 0x4441;\n\t"                // outstanding byte = (low >> 8) & 0xFF
-        "@sh shl.b32 %1, %1, 8;\n\t"
+        "@one mad.lo.u32 %0, r0, 1, %0;\n\t"                // low += range - range1
+        "setp.lt.u32 sh, %1, 0x100;\n\t"
+        "mad.hi.u32 a, %2, %6, %5;\n\t"                     // ring + row * row pitch
+        "shr.u32 b, %0, 8;\n\t"
+        "@sh st.shared.u32 [a], b;\n\t"
+        "@sh add.u32 %2, %2, 0x8000000;\n\t"                // next row (mod 32)
+        "@sh mad.lo.u32 %1, %1, 256, 0;\n\t"                // range <<= 8
         "@sh prmt.b32 %0, %0, 0, 0x4404;\n\t}"              // low = (low & 0xFF) << 8
-        : "+r"(c.low), "+r"(c.range), "+r"(c.out_byte), "+r"(c.pos), "=r"(t), "=r"(slow)
-        : "r"(c.thr), "r"(p24), "r"(one), "r"(c.ring) : "memory");
-    if (__builtin_expect(slow != 0u, 0)) {
-        const RacOut o = rac_output_slow(t + 0xFF01u, c.out_byte, c.out_count, c.pos, c.fl, c.ring, c.cap, c.out);
-        c.out_byte = o.out_byte; c.out_count = o.out_count; c.pos = o.pos; c.fl = o.fl;
-        c.thr = o.out_count ? 0xFFFFFFFFu : 0xFEu;
-    }
+        : "+r"(c.low), "+r"(c.range), "+r"(c.posx)
+        : "r"(p24), "r"(one), "r"(c.ring), "r"(rowmul) : "memory");
 }
 
-__device__ __forceinline__ void rac_code_word(Rac &c, uint32_t w)
+template <uint32_t ROWMUL>
+__device__ __forceinline__ void rac_code_word(Rac &c, uint32_t w, uint32_t rowmul_rt)
 {
-    rac_code(c, w << 24, w & 0x100u);
-    rac_code(c, __byte_perm(w, 0u, 0x2444), w & 0x1000000u);
+    rac_code<ROWMUL>(c, w << 24, w & 0x100u, rowmul_rt);
+    rac_code<ROWMUL>(c, __byte_perm(w, 0u, 0x2444), w & 0x1000000u, rowmul_rt);
+}
+
+// 8 finished entries of the lane: ring -> scratch region, predicated (the lanes of a warp fill their rings at different
+// speeds); full = the lane has 8 or more entries waiting
+template <uint32_t ROWMUL>
+__device__ __forceinline__ void rac_flush8(Rac &c, uint32_t full, uint32_t rowmul_rt)
+{
+    const uint32_t rowmul = ROWMUL ? ROWMUL : rowmul_rt;
+    const uint32_t pitch = rowmul >> 5;
+    const uint32_t at = c.ring + __umulhi(c.flx, rowmul);   // 8 entries never wrap: flx counts whole groups of 8, the ring holds 32
+    uint32_t e[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) e[k] = 0u;
+    if (full) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(e[k]) : "r"(at + (uint32_t)k * pitch) : "memory");
+    }
+    if (full && c.nfl + 8u <= c.cap) {
+        uint4 v;
+        v.x = __byte_perm(e[0], e[1], 0x5410); v.y = __byte_perm(e[2], e[3], 0x5410);     // 16 bits of every entry
+        v.z = __byte_perm(e[4], e[5], 0x5410); v.w = __byte_perm(e[6], e[7], 0x5410);
+        *reinterpret_cast<uint4 *>(c.out + c.nfl) = v;
+    }
+    if (full) { c.flx += 8u * kRowUnit; c.nfl += 8u; }
 }
 
 // decision source of one coder: -1 = the slice's prefix (keyframe bit, slice header), 0..nruns-1 = sample runs,
@@ -617,17 +587,47 @@ struct RacGen {
 };
 
 constexpr int kRangeThreads = 32;
-constexpr int kRangeChunk = 8;            // 16-byte decision vectors per chunk (one 128-byte line per lane)
-constexpr int kRangeDepth = 4;            // chunk slots per lane (power of two): kRangeDepth-1 chunks in flight
+constexpr int kRangeChunk = 8;            // 16-byte decision vectors per chunk (128 bytes per lane)
+constexpr int kRangeDepth = 3;            // chunk slots per lane: kRangeDepth-1 chunks in flight
+constexpr int kRangeLanePitch = kRangeChunk * 16 + 16;    // bytes between the chunks of neighbouring lanes inside a slot: an odd
+                                                          // number of 16-byte units, so the 128-bit reads of a warp spread over all banks
 
-template <int LANES>        // coders per warp known at compile time (16: the common case, immediate strides) or 0 = `lanes_rt`
+__device__ __forceinline__ void rc_mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void rc_mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void rc_mbar_wait(uint32_t bar, uint32_t phase)
+{
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x989680;\n\t"
+        "@P1 bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}"
+        :: "r"(bar), "r"(phase) : "memory");
+}
+
+// The decision streams come in through the TMA engine, one bulk copy (cp.async.bulk, SASS UBLKCP) per lane and chunk:
+// the 32 coders of a warp read 32 different streams that lie tens of megabytes apart, i.e. every access of the warp
+// touches 32 different pages.  Issued as ordinary (or cp.async) loads, these accesses sit in the SM's in-order
+// load/store path while their addresses are translated -- with batches beyond the reach of the TLBs (>= 1024 frames)
+// every coder step then waited behind them (the kernel took twice as long per decision as with 512-frame batches).  A
+// bulk copy is a descriptor handed to the copy engine: translation and transfer happen off the warp's path, one request
+// per 128 bytes instead of eight.
+template <int LANES>        // coders per warp known at compile time (32: the common case, immediate strides) or 0 = `lanes_rt`
 __global__ void __launch_bounds__(kRangeThreads) k_rangecode(const EncDeviceTables T, const EncBatch B, const int lanes_rt)
 {
     const int lanes = LANES ? LANES : lanes_rt;
     const Layout &L = T.layout;
-    if ((int)threadIdx.x >= lanes) return;
     const int idx = blockIdx.x * lanes + threadIdx.x;
-    if (idx >= B.nframes * L.nslices) return;
+    const bool live = (int)threadIdx.x < lanes && idx < B.nframes * L.nslices;
+    const uint32_t mask = __ballot_sync(0xFFFFFFFFu, live);
+    if (!live) return;
     if (B.status[0]) return;
     // a warp holds the same slice of consecutive frames: their streams have similar lengths
     const int s = idx / B.nframes, f = idx - s * B.nframes;
@@ -635,29 +635,37 @@ __global__ void __launch_bounds__(kRangeThreads) k_rangecode(const EncDeviceTabl
     const int key = B.frame_key[f] ? 1 : 0;
     const int nruns = g.nruns;
 
-    // sized by the lanes in use (544 bytes per coder), so that half-filled warps do not halve the warps an SM holds
-    extern __shared__ __align__(32) uint8_t s_range_dyn[];
-    uint4 *s_vec = reinterpret_cast<uint4 *>(s_range_dyn);                              // [chunk slot][vector][lane]
-    uint8_t *s_ring = s_range_dyn + (size_t)kRangeDepth * kRangeChunk * lanes * 16;      // [lane][32]
-    const uint32_t vstride = (uint32_t)lanes * 16u, cstride = (uint32_t)kRangeChunk * vstride;
+    // sized by the lanes in use, so that half-filled warps do not halve the warps an SM holds:
+    // [ring: 32 rows x lanes x 4][chunk slots: kRangeDepth x lanes x kRangeLanePitch][mbarriers: kRangeDepth x 8]
+    extern __shared__ __align__(16) uint8_t s_range_dyn[];
+    constexpr uint32_t kRowMul = (uint32_t)LANES * 4u * 32u;
+    const uint32_t stride = (uint32_t)lanes * 4u;                                        // bytes between the rows of the ring
+    const uint32_t rowmul = stride * 32u;
+    const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(s_range_dyn);
+    const uint32_t slotstride = (uint32_t)lanes * kRangeLanePitch;
+    const uint32_t vec_base = smem0 + (uint32_t)kRingRows * stride + threadIdx.x * kRangeLanePitch;
+    const uint32_t bar0 = smem0 + (uint32_t)kRingRows * stride + (uint32_t)kRangeDepth * slotstride;
     Rac c;
-    c.low = 0; c.range = 0xFF00u; c.out_byte = 0; c.out_count = 0; c.thr = 0xFEu;   // ff_init_range_encoder (+ dummy outstanding byte)
-    c.out = B.scratch + (size_t)f * L.scratch_per_frame + g.scratch_off;
-    c.pos = kScratchLead - 1; c.fl = 0; c.cap = g.scratch_cap;
-    c.ring = (uint32_t)__cvta_generic_to_shared(s_ring + threadIdx.x * 32);
+    c.low = 0; c.range = 0xFF00u;                                                        // ff_init_range_encoder
+    c.out = reinterpret_cast<uint16_t *>(B.scratch) + (size_t)f * L.scratch_per_frame + g.scratch_off;
+    c.posx = 0; c.flx = 0; c.nfl = 0; c.cap = g.scratch_cap;
+    c.ring = smem0 + threadIdx.x * 4u;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kRangeDepth; i++) rc_mbar_init(bar0 + 8u * i, (uint32_t)__popc(mask));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp(mask);
 
     const uint16_t *dec_frame = B.dec + (size_t)f * L.dec_per_frame;
     const uint32_t *run_cnt = B.run_cnt + (size_t)f * L.runs_per_frame + g.run_first;
     const uint8_t *run_pc = T.run_pc + g.run_first;
 
-    const uint32_t vec_base = (uint32_t)__cvta_generic_to_shared(s_vec + threadIdx.x);
     RacGen gen;
     gen.ptr = nullptr; gen.rem = 0; gen.last_valid = 0; gen.r = -2; gen.cur0 = gen.cur1 = gen.cur2 = 0u;
 
-    // Next chunk of the lane's stream: up to kRangeChunk consecutive 16-byte vectors of the current source, copied into
-    // chunk slot `slot` of the lane's shared-memory ring with cp.async (no register is tied to the data while it is in
-    // flight; the vectors of a chunk are requested back to back, so DRAM sees one 128-byte access per lane, not eight
-    // scattered 16-byte ones).  Returns nvec | decisions_in_last_vector << 4 (0 = the stream has ended).
+    // Next chunk of the lane's stream: up to kRangeChunk consecutive 16-byte vectors of the current source, brought into
+    // chunk slot `slot` by one bulk copy that signals the slot's mbarrier; every lane of the warp arrives on that barrier
+    // with the bytes it expects (none once its stream has ended).  Returns nvec | decisions_in_last_vector << 4 (0 = ended).
     auto fetch = [&](uint32_t slot) -> uint32_t {
         uint32_t desc = 0u;
         if (gen.rem == 0u) {
@@ -687,39 +695,42 @@ __global__ void __launch_bounds__(kRangeThreads) k_rangecode(const EncDeviceTabl
                 }
             }
         }
-        if (gen.rem) {
-            const uint32_t nv = min(gen.rem, (uint32_t)kRangeChunk);
-            const uint32_t dst = vec_base + slot * cstride;
-#pragma unroll
-            for (uint32_t j = 0; j < (uint32_t)kRangeChunk; j++)
-                if (j < nv) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst + j * vstride), "l"(gen.ptr + j) : "memory");
+        const uint32_t bar = bar0 + 8u * slot;
+        const uint32_t nv = min(gen.rem, (uint32_t)kRangeChunk);
+        rc_mbar_expect_tx(bar, nv * 16u);
+        if (nv) {
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         :: "r"(vec_base + slot * slotstride), "l"(gen.ptr), "r"(nv * 16u), "r"(bar) : "memory");
             gen.ptr += nv;
             gen.rem -= nv;
             desc = nv | (gen.rem ? 8u : gen.last_valid) << 4;
         }
-        asm volatile("cp.async.commit_group;" ::: "memory");
         return desc;
     };
 
-    // kRangeDepth chunks in flight per lane; dq holds their descriptors, 8 bits each, oldest in the low bits
+    // kRangeDepth - 1 chunks in flight per lane; dq holds the descriptors, 8 bits each, oldest in the low bits
     uint32_t dq = 0u;
 #pragma unroll
     for (int i = 0; i < kRangeDepth - 1; i++) dq |= fetch((uint32_t)i) << (8 * i);
-    uint32_t slot = 0u;
+    uint32_t slot = 0u, phases = 0u;                          // bit i of phases: parity the next wait on slot i looks for
 #pragma unroll 1
     for (;;) {
         const uint32_t nv = dq & 0xFu, last_valid = (dq >> 4) & 0xFu;
-        if (nv == 0u) break;
-        dq = (dq >> 8) | fetch((slot + kRangeDepth - 1) & (kRangeDepth - 1)) << (8 * (kRangeDepth - 2));
-        asm volatile("cp.async.wait_group %0;" :: "n"(kRangeDepth - 1) : "memory");
-        uint32_t at = vec_base + slot * cstride;
-        slot = (slot + 1u) & (kRangeDepth - 1);
-        uint4 v;
-        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(at) : "memory");
+        if (!__any_sync(mask, nv != 0u)) break;               // the warp leaves together: every lane arrives on every barrier
+        // the slot refilled now is the one the whole warp has finished reading in the previous round
+        uint32_t nslot = slot + (uint32_t)(kRangeDepth - 1);
+        if (nslot >= (uint32_t)kRangeDepth) nslot -= (uint32_t)kRangeDepth;
+        dq = (dq >> 8) | fetch(nslot) << (8 * (kRangeDepth - 2));
+        rc_mbar_wait(bar0 + 8u * slot, (phases >> slot) & 1u);
+        phases ^= 1u << slot;
+        uint32_t at = vec_base + slot * slotstride;
+        slot = slot + 1u == (uint32_t)kRangeDepth ? 0u : slot + 1u;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (nv) asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(at) : "memory");
 #pragma unroll 1
         for (uint32_t j = nv; j; j--) {
             uint4 cur = v;
-            at += vstride;
+            at += 16u;
             // the next vector of the chunk is read while this one is coded (the chunk has landed as a whole)
             if (j > 1u) asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(at) : "memory");
             if (j == 1u && last_valid < 8u) {                     // end of a run: what follows in the vector is not ours
@@ -729,12 +740,21 @@ __global__ void __launch_bounds__(kRangeThreads) k_rangecode(const EncDeviceTabl
                 if (k <= 2u) cur.y = 0u; else if (k == 3u) cur.y &= 0xFFFFu;
                 if (k == 1u) cur.x &= 0xFFFFu;
             }
-            rac_code_word(c, cur.x);
-            rac_code_word(c, cur.y);
-            rac_code_word(c, cur.z);
-            rac_code_word(c, cur.w);
-            rac_flush16_if_full(c);                               // at most 8 bytes per vector on the straight line
+            rac_code_word<kRowMul>(c, cur.x, rowmul);
+            rac_code_word<kRowMul>(c, cur.y, rowmul);
+            rac_code_word<kRowMul>(c, cur.z, rowmul);
+            rac_code_word<kRowMul>(c, cur.w, rowmul);
+            // a vector adds at most 8 entries: a lane with 16 or more waiting makes room now (rare: the scheduled flush
+            // below keeps a lane under 8 + what 8 vectors produce, ~14 on camera content; bursts of improbable bits do more)
+            if (__any_sync(__activemask(), c.posx - c.flx >= 16u * kRowUnit)) {
+                rac_flush8<kRowMul>(c, c.posx - c.flx >= 16u * kRowUnit, rowmul);
+                rac_flush8<kRowMul>(c, c.posx - c.flx >= 16u * kRowUnit, rowmul);
+            }
         }
+        __syncwarp(mask);
+        // scheduled flush, once per chunk: every lane moves its whole groups of 8 entries
+        while (__any_sync(mask, c.posx - c.flx >= 8u * kRowUnit))
+            rac_flush8<kRowMul>(c, c.posx - c.flx >= 8u * kRowUnit, rowmul);
     }
     // ff_rac_terminate (rangecoder.c:104-116): range = 0xFF, low += 0xFF, renormalise; range = 0xFF, renormalise.  A
     // decision with p = 0, bit = 0 changes nothing, so forcing the range below 0x100 in front of one is exactly a
@@ -743,13 +763,18 @@ __global__ void __launch_bounds__(kRangeThreads) k_rangecode(const EncDeviceTabl
 #pragma unroll 1
     for (int t = 0; t < 2; t++) {
         c.range = 0xFFu;
-        rac_code(c, 0u, 0u);
+        rac_code<kRowMul>(c, 0u, 0u, rowmul);
     }
-    while (c.fl < c.pos) rac_flush16(c);
+    // the entry of the last renormalisation is what the reference keeps in outstanding_byte and never writes
+    const uint32_t nent = c.nfl + ((c.posx - c.flx) >> 27);
+    // the rest of the ring (the last group may run past the last entry: the region is padded and nobody reads that)
+    while (c.nfl < nent) rac_flush8<kRowMul>(c, 1u, rowmul);
 
-    B.slice_bytes[f * L.nslices + s] = c.pos - kScratchLead;
-    if (((c.pos + 15u) & ~15u) > c.cap) atomicMax(&B.status[1], (unsigned long long)c.pos + 16ull);
+    B.slice_bytes[f * L.nslices + s] = nent - 1u;
+    if (((nent + 7u) & ~7u) > c.cap) atomicMax(&B.status[1], (unsigned long long)nent + 8ull);
 }
+
+static int rangecode_smem(int lanes) { return lanes * (kRingRows * 4 + kRangeDepth * kRangeLanePitch) + kRangeDepth * 8; }
 
 void launch_rangecode(const EncDeviceTables &t, const EncBatch &b, cudaStream_t s)
 {
@@ -757,21 +782,22 @@ void launch_rangecode(const EncDeviceTables &t, const EncBatch &b, cudaStream_t 
     // FFV1B200_RANGE_LANES forces the coders per warp (read at every launch: the parity tests walk through all variants)
     int forced = 0;
     if (const char *v = getenv("FFV1B200_RANGE_LANES")) { forced = atoi(v); if (forced < 1 || forced > 32 || (forced & (forced - 1))) forced = 0; }
+    // A coder is one dependent chain (~25 cycles per decision) and a warp costs the same issue slots whatever the number
+    // of its lanes that carry a coder: full warps, unless that would leave SM sub-partitions without any warp at all
     int lanes = forced;
-    if (!lanes) {                                  // the coders are bound by latency: ~10 warps per SM before warps are filled up
-        lanes = 4;
-        while (lanes < 16 && n / lanes > 148 * 12) lanes *= 2;
-        if (n / lanes > 148 * 26) lanes = 32;      // 16 coders per warp (the measured optimum) as long as the warps stay resident
+    if (!lanes) {
+        lanes = 32;
+        while (lanes > 4 && n / lanes < 148 * 4) lanes >>= 1;
     }
     static bool attr = false;
-    if (!attr) {                                    // 26 resident warps of 8.7 KB need the large shared-memory carveout
-        cudaFuncSetAttribute(k_rangecode<16>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (!attr) {                                    // ~10 resident warps of 20 KB need the large shared-memory carveout
+        cudaFuncSetAttribute(k_rangecode<32>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaFuncSetAttribute(k_rangecode<0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         attr = true;
     }
-    const int smem = lanes * (32 + kRangeDepth * kRangeChunk * 16);
+    const int smem = rangecode_smem(lanes);
     if (getenv("FFV1B200_DEBUG")) fprintf(stderr, "k_rangecode: %d coders, %d lanes\n", n, lanes);
-    if (lanes == 16) k_rangecode<16><<<(n + lanes - 1) / lanes, kRangeThreads, smem, s>>>(t, b, lanes);
+    if (lanes == 32) k_rangecode<32><<<(n + lanes - 1) / lanes, kRangeThreads, smem, s>>>(t, b, lanes);
     else k_rangecode<0><<<(n + lanes - 1) / lanes, kRangeThreads, smem, s>>>(t, b, lanes);
 }
 
@@ -1277,6 +1303,31 @@ __device__ __forceinline__ uint32_t gf_mulmod(uint32_t a, uint32_t b)
 
 constexpr int kPackThreads = 256;
 
+// ---- carry resolution of k_rangecode's output (16-bit entries v[k] = byte | carry << 8, see k_rangecode) ----------------
+// What is added to entry k-1: the carry out of entries k, k+1, ... -- an entry of exactly 0x0FF passes a carry on, an
+// entry with bit 8 set generates one, anything else absorbs it (renorm_encoder's outstanding_count / outstanding_byte
+// bookkeeping, rangecoder.h:52-75, read backwards).  n = number of entries (the dropped last one included).
+__device__ __forceinline__ uint32_t pack_carry_from(const uint16_t *v, uint32_t k, uint32_t n)
+{
+    for (; k < n; k++) {
+        const uint32_t e = v[k];
+        if (e != 0xFFu) return e >> 8;
+    }
+    return 0u;
+}
+
+// payload bytes k..k+3 (k + 3 < n), first byte in the most significant position
+__device__ __forceinline__ uint32_t pack_resolved_be(const uint16_t *v, uint32_t k, uint32_t n)
+{
+    const uint32_t e0 = v[k], e1 = v[k + 1], e2 = v[k + 2], e3 = v[k + 3];
+    return (e0 << 24) + (e1 << 16) + (e2 << 8) + e3 + pack_carry_from(v, k + 4u, n);
+}
+
+__device__ __forceinline__ uint32_t pack_resolved_byte(const uint16_t *v, uint32_t k, uint32_t n)
+{
+    return (v[k] + pack_carry_from(v, k + 1u, n)) & 0xFFu;
+}
+
 // One CTA per (frame, slice): copy the coder output to its final place, append the 24-bit length and the
 // error-check trailer.
 //   CRC (libavutil AV_CRC_32_IEEE: MSB-first 0x04C11DB7, init 0, no final xor = plain polynomial remainder):
@@ -1285,6 +1336,7 @@ constexpr int kPackThreads = 256;
 //   own partial CRC (square-and-multiply over precomputed x^(8*2^j)) and a XOR reduction finishes the job.
 //   Copy: the packet position has arbitrary byte alignment, so destination-aligned 32-bit words are built from two
 //   source words with a funnel shift; the stores of a warp are contiguous.
+template <bool C16>       // C16: the coder output is k_rangecode's 16-bit entries (range-coder modes); else plain bytes (Golomb-Rice)
 __global__ void __launch_bounds__(kPackThreads) k_pack_slices(const EncDeviceTables T, const EncBatch B)
 {
     __shared__ uint32_t s_tab[4][256];          // s_tab[k][b] = (b * x^(8k+32)) mod P
@@ -1317,10 +1369,26 @@ __global__ void __launch_bounds__(kPackThreads) k_pack_slices(const EncDeviceTab
     const uint32_t nb = B.slice_bytes[f * ns + s];
     const uint8_t *src = B.scratch + (size_t)f * L.scratch_per_frame + T.slices[s].scratch_off + kScratchLead;   // 4-byte aligned
     uint8_t *dst = B.out + off;
+    const uint16_t *v16 = reinterpret_cast<const uint16_t *>(B.scratch) + (size_t)f * L.scratch_per_frame + T.slices[s].scratch_off;
+    const uint32_t nent = nb + 1u;                                        // entries of the slice (C16)
     __syncthreads();
 
     // ---- copy: head bytes up to the first aligned destination word, aligned words, tail bytes
-    {
+    if (C16) {
+        const uint32_t head = min(nb, (uint32_t)((4u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 3u)) & 3u));
+        if ((uint32_t)tid < head) dst[tid] = (uint8_t)pack_resolved_byte(v16, (uint32_t)tid, nent);
+        const uint32_t nwords = (nb - head) >> 2;
+        uint32_t *dst32 = reinterpret_cast<uint32_t *>(dst + head);
+        for (uint32_t w = tid; w < nwords; w += kPackThreads)
+            dst32[w] = __byte_perm(pack_resolved_be(v16, head + 4u * w, nent), 0u, 0x0123);
+        const uint32_t done = head + nwords * 4u;
+        if ((uint32_t)tid < nb - done) dst[done + tid] = (uint8_t)pack_resolved_byte(v16, done + (uint32_t)tid, nent);
+        if (tid == 0) {
+            uint32_t q = nb;
+            if (has_len) { dst[q] = (uint8_t)(nb >> 16); dst[q + 1] = (uint8_t)(nb >> 8); dst[q + 2] = (uint8_t)nb; q += 3; }
+            if (T.ec) dst[q] = 0;
+        }
+    } else {
         const uint32_t head = min(nb, (uint32_t)((4u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 3u)) & 3u));
         if ((uint32_t)tid < head) dst[tid] = src[tid];
         const uint32_t nwords = (nb - head) >> 2;
@@ -1352,14 +1420,15 @@ __global__ void __launch_bounds__(kPackThreads) k_pack_slices(const EncDeviceTab
     {
         const uint32_t *src32 = reinterpret_cast<const uint32_t *>(src);
         for (uint32_t w = w0; w < w1; w++) {
-            const uint32_t v = src32[w] ^ __byte_perm(crc, 0, 0x0123);    // message bytes are MSB-first: fold crc in byte order
+            // message bytes are MSB-first: fold crc in byte order
+            const uint32_t v = (C16 ? __byte_perm(pack_resolved_be(v16, 4u * w, nent), 0u, 0x0123) : src32[w]) ^ __byte_perm(crc, 0, 0x0123);
             crc = s_tab[3][v & 0xFFu] ^ s_tab[2][(v >> 8) & 0xFFu] ^ s_tab[1][(v >> 16) & 0xFFu] ^ s_tab[0][v >> 24];
         }
     }
     uint32_t after = (nw_all - w1) * 4u + (nb & 3u) + tail_bytes;         // message bytes behind this thread's chunk
     if (tid == kPackThreads - 1) {
         // the last thread also takes the 0..3 payload bytes behind the last whole word and the trailer bytes
-        for (uint32_t i = nw_all * 4u; i < nb; i++) crc = (crc << 8) ^ s_tab[0][(crc >> 24) ^ src[i]];
+        for (uint32_t i = nw_all * 4u; i < nb; i++) crc = (crc << 8) ^ s_tab[0][(crc >> 24) ^ (C16 ? pack_resolved_byte(v16, i, nent) : (uint32_t)src[i])];
         if (has_len) {
             crc = (crc << 8) ^ s_tab[0][(crc >> 24) ^ ((nb >> 16) & 0xFFu)];
             crc = (crc << 8) ^ s_tab[0][(crc >> 24) ^ ((nb >> 8) & 0xFFu)];
@@ -1389,7 +1458,8 @@ __global__ void __launch_bounds__(kPackThreads) k_pack_slices(const EncDeviceTab
 void launch_pack(const EncDeviceTables &t, const EncBatch &b, cudaStream_t s)
 {
     k_pack_layout<<<1, 1024, 0, s>>>(t, b);
-    k_pack_slices<<<b.nframes * t.layout.nslices, kPackThreads, 0, s>>>(t, b);
+    if (t.layout.golomb) k_pack_slices<false><<<b.nframes * t.layout.nslices, kPackThreads, 0, s>>>(t, b);
+    else                 k_pack_slices<true><<<b.nframes * t.layout.nslices, kPackThreads, 0, s>>>(t, b);
 }
 
 cudaError_t configure_kernels(const Layout &L)

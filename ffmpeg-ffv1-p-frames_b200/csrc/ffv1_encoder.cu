@@ -138,7 +138,8 @@ int alloc_buffers(FFV1B200Encoder *e)
     CU_TRY(e->d_rec.alloc((size_t)L.rec_per_frame * F));
     CU_TRY(e->d_run_cnt.alloc((size_t)L.runs_per_frame * F));
     CU_TRY(e->d_slice_bytes.alloc((size_t)L.nslices * F));
-    CU_TRY(e->d_scratch.alloc((size_t)L.scratch_per_frame * F));
+    // coder output: bytes (Golomb-Rice) or k_rangecode's 16-bit entries, `scratch_cap` of them per slice
+    CU_TRY(e->d_scratch.alloc((size_t)L.scratch_per_frame * F * (L.golomb ? 1 : 2)));
     if (!L.golomb || e->golomb_lists) CU_TRY(e->d_dec.alloc((size_t)L.dec_per_frame * F + 64));   // Golomb lists: the code words
     const size_t state_bytes = (size_t)L.nslices * L.npc * L.ctx_count * 32;
     for (int k = 0; k < kCarry; k++) {
@@ -287,7 +288,7 @@ int recover(FFV1B200Encoder *e, bool own_out, cudaStream_t s)
                 }
                 e->tab.layout.scratch_per_frame = cur;
                 e->d_scratch.release();
-                CU_TRY(e->d_scratch.alloc((size_t)cur * e->max_batch));
+                CU_TRY(e->d_scratch.alloc((size_t)cur * e->max_batch * (e->tab.layout.golomb ? 1 : 2)));
                 CU_TRY(e->d_slices.upload(e->tab.slices.data(), e->tab.slices.size(), s));
                 again = true;
             } else if (st[2]) {     // the packet area was too small
