@@ -117,19 +117,4 @@ cudaError_t configure_pixel_fast(const FastPlan &plan);
 void launch_pixel_fast(const EncDeviceTables &t, const EncBatch &b, const FastPlan &plan, const FastItemDesc *d_items, int num_sms,
                        cudaStream_t s, const uint8_t *const *frame0_planes, long long frame_stride);
 
-// state replay fused into one kernel (ffv1_replay_fused.cu)
-struct FusedSeg { uint32_t rec_off; uint16_t w; uint16_t run; };     // <= 128 samples of one line (slice-relative record offset, run index)
-struct FusedSlice { int32_t seg_first[3]; int32_t seg_count[3]; };   // per plane context: its segments, coding order
-struct FusedPlan {
-    std::vector<FusedSeg> segs;
-    std::vector<FusedSlice> slices;
-    bool ok = false;
-    int32_t smem_bytes = 0;
-};
-bool fused_replay_supported(const Layout &L);
-void build_fused_plan(const Tables &tab, FusedPlan &plan);
-cudaError_t configure_fused_replay(const FusedPlan &plan);
-void launch_fused_replay(const EncDeviceTables &t, const EncBatch &b, const FusedPlan &plan, const FusedSeg *d_segs,
-                         const FusedSlice *d_slices, cudaStream_t s);
-
 } // namespace ffv1

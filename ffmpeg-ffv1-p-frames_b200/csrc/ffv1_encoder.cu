@@ -67,7 +67,6 @@ struct FFV1B200Encoder {
     DevBuf<SliceGeom> d_slices; DevBuf<LineDesc> d_lines; DevBuf<int32_t> d_pc_lines; DevBuf<TileDesc> d_tiles;
     DevBuf<CtxTile> d_ctiles;
     FastPlan fast_plan; DevBuf<FastItemDesc> d_fast_items;
-    FusedPlan fused_plan; DevBuf<FusedSeg> d_fused_segs; DevBuf<FusedSlice> d_fused_slices;
     DevBuf<int16_t> d_quant; DevBuf<uint8_t> d_lut, d_one_pow, d_run_pc;
     // shared intermediates
     DevBuf<uint32_t> d_rec, d_run_cnt, d_slice_bytes, d_line_pos, d_ctx_hist, d_list_start, d_list_count;
@@ -78,7 +77,7 @@ struct FFV1B200Encoder {
     uint64_t submitted = 0, collected = 0;      // batch counters; slot of batch k = k % kSlots
     int carry_next = 0;                          // ring index holding the state after the last submitted batch
     double dec_per_sample = 5.0;
-    bool state_in_smem = true, fast_pixel = false, ctx_replay = false, fused_replay = false, golomb_lists = false;
+    bool state_in_smem = true, fast_pixel = false, ctx_replay = false, golomb_lists = false;
     int max_plane_width = 0, num_sms = 148, max_ctile_samples = 0;
     FFV1B200EncStats stats{};
     int last_slot = 0;
@@ -148,7 +147,7 @@ int alloc_buffers(FFV1B200Encoder *e)
     }
     const size_t g = e->cfg.gop_size > 0 ? e->cfg.gop_size : 1;
     const size_t nseg_max = (F + g - 1) / g + 1;
-    if ((e->ctx_replay && !e->fused_replay) || e->golomb_lists) {
+    if (e->ctx_replay || e->golomb_lists) {
         const size_t nchains = nseg_max * L.nslices * L.npc;
         CU_TRY(e->d_line_pos.alloc((size_t)L.lines_per_frame * F));
         CU_TRY(e->d_ctx_hist.alloc((size_t)L.ctiles_per_frame * L.ctx_count * F));
@@ -157,7 +156,7 @@ int alloc_buffers(FFV1B200Encoder *e)
         CU_TRY(e->d_list_order.alloc(nchains * L.ctx_count));
         CU_TRY(e->d_lists.alloc((size_t)L.samples_per_frame * F));
     }
-    if ((!e->state_in_smem && !e->ctx_replay && !e->fused_replay) || (L.golomb && !e->golomb_lists))
+    if ((!e->state_in_smem && !e->ctx_replay) || (L.golomb && !e->golomb_lists))
         CU_TRY(e->d_state_seg.alloc(state_bytes * nseg_max));            // one state set per GOP segment of a batch
     for (Slot &sl : e->slot) {
         CU_TRY(sl.d_planes.alloc(F * 4)); CU_TRY(sl.h_planes.alloc(F * 4));
@@ -240,8 +239,7 @@ int enqueue_kernels(FFV1B200Encoder *e, Slot &sl, cudaStream_t s)
     }
     else         launch_pixel(t, b, s);
     cudaEventRecord(sl.ev[1], s);
-    if (e->fused_replay) launch_fused_replay(t, b, e->fused_plan, e->d_fused_segs.p, e->d_fused_slices.p, s);
-    else if (e->ctx_replay) launch_ctx_replay(t, b, e->max_ctile_samples, s);
+    if (e->ctx_replay) launch_ctx_replay(t, b, e->max_ctile_samples, s);
     else if (!L.golomb) launch_replay(t, b, s);
     cudaEventRecord(sl.ev[2], s);
     if (!L.golomb) launch_rangecode(t, b, s);
@@ -250,7 +248,7 @@ int enqueue_kernels(FFV1B200Encoder *e, Slot &sl, cudaStream_t s)
     cudaEventRecord(sl.ev[3], s);
     launch_pack(t, b, s);
     cudaEventRecord(sl.ev[4], s);
-    e->stats.kernel_launches += L.golomb ? (e->golomb_lists ? 8 : 4) : (e->fused_replay ? 5 : (e->ctx_replay ? 9 : 5));
+    e->stats.kernel_launches += L.golomb ? (e->golomb_lists ? 8 : 4) : (e->ctx_replay ? 9 : 5);
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaMemcpyAsync(sl.h_status.p, sl.d_status.p, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost, s));
     CU_TRY(cudaMemcpyAsync(sl.h_pkt_size.p, sl.d_pkt_size.p, sizeof(uint32_t) * nframes, cudaMemcpyDeviceToHost, s));
@@ -403,16 +401,6 @@ int ffv1b200_enc_open(FFV1B200Encoder **out, const FFV1B200EncParams *p)
     e->ctx_replay = ctx_replay_supported(L);
     if (const char *v = getenv("FFV1B200_REPLAY")) { if (!strcmp(v, "warp")) e->ctx_replay = false; }
     if (e->ctx_replay) CU_TRY(configure_ctx_replay(L));
-    // experimental: the whole state replay in one kernel (FFV1B200_REPLAY=fused); bit-exact, but measured slower than the
-    // per-context list kernels on B200 (profiles/r01_replay_fused.txt), so it is not the default
-    build_fused_plan(e->tab, e->fused_plan);
-    e->fused_replay = false;
-    if (const char *v = getenv("FFV1B200_REPLAY")) { if (!strcmp(v, "fused")) e->fused_replay = e->fused_plan.ok; }
-    if (e->fused_replay) {
-        CU_TRY(configure_fused_replay(e->fused_plan));
-        CU_TRY(e->d_fused_segs.upload(e->fused_plan.segs.data(), e->fused_plan.segs.size(), e->s_comp));
-        CU_TRY(e->d_fused_slices.upload(e->fused_plan.slices.data(), e->fused_plan.slices.size(), e->s_comp));
-    }
     for (auto &g : e->tab.slices) for (int pl = 0; pl < L.nplanes; pl++) e->max_plane_width = std::max(e->max_plane_width, g.pw[pl]);
     for (const CtxTile &ct : e->tab.ctiles) {
         const SliceGeom &g = e->tab.slices[ct.slice];

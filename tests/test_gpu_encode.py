@@ -228,20 +228,6 @@ def test_pixel_fast_row_copy_path(B, cid, monkeypatch):
         exp, key = o.encode(f)
         assert got[i][0] == exp and got[i][1] == key, "packet %d differs" % i
 
-@pytest.mark.parametrize("cid", ["c2_gop_range_24sl", "range_flat", "yuva420p", "fate_v3_bgr0", "slices9_random8", "default_big_autov3"])
-def test_fused_replay_kernel(B, cid, monkeypatch):
-    """experimental single-kernel state replay (FFV1B200_REPLAY=fused, 8-bit content): same packets as the list kernels"""
-    case = [c for c in CASES if c[0] == cid][0]
-    _, w, h, fmt, opts, kind, n = case
-    frames = make_frames(case)
-    o = O.Encoder(w, h, fmt, **opts)
-    monkeypatch.setenv("FFV1B200_REPLAY", "fused")
-    g = B.FFV1Encoder(w, h, fmt, max_batch_frames=4, **gpu_opts(opts))
-    got = g.encode_batch(frames)
-    for i, f in enumerate(frames):
-        exp, key = o.encode(f)
-        assert got[i][0] == exp and got[i][1] == key, "packet %d differs" % i
-
 FULL = [   # BASELINE.json configs[2] and [3] at full size, with the options the reference actually accepts (SURVEY section 0.4)
     ("c3_full_1080p_422p10_ctx1", 1920, 1080, "yuv422p10le", dict(gop=16, level=3, coder=0, context=1), 1235),
     ("c4_full_2160p_gbrp14_30sl", 3840, 2160, "gbrp14le",    dict(gop=16, level=3, coder=2, context=0, slices=30), 1236),
