@@ -101,6 +101,47 @@ def fate_avi(raw, nframes, w, h, pix_fmt, level, slices):
         raise RuntimeError("fate_avi failed %d" % n)
     return out[:n].tobytes()
 
+def mux(muxer, codec, raw, nframes, w, h, pix_fmt, level=-1, slices=0, batch=0):
+    """encode with the named registered encoder and mux with the reference's "avi" or "nut" muxer, in memory"""
+    L = lib()
+    L.ffv1ref_mux_named.restype = ctypes.c_int64
+    L.ffv1ref_mux_named.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                    ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64]
+    raw = np.ascontiguousarray(raw)
+    out = np.zeros(len(raw) + (4 << 20), np.uint8)
+    n = L.ffv1ref_mux_named(muxer.encode(), codec.encode(), batch, raw.ctypes.data, nframes, w, h, pix_fmt.encode(), level, slices,
+                            out.ctypes.data, len(out))
+    if n < 0:
+        raise RuntimeError("mux failed %d" % n)
+    return out[:n].copy()
+
+def nut_decode(decoder, data, max_bytes, opts=""):
+    """the reference's NUT demuxer feeding the named registered decoder; returns (frames as one uint8 array, count, pix_fmt)"""
+    L = lib()
+    L.ffv1ref_nut_decode_named.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64,
+                                           ctypes.POINTER(ctypes.c_int), ctypes.c_char_p]
+    data = np.ascontiguousarray(data)
+    dst = np.zeros(max_bytes + 1024, np.uint8)
+    fb = ctypes.c_int(); name = ctypes.create_string_buffer(32)
+    k = L.ffv1ref_nut_decode_named(decoder.encode(), opts.encode(), data.ctypes.data, len(data), dst.ctypes.data, len(dst), ctypes.byref(fb), name)
+    if k < 0:
+        raise RuntimeError("nut_decode failed %d" % k)
+    return dst[:k * fb.value], k, name.value.decode()
+
+def sws_convert(raw, w, h, dst_fmt, src_fmt="yuv420p"):
+    """FATE's pixel-format conversion of a clip (ffmpeg's auto-inserted scale filter with -sws_flags
+    neighbor+bitexact+accurate_rnd, tests/fate/vcodec.mak:119-127) by the reference's own libswscale"""
+    L = lib()
+    L.ffv1ref_sws_convert.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    ssz = L.ffv1ref_sws_convert(None, dst_fmt.encode(), None, src_fmt.encode(), w, h, 0)
+    n = len(raw) // ssz
+    dsz = L.ffv1ref_sws_convert(None, src_fmt.encode(), None, dst_fmt.encode(), w, h, 0)
+    dst = np.zeros(dsz * n, np.uint8)
+    r = L.ffv1ref_sws_convert(np.ascontiguousarray(raw).ctypes.data, src_fmt.encode(), dst.ctypes.data, dst_fmt.encode(), w, h, n)
+    if r != dsz:
+        raise RuntimeError("sws_convert failed %d" % r)
+    return dst
+
 def vsynth(name, reference="/root/reference"):
     """FATE's synthetic clips made by the reference's own generators (tests/videogen.c, tests/rotozoom.c,
     tests/Makefile:34-44), compiled into oracle/_ref/.  Returns (uint8 array, w, h)."""
@@ -108,7 +149,7 @@ def vsynth(name, reference="/root/reference"):
     d = os.path.join(_HERE, "_ref")
     for tool in ("videogen", "rotozoom"):
         exe = os.path.join(d, tool)
-        if not os.path.exists(exe):
+        if not os.path.exists(exe) and os.path.isdir(reference):
             subprocess.check_call(["gcc", "-O2", "-w", "-o", exe, os.path.join(reference, "tests", tool + ".c"), "-lm"])
     with tempfile.TemporaryDirectory() as td:
         out = os.path.join(td, name + ".yuv")
@@ -117,6 +158,9 @@ def vsynth(name, reference="/root/reference"):
         elif name == "vsynth3":
             subprocess.check_call([os.path.join(d, "videogen"), out, "34", "34"]); w, h = 34, 34
         elif name == "vsynth2":
+            pre = os.path.join(d, "vsynth2.yuv")          # written by oracle/Makefile where the reference tree is mounted
+            if os.path.exists(pre):
+                return np.fromfile(pre, np.uint8), 352, 288
             subprocess.check_call([os.path.join(d, "rotozoom"), os.path.join(reference, "tests", "reference.pnm"), out]); w, h = 352, 288
         else:
             raise ValueError(name)

@@ -421,6 +421,38 @@ double ffv1ref_bench_decode(const char *name, int w, int h, const uint8_t *extra
     return (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
 }
 
+/* ---- FATE's input conversion (tests/fate/vcodec.mak:119-127: -pix_fmt yuv422p10 / yuv444p16 / bgr0 with
+ * -sws_flags neighbor+bitexact, to which fate-run.sh:167 appends +accurate_rnd+bitexact): what ffmpeg's auto-inserted scale
+ * filter does to the yuv420p clip (libavfilter/vf_scale.c:373-423: one SwsContext from the option API, MPEG-2 chroma
+ * position 128 for a yuv420p side), frame by frame.  src/dst hold tightly packed frames.  Returns bytes per dst frame. */
+#include "libswscale/swscale.h"
+int ffv1ref_sws_convert(const uint8_t *src, const char *src_fmt, uint8_t *dst, const char *dst_fmt, int w, int h, int nframes)
+{
+    enum AVPixelFormat sf = av_get_pix_fmt(src_fmt), df = av_get_pix_fmt(dst_fmt);
+    struct SwsContext *s;
+    int ssize, dsize, i;
+    if (sf == AV_PIX_FMT_NONE || df == AV_PIX_FMT_NONE) return -1;
+    ssize = av_image_get_buffer_size(sf, w, h, 1);
+    dsize = av_image_get_buffer_size(df, w, h, 1);
+    if (!dst) return dsize;
+    s = sws_alloc_context();
+    av_opt_set_int(s, "srcw", w, 0); av_opt_set_int(s, "srch", h, 0); av_opt_set_int(s, "src_format", sf, 0);
+    av_opt_set_int(s, "dstw", w, 0); av_opt_set_int(s, "dsth", h, 0); av_opt_set_int(s, "dst_format", df, 0);
+    av_opt_set_int(s, "sws_flags", SWS_POINT | SWS_BITEXACT | SWS_ACCURATE_RND, 0);
+    av_opt_set_int(s, "param0", SWS_PARAM_DEFAULT, 0); av_opt_set_int(s, "param1", SWS_PARAM_DEFAULT, 0);
+    av_opt_set_int(s, "src_h_chr_pos", -513, 0); av_opt_set_int(s, "src_v_chr_pos", sf == AV_PIX_FMT_YUV420P ? 128 : -513, 0);
+    av_opt_set_int(s, "dst_h_chr_pos", -513, 0); av_opt_set_int(s, "dst_v_chr_pos", df == AV_PIX_FMT_YUV420P ? 128 : -513, 0);
+    if (sws_init_context(s, NULL, NULL) < 0) { sws_freeContext(s); return -2; }
+    for (i = 0; i < nframes; i++) {
+        uint8_t *sp[4], *dp[4]; int sl[4], dl[4];
+        av_image_fill_arrays(sp, sl, src + (int64_t)i * ssize, sf, w, h, 1);
+        av_image_fill_arrays(dp, dl, dst + (int64_t)i * dsize, df, w, h, 1);
+        sws_scale(s, (const uint8_t *const *)sp, sl, 0, h, dp, dl);
+    }
+    sws_freeContext(s);
+    return dsize;
+}
+
 /* CRC helper so tests can pin libavutil's AV_CRC_32_IEEE convention (crc.c:357-380). */
 #include "libavutil/crc.h"
 unsigned ffv1ref_crc32_ieee(unsigned init, const uint8_t *buf, int len)
@@ -435,8 +467,14 @@ unsigned ffv1ref_crc32_ieee(unsigned init, const uint8_t *buf, int len)
  * ---------------------------------------------------------------------------------------------- */
 #include "libavformat/avformat.h"
 #include "libavformat/avio.h"
+#include "libavformat/internal.h"
 
 extern AVOutputFormat ff_avi_muxer;
+extern AVOutputFormat ff_nut_muxer;
+extern AVInputFormat ff_nut_demuxer;
+/* libavformat/nut.c lists the MOV video tags as a fallback table; libavformat/isom.c is not part of this build */
+const AVCodecTag ff_codec_movvideo_tags[] = { { AV_CODEC_ID_NONE, 0 } };
+static AVOutputFormat *g_muxer = &ff_avi_muxer;          /* container fate_avi_impl writes */
 
 typedef struct MemOut { uint8_t *buf; int64_t cap, pos, size; } MemOut;
 static int mem_write(void *opaque, uint8_t *buf, int n)
@@ -493,8 +531,8 @@ static int64_t fate_avi_impl(AVCodec *codec, int batch, const uint8_t *raw, int 
     uint8_t *iobuf;
     int i, ret, fsize;
     reg();
-    if (!fmt_registered) { av_register_output_format(&ff_avi_muxer); fmt_registered = 1; }
-    if (avformat_alloc_output_context2(&oc, &ff_avi_muxer, NULL, NULL) < 0) return -1;
+    if (!fmt_registered) { av_register_output_format(&ff_avi_muxer); av_register_output_format(&ff_nut_muxer); fmt_registered = 1; }
+    if (avformat_alloc_output_context2(&oc, g_muxer, NULL, NULL) < 0) return -1;
     iobuf = av_malloc(32768);
     oc->pb = avio_alloc_context(iobuf, 32768, 1, &mo, NULL, mem_write, mem_seek);
     oc->flags |= AVFMT_FLAG_BITEXACT;
@@ -562,3 +600,91 @@ static int64_t fate_avi_impl(AVCodec *codec, int batch, const uint8_t *raw, int 
     avformat_free_context(oc);
     return mo.size;
 }
+
+/* ---- container round trip: the same encode-and-mux procedure into NUT (libavformat/nutenc.c), and
+ * the way back: the reference's NUT demuxer (nutdec.c) feeding a named decoder.  Everything in memory. */
+int64_t ffv1ref_mux_named(const char *muxer, const char *name, int batch, const uint8_t *raw, int nframes, int w, int h,
+                          const char *pix_fmt, int level, int slices, uint8_t *out, int64_t cap)
+{
+    int64_t r;
+    reg();
+    AVCodec *codec = avcodec_find_encoder_by_name(name);
+    if (!codec) return -1;
+    g_muxer = !strcmp(muxer, "nut") ? &ff_nut_muxer : &ff_avi_muxer;
+    r = fate_avi_impl(codec, batch, raw, nframes, w, h, pix_fmt, level, slices, out, cap);
+    g_muxer = &ff_avi_muxer;
+    return r;
+}
+
+typedef struct MemIn { const uint8_t *buf; int64_t size, pos; } MemIn;
+static int mem_read(void *opaque, uint8_t *buf, int n)
+{
+    MemIn *m = opaque;
+    if (m->pos >= m->size) return AVERROR_EOF;
+    if (n > m->size - m->pos) n = (int)(m->size - m->pos);
+    memcpy(buf, m->buf + m->pos, n);
+    m->pos += n;
+    return n;
+}
+static int64_t mem_in_seek(void *opaque, int64_t off, int whence)
+{
+    MemIn *m = opaque;
+    if (whence == AVSEEK_SIZE) return m->size;
+    if (whence == SEEK_CUR) off += m->pos;
+    else if (whence == SEEK_END) off += m->size;
+    if (off < 0 || off > m->size) return -1;
+    m->pos = off;
+    return off;
+}
+
+/* NUT file in memory -> pictures of the named decoder, tightly packed one after the other in dst.  Returns the number of
+ * pictures (the decoder is drained with empty packets at the end), < 0 on error; *frame_bytes = bytes per picture. */
+int ffv1ref_nut_decode_named(const char *decoder, const char *dec_opts, const uint8_t *file, int64_t size,
+                             uint8_t *dst, int64_t cap, int *frame_bytes, char *fmt_name)
+{
+    static int registered;
+    AVFormatContext *ic = avformat_alloc_context();
+    MemIn mi = { file, size, 0 };
+    AVCodec *codec;
+    AVCodecContext *dc;
+    AVFrame *frame = av_frame_alloc();
+    AVPacket pkt;
+    uint8_t *iobuf = av_malloc(32768);
+    int ret, n = 0, got, fb = 0, eof = 0;
+    reg();
+    if (!registered) { av_register_input_format(&ff_nut_demuxer); registered = 1; }
+    ic->pb = avio_alloc_context(iobuf, 32768, 0, &mi, mem_read, NULL, mem_in_seek);
+    if ((ret = avformat_open_input(&ic, NULL, &ff_nut_demuxer, NULL)) < 0) return ret;
+    if (ic->nb_streams < 1) return -10;
+    codec = avcodec_find_decoder_by_name(decoder);
+    if (!codec) return -11;
+    dc = avcodec_alloc_context3(codec);
+    if ((ret = avcodec_parameters_to_context(dc, ic->streams[0]->codecpar)) < 0) return ret;
+    dc->flags |= AV_CODEC_FLAG_BITEXACT;
+    dc->thread_count = 1;
+    if (dec_opts && *dec_opts && av_set_options_string(dc->priv_data, dec_opts, "=", ":") < 0) return -12;
+    if ((ret = avcodec_open2(dc, codec, NULL)) < 0) return ret;
+    for (;;) {
+        av_init_packet(&pkt); pkt.data = NULL; pkt.size = 0;
+        if (!eof && av_read_frame(ic, &pkt) < 0) eof = 1;
+        ret = avcodec_decode_video2(dc, frame, &got, &pkt);
+        if (!eof) av_packet_unref(&pkt);
+        if (ret < 0) return ret;
+        if (got) {
+            fb = av_image_get_buffer_size(frame->format, frame->width, frame->height, 1);
+            if ((int64_t)(n + 1) * fb > cap) return -13;
+            av_image_copy_to_buffer(dst + (int64_t)n * fb, fb, (const uint8_t *const *)frame->data, frame->linesize,
+                                    frame->format, frame->width, frame->height, 1);
+            if (fmt_name) { strncpy(fmt_name, av_get_pix_fmt_name(frame->format), 31); fmt_name[31] = 0; }
+            av_frame_unref(frame);
+            n++;
+        } else if (eof) break;
+    }
+    if (frame_bytes) *frame_bytes = fb;
+    av_frame_free(&frame);
+    avcodec_close(dc); avcodec_free_context(&dc);
+    av_freep(&ic->pb->buffer); av_freep(&ic->pb);
+    avformat_close_input(&ic);
+    return n;
+}
+

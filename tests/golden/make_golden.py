@@ -35,11 +35,11 @@ print("wrote", len(out), "cases")
 
 def fate_goldens(reference="/root/reference"):
     """tests/golden/fate_vsynth.json: the md5 / size lines of the reference's own FATE goldens for this path
-    (tests/ref/vsynth/vsynth{1,2,3}-ffv1{,-v0,-v3-yuv420p}); test vectors only, used by tests/test_gpu_dropin_avcodec.py"""
+    (tests/ref/vsynth/vsynth{1,2,3}-ffv1{,-v0,-v3-yuv420p,-v3-yuv422p10,-v3-yuv444p16,-v3-bgr0}); test vectors only, used by tests/test_gpu_dropin_avcodec.py"""
     import json, os
     out = {}
     for clip in ("vsynth1", "vsynth2", "vsynth3"):
-        for name in ("ffv1", "ffv1-v0", "ffv1-v3-yuv420p"):
+        for name in ("ffv1", "ffv1-v0", "ffv1-v3-yuv420p", "ffv1-v3-yuv422p10", "ffv1-v3-yuv444p16", "ffv1-v3-bgr0"):
             lines = open(os.path.join(reference, "tests/ref/vsynth/%s-%s" % (clip, name))).read().split("\n")
             out["%s-%s" % (clip, name)] = {"avi_md5": lines[0].split()[0], "avi_size": int(lines[1].split()[0]),
                                            "decoded_md5": lines[2].split()[0]}
