@@ -14,7 +14,9 @@
  * option) so that the GPU sees many GOPs at once, and the batches are PIPELINED:
  *
  *   caller thread   encode2(frame): reference the frame, hand it to the copy workers, return a finished packet if one waits
- *   copy workers    pageable AVFrame rows -> one of three pinned staging areas ("copy_threads" option), off the caller thread
+ *   copy workers    pageable AVFrame rows -> one of three pinned staging areas ("copy_threads" option), and finished packets
+ *                   -> refcounted AVPacket buffers, both off the caller thread (libavcodec's encode wrapper wants every
+ *                   packet in a buffer of its own, utils.c:1965-1995: one 1.2 MB copy per 1080p packet)
  *   batch full      ffv1b200_enc_submit_host(staging area): H2D copies + kernels are queued and the call returns; the
  *                   packets of the batch before last are collected (ffv1b200_enc_collect_async) into one of two pinned
  *                   output areas and handed out one per call
@@ -45,10 +47,12 @@
 #define NOUT   2                       /* packet areas: one being handed out + one being written */
 
 /* ------------------------------------------------------------------------------------------------ encoder */
+struct ReadyPacket;
 typedef struct CopyJob {
-    AVFrame *src;                      /* reference held until the rows are copied */
-    uint8_t *dst;                      /* frame slot inside a staging area */
+    AVFrame *src;                      /* frame job: reference held until the rows are copied */
+    uint8_t *dst;                      /*            frame slot inside a staging area */
     int stage;
+    struct ReadyPacket *rp;            /* packet job (src == NULL): bytes of a finished packet -> its own AVBufferRef */
 } CopyJob;
 
 typedef struct Batch {
@@ -60,6 +64,8 @@ typedef struct ReadyPacket {
     const uint8_t *data;
     int size, flags, out;              /* out: packet area the bytes live in, -1 = own allocation (freed after hand-out) */
     int64_t pts;
+    AVBufferRef *buf;                  /* the packet in a buffer of its own, made by a copy worker (else NULL) */
+    int copied;                        /* the worker is done with this entry (or no worker was asked) */
 } ReadyPacket;
 
 typedef struct B200EncContext {
@@ -119,11 +125,24 @@ static void *copy_worker(void *arg)
         s->job_head = (s->job_head + 1) % s->job_cap;
         s->job_count--;
         pthread_mutex_unlock(&s->lock);
-        copy_frame_rows(s, j.src, j.dst);
-        av_frame_free(&j.src);
-        pthread_mutex_lock(&s->lock);
-        if (--s->outstanding[j.stage] == 0)
+        if (j.src) {
+            copy_frame_rows(s, j.src, j.dst);
+            av_frame_free(&j.src);
+            pthread_mutex_lock(&s->lock);
+            if (--s->outstanding[j.stage] == 0)
+                pthread_cond_broadcast(&s->job_done);
+        } else {
+            /* the buffer av_new_packet() would make (reallocatable, padded), filled here instead of on the caller's thread */
+            AVBufferRef *buf = NULL;
+            if (av_buffer_realloc(&buf, j.rp->size + AV_INPUT_BUFFER_PADDING_SIZE) >= 0) {
+                memcpy(buf->data, j.rp->data, j.rp->size);
+                memset(buf->data + j.rp->size, 0, AV_INPUT_BUFFER_PADDING_SIZE);
+            }
+            pthread_mutex_lock(&s->lock);
+            j.rp->buf = buf;                               /* NULL: out of memory, the caller copies itself */
+            j.rp->copied = 1;
             pthread_cond_broadcast(&s->job_done);
+        }
     }
     pthread_mutex_unlock(&s->lock);
     return NULL;
@@ -139,7 +158,26 @@ static void ready_push(B200EncContext *s, const uint8_t *data, int size, int fla
 {
     ReadyPacket *r = &s->ready[(s->ready_head + s->ready_count) % s->ready_cap];
     r->data = data; r->size = size; r->flags = flags; r->pts = pts; r->out = out;
+    r->buf = NULL; r->copied = 1;
     s->ready_count++;
+}
+
+/* hands the packets pushed last (the n newest entries, their bytes complete) to the copy workers */
+static void ready_precopy(B200EncContext *s, int n)
+{
+    int i;
+    if (!s->nthreads)
+        return;
+    pthread_mutex_lock(&s->lock);
+    for (i = s->ready_count - n; i < s->ready_count; i++) {
+        ReadyPacket *r = &s->ready[(s->ready_head + i) % s->ready_cap];
+        CopyJob *j = &s->jobs[(s->job_head + s->job_count) % s->job_cap];
+        r->copied = 0;
+        j->src = NULL; j->dst = NULL; j->stage = 0; j->rp = r;
+        s->job_count++;
+    }
+    pthread_cond_broadcast(&s->has_job);
+    pthread_mutex_unlock(&s->lock);
 }
 
 /* the packet area `o` is about to be overwritten: packets of it that have not been handed out yet move to their own
@@ -147,9 +185,18 @@ static void ready_push(B200EncContext *s, const uint8_t *data, int size, int fla
 static int spill_area(B200EncContext *s, int o)
 {
     int i;
+    if (s->nthreads) {                                     /* packets the workers are still copying out of this area */
+        pthread_mutex_lock(&s->lock);
+        for (i = 0; i < s->ready_count; i++) {
+            ReadyPacket *r = &s->ready[(s->ready_head + i) % s->ready_cap];
+            while (r->out == o && !r->copied)
+                pthread_cond_wait(&s->job_done, &s->lock);
+        }
+        pthread_mutex_unlock(&s->lock);
+    }
     for (i = 0; i < s->ready_count; i++) {
         ReadyPacket *r = &s->ready[(s->ready_head + i) % s->ready_cap];
-        if (r->out == o) {
+        if (r->out == o && !r->buf) {
             uint8_t *c = av_malloc(r->size ? r->size : 1);
             if (!c)
                 return AVERROR(ENOMEM);
@@ -196,6 +243,13 @@ static int collect_oldest(AVCodecContext *avctx)
     s->out_unsynced = 1;
     for (i = 0; i < b.n; i++)
         ready_push(s, s->out[o] + s->pkts[i].offset, s->pkts[i].size, s->pkts[i].flags, b.pts[i], o);
+    if (s->nthreads) {
+        /* the workers turn the batch into AVPacket buffers while the caller gathers the next frames; they need the bytes
+         * now (the next batch's kernels are already queued on the device, so nothing idles while the copy lands) */
+        if ((ret = sync_output(avctx)) < 0)
+            return ret;
+        ready_precopy(s, b.n);
+    }
     s->inflight[0] = s->inflight[1];
     s->inflight[1] = b;                                  /* keeps its pts array for reuse */
     s->ninflight--;
@@ -295,6 +349,7 @@ static av_cold int b200_encode_close(AVCodecContext *avctx)
         ReadyPacket *r = &s->ready[(s->ready_head + i) % s->ready_cap];
         if (r->out < 0)
             av_free((void *)r->data);
+        av_buffer_unref(&r->buf);
     }
     ffv1b200_enc_close(s->enc);                          /* waits for everything in flight */
     s->enc = NULL;
@@ -391,7 +446,7 @@ static av_cold int b200_encode_init(AVCodecContext *avctx)
         for (i = 0; i < NSTAGE; i++)
             if (!(s->stage[i] = ffv1b200_host_alloc(s->frame_stride * s->batch, s->device)))
                 goto nomem;
-        s->job_cap = s->batch + 1;
+        s->job_cap = 4 * s->batch + 8;                   /* frames being gathered + packets of the batches handed out */
         if (!(s->jobs = av_mallocz_array(s->job_cap, sizeof(*s->jobs))))
             goto nomem;
         pthread_mutex_init(&s->lock, NULL); pthread_cond_init(&s->has_job, NULL); pthread_cond_init(&s->job_done, NULL);
@@ -439,7 +494,7 @@ static int b200_encode_frame(AVCodecContext *avctx, AVPacket *pkt, const AVFrame
         } else if (s->nthreads) {
             pthread_mutex_lock(&s->lock);
             CopyJob *j = &s->jobs[(s->job_head + s->job_count) % s->job_cap];
-            j->src = ref; j->stage = s->cur;
+            j->src = ref; j->stage = s->cur; j->rp = NULL;
             j->dst = s->stage[s->cur] + (size_t)s->nfill * s->frame_stride;
             s->job_count++;
             s->outstanding[s->cur]++;
@@ -461,11 +516,22 @@ static int b200_encode_frame(AVCodecContext *avctx, AVPacket *pkt, const AVFrame
     }
     if (s->ready_count) {
         ReadyPacket *r = &s->ready[s->ready_head];
-        if (r->out >= 0 && (ret = sync_output(avctx)) < 0)
-            return ret;
-        if ((ret = av_new_packet(pkt, r->size)) < 0)
-            return ret;
-        memcpy(pkt->data, r->data, r->size);
+        if (s->nthreads) {
+            pthread_mutex_lock(&s->lock);
+            while (!r->copied)
+                pthread_cond_wait(&s->job_done, &s->lock);
+            pthread_mutex_unlock(&s->lock);
+        }
+        if (r->buf) {                                    /* made by a worker: the packet takes the buffer over */
+            pkt->buf = r->buf; r->buf = NULL;
+            pkt->data = pkt->buf->data; pkt->size = r->size;
+        } else {
+            if (r->out >= 0 && (ret = sync_output(avctx)) < 0)
+                return ret;
+            if ((ret = av_new_packet(pkt, r->size)) < 0)
+                return ret;
+            memcpy(pkt->data, r->data, r->size);
+        }
         pkt->pts = pkt->dts = r->pts;
         if (r->flags & FFV1B200_PKT_FLAG_KEY)
             pkt->flags |= AV_PKT_FLAG_KEY;
