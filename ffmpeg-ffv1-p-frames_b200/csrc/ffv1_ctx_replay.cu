@@ -220,10 +220,17 @@ __global__ void __launch_bounds__(128) k_dec_layout(const EncDeviceTables T, con
     if ((threadIdx.x & 31) == 0 && ndec) atomicAdd(&B.status[3], ndec);
 }
 
+// List entry formats.  FMT 0: 8 bytes {position of the symbol's first decision, residual | frame << 16} (k_replay_ctx,
+// Golomb-Rice).  FMT 1: 4 bytes, position | residual << 22 (k_replay_grp: 8-bit content, residuals fit 10 bits, a window
+// lies inside one frame so the frame index is not needed; a (slice, plane context) decision region must stay below
+// 2^22 entries).  Half the list traffic, and the staged scatter fits four CTAs per SM instead of three.
+constexpr uint32_t kGrpPosBits = 22;
+
 // ------------------------------------------------------------------------------------------------ k_ctx_scatter
 // One warp per context tile; its lines are walked in coding order with one running list position per context in
 // shared memory (initialised from k_ctx_scan's tile bases), so the scatter is stable by construction: inside a
 // 32-sample group match.any ranks order the samples of a context, the leader advances the context's position.
+template <int FMT>
 __global__ void __launch_bounds__(kScatterThreads) k_ctx_scatter(const EncDeviceTables T, const EncBatch B)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -248,7 +255,9 @@ __global__ void __launch_bounds__(kScatterThreads) k_ctx_scatter(const EncDevice
     __syncwarp();
     const uint32_t *rec_slice = B.rec + (size_t)f * L.rec_per_frame + g.rec_first;
     const int32_t *my_lines = T.pc_lines + g.pc_line_first[ct.pc] + ct.first;
-    uint2 *list = B.lists + (size_t)f0 * L.samples_per_frame + (size_t)seglen * g.list_off[ct.pc];
+    const size_t list_at = (size_t)f0 * L.samples_per_frame + (size_t)seglen * g.list_off[ct.pc];
+    uint2 *list = B.lists + list_at;
+    uint32_t *list32 = reinterpret_cast<uint32_t *>(B.lists) + list_at;
     const uint32_t *line_pos = B.line_pos + (size_t)f * L.lines_per_frame + g.line_first;
     for (int l = 0; l < ct.nlines; l++) {
         const int line = my_lines[l];
@@ -272,7 +281,10 @@ __global__ void __launch_bounds__(kScatterThreads) k_ctx_scatter(const EncDevice
                 const uint32_t incl = cr_incl_scan(nd, lane);
                 const uint32_t grp = same_key_lanes(ctx, __ballot_sync(0xFFFFFFFFu, act));       // contexts of this path are < 1024
                 const uint32_t rank = __popc(grp & lt_mask);
-                if (act) list[s_off[ctx] + rank] = make_uint2(pos + incl - nd, (r & 0xFFFFu) | ((uint32_t)f << 16));
+                if (act) {
+                    if (FMT == 1) list32[s_off[ctx] + rank] = (pos + incl - nd) | (r << kGrpPosBits);
+                    else list[s_off[ctx] + rank] = make_uint2(pos + incl - nd, (r & 0xFFFFu) | ((uint32_t)f << 16));
+                }
                 __syncwarp();
                 if (act && rank == 0u) s_off[ctx] += __popc(grp);
                 __syncwarp();
@@ -291,7 +303,7 @@ __global__ void __launch_bounds__(kScatterThreads) k_ctx_scatter(const EncDevice
 constexpr int kScatterSmThreads = 512;
 constexpr int kScatterSmMaxSamples = 5632;               // per tile (16 lines of <= 352 samples): 44 KB of entries
 
-template <bool GOLOMB>
+template <bool GOLOMB, int FMT>
 __global__ void __launch_bounds__(kScatterSmThreads) k_ctx_scatter_sm(const EncDeviceTables T, const EncBatch B)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -306,6 +318,7 @@ __global__ void __launch_bounds__(kScatterSmThreads) k_ctx_scatter_sm(const EncD
     uint16_t *s_cnt = s_start + ((nctx + 7) & ~7);                      // [nctx]
     uint16_t *s_ne = s_cnt + ((nctx + 7) & ~7);                         // [nctx] the contexts that occur in the tile
     uint2 *s_ent = reinterpret_cast<uint2 *>(s_ne + ((nctx + 7) & ~7));
+    uint32_t *s_ent32 = reinterpret_cast<uint32_t *>(s_ent);
     const int tile = blockIdx.x, f = blockIdx.y;
     const CtxTile ct = T.ctiles[tile];
     const SliceGeom &g = T.slices[ct.slice];
@@ -405,21 +418,30 @@ __global__ void __launch_bounds__(kScatterSmThreads) k_ctx_scatter_sm(const EncD
             uint32_t off = 0u;
             if (act && rank == 0u) off = (atomicAdd(&wh[ctx], (uint32_t)__popc(grp) << sh) >> sh) & 0xFFFFu;
             off = __shfl_sync(0xFFFFFFFFu, off, (__ffs(grp) - 1) & 31);
-            if (act) s_ent[(uint32_t)s_start[ctx] + off + rank] = make_uint2(GOLOMB ? rec_line + (uint32_t)(x0 + lane) : pos + in - nd,
-                                                                            (r & 0xFFFFu) | ((uint32_t)f << 16));
+            if (act) {
+                const uint32_t at = (uint32_t)s_start[ctx] + off + rank;
+                if (FMT == 1) s_ent32[at] = (pos + in - nd) | (r << kGrpPosBits);
+                else s_ent[at] = make_uint2(GOLOMB ? rec_line + (uint32_t)(x0 + lane) : pos + in - nd, (r & 0xFFFFu) | ((uint32_t)f << 16));
+            }
             if (!GOLOMB) pos += __shfl_sync(0xFFFFFFFFu, in, 31);
         }
     }
     __syncthreads();
     // runs -> lists: one warp per context, 8 bytes per lane, contiguous
-    uint2 *list = B.lists + (size_t)f0 * L.samples_per_frame + (size_t)seglen * g.list_off[ct.pc];
+    const size_t list_at = (size_t)f0 * L.samples_per_frame + (size_t)seglen * g.list_off[ct.pc];
     const int nne = s_nne;
     for (int i = warp; i < nne; i += kScatterSmThreads / 32) {
         const int c = s_ne[i];
         const uint32_t n = s_cnt[c];
-        uint2 *dst = list + s_goff[c];
-        const uint2 *src = s_ent + s_start[c];
-        for (uint32_t i = lane; i < n; i += 32) dst[i] = src[i];
+        if (FMT == 1) {
+            uint32_t *dst = reinterpret_cast<uint32_t *>(B.lists) + list_at + s_goff[c];
+            const uint32_t *src = s_ent32 + s_start[c];
+            for (uint32_t i = lane; i < n; i += 32) dst[i] = src[i];
+        } else {
+            uint2 *dst = B.lists + list_at + s_goff[c];
+            const uint2 *src = s_ent + s_start[c];
+            for (uint32_t i = lane; i < n; i += 32) dst[i] = src[i];
+        }
     }
 }
 
@@ -683,7 +705,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_replay_grp(const En
         for (int i = tid; i < nctx * 2; i += THREADS)
             st4[i] = key ? make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u) : cin4[i];
     }
-    const uint2 *chain_list = B.lists + (size_t)f0 * L.samples_per_frame + (size_t)(f1 - f0) * sg.list_off[pc];
+    const uint32_t *chain_list = reinterpret_cast<const uint32_t *>(B.lists) + (size_t)f0 * L.samples_per_frame + (size_t)(f1 - f0) * sg.list_off[pc];
     const uint32_t *lstart = B.list_start + (size_t)chain * nctx;
     const uint32_t *lcount = B.list_count + (size_t)chain * nctx;
     const uint16_t *order = B.list_order + (size_t)chain * nctx;
@@ -724,10 +746,10 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_replay_grp(const En
         __syncthreads();
 
         uint32_t n_left = 0u, st = 0u;
-        uint2 nx = make_uint2(0u, 0u);
+        uint32_t nx = 0u;
         int c = -1;
         bool exhausted = false;                                      // no lists left in this frame for my group
-        const uint2 *lp = chain_list;
+        const uint32_t *lp = chain_list;
         for (;;) {
             // ---- groups that finished their list take the next one (longest first)
             if (n_left == 0u && !exhausted) {
@@ -744,14 +766,15 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_replay_grp(const En
                     c = cc; n_left = b1 - b0;
                     lp = chain_list + s_lstart[cc] + b0;
                     st = has_slot ? s_state[cc * 32 + slot] : 0u;
-                    nx = (uint32_t)g < n_left ? lp[g] : make_uint2(0u, 0u);
+                    nx = (uint32_t)g < n_left ? lp[g] : 0u;
                     break;
                 }
             }
             if (!__any_sync(0xFFFFFFFFu, n_left != 0u)) break;
             // ---- a block of up to G symbols per group: masks and positions, one symbol per lane
             const uint32_t m = min((uint32_t)G, n_left);
-            const uint2 en = (uint32_t)g < m ? nx : make_uint2(0u, 0u);
+            const uint32_t ent = (uint32_t)g < m ? nx : 0u;
+            const uint2 en = make_uint2(ent & ((1u << kGrpPosBits) - 1u), (uint32_t)((int)ent >> kGrpPosBits) & 0xFFFFu);   // position, residual
             // the next block of the list is fetched while this one is replayed (the longest list of a frame is the
             // critical path of the whole CTA: its loads must not be exposed)
             if ((uint32_t)(G + g) < n_left) nx = lp[G + g];
@@ -818,15 +841,19 @@ bool ctx_replay_supported(const Layout &L)
 bool ctx_lists_configurable(const Layout &L) { return L.ctx_count <= kMaxListCtx; }
 
 int ctx_scatter_smem_bytes(const Layout &L) { return (kScatterThreads / 32) * L.ctx_count * 4; }
-int ctx_scatter_sm_smem_bytes(const Layout &L) { return 9 * L.ctx_count * 4 + 3 * ((L.ctx_count + 7) & ~7) * 2 + kScatterSmMaxSamples * 8; }
+int ctx_scatter_sm_smem_bytes(const Layout &L, int fmt = 0) { return 9 * L.ctx_count * 4 + 3 * ((L.ctx_count + 7) & ~7) * 2 + kScatterSmMaxSamples * (fmt == 1 ? 4 : 8); }
 
 cudaError_t configure_ctx_replay(const Layout &L)
 {
-    cudaError_t e = cudaFuncSetAttribute(k_ctx_scatter_sm<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx_scatter_sm_smem_bytes(L));
+    cudaError_t e = cudaFuncSetAttribute(k_ctx_scatter_sm<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx_scatter_sm_smem_bytes(L));
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_ctx_scatter_sm<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx_scatter_sm_smem_bytes(L));
+    e = cudaFuncSetAttribute(k_ctx_scatter_sm<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx_scatter_sm_smem_bytes(L, 1));
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_ctx_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx_scatter_smem_bytes(L));
+    e = cudaFuncSetAttribute(k_ctx_scatter_sm<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx_scatter_sm_smem_bytes(L));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_ctx_scatter<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx_scatter_smem_bytes(L));
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_ctx_scatter<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx_scatter_smem_bytes(L));
 }
 
 // Golomb-Rice mode: per-context lists of the samples that get a VLC code ({record index, residual | frame << 16})
@@ -843,10 +870,10 @@ void launch_golomb_lists(const EncDeviceTables &t, const EncBatch &b, cudaStream
     dim3 tiles(L.ctiles_per_frame, b.nframes);
     k_ctx_hist<true><<<tiles, kHistThreads, 0, s>>>(t, b);
     k_ctx_scan<<<nchains, kScanThreads, 0, s>>>(t, b);
-    k_ctx_scatter_sm<true><<<tiles, kScatterSmThreads, ctx_scatter_sm_smem_bytes(L), s>>>(t, b);
+    k_ctx_scatter_sm<true, 0><<<tiles, kScatterSmThreads, ctx_scatter_sm_smem_bytes(L), s>>>(t, b);
 }
 
-void launch_ctx_replay(const EncDeviceTables &t, const EncBatch &b, int max_tile_samples, cudaStream_t s)
+void launch_ctx_replay(const EncDeviceTables &t, const EncBatch &b, int max_tile_samples, uint32_t max_dec_cap, cudaStream_t s)
 {
     const Layout &L = t.layout;
     const int nchains = b.nseg * L.nslices * L.npc;
@@ -855,19 +882,22 @@ void launch_ctx_replay(const EncDeviceTables &t, const EncBatch &b, int max_tile
     k_ctx_scan<<<nchains, kScanThreads, 0, s>>>(t, b);
     const int n = b.nframes * L.nslices * L.npc;
     k_dec_layout<<<(n + 127) / 128, 128, 0, s>>>(t, b);
+    int grp = 2;
+    if (const char *v = getenv("FFV1B200_REPLAY_GROUPS")) grp = atoi(v);
+    // 8-bit content (residuals folded to <= 9 bits): two lists per warp (k_replay_grp) over 4-byte list entries
+    // (position | residual << 22): a (slice, plane context) decision region must stay below 2^22 entries
+    const bool grp_ok = (grp == 1 || grp == 2) && L.coded_bits <= 9 && L.dec_per_frame < 0x7FFFFFFFu && max_dec_cap < (1u << kGrpPosBits);
     // tiles that fit the shared-memory sort (slices up to 352 samples wide) take the staged scatter
     int staged = 1;
     if (const char *v = getenv("FFV1B200_SCATTER")) staged = strcmp(v, "direct") ? 1 : 0;
     if (staged && max_tile_samples <= kScatterSmMaxSamples) {
-        k_ctx_scatter_sm<false><<<tiles, kScatterSmThreads, ctx_scatter_sm_smem_bytes(L), s>>>(t, b);
+        if (grp_ok) k_ctx_scatter_sm<false, 1><<<tiles, kScatterSmThreads, ctx_scatter_sm_smem_bytes(L, 1), s>>>(t, b);
+        else        k_ctx_scatter_sm<false, 0><<<tiles, kScatterSmThreads, ctx_scatter_sm_smem_bytes(L), s>>>(t, b);
     } else {
         dim3 stiles((L.ctiles_per_frame + kScatterThreads / 32 - 1) / (kScatterThreads / 32), b.nframes);
-        k_ctx_scatter<<<stiles, kScatterThreads, ctx_scatter_smem_bytes(L), s>>>(t, b);
+        if (grp_ok) k_ctx_scatter<1><<<stiles, kScatterThreads, ctx_scatter_smem_bytes(L), s>>>(t, b);
+        else        k_ctx_scatter<0><<<stiles, kScatterThreads, ctx_scatter_smem_bytes(L), s>>>(t, b);
     }
-    int grp = 2;
-    if (const char *v = getenv("FFV1B200_REPLAY_GROUPS")) grp = atoi(v);
-    // 8-bit content (residuals folded to <= 9 bits): two lists per warp; a frame's decision area must fit 32-bit offsets
-    const bool grp_ok = L.coded_bits <= 9 && L.dec_per_frame < 0x7FFFFFFFu;
     int window = 3;
     if (const char *v = getenv("FFV1B200_REPLAY_WINDOW")) { window = atoi(v); if (window < 1) window = 1 << 20; }
     if (grp == 1 && grp_ok) k_replay_grp<4, 1024><<<nchains, 1024, replay_grp_smem(L), s>>>(t, b, window);

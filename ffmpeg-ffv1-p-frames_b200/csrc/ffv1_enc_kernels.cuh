@@ -87,7 +87,7 @@ cudaError_t configure_kernels(const Layout &L);
 // context-decomposed state replay (ffv1_ctx_replay.cu)
 bool ctx_replay_supported(const Layout &L);
 cudaError_t configure_ctx_replay(const Layout &L);
-void launch_ctx_replay(const EncDeviceTables &t, const EncBatch &b, int max_tile_samples, cudaStream_t s);
+void launch_ctx_replay(const EncDeviceTables &t, const EncBatch &b, int max_tile_samples, uint32_t max_dec_cap, cudaStream_t s);
 // tuned per-pixel pass for planar sources (ffv1_pixel_fast.cu)
 // one work item of a frame: up to 32 rows x <= 512 bytes of one slice-plane (everything the kernel needs, precomputed)
 struct alignas(16) FastItemDesc {

@@ -239,7 +239,11 @@ int enqueue_kernels(FFV1B200Encoder *e, Slot &sl, cudaStream_t s)
     }
     else         launch_pixel(t, b, s);
     cudaEventRecord(sl.ev[1], s);
-    if (e->ctx_replay) launch_ctx_replay(t, b, e->max_ctile_samples, s);
+    if (e->ctx_replay) {
+        uint32_t max_dec_cap = 0;
+        for (const SliceGeom &g : e->tab.slices) for (int pc = 0; pc < 3; pc++) max_dec_cap = std::max(max_dec_cap, g.dec_cap[pc]);
+        launch_ctx_replay(t, b, e->max_ctile_samples, max_dec_cap, s);
+    }
     else if (!L.golomb) launch_replay(t, b, s);
     cudaEventRecord(sl.ev[2], s);
     if (!L.golomb) launch_rangecode(t, b, s);
