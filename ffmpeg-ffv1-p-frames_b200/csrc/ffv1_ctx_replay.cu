@@ -25,7 +25,8 @@ constexpr int kHistThreads = 256;
 constexpr int kScanThreads = 1024;                       // one context per thread (<= kMaxListCtx)
 constexpr int kScatterThreads = 128;                     // four tiles (one warp each) per CTA
 constexpr int kCtxThreads = 1024;
-constexpr int kMaxListCtx = 1024;
+constexpr int kMaxListCtx = 1024;                        // shared-memory sort / two-lists-per-warp replay / Golomb-Rice lists
+constexpr int kMaxBigListCtx = 8192;                     // large context model (7563 contexts): direct scatter, model in global memory
 
 __device__ __forceinline__ uint32_t cr_incl_scan(uint32_t v, int lane)
 {
@@ -37,12 +38,13 @@ __device__ __forceinline__ uint32_t cr_incl_scan(uint32_t v, int lane)
     return v;
 }
 
-// lanes (among `active`) holding the same 10-bit key as the caller: ten ballots (match.any is far slower here)
+// lanes (among `active`) holding the same KEYBITS-bit key as the caller: one ballot per bit (match.any is far slower here)
+template <int KEYBITS>
 __device__ __forceinline__ uint32_t same_key_lanes(uint32_t key, uint32_t active)
 {
     uint32_t grp = active;
 #pragma unroll
-    for (int b = 0; b < 10; b++) {
+    for (int b = 0; b < KEYBITS; b++) {
         const bool bit = (key >> b) & 1u;
         const uint32_t m = __ballot_sync(0xFFFFFFFFu, bit);
         grp &= bit ? m : ~m;
@@ -74,7 +76,7 @@ __device__ __forceinline__ uint32_t gr_run_members(uint32_t ctx0, uint32_t zero,
 template <bool GOLOMB>
 __global__ void __launch_bounds__(kHistThreads) k_ctx_hist(const EncDeviceTables T, const EncBatch B)
 {
-    __shared__ uint32_t s_hist[kMaxListCtx];
+    extern __shared__ uint32_t s_hist[];                    // [ctx_count]
     const Layout &L = T.layout;
     const CtxTile ct = T.ctiles[blockIdx.x];
     const int f = blockIdx.y;
@@ -117,15 +119,15 @@ __global__ void __launch_bounds__(kHistThreads) k_ctx_hist(const EncDeviceTables
 // ------------------------------------------------------------------------------------------------ k_ctx_scan
 __global__ void __launch_bounds__(kScanThreads) k_ctx_scan(const EncDeviceTables T, const EncBatch B)
 {
-    __shared__ uint32_t s_total[kMaxListCtx];
-    __shared__ uint32_t s_start[kMaxListCtx];
-    __shared__ uint32_t s_warp[8];
+    extern __shared__ uint32_t s_scan[];                    // [ctx_count] list lengths, [ctx_count] list starts
+    __shared__ uint32_t s_warp[kScanThreads / 32];
     const Layout &L = T.layout;
     const int chain = blockIdx.x;
     const int pc = chain % L.npc, s = (chain / L.npc) % L.nslices, seg = chain / (L.npc * L.nslices);
     const SliceGeom &g = T.slices[s];
     const int f0 = B.seg_first[seg], f1 = B.seg_first[seg + 1];
     const int nctx = L.ctx_count, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t *s_total = s_scan, *s_start = s_scan + nctx;
     const int t0 = g.ct_first[pc], nt = g.ct_count[pc];
     for (int c = tid; c < nctx; c += kScanThreads) {
         uint32_t run = 0;
@@ -144,18 +146,17 @@ __global__ void __launch_bounds__(kScanThreads) k_ctx_scan(const EncDeviceTables
         s_total[c] = run;
     }
     __syncthreads();
-    // exclusive scan over the contexts: 4 consecutive contexts per thread (the first 256 threads)
+    // exclusive scan over the contexts: K consecutive contexts per thread (1 for the small model, 8 for 7563 contexts)
     {
-        uint32_t v[4], sum = 0;
-#pragma unroll
-        for (int k = 0; k < 4; k++) { const int c = tid * 4 + k; v[k] = c < nctx ? s_total[c] : 0u; sum += v[k]; }
+        const int K = (nctx + kScanThreads - 1) / kScanThreads;
+        uint32_t sum = 0;
+        for (int k = 0; k < K; k++) { const int c = tid * K + k; if (c < nctx) sum += s_total[c]; }
         const uint32_t incl = cr_incl_scan(sum, lane);
-        if (lane == 31 && warp < 8) s_warp[warp] = incl;
+        if (lane == 31) s_warp[warp] = incl;
         __syncthreads();
         uint32_t base = incl - sum;
-        for (int w = 0; w < min(warp, 8); w++) base += s_warp[w];
-#pragma unroll
-        for (int k = 0; k < 4; k++) { const int c = tid * 4 + k; if (c < nctx) s_start[c] = base; base += v[k]; }
+        for (int w = 0; w < warp; w++) base += s_warp[w];
+        for (int k = 0; k < K; k++) { const int c = tid * K + k; if (c < nctx) { s_start[c] = base; base += s_total[c]; } }
     }
     __syncthreads();
     for (int c = tid; c < nctx; c += kScanThreads) {
@@ -230,7 +231,7 @@ constexpr uint32_t kGrpPosBits = 22;
 // One warp per context tile; its lines are walked in coding order with one running list position per context in
 // shared memory (initialised from k_ctx_scan's tile bases), so the scatter is stable by construction: inside a
 // 32-sample group match.any ranks order the samples of a context, the leader advances the context's position.
-template <int FMT>
+template <int FMT, int KEYBITS>
 __global__ void __launch_bounds__(kScatterThreads) k_ctx_scatter(const EncDeviceTables T, const EncBatch B)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -279,7 +280,7 @@ __global__ void __launch_bounds__(kScatterThreads) k_ctx_scatter(const EncDevice
                 const uint32_t ctx = r >> 16;
                 const uint32_t nd = act ? decisions_of((int)(int16_t)(r & 0xFFFFu)) : 0u;
                 const uint32_t incl = cr_incl_scan(nd, lane);
-                const uint32_t grp = same_key_lanes(ctx, __ballot_sync(0xFFFFFFFFu, act));       // contexts of this path are < 1024
+                const uint32_t grp = same_key_lanes<KEYBITS>(ctx, __ballot_sync(0xFFFFFFFFu, act));   // contexts are < 2^KEYBITS
                 const uint32_t rank = __popc(grp & lt_mask);
                 if (act) {
                     if (FMT == 1) list32[s_off[ctx] + rank] = (pos + incl - nd) | (r << kGrpPosBits);
@@ -481,15 +482,17 @@ __device__ __forceinline__ void visit_step(uint16_t *addr, uint32_t val, uint32_
                  : "+r"(st) : "l"(addr), "h"((unsigned short)val), "r"(saddr), "r"(pred) : "memory");
 }
 
-template <bool HIGH_E>
+// GSTATE: the chain's model stays in global memory (B.state_seg; the large context model's 7563 x 32 bytes do not fit an
+// SM's shared memory).  A list only reads its row when it is taken up and writes it back when the frame's part is done.
+template <bool HIGH_E, bool GSTATE>
 __global__ void __launch_bounds__(kCtxThreads, 1) k_replay_ctx(const EncDeviceTables T, const EncBatch B)
 {
     extern __shared__ __align__(16) unsigned char s_state_raw[];     // [ctx_count][32] the chain's model
     __shared__ uint8_t s_lut[512];
     __shared__ uint4 s_blk_all[kCtxThreads];
     __shared__ int s_next;
-    uint8_t *s_state = s_state_raw;
     const Layout &L = T.layout;
+    uint8_t *s_state = GSTATE ? B.state_seg + (size_t)blockIdx.x * ((size_t)L.ctx_count * 32) : s_state_raw;
     const int tid = threadIdx.x, lane = tid & 31;
     uint4 *s_blk = s_blk_all + (tid & ~31);
     const uint32_t lut_base = (uint32_t)__cvta_generic_to_shared(s_lut);
@@ -833,10 +836,14 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_replay_grp(const En
 
 static int replay_grp_smem(const Layout &L) { return L.ctx_count * (32 + 12 + 2) + 16; }
 
+static bool big_model(const Layout &L) { return L.ctx_count > kMaxListCtx; }
+
 bool ctx_replay_supported(const Layout &L)
 {
-    return !L.golomb && L.ctx_count <= kMaxListCtx;
+    return !L.golomb && L.ctx_count <= kMaxBigListCtx;
 }
+
+bool ctx_replay_needs_global_state(const Layout &L) { return big_model(L); }
 
 bool ctx_lists_configurable(const Layout &L) { return L.ctx_count <= kMaxListCtx; }
 
@@ -845,15 +852,21 @@ int ctx_scatter_sm_smem_bytes(const Layout &L, int fmt = 0) { return 9 * L.ctx_c
 
 cudaError_t configure_ctx_replay(const Layout &L)
 {
-    cudaError_t e = cudaFuncSetAttribute(k_ctx_scatter_sm<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx_scatter_sm_smem_bytes(L));
+    cudaError_t e;
+    if (big_model(L)) {
+        e = cudaFuncSetAttribute(k_ctx_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, L.ctx_count * 8);
+        if (e != cudaSuccess) return e;
+        return cudaFuncSetAttribute(k_ctx_scatter<0, 13>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx_scatter_smem_bytes(L));
+    }
+    e = cudaFuncSetAttribute(k_ctx_scatter_sm<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx_scatter_sm_smem_bytes(L));
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_ctx_scatter_sm<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx_scatter_sm_smem_bytes(L, 1));
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_ctx_scatter_sm<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx_scatter_sm_smem_bytes(L));
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_ctx_scatter<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx_scatter_smem_bytes(L));
+    e = cudaFuncSetAttribute(k_ctx_scatter<0, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx_scatter_smem_bytes(L));
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_ctx_scatter<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx_scatter_smem_bytes(L));
+    return cudaFuncSetAttribute(k_ctx_scatter<1, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx_scatter_smem_bytes(L));
 }
 
 // Golomb-Rice mode: per-context lists of the samples that get a VLC code ({record index, residual | frame << 16})
@@ -868,8 +881,8 @@ void launch_golomb_lists(const EncDeviceTables &t, const EncBatch &b, cudaStream
     const Layout &L = t.layout;
     const int nchains = b.nseg * L.nslices * L.npc;
     dim3 tiles(L.ctiles_per_frame, b.nframes);
-    k_ctx_hist<true><<<tiles, kHistThreads, 0, s>>>(t, b);
-    k_ctx_scan<<<nchains, kScanThreads, 0, s>>>(t, b);
+    k_ctx_hist<true><<<tiles, kHistThreads, L.ctx_count * 4, s>>>(t, b);
+    k_ctx_scan<<<nchains, kScanThreads, L.ctx_count * 8, s>>>(t, b);
     k_ctx_scatter_sm<true, 0><<<tiles, kScatterSmThreads, ctx_scatter_sm_smem_bytes(L), s>>>(t, b);
 }
 
@@ -878,10 +891,19 @@ void launch_ctx_replay(const EncDeviceTables &t, const EncBatch &b, int max_tile
     const Layout &L = t.layout;
     const int nchains = b.nseg * L.nslices * L.npc;
     dim3 tiles(L.ctiles_per_frame, b.nframes);
-    k_ctx_hist<false><<<tiles, kHistThreads, 0, s>>>(t, b);
-    k_ctx_scan<<<nchains, kScanThreads, 0, s>>>(t, b);
+    k_ctx_hist<false><<<tiles, kHistThreads, L.ctx_count * 4, s>>>(t, b);
+    k_ctx_scan<<<nchains, kScanThreads, L.ctx_count * 8, s>>>(t, b);
     const int n = b.nframes * L.nslices * L.npc;
     k_dec_layout<<<(n + 127) / 128, 128, 0, s>>>(t, b);
+    dim3 stiles((L.ctiles_per_frame + kScatterThreads / 32 - 1) / (kScatterThreads / 32), b.nframes);
+    if (big_model(L)) {
+        // large context model: lists straight from the records (a tile's per-line histograms would not fit shared memory),
+        // one CTA per chain replays them against the model in global memory
+        k_ctx_scatter<0, 13><<<stiles, kScatterThreads, ctx_scatter_smem_bytes(L), s>>>(t, b);
+        if (L.coded_bits <= 10) k_replay_ctx<false, true><<<nchains, kCtxThreads, 0, s>>>(t, b);
+        else                    k_replay_ctx<true, true><<<nchains, kCtxThreads, 0, s>>>(t, b);
+        return;
+    }
     int grp = 2;
     if (const char *v = getenv("FFV1B200_REPLAY_GROUPS")) grp = atoi(v);
     // 8-bit content (residuals folded to <= 9 bits): two lists per warp (k_replay_grp) over 4-byte list entries
@@ -894,9 +916,8 @@ void launch_ctx_replay(const EncDeviceTables &t, const EncBatch &b, int max_tile
         if (grp_ok) k_ctx_scatter_sm<false, 1><<<tiles, kScatterSmThreads, ctx_scatter_sm_smem_bytes(L, 1), s>>>(t, b);
         else        k_ctx_scatter_sm<false, 0><<<tiles, kScatterSmThreads, ctx_scatter_sm_smem_bytes(L), s>>>(t, b);
     } else {
-        dim3 stiles((L.ctiles_per_frame + kScatterThreads / 32 - 1) / (kScatterThreads / 32), b.nframes);
-        if (grp_ok) k_ctx_scatter<1><<<stiles, kScatterThreads, ctx_scatter_smem_bytes(L), s>>>(t, b);
-        else        k_ctx_scatter<0><<<stiles, kScatterThreads, ctx_scatter_smem_bytes(L), s>>>(t, b);
+        if (grp_ok) k_ctx_scatter<1, 10><<<stiles, kScatterThreads, ctx_scatter_smem_bytes(L), s>>>(t, b);
+        else        k_ctx_scatter<0, 10><<<stiles, kScatterThreads, ctx_scatter_smem_bytes(L), s>>>(t, b);
     }
     int window = 3;
     if (const char *v = getenv("FFV1B200_REPLAY_WINDOW")) { window = atoi(v); if (window < 1) window = 1 << 20; }
@@ -908,8 +929,8 @@ void launch_ctx_replay(const EncDeviceTables &t, const EncBatch &b, int max_tile
         else if (threads == 256) k_replay_grp<4, 256><<<nchains, 256, replay_grp_smem(L), s>>>(t, b, window);
         else                     k_replay_grp<4, 512><<<nchains, 512, replay_grp_smem(L), s>>>(t, b, window);
     }
-    else if (L.coded_bits <= 10) k_replay_ctx<false><<<nchains, kCtxThreads, L.ctx_count * 32, s>>>(t, b);
-    else                    k_replay_ctx<true><<<nchains, kCtxThreads, L.ctx_count * 32, s>>>(t, b);
+    else if (L.coded_bits <= 10) k_replay_ctx<false, false><<<nchains, kCtxThreads, L.ctx_count * 32, s>>>(t, b);
+    else                    k_replay_ctx<true, false><<<nchains, kCtxThreads, L.ctx_count * 32, s>>>(t, b);
 }
 
 } // namespace ffv1

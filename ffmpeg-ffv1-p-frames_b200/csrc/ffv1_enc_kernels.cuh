@@ -86,6 +86,7 @@ void launch_pack(const EncDeviceTables &t, const EncBatch &b, cudaStream_t s);
 cudaError_t configure_kernels(const Layout &L);
 // context-decomposed state replay (ffv1_ctx_replay.cu)
 bool ctx_replay_supported(const Layout &L);
+bool ctx_replay_needs_global_state(const Layout &L);      // large context model: B.state_seg holds one model per chain
 cudaError_t configure_ctx_replay(const Layout &L);
 void launch_ctx_replay(const EncDeviceTables &t, const EncBatch &b, int max_tile_samples, uint32_t max_dec_cap, cudaStream_t s);
 // tuned per-pixel pass for planar sources (ffv1_pixel_fast.cu)

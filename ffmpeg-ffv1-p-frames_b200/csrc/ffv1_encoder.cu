@@ -156,7 +156,7 @@ int alloc_buffers(FFV1B200Encoder *e)
         CU_TRY(e->d_list_order.alloc(nchains * L.ctx_count));
         CU_TRY(e->d_lists.alloc((size_t)L.samples_per_frame * F));
     }
-    if ((!e->state_in_smem && !e->ctx_replay) || (L.golomb && !e->golomb_lists))
+    if ((!e->state_in_smem && !e->ctx_replay) || (e->ctx_replay && ctx_replay_needs_global_state(L)) || (L.golomb && !e->golomb_lists))
         CU_TRY(e->d_state_seg.alloc(state_bytes * nseg_max));            // one state set per GOP segment of a batch
     for (Slot &sl : e->slot) {
         CU_TRY(sl.d_planes.alloc(F * 4)); CU_TRY(sl.h_planes.alloc(F * 4));
