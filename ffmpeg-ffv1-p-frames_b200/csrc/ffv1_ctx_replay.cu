@@ -522,6 +522,20 @@ __global__ void __launch_bounds__(kCtxThreads, 1) k_replay_ctx(const EncDeviceTa
     const int slot = slot_of_lane(lane);
     const uint32_t lanebit = 1u << lane, lt_mask = lanebit - 1u;
     const int t0 = g.ct_first[pc];
+    // list bookkeeping of the current frame in shared memory (behind the model, when that is there too): where the
+    // frame's part of every list starts, how long it is, and the processing order -- taking the next list costs no
+    // global load (with 7563 mostly short lists the dependent loads of a take were most of the kernel's time)
+    uint32_t *s_at = reinterpret_cast<uint32_t *>(s_state_raw + (GSTATE ? 0 : (size_t)nctx * 32));
+    uint32_t *s_n = s_at + nctx;
+    uint16_t *s_order = reinterpret_cast<uint16_t *>(s_n + nctx);
+    __shared__ int s_nlists;
+    if (tid == 0) s_nlists = 0;
+    __syncthreads();
+    for (int i = tid; i < nctx; i += kCtxThreads) {
+        const uint16_t c = order[i];
+        s_order[i] = c;
+        if (lcount[c]) atomicMax(&s_nlists, i + 1);             // the order is by list length: the non-empty lists come first
+    }
 
     // Frame after frame: all warps of the CTA work on the same (chain, frame), so the decision region they scatter
     // into (one frame of one slice-plane-context, < 1 MB) is completed while it is still in L2 -- with every list
@@ -529,23 +543,28 @@ __global__ void __launch_bounds__(kCtxThreads, 1) k_replay_ctx(const EncDeviceTa
     for (int f = f0; f < f1; f++) {
       __syncthreads();                                              // model loaded / previous frame finished
       if (tid == 0) s_next = 0;
+      {
+        // symbols of context c that precede frame f (f+1) inside the chain = scanned histogram of the chain's first tile
+        const uint32_t *before = B.ctx_hist + ((size_t)f * L.ctiles_per_frame + t0) * nctx;
+        const uint32_t *before_next = B.ctx_hist + ((size_t)(f + 1) * L.ctiles_per_frame + t0) * nctx;
+        const bool more = f + 1 < f1;
+        for (int i = tid; i < nctx; i += kCtxThreads) {
+            const uint32_t b0 = before[i], b1 = more ? before_next[i] : lcount[i];
+            s_at[i] = lstart[i] + b0; s_n[i] = b1 - b0;
+        }
+      }
       __syncthreads();
-      // symbols of context c that precede frame f (f+1) inside the chain = scanned histogram of the chain's first tile
-      const uint32_t *before = B.ctx_hist + ((size_t)f * L.ctiles_per_frame + t0) * nctx;
-      const uint32_t *before_next = B.ctx_hist + ((size_t)(f + 1) * L.ctiles_per_frame + t0) * nctx;
+      const int nlists = s_nlists;
       for (;;) {
         int oi = 0;
         if (lane == 0) oi = atomicAdd(&s_next, 1);
         oi = __shfl_sync(0xFFFFFFFFu, oi, 0);
-        if (oi >= nctx) break;
-        const int c = order[oi];
-        const uint32_t ntot = lcount[c];
-        if (ntot == 0u) break;                                  // contexts are ordered by the length of their chain list
-        const uint32_t b0 = before[c], b1 = f + 1 < f1 ? before_next[c] : ntot;
-        const uint32_t n = b1 - b0;
+        if (oi >= nlists) break;
+        const int c = s_order[oi];
+        const uint32_t n = s_n[c];
         if (n == 0u) continue;
         uint32_t st = s_state[c * 32 + slot];
-        const uint2 *lp = chain_list + lstart[c] + b0;
+        const uint2 *lp = chain_list + s_at[c];
         uint2 nx = lane < n ? lp[lane] : make_uint2(0u, 0u);
         for (uint32_t j0 = 0; j0 < n; j0 += 32u) {
             const uint32_t m = min(32u, n - j0);
@@ -856,6 +875,10 @@ cudaError_t configure_ctx_replay(const Layout &L)
     if (big_model(L)) {
         e = cudaFuncSetAttribute(k_ctx_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, L.ctx_count * 8);
         if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(k_replay_ctx<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.ctx_count * 10);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(k_replay_ctx<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.ctx_count * 10);
+        if (e != cudaSuccess) return e;
         return cudaFuncSetAttribute(k_ctx_scatter<0, 13>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx_scatter_smem_bytes(L));
     }
     e = cudaFuncSetAttribute(k_ctx_scatter_sm<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx_scatter_sm_smem_bytes(L));
@@ -900,8 +923,8 @@ void launch_ctx_replay(const EncDeviceTables &t, const EncBatch &b, int max_tile
         // large context model: lists straight from the records (a tile's per-line histograms would not fit shared memory),
         // one CTA per chain replays them against the model in global memory
         k_ctx_scatter<0, 13><<<stiles, kScatterThreads, ctx_scatter_smem_bytes(L), s>>>(t, b);
-        if (L.coded_bits <= 10) k_replay_ctx<false, true><<<nchains, kCtxThreads, 0, s>>>(t, b);
-        else                    k_replay_ctx<true, true><<<nchains, kCtxThreads, 0, s>>>(t, b);
+        if (L.coded_bits <= 10) k_replay_ctx<false, true><<<nchains, kCtxThreads, L.ctx_count * 10, s>>>(t, b);
+        else                    k_replay_ctx<true, true><<<nchains, kCtxThreads, L.ctx_count * 10, s>>>(t, b);
         return;
     }
     int grp = 2;
@@ -929,8 +952,8 @@ void launch_ctx_replay(const EncDeviceTables &t, const EncBatch &b, int max_tile
         else if (threads == 256) k_replay_grp<4, 256><<<nchains, 256, replay_grp_smem(L), s>>>(t, b, window);
         else                     k_replay_grp<4, 512><<<nchains, 512, replay_grp_smem(L), s>>>(t, b, window);
     }
-    else if (L.coded_bits <= 10) k_replay_ctx<false, false><<<nchains, kCtxThreads, L.ctx_count * 32, s>>>(t, b);
-    else                    k_replay_ctx<true, false><<<nchains, kCtxThreads, L.ctx_count * 32, s>>>(t, b);
+    else if (L.coded_bits <= 10) k_replay_ctx<false, false><<<nchains, kCtxThreads, L.ctx_count * 42, s>>>(t, b);
+    else                    k_replay_ctx<true, false><<<nchains, kCtxThreads, L.ctx_count * 42, s>>>(t, b);
 }
 
 } // namespace ffv1

@@ -737,10 +737,12 @@ void build_tables(const Config &c, Tables &t)
             g.pc_nlines[pc] = (int32_t)t.pc_lines.size() - g.pc_line_first[pc];
             g.pc_samples[pc] = ns;
             g.ct_first[pc] = (int32_t)t.ctiles.size();
-            for (int l0 = 0; l0 < g.pc_nlines[pc]; l0 += kCtxTileLines) {
+            // the large context model's tiles are four times as tall: a tile carries a histogram of all 7563 contexts
+            const int tile_lines = L.ctx_count > 1024 ? 4 * kCtxTileLines : kCtxTileLines;
+            for (int l0 = 0; l0 < g.pc_nlines[pc]; l0 += tile_lines) {
                 CtxTile ct;
                 ct.slice = (uint16_t)si; ct.pc = (uint8_t)pc; ct.first = (uint32_t)l0;
-                ct.nlines = (uint8_t)std::min(kCtxTileLines, g.pc_nlines[pc] - l0);
+                ct.nlines = (uint8_t)std::min(tile_lines, g.pc_nlines[pc] - l0);
                 t.ctiles.push_back(ct);
             }
             g.ct_count[pc] = (int32_t)t.ctiles.size() - g.ct_first[pc];

@@ -50,7 +50,7 @@ def clip_s2(n):
     return b.s2_clip(n)
 
 CONFIGS = {
-    "c3": dict(w=1920, h=1080, fmt="yuv422p10le", opts=dict(level=3, coder=0, context=1), clip=clip_s3, nclip=16, frames=1024,
+    "c3": dict(w=1920, h=1080, fmt="yuv422p10le", opts=dict(level=3, coder=0, context=1), clip=clip_s3, nclip=16, frames=512,
                what="BASELINE configs[2]: 1080p yuv422p10, GOP 16, coder 0 requested (range coder forced), context=1, 4 slices"),
     "c4": dict(w=3840, h=2160, fmt="gbrp14le", opts=dict(level=3, coder=2, context=0, slices=30), clip=clip_s4, nclip=4, frames=64,
                what="BASELINE configs[3]: 2160p gbrp14le (RCT, 15-bit residuals), GOP 16, coder=2, 30 slices"),
