@@ -506,12 +506,12 @@ __global__ void __launch_bounds__(kCtxThreads, 1) k_replay_ctx(const EncDeviceTa
     const bool key = B.frame_key[f0] != 0;
     const bool hand_over = f1 == B.nframes;
     const size_t coff = ((size_t)s * L.npc + pc) * ((size_t)nctx * 32);
-    // ---- the chain's model: 128 on keyframes (ffv1.c:177-202), else what the previous batch left
+    // ---- the chain's model: the initial states on keyframes (128, or a two-pass encode's table; ffv1.c:177-202), else what the previous batch left
     {
         const uint4 *cin4 = reinterpret_cast<const uint4 *>(B.carry_in + coff);
         uint4 *st4 = reinterpret_cast<uint4 *>(s_state);
         for (int i = tid; i < nctx * 2; i += kCtxThreads)
-            st4[i] = key ? make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u) : cin4[i];
+            st4[i] = key ? (T.init_state ? reinterpret_cast<const uint4 *>(T.init_state)[i] : make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u)) : cin4[i];
     }
 
     const uint2 *chain_list = B.lists + (size_t)f0 * L.samples_per_frame + (size_t)(f1 - f0) * g.list_off[pc];
@@ -725,7 +725,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_replay_grp(const En
         const uint4 *cin4 = reinterpret_cast<const uint4 *>(B.carry_in + coff);
         uint4 *st4 = reinterpret_cast<uint4 *>(s_state);
         for (int i = tid; i < nctx * 2; i += THREADS)
-            st4[i] = key ? make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u) : cin4[i];
+            st4[i] = key ? (T.init_state ? reinterpret_cast<const uint4 *>(T.init_state)[i] : make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u)) : cin4[i];
     }
     const uint32_t *chain_list = reinterpret_cast<const uint32_t *>(B.lists) + (size_t)f0 * L.samples_per_frame + (size_t)(f1 - f0) * sg.list_off[pc];
     const uint32_t *lstart = B.list_start + (size_t)chain * nctx;

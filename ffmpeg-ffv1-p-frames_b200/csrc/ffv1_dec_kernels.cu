@@ -573,10 +573,12 @@ __global__ void __launch_bounds__(32 * kDecWarps, MINB) k_decode(const DecDevice
         if (key) {
             for (int pc = 0; pc < 3; pc++) {
                 uint8_t *m = models + (size_t)pc * T.state_stride;
-                const int nctx = T.ctx_count[qti[pc < T.plane_count ? pc : 0]];
+                const int set = qti[pc < T.plane_count ? pc : 0];
+                const int nctx = T.ctx_count[set];
                 if (!golomb) {
                     uint32_t *m4 = reinterpret_cast<uint32_t *>(m);
-                    for (int i = lane; i < nctx * 8; i += 32) m4[i] = 0x80808080u;
+                    const uint32_t *i4 = reinterpret_cast<const uint32_t *>(T.model_init[set]);      // ffv1.c:188-190
+                    for (int i = lane; i < nctx * 8; i += 32) m4[i] = i4 ? i4[i] : 0x80808080u;
                 } else {
                     uint2 *m8 = reinterpret_cast<uint2 *>(m);
                     // VlcState {drift 0, error_sum 4, bias 0, count 1}

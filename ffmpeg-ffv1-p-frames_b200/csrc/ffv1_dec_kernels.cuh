@@ -18,6 +18,7 @@ struct DecDeviceTables {
     int64_t frame_bytes;
     const int16_t *quant;               // [2][5][256]
     const uint8_t *lut;                 // [512] zero_state | one_state the slice coders run with
+    const uint8_t *model_init[2];       // per table set: [ctx_count][32] states a keyframe starts from (two-pass streams), or null = 128
     int64_t state_stride;               // bytes of one (slice, plane context) model
     int32_t ring_w;                     // int16 elements per ring row
     int32_t smem_model;                 // bytes of shared memory per chain for the current plane context's model (0 = keep it in global memory)

@@ -18,7 +18,7 @@ struct FFV1B200Decoder {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[4] = {nullptr};
     DecDeviceTables tab{};
-    DevBuf<int16_t> d_quant; DevBuf<uint8_t> d_lut;
+    DevBuf<int16_t> d_quant; DevBuf<uint8_t> d_lut, d_model_init[2];
     DevBuf<uint8_t> d_pkt, d_out, d_state, d_prev, d_frame_key;
     PinnedBuf<uint8_t> h_pkt, h_frame_key;
     DevBuf<int16_t> d_ring;
@@ -87,6 +87,13 @@ static int configure(FFV1B200Decoder *d)
     coder_state_tables(c, lut, lut + 256);
     CU_TRY(d->d_lut.upload(lut, 512, d->stream));
     t.quant = d->d_quant.p; t.lut = d->d_lut.p;
+    for (int i = 0; i < 2; i++) {
+        t.model_init[i] = nullptr;
+        if (!c.initial_states[i].empty() && c.ac != AC_GOLOMB) {
+            CU_TRY(d->d_model_init[i].upload(c.initial_states[i].data(), c.initial_states[i].size(), d->stream));
+            t.model_init[i] = d->d_model_init[i].p;
+        }
+    }
 
     const size_t F = (size_t)d->max_batch;
     d->nsets = d->max_batch + 1;

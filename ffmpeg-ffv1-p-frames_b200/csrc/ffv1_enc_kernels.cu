@@ -377,7 +377,7 @@ k_replay(const EncDeviceTables T, const EncBatch B)
         const uint32_t *in4 = reinterpret_cast<const uint32_t *>(B.carry_in + coff);
         uint32_t *st4 = reinterpret_cast<uint32_t *>(st);
         for (int i = lane; i < nctx * 8; i += 32)
-            st4[(i >> 3) * (RS / 4) + (i & 7)] = key ? 0x80808080u : in4[i];
+            st4[(i >> 3) * (RS / 4) + (i & 7)] = key ? (T.init_state ? reinterpret_cast<const uint32_t *>(T.init_state)[i] : 0x80808080u) : in4[i];
         __syncwarp();
     }
 
@@ -1460,6 +1460,90 @@ void launch_pack(const EncDeviceTables &t, const EncBatch &b, cudaStream_t s)
     k_pack_layout<<<1, 1024, 0, s>>>(t, b);
     if (t.layout.golomb) k_pack_slices<false><<<b.nframes * t.layout.nslices, kPackThreads, 0, s>>>(t, b);
     else                 k_pack_slices<true><<<b.nframes * t.layout.nslices, kPackThreads, 0, s>>>(t, b);
+}
+
+// =================================================================================================
+// k_pass1_stats: the statistics a first pass collects (AV_CODEC_FLAG_PASS1; put_symbol_inline's rc_stat / rc_stat2
+// arguments, ffv1enc.c:193-200, 320-322), from what the encode left in device memory:
+//   rc_stat[state][bit]            <- the decision entries (state before the update | bit << 8) of the sample runs
+//   rc_stat2[context][slot][bit]   <- the records: which slots a residual visits and with which bits does not depend on
+//                                     the adaptive state (ffv1enc.c:202-229)
+// One CTA per (slice, frame).  PRIV: the per-context counters of the CTA are gathered in shared memory first (small
+// context model: 666 x 64 counters); otherwise every count is a global atomic.  Not on the speed path.
+// =================================================================================================
+constexpr int kStatsThreads = 512;
+
+template <bool PRIV>
+__global__ void __launch_bounds__(kStatsThreads) k_pass1_stats(const EncDeviceTables T, const EncBatch B, unsigned long long *rc_stat,
+                                                               unsigned long long *rc_stat2)
+{
+    extern __shared__ uint32_t s_stat2[];                    // PRIV: [ctx_count * 64]
+    __shared__ uint32_t s_stat[512];
+    const Layout &L = T.layout;
+    const int s = blockIdx.x, f = blockIdx.y, tid = threadIdx.x;
+    const SliceGeom &g = T.slices[s];
+    if (B.status[0] | B.status[1] | B.status[2]) return;     // a scratch area overflowed: the batch is coded again
+    for (int i = tid; i < 512; i += kStatsThreads) s_stat[i] = 0u;
+    if (PRIV) for (int i = tid; i < L.ctx_count * 64; i += kStatsThreads) s_stat2[i] = 0u;
+    __syncthreads();
+    // ---- records -> per-context slot/bit counts
+    const uint32_t *rec_slice = B.rec + (size_t)f * L.rec_per_frame + g.rec_first;
+    for (int li = 0; li < g.nlines; li++) {
+        const LineDesc ld = T.lines[g.line_first + li];
+        const uint32_t *recp = rec_slice + ld.rec_off;
+        for (int x = tid; x < ld.w; x += kStatsThreads) {
+            const uint32_t r = recp[x];
+            const uint32_t base = (r >> 16) * 64u;
+            const int d = (int)(int16_t)(r & 0xFFFFu);
+            auto count = [&](int slot, int bit) {
+                if (PRIV) atomicAdd(&s_stat2[base + slot * 2 + bit], 1u);
+                else atomicAdd(&rc_stat2[base + slot * 2 + bit], 1ull);
+            };
+            if (d == 0) { count(0, 1); continue; }
+            const uint32_t a = (uint32_t)abs(d);
+            const int e = 31 - __clz(a);
+            count(0, 0);
+            for (int i = 0; i < e; i++) count(1 + min(i, 9), 1);
+            count(1 + min(e, 9), 0);
+            for (int i = e - 1; i >= 0; i--) count(22 + min(i, 9), (a >> i) & 1u);
+            count(11 + min(e, 10), d < 0);
+        }
+    }
+    // ---- decisions of the slice's sample runs -> counts per (state, bit)
+    {
+        const uint16_t *dec_frame = B.dec + (size_t)f * L.dec_per_frame;
+        const uint32_t *run_cnt = B.run_cnt + (size_t)f * L.runs_per_frame + g.run_first;
+        const uint8_t *run_pc = T.run_pc + g.run_first;
+        uint32_t cur[3] = {0u, 0u, 0u};
+        for (int r = 0; r < g.nruns; r++) {
+            const int pc = run_pc[r];
+            const uint32_t n = run_cnt[r];
+            const uint16_t *src = dec_frame + g.dec_off[pc] + cur[pc];
+            cur[pc] = (cur[pc] + n + 7u) & ~7u;
+            for (uint32_t i = tid; i < n; i += kStatsThreads) atomicAdd(&s_stat[src[i] & 0x1FFu], 1u);
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < 512; i += kStatsThreads)
+        if (s_stat[i]) atomicAdd(&rc_stat[(i & 0xFF) * 2 + (i >> 8)], (unsigned long long)s_stat[i]);
+    if (PRIV)
+        for (int i = tid; i < L.ctx_count * 64; i += kStatsThreads)
+            if (s_stat2[i]) atomicAdd(&rc_stat2[i], (unsigned long long)s_stat2[i]);
+}
+
+cudaError_t launch_pass1_stats(const EncDeviceTables &t, const EncBatch &b, unsigned long long *rc_stat, unsigned long long *rc_stat2,
+                               cudaStream_t s)
+{
+    const Layout &L = t.layout;
+    dim3 grid(L.nslices, b.nframes);
+    const int smem = L.ctx_count * 64 * 4;
+    if (smem <= 200 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k_pass1_stats<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        k_pass1_stats<true><<<grid, kStatsThreads, smem, s>>>(t, b, rc_stat, rc_stat2);
+    } else
+        k_pass1_stats<false><<<grid, kStatsThreads, 0, s>>>(t, b, rc_stat, rc_stat2);
+    return cudaGetLastError();
 }
 
 cudaError_t configure_kernels(const Layout &L)

@@ -60,6 +60,7 @@ struct EncDeviceTables {
     const CtxTile *ctiles;
     const int16_t *quant;               // [5][256]
     const uint8_t *trans_lut;           // [512]: zero_state, one_state of the slice coders
+    const uint8_t *init_state;          // [ctx_count][32] states a keyframe starts from (two-pass encode), or null = all 128
     const uint8_t *one_pow;             // [33][256]: one_state applied k times (runs of zero residuals in one context)
     const uint8_t *run_pc;              // [runs_per_frame] plane context of every run
     const uint8_t *gprefix;             // Golomb-Rice mode: [nslices][2][kMaxGolombPrefix] bytes every slice starts with
@@ -84,6 +85,9 @@ void launch_golomb_lists(const EncDeviceTables &t, const EncBatch &b, cudaStream
 void launch_golomb_coder(const EncDeviceTables &t, const EncBatch &b, cudaStream_t s);
 void launch_pack(const EncDeviceTables &t, const EncBatch &b, cudaStream_t s);
 cudaError_t configure_kernels(const Layout &L);
+// first-pass statistics of a coded batch (range-coder modes): rc_stat[256][2], rc_stat2[ctx_count][32][2], accumulated
+cudaError_t launch_pass1_stats(const EncDeviceTables &t, const EncBatch &b, unsigned long long *rc_stat, unsigned long long *rc_stat2,
+                               cudaStream_t s);
 // context-decomposed state replay (ffv1_ctx_replay.cu)
 bool ctx_replay_supported(const Layout &L);
 bool ctx_replay_needs_global_state(const Layout &L);      // large context model: B.state_seg holds one model per chain

@@ -67,7 +67,10 @@ struct FFV1B200Encoder {
     DevBuf<SliceGeom> d_slices; DevBuf<LineDesc> d_lines; DevBuf<int32_t> d_pc_lines; DevBuf<TileDesc> d_tiles;
     DevBuf<CtxTile> d_ctiles;
     FastPlan fast_plan; DevBuf<FastItemDesc> d_fast_items;
-    DevBuf<int16_t> d_quant; DevBuf<uint8_t> d_lut, d_one_pow, d_run_pc;
+    DevBuf<int16_t> d_quant; DevBuf<uint8_t> d_lut, d_one_pow, d_run_pc, d_init_state;
+    // first pass of a two-pass encode: statistics accumulated on the device, keyframes coded so far
+    DevBuf<unsigned long long> d_rc_stat, d_rc_stat2;
+    int gob_count = 0;
     // shared intermediates
     DevBuf<uint32_t> d_rec, d_run_cnt, d_slice_bytes, d_line_pos, d_ctx_hist, d_list_start, d_list_count;
     DevBuf<uint16_t> d_dec, d_list_order;
@@ -180,6 +183,7 @@ EncDeviceTables device_tables(FFV1B200Encoder *e, const Slot &sl)
     t.slices = e->d_slices.p; t.lines = e->d_lines.p; t.pc_lines = e->d_pc_lines.p; t.tiles = e->d_tiles.p;
     t.ctiles = e->d_ctiles.p;
     t.quant = e->d_quant.p; t.trans_lut = e->d_lut.p; t.one_pow = e->d_one_pow.p; t.run_pc = e->d_run_pc.p;
+    t.init_state = e->d_init_state.p;
     t.gprefix = sl.d_gprefix.p; t.gprefix_len = sl.d_gprefix_len.p; t.prefix = sl.d_prefix.p; t.prefix_len = sl.d_prefix_len.p;
     t.ec = e->cfg.ec; t.version = e->cfg.version; t.state_in_smem = e->state_in_smem ? 1 : 0;
     return t;
@@ -192,6 +196,7 @@ void plan_batch(FFV1B200Encoder *e, Slot &sl, int nframes, int64_t pn)
     for (int f = 0; f < nframes; f++) {
         const bool key = e->cfg.gop_size == 0 || ((pn + f) % e->cfg.gop_size) == 0;
         sl.h_frame_key.p[f] = key ? 1 : 0;
+        if (key) e->gob_count++;                              // ffv1enc.c:1302
         if (f == 0 || key) sl.h_seg_first.p[nseg++] = f;
         sl.h_frame_seg.p[f] = nseg - 1;
     }
@@ -252,6 +257,10 @@ int enqueue_kernels(FFV1B200Encoder *e, Slot &sl, cudaStream_t s)
     cudaEventRecord(sl.ev[3], s);
     launch_pack(t, b, s);
     cudaEventRecord(sl.ev[4], s);
+    if ((e->cfg.pass_flags & kPass1) && !L.golomb) {          // the reference gathers statistics in the range-coder modes only
+        CU_TRY(launch_pass1_stats(t, b, e->d_rc_stat.p, e->d_rc_stat2.p, s));
+        e->stats.kernel_launches++;
+    }
     e->stats.kernel_launches += L.golomb ? (e->golomb_lists ? 8 : 4) : (e->ctx_replay ? 9 : 5);
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaMemcpyAsync(sl.h_status.p, sl.d_status.p, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost, s));
@@ -365,11 +374,46 @@ int finish_output(FFV1B200Encoder *e)
 
 extern "C" {
 
+static EncOptions options_of(const FFV1B200EncParams *p)
+{
+    EncOptions o{p->width, p->height, p->pix_fmt, p->gop_size, p->level, p->slices, p->coder, p->context, p->slicecrc};
+    if (p->flags & FFV1B200_FLAG_PASS1) o.pass_flags |= kPass1;
+    if (p->flags & FFV1B200_FLAG_PASS2) o.pass_flags |= kPass2;
+    if (p->stats_in) o.stats_in = p->stats_in;
+    o.strict_experimental = p->strict_std_compliance <= -2;
+    return o;
+}
+
+int ffv1b200_enc_resolve(const FFV1B200EncParams *p, FFV1B200EncInfo *i, uint8_t *extradata, int cap, int *size)
+{
+    if (!p || !p->pix_fmt) return fail(FFV1B200_ERR_EINVAL, "null argument");
+    Config c;
+    std::string err;
+    int r = resolve_encoder(options_of(p), c, err);
+    if (r < 0) return fail(r, err);
+    if (i) {
+        memset(i, 0, sizeof(*i));
+        i->version = c.version; i->micro_version = c.micro_version; i->ac = c.ac; i->colorspace = c.colorspace;
+        i->bits_per_raw_sample = c.bits; i->chroma_planes = c.chroma_planes; i->chroma_h_shift = c.chroma_h_shift;
+        i->chroma_v_shift = c.chroma_v_shift; i->transparency = c.transparency; i->num_h_slices = c.num_h_slices;
+        i->num_v_slices = c.num_v_slices; i->slice_count = c.slice_count(); i->ec = c.ec; i->intra = c.intra;
+        i->context_count = c.context_count[c.context_model]; i->plane_count = c.plane_count;
+        i->frame_bytes = c.frame_bytes();
+    }
+    const std::vector<uint8_t> xd = write_extradata(c);
+    if (size) *size = (int)xd.size();
+    if (extradata) {
+        if ((int)xd.size() > cap) return fail(FFV1B200_ERR_BUFFER_TOO_SMALL, "extradata buffer too small");
+        if (!xd.empty()) memcpy(extradata, xd.data(), xd.size());
+    }
+    return 0;
+}
+
 int ffv1b200_enc_open(FFV1B200Encoder **out, const FFV1B200EncParams *p)
 {
     if (!out || !p || !p->pix_fmt) return fail(FFV1B200_ERR_EINVAL, "null argument");
     *out = nullptr;
-    EncOptions o{p->width, p->height, p->pix_fmt, p->gop_size, p->level, p->slices, p->coder, p->context, p->slicecrc};
+    const EncOptions o = options_of(p);
     std::unique_ptr<FFV1B200Encoder> e(new FFV1B200Encoder());
     std::string err;
     int r = resolve_encoder(o, e->cfg, err);
@@ -434,6 +478,18 @@ int ffv1b200_enc_open(FFV1B200Encoder **out, const FFV1B200EncParams *p)
         for (int q = 0; q < 256; q++) one_pow[k * 256 + q] = lut[256 + one_pow[(k - 1) * 256 + q]];
     CU_TRY(e->d_one_pow.upload(one_pow.data(), one_pow.size(), s));
     CU_TRY(e->d_run_pc.upload(e->tab.run_pc.data(), e->tab.run_pc.size(), s));
+    {
+        // second pass: the states a keyframe starts from (ffv1.c:188-190), for the table set in use
+        const std::vector<uint8_t> &init = e->cfg.initial_states[e->cfg.context_model];
+        bool coded = false;
+        for (uint8_t v : init) if (v != 128) { coded = true; break; }
+        if (coded && !L.golomb) CU_TRY(e->d_init_state.upload(init.data(), init.size(), s));
+    }
+    if (e->cfg.pass_flags & kPass1) {
+        CU_TRY(e->d_rc_stat.alloc(512)); CU_TRY(e->d_rc_stat2.alloc((size_t)L.ctx_count * 64));
+        CU_TRY(cudaMemsetAsync(e->d_rc_stat.p, 0, 512 * sizeof(unsigned long long), s));
+        CU_TRY(cudaMemsetAsync(e->d_rc_stat2.p, 0, (size_t)L.ctx_count * 64 * sizeof(unsigned long long), s));
+    }
     r = alloc_buffers(e.get());
     if (r < 0) return r;
     CU_TRY(cudaStreamSynchronize(s));
@@ -725,6 +781,27 @@ int ffv1b200_enc_stats(const FFV1B200Encoder *e, FFV1B200EncStats *s)
     if (!e || !s) return FFV1B200_ERR_EINVAL;
     *s = e->stats;
     return 0;
+}
+
+int ffv1b200_enc_stats_out(FFV1B200Encoder *e, char *buf, size_t cap, size_t *needed)
+{
+    if (!e || !buf) return fail(FFV1B200_ERR_EINVAL, "null argument");
+    if (!(e->cfg.pass_flags & kPass1)) return fail(FFV1B200_ERR_EINVAL, "the encoder was not opened with FFV1B200_FLAG_PASS1");
+    if (e->submitted != e->collected) return fail(FFV1B200_ERR_EINVAL, "collect the batches in flight first");
+    CU_TRY(cudaSetDevice(e->device));
+    CU_TRY(cudaStreamSynchronize(e->s_comp));
+    PassStats st;
+    const Config &c = e->cfg;
+    for (int i = 0; i < 2; i++) st.rc_stat2[i].assign((size_t)c.context_count[i] * 64, 0);
+    static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "counter width");
+    CU_TRY(cudaMemcpy(st.rc_stat, e->d_rc_stat.p, sizeof(st.rc_stat), cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(st.rc_stat2[c.context_model].data(), e->d_rc_stat2.p, st.rc_stat2[c.context_model].size() * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    st.gob_count = e->gob_count;
+    const std::string text = format_stats(c, st);
+    if (needed) *needed = text.size() + 1;
+    if (text.size() + 1 > cap) return fail(FFV1B200_ERR_BUFFER_TOO_SMALL, "stats buffer too small: need " + std::to_string(text.size() + 1) + " bytes");
+    memcpy(buf, text.c_str(), text.size() + 1);
+    return (int)text.size();
 }
 
 int64_t ffv1b200_enc_debug_records(FFV1B200Encoder *e, int frame, int slice, uint32_t *dst, int64_t cap)

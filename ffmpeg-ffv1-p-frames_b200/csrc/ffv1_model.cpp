@@ -4,6 +4,8 @@
 #include <cstring>
 #include <cstdlib>
 #include <algorithm>
+#include <cmath>
+#include <cinttypes>
 
 namespace ffv1 {
 
@@ -293,7 +295,7 @@ int resolve_encoder(const EncOptions &o, Config &c, std::string &err)
 
     // version selection, ffv1enc.c:676-706
     int version = 0;
-    if (o.slices > 1) version = 2;
+    if (o.slices > 1 || (o.pass_flags & (kPass1 | kPass2))) version = 2;
     if (o.slices == 0 && o.level < 0 && o.width * o.height > 720 * 576) version = 2;
     if (o.level <= 0 && version == 2) version = 3;
     if (o.level >= 0 && o.level <= 4) {
@@ -341,6 +343,185 @@ int resolve_encoder(const EncOptions &o, Config &c, std::string &err)
             return FFV1B200_ERR_ENOSYS;
         }
     }
+    c.pass_flags = o.pass_flags;
+    if (!o.stats_in.empty()) {                            // ffv1enc.c:906-986 (runs before the slice grid is chosen; independent of it)
+        if (c.version < 2) { err = "two-pass statistics need FFV1 version 2 or later"; return FFV1B200_ERR_EINVAL; }
+        int r = apply_stats(c, o.stats_in, err);
+        if (r < 0) return r;
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// two-pass coding: statistics text, state-transition table sorting, initial states
+// ------------------------------------------------------------------------------------------------
+std::string format_stats(const Config &c, const PassStats &st)
+{
+    // the text encode_frame leaves in stats_out when it is flushed (ffv1enc.c:1261-1275)
+    std::string out;
+    char tmp[64];
+    for (int j = 0; j < 256; j++) {
+        snprintf(tmp, sizeof(tmp), "%" PRIu64 " %" PRIu64 " ", st.rc_stat[j][0], st.rc_stat[j][1]);
+        out += tmp;
+    }
+    out += "\n";
+    for (int i = 0; i < 2; i++)
+        for (int j = 0; j < c.context_count[i]; j++)
+            for (int m = 0; m < 32; m++) {
+                const uint64_t *v = &st.rc_stat2[i][((size_t)j * 32 + m) * 2];
+                snprintf(tmp, sizeof(tmp), "%" PRIu64 " %" PRIu64 " ", v[0], v[1]);
+                out += tmp;
+            }
+    snprintf(tmp, sizeof(tmp), "%d\n", st.gob_count);
+    out += tmp;
+    return out;
+}
+
+namespace {
+// cost in bits of coding the decisions counted in `n` (n[0] zeros, n[1] ones) with probability state `state`
+inline double stat_term0(const uint64_t n[2], int state) { return n[0] * -log2((256 - state) / 256.0); }
+inline double stat_term1(const uint64_t n[2], int state) { return n[1] * -log2(state / 256.0); }
+
+// sort_stt (ffv1enc.c:621-667): neighbouring entries of the transition table are exchanged while that shortens the
+// first pass's decisions.  The sums keep the reference's left-to-right order of the eight terms (its cost macros expand
+// without parentheses), and the counters are exchanged through an int like its FFSWAP(int, ...).
+void sort_transition_table(uint64_t rc_stat[256][2], uint8_t stt[256])
+{
+    auto cost8 = [&](int a, int an, int b, int bn) {
+        // COST2(a, an) + COST2(b, bn)
+        double s = stat_term0(rc_stat[a], an);
+        s = s + stat_term1(rc_stat[a], an);
+        s = s + stat_term0(rc_stat[256 - a], 256 - an);
+        s = s + stat_term1(rc_stat[256 - a], 256 - an);
+        s = s + stat_term0(rc_stat[b], bn);
+        s = s + stat_term1(rc_stat[b], bn);
+        s = s + stat_term0(rc_stat[256 - b], 256 - bn);
+        s = s + stat_term1(rc_stat[256 - b], 256 - bn);
+        return s;
+    };
+    auto swap_counts = [&](uint64_t &x, uint64_t &y) { const int t = (int)y; y = x; x = (uint64_t)(int64_t)t; };
+    auto swap_u8 = [&](uint8_t &x, uint8_t &y) { const uint8_t t = y; y = x; x = t; };
+    bool changed;
+    do {
+        changed = false;
+        for (int i = 12; i < 244; i++)
+            for (int i2 = i + 1; i2 < 245 && i2 < i + 4; i2++) {
+                const double keep = cost8(i, i, i2, i2), swapped = cost8(i, i2, i2, i);
+                if (!(keep - swapped > keep * (1e-14)) || i == 128 || i2 == 128) continue;
+                swap_u8(stt[i], stt[i2]);
+                swap_counts(rc_stat[i][0], rc_stat[i2][0]);
+                swap_counts(rc_stat[i][1], rc_stat[i2][1]);
+                const bool mirror = i != 256 - i2;
+                if (mirror) {
+                    swap_u8(stt[256 - i], stt[256 - i2]);
+                    swap_counts(rc_stat[256 - i][0], rc_stat[256 - i2][0]);
+                    swap_counts(rc_stat[256 - i][1], rc_stat[256 - i2][1]);
+                }
+                for (int j = 1; j < 256; j++) {
+                    if (stt[j] == i) stt[j] = (uint8_t)i2;
+                    else if (stt[j] == i2) stt[j] = (uint8_t)i;
+                    if (mirror) {
+                        if (stt[256 - j] == 256 - i) stt[256 - j] = (uint8_t)(256 - i2);
+                        else if (stt[256 - j] == 256 - i2) stt[256 - j] = (uint8_t)(256 - i);
+                    }
+                }
+                changed = true;
+            }
+    } while (changed);
+}
+
+// find_best_state (ffv1enc.c:139-183): best[i][k] = the start state from which k further decisions of a source with
+// P(one) = i/256 cost least, found by following the occupancy of the states through the transition table.
+void best_start_states(std::vector<uint8_t> &best, const uint8_t one_state[256])
+{
+    best.assign(256 * 256, 0);
+    double l2[256];
+    l2[0] = 0.0;
+    for (int i = 1; i < 256; i++) l2[i] = log2(i / 256.0);
+    std::vector<double> shortest(256);
+    for (int i = 0; i < 256; i++) {
+        const double p = i / 256.0;
+        std::fill(shortest.begin(), shortest.end(), (double)(1 << 30));
+        for (int j = std::max(i - 10, 1); j < std::min(i + 11, 256); j++) {
+            if (!one_state[j]) continue;
+            double occ[256] = {0}, next[256];
+            double len = 0;
+            occ[j] = 1.0;
+            for (int k = 0; k < 256; k++) {
+                for (int m = 1; m < 256; m++)
+                    if (occ[m]) len -= occ[m] * (p * l2[m] + (1 - p) * l2[256 - m]);
+                if (len < shortest[k]) { shortest[k] = len; best[(size_t)i * 256 + k] = (uint8_t)j; }
+                std::fill(next, next + 256, 0.0);
+                for (int m = 1; m < 256; m++)
+                    if (occ[m]) {
+                        next[one_state[m]] += occ[m] * p;
+                        next[256 - one_state[256 - m]] += occ[m] * (1 - p);
+                    }
+                memcpy(occ, next, sizeof(occ));
+            }
+        }
+    }
+}
+
+inline int clip_int(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+inline int clip_u8(int v) { return (v & ~0xFF) ? (~v >> 31) & 0xFF : v; }
+} // namespace
+
+int apply_stats(Config &c, const std::string &stats_in, std::string &err)
+{
+    // parse (ffv1enc.c:906-948): blocks of 256x2 + contexts x 32 x 2 counters + gob_count; the last block counts
+    uint64_t rc_stat[256][2];
+    std::vector<uint64_t> rc_stat2[2];
+    for (int i = 0; i < 2; i++) rc_stat2[i].assign((size_t)c.context_count[i] * 64, 0);
+    int gob_count = 0;
+    const char *p = stats_in.c_str();
+    char *next;
+    for (;;) {
+        for (int j = 0; j < 256; j++)
+            for (int i = 0; i < 2; i++) {
+                rc_stat[j][i] = (uint64_t)strtol(p, &next, 0);
+                if (next == p) { err = "2Pass file invalid at " + std::to_string(j) + " " + std::to_string(i); return FFV1B200_ERR_INVALIDDATA; }
+                p = next;
+            }
+        for (int i = 0; i < 2; i++)
+            for (size_t n = 0; n < rc_stat2[i].size(); n++) {
+                rc_stat2[i][n] = (uint64_t)strtol(p, &next, 0);
+                if (next == p) { err = "2Pass file invalid (context statistics)"; return FFV1B200_ERR_INVALIDDATA; }
+                p = next;
+            }
+        gob_count = (int)strtol(p, &next, 0);
+        if (next == p || gob_count <= 0) { err = "2Pass file invalid"; return FFV1B200_ERR_INVALIDDATA; }
+        p = next;
+        while (*p == '\n' || *p == ' ') p++;
+        if (!*p) break;
+    }
+    if (c.ac == AC_RANGE_CUSTOM) sort_transition_table(rc_stat, c.state_transition);
+    std::vector<uint8_t> best;
+    best_start_states(best, c.state_transition);
+    // initial states (ffv1enc.c:954-984): contexts with few observations share the estimate of the ones before them
+    for (int i = 0; i < 2; i++) {
+        const int nctx = c.context_count[i];
+        std::vector<uint8_t> &init = c.initial_states[i];
+        init.assign((size_t)nctx * 32, 128);
+        for (int k = 0; k < 32; k++) {
+            double a = 0, b = 0;
+            int jp = 0;
+            for (int j = 0; j < nctx; j++) {
+                const uint64_t n0 = rc_stat2[i][((size_t)j * 32 + k) * 2], n1 = rc_stat2[i][((size_t)j * 32 + k) * 2 + 1];
+                double pr = 128;
+                if ((n0 + n1 > 200 && j) || a + b > 200) {
+                    if (a + b) pr = 256.0 * b / (a + b);
+                    init[(size_t)jp * 32 + k] = best[(size_t)clip_int((int)round(pr), 1, 255) * 256 + clip_u8((int)((a + b) / gob_count))];
+                    for (jp++; jp < j; jp++) init[(size_t)jp * 32 + k] = init[(size_t)(jp - 1) * 32 + k];
+                    a = b = 0;
+                }
+                a += n0;
+                b += n1;
+                if (a + b) pr = 256.0 * b / (a + b);
+                init[(size_t)j * 32 + k] = best[(size_t)clip_int((int)round(pr), 1, 255) * 256 + clip_u8((int)((a + b) / gob_count))];
+            }
+        }
+    }
     return 0;
 }
 
@@ -381,7 +562,20 @@ std::vector<uint8_t> write_extradata(const Config &c)
     bc.put_symbol(st, 2, false);
     for (int t = 0; t < 2; t++)
         for (int i = 0; i < 5; i++) put_quant_table(bc, c.quant_tables[t][i]);
-    for (int t = 0; t < 2; t++) bc.put(st, 0);            // initial states stay 128 (2-pass is out of scope)
+    uint8_t st2[32][kStateSlots];                          // ffv1enc.c:591-606: one coder state row per slot, shared by both sets
+    memset(st2, 128, sizeof(st2));
+    for (int t = 0; t < 2; t++) {
+        const std::vector<uint8_t> &init = c.initial_states[t];
+        bool coded = false;
+        for (uint8_t v : init) if (v != 128) { coded = true; break; }
+        bc.put(st, coded);
+        if (!coded) continue;
+        for (int j = 0; j < c.context_count[t]; j++)
+            for (int k = 0; k < 32; k++) {
+                const int pred = j ? init[(size_t)(j - 1) * 32 + k] : 128;
+                bc.put_symbol(st2[k], (int8_t)(init[(size_t)j * 32 + k] - pred), true);
+            }
+    }
     if (c.version > 2) {
         bc.put_symbol(st, c.ec, false);
         bc.put_symbol(st, c.intra, false);
@@ -486,8 +680,19 @@ int parse_extradata(const uint8_t *d, int n, int width, int height, Config &c, s
         }
         c.context_count[t] = (count + 1) / 2;
     }
-    for (int t = 0; t < qtc; t++)
-        if (bd.get(st)) { err = "2-pass initial states are not supported"; return FFV1B200_ERR_ENOSYS; }
+    uint8_t st2[32][kStateSlots];                          // ffv1dec.c:591-600: initial states of a two-pass encode
+    memset(st2, 128, sizeof(st2));
+    for (int t = 0; t < qtc; t++) {
+        c.initial_states[t].clear();
+        if (!bd.get(st)) continue;
+        std::vector<uint8_t> &init = c.initial_states[t];
+        init.assign((size_t)c.context_count[t] * 32, 128);
+        for (int j = 0; j < c.context_count[t]; j++)
+            for (int k = 0; k < 32; k++) {
+                const int pred = j ? init[(size_t)(j - 1) * 32 + k] : 128;
+                init[(size_t)j * 32 + k] = (uint8_t)((pred + bd.get_symbol(st2[k], true)) & 0xFF);
+            }
+    }
     if (c.version > 2) {
         c.ec = bd.get_symbol(st, false);
         if (c.micro_version > 2) c.intra = bd.get_symbol(st, false);

@@ -125,6 +125,10 @@ struct Config {
     int16_t quant_tables[2][5][256];
     int context_count[2] = {0, 0};
     int bytes_per_sample = 1;
+    // two-pass coding (ffv1enc.c:906-986): per quantisation-table set, [context][32] state bytes a keyframe starts from;
+    // empty = every state 128.  Written into the extradata (ffv1enc.c:591-606), read back by ffv1dec.c:591-606.
+    std::vector<uint8_t> initial_states[2];
+    int pass_flags = 0;                        // kPass1 / kPass2 (AV_CODEC_FLAG_PASS1 / _PASS2)
     int nb_src_planes = 0;                     // AVFrame planes of the pix_fmt
     int src_hshift[4] = {0,0,0,0}, src_vshift[4] = {0,0,0,0};
     int pixel_bytes[4] = {1,1,1,1};            // bytes per pixel in each source plane
@@ -134,8 +138,12 @@ struct Config {
     void plane_dims(int i, int *rows, int *row_bytes) const;
 };
 
+constexpr int kPass1 = 1, kPass2 = 2;
 struct EncOptions {
     int width, height; std::string pix_fmt; int gop_size, level, slices, coder, context, slicecrc;
+    int pass_flags = 0;          // kPass1: collect statistics; kPass2 (or any stats_in): code with the tables derived from them
+    std::string stats_in;        // AVCodecContext.stats_in: the text a first pass left in stats_out
+    int strict_experimental = 0; // AVCodecContext.strict_std_compliance <= FF_COMPLIANCE_EXPERIMENTAL
 };
 
 // encode_init: returns 0 or a negative AVERROR-style code with a message in err
@@ -150,6 +158,17 @@ int parse_frame_prefix_v01(const uint8_t *pkt, int size, int width, int height, 
                            PrefixState &ps, std::string &err);
 
 std::vector<uint8_t> write_extradata(const Config &c);
+
+// Two-pass statistics (ffv1enc.c:193-200, 1236-1276): rc_stat[state][bit] over all sample decisions,
+// rc_stat2[table set][context][slot][bit]; gob_count = keyframes coded.  format_stats writes AVCodecContext.stats_out's text.
+struct PassStats {
+    uint64_t rc_stat[256][2];
+    std::vector<uint64_t> rc_stat2[2];         // [context_count[i] * 32 * 2]
+    int gob_count = 0;
+};
+std::string format_stats(const Config &c, const PassStats &st);
+// stats_in -> sorted state-transition table (custom-table coder) and initial states; 0 or a negative error
+int apply_stats(Config &c, const std::string &stats_in, std::string &err);
 
 void default_state_tables(uint8_t zero_state[256], uint8_t one_state[256]);
 // transition tables a slice coder runs with: default table, custom entries 1..255 overriding for AC_RANGE_CUSTOM

@@ -17,7 +17,10 @@ class _EncParams(ctypes.Structure):
     _fields_ = [("width", ctypes.c_int), ("height", ctypes.c_int), ("pix_fmt", ctypes.c_char_p),
                 ("gop_size", ctypes.c_int), ("level", ctypes.c_int), ("slices", ctypes.c_int),
                 ("coder", ctypes.c_int), ("context", ctypes.c_int), ("slicecrc", ctypes.c_int),
-                ("device", ctypes.c_int), ("max_batch_frames", ctypes.c_int), ("first_picture_number", ctypes.c_int64)]
+                ("device", ctypes.c_int), ("max_batch_frames", ctypes.c_int), ("first_picture_number", ctypes.c_int64),
+                ("flags", ctypes.c_int), ("stats_in", ctypes.c_char_p), ("strict_std_compliance", ctypes.c_int)]
+
+FLAG_PASS1, FLAG_PASS2 = 1 << 9, 1 << 10      # AV_CODEC_FLAG_PASS1 / _PASS2
 
 class _FrameProps(ctypes.Structure):
     _fields_ = [("sar_num", ctypes.c_int), ("sar_den", ctypes.c_int), ("picture_structure", ctypes.c_int)]
@@ -85,6 +88,7 @@ def lib():
                                                  ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(Packet), ctypes.POINTER(ctypes.c_size_t),
                                                  ctypes.c_void_p]
         L.ffv1b200_enc_stats.argtypes = [ctypes.c_void_p, ctypes.POINTER(EncStats)]
+        L.ffv1b200_enc_stats_out.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]
         L.ffv1b200_enc_debug_records.restype = ctypes.c_int64
         L.ffv1b200_enc_debug_records.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64]
         L.ffv1b200_dec_open.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(_DecParams)]
@@ -136,15 +140,29 @@ def plane_shapes(pix_fmt, w, h):
 def frame_bytes(pix_fmt, w, h):
     return sum(r * b for r, b in plane_shapes(pix_fmt, w, h))
 
+def resolve_encoder(width, height, pix_fmt, g=12, level=-1, coder=0, context=0, slices=0, slicecrc=-1, flags=0, stats_in=None, strict=0):
+    """encode_init's host half (no GPU needed): returns (info, extradata) or raises FFV1Error like FFV1Encoder would"""
+    if isinstance(stats_in, str):
+        stats_in = stats_in.encode()
+    p = _EncParams(width, height, pix_fmt.encode(), g, level, slices, coder, context, slicecrc, 0, 0, 0, flags, stats_in, strict)
+    info, n = _EncInfo(), ctypes.c_int()
+    L = lib()
+    L.ffv1b200_enc_resolve.argtypes = [ctypes.POINTER(_EncParams), ctypes.POINTER(_EncInfo), ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
+    buf = ctypes.create_string_buffer(1 << 20)
+    _check(L.ffv1b200_enc_resolve(ctypes.byref(p), ctypes.byref(info), buf, 1 << 20, ctypes.byref(n)))
+    return info, buf.raw[:n.value]
+
 class FFV1Encoder:
     """Mirror of ff_ffv1_encoder (ffv1enc.c:1415-1444): __init__ = init, encode2/flush = encode2 (CAP_DELAY), close."""
 
     def __init__(self, width, height, pix_fmt, g=12, level=-1, coder=0, context=0, slices=0, slicecrc=-1,
-                 device=0, max_batch_frames=64, first_picture_number=0):
+                 device=0, max_batch_frames=64, first_picture_number=0, flags=0, stats_in=None, strict=0):
         self._h = ctypes.c_void_p()
         self.width, self.height, self.pix_fmt = width, height, pix_fmt
+        if isinstance(stats_in, str):
+            stats_in = stats_in.encode()
         p = _EncParams(width, height, pix_fmt.encode(), g, level, slices, coder, context, slicecrc, device,
-                       max_batch_frames, first_picture_number)
+                       max_batch_frames, first_picture_number, flags, stats_in, strict)
         _check(lib().ffv1b200_enc_open(ctypes.byref(self._h), ctypes.byref(p)))
         self.info = _EncInfo()
         _check(lib().ffv1b200_enc_info(self._h, ctypes.byref(self.info)))
@@ -159,6 +177,19 @@ class FFV1Encoder:
         ptr, n = ctypes.c_void_p(), ctypes.c_int()
         _check(lib().ffv1b200_enc_extradata(self._h, ctypes.byref(ptr), ctypes.byref(n)))
         return ctypes.string_at(ptr, n.value) if n.value else b""
+
+    def stats_out(self):
+        """first pass (flags=FLAG_PASS1): AVCodecContext.stats_out as the reference leaves it when flushed (ffv1enc.c:1235-1277)"""
+        need = ctypes.c_size_t()
+        cap = 1 << 20
+        while True:
+            buf = ctypes.create_string_buffer(cap)
+            r = lib().ffv1b200_enc_stats_out(self._h, buf, cap, ctypes.byref(need))
+            if r == ERR_BUFFER_TOO_SMALL:
+                cap = need.value
+                continue
+            _check(r)
+            return buf.value.decode()
 
     def set_frame_props(self, sar=(0, 1), picture_structure=3):
         fp = _FrameProps(sar[0], sar[1], picture_structure)

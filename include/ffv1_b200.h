@@ -10,6 +10,7 @@
  *   ffv1b200_enc_encode_* / _submit_host / _collect
  *                                <- ff_ffv1_encoder.encode2 = encode_frame  libavcodec/ffv1enc.c:1222-1373
  *                                   (batched: CAP_DELAY lets a codec hold frames, ffv1enc.c:1424)
+ *   ffv1b200_enc_stats_out       <- avctx->stats_out at flush (first pass)      libavcodec/ffv1enc.c:1235-1277
  *   ffv1b200_enc_close           <- ff_ffv1_encoder.close   = encode_close  libavcodec/ffv1enc.c:1375-1379
  *   ffv1b200_dec_open            <- ff_ffv1_decoder.init    = decode_init   libavcodec/ffv1dec.c:876-893
  *   ffv1b200_dec_decode_*        <- ff_ffv1_decoder.decode  = decode_frame  libavcodec/ffv1dec.c:895-1035
@@ -60,7 +61,14 @@ typedef struct FFV1B200EncParams {
     int max_batch_frames;     /* capacity of one ffv1b200_enc_encode_* call (0 = default 64) */
     int64_t first_picture_number; /* picture_number of the first frame this instance will see (GOP-aligned multi-GPU
                                      shards continue the global count); normally 0 */
+    int flags;                /* AVCodecContext.flags & (AV_CODEC_FLAG_PASS1 | AV_CODEC_FLAG_PASS2): two-pass coding
+                                 (ffv1enc.c:680, 898-986, 1013-1027); 0 = single pass */
+    const char *stats_in;     /* AVCodecContext.stats_in: the first pass's statistics text (ffv1b200_enc_stats_out), or NULL */
+    int strict_std_compliance;/* AVCodecContext.strict_std_compliance; <= -2 (FF_COMPLIANCE_EXPERIMENTAL) unlocks level 4 */
 } FFV1B200EncParams;
+
+#define FFV1B200_FLAG_PASS1 (1 << 9)             /* = AV_CODEC_FLAG_PASS1 */
+#define FFV1B200_FLAG_PASS2 (1 << 10)            /* = AV_CODEC_FLAG_PASS2 */
 
 /* Per-frame side information that is coded into every slice header (ffv1enc.c:1044-1049). */
 typedef struct FFV1B200FrameProps {
@@ -124,6 +132,10 @@ typedef struct FFV1B200EncInfo {
     int64_t frame_bytes;         /* tightly packed input frame size */
 } FFV1B200EncInfo;
 int  ffv1b200_enc_info(const FFV1B200Encoder *enc, FFV1B200EncInfo *info);
+/* The host half of encode_init alone (option resolution ffv1enc.c:676-1000, two-pass statistics 906-986, write_extradata
+ * 545-619): needs no CUDA device.  Fills *info (may be NULL; samples_per_frame / max_batch_frames stay 0) and copies
+ * the extradata the encoder would publish (extradata may be NULL to query *size).  Same errors as ffv1b200_enc_open. */
+int  ffv1b200_enc_resolve(const FFV1B200EncParams *params, FFV1B200EncInfo *info, uint8_t *extradata, int cap, int *size);
 
 void ffv1b200_enc_set_frame_props(FFV1B200Encoder *enc, const FFV1B200FrameProps *props);
 
@@ -172,6 +184,13 @@ int  ffv1b200_enc_encode_cuda(FFV1B200Encoder *enc, int nframes,
                               uint8_t *out, size_t out_cap, FFV1B200Packet *pkts, size_t *needed);
 
 int  ffv1b200_enc_stats(const FFV1B200Encoder *enc, FFV1B200EncStats *stats);
+
+/* First pass of a two-pass encode (flags & FFV1B200_FLAG_PASS1): the text the reference leaves in
+ * AVCodecContext.stats_out when the encoder is flushed (encode_frame with a NULL frame, ffv1enc.c:1235-1277), over all
+ * frames coded so far.  Every batch must have been collected.  Writes a NUL-terminated string; returns its length, or
+ * FFV1B200_ERR_BUFFER_TOO_SMALL with *needed = bytes required (terminator included).  The text is what a second encoder
+ * takes as FFV1B200EncParams.stats_in. */
+int  ffv1b200_enc_stats_out(FFV1B200Encoder *enc, char *buf, size_t cap, size_t *needed);
 
 /* Test hook: run only the per-pixel pass on frames already uploaded by the last encode call and copy the
  * (context<<16 | diff&0xffff) records of one frame/slice (coding order) to host.  Returns the record count. */

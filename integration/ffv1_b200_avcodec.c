@@ -398,6 +398,10 @@ static av_cold int b200_encode_init(AVCodecContext *avctx)
     p.device = s->device;
     p.max_batch_frames = s->batch;
     p.first_picture_number = 0;
+    /* two-pass coding and the experimental gate, as encode_init reads them (ffv1enc.c:680, 703, 906) */
+    p.flags = avctx->flags & (AV_CODEC_FLAG_PASS1 | AV_CODEC_FLAG_PASS2);
+    p.stats_in = avctx->stats_in;
+    p.strict_std_compliance = avctx->strict_std_compliance;
     if ((ret = ffv1b200_enc_open(&s->enc, &p)) < 0)
         return b200_err(avctx, ret);
     /* from here on every failure goes through b200_encode_close (this codec cannot set the internal
@@ -513,6 +517,19 @@ static int b200_encode_frame(AVCodecContext *avctx, AVPacket *pkt, const AVFrame
         while (!s->ready_count && s->ninflight)
             if ((ret = collect_oldest(avctx)) < 0)
                 return ret;
+        /* first pass: once everything is coded the statistics go to stats_out, like the reference's flush call
+         * (ffv1enc.c:1235-1277; lavc frees stats_out in avcodec_close) */
+        if ((avctx->flags & AV_CODEC_FLAG_PASS1) && !s->ninflight) {
+            size_t need = 0;
+            char probe[1];
+            if (ffv1b200_enc_stats_out(s->enc, probe, 0, &need) == FFV1B200_ERR_BUFFER_TOO_SMALL && need) {
+                av_freep(&avctx->stats_out);
+                if (!(avctx->stats_out = av_malloc(need)))
+                    return AVERROR(ENOMEM);
+                if ((ret = ffv1b200_enc_stats_out(s->enc, avctx->stats_out, need, NULL)) < 0)
+                    return b200_err(avctx, ret);
+            }
+        }
     }
     if (s->ready_count) {
         ReadyPacket *r = &s->ready[s->ready_head];

@@ -38,10 +38,19 @@ def lib():
     return _LIB
 
 class Encoder:
-    def __init__(self, w, h, pix_fmt, gop=12, level=-1, coder=0, context=0, slices=0, slicecrc=-1, threads=1):
+    def __init__(self, w, h, pix_fmt, gop=12, level=-1, coder=0, context=0, slices=0, slicecrc=-1, threads=1,
+                 strict_experimental=0, two_pass=0, stats_in=None):
+        """two_pass: 1 = first pass (AV_CODEC_FLAG_PASS1, statistics via stats_out()), 2 = second pass with stats_in"""
         self.h_ = None
         self.w, self.h, self.pix_fmt = w, h, pix_fmt
-        self.h_ = lib().ffv1ref_enc_open(w, h, pix_fmt.encode(), gop, level, coder, context, slices, slicecrc, threads, 0)
+        if isinstance(stats_in, str):
+            stats_in = stats_in.encode()
+        L = lib()
+        L.ffv1ref_enc_open_2pass.restype = ctypes.c_void_p
+        L.ffv1ref_enc_open_2pass.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_char_p] + [ctypes.c_int] * 9 + [ctypes.c_char_p]
+        L.ffv1ref_enc_stats_out.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int]
+        self.h_ = L.ffv1ref_enc_open_2pass(w, h, pix_fmt.encode(), gop, level, coder, context, slices, slicecrc, threads,
+                                           strict_experimental, two_pass, stats_in)
         if not self.h_:
             raise ValueError("reference encoder refused these options")
         self.cap = 65536 + pixfmt.frame_bytes(pix_fmt, w, h) * 4
@@ -51,6 +60,13 @@ class Encoder:
         b = ctypes.create_string_buffer(1 << 20)
         n = lib().ffv1ref_enc_extradata(self.h_, b, 1 << 20)
         return b.raw[:max(n, 0)]
+    def stats_out(self):
+        """flushes the encoder and returns AVCodecContext.stats_out (first pass)"""
+        buf = ctypes.create_string_buffer(8 << 20)
+        n = lib().ffv1ref_enc_stats_out(self.h_, buf, 8 << 20)
+        if n < 0:
+            raise RuntimeError("no statistics (%d)" % n)
+        return buf.value.decode()
     def encode(self, frame, sar=(0, 1), interlaced=0, tff=0):
         planes = split_planes(np.ascontiguousarray(frame).view(np.uint8).reshape(-1), self.pix_fmt, self.w, self.h)
         ptrs, strides = _plane_args(planes)

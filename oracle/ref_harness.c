@@ -49,6 +49,37 @@ void *ffv1ref_enc_open(int w, int h, const char *pix_fmt, int gop, int level, in
     return enc_open_impl(&ff_ffv1_encoder, w, h, pix_fmt, gop, level, coder, context, slices, slicecrc, threads, strict_experimental, 0);
 }
 
+/* Two-pass coding: pass = 1 sets AV_CODEC_FLAG_PASS1 (statistics into stats_out), pass = 2 sets AV_CODEC_FLAG_PASS2;
+ * stats_in (may be NULL) is handed to the encoder as AVCodecContext.stats_in (ffv1enc.c:906-986). */
+static int g_pass;
+static const char *g_stats_in;
+void *ffv1ref_enc_open_2pass(int w, int h, const char *pix_fmt, int gop, int level, int coder, int context,
+                             int slices, int slicecrc, int threads, int strict_experimental, int pass, const char *stats_in)
+{
+    void *r;
+    reg();
+    g_pass = pass; g_stats_in = stats_in;
+    r = enc_open_impl(&ff_ffv1_encoder, w, h, pix_fmt, gop, level, coder, context, slices, slicecrc, threads, strict_experimental, 0);
+    g_pass = 0; g_stats_in = NULL;
+    return r;
+}
+
+/* flushes the encoder (frame = NULL: encode_frame then writes the statistics text, ffv1enc.c:1235-1277) and copies
+ * AVCodecContext.stats_out; returns its length or <0 */
+int ffv1ref_enc_stats_out(void *h, char *dst, int cap)
+{
+    RefEnc *e = h;
+    AVPacket pkt;
+    int got = 0, n;
+    av_init_packet(&pkt); pkt.data = NULL; pkt.size = 0;
+    if (avcodec_encode_video2(e->ctx, &pkt, NULL, &got) < 0) return -1;
+    if (!e->ctx->stats_out) return -3;
+    n = (int)strlen(e->ctx->stats_out);
+    if (n + 1 > cap) return -2;
+    memcpy(dst, e->ctx->stats_out, n + 1);
+    return n;
+}
+
 /* Drop-in test support: register an out-of-tree AVCodec (the ffv1_b200 shim) with THIS libavcodec and open it by
  * name through the same public API path (avcodec_find_encoder_by_name, utils.c:3051). */
 void ffv1ref_register_codec(AVCodec *codec) { reg(); avcodec_register(codec); }
@@ -76,6 +107,9 @@ static void *enc_open_impl(AVCodec *codec, int w, int h, const char *pix_fmt, in
     e->ctx->slices = slices;
     e->ctx->flags |= AV_CODEC_FLAG_BITEXACT;
     if (strict_experimental) e->ctx->strict_std_compliance = FF_COMPLIANCE_EXPERIMENTAL;
+    if (g_pass == 1) e->ctx->flags |= AV_CODEC_FLAG_PASS1;
+    if (g_pass == 2) e->ctx->flags |= AV_CODEC_FLAG_PASS2;
+    if (g_stats_in) e->ctx->stats_in = av_strdup(g_stats_in);
     if (threads > 1) { e->ctx->thread_count = threads; e->ctx->thread_type = FF_THREAD_SLICE; }
     else e->ctx->thread_count = 1;
     av_opt_set_int(e->ctx->priv_data, "coder", coder, 0);

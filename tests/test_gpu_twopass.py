@@ -1,0 +1,62 @@
+"""Two-pass coding on the GPU (-m gpu): the first pass's statistics text, the second pass's packets and their decoding
+against the reference build's own output (tests/golden/twopass.json; the live reference build where it travelled)."""
+import base64, hashlib, json, os, zlib, numpy as np, pytest
+from twopass_cases import TWOPASS_CASES, make_frames
+
+pytestmark = pytest.mark.gpu
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "twopass.json")))
+
+def md5(b):
+    return hashlib.md5(bytes(b)).hexdigest()
+
+def gpu_opts(opts):
+    o = dict(opts)
+    o["g"] = o.pop("gop")
+    return o
+
+@pytest.mark.parametrize("batch", [64, 2], ids=["one_batch", "batches_of_2"])
+@pytest.mark.parametrize("case", TWOPASS_CASES, ids=[c[0] for c in TWOPASS_CASES])
+def test_first_pass_statistics(case, batch):
+    import ffv1_b200
+    cid, w, h, fmt, opts, n = case
+    frames = make_frames(case)
+    g = GOLD[cid]
+    assert md5(b"".join(f.tobytes() for f in frames)) == g["input_md5"]
+    enc = ffv1_b200.FFV1Encoder(w, h, fmt, max_batch_frames=batch, flags=ffv1_b200.FLAG_PASS1, **gpu_opts(opts))
+    assert enc.extradata.hex() == g["pass1_extradata"]
+    got = enc.encode_batch(frames)
+    assert [[len(p), md5(p), int(k)] for p, k in got] == g["pass1_packets"]
+    stats = enc.stats_out()
+    want = zlib.decompress(base64.b64decode(g["stats_z"])).decode()
+    assert len(stats) == len(want) and stats == want
+
+@pytest.mark.parametrize("case", TWOPASS_CASES, ids=[c[0] for c in TWOPASS_CASES])
+def test_second_pass_packets_and_decode(case):
+    import ffv1_b200
+    cid, w, h, fmt, opts, n = case
+    frames = make_frames(case)
+    g = GOLD[cid]
+    stats = zlib.decompress(base64.b64decode(g["stats_z"])).decode()
+    enc = ffv1_b200.FFV1Encoder(w, h, fmt, max_batch_frames=3, flags=ffv1_b200.FLAG_PASS2, stats_in=stats, **gpu_opts(opts))
+    assert enc.extradata.hex() == g["pass2_extradata"]
+    got = enc.encode_batch(frames)                      # batches of 3 against GOPs of 2 / 3: states carry over
+    assert [[len(p), md5(p), int(k)] for p, k in got] == g["pass2_packets"]
+    dec = ffv1_b200.FFV1Decoder(w, h, enc.extradata, max_batch_frames=4)
+    outs = dec.decode_batch([p for p, _ in got])
+    for i, f in enumerate(frames):
+        assert np.array_equal(outs[i][0], f.view(np.uint8).reshape(-1)), "frame %d does not round-trip" % i
+
+def test_gpu_statistics_feed_the_reference_second_pass(ref=None):
+    """the text of the CUDA first pass, given to the reference's second pass, yields the reference's own second-pass stream"""
+    from oracle import ffv1_ref
+    if not ffv1_ref.available():
+        pytest.skip("reference build not present")
+    import ffv1_b200
+    case = TWOPASS_CASES[0]
+    cid, w, h, fmt, opts, n = case
+    frames = make_frames(case)
+    enc = ffv1_b200.FFV1Encoder(w, h, fmt, max_batch_frames=8, flags=ffv1_b200.FLAG_PASS1, **gpu_opts(opts))
+    enc.encode_batch(frames)
+    e2 = ffv1_ref.Encoder(w, h, fmt, two_pass=2, stats_in=enc.stats_out(), **opts)
+    assert e2.extradata.hex() == GOLD[cid]["pass2_extradata"]
+    assert [[len(p), md5(p), int(k)] for p, k in (e2.encode(f) for f in frames)] == GOLD[cid]["pass2_packets"]
