@@ -433,6 +433,20 @@ __device__ __forceinline__ void dec_line_rc(SliceRd &sr, uint8_t *model, const i
     fr_close(c, sr.rc);
 }
 
+// Version 4, slice_coding_mode 1 ("PCM", ffv1dec.c:111-122): every sample is `bits` raw bits, each decoded with a
+// fresh state 128 (an even split of the interval); no prediction, no adaptive state.
+__device__ void dec_line_pcm(SliceRd &sr, const uint16_t *lut, int16_t *cur, int w, int bits)
+{
+    for (int x = 0; x < w; x++) {
+        int v = 0;
+        for (int i = 0; i < bits; i++) {
+            uint8_t st = 128;
+            v += v + rd_get(sr.rc, &st, lut);
+        }
+        cur[x] = (int16_t)v;
+    }
+}
+
 // ---- the common case (planar, range coder, three-table context, model and lines in shared memory): what one lane has to
 // do per sample is cut down to what depends on the sample decoded just before.  The warp prepares every line in parallel:
 // per x a record {T = top[x], q12 = Q1[LT-T] + Q2[T-RT]} from the finished line above; the serial lane reads one record,
@@ -512,6 +526,7 @@ __global__ void __launch_bounds__(32 * kDecWarps, MINB) k_decode(const DecDevice
         SliceRd sr;
         int sx = 0, sy = 0, sw = 0, sh = 0, qti[3] = {0, 0, 0};
         int bad = 0;
+        int v4 = 1 | 1 << 4;                // version 4 header fields: rct_by | rct_ry << 4 | coding mode << 8 | reset contexts << 16
         if (lane == 0) {
             sr.golomb = golomb; sr.run_index = 0; sr.err = 0;
             rd_init(sr.rc, sbeg, ssize);
@@ -550,6 +565,18 @@ __global__ void __launch_bounds__(32 * kDecWarps, MINB) k_decode(const DecDevice
                 rd_symbol(sr.rc, st, s_lut, false, sr.err);      // picture structure
                 rd_symbol(sr.rc, st, s_lut, false, sr.err);      // sample aspect ratio num
                 rd_symbol(sr.rc, st, s_lut, false, sr.err);      // sample aspect ratio den
+                if (T.version > 3) {                             // ffv1dec.c:345-356
+                    const int reset = rd_get(sr.rc, st, s_lut);
+                    const int mode = rd_symbol(sr.rc, st, s_lut, false, sr.err);
+                    int by = 1, ry = 1;
+                    if (mode != 1) {
+                        by = rd_symbol(sr.rc, st, s_lut, false, sr.err);
+                        ry = rd_symbol(sr.rc, st, s_lut, false, sr.err);
+                        if ((unsigned long long)(unsigned)by + (unsigned)ry > 4ull) bad = 1;   // "slice_rct_y_coef out of range"
+                    }
+                    if ((unsigned)mode > 255u || (mode == 1 && golomb)) bad = 1;               // PCM slices are range coded (ffv1enc.c:1209)
+                    v4 = (by & 15) | (ry & 15) << 4 | (mode & 255) << 8 | reset << 16;
+                }
             }
             if (sw + 2 * kDecRingPad > T.ring_w) bad = 1;
             if (!bad && golomb) {                                                       // ffv1dec.c:427-434
@@ -568,9 +595,12 @@ __global__ void __launch_bounds__(32 * kDecWarps, MINB) k_decode(const DecDevice
         sw = __shfl_sync(0xFFFFFFFFu, sw, 0); sh = __shfl_sync(0xFFFFFFFFu, sh, 0);
         qti[0] = __shfl_sync(0xFFFFFFFFu, qti[0], 0); qti[1] = __shfl_sync(0xFFFFFFFFu, qti[1], 0);
         qti[2] = __shfl_sync(0xFFFFFFFFu, qti[2], 0);
+        v4 = __shfl_sync(0xFFFFFFFFu, v4, 0);
+        const int rct_by = v4 & 15, rct_ry = (v4 >> 4) & 15, coding_mode = (v4 >> 8) & 255;
+        const bool pcm = coding_mode == 1;
 
-        // ---- keyframe: reset the models (ffv1.c:177-202)
-        if (key) {
+        // ---- keyframe (or a version-4 slice that asks for it, ffv1dec.c:419-420): reset the models (ffv1.c:177-202)
+        if (key || (v4 >> 16)) {
             for (int pc = 0; pc < 3; pc++) {
                 uint8_t *m = models + (size_t)pc * T.state_stride;
                 const int set = qti[pc < T.plane_count ? pc : 0];
@@ -621,7 +651,7 @@ __global__ void __launch_bounds__(32 * kDecWarps, MINB) k_decode(const DecDevice
                 }
                 const bool ring_sm = T.smem_ring_w && w + 2 * kDecRingPad <= T.smem_ring_w;
                 const int rw = ring_sm ? T.smem_ring_w : T.ring_w;
-                if (!golomb && ring_sm && !q[3 * 256 + 127]) {
+                if (!golomb && ring_sm && !q[3 * 256 + 127] && !pcm) {
                     LineRec *rec = reinterpret_cast<LineRec *>(s_ring);
                     for (int x = lane; x < w; x += 32) rec[x] = LineRec{0, 0, 0, 0};
                     __syncwarp();
@@ -676,7 +706,9 @@ __global__ void __launch_bounds__(32 * kDecWarps, MINB) k_decode(const DecDevice
                     if (lane == 0) {
                         cur[-1] = top[0];                 // ffv1dec.c:199-200
                         top[w] = top[w - 1];
-                        if (golomb)
+                        if (pcm)
+                            dec_line_pcm(sr, s_lut, cur, w, bits);
+                        else if (golomb)
                             dec_line(sr, model, q, s_lut, cur, top, top2, w, bits);
                         else if (model_sm && ring_sm) {
                             // the common case, spelled out on the shared-memory arrays so that the loads are LDS
@@ -728,7 +760,8 @@ __global__ void __launch_bounds__(32 * kDecWarps, MINB) k_decode(const DecDevice
                         top[sw] = top[sw - 1];
                         uint8_t *model = models + (size_t)pc * T.state_stride;
                         const int16_t *q = s_quant + qti[pc < T.plane_count ? pc : 0] * 5 * 256;
-                        if (golomb) dec_line(sr, model, q, s_lut, cur, top, top2, sw, bits);
+                        if (pcm) dec_line_pcm(sr, s_lut, cur, sw, bits - 1);                    // ffv1dec.c:255: no extra bit without the RCT
+                        else if (golomb) dec_line(sr, model, q, s_lut, cur, top, top2, sw, bits);
                         else if (q[3 * 256 + 127]) dec_line_rc<true>(sr, model, q, s_lut, cur, top, top2, sw, bits);
                         else dec_line_rc<false>(sr, model, q, s_lut, cur, top, top2, sw, bits);
                     }
@@ -738,9 +771,11 @@ __global__ void __launch_bounds__(32 * kDecWarps, MINB) k_decode(const DecDevice
                 for (int x = lane; x < sw; x += 32) {
                     int g = gr[x], b = br[x], r = rr[x];
                     const int a = nplanes == 4 ? ar[x] : 0;
-                    b -= offset; r -= offset;
-                    g -= (b + r) >> 2;
-                    b += g; r += g;
+                    if (!pcm) {                                                               // ffv1dec.c:263-269
+                        b -= offset; r -= offset;
+                        g -= (b * rct_by + r * rct_ry) >> 2;
+                        b += g; r += g;
+                    }
                     if (T.rgb32) {
                         uint32_t *d = reinterpret_cast<uint32_t *>(frame + T.plane_off[0] + (size_t)(sy + y) * T.plane_pitch[0]) + sx + x;
                         *d = (uint32_t)(b & 0xFF) | ((uint32_t)(g & 0xFF) << 8) | ((uint32_t)(r & 0xFF) << 16) | ((uint32_t)(a & 0xFF) << 24);

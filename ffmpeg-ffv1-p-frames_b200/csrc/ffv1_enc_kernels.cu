@@ -46,13 +46,15 @@ __device__ __forceinline__ int raw_planar(const Layout &L, const uint8_t *const 
     return (int)(int16_t)(v >> L.sample_shift);
 }
 
+// {ry, by} of the 15 candidates of choose_rct_params (ffv1enc.c:1066-1084), packed ry | by << 4
+__constant__ uint8_t c_rct_coef[15] = {0x00, 0x11, 0x22, 0x20, 0x02, 0x04, 0x40, 0x30, 0x03, 0x13, 0x31, 0x21, 0x12, 0x10, 0x01};
+
 template <int SRC>
-__device__ __forceinline__ void raw_rgb(const Layout &L, const uint8_t *const *pl, const int32_t *ls,
-                                        const SliceGeom &g, int x, int y, int out[4])
+__device__ __forceinline__ void load_bgr(const uint8_t *const *pl, const int32_t *ls, const SliceGeom &g, int x, int y,
+                                         int &b, int &gg, int &r, int &a)
 {
-    // ffv1enc.c:431-458: b,g,r[,a] from packed BGRA or from data[0],data[1],data[2] (the reference's naming; for
-    // GBRP that makes plane 1 the RCT base channel), then b-=g; r-=g; g+=(b+r)>>2; b+=off; r+=off
-    int b, gg, r, a = 0;
+    // ffv1enc.c:431-442 / 1103-1112: packed BGRA, or data[0], data[1], data[2] under the reference's names b, g, r
+    a = 0;
     if (SRC == SRC_RGB32) {
         unsigned v = *reinterpret_cast<const uint32_t *>(pl[0] + (size_t)(g.y0 + y) * ls[0] + 4 * (g.x0 + x));
         b = v & 0xFF; gg = (v >> 8) & 0xFF; r = (v >> 16) & 0xFF; a = v >> 24;
@@ -61,10 +63,87 @@ __device__ __forceinline__ void raw_rgb(const Layout &L, const uint8_t *const *p
         gg = *reinterpret_cast<const uint16_t *>(pl[1] + (size_t)(g.y0 + y) * ls[1] + 2 * (g.x0 + x));
         r  = *reinterpret_cast<const uint16_t *>(pl[2] + (size_t)(g.y0 + y) * ls[2] + 2 * (g.x0 + x));
     }
+}
+
+template <int SRC>
+__device__ __forceinline__ void raw_rgb(const Layout &L, const uint8_t *const *pl, const int32_t *ls,
+                                        const SliceGeom &g, int x, int y, int out[4], int by, int ry)
+{
+    // ffv1enc.c:431-458: b,g,r[,a] from packed BGRA or from data[0],data[1],data[2] (the reference's naming; for
+    // GBRP that makes plane 1 the RCT base channel), then b-=g; r-=g; g+=(b+r)>>2; b+=off; r+=off
+    int b, gg, r, a;
+    load_bgr<SRC>(pl, ls, g, x, y, b, gg, r, a);
     b -= gg; r -= gg;
-    gg += (b + r) >> 2;
+    gg += (b * by + r * ry) >> 2;                       // version <= 3: by = ry = 1 (ffv1enc.c:447-451, 1165-1167)
     b += L.rct_offset; r += L.rct_offset;
     out[0] = (int16_t)gg; out[1] = (int16_t)b; out[2] = (int16_t)r; out[3] = (int16_t)a;
+}
+
+// choose_rct_params (ffv1enc.c:1064-1144): for every slice of an RGB frame, the coefficient pair that minimises the sum of
+// |second-order difference of the luma-like channel| over the slice.  The reference walks the slice row by row keeping
+// the previous row's horizontal differences; spelled per pixel that is the 2x2 stencil d(x,y) = h(x,y) - h(x,y-1) with
+// h(x,y) = v(x,y) - v(x-1,y), for x >= 1 and y >= 1.  One CTA per (slice, frame); the 15 sums are 32-bit and wrap like the
+// reference's int accumulators; the first minimum wins.
+constexpr int kRctThreads = 256;
+
+template <int SRC>
+__global__ void __launch_bounds__(kRctThreads) k_rct_search(const EncDeviceTables T, const EncBatch B, uint8_t *rct_idx)
+{
+    __shared__ uint32_t s_part[kRctThreads / 32][15];
+    const Layout &L = T.layout;
+    const int s = blockIdx.x, f = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const SliceGeom &g = T.slices[s];
+    const uint8_t *pl[4];
+    int32_t ls[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) { pl[i] = B.planes[f * 4 + i]; ls[i] = B.linesize[i]; }
+    uint32_t stat[15];
+#pragma unroll
+    for (int i = 0; i < 15; i++) stat[i] = 0u;
+    const int w1 = g.w - 1, n = w1 * (g.h - 1);
+    for (int i = tid; i < n; i += kRctThreads) {
+        const int y = 1 + i / w1, x = 1 + i - (y - 1) * w1;
+        int b[4], gg[4], r[4], a;
+        load_bgr<SRC>(pl, ls, g, x, y, b[0], gg[0], r[0], a);
+        load_bgr<SRC>(pl, ls, g, x - 1, y, b[1], gg[1], r[1], a);
+        load_bgr<SRC>(pl, ls, g, x, y - 1, b[2], gg[2], r[2], a);
+        load_bgr<SRC>(pl, ls, g, x - 1, y - 1, b[3], gg[3], r[3], a);
+        // the previous row's differences pass through the reference's int16_t sample buffer
+        const int bg = (gg[0] - gg[1]) - (int)(int16_t)(gg[2] - gg[3]);
+        int bb = (b[0] - b[1]) - (int)(int16_t)(b[2] - b[3]);
+        int br = (r[0] - r[1]) - (int)(int16_t)(r[2] - r[3]);
+        br -= bg; bb -= bg;
+#pragma unroll
+        for (int k = 0; k < 15; k++) {
+            const int ry = c_rct_coef[k] & 15, by = c_rct_coef[k] >> 4;
+            stat[k] += (uint32_t)abs(bg + ((br * ry + bb * by) >> 2));
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 15; k++) {
+        uint32_t v = stat[k];
+#pragma unroll
+        for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, d);
+        if (lane == 0) s_part[warp][k] = v;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int best = 0, best_v = 0;
+        for (int k = 0; k < 15; k++) {
+            uint32_t v = 0;
+            for (int wv = 0; wv < kRctThreads / 32; wv++) v += s_part[wv][k];
+            if (k == 0 || (int)v < best_v) { best = k; best_v = (int)v; }
+        }
+        rct_idx[f * L.nslices + s] = (uint8_t)best;
+    }
+}
+
+void launch_rct_search(const EncDeviceTables &t, const EncBatch &b, cudaStream_t s)
+{
+    dim3 grid(t.layout.nslices, b.nframes);
+    uint8_t *out = const_cast<uint8_t *>(b.rct_idx);
+    if (t.layout.src_kind == SRC_RGB32) k_rct_search<SRC_RGB32><<<grid, kRctThreads, 0, s>>>(t, b, out);
+    else                                k_rct_search<SRC_GBRP16><<<grid, kRctThreads, 0, s>>>(t, b, out);
 }
 
 template <int SRC, int NIN>
@@ -94,6 +173,8 @@ k_pixel(const EncDeviceTables T, const EncBatch B)
 
     const int w = g.pw[td.plane];
     const int bits = L.coded_bits;
+    int rct_by = 1, rct_ry = 1;
+    if (RGB && B.rct_idx) { const int cf = c_rct_coef[B.rct_idx[f * L.nslices + td.slice]]; rct_ry = cf & 15; rct_by = cf >> 4; }
     uint32_t *rec_slice = B.rec + (size_t)f * L.rec_per_frame + g.rec_first;
     const LineDesc *lines = T.lines + g.line_first;
 
@@ -117,7 +198,7 @@ k_pixel(const EncDeviceTables T, const EncBatch B)
                     S[rr * kPixelRowElems + col] = (int16_t)v;
                 } else {
                     int v[4] = {0, 0, 0, 0};
-                    if (!zero) raw_rgb<SRC>(L, pl, ls, g, x, yy, v);
+                    if (!zero) raw_rgb<SRC>(L, pl, ls, g, x, yy, v, rct_by, rct_ry);
 #pragma unroll
                     for (int p = 0; p < 4; p++)
                         if (p < npl) S[p * plane_stride + rr * kPixelRowElems + col] = (int16_t)v[p];
@@ -674,10 +755,11 @@ __global__ void __launch_bounds__(kRangeThreads) k_rangecode(const EncDeviceTabl
                 const uint16_t *src;
                 uint32_t n;
                 if (r < 0) {
-                    src = T.prefix + (size_t)(s * 2 + key) * kMaxPrefix;
-                    n = (uint32_t)T.prefix_len[s * 2 + key];
+                    const int var = B.rct_idx ? B.rct_idx[f * L.nslices + s] : 0;
+                    src = T.prefix + ((size_t)(s * 2 + key) * T.nvar + var) * kMaxPrefix;
+                    n = (uint32_t)T.prefix_len[(s * 2 + key) * T.nvar + var];
                 } else if (r == nruns) {
-                    src = T.prefix + (size_t)L.nslices * 2 * kMaxPrefix;      // one extra row holding the entry "129"
+                    src = T.prefix + (size_t)L.nslices * 2 * T.nvar * kMaxPrefix;      // one extra row holding the entry "129"
                     n = 1u;
                 } else {
                     const int pc = run_pc[r];
@@ -889,8 +971,9 @@ __global__ void __launch_bounds__(32) k_golomb(const EncDeviceTables T, const En
     for (int f = f0; f < f1; f++) {
         const int key = B.frame_key[f] ? 1 : 0;
         uint8_t *out = B.scratch + (size_t)f * L.scratch_per_frame + g.scratch_off + kScratchLead;
-        const int npre = T.gprefix_len[s * 2 + key];
-        const uint8_t *pre = T.gprefix + (size_t)(s * 2 + key) * kMaxGolombPrefix;
+        const int hv = (s * 2 + key) * T.nvar + (B.rct_idx ? B.rct_idx[f * L.nslices + s] : 0);       // header variant
+        const int npre = T.gprefix_len[hv];
+        const uint8_t *pre = T.gprefix + (size_t)hv * kMaxGolombPrefix;
         for (int i = lane; i < npre; i += 32) out[i] = pre[i];
         // every lane walks the lines (32 records per coalesced load, handed to lane 0 through shuffles); lane 0 codes
         {
@@ -1114,8 +1197,9 @@ __global__ void __launch_bounds__(32 * kGrPackWarps) k_gr_pack(const EncDeviceTa
     uint8_t *out = B.scratch + (size_t)f * L.scratch_per_frame + g.scratch_off + kScratchLead;     // 4-byte aligned
     uint32_t *out32 = reinterpret_cast<uint32_t *>(out);
     const uint32_t cap = g.scratch_cap - kScratchLead;
-    const int npre = T.gprefix_len[s * 2 + key];
-    const uint8_t *pre = T.gprefix + (size_t)(s * 2 + key) * kMaxGolombPrefix;
+    const int hv = (s * 2 + key) * T.nvar + (B.rct_idx ? B.rct_idx[f * L.nslices + s] : 0);           // header variant
+    const int npre = T.gprefix_len[hv];
+    const uint8_t *pre = T.gprefix + (size_t)hv * kMaxGolombPrefix;
     for (int i = lane; i < (npre & ~3); i += 32) if ((uint32_t)i < cap) out[i] = pre[i];             // whole words of the prefix
     uint32_t *win = s_win[warp];
     for (int i = lane; i < kGrPackWin; i += 32) win[i] = 0u;

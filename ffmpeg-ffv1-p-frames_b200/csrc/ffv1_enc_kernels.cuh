@@ -42,6 +42,7 @@ struct EncBatch {
     uint32_t *list_count;               // [chains][ctx_count]
     uint16_t *list_order;               // [chains][ctx_count] contexts, longest list first
     uint2 *lists;                       // [nframes * samples_per_frame] {decision position, residual | frame << 16}
+    const uint8_t *rct_idx;             // version-4 RGB: [nframes][nslices] index of the slice's RCT coefficient pair (else null)
     // adaptive state
     uint8_t *state_seg;                 // global-state mode: [nseg][nslices][npc][ctx_count*32]
     const uint8_t *carry_in;            // [nslices][npc][ctx_count*32]
@@ -70,10 +71,13 @@ struct EncDeviceTables {
     int32_t ec;
     int32_t version;
     int32_t state_in_smem;
+    int32_t nvar;                       // slice-header variants per (slice, keyframe flag): 15 for version-4 RGB, else 1
 };
 
 int  pixel_smem_bytes(const Layout &L);
 void launch_pixel(const EncDeviceTables &t, const EncBatch &b, cudaStream_t s);
+// version 4, RGB: per-slice choice among the 15 RCT coefficient pairs (choose_rct_params, ffv1enc.c:1064-1144) -> b.rct_idx
+void launch_rct_search(const EncDeviceTables &t, const EncBatch &b, cudaStream_t s);
 int  replay_smem_bytes(const Layout &L);
 void launch_replay(const EncDeviceTables &t, const EncBatch &b, cudaStream_t s);
 void launch_rangecode(const EncDeviceTables &t, const EncBatch &b, cudaStream_t s);

@@ -76,6 +76,7 @@ struct FFV1B200Encoder {
     DevBuf<uint16_t> d_dec, d_list_order;
     DevBuf<uint2> d_lists;
     DevBuf<uint8_t> d_scratch, d_state_seg, d_carry[kCarry];
+    DevBuf<uint8_t> d_rct_idx;       // version-4 RGB: RCT coefficient pair chosen for every (frame, slice)
     Slot slot[kSlots];
     uint64_t submitted = 0, collected = 0;      // batch counters; slot of batch k = k % kSlots
     int carry_next = 0;                          // ring index holding the state after the last submitted batch
@@ -101,29 +102,34 @@ int upload_prefixes(FFV1B200Encoder *e, Slot &sl, cudaStream_t s)
     if (sl.prefix_valid && sl.props.sar_num == pr.sar_num && sl.props.sar_den == pr.sar_den && sl.props.picture_structure == pr.picture_structure)
         return 0;
     const int ns = e->cfg.slice_count();
+    const int nvar = rct_variants(e->cfg);                                   // version-4 RGB: one header per RCT coefficient pair
     if (e->tab.layout.golomb) {
-        std::vector<uint8_t> gp((size_t)ns * 2 * kMaxGolombPrefix, 0);
-        std::vector<int32_t> gl((size_t)ns * 2, 0);
+        std::vector<uint8_t> gp((size_t)ns * 2 * nvar * kMaxGolombPrefix, 0);
+        std::vector<int32_t> gl((size_t)ns * 2 * nvar, 0);
         for (int sx = 0; sx < ns; sx++)
-            for (int key = 0; key < 2; key++) {
-                std::vector<uint8_t> b = slice_prefix_bytes(e->cfg, sx, key != 0, pr.sar_num, pr.sar_den, pr.picture_structure);
-                if ((int)b.size() > kMaxGolombPrefix) return fail(FFV1B200_ERR_EINVAL, "slice header too long");
-                std::copy(b.begin(), b.end(), gp.begin() + (size_t)(sx * 2 + key) * kMaxGolombPrefix);
-                gl[sx * 2 + key] = (int32_t)b.size();
-            }
+            for (int key = 0; key < 2; key++)
+                for (int v = 0; v < nvar; v++) {
+                    std::vector<uint8_t> b = slice_prefix_bytes(e->cfg, sx, key != 0, pr.sar_num, pr.sar_den, pr.picture_structure, v);
+                    if ((int)b.size() > kMaxGolombPrefix) return fail(FFV1B200_ERR_EINVAL, "slice header too long");
+                    const size_t at = (size_t)(sx * 2 + key) * nvar + v;
+                    std::copy(b.begin(), b.end(), gp.begin() + at * kMaxGolombPrefix);
+                    gl[at] = (int32_t)b.size();
+                }
         CU_TRY(sl.d_gprefix.upload(gp.data(), gp.size(), s));
         CU_TRY(sl.d_gprefix_len.upload(gl.data(), gl.size(), s));
     } else {
-        std::vector<uint16_t> pre((size_t)(ns * 2 + 1) * kMaxPrefix, 0);
-        pre[(size_t)ns * 2 * kMaxPrefix] = 129;                              // the decision that closes every slice (state 129, bit 0)
-        std::vector<int32_t> len((size_t)ns * 2, 0);
+        std::vector<uint16_t> pre((size_t)(ns * 2 * nvar + 1) * kMaxPrefix, 0);
+        pre[(size_t)ns * 2 * nvar * kMaxPrefix] = 129;                       // the decision that closes every slice (state 129, bit 0)
+        std::vector<int32_t> len((size_t)ns * 2 * nvar, 0);
         for (int sx = 0; sx < ns; sx++)
-            for (int key = 0; key < 2; key++) {
-                std::vector<uint16_t> d = slice_prefix_decisions(e->cfg, sx, key != 0, pr.sar_num, pr.sar_den, pr.picture_structure);
-                if ((int)d.size() > kMaxPrefix) return fail(FFV1B200_ERR_EINVAL, "slice header too long");
-                std::copy(d.begin(), d.end(), pre.begin() + (size_t)(sx * 2 + key) * kMaxPrefix);
-                len[sx * 2 + key] = (int32_t)d.size();
-            }
+            for (int key = 0; key < 2; key++)
+                for (int v = 0; v < nvar; v++) {
+                    std::vector<uint16_t> d = slice_prefix_decisions(e->cfg, sx, key != 0, pr.sar_num, pr.sar_den, pr.picture_structure, v);
+                    if ((int)d.size() > kMaxPrefix) return fail(FFV1B200_ERR_EINVAL, "slice header too long");
+                    const size_t at = (size_t)(sx * 2 + key) * nvar + v;
+                    std::copy(d.begin(), d.end(), pre.begin() + at * kMaxPrefix);
+                    len[at] = (int32_t)d.size();
+                }
         CU_TRY(sl.d_prefix.upload(pre.data(), pre.size(), s));
         CU_TRY(sl.d_prefix_len.upload(len.data(), len.size(), s));
     }
@@ -140,6 +146,7 @@ int alloc_buffers(FFV1B200Encoder *e)
     CU_TRY(e->d_rec.alloc((size_t)L.rec_per_frame * F));
     CU_TRY(e->d_run_cnt.alloc((size_t)L.runs_per_frame * F));
     CU_TRY(e->d_slice_bytes.alloc((size_t)L.nslices * F));
+    if (rct_variants(e->cfg) > 1) CU_TRY(e->d_rct_idx.alloc((size_t)L.nslices * F));
     // coder output: bytes (Golomb-Rice) or k_rangecode's 16-bit entries, `scratch_cap` of them per slice
     CU_TRY(e->d_scratch.alloc((size_t)L.scratch_per_frame * F * (L.golomb ? 1 : 2)));
     if (!L.golomb || e->golomb_lists) CU_TRY(e->d_dec.alloc((size_t)L.dec_per_frame * F + 64));   // Golomb lists: the code words
@@ -186,6 +193,7 @@ EncDeviceTables device_tables(FFV1B200Encoder *e, const Slot &sl)
     t.init_state = e->d_init_state.p;
     t.gprefix = sl.d_gprefix.p; t.gprefix_len = sl.d_gprefix_len.p; t.prefix = sl.d_prefix.p; t.prefix_len = sl.d_prefix_len.p;
     t.ec = e->cfg.ec; t.version = e->cfg.version; t.state_in_smem = e->state_in_smem ? 1 : 0;
+    t.nvar = rct_variants(e->cfg);
     return t;
 }
 
@@ -232,8 +240,10 @@ int enqueue_kernels(FFV1B200Encoder *e, Slot &sl, cudaStream_t s)
     b.status = sl.d_status.p;
     b.line_pos = e->d_line_pos.p; b.ctx_hist = e->d_ctx_hist.p;
     b.list_start = e->d_list_start.p; b.list_count = e->d_list_count.p; b.list_order = e->d_list_order.p; b.lists = e->d_lists.p;
+    b.rct_idx = e->d_rct_idx.p;
 
     cudaEventRecord(sl.ev[0], s);
+    if (t.nvar > 1) { launch_rct_search(t, b, s); e->stats.kernel_launches++; }      // choose_rct_params, before the RCT is applied
     if (sl.fast) {
         // tensor-map TMA needs the frames of the batch at a constant distance (true for the staged host path)
         long long fstride = nframes > 1 ? (long long)(sl.h_planes.p[4] - sl.h_planes.p[0]) : 0;

@@ -303,7 +303,13 @@ int resolve_encoder(const EncOptions &o, Config &c, std::string &err)
         version = o.level;
     }
     c.ec = o.slicecrc < 0 ? (version >= 3) : o.slicecrc;
-    if (version == 2 || version > 3) { err = "FFV1 versions 2 and 4 are experimental in the reference and not provided"; return FFV1B200_ERR_INVALIDDATA; }
+    // ffv1enc.c:703-706: versions 2 and 4 are experimental.  Version 4 (micro version 2: per-slice RCT coefficients, slice
+    // coding mode, context reset flag) is provided behind -strict experimental; version 2 is not.
+    if ((version == 2 || version > 3) && !o.strict_experimental) {
+        err = "Version 2 needed for requested features but version 2 is experimental and not enabled";
+        return FFV1B200_ERR_INVALIDDATA;
+    }
+    if (version == 2) { err = "FFV1 version 2 (an abandoned experimental bitstream) is not provided"; return FFV1B200_ERR_ENOSYS; }
 
     // coder remaps, ffv1enc.c:708-718, 755-759, 810-814
     int ac = o.coder;
@@ -317,7 +323,7 @@ int resolve_encoder(const EncOptions &o, Config &c, std::string &err)
     }
     c.ac = ac;
     c.version = version;
-    c.micro_version = version == 3 ? 4 : 0;
+    c.micro_version = version == 3 ? 4 : (version == 4 ? 2 : 0);              // ffv1enc.c:565-569
     c.context_model = o.context;
     c.gop_size = o.gop_size;
     c.intra = o.gop_size < 2;
@@ -330,7 +336,8 @@ int resolve_encoder(const EncOptions &o, Config &c, std::string &err)
         for (int i = 1; i < 256; i++) c.state_transition[i] = one[i];
     }
     fill_quant_tables(c);
-    c.plane_count = c.transparency ? 3 : 2;               // ffv1enc.c:720, 890-891
+    c.plane_count = c.transparency ? 3 : 2;               // ffv1enc.c:720, 890-893
+    if (!c.chroma_planes && version > 3) c.plane_count--;
 
     c.num_h_slices = c.num_v_slices = 1;
     if (version > 1) {                                    // ffv1enc.c:988-1000
@@ -699,7 +706,7 @@ int parse_extradata(const uint8_t *d, int n, int width, int height, Config &c, s
     }
     if (bd.bad) { err = "damaged global header"; return FFV1B200_ERR_INVALIDDATA; }
     if (c.version > 2 && (n < 4 || crc32_ieee(0, d, n) != 0)) { err = "CRC mismatch in global header"; return FFV1B200_ERR_INVALIDDATA; }
-    if (c.version != 3) { err = "only FFV1 version 3 extradata is supported"; return FFV1B200_ERR_ENOSYS; }
+    if (c.version != 3 && c.version != 4) { err = "only FFV1 version 3 and 4 extradata is supported"; return FFV1B200_ERR_ENOSYS; }
     if (!c.bits) c.bits = 8;
     if (!select_pix_fmt(c)) { err = "format not supported"; return FFV1B200_ERR_ENOSYS; }
     return 0;
@@ -790,7 +797,13 @@ static void put_v01_header(BinCoder &bc, const Config &c)
     for (int i = 0; i < 5; i++) put_quant_table(bc, c.quant_tables[c.context_model][i]);
 }
 
-static void put_prefix(BinCoder &bc, const Config &c, int si, bool key, int sar_num, int sar_den, int ps)
+const int kRctCoef[kRctVariants][2] = {                   // {ry, by}: the candidates of choose_rct_params (ffv1enc.c:1066-1084)
+    {0, 0}, {1, 1}, {2, 2}, {0, 2}, {2, 0}, {4, 0}, {0, 4}, {0, 3}, {3, 0}, {3, 1}, {1, 3}, {1, 2}, {2, 1}, {0, 1}, {1, 0},
+};
+
+int rct_variants(const Config &c) { return c.version > 3 && c.colorspace == 1 ? kRctVariants : 1; }
+
+static void put_prefix(BinCoder &bc, const Config &c, int si, bool key, int sar_num, int sar_den, int ps, int variant)
 {
     if (si == 0) {
         uint8_t keystate = 128;                                                       // ffv1enc.c:1299-1307
@@ -811,22 +824,31 @@ static void put_prefix(BinCoder &bc, const Config &c, int si, bool key, int sar_
         bc.put_symbol(st, ps, false);
         bc.put_symbol(st, sar_num, false);
         bc.put_symbol(st, sar_den, false);
+        if (c.version > 3) {                                                          // ffv1enc.c:1052-1061
+            // slice_coding_mode is always 0 here (the PCM fallback needs > 12 bytes per pixel); planar
+            // YUV / gray content has no RCT and codes the neutral coefficients 1, 1
+            const int by = c.colorspace == 1 ? kRctCoef[variant][1] : 1, ry = c.colorspace == 1 ? kRctCoef[variant][0] : 1;
+            bc.put(st, 0);                                                            // "reset contexts" flag, on state[0]
+            bc.put_symbol(st, 0, false);
+            bc.put_symbol(st, by, false);
+            bc.put_symbol(st, ry, false);
+        }
     }
 }
 
-std::vector<uint16_t> slice_prefix_decisions(const Config &c, int si, bool key, int sar_num, int sar_den, int ps)
+std::vector<uint16_t> slice_prefix_decisions(const Config &c, int si, bool key, int sar_num, int sar_den, int ps, int variant)
 {
     BinCoder bc;
     bc.record_only = true;
-    put_prefix(bc, c, si, key, sar_num, sar_den, ps);
+    put_prefix(bc, c, si, key, sar_num, sar_den, ps, variant);
     return bc.decisions;
 }
 
-std::vector<uint8_t> slice_prefix_bytes(const Config &c, int si, bool key, int sar_num, int sar_den, int ps)
+std::vector<uint8_t> slice_prefix_bytes(const Config &c, int si, bool key, int sar_num, int sar_den, int ps, int variant)
 {
     // Golomb-Rice mode (ffv1enc.c:1176-1183): the range-coded part of a slice is closed before the bit stream starts
     BinCoder bc;
-    put_prefix(bc, c, si, key, sar_num, sar_den, ps);
+    put_prefix(bc, c, si, key, sar_num, sar_den, ps, variant);
     if (c.version > 2) { uint8_t s129 = 129; bc.put(&s129, 0); }
     if (c.version > 2 || si == 0) { bc.terminate(); return bc.bytes; }
     return std::vector<uint8_t>();

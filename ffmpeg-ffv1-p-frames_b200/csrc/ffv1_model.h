@@ -176,13 +176,18 @@ void coder_state_tables(const Config &c, uint8_t zero_state[256], uint8_t one_st
 
 // (probability state, bit) pairs, packed p | bit<<8, of everything a slice codes BEFORE its first sample:
 // [keyframe bit on slice 0] + slice header symbols (version 3) [+ the state-129 bit in golomb mode].
+// Version 4: the header of an RGB slice ends with the RCT coefficients chosen for it (ffv1enc.c:1052-1061), one of
+// kRctVariants pairs; `variant` selects the pair (ignored otherwise).  kRctCoef[v] = {ry, by}.
+constexpr int kRctVariants = 15;
+extern const int kRctCoef[kRctVariants][2];
+int rct_variants(const Config &c);           // header variants per (slice, keyframe flag): 15 for version-4 RGB, else 1
 std::vector<uint16_t> slice_prefix_decisions(const Config &c, int slice_index, bool key_frame,
-                                             int sar_num, int sar_den, int picture_structure);
+                                             int sar_num, int sar_den, int picture_structure, int variant = 0);
 
 // Golomb-Rice mode: the BYTES a slice starts with (range-coded key bit / header, the state-129 bit of version 3,
 // ff_rac_terminate); the MSB-first bit stream of the samples follows them (ffv1enc.c:1176-1183).
 std::vector<uint8_t> slice_prefix_bytes(const Config &c, int slice_index, bool key_frame,
-                                        int sar_num, int sar_den, int picture_structure);
+                                        int sar_num, int sar_den, int picture_structure, int variant = 0);
 
 void slice_rect(const Config &c, int i, int *x0, int *y0, int *w, int *h);
 

@@ -363,6 +363,12 @@ static void fill_tables(ffv1o_params *p)
 int ffv1o_resolve(ffv1o_params *p, int width, int height, const char *pix_fmt, int gop_size,
                   int level, int coder, int context, int slices, int slicecrc)
 {
+    return ffv1o_resolve_ex(p, width, height, pix_fmt, gop_size, level, coder, context, slices, slicecrc, 0);
+}
+
+int ffv1o_resolve_ex(ffv1o_params *p, int width, int height, const char *pix_fmt, int gop_size,
+                     int level, int coder, int context, int slices, int slicecrc, int strict_experimental)
+{
     const PixFmt *pf = NULL;
     size_t i;
     int version = 0;
@@ -383,7 +389,8 @@ int ffv1o_resolve(ffv1o_params *p, int width, int height, const char *pix_fmt, i
         version = level;
     }
     p->ec = slicecrc < 0 ? (version >= 3) : slicecrc;                      /* 699-701 */
-    if (version == 2 || version > 3) return E_INVALIDDATA;                 /* 703-706: experimental only */
+    if ((version == 2 || version > 3) && !strict_experimental) return E_INVALIDDATA;   /* 703-706: experimental only */
+    if (version == 2) return E_NOSYS;                                      /* the abandoned version-2 bitstream is not restated */
 
     /* 715-718 */
     if (coder == 1) coder = FFV1O_AC_RANGE_CUSTOM;
@@ -414,7 +421,7 @@ int ffv1o_resolve(ffv1o_params *p, int width, int height, const char *pix_fmt, i
     }
     p->ac = coder;
     p->version = version;
-    p->micro_version = version == 3 ? 4 : 0;                               /* 565-567 */
+    p->micro_version = version == 3 ? 4 : (version == 4 ? 2 : 0);          /* 565-569 */
     p->context_model = context;
     p->gop_size = gop_size;
     p->intra = gop_size < 2;                                               /* 610 */
@@ -432,6 +439,7 @@ int ffv1o_resolve(ffv1o_params *p, int width, int height, const char *pix_fmt, i
     fill_tables(p);
 
     p->plane_count = p->transparency ? 3 : 2;                              /* 720, 890-891 */
+    if (!p->chroma_planes && version > 3) p->plane_count--;                /* 892-893 */
 
     p->num_h_slices = p->num_v_slices = 1;
     if (version > 1) {                                                     /* 988-1000 */
@@ -629,6 +637,7 @@ typedef struct {
     int      alloc_ctx[3];
     int      x0, y0, w, h;  /* luma geometry */
     int      damaged;
+    int      coding_mode, rct_by, rct_ry;   /* version 4 slice header fields */
 } SliceModel;
 
 static void slice_geometry(const ffv1o_params *p, int i, int *x0, int *y0, int *w, int *h)
@@ -719,8 +728,18 @@ static int coded_bits(const ffv1o_params *p)
 /* Gather the int16 sample arrays of slice (x0,y0,w,h).  Returns the number of arrays in out[]:
  *   YUV planar: Y, [U, V], [A]      YA8: Y, A      RGB: G', B', R', [A] after the RCT.
  * pc[] receives the plane-context index each array is coded with, cw/ch its size. */
+static int gather_slice_ex(const ffv1o_params *p, const uint8_t *const planes[4], const int strides[4],
+                           int x0, int y0, int w, int h, Plane16 out[4], int pc[4], int by, int ry, int pcm);
 static int gather_slice(const ffv1o_params *p, const uint8_t *const planes[4], const int strides[4],
                         int x0, int y0, int w, int h, Plane16 out[4], int pc[4])
+{
+    return gather_slice_ex(p, planes, strides, x0, y0, w, h, out, pc, 1, 1, 0);
+}
+
+/* by, ry: RCT coefficients of the slice (1, 1 before version 4); pcm: slice_coding_mode 1 keeps b, g, r as they are
+ * (ffv1enc.c:447-453) */
+static int gather_slice_ex(const ffv1o_params *p, const uint8_t *const planes[4], const int strides[4],
+                           int x0, int y0, int w, int h, Plane16 out[4], int pc[4], int by, int ry, int pcm)
 {
     int n = 0, x, y, k;
     if (p->colorspace == 0) {
@@ -783,9 +802,11 @@ static int gather_slice(const ffv1o_params *p, const uint8_t *const planes[4], c
                     const uint8_t *q2 = planes[2] + (size_t)(y0 + y) * strides[2] + 2 * (size_t)(x0 + x);
                     b = q0[0] | (q0[1] << 8); g = q1[0] | (q1[1] << 8); r = q2[0] | (q2[1] << 8);
                 }
-                b -= g; r -= g;
-                g += (b + r) >> 2;
-                b += offset; r += offset;
+                if (!pcm) {
+                    b -= g; r -= g;
+                    g += (b * by + r * ry) >> 2;
+                    b += offset; r += offset;
+                }
                 out[0].s[(size_t)y * w + x] = (int16_t)g;
                 out[1].s[(size_t)y * w + x] = (int16_t)b;
                 out[2].s[(size_t)y * w + x] = (int16_t)r;
@@ -803,6 +824,7 @@ typedef struct {
     BitW  bw;
     int   golomb;
     int   run_index;
+    int   pcm;           /* version 4: slice_coding_mode 1 */
     uint64_t symbols;
 } SliceCoder;
 
@@ -850,6 +872,13 @@ static void encode_line(const ffv1o_params *p, SliceCoder *sc, SliceModel *m, in
                         const Plane16 *P, int y, int bits)
 {
     int x, run_count = 0, run_mode = 0;
+    if (sc->pcm) {                                     /* ffv1enc.c:294-304: `bits` raw bits, each on a fresh state 128 */
+        for (x = 0; x < P->w; x++) {
+            int i, v = sample_at(P, x, y);
+            for (i = bits - 1; i >= 0; i--) { uint8_t st = 128; rce_put(&sc->rc, &st, (v >> i) & 1); }
+        }
+        return;
+    }
     for (x = 0; x < P->w; x++) {
         int ctx = context_at(q, P, x, y);
         int diff = sample_at(P, x, y) - predict_at(P, x, y);
@@ -912,6 +941,8 @@ ffv1o_encoder *ffv1o_encoder_new(const ffv1o_params *p)
         slice_geometry(p, i, &e->sm[i].x0, &e->sm[i].y0, &e->sm[i].w, &e->sm[i].h);
     return e;
 }
+void ffv1o_encoder_set_force_pcm(ffv1o_encoder *e, int on) { e->p.force_pcm = on; }
+
 void ffv1o_encoder_free(ffv1o_encoder *e)
 {
     int i;
@@ -953,6 +984,50 @@ static void write_v01_header(const ffv1o_params *p, RcEnc *c)
     for (i = 0; i < 5; i++) put_quant_table(c, p->quant_tables[p->context_model][i]);
 }
 
+/* choose_rct_params (ffv1enc.c:1064-1144): the candidate whose luma-like channel has the smallest sum of absolute
+ * second-order differences over the slice; {ry, by} per candidate, first minimum wins, int accumulators */
+static const int rct_candidates[15][2] = {
+    {0, 0}, {1, 1}, {2, 2}, {0, 2}, {2, 0}, {4, 0}, {0, 4}, {0, 3}, {3, 0}, {3, 1}, {1, 3}, {1, 2}, {2, 1}, {0, 1}, {1, 0},
+};
+
+static void rct_search(const ffv1o_params *p, const uint8_t *const planes[4], const int strides[4],
+                       int x0, int y0, int w, int h, int *by, int *ry)
+{
+    unsigned stat[15] = { 0 };
+    int16_t *prev = calloc((size_t)w * 3 + 3, sizeof(int16_t));
+    int x, y, i, best = 0;
+    for (y = 0; y < h; y++) {
+        int last[3] = { 0, 0, 0 };
+        for (x = 0; x < w; x++) {
+            int v[3], d[3];                            /* g, b, r under the reference's plane naming */
+            if (p->layout == FFV1O_LAYOUT_RGB32) {
+                const uint8_t *q = planes[0] + (size_t)(y0 + y) * strides[0] + 4 * (size_t)(x0 + x);
+                v[1] = q[0]; v[0] = q[1]; v[2] = q[2];
+            } else {
+                const uint8_t *q0 = planes[0] + (size_t)(y0 + y) * strides[0] + 2 * (size_t)(x0 + x);
+                const uint8_t *q1 = planes[1] + (size_t)(y0 + y) * strides[1] + 2 * (size_t)(x0 + x);
+                const uint8_t *q2 = planes[2] + (size_t)(y0 + y) * strides[2] + 2 * (size_t)(x0 + x);
+                v[1] = q0[0] | (q0[1] << 8); v[0] = q1[0] | (q1[1] << 8); v[2] = q2[0] | (q2[1] << 8);
+            }
+            for (i = 0; i < 3; i++) d[i] = v[i] - last[i];
+            if (x && y) {
+                int bg = d[0] - prev[x * 3], bb = d[1] - prev[x * 3 + 1], br = d[2] - prev[x * 3 + 2];
+                br -= bg; bb -= bg;
+                for (i = 0; i < 15; i++) {
+                    int t = bg + ((br * rct_candidates[i][0] + bb * rct_candidates[i][1]) >> 2);
+                    stat[i] += (unsigned)(t < 0 ? -t : t);
+                }
+            }
+            for (i = 0; i < 3; i++) { prev[x * 3 + i] = (int16_t)d[i]; last[i] = v[i]; }
+        }
+    }
+    for (i = 1; i < 15; i++)
+        if ((int)stat[i] < (int)stat[best]) best = i;
+    free(prev);
+    *by = rct_candidates[best][1];
+    *ry = rct_candidates[best][0];
+}
+
 static void write_slice_header(const ffv1o_params *p, RcEnc *c, const SliceModel *m,
                                int sar_num, int sar_den, int picture_structure)
 {
@@ -968,6 +1043,14 @@ static void write_slice_header(const ffv1o_params *p, RcEnc *c, const SliceModel
     rce_symbol(c, st, picture_structure, 0);
     rce_symbol(c, st, sar_num, 0);
     rce_symbol(c, st, sar_den, 0);
+    if (p->version > 3) {                              /* ffv1enc.c:1052-1061 */
+        rce_put(c, st, m->coding_mode == 1);           /* "reset contexts", on state[0] */
+        rce_symbol(c, st, m->coding_mode, 0);
+        if (m->coding_mode != 1) {
+            rce_symbol(c, st, m->rct_by, 0);
+            rce_symbol(c, st, m->rct_ry, 0);
+        }
+    }
 }
 
 long ffv1o_encode_frame(ffv1o_encoder *e, const uint8_t *const planes[4], const int strides[4],
@@ -1008,6 +1091,16 @@ long ffv1o_encode_frame(ffv1o_encoder *e, const uint8_t *const planes[4], const 
             if ((r = model_alloc(m, k, nctx, golomb)) < 0) { free(sbuf); return r; }
             if (key) model_reset(m, k, nctx, golomb);                              /* 1171-1172 */
         }
+        /* version 4 (1162-1168): RGB slices search their RCT coefficients.  (The reference runs the same search over
+         * planar YUV / gray frames, reading their first plane as packed RGB and beyond its rows -- values no decoder
+         * uses and no other encoder can reproduce; the neutral pair 1, 1 is coded for those.) */
+        m->coding_mode = (p->version > 3 && p->force_pcm && !golomb) ? 1 : 0;
+        m->rct_by = m->rct_ry = 1;
+        if (p->version > 3 && p->colorspace == 1) rct_search(p, planes, strides, m->x0, m->y0, m->w, m->h, &m->rct_by, &m->rct_ry);
+        sc.pcm = m->coding_mode == 1;
+        if (sc.pcm)                                                                /* 1054-1055: a PCM slice clears its state */
+            for (k = 0; k < 3; k++)
+                if (m->alloc_ctx[k]) model_reset(m, k, nctx, golomb);
         if (p->version > 2) write_slice_header(p, &sc.rc, m, sar_num, sar_den, picture_structure);
         if (golomb) {                                                              /* 1176-1183 */
             if (p->version > 2) { uint8_t s129 = 129; rce_put(&sc.rc, &s129, 0); }
@@ -1015,7 +1108,7 @@ long ffv1o_encode_frame(ffv1o_encoder *e, const uint8_t *const planes[4], const 
             sc.bw.buf = sbuf + ac_bytes; sc.bw.cap = scap - ac_bytes; sc.bw.bitpos = 0;
         }
 
-        npl = gather_slice(p, planes, strides, m->x0, m->y0, m->w, m->h, pl, pc);
+        npl = gather_slice_ex(p, planes, strides, m->x0, m->y0, m->w, m->h, pl, pc, m->rct_by, m->rct_ry, sc.pcm);
         if (npl < 0) { free(sbuf); return npl; }
         if (p->colorspace == 0) {
             for (k = 0; k < npl; k++) {                                            /* 1185-1201 */
@@ -1026,8 +1119,8 @@ long ffv1o_encode_frame(ffv1o_encoder *e, const uint8_t *const planes[4], const 
         } else {
             sc.run_index = 0;                                                      /* 423 */
             for (y = 0; y < m->h; y++)
-                for (k = 0; k < npl; k++)                                          /* 459-469 */
-                    encode_line(p, &sc, m, pc[k], p->quant_tables[p->context_model], &pl[k], y, bits);
+                for (k = 0; k < npl; k++)                                          /* 459-469: PCM slices code the raw depth */
+                    encode_line(p, &sc, m, pc[k], p->quant_tables[p->context_model], &pl[k], y, bits - sc.pcm);
         }
         for (k = 0; k < npl; k++) free(pl[k].s);
 
@@ -1154,6 +1247,7 @@ typedef struct {
     BitR  br;
     int   golomb;
     int   run_index;
+    int   pcm;           /* version 4: slice_coding_mode 1 */
 } SliceReader;
 
 static void decode_line(SliceReader *sr, SliceModel *m, int pcidx, const int16_t q[5][256],
@@ -1161,6 +1255,14 @@ static void decode_line(SliceReader *sr, SliceModel *m, int pcidx, const int16_t
 {
     /* ffv1dec.c:100-181 */
     int x, run_count = 0, run_mode = 0;
+    if (sr->pcm) {                                     /* 111-122 */
+        for (x = 0; x < P->w; x++) {
+            int i, v = 0;
+            for (i = 0; i < bits; i++) { uint8_t st = 128; v += v + rcd_get(&sr->rc, &st); }
+            P->s[(size_t)y * P->w + x] = (int16_t)v;
+        }
+        return;
+    }
     for (x = 0; x < P->w; x++) {
         int ctx = context_at(q, P, x, y), sign = 0, diff;
         if (ctx < 0) { ctx = -ctx; sign = 1; }
@@ -1196,7 +1298,7 @@ static void decode_line(SliceReader *sr, SliceModel *m, int pcidx, const int16_t
 }
 
 static void scatter_slice(const ffv1o_params *p, uint8_t *const planes[4], const int strides[4],
-                          int x0, int y0, int w, int h, Plane16 pl[4], int npl)
+                          int x0, int y0, int w, int h, Plane16 pl[4], int npl, int by, int ry, int pcm)
 {
     int x, y, k;
     if (p->colorspace == 0) {
@@ -1227,9 +1329,11 @@ static void scatter_slice(const ffv1o_params *p, uint8_t *const planes[4], const
             for (x = 0; x < w; x++) {
                 int g = pl[0].s[(size_t)y * w + x], b = pl[1].s[(size_t)y * w + x], r = pl[2].s[(size_t)y * w + x];
                 int a = npl == 4 ? pl[3].s[(size_t)y * w + x] : 0;
-                b -= offset; r -= offset;
-                g -= (b + r) >> 2;
-                b += g; r += g;
+                if (!pcm) {                                                              /* ffv1dec.c:263-269 */
+                    b -= offset; r -= offset;
+                    g -= (b * by + r * ry) >> 2;
+                    b += g; r += g;
+                }
                 if (p->layout == FFV1O_LAYOUT_RGB32) {
                     uint8_t *q = planes[0] + (size_t)(y0 + y) * strides[0] + 4 * (size_t)(x0 + x);
                     unsigned v = (unsigned)b + ((unsigned)g << 8) + ((unsigned)r << 16) + ((unsigned)a << 24);
@@ -1335,7 +1439,7 @@ int ffv1o_decode_frame(ffv1o_decoder *d, const uint8_t *pkt, long size,
         SliceModel *m = &d->sm[si];
         SliceReader sr;
         Plane16 pl[4];
-        int pc[4], npl = 0, k, y, bits, nctx, qti[3] = { 0, 0, 0 }, golomb;
+        int pc[4], npl = 0, k, y, bits, nctx, qti[3] = { 0, 0, 0 }, golomb, reset_contexts = 0;
         const uint8_t *sbeg = pkt + starts[si];
         memset(&sr, 0, sizeof(sr));
         if (si == 0) { sr.rc = c0; sr.rc.end = pkt + ends[0]; }                      /* 984-987 */
@@ -1367,7 +1471,18 @@ int ffv1o_decode_frame(ffv1o_decoder *d, const uint8_t *pkt, long size,
             ps = rcd_symbol(&sr.rc, st, 0, &err); (void)ps;
             rcd_symbol(&sr.rc, st, 0, &err);     /* SAR num */
             rcd_symbol(&sr.rc, st, 0, &err);     /* SAR den */
+            m->coding_mode = 0; m->rct_by = m->rct_ry = 1; reset_contexts = 0;
+            if (p->version > 3) {                /* ffv1dec.c:345-356 */
+                reset_contexts = rcd_get(&sr.rc, st);
+                m->coding_mode = rcd_symbol(&sr.rc, st, 0, &err);
+                if (m->coding_mode != 1) {
+                    m->rct_by = rcd_symbol(&sr.rc, st, 0, &err);
+                    m->rct_ry = rcd_symbol(&sr.rc, st, 0, &err);
+                    if ((uint64_t)(unsigned)m->rct_by + (uint64_t)(unsigned)m->rct_ry > 4) { m->damaged = 1; continue; }
+                }
+            }
         } else {
+            m->coding_mode = 0; m->rct_by = m->rct_ry = 1; reset_contexts = 0;
             slice_geometry(p, si, &m->x0, &m->y0, &m->w, &m->h);
         }
         golomb = sr.golomb = (p->ac == FFV1O_AC_GOLOMB);
@@ -1378,7 +1493,7 @@ int ffv1o_decode_frame(ffv1o_decoder *d, const uint8_t *pkt, long size,
             if (!used) continue;
             nctx = p->context_count[qti[k < p->plane_count ? k : 0]];
             if ((r = model_alloc(m, k, nctx, golomb)) < 0) return r;
-            if (key) model_reset(m, k, nctx, golomb);                                /* 419-420 */
+            if (key || reset_contexts) model_reset(m, k, nctx, golomb);              /* 419-420 */
         }
         if (golomb) {                                                                /* 427-434 */
             long acb;
@@ -1415,6 +1530,7 @@ int ffv1o_decode_frame(ffv1o_decoder *d, const uint8_t *pkt, long size,
                 if (!pl[k].s) return E_NOMEM;
             }
         }
+        sr.pcm = m->coding_mode == 1;
         if (p->colorspace == 0) {
             for (k = 0; k < npl; k++) {
                 sr.run_index = 0;
@@ -1425,7 +1541,7 @@ int ffv1o_decode_frame(ffv1o_decoder *d, const uint8_t *pkt, long size,
             sr.run_index = 0;
             for (y = 0; y < m->h; y++)
                 for (k = 0; k < npl; k++)
-                    decode_line(&sr, m, pc[k], p->quant_tables[qti[pc[k] < p->plane_count ? pc[k] : 0]], &pl[k], y, bits, &err);
+                    decode_line(&sr, m, pc[k], p->quant_tables[qti[pc[k] < p->plane_count ? pc[k] : 0]], &pl[k], y, bits - sr.pcm, &err);
         }
         if (!golomb && p->version > 2) {                                             /* 459-467 */
             uint8_t s129 = 129;
@@ -1434,7 +1550,7 @@ int ffv1o_decode_frame(ffv1o_decoder *d, const uint8_t *pkt, long size,
             v = sr.rc.end - sr.rc.ptr - 2 - 5 * p->ec;
             if (v) m->damaged = 1;
         }
-        scatter_slice(p, planes, strides, m->x0, m->y0, m->w, m->h, pl, npl);
+        scatter_slice(p, planes, strides, m->x0, m->y0, m->w, m->h, pl, npl, m->rct_by, m->rct_ry, sr.pcm);
         for (k = 0; k < npl; k++) free(pl[k].s);
     }
     if (damaged_mask)

@@ -51,12 +51,20 @@ typedef struct ffv1o_params {
     uint8_t state_transition[256];
     int16_t quant_tables[2][5][256];
     int context_count[2];
+    /* version 4 (micro version 2, needs strict_experimental): per-slice RCT coefficients, slice coding mode, reset flag.
+     * force_pcm is a TEST KNOB: every slice is coded in slice_coding_mode 1 ("PCM", ffv1enc.c:294-304, 1207-1217), which
+     * the reference only does when a slice outgrows its buffer -- used to give the decoders PCM streams. */
+    int force_pcm;
 } ffv1o_params;
 
 /* Option resolution = encode_init (ffv1enc.c:669-1029).  Returns 0, or a negative code:
  * -22 EINVAL, -38 ENOSYS (unsupported format / slice count), -1094995529 INVALIDDATA. */
 int ffv1o_resolve(ffv1o_params *p, int width, int height, const char *pix_fmt, int gop_size,
                   int level, int coder, int context, int slices, int slicecrc);
+
+/* same, with AVCodecContext.strict_std_compliance <= FF_COMPLIANCE_EXPERIMENTAL: unlocks level 4 (ffv1enc.c:703-706) */
+int ffv1o_resolve_ex(ffv1o_params *p, int width, int height, const char *pix_fmt, int gop_size,
+                     int level, int coder, int context, int slices, int slicecrc, int strict_experimental);
 
 int ffv1o_write_extradata(const ffv1o_params *p, uint8_t *dst, int cap);                 /* ffv1enc.c:545-619 */
 int ffv1o_parse_extradata(ffv1o_params *p, int width, int height, const uint8_t *d, int n); /* ffv1dec.c:521-636 */
@@ -69,6 +77,8 @@ long ffv1o_encode_frame(ffv1o_encoder *e, const uint8_t *const planes[4], const 
                         uint8_t *dst, long cap, int *key_frame);
 /* total binary range-coder decisions (or golomb symbols) coded so far -- used for reporting */
 uint64_t ffv1o_encoder_decisions(const ffv1o_encoder *e);
+/* test knob (see ffv1o_params.force_pcm), switchable between frames */
+void ffv1o_encoder_set_force_pcm(ffv1o_encoder *e, int on);
 void ffv1o_encoder_free(ffv1o_encoder *e);
 
 typedef struct ffv1o_decoder ffv1o_decoder;

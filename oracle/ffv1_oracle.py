@@ -13,7 +13,7 @@ class Params(ctypes.Structure):
         "ec", "intra", "gop_size", "num_h_slices", "num_v_slices", "plane_count")] + [
         ("state_transition", ctypes.c_uint8 * 256),
         ("quant_tables", ctypes.c_int16 * (2 * 5 * 256)),
-        ("context_count", ctypes.c_int * 2)]
+        ("context_count", ctypes.c_int * 2), ("force_pcm", ctypes.c_int)]
 
 def build():
     subprocess.check_call(["make", "-s", "-C", _HERE, "oracle"])
@@ -26,6 +26,7 @@ def lib():
             build()
         L = ctypes.CDLL(path)
         L.ffv1o_resolve.argtypes = [ctypes.POINTER(Params), ctypes.c_int, ctypes.c_int, ctypes.c_char_p] + [ctypes.c_int] * 6
+        L.ffv1o_resolve_ex.argtypes = [ctypes.POINTER(Params), ctypes.c_int, ctypes.c_int, ctypes.c_char_p] + [ctypes.c_int] * 7
         L.ffv1o_write_extradata.argtypes = [ctypes.POINTER(Params), ctypes.c_void_p, ctypes.c_int]
         L.ffv1o_parse_extradata.argtypes = [ctypes.POINTER(Params), ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
         L.ffv1o_encoder_new.restype = ctypes.c_void_p
@@ -67,11 +68,13 @@ def _plane_args(planes):
     strides = (ctypes.c_int * 4)(*([pl.strides[0] for pl in planes] + [0] * (4 - len(planes))))
     return ptrs, strides
 
-def resolve(w, h, pix_fmt, gop=12, level=-1, coder=0, context=0, slices=0, slicecrc=-1):
+def resolve(w, h, pix_fmt, gop=12, level=-1, coder=0, context=0, slices=0, slicecrc=-1, strict_experimental=0, force_pcm=0):
+    """strict_experimental unlocks level 4; force_pcm (test knob) codes every version-4 slice in slice_coding_mode 1"""
     p = Params()
-    r = lib().ffv1o_resolve(ctypes.byref(p), w, h, pix_fmt.encode(), gop, level, coder, context, slices, slicecrc)
+    r = lib().ffv1o_resolve_ex(ctypes.byref(p), w, h, pix_fmt.encode(), gop, level, coder, context, slices, slicecrc, strict_experimental)
     if r < 0:
         raise ValueError("ffv1o_resolve failed: %d" % r)
+    p.force_pcm = force_pcm
     return p
 
 def extradata(p):
@@ -100,6 +103,10 @@ class Encoder:
         if n < 0:
             raise RuntimeError("oracle encode failed %d" % n)
         return self.buf.raw[:n], bool(key.value)
+    def set_force_pcm(self, on):
+        """test knob: the following frames' slices are coded in slice_coding_mode 1 (version 4)"""
+        lib().ffv1o_encoder_set_force_pcm.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        lib().ffv1o_encoder_set_force_pcm(self.h_, int(on))
     @property
     def decisions(self):
         return lib().ffv1o_encoder_decisions(self.h_)
