@@ -371,7 +371,7 @@ std::string format_stats(const Config &c, const PassStats &st)
         snprintf(tmp, sizeof(tmp), "%" PRIu64 " %" PRIu64 " ", st.rc_stat[j][0], st.rc_stat[j][1]);
         out += tmp;
     }
-    out += "\n";
+    // (the reference writes a newline here and overwrites it with the next number: its pointer is not advanced, ffv1enc.c:1266)
     for (int i = 0; i < 2; i++)
         for (int j = 0; j < c.context_count[i]; j++)
             for (int m = 0; m < 32; m++) {

