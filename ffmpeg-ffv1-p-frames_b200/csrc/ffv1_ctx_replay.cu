@@ -446,6 +446,163 @@ __global__ void __launch_bounds__(kScatterSmThreads) k_ctx_scatter_sm(const EncD
     }
 }
 
+// ------------------------------------------------------------------------------------------------ k_tile_sort
+// Tile-sorted lists (Layout::tiled_lists).  The chain-wide lists above need the position of every tile inside every
+// list before a single entry can be placed: a histogram pass over all records and a scan along every chain.  Here a
+// context's list stays cut into one run per tile: the tile is sorted by context in shared memory (as k_ctx_scatter_sm
+// does) and leaves as ONE contiguous block at a place that only depends on the geometry, together with a table of where
+// each context's run starts inside the block.  Decision positions are relative to the tile; k_tile_layout turns the
+// tiles' decision counts into their places in the decision region.  k_replay_grp<TILED> walks a chain tile after tile.
+// No histogram kernel, no scan kernel, no per-tile base tables to read back, and the block leaves with full-width
+// coalesced stores (the per-context runs of the chain-wide lists average a dozen entries per store).
+constexpr int kTileSortThreads = 32 * (kTiledLines / 2);  // two lines of the tile per warp
+constexpr int kTileSortRows = kTileSortThreads / 64;      // per-warp context counts: two warps share a word
+
+__global__ void __launch_bounds__(kTileSortThreads) k_tile_sort(const EncDeviceTables T, const EncBatch B)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ uint32_t s_wtot[kTileSortThreads / 32];
+    __shared__ uint32_t s_wnd[kTileSortThreads / 32];                    // decisions of every warp's lines, then their first position
+    const Layout &L = T.layout;
+    const int nctx = L.ctx_count, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t *s_wh = reinterpret_cast<uint32_t *>(smem_raw);             // [rows][nctx] per-warp counts, two warps per word
+    uint16_t *s_start = reinterpret_cast<uint16_t *>(s_wh + kTileSortRows * nctx);   // [pitch] start of every context's run; [nctx] = entries
+    uint32_t *s_ent = reinterpret_cast<uint32_t *>(s_start + B.tile_tab_pitch);
+    const int tile = blockIdx.x, f = blockIdx.y;
+    const CtxTile ct = T.ctiles[tile];
+    const SliceGeom &g = T.slices[ct.slice];
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    for (int i = tid; i < kTileSortRows * nctx; i += kTileSortThreads) s_wh[i] = 0u;
+    __syncthreads();
+    const uint32_t *rec_slice = B.rec + (size_t)f * L.rec_per_frame + g.rec_first;
+    const int32_t *my_lines = T.pc_lines + g.pc_line_first[ct.pc] + ct.first;
+    // ---- pass 1: context counts and decisions of the warp's lines
+    const uint32_t *recp[2] = {nullptr, nullptr};
+    int w[2] = {0, 0};
+    uint32_t *wh = s_wh + (warp >> 1) * nctx;
+    const int sh = (warp & 1) * 16;
+    {
+        uint32_t nd = 0;
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const int li = 2 * warp + k;
+            if (li < ct.nlines) {
+                const LineDesc ld = T.lines[g.line_first + my_lines[li]];
+                recp[k] = rec_slice + ld.rec_off;
+                w[k] = ld.w;
+                for (int x = lane; x < w[k]; x += 32) {
+                    const uint32_t r = recp[k][x];
+                    nd += decisions_of((int)(int16_t)(r & 0xFFFFu));
+                    atomicAdd(&wh[r >> 16], 1u << sh);
+                }
+            }
+        }
+        nd = __reduce_add_sync(0xFFFFFFFFu, nd);
+        if (lane == 0) s_wnd[warp] = nd;
+    }
+    __syncthreads();
+    // ---- per context (two per thread): counts of the warps -> exclusive offsets in place; block scan of the totals
+    uint32_t cc[2] = {0u, 0u};
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+        const int c = 2 * tid + j;
+        if (c < nctx) {
+            uint32_t run = 0;
+#pragma unroll
+            for (int h = 0; h < kTileSortRows; h++) {
+                const uint32_t v = s_wh[h * nctx + c];
+                const uint32_t lo = v & 0xFFFFu, hi = v >> 16;
+                s_wh[h * nctx + c] = run | ((run + lo) << 16);
+                run += lo + hi;
+            }
+            cc[j] = run;
+        }
+    }
+    const uint32_t pair = cc[0] + cc[1];
+    const uint32_t incl = cr_incl_scan(pair, lane);
+    if (lane == 31) s_wtot[warp] = incl;
+    __syncthreads();
+    {
+        uint32_t base = incl - pair;
+        for (int ww = 0; ww < warp; ww++) base += s_wtot[ww];
+        if (2 * tid < nctx) s_start[2 * tid] = (uint16_t)base;
+        if (2 * tid + 1 < nctx) s_start[2 * tid + 1] = (uint16_t)(base + cc[0]);
+        if (2 * tid == nctx || 2 * tid + 1 == nctx) s_start[nctx] = (uint16_t)(base + (2 * tid == nctx ? 0u : cc[0]));
+        if (tid == 0) {                                                   // first decision of every warp's lines; the tile's total
+            uint32_t run = 0;
+            for (int ww = 0; ww < kTileSortThreads / 32; ww++) { const uint32_t v = s_wnd[ww]; s_wnd[ww] = run; run += v; }
+            B.tile_nd[(size_t)f * L.ctiles_per_frame + tile] = run;
+        }
+    }
+    __syncthreads();
+    // ---- pass 2: stable placement, entry = position of the symbol's first decision inside the tile | residual << 22
+    {
+        uint32_t pos = s_wnd[warp];
+#pragma unroll
+        for (int k = 0; k < 2; k++)
+            for (int x0 = 0; x0 < w[k]; x0 += 32) {
+                const bool act = x0 + lane < w[k];
+                const uint32_t r = act ? recp[k][x0 + lane] : 0u;
+                const uint32_t ctx = r >> 16;
+                const uint32_t nd = act ? decisions_of((int)(int16_t)(r & 0xFFFFu)) : 0u;
+                const uint32_t in = cr_incl_scan(nd, lane);
+                const uint32_t grp = __match_any_sync(0xFFFFFFFFu, act ? ctx : 0xFFFFFFFFu);
+                const uint32_t rank = __popc(grp & lt_mask);
+                uint32_t off = 0u;
+                if (act && rank == 0u) off = (atomicAdd(&wh[ctx], (uint32_t)__popc(grp) << sh) >> sh) & 0xFFFFu;
+                off = __shfl_sync(0xFFFFFFFFu, off, (__ffs(grp) - 1) & 31);
+                if (act) s_ent[(uint32_t)s_start[ctx] + off + rank] = (pos + in - nd) | (r << kGrpPosBits);
+                pos += __shfl_sync(0xFFFFFFFFu, in, 31);
+            }
+    }
+    __syncthreads();
+    // ---- the block and its table leave with coalesced stores
+    const int seg = B.frame_seg[f];
+    const int f0 = B.seg_first[seg], seglen = B.seg_first[seg + 1] - f0;
+    uint32_t *dst = reinterpret_cast<uint32_t *>(B.lists) + (size_t)f0 * L.samples_per_frame + (size_t)seglen * g.list_off[ct.pc] +
+                    (size_t)(f - f0) * g.pc_samples[ct.pc] + ct.sample_first;
+    for (uint32_t i = tid; i < ct.nsamples; i += kTileSortThreads) dst[i] = s_ent[i];
+    uint16_t *tab = B.tile_tab + ((size_t)f * L.ctiles_per_frame + tile) * B.tile_tab_pitch;
+    for (int i = tid; i <= nctx; i += kTileSortThreads) tab[i] = s_start[i];
+}
+
+// ------------------------------------------------------------------------------------------------ k_tile_layout
+// per (frame, slice, plane context): the tiles' decision counts -> their first decision inside the region (one run per
+// plane context on this path), the run's length for k_rangecode, overflow detection, the batch's decision count
+__global__ void __launch_bounds__(128) k_tile_layout(const EncDeviceTables T, const EncBatch B)
+{
+    const Layout &L = T.layout;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long ndec = 0;
+    if (idx < B.nframes * L.nslices * L.npc) {
+        const int pc = idx % L.npc, s = (idx / L.npc) % L.nslices, f = idx / (L.npc * L.nslices);
+        const SliceGeom &g = T.slices[s];
+        const int nt = g.ct_count[pc];
+        if (nt) {
+            uint32_t *nd = B.tile_nd + (size_t)f * L.ctiles_per_frame + g.ct_first[pc];
+            uint32_t pos = 0;
+            for (int tb = 0; tb < nt; tb += 8) {
+                uint32_t v[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) v[k] = tb + k < nt ? nd[tb + k] : 0u;
+#pragma unroll
+                for (int k = 0; k < 8; k++)
+                    if (tb + k < nt) { nd[tb + k] = pos; pos += v[k]; }
+            }
+            const uint32_t run = T.lines[g.line_first + T.pc_lines[g.pc_line_first[pc]]].run;
+            B.run_cnt[(size_t)f * L.runs_per_frame + g.run_first + run] = pos;
+            ndec = pos;
+            if (pos + 8u > g.dec_cap[pc]) {
+                const unsigned long long ns = g.pc_samples[pc];
+                atomicMax(&B.status[0], ((unsigned long long)(pos + 8u) * 256ull + ns - 1) / ns + 1ull);
+            }
+        }
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) ndec += __shfl_xor_sync(0xFFFFFFFFu, ndec, d);
+    if ((threadIdx.x & 31) == 0 && ndec) atomicAdd(&B.status[3], ndec);
+}
+
 // ------------------------------------------------------------------------------------------------ k_replay_ctx
 // Lane <-> state slot permutation.  put_symbol_inline visits the slots of a symbol in the order
 //   0 | 1..e+1 | 22+e-1 .. 22 | 11+e                                  (ffv1enc.c:202-229, e <= 9)
@@ -685,9 +842,12 @@ __device__ __noinline__ void replay_symbol_serial(uint8_t *row, const uint8_t *l
     }
 }
 
-template <int EMAX, int THREADS>
-__global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_replay_grp(const EncDeviceTables T, const EncBatch B, const int window)
+// TILED: the lists are kept tile by tile (k_tile_sort): a window is one tile, the window's part of a list is the
+// context's run inside the tile's block, and the entries' positions count from the tile's first decision.
+template <int EMAX, int THREADS, bool TILED>
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_replay_grp(const EncDeviceTables T, const EncBatch B, const int window_rt)
 {
+    const int window = TILED ? 1 : window_rt;
     constexpr int G = 16;
     static_assert(3 * EMAX + 3 <= G, "roles must fit a group");
     extern __shared__ __align__(16) unsigned char s_state_raw[];     // [ctx_count][32] the chain's model
@@ -718,6 +878,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_replay_grp(const En
     uint32_t *s_b0 = s_lstart + nctx, *s_b1 = s_b0 + nctx;                                // [nctx] the window's part of every list
     uint16_t *s_order = reinterpret_cast<uint16_t *>(s_b1 + nctx);                          // [nctx] contexts, longest list first
     __shared__ int s_nlists;
+    __shared__ int s_nl[2];                                          // TILED: lists queued in the current / the next window
     const bool key = B.frame_key[f0] != 0;
     const bool hand_over = f1 == B.nframes;
     const size_t coff = ((size_t)s * L.npc + pc) * ((size_t)nctx * 32);
@@ -732,8 +893,32 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_replay_grp(const En
     const uint32_t *lcount = B.list_count + (size_t)chain * nctx;
     const uint16_t *order = B.list_order + (size_t)chain * nctx;
     uint16_t *dec_pc = B.dec + sg.dec_off[pc];
-    if (tid == 0) s_nlists = 0;
+    const int t0 = sg.ct_first[pc];
+    const int nt = sg.ct_count[pc];
+    if (tid == 0) { s_nlists = 0; s_nl[0] = 0; s_nl[1] = 0; }
     __syncthreads();
+    if (TILED) {
+        // processing order: by how often the contexts occur in the chain's first frame (what matters is that the long
+        // lists of a window start first; contexts that frame does not use come last)
+        for (int i = tid; i < nctx; i += THREADS) {
+            uint32_t n = 0;
+            for (int tt = 0; tt < nt; tt++) {                        // the tiles of the chain's first frame
+                const uint16_t *tab = B.tile_tab + ((size_t)f0 * L.ctiles_per_frame + t0 + tt) * B.tile_tab_pitch;
+                n += (uint32_t)tab[i + 1] - (uint32_t)tab[i];
+            }
+            s_b0[i] = n;
+        }
+        __syncthreads();
+        for (int c = tid; c < nctx; c += THREADS) {
+            const uint32_t mine = s_b0[c];
+            int rank = 0;
+            for (int o = 0; o < nctx; o++) {
+                const uint32_t v = s_b0[o];
+                rank += (v > mine) || (v == mine && o < c);
+            }
+            s_order[rank] = (uint16_t)c;
+        }
+    } else
     for (int i = tid; i < nctx; i += THREADS) {
         s_lstart[i] = lstart[i];
         const uint16_t c = order[i];
@@ -745,20 +930,51 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_replay_grp(const En
     const bool has_slot = slot >= 0;
     const uint32_t lanebit = 1u << g, lt_mask = lanebit - 1u;
     const int rot = (g - 8) & 31;                                    // rotr(bits, rot) puts my bit at bit 8
-    const int t0 = sg.ct_first[pc];
 
     // Window after window (`window` context tiles of a frame): all warps of the CTA work on the same stretch of the
     // (frame, slice, plane context) decision region, which is then completed while it is still in L2 (with whole frames
     // per round, 296 resident CTAs x 0.8 MB of half-written sectors thrashed the 126 MB L2: 3x DRAM traffic).  Measured
     // optimum on B200: 256-thread CTAs (4 per SM) x 3 tiles; the time follows (resident CTAs x window), i.e. the L2 footprint.
-    const int nt = sg.ct_count[pc];
+    int wi = 0;                                                      // windows done
     for (int f = f0; f < f1; f++)
-    for (int tw = 0; tw < nt; tw += window) {
+    for (int tw = 0; tw < nt; tw += window, wi++) {
         uint16_t *dec_f = dec_pc + (size_t)f * L.dec_per_frame;
+        const uint32_t *blk = chain_list;                            // TILED: the tile's block of entries
         __syncthreads();                                             // model loaded / previous window finished
         if (tid == 0) s_next = 0;
         const bool last_win = tw + window >= nt;
-        {
+        if (TILED) {
+            // the window's part of every list, indexed by the list's place in the processing order; the queue ends behind
+            // the last context that occurs in the tile (the tail of the order is contexts the content hardly ever uses)
+            const size_t ti = (size_t)f * L.ctiles_per_frame + t0 + tw;
+            const uint16_t *tab = B.tile_tab + ti * B.tile_tab_pitch;
+            if (tid == 0) s_nl[(wi + 1) & 1] = 0;
+            int last = 0;
+            for (int i = tid; i < nctx; i += THREADS) {
+                const int c = s_order[i];
+                const uint32_t a = tab[c], b = tab[c + 1];
+                s_b0[i] = a; s_b1[i] = b;
+                if (b > a) last = i + 1;
+            }
+            last = __reduce_max_sync(0xFFFFFFFFu, last);
+            if (lane == 0 && last) atomicMax(&s_nl[wi & 1], last);
+            // the next window's table and entries are on their way into L2 while this one is replayed
+            {
+                int nf = f, ntw = tw + 1;
+                if (ntw >= nt) { ntw = 0; nf = f + 1; }
+                if (nf < f1) {
+                    const size_t nti = (size_t)nf * L.ctiles_per_frame + t0 + ntw;
+                    const char *ntab = reinterpret_cast<const char *>(B.tile_tab + nti * B.tile_tab_pitch);
+                    const CtxTile nct = T.ctiles[t0 + ntw];
+                    const char *nblk = reinterpret_cast<const char *>(chain_list + (size_t)(nf - f0) * sg.pc_samples[pc] + nct.sample_first);
+                    if (tid * 128 < B.tile_tab_pitch * 2) asm volatile("prefetch.global.L2 [%0];" :: "l"(ntab + tid * 128));
+                    for (uint32_t o = tid * 128u; o < nct.nsamples * 4u; o += THREADS * 128u) asm volatile("prefetch.global.L2 [%0];" :: "l"(nblk + o));
+                    if (tid == THREADS - 1) asm volatile("prefetch.global.L2 [%0];" :: "l"(B.tile_nd + nti));
+                }
+            }
+            blk = chain_list + (size_t)(f - f0) * sg.pc_samples[pc] + T.ctiles[t0 + tw].sample_first;
+            dec_f += B.tile_nd[ti];
+        } else {
             const uint32_t *bf = B.ctx_hist + ((size_t)f * L.ctiles_per_frame + t0 + tw) * nctx;
             const uint32_t *bn = last_win ? B.ctx_hist + ((size_t)(f + 1) * L.ctiles_per_frame + t0) * nctx
                                           : B.ctx_hist + ((size_t)f * L.ctiles_per_frame + t0 + tw + window) * nctx;
@@ -766,6 +982,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_replay_grp(const En
             for (int i = tid; i < nctx; i += THREADS) { s_b0[i] = bf[i]; s_b1[i] = use_bn ? bn[i] : lcount[i]; }
         }
         __syncthreads();
+        const int nlists = TILED ? s_nl[wi & 1] : s_nlists;
 
         uint32_t n_left = 0u, st = 0u;
         uint32_t nx = 0u;
@@ -781,12 +998,12 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_replay_grp(const En
                     int oi = 0;
                     if (g == 0) oi = atomicAdd(&s_next, 1);
                     oi = __shfl_sync(gmask, oi, 0, G);
-                    if (oi >= s_nlists) { exhausted = true; break; }
+                    if (oi >= nlists) { exhausted = true; break; }
                     const int cc = s_order[oi];
-                    const uint32_t b0 = s_b0[cc], b1 = s_b1[cc];
+                    const uint32_t b0 = s_b0[TILED ? oi : cc], b1 = s_b1[TILED ? oi : cc];
                     if (b1 == b0) continue;
                     c = cc; n_left = b1 - b0;
-                    lp = chain_list + s_lstart[cc] + b0;
+                    lp = (TILED ? blk : chain_list + s_lstart[cc]) + b0;
                     st = has_slot ? s_state[cc * 32 + slot] : 0u;
                     nx = (uint32_t)g < n_left ? lp[g] : 0u;
                     break;
@@ -854,6 +1071,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_replay_grp(const En
 }
 
 static int replay_grp_smem(const Layout &L) { return L.ctx_count * (32 + 12 + 2) + 16; }
+static int tile_sort_smem(const Layout &L, int pitch) { return kTileSortRows * L.ctx_count * 4 + pitch * 2 + kTiledMaxSamples * 4; }
 
 static bool big_model(const Layout &L) { return L.ctx_count > kMaxListCtx; }
 
@@ -881,6 +1099,8 @@ cudaError_t configure_ctx_replay(const Layout &L)
         if (e != cudaSuccess) return e;
         return cudaFuncSetAttribute(k_ctx_scatter<0, 13>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx_scatter_smem_bytes(L));
     }
+    if (L.tiled_lists)
+        return cudaFuncSetAttribute(k_tile_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_sort_smem(L, (L.ctx_count + 8) & ~7));
     e = cudaFuncSetAttribute(k_ctx_scatter_sm<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx_scatter_sm_smem_bytes(L));
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_ctx_scatter_sm<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx_scatter_sm_smem_bytes(L, 1));
@@ -909,14 +1129,30 @@ void launch_golomb_lists(const EncDeviceTables &t, const EncBatch &b, cudaStream
     k_ctx_scatter_sm<true, 0><<<tiles, kScatterSmThreads, ctx_scatter_sm_smem_bytes(L), s>>>(t, b);
 }
 
+// tile-sorted lists: sort -> decision layout -> replay (a window per tile)
+static void launch_tiled_replay(const EncDeviceTables &t, const EncBatch &b, int nchains, cudaStream_t s)
+{
+    const Layout &L = t.layout;
+    dim3 tiles(L.ctiles_per_frame, b.nframes);
+    const int n = b.nframes * L.nslices * L.npc;
+    k_tile_sort<<<tiles, kTileSortThreads, tile_sort_smem(L, b.tile_tab_pitch), s>>>(t, b);
+    k_tile_layout<<<(n + 127) / 128, 128, 0, s>>>(t, b);
+    int threads = 256;
+    if (const char *v = getenv("FFV1B200_REPLAY_THREADS")) threads = atoi(v);
+    if (threads == 128)      k_replay_grp<4, 128, true><<<nchains, 128, replay_grp_smem(L), s>>>(t, b, 1);
+    else if (threads == 512) k_replay_grp<4, 512, true><<<nchains, 512, replay_grp_smem(L), s>>>(t, b, 1);
+    else                     k_replay_grp<4, 256, true><<<nchains, 256, replay_grp_smem(L), s>>>(t, b, 1);
+}
+
 void launch_ctx_replay(const EncDeviceTables &t, const EncBatch &b, int max_tile_samples, uint32_t max_dec_cap, cudaStream_t s)
 {
     const Layout &L = t.layout;
     const int nchains = b.nseg * L.nslices * L.npc;
     dim3 tiles(L.ctiles_per_frame, b.nframes);
+    const int n = b.nframes * L.nslices * L.npc;
+    if (L.tiled_lists) { launch_tiled_replay(t, b, nchains, s); return; }
     k_ctx_hist<false><<<tiles, kHistThreads, L.ctx_count * 4, s>>>(t, b);
     k_ctx_scan<<<nchains, kScanThreads, L.ctx_count * 8, s>>>(t, b);
-    const int n = b.nframes * L.nslices * L.npc;
     k_dec_layout<<<(n + 127) / 128, 128, 0, s>>>(t, b);
     dim3 stiles((L.ctiles_per_frame + kScatterThreads / 32 - 1) / (kScatterThreads / 32), b.nframes);
     if (big_model(L)) {
@@ -944,13 +1180,13 @@ void launch_ctx_replay(const EncDeviceTables &t, const EncBatch &b, int max_tile
     }
     int window = 3;
     if (const char *v = getenv("FFV1B200_REPLAY_WINDOW")) { window = atoi(v); if (window < 1) window = 1 << 20; }
-    if (grp == 1 && grp_ok) k_replay_grp<4, 1024><<<nchains, 1024, replay_grp_smem(L), s>>>(t, b, window);
+    if (grp == 1 && grp_ok) k_replay_grp<4, 1024, false><<<nchains, 1024, replay_grp_smem(L), s>>>(t, b, window);
     else if (grp == 2 && grp_ok) {
         int threads = 256;
         if (const char *v = getenv("FFV1B200_REPLAY_THREADS")) threads = atoi(v);
-        if (threads == 128)      k_replay_grp<4, 128><<<nchains, 128, replay_grp_smem(L), s>>>(t, b, window);
-        else if (threads == 256) k_replay_grp<4, 256><<<nchains, 256, replay_grp_smem(L), s>>>(t, b, window);
-        else                     k_replay_grp<4, 512><<<nchains, 512, replay_grp_smem(L), s>>>(t, b, window);
+        if (threads == 128)      k_replay_grp<4, 128, false><<<nchains, 128, replay_grp_smem(L), s>>>(t, b, window);
+        else if (threads == 256) k_replay_grp<4, 256, false><<<nchains, 256, replay_grp_smem(L), s>>>(t, b, window);
+        else                     k_replay_grp<4, 512, false><<<nchains, 512, replay_grp_smem(L), s>>>(t, b, window);
     }
     else if (L.coded_bits <= 10) k_replay_ctx<false, false><<<nchains, kCtxThreads, L.ctx_count * 42, s>>>(t, b);
     else                    k_replay_ctx<true, false><<<nchains, kCtxThreads, L.ctx_count * 42, s>>>(t, b);

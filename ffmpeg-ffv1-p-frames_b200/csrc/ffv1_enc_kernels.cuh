@@ -42,6 +42,10 @@ struct EncBatch {
     uint32_t *list_count;               // [chains][ctx_count]
     uint16_t *list_order;               // [chains][ctx_count] contexts, longest list first
     uint2 *lists;                       // [nframes * samples_per_frame] {decision position, residual | frame << 16}
+    // tile-sorted lists (Layout::tiled_lists; the buffers alias ctx_hist / line_pos)
+    uint16_t *tile_tab;                 // [nframes][ctiles_per_frame][tile_tab_pitch] start of every context's run inside the tile's block
+    uint32_t *tile_nd;                  // [nframes][ctiles_per_frame] decisions of the tile, then its first decision in the region
+    int32_t tile_tab_pitch;             // entries per table: ctx_count + 1 rounded up to 8
     const uint8_t *rct_idx;             // version-4 RGB: [nframes][nslices] index of the slice's RCT coefficient pair (else null)
     // adaptive state
     uint8_t *state_seg;                 // global-state mode: [nseg][nslices][npc][ctx_count*32]

@@ -241,6 +241,11 @@ int enqueue_kernels(FFV1B200Encoder *e, Slot &sl, cudaStream_t s)
     b.line_pos = e->d_line_pos.p; b.ctx_hist = e->d_ctx_hist.p;
     b.list_start = e->d_list_start.p; b.list_count = e->d_list_count.p; b.list_order = e->d_list_order.p; b.lists = e->d_lists.p;
     b.rct_idx = e->d_rct_idx.p;
+    if (L.tiled_lists) {        // the tile tables and tile decision counts live where the chain-wide lists keep their histograms
+        b.tile_tab_pitch = (L.ctx_count + 8) & ~7;
+        b.tile_tab = reinterpret_cast<uint16_t *>(e->d_ctx_hist.p);
+        b.tile_nd = e->d_line_pos.p;
+    }
 
     cudaEventRecord(sl.ev[0], s);
     if (t.nvar > 1) { launch_rct_search(t, b, s); e->stats.kernel_launches++; }      // choose_rct_params, before the RCT is applied
@@ -271,7 +276,7 @@ int enqueue_kernels(FFV1B200Encoder *e, Slot &sl, cudaStream_t s)
         CU_TRY(launch_pass1_stats(t, b, e->d_rc_stat.p, e->d_rc_stat2.p, s));
         e->stats.kernel_launches++;
     }
-    e->stats.kernel_launches += L.golomb ? (e->golomb_lists ? 8 : 4) : (e->ctx_replay ? 9 : 5);
+    e->stats.kernel_launches += L.golomb ? (e->golomb_lists ? 8 : 4) : (e->ctx_replay ? (L.tiled_lists ? 7 : 9) : 5);
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaMemcpyAsync(sl.h_status.p, sl.d_status.p, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost, s));
     CU_TRY(cudaMemcpyAsync(sl.h_pkt_size.p, sl.d_pkt_size.p, sizeof(uint32_t) * nframes, cudaMemcpyDeviceToHost, s));

@@ -963,16 +963,6 @@ void build_tables(const Config &c, Tables &t)
                 if (t.lines[g.line_first + li].pc == pc) { t.pc_lines.push_back(li); ns += t.lines[g.line_first + li].w; }
             g.pc_nlines[pc] = (int32_t)t.pc_lines.size() - g.pc_line_first[pc];
             g.pc_samples[pc] = ns;
-            g.ct_first[pc] = (int32_t)t.ctiles.size();
-            // the large context model's tiles are four times as tall: a tile carries a histogram of all 7563 contexts
-            const int tile_lines = L.ctx_count > 1024 ? 4 * kCtxTileLines : kCtxTileLines;
-            for (int l0 = 0; l0 < g.pc_nlines[pc]; l0 += tile_lines) {
-                CtxTile ct;
-                ct.slice = (uint16_t)si; ct.pc = (uint8_t)pc; ct.first = (uint32_t)l0;
-                ct.nlines = (uint8_t)std::min(tile_lines, g.pc_nlines[pc] - l0);
-                t.ctiles.push_back(ct);
-            }
-            g.ct_count[pc] = (int32_t)t.ctiles.size() - g.ct_first[pc];
             g.list_off[pc] = list_cursor;
             list_cursor += ns;
         }
@@ -981,6 +971,44 @@ void build_tables(const Config &c, Tables &t)
         g.scratch_off = scratch_cursor;
         g.scratch_cap = (uint32_t)(((raw + raw / 8 + 4096) + 255) & ~255ull);
         scratch_cursor += g.scratch_cap;
+    }
+    // ---- context tiles: the units of the per-context list builders (ffv1_ctx_replay.cu).  16 consecutive lines of a
+    // (slice, plane context); 64 for the large context model (a tile carries a histogram of all 7563 contexts); 32 for the
+    // tile-sorted lists of 8-bit planar range-coded content (see Layout::tiled_lists)
+    {
+        bool tiled = !L.golomb && L.ctx_count <= 1024 && L.coded_bits <= 9;
+        if (const char *v = getenv("FFV1B200_TILED")) { if (atoi(v) == 0) tiled = false; }     // A/B switch: the chain-wide lists
+        for (const SliceGeom &g : t.slices)
+            for (int pc = 0; pc < 3 && tiled; pc++) {
+                uint32_t widest = 0;
+                for (int i = 0; i < g.pc_nlines[pc]; i++) {
+                    const LineDesc &ld = t.lines[g.line_first + t.pc_lines[g.pc_line_first[pc] + i]];
+                    if (ld.run != t.lines[g.line_first + t.pc_lines[g.pc_line_first[pc]]].run) tiled = false;   // one run per plane context
+                    widest = std::max<uint32_t>(widest, ld.w);
+                }
+                if (widest * kTiledLines > (uint32_t)kTiledMaxSamples) tiled = false;
+            }
+        L.tiled_lists = tiled ? 1 : 0;
+        const int tile_lines = L.ctx_count > 1024 ? 4 * kCtxTileLines : (tiled ? kTiledLines : kCtxTileLines);
+        for (size_t si = 0; si < t.slices.size(); si++) {
+            SliceGeom &g = t.slices[si];
+            for (int pc = 0; pc < 3; pc++) {
+                g.ct_first[pc] = (int32_t)t.ctiles.size();
+                uint32_t before = 0;
+                for (int l0 = 0; l0 < g.pc_nlines[pc]; l0 += tile_lines) {
+                    CtxTile ct;
+                    ct.slice = (uint16_t)si; ct.pc = (uint8_t)pc; ct.first = (uint32_t)l0;
+                    ct.nlines = (uint8_t)std::min(tile_lines, g.pc_nlines[pc] - l0);
+                    ct.sample_first = before;
+                    uint32_t ns = 0;
+                    for (int i = 0; i < ct.nlines; i++) ns += t.lines[g.line_first + t.pc_lines[g.pc_line_first[pc] + l0 + i]].w;
+                    ct.nsamples = ns;
+                    before += ns;
+                    t.ctiles.push_back(ct);
+                }
+                g.ct_count[pc] = (int32_t)t.ctiles.size() - g.ct_first[pc];
+            }
+        }
     }
     L.lines_per_frame = (int32_t)t.lines.size();
     L.tiles_per_frame = (int32_t)t.tiles.size();

@@ -78,9 +78,13 @@ struct CtxTile {
     uint16_t slice;
     uint8_t  pc;
     uint8_t  nlines;
-    uint32_t first;      // index of its first line in the (slice, plane context) line list
+    uint32_t first;        // index of its first line in the (slice, plane context) line list
+    uint32_t sample_first; // samples of the (slice, plane context) in front of the tile
+    uint32_t nsamples;
 };
 constexpr int kCtxTileLines = 16;
+constexpr int kTiledLines = 48;            // tile-sorted lists: lines per tile, and the largest tile the sort holds
+constexpr int kTiledMaxSamples = 16896;    // (48 lines of <= 352 samples)
 
 struct Layout {
     int32_t width, height;
@@ -103,6 +107,8 @@ struct Layout {
     int32_t ctiles_per_frame;
     uint32_t samples_per_frame;  // coded samples (no padding)
     uint32_t dec_per_frame;  // decision entries per frame (all regions; set by layout_decisions)
+    int32_t tiled_lists;     // the per-context lists are kept tile by tile (k_tile_sort / k_replay_grp<TILED>): 8-bit content,
+                             // small context model, range coder, one run per plane context, slices <= 352 samples wide
     int32_t rct_offset;      // 1 << bits for RGB
     PlaneInfo plane[4];
 };
