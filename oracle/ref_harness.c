@@ -41,6 +41,9 @@ typedef struct RefEnc {
  * each slice header, ffv1enc.c:1048-1049). */
 static void *enc_open_impl(AVCodec *codec, int w, int h, const char *pix_fmt, int gop, int level, int coder, int context,
                            int slices, int slicecrc, int threads, int strict_experimental, int batch);
+static int g_pass;
+static const char *g_stats_in;
+
 
 void *ffv1ref_enc_open(int w, int h, const char *pix_fmt, int gop, int level, int coder, int context,
                        int slices, int slicecrc, int threads, int strict_experimental)
@@ -51,8 +54,6 @@ void *ffv1ref_enc_open(int w, int h, const char *pix_fmt, int gop, int level, in
 
 /* Two-pass coding: pass = 1 sets AV_CODEC_FLAG_PASS1 (statistics into stats_out), pass = 2 sets AV_CODEC_FLAG_PASS2;
  * stats_in (may be NULL) is handed to the encoder as AVCodecContext.stats_in (ffv1enc.c:906-986). */
-static int g_pass;
-static const char *g_stats_in;
 void *ffv1ref_enc_open_2pass(int w, int h, const char *pix_fmt, int gop, int level, int coder, int context,
                              int slices, int slicecrc, int threads, int strict_experimental, int pass, const char *stats_in)
 {
@@ -91,6 +92,20 @@ void *ffv1ref_enc_open_named(const char *name, int w, int h, const char *pix_fmt
     AVCodec *codec = avcodec_find_encoder_by_name(name);
     if (!codec) return NULL;
     return enc_open_impl(codec, w, h, pix_fmt, gop, level, coder, context, slices, slicecrc, 1, 0, batch);
+}
+
+/* the same, with -strict experimental and the two-pass options (pass: 0 none, 1 = AV_CODEC_FLAG_PASS1, 2 = _PASS2) */
+void *ffv1ref_enc_open_named_ex(const char *name, int w, int h, const char *pix_fmt, int gop, int level, int coder, int context,
+                                int slices, int slicecrc, int batch, int strict_experimental, int pass, const char *stats_in)
+{
+    void *r;
+    reg();
+    AVCodec *codec = avcodec_find_encoder_by_name(name);
+    if (!codec) return NULL;
+    g_pass = pass; g_stats_in = stats_in;
+    r = enc_open_impl(codec, w, h, pix_fmt, gop, level, coder, context, slices, slicecrc, 1, strict_experimental, batch);
+    g_pass = 0; g_stats_in = NULL;
+    return r;
 }
 
 static void *enc_open_impl(AVCodec *codec, int w, int h, const char *pix_fmt, int gop, int level, int coder, int context,

@@ -249,3 +249,69 @@ def test_nut_round_trip_through_the_dropin(lavc, fmt, level, slices):
         out, n, name = ffv1_ref.nut_decode(dec, ours, len(src), opts)
         assert n == 50 and name == fmt, (dec, opts, n, name)
         assert np.array_equal(out.reshape(50, -1), want), (dec, opts)
+
+def _run_named(L, name, w, h, fmt, opts, frames, batch, strict=0, two_pass=0, stats_in=None, want_stats=False):
+    L.ffv1ref_enc_open_named_ex.restype = ctypes.c_void_p
+    L.ffv1ref_enc_open_named_ex.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_char_p] + [ctypes.c_int] * 9 + [ctypes.c_char_p]
+    L.ffv1ref_enc_stats_out.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int]
+    o = dict(gop=12, level=-1, coder=0, context=0, slices=0, slicecrc=-1); o.update(opts)
+    if isinstance(stats_in, str):
+        stats_in = stats_in.encode()
+    hnd = L.ffv1ref_enc_open_named_ex(name.encode(), w, h, fmt.encode(), o["gop"], o["level"], o["coder"], o["context"],
+                                      o["slices"], o["slicecrc"], batch, strict, two_pass, stats_in)
+    assert hnd, "avcodec_open2(%s) failed" % name
+    ed = ctypes.create_string_buffer(1 << 16)
+    ned = L.ffv1ref_enc_extradata(hnd, ed, 1 << 16)
+    cap = 65536 + pixfmt.frame_bytes(fmt, w, h) * 4
+    buf = ctypes.create_string_buffer(cap)
+    key = ctypes.c_int()
+    pkts = []
+    for f in frames:
+        planes = split_planes(np.ascontiguousarray(f).view(np.uint8).reshape(-1), fmt, w, h)
+        ptrs, strides = _plane_args(planes)
+        r = L.ffv1ref_enc_frame(hnd, ptrs, strides, 0, 1, 0, 0, buf, cap, ctypes.byref(key))
+        assert r >= 0
+        if r:
+            pkts.append(buf.raw[:r])
+    while True:
+        r = L.ffv1ref_enc_frame(hnd, None, None, 0, 1, 0, 0, buf, cap, ctypes.byref(key))
+        assert r >= 0
+        if not r:
+            break
+        pkts.append(buf.raw[:r])
+    stats = None
+    if want_stats:
+        sb = ctypes.create_string_buffer(8 << 20)
+        n = L.ffv1ref_enc_stats_out(hnd, sb, 8 << 20)
+        assert n > 0
+        stats = sb.value.decode()
+    L.ffv1ref_enc_close(hnd)
+    return ed.raw[:max(ned, 0)], pkts, stats
+
+def test_two_pass_through_avcodec_api(lavc):
+    """-pass 1 / -pass 2 with -c:v ffv1_b200: stats_out after the flush and the second pass's stream equal the reference
+    codec's (AV_CODEC_FLAG_PASS1/2 and stats_in reach the library through the shim)"""
+    from twopass_cases import TWOPASS_CASES, make_frames as tp_frames
+    case = TWOPASS_CASES[0]
+    cid, w, h, fmt, opts, n = case
+    frames = tp_frames(case)
+    ed_r, p_r, st_r = _run_named(lavc, "ffv1", w, h, fmt, opts, frames, 0, two_pass=1, want_stats=True)
+    ed_g, p_g, st_g = _run_named(lavc, "ffv1_b200", w, h, fmt, opts, frames, 4, two_pass=1, want_stats=True)
+    assert ed_r == ed_g and p_r == p_g and st_r == st_g
+    ed_r2, p_r2, _ = _run_named(lavc, "ffv1", w, h, fmt, opts, frames, 0, two_pass=2, stats_in=st_r)
+    ed_g2, p_g2, _ = _run_named(lavc, "ffv1_b200", w, h, fmt, opts, frames, 4, two_pass=2, stats_in=st_g)
+    assert ed_r2 == ed_g2 and p_r2 == p_g2 and len(ed_r2) > len(ed_r)
+
+def test_level4_through_avcodec_api(lavc):
+    """-level 4 -strict experimental with -c:v ffv1_b200 on RGB content: the reference codec's own bytes; without -strict
+    both refuse"""
+    from level4_cases import LEVEL4_CASES, make_frames as l4_frames
+    for case in [c for c in LEVEL4_CASES if c[0] in ("l4_bgr0_range", "l4_bgra_golomb", "l4_gbrp9")]:
+        cid, w, h, fmt, opts, n, exact = case
+        frames = l4_frames(case)
+        ed_r, p_r, _ = _run_named(lavc, "ffv1", w, h, fmt, opts, frames, 0, strict=1)
+        ed_g, p_g, _ = _run_named(lavc, "ffv1_b200", w, h, fmt, opts, frames, 2, strict=1)
+        assert ed_r == ed_g and p_r == p_g, cid
+    lavc.ffv1ref_enc_open_named_ex.restype = ctypes.c_void_p
+    for name in (b"ffv1", b"ffv1_b200"):
+        assert not lavc.ffv1ref_enc_open_named_ex(name, 96, 80, b"bgr0", 3, 4, 1, 0, 4, -1, 2, 0, 0, None)
