@@ -410,7 +410,7 @@ def main():
             try:                                     # decoder of the same stream (extra information, not the metric)
                 sys.path.insert(0, os.path.join(ROOT, "tools"))
                 import bench_decode
-                line["decode"] = bench_decode.run(512, 512, 1, 0 if args.no_cpu_baseline else 33)
+                line["decode"] = bench_decode.run(2048, 2048, 1, 0 if args.no_cpu_baseline else 33)     # 2048-frame batch, like the encoder's step
             except Exception as ex:
                 line["decode"] = {"value": None, "note": repr(ex)}
         print(json.dumps(line))

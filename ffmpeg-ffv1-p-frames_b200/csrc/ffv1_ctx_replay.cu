@@ -476,22 +476,19 @@ __global__ void __launch_bounds__(kTileSortThreads) k_tile_sort(const EncDeviceT
     __syncthreads();
     const uint32_t *rec_slice = B.rec + (size_t)f * L.rec_per_frame + g.rec_first;
     const int32_t *my_lines = T.pc_lines + g.pc_line_first[ct.pc] + ct.first;
-    // ---- pass 1: context counts and decisions of the warp's lines
-    const uint32_t *recp[2] = {nullptr, nullptr};
-    int w[2] = {0, 0};
+    // ---- pass 1: context counts and decisions of the warp's lines (2, or 4 in the tall tiles of narrow planes)
+    const int lpw = (ct.nlines + kTileSortThreads / 32 - 1) / (kTileSortThreads / 32);
     uint32_t *wh = s_wh + (warp >> 1) * nctx;
     const int sh = (warp & 1) * 16;
     {
         uint32_t nd = 0;
-#pragma unroll
-        for (int k = 0; k < 2; k++) {
-            const int li = 2 * warp + k;
+        for (int k = 0; k < lpw; k++) {
+            const int li = lpw * warp + k;
             if (li < ct.nlines) {
                 const LineDesc ld = T.lines[g.line_first + my_lines[li]];
-                recp[k] = rec_slice + ld.rec_off;
-                w[k] = ld.w;
-                for (int x = lane; x < w[k]; x += 32) {
-                    const uint32_t r = recp[k][x];
+                const uint32_t *recp = rec_slice + ld.rec_off;
+                for (int x = lane; x < ld.w; x += 32) {
+                    const uint32_t r = recp[x];
                     nd += decisions_of((int)(int16_t)(r & 0xFFFFu));
                     atomicAdd(&wh[r >> 16], 1u << sh);
                 }
@@ -538,11 +535,15 @@ __global__ void __launch_bounds__(kTileSortThreads) k_tile_sort(const EncDeviceT
     // ---- pass 2: stable placement, entry = position of the symbol's first decision inside the tile | residual << 22
     {
         uint32_t pos = s_wnd[warp];
-#pragma unroll
-        for (int k = 0; k < 2; k++)
-            for (int x0 = 0; x0 < w[k]; x0 += 32) {
-                const bool act = x0 + lane < w[k];
-                const uint32_t r = act ? recp[k][x0 + lane] : 0u;
+        for (int k = 0; k < lpw; k++) {
+            const int li = lpw * warp + k;
+            if (li >= ct.nlines) break;
+            const LineDesc ld = T.lines[g.line_first + my_lines[li]];
+            const uint32_t *recp = rec_slice + ld.rec_off;
+            const int w = ld.w;
+            for (int x0 = 0; x0 < w; x0 += 32) {
+                const bool act = x0 + lane < w;
+                const uint32_t r = act ? recp[x0 + lane] : 0u;
                 const uint32_t ctx = r >> 16;
                 const uint32_t nd = act ? decisions_of((int)(int16_t)(r & 0xFFFFu)) : 0u;
                 const uint32_t in = cr_incl_scan(nd, lane);
@@ -554,6 +555,7 @@ __global__ void __launch_bounds__(kTileSortThreads) k_tile_sort(const EncDeviceT
                 if (act) s_ent[(uint32_t)s_start[ctx] + off + rank] = (pos + in - nd) | (r << kGrpPosBits);
                 pos += __shfl_sync(0xFFFFFFFFu, in, 31);
             }
+        }
     }
     __syncthreads();
     // ---- the block and its table leave with coalesced stores

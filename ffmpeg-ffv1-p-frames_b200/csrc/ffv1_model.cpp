@@ -989,10 +989,18 @@ void build_tables(const Config &c, Tables &t)
                 if (widest * kTiledLines > (uint32_t)kTiledMaxSamples) tiled = false;
             }
         L.tiled_lists = tiled ? 1 : 0;
-        const int tile_lines = L.ctx_count > 1024 ? 4 * kCtxTileLines : (tiled ? kTiledLines : kCtxTileLines);
         for (size_t si = 0; si < t.slices.size(); si++) {
             SliceGeom &g = t.slices[si];
             for (int pc = 0; pc < 3; pc++) {
+                int tile_lines = L.ctx_count > 1024 ? 4 * kCtxTileLines : (tiled ? kTiledLines : kCtxTileLines);
+                if (tiled) {
+                    // narrow planes (subsampled chroma) take twice the lines: a tile is the replay's window, and the
+                    // sort's per-tile set-up is the same whatever the tile holds
+                    uint32_t widest = 0;
+                    for (int i = 0; i < g.pc_nlines[pc]; i++)
+                        widest = std::max<uint32_t>(widest, t.lines[g.line_first + t.pc_lines[g.pc_line_first[pc] + i]].w);
+                    if (widest * 2 * kTiledLines <= (uint32_t)kTiledMaxSamples) tile_lines = 2 * kTiledLines;
+                }
                 g.ct_first[pc] = (int32_t)t.ctiles.size();
                 uint32_t before = 0;
                 for (int l0 = 0; l0 < g.pc_nlines[pc]; l0 += tile_lines) {
