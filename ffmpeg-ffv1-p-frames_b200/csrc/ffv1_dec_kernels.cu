@@ -452,8 +452,11 @@ __device__ void dec_line_pcm(SliceRd &sr, const uint16_t *lut, int16_t *cur, int
 // per x a record {T = top[x], q12 = Q1[LT-T] + Q2[T-RT]} from the finished line above; the serial lane reads one record,
 // adds Q0[L-LT], decodes, and stores the sample into the record; the warp then writes the line out and turns `cur` into
 // the next line's `top`.
-struct __align__(8) LineRec { int16_t top, q12, cur, pad; };
+// FIVE: the five-table context model (ffv1.h:176-186) adds Q3[LL - L], which the serial lane looks up, and Q4[TT - T],
+// which the warp folds into q12 from the line two rows up (kept in `top2`).
+struct __align__(8) LineRec { int16_t top, q12, cur, top2; };
 
+template <bool FIVE>
 __device__ __forceinline__ void dec_line_rec(SliceRd &sr, uint8_t *model, const int16_t *q, const uint16_t *lut, LineRec *rec,
                                              int w, int bits, int topm1)
 {
@@ -464,11 +467,13 @@ __device__ __forceinline__ void dec_line_rec(SliceRd &sr, uint8_t *model, const 
     uint32_t lut_sa = (uint32_t)__cvta_generic_to_shared(lut), q_sa = (uint32_t)__cvta_generic_to_shared(q);
     asm volatile("" : "+r"(lut_sa), "+r"(q_sa));         // keep them in registers (otherwise re-derived from %cluster_ctarank per sample)
     int L = rec[0].top, LT = topm1;                      // sample[1][-1] = sample[0][0] (ffv1dec.c:199)
+    int LL = 0;                                          // sample[1][-2] stays 0
     LineRec *r = rec, *const rend = rec + w;
     do {
         const int Tp = r->top, q12 = r->q12;
         const int d = L - LT;
-        const int ctx = lds_s16(q_sa + 2u * (uint32_t)(d & 0xFF)) + q12;
+        int ctx = lds_s16(q_sa + 2u * (uint32_t)(d & 0xFF)) + q12;
+        if (FIVE) { ctx += lds_s16(q_sa + 2u * (768u + (uint32_t)((LL - L) & 0xFF))); LL = L; }
         const int pred = median3(L, Tp, d + Tp);
         int diff = fr_symbol(c, model + (size_t)abs(ctx) * 32, lut, lut_sa, err);
         if (ctx < 0) diff = -diff;
@@ -651,7 +656,8 @@ __global__ void __launch_bounds__(32 * kDecWarps, MINB) k_decode(const DecDevice
                 }
                 const bool ring_sm = T.smem_ring_w && w + 2 * kDecRingPad <= T.smem_ring_w;
                 const int rw = ring_sm ? T.smem_ring_w : T.ring_w;
-                if (!golomb && ring_sm && !q[3 * 256 + 127] && !pcm) {
+                if (!golomb && ring_sm && !pcm) {
+                    const bool five = q[3 * 256 + 127] != 0;
                     LineRec *rec = reinterpret_cast<LineRec *>(s_ring);
                     for (int x = lane; x < w; x += 32) rec[x] = LineRec{0, 0, 0, 0};
                     __syncwarp();
@@ -660,15 +666,18 @@ __global__ void __launch_bounds__(32 * kDecWarps, MINB) k_decode(const DecDevice
                         const int cm1 = rec[0].top;
                         for (int x = lane; x < w; x += 32) {
                             const int Tp = rec[x].top, LTv = x ? rec[x - 1].top : topm1, RTv = x + 1 < w ? rec[x + 1].top : Tp;
-                            rec[x].q12 = (int16_t)(q[256 + ((LTv - Tp) & 0xFF)] + q[512 + ((Tp - RTv) & 0xFF)]);
+                            int q12 = q[256 + ((LTv - Tp) & 0xFF)] + q[512 + ((Tp - RTv) & 0xFF)];
+                            if (five) q12 += q[1024 + ((rec[x].top2 - Tp) & 0xFF)];
+                            rec[x].q12 = (int16_t)q12;
                         }
                         __syncwarp();
 #ifdef FFV1_DEC_PROBE
                         const long long pt0 = clock64();
 #endif
                         if (lane == 0) {
-                            if (model_sm) dec_line_rec(sr, s_model, q, s_lut, rec, w, bits, topm1);
-                            else dec_line_rec(sr, model, q, s_lut, rec, w, bits, topm1);
+                            if (five) dec_line_rec<true>(sr, model_sm ? s_model : model, q, s_lut, rec, w, bits, topm1);
+                            else if (model_sm) dec_line_rec<false>(sr, s_model, q, s_lut, rec, w, bits, topm1);
+                            else dec_line_rec<false>(sr, model, q, s_lut, rec, w, bits, topm1);
                         }
 #ifdef FFV1_DEC_PROBE
                         probe_serial += clock64() - pt0; probe_samples += w;
@@ -680,6 +689,7 @@ __global__ void __launch_bounds__(32 * kDecWarps, MINB) k_decode(const DecDevice
                             for (int x = lane; x < w; x += 32) {
                                 const int16_t v = rec[x].cur;
                                 dst[(px0 + x) * pstep + poff] = (uint8_t)v;
+                                rec[x].top2 = rec[x].top;
                                 rec[x].top = v;
                             }
                         } else {
@@ -688,6 +698,7 @@ __global__ void __launch_bounds__(32 * kDecWarps, MINB) k_decode(const DecDevice
                             for (int x = lane; x < w; x += 32) {
                                 const int16_t v = rec[x].cur;
                                 d16[x] = (uint16_t)((uint16_t)v << shl);
+                                rec[x].top2 = rec[x].top;
                                 rec[x].top = v;
                             }
                         }

@@ -11,7 +11,7 @@ without the built library, or calling it without a B200-class GPU, raises -- the
 Option names and meaning follow the reference encoder (ffv1enc.c:1383-1399 and the generic -g/-level/-slices).
 """
 from .codec import (FFV1Encoder, FFV1Decoder, FFV1Error, lib, library_path, device_count, frame_bytes, resolve_encoder,
-                    FLAG_PASS1, FLAG_PASS2,
+                    FLAG_PASS1, FLAG_PASS2, FFV1Uploader, encode_cuda,
                     plane_shapes, EncStats, Packet, bind_thread_to_device)
 from .partition import gop_aligned_ranges, reinterleave
 

@@ -350,6 +350,73 @@ class FFV1Encoder:
         except Exception:
             pass
 
+class FFV1Uploader:
+    """On-GPU input preparation (hwupload_cuda + the format conversion of scale_npp, include/ffv1_b200.h): host frames in a
+    capture / hardware-decoder layout -> device frames in one of the encoder's pix_fmts."""
+
+    def __init__(self, width, height, src_pix_fmt, dst_pix_fmt=None, pool_frames=16, device=0):
+        L = lib()
+        L.ffv1b200_upload_open.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_int,
+                                           ctypes.c_int, ctypes.c_int]
+        L.ffv1b200_upload_close.argtypes = [ctypes.c_void_p]
+        L.ffv1b200_upload_close.restype = None
+        L.ffv1b200_upload_pix_fmt.argtypes = [ctypes.c_void_p]
+        L.ffv1b200_upload_pix_fmt.restype = ctypes.c_char_p
+        L.ffv1b200_upload_frames.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int),
+                                             ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int)]
+        L.ffv1b200_enc_encode_cuda.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int),
+                                               ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(Packet), ctypes.POINTER(ctypes.c_size_t)]
+        self._h = ctypes.c_void_p()
+        self.pool = pool_frames
+        _check(L.ffv1b200_upload_open(ctypes.byref(self._h), src_pix_fmt.encode(), dst_pix_fmt.encode() if dst_pix_fmt else None,
+                                      width, height, pool_frames, device))
+        self.pix_fmt = L.ffv1b200_upload_pix_fmt(self._h).decode()
+
+    def upload(self, frames, plane_rows_bytes):
+        """frames: contiguous uint8 arrays (planes back to back, tightly packed); plane_rows_bytes: [(rows, row bytes)] of the
+        source layout.  Returns (device plane pointer table, linesizes) for FFV1Encoder.encode_cuda."""
+        n = len(frames)
+        planes = (ctypes.c_void_p * (4 * n))()
+        ls = (ctypes.c_int * (4 * n))()
+        keep = []
+        for f, fr in enumerate(frames):
+            a = np.ascontiguousarray(fr).view(np.uint8).reshape(-1)
+            keep.append(a)
+            off = 0
+            for i, (rows, rb) in enumerate(plane_rows_bytes):
+                planes[4 * f + i] = a.ctypes.data + off
+                ls[4 * f + i] = rb
+                off += rows * rb
+        dpl = (ctypes.c_void_p * (4 * n))()
+        dls = (ctypes.c_int * 4)()
+        _check(lib().ffv1b200_upload_frames(self._h, n, planes, ls, dpl, dls))
+        return dpl, dls
+
+    def close(self):
+        if self._h:
+            lib().ffv1b200_upload_close(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+def encode_cuda(enc, d_planes, d_linesizes, nframes):
+    """AV_PIX_FMT_CUDA frames (device plane pointers, one linesize set) -> [(packet bytes, key)] (ffv1b200_enc_encode_cuda)"""
+    fb = int(enc.info.frame_bytes)
+    cap = nframes * (fb + fb // 4 + 65536)
+    out = np.empty(cap, np.uint8)
+    pk = (Packet * nframes)()
+    need = ctypes.c_size_t()
+    ls = (ctypes.c_int * (4 * nframes))(*([d_linesizes[i] for i in range(4)] * nframes))
+    L = lib()
+    L.ffv1b200_enc_encode_cuda.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int),
+                                           ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(Packet), ctypes.POINTER(ctypes.c_size_t)]
+    _check(L.ffv1b200_enc_encode_cuda(enc._h, nframes, d_planes, ls, out.ctypes.data, cap, pk, ctypes.byref(need)))
+    return [(out[p.offset:p.offset + p.size].tobytes(), bool(p.flags & 1)) for p in pk]
+
 class FFV1Decoder:
     """Mirror of ff_ffv1_decoder (ffv1dec.c:1139-1153): __init__ = decode_init, decode/decode_batch = decode_frame."""
 

@@ -196,6 +196,29 @@ int  ffv1b200_enc_stats_out(FFV1B200Encoder *enc, char *buf, size_t cap, size_t 
  * (context<<16 | diff&0xffff) records of one frame/slice (coding order) to host.  Returns the record count. */
 int64_t ffv1b200_enc_debug_records(FFV1B200Encoder *enc, int frame_in_batch, int slice, uint32_t *dst, int64_t cap);
 
+/* ------------------------------------------------------------------ on-GPU input preparation
+ * The reference feeds a hardware encoder through its filter graph: vf_hwupload_cuda (libavfilter/vf_hwupload_cuda.c:144,
+ * system-memory AVFrame -> AV_PIX_FMT_CUDA frame from a pool) and the pixel-format conversion of vf_scale_npp
+ * (libavfilter/vf_scale_npp.c).  An uploader does both for this codec: frames in a capture / hardware-decoder layout
+ *     nv12 -> yuv420p    p010le -> yuv420p10le    yuyv422, uyvy422 -> yuv422p    rgb24, bgr24 -> bgr0    rgba -> bgra
+ * or already in one of the encoder's pix_fmts (upload only) become device frames the encoder takes
+ * (ffv1b200_enc_encode_cuda / _encode_device).  Samples are re-arranged, never changed (P010's 10 bits move down). */
+typedef struct FFV1B200Uploader FFV1B200Uploader;
+/* dst_pix_fmt may be NULL (the format the source maps to); pool_frames = frames per call the pool holds */
+int  ffv1b200_upload_open(FFV1B200Uploader **up, const char *src_pix_fmt, const char *dst_pix_fmt, int width, int height,
+                          int pool_frames, int device);
+void ffv1b200_upload_close(FFV1B200Uploader *up);
+const char *ffv1b200_upload_pix_fmt(const FFV1B200Uploader *up);     /* pix_fmt of the device frames */
+/* nframes (<= pool_frames) host frames -> device frames: d_planes[f*4+i] / d_linesizes[i] as the encoder's device entry
+ * points take them; valid until the next call on this uploader.  Blocking.  Returns nframes or a negative error. */
+int  ffv1b200_upload_frames(FFV1B200Uploader *up, int nframes, const uint8_t *const *planes, const int *linesizes,
+                            void **d_planes, int *d_linesizes);
+/* the conversion alone, for frames already in device memory (a hardware decoder's NV12 / P010 surfaces): d_src_planes[i],
+ * src_linesizes[i] (multiples of 4) of frame 0, consecutive frames src_frame_stride bytes apart.  Ordered on `stream`
+ * (a cudaStream_t) when that is non-NULL, else blocking. */
+int  ffv1b200_convert_device(FFV1B200Uploader *up, int nframes, const void *const *d_src_planes, const int *src_linesizes,
+                             long long src_frame_stride, void **d_planes, int *d_linesizes, void *stream);
+
 /* ------------------------------------------------------------------ decoder */
 
 typedef struct FFV1B200DecParams {
