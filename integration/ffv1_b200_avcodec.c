@@ -332,6 +332,7 @@ static av_cold int b200_encode_close(AVCodecContext *avctx)
 {
     B200EncContext *s = avctx->priv_data;
     int i;
+    av_freep(&avctx->stats_out);                        /* the codec owns it, as in ff_ffv1_close (ffv1.c:229) */
     if (s->threads) {
         pthread_mutex_lock(&s->lock);
         s->quit = 1;
@@ -518,7 +519,7 @@ static int b200_encode_frame(AVCodecContext *avctx, AVPacket *pkt, const AVFrame
             if ((ret = collect_oldest(avctx)) < 0)
                 return ret;
         /* first pass: once everything is coded the statistics go to stats_out, like the reference's flush call
-         * (ffv1enc.c:1235-1277; lavc frees stats_out in avcodec_close) */
+         * (ffv1enc.c:1235-1277; freed in close like ffv1.c:229) */
         if ((avctx->flags & AV_CODEC_FLAG_PASS1) && !s->ninflight) {
             size_t need = 0;
             char probe[1];
