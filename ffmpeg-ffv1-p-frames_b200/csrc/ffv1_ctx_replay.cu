@@ -845,9 +845,11 @@ __device__ __noinline__ void replay_symbol_serial(uint8_t *row, const uint8_t *l
 }
 
 // TILED: the lists are kept tile by tile (k_tile_sort): a window is one tile, the window's part of a list is the
-// context's run inside the tile's block, and the entries' positions count from the tile's first decision.
+// context's run inside the tile's block, and the entries' positions count from the tile's first decision.  Three
+// 256-thread CTAs per SM (80 registers, no spills) beat four (64 registers): 141 vs 146 ms per 2048 frames; five (48
+// registers) 176 ms, six 128-thread CTAs 184 ms, two of 384 threads 150 ms -- the time follows the windows in flight.
 template <int EMAX, int THREADS, bool TILED>
-__global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_replay_grp(const EncDeviceTables T, const EncBatch B, const int window_rt)
+__global__ void __launch_bounds__(THREADS, (TILED ? 768 : 1024) / THREADS) k_replay_grp(const EncDeviceTables T, const EncBatch B, const int window_rt)
 {
     const int window = TILED ? 1 : window_rt;
     constexpr int G = 16;
@@ -1142,6 +1144,7 @@ static void launch_tiled_replay(const EncDeviceTables &t, const EncBatch &b, int
     int threads = 256;
     if (const char *v = getenv("FFV1B200_REPLAY_THREADS")) threads = atoi(v);
     if (threads == 128)      k_replay_grp<4, 128, true><<<nchains, 128, replay_grp_smem(L), s>>>(t, b, 1);
+    else if (threads == 384) k_replay_grp<4, 384, true><<<nchains, 384, replay_grp_smem(L), s>>>(t, b, 1);
     else if (threads == 512) k_replay_grp<4, 512, true><<<nchains, 512, replay_grp_smem(L), s>>>(t, b, 1);
     else                     k_replay_grp<4, 256, true><<<nchains, 256, replay_grp_smem(L), s>>>(t, b, 1);
 }
