@@ -68,3 +68,30 @@ def test_gpu_statistics_feed_the_reference_second_pass(ref=None):
     e2 = ffv1_ref.Encoder(w, h, fmt, two_pass=2, stats_in=enc.stats_out(), **opts)
     assert e2.extradata.hex() == GOLD[cid]["pass2_extradata"]
     assert [[len(p), md5(p), int(k)] for p, k in (e2.encode(f) for f in frames)] == GOLD[cid]["pass2_packets"]
+
+def test_two_pass_at_level_4():
+    """both experimental features together (version 4 + statistics), RGB content, against the live reference build"""
+    from oracle import ffv1_ref, synth
+    if not ffv1_ref.available():
+        pytest.skip("reference build not present")
+    import ffv1_b200
+    w, h, fmt = 96, 80, "bgr0"
+    gen = synth.Noisy(w, h, fmt, 5)
+    frames = [gen.next() for _ in range(5)]
+    opts = dict(gop=3, level=4, coder=1, slices=4)
+    r1 = ffv1_ref.Encoder(w, h, fmt, two_pass=1, strict_experimental=1, **opts)
+    p1 = [r1.encode(f) for f in frames]
+    stats = r1.stats_out()
+    g1 = ffv1_b200.FFV1Encoder(w, h, fmt, max_batch_frames=4, flags=ffv1_b200.FLAG_PASS1, strict=-2, **gpu_opts(opts))
+    assert g1.extradata == r1.extradata and g1.encode_batch(frames) == p1 and g1.stats_out() == stats
+    r2 = ffv1_ref.Encoder(w, h, fmt, two_pass=2, stats_in=stats, strict_experimental=1, **opts)
+    g2 = ffv1_b200.FFV1Encoder(w, h, fmt, max_batch_frames=4, flags=ffv1_b200.FLAG_PASS2, stats_in=stats, strict=-2, **gpu_opts(opts))
+    assert g2.extradata == r2.extradata
+    got = g2.encode_batch(frames)
+    assert got == [r2.encode(f) for f in frames]
+    dec = ffv1_b200.FFV1Decoder(w, h, g2.extradata, max_batch_frames=5)
+    outs = dec.decode_batch([p for p, _ in got])
+    for i, f in enumerate(frames):
+        src = f.view(np.uint8).reshape(-1)
+        keep = np.ones(len(src), bool); keep[3::4] = False
+        assert np.array_equal(np.asarray(outs[i][0]).reshape(-1)[keep], src[keep])
