@@ -458,6 +458,10 @@ __global__ void __launch_bounds__(kScatterSmThreads) k_ctx_scatter_sm(const EncD
 constexpr int kTileSortThreads = 32 * (kTiledLines / 2);  // two lines of the tile per warp
 constexpr int kTileSortRows = kTileSortThreads / 64;      // per-warp context counts: two warps share a word
 
+// GOLOMB: Golomb-Rice mode -- only the samples that get a VLC code are listed (run mode absorbs zero residuals, ffv1enc.c:
+// 327-357; gr_run_members), an entry is the sample's record index inside the tile | its residual << 22 (the residual that
+// ends a run is coded minus one), and no decisions are counted.
+template <bool GOLOMB>
 __global__ void __launch_bounds__(kTileSortThreads) k_tile_sort(const EncDeviceTables T, const EncBatch B)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -480,6 +484,7 @@ __global__ void __launch_bounds__(kTileSortThreads) k_tile_sort(const EncDeviceT
     const int lpw = (ct.nlines + kTileSortThreads / 32 - 1) / (kTileSortThreads / 32);
     uint32_t *wh = s_wh + (warp >> 1) * nctx;
     const int sh = (warp & 1) * 16;
+    const uint32_t tile_rec0 = T.lines[g.line_first + my_lines[0]].rec_off;       // GOLOMB: record indices count from here
     {
         uint32_t nd = 0;
         for (int k = 0; k < lpw; k++) {
@@ -487,6 +492,17 @@ __global__ void __launch_bounds__(kTileSortThreads) k_tile_sort(const EncDeviceT
             if (li < ct.nlines) {
                 const LineDesc ld = T.lines[g.line_first + my_lines[li]];
                 const uint32_t *recp = rec_slice + ld.rec_off;
+                if (GOLOMB) {
+                    uint32_t carry = 0u;
+                    for (int x0 = 0; x0 < ld.w; x0 += 32) {
+                        const bool act = x0 + lane < ld.w;
+                        const uint32_t r = act ? recp[x0 + lane] : 0xFFFF0001u;
+                        const uint32_t zero = __ballot_sync(0xFFFFFFFFu, act && (r & 0xFFFFu) == 0u);
+                        const uint32_t ctx0 = __ballot_sync(0xFFFFFFFFu, act && (r >> 16) == 0u);
+                        const uint32_t mem = gr_run_members(ctx0, zero, carry);
+                        if (act && !((mem & zero) >> lane & 1u)) atomicAdd(&wh[r >> 16], 1u << sh);
+                    }
+                } else
                 for (int x = lane; x < ld.w; x += 32) {
                     const uint32_t r = recp[x];
                     nd += decisions_of((int)(int16_t)(r & 0xFFFFu));
@@ -541,19 +557,32 @@ __global__ void __launch_bounds__(kTileSortThreads) k_tile_sort(const EncDeviceT
             const LineDesc ld = T.lines[g.line_first + my_lines[li]];
             const uint32_t *recp = rec_slice + ld.rec_off;
             const int w = ld.w;
+            uint32_t gcarry = 0u;
             for (int x0 = 0; x0 < w; x0 += 32) {
-                const bool act = x0 + lane < w;
-                const uint32_t r = act ? recp[x0 + lane] : 0u;
+                bool act = x0 + lane < w;
+                uint32_t r = act ? recp[x0 + lane] : (GOLOMB ? 0xFFFF0001u : 0u);
+                if (GOLOMB) {
+                    const uint32_t zero = __ballot_sync(0xFFFFFFFFu, act && (r & 0xFFFFu) == 0u);
+                    const uint32_t ctx0 = __ballot_sync(0xFFFFFFFFu, act && (r >> 16) == 0u);
+                    const uint32_t mem = gr_run_members(ctx0, zero, gcarry);
+                    const bool inrun = (mem >> lane) & 1u;
+                    const int d = (int)(int16_t)(r & 0xFFFFu);
+                    if (inrun && d == 0) act = false;                         // absorbed into the run: no code, no list entry
+                    else if (inrun && d > 0) r = (r & 0xFFFF0000u) | (uint32_t)(d - 1);   // the residual that ends a run (ffv1enc.c:345-346)
+                }
                 const uint32_t ctx = r >> 16;
-                const uint32_t nd = act ? decisions_of((int)(int16_t)(r & 0xFFFFu)) : 0u;
-                const uint32_t in = cr_incl_scan(nd, lane);
+                const uint32_t nd = (act && !GOLOMB) ? decisions_of((int)(int16_t)(r & 0xFFFFu)) : 0u;
+                const uint32_t in = GOLOMB ? 0u : cr_incl_scan(nd, lane);
                 const uint32_t grp = __match_any_sync(0xFFFFFFFFu, act ? ctx : 0xFFFFFFFFu);
                 const uint32_t rank = __popc(grp & lt_mask);
                 uint32_t off = 0u;
                 if (act && rank == 0u) off = (atomicAdd(&wh[ctx], (uint32_t)__popc(grp) << sh) >> sh) & 0xFFFFu;
                 off = __shfl_sync(0xFFFFFFFFu, off, (__ffs(grp) - 1) & 31);
-                if (act) s_ent[(uint32_t)s_start[ctx] + off + rank] = (pos + in - nd) | (r << kGrpPosBits);
-                pos += __shfl_sync(0xFFFFFFFFu, in, 31);
+                if (act) {
+                    const uint32_t where = GOLOMB ? ld.rec_off - tile_rec0 + (uint32_t)(x0 + lane) : pos + in - nd;
+                    s_ent[(uint32_t)s_start[ctx] + off + rank] = where | (r << kGrpPosBits);
+                }
+                if (!GOLOMB) pos += __shfl_sync(0xFFFFFFFFu, in, 31);
             }
         }
     }
@@ -563,7 +592,8 @@ __global__ void __launch_bounds__(kTileSortThreads) k_tile_sort(const EncDeviceT
     const int f0 = B.seg_first[seg], seglen = B.seg_first[seg + 1] - f0;
     uint32_t *dst = reinterpret_cast<uint32_t *>(B.lists) + (size_t)f0 * L.samples_per_frame + (size_t)seglen * g.list_off[ct.pc] +
                     (size_t)(f - f0) * g.pc_samples[ct.pc] + ct.sample_first;
-    for (uint32_t i = tid; i < ct.nsamples; i += kTileSortThreads) dst[i] = s_ent[i];
+    const uint32_t nent = GOLOMB ? (uint32_t)s_start[nctx] : ct.nsamples;
+    for (uint32_t i = tid; i < nent; i += kTileSortThreads) dst[i] = s_ent[i];
     uint16_t *tab = B.tile_tab + ((size_t)f * L.ctiles_per_frame + tile) * B.tile_tab_pitch;
     for (int i = tid; i <= nctx; i += kTileSortThreads) tab[i] = s_start[i];
 }
@@ -1103,8 +1133,11 @@ cudaError_t configure_ctx_replay(const Layout &L)
         if (e != cudaSuccess) return e;
         return cudaFuncSetAttribute(k_ctx_scatter<0, 13>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx_scatter_smem_bytes(L));
     }
-    if (L.tiled_lists)
-        return cudaFuncSetAttribute(k_tile_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_sort_smem(L, (L.ctx_count + 8) & ~7));
+    if (L.tiled_lists) {
+        e = cudaFuncSetAttribute(k_tile_sort<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_sort_smem(L, (L.ctx_count + 8) & ~7));
+        if (e != cudaSuccess) return e;
+        return cudaFuncSetAttribute(k_tile_sort<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_sort_smem(L, (L.ctx_count + 8) & ~7));
+    }
     e = cudaFuncSetAttribute(k_ctx_scatter_sm<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx_scatter_sm_smem_bytes(L));
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_ctx_scatter_sm<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx_scatter_sm_smem_bytes(L, 1));
@@ -1119,7 +1152,7 @@ cudaError_t configure_ctx_replay(const Layout &L)
 // Golomb-Rice mode: per-context lists of the samples that get a VLC code ({record index, residual | frame << 16})
 bool golomb_lists_supported(const Layout &L, int max_tile_samples)
 {
-    return L.golomb && L.ctx_count <= kMaxListCtx && max_tile_samples <= kScatterSmMaxSamples &&
+    return L.golomb && L.ctx_count <= kMaxListCtx && (L.tiled_lists || max_tile_samples <= kScatterSmMaxSamples) &&
            (unsigned long long)L.rec_per_frame * 2ull <= L.dec_per_frame;
 }
 
@@ -1128,6 +1161,10 @@ void launch_golomb_lists(const EncDeviceTables &t, const EncBatch &b, cudaStream
     const Layout &L = t.layout;
     const int nchains = b.nseg * L.nslices * L.npc;
     dim3 tiles(L.ctiles_per_frame, b.nframes);
+    if (L.tiled_lists) {            // tile-sorted lists: k_gr_replay<TILED> walks them tile after tile
+        k_tile_sort<true><<<tiles, kTileSortThreads, tile_sort_smem(L, b.tile_tab_pitch), s>>>(t, b);
+        return;
+    }
     k_ctx_hist<true><<<tiles, kHistThreads, L.ctx_count * 4, s>>>(t, b);
     k_ctx_scan<<<nchains, kScanThreads, L.ctx_count * 8, s>>>(t, b);
     k_ctx_scatter_sm<true, 0><<<tiles, kScatterSmThreads, ctx_scatter_sm_smem_bytes(L), s>>>(t, b);
@@ -1139,7 +1176,7 @@ static void launch_tiled_replay(const EncDeviceTables &t, const EncBatch &b, int
     const Layout &L = t.layout;
     dim3 tiles(L.ctiles_per_frame, b.nframes);
     const int n = b.nframes * L.nslices * L.npc;
-    k_tile_sort<<<tiles, kTileSortThreads, tile_sort_smem(L, b.tile_tab_pitch), s>>>(t, b);
+    k_tile_sort<false><<<tiles, kTileSortThreads, tile_sort_smem(L, b.tile_tab_pitch), s>>>(t, b);
     k_tile_layout<<<(n + 127) / 128, 128, 0, s>>>(t, b);
     int threads = 256;
     if (const char *v = getenv("FFV1B200_REPLAY_THREADS")) threads = atoi(v);

@@ -1058,8 +1058,44 @@ constexpr int kGrSlots = 8;               // context lists per lane (ctx_count <
 // bases staged in shared memory) so that the code words it scatters into the code array land in a stretch that is
 // completed while it is still in L2 -- with every lane running through its whole list at its own pace each 4-byte
 // store was a read-modify-write of a DRAM sector.
-__global__ void __launch_bounds__(kGrThreads, 8) k_gr_replay(const EncDeviceTables T, const EncBatch B, const int window)
+// put_vlc_symbol + set_sr_golomb (ffv1enc.c:240-269, golomb.h:554-563) and update_vlc_state (ffv1.h:192-224) for one
+// sample, branch-free: the lanes of a warp run different lists, and the longest list of the chain is the critical path
+// of the CTA.  Writes the code word value | length << 26.
+__device__ __forceinline__ void gr_code_one(uint32_t *dst, int v, int bits, int &drift, int &esum, int &bias, int &count)
 {
+    const int cn = count, es = esum;
+    v = ((v - bias) << (32 - bits)) >> (32 - bits);      // fold
+    // k = smallest k with (count << k) >= error_sum: floor-log2 difference, plus one if that falls short
+    const int t = max(__clz(cn) - __clz(es), 0);
+    const int k = es > cn ? t + (((uint32_t)cn << t) < (uint32_t)es ? 1 : 0) : 0;
+    const int cd = v ^ ((2 * drift + cn) >> 31);
+    int m = -2 * cd - 1;
+    m ^= m >> 31;
+    const int e = m >> k;
+    const bool esc = e >= 12;
+    const uint32_t len = esc ? (uint32_t)(12 + bits) : (uint32_t)(e + k + 1);
+    const uint32_t val = esc ? (uint32_t)(m - 11) : (1u << k) + ((uint32_t)m & ((1u << k) - 1u));
+    *dst = val | (len << 26);
+    int d2 = drift + v, e2 = es + abs(v), c2 = cn;
+    const int half = cn == 128 ? 1 : 0;
+    c2 >>= half; d2 >>= half; e2 >>= half;
+    c2++;
+    const bool neg = d2 <= -c2, pos = d2 > 0;
+    int b2 = bias + (pos ? 1 : 0) - (neg ? 1 : 0);
+    b2 = max(-128, min(127, b2));
+    d2 += neg ? c2 : (pos ? -c2 : 0);
+    if (neg) d2 = max(d2, -c2 + 1);
+    if (pos) d2 = min(d2, 0);
+    drift = d2; esum = e2; count = c2; bias = b2;
+}
+
+// TILED (Layout::tiled_lists, ffv1_ctx_replay.cu:k_tile_sort<GOLOMB>): the lists are kept tile by tile -- a window is one
+// tile, a list's part of it is the context's run inside the tile's block (4-byte entries: record index inside the
+// tile | residual << 22), and the lane <-> context assignment is by how often the contexts occur in the chain's first frame.
+template <bool TILED>
+__global__ void __launch_bounds__(kGrThreads, 8) k_gr_replay(const EncDeviceTables T, const EncBatch B, const int window_rt)
+{
+    const int window = TILED ? 1 : window_rt;
     extern __shared__ __align__(16) uint32_t s_gr[];                        // [2][nctx] the window's part of every list
     const Layout &L = T.layout;
     const int tid = threadIdx.x;
@@ -1075,7 +1111,30 @@ __global__ void __launch_bounds__(kGrThreads, 8) k_gr_replay(const EncDeviceTabl
     const size_t sbase = ((size_t)s * L.npc + pc) * (pc_bytes / 8);
     const bool key = B.frame_key[f0] != 0;
     const int bits = L.coded_bits;
-    // my lists: contexts order[tid], order[tid + 256], ... (the order is by decreasing list length)
+    const int t0 = g.ct_first[pc], nt = g.ct_count[pc];
+    uint16_t *s_ord = reinterpret_cast<uint16_t *>(s_b1);                       // TILED: contexts by decreasing frequency (set-up only)
+    if (TILED) {
+        for (int i = tid; i < nctx; i += kGrThreads) {
+            uint32_t n = 0;
+            for (int tt = 0; tt < nt; tt++) {
+                const uint16_t *tab = B.tile_tab + ((size_t)f0 * L.ctiles_per_frame + t0 + tt) * B.tile_tab_pitch;
+                n += (uint32_t)tab[i + 1] - (uint32_t)tab[i];
+            }
+            s_b0[i] = n;
+        }
+        __syncthreads();
+        for (int c = tid; c < nctx; c += kGrThreads) {
+            const uint32_t mine = s_b0[c];
+            int rank = 0;
+            for (int o = 0; o < nctx; o++) {
+                const uint32_t v = s_b0[o];
+                rank += (v > mine) || (v == mine && o < c);
+            }
+            s_ord[rank] = (uint16_t)c;
+        }
+        __syncthreads();
+    }
+    // my lists: contexts order[tid], order[tid + 128], ... (the order is by decreasing list length)
     int ctx[kGrSlots], drift[kGrSlots], esum[kGrSlots], bias[kGrSlots], count[kGrSlots];
     uint32_t lstart[kGrSlots];
 #pragma unroll
@@ -1083,9 +1142,9 @@ __global__ void __launch_bounds__(kGrThreads, 8) k_gr_replay(const EncDeviceTabl
         const int oi = tid + j * kGrThreads;
         ctx[j] = -1; drift[j] = 0; esum[j] = 4; bias[j] = 0; count[j] = 1; lstart[j] = 0u;   // {0,4,0,1} on keyframes (ffv1.c:194-199)
         if (oi < nctx) {
-            const int c = B.list_order[(size_t)chain * nctx + oi];
+            const int c = TILED ? (int)s_ord[oi] : (int)B.list_order[(size_t)chain * nctx + oi];
             ctx[j] = c;
-            lstart[j] = B.list_start[(size_t)chain * nctx + c];
+            if (!TILED) lstart[j] = B.list_start[(size_t)chain * nctx + c];
             if (!key) {
                 const uint2 v = reinterpret_cast<const uint2 *>(B.carry_in)[sbase + c];
                 drift[j] = (int)(int16_t)(v.x & 0xFFFFu); esum[j] = (int)(v.x >> 16);
@@ -1094,22 +1153,51 @@ __global__ void __launch_bounds__(kGrThreads, 8) k_gr_replay(const EncDeviceTabl
         }
     }
     const size_t code_frame = L.dec_per_frame / 2;                          // 32-bit words per frame in the code array
-    const int t0 = g.ct_first[pc], nt = g.ct_count[pc];
+    const uint32_t *chain_list32 = reinterpret_cast<const uint32_t *>(B.lists) + (size_t)f0 * L.samples_per_frame + (size_t)(f1 - f0) * g.list_off[pc];
+    __syncthreads();                                                        // (TILED: s_ord is read by everybody before s_b1 is reused)
     for (int f = f0; f < f1; f++) {
         uint32_t *code = reinterpret_cast<uint32_t *>(B.dec) + (size_t)f * code_frame + g.rec_first;
         for (int tw = 0; tw < nt; tw += window) {
             __syncthreads();                                                // everybody is done with the previous window's bounds
             const bool last_win = tw + window >= nt;
+            const uint32_t *blk = chain_list32;
+            uint32_t *code_w = code;
+            if (TILED) {
+                const CtxTile ct = T.ctiles[t0 + tw];
+                const uint16_t *tab = B.tile_tab + ((size_t)f * L.ctiles_per_frame + t0 + tw) * B.tile_tab_pitch;
+                for (int i = tid; i < nctx; i += kGrThreads) { s_b0[i] = tab[i]; s_b1[i] = tab[i + 1]; }
+                blk = chain_list32 + (size_t)(f - f0) * g.pc_samples[pc] + ct.sample_first;
+                // the tile's record indices count from its first line
+                code_w = code + T.lines[g.line_first + T.pc_lines[g.pc_line_first[pc] + ct.first]].rec_off;
+            } else {
             const uint32_t *bf = B.ctx_hist + ((size_t)f * L.ctiles_per_frame + t0 + tw) * nctx;
             const uint32_t *bn = last_win ? B.ctx_hist + ((size_t)(f + 1) * L.ctiles_per_frame + t0) * nctx
                                           : B.ctx_hist + ((size_t)f * L.ctiles_per_frame + t0 + tw + window) * nctx;
             const bool use_bn = !last_win || f + 1 < f1;
             for (int i = tid; i < nctx; i += kGrThreads) { s_b0[i] = bf[i]; s_b1[i] = use_bn ? bn[i] : lcount[i]; }
+            }
             __syncthreads();
 #pragma unroll
             for (int j = 0; j < kGrSlots; j++) {
                 if (ctx[j] < 0) continue;
                 const uint32_t b0 = s_b0[ctx[j]], b1 = s_b1[ctx[j]];
+                if (TILED) {
+                    // same walk over 4-byte entries of the tile's block
+                    uint32_t nxt[4];
+#pragma unroll
+                    for (int q = 0; q < 4; q++) nxt[q] = b0 + q < b1 ? blk[b0 + q] : 0u;
+                    for (uint32_t i = b0; i < b1; i += 4u) {
+                        uint32_t cur[4];
+#pragma unroll
+                        for (int q = 0; q < 4; q++) { cur[q] = nxt[q]; if (i + 4u + q < b1) nxt[q] = blk[i + 4u + q]; }
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            if (i + q >= b1) break;
+                            gr_code_one(code_w + (cur[q] & 0x3FFFFFu), (int)cur[q] >> 22, bits, drift[j], esum[j], bias[j], count[j]);
+                        }
+                    }
+                    continue;
+                }
                 const uint2 *lp = chain_list + lstart[j];
                 // four entries per round, the next round's loads in flight while this one is coded: with ~2000 lists
                 // streaming per SM the lines do not survive in L1, so every load is an L2 (or DRAM) round trip
@@ -1124,34 +1212,7 @@ __global__ void __launch_bounds__(kGrThreads, 8) k_gr_replay(const EncDeviceTabl
                     for (int q = 0; q < 4; q++) {
                         if (i + q >= b1) break;
                         const uint2 en = cur[q];
-                        int v = (int)(int16_t)(en.y & 0xFFFFu);
-                        // put_vlc_symbol + set_sr_golomb (ffv1enc.c:240-269, golomb.h:554-563), branch-free: the lanes of a
-                        // warp run different lists, and the longest list of the chain is the critical path of the CTA
-                        const int cn = count[j], es = esum[j];
-                        v = ((v - bias[j]) << (32 - bits)) >> (32 - bits);      // fold
-                        // k = smallest k with (count << k) >= error_sum: floor-log2 difference, plus one if that falls short
-                        const int t = max(__clz(cn) - __clz(es), 0);
-                        const int k = es > cn ? t + (((uint32_t)cn << t) < (uint32_t)es ? 1 : 0) : 0;
-                        const int cd = v ^ ((2 * drift[j] + cn) >> 31);
-                        int m = -2 * cd - 1;
-                        m ^= m >> 31;
-                        const int e = m >> k;
-                        const bool esc = e >= 12;
-                        const uint32_t len = esc ? (uint32_t)(12 + bits) : (uint32_t)(e + k + 1);
-                        const uint32_t val = esc ? (uint32_t)(m - 11) : (1u << k) + ((uint32_t)m & ((1u << k) - 1u));
-                        code[en.x] = val | (len << 26);
-                        // update_vlc_state (ffv1.h:192-224)
-                        int d2 = drift[j] + v, e2 = es + abs(v), c2 = cn;
-                        const int half = cn == 128 ? 1 : 0;
-                        c2 >>= half; d2 >>= half; e2 >>= half;
-                        c2++;
-                        const bool neg = d2 <= -c2, pos = d2 > 0;
-                        int b2 = bias[j] + (pos ? 1 : 0) - (neg ? 1 : 0);
-                        b2 = max(-128, min(127, b2));
-                        d2 += neg ? c2 : (pos ? -c2 : 0);
-                        if (neg) d2 = max(d2, -c2 + 1);
-                        if (pos) d2 = min(d2, 0);
-                        drift[j] = d2; esum[j] = e2; count[j] = c2; bias[j] = b2;
+                        gr_code_one(code + en.x, (int)(int16_t)(en.y & 0xFFFFu), bits, drift[j], esum[j], bias[j], count[j]);
                     }
                 }
             }
@@ -1336,7 +1397,8 @@ void launch_golomb_coder(const EncDeviceTables &t, const EncBatch &b, cudaStream
     const Layout &L = t.layout;
     int window = 3;
     if (const char *v = getenv("FFV1B200_GOLOMB_WINDOW")) { window = atoi(v); if (window < 1) window = 1 << 20; }
-    k_gr_replay<<<b.nseg * L.nslices * L.npc, kGrThreads, 2 * L.ctx_count * sizeof(uint32_t), s>>>(t, b, window);
+    if (L.tiled_lists) k_gr_replay<true><<<b.nseg * L.nslices * L.npc, kGrThreads, 2 * L.ctx_count * sizeof(uint32_t), s>>>(t, b, 1);
+    else k_gr_replay<false><<<b.nseg * L.nslices * L.npc, kGrThreads, 2 * L.ctx_count * sizeof(uint32_t), s>>>(t, b, window);
     k_gr_pack<<<(b.nframes * L.nslices + kGrPackWarps - 1) / kGrPackWarps, 32 * kGrPackWarps, 0, s>>>(t, b);
 }
 
