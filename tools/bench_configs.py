@@ -7,7 +7,7 @@ own CPU encoder on the same options and the same clip (one JSON line per configu
   c4   configs[3]  3840x2160 gbrp14le (the legal stand-in for RGB48), GOP 16, coder=2, 30 slices   -- clip S4
   gr   configs[1]'s clip with coder=0: Golomb-Rice / run mode, the reference's default for 8-bit content
 
-usage: bench_configs.py [c3|c4|gr ...] [--frames N] [--steps K]
+usage: bench_configs.py [c3|c4|gr|p10 ...] [--frames N] [--steps K]
 value = frames resident in HBM (CUDA events); e2e = pinned host frames -> host packets through submit_host/collect_async.
 The packets of these configurations are compared with the oracle at full size by tests/test_gpu_encode.py
 (test_full_size_configs); here the stream is only decoded back by the CUDA decoder (first GOP, bit-exact round trip)."""
@@ -22,6 +22,20 @@ def clip_s3(n):
     rng = np.random.default_rng(1235)
     yy, xx = np.mgrid[0:H, 0:W]
     cx, cy = xx[:, ::2], yy[:, ::2]
+    out = []
+    for k in range(n):
+        Y = np.clip(4 * ((0.1 * xx + 0.07 * yy + 1.5 * k) % 256) + rng.normal(0, 8, (H, W)), 0, 1023)
+        U = np.clip(512 + 80 * np.sin((cx + 3 * k) / 97) + rng.normal(0, 6, cx.shape), 0, 1023)
+        V = np.clip(512 + 80 * np.cos((cy + 2 * k) / 71) + rng.normal(0, 6, cy.shape), 0, 1023)
+        out.append(np.concatenate([p.astype("<u2").ravel() for p in (Y, U, V)]).view(np.uint8))
+    return np.stack(out)
+
+def clip_p10(n):
+    """S2's formulas at 10 bits, 4:2:0, seed 1237 (planes uint16 little endian): 1080p yuv420p10le, the small context model"""
+    W, H = 1920, 1080
+    rng = np.random.default_rng(1237)
+    yy, xx = np.mgrid[0:H, 0:W]
+    cx, cy = xx[::2, ::2], yy[::2, ::2]
     out = []
     for k in range(n):
         Y = np.clip(4 * ((0.1 * xx + 0.07 * yy + 1.5 * k) % 256) + rng.normal(0, 8, (H, W)), 0, 1023)
@@ -54,6 +68,8 @@ CONFIGS = {
                what="BASELINE configs[2]: 1080p yuv422p10, GOP 16, coder 0 requested (range coder forced), context=1, 4 slices"),
     "c4": dict(w=3840, h=2160, fmt="gbrp14le", opts=dict(level=3, coder=2, context=0, slices=30), clip=clip_s4, nclip=4, frames=64,
                what="BASELINE configs[3]: 2160p gbrp14le (RCT, 15-bit residuals), GOP 16, coder=2, 30 slices"),
+    "p10": dict(w=1920, h=1080, fmt="yuv420p10le", opts=dict(level=3, coder=1, context=0, slices=24), clip=clip_p10, nclip=16, frames=512,
+                what="1080p yuv420p10le, GOP 16, range coder, context=0 (666 contexts), 24 slices: the 10-bit sibling of configs[1]"),
     "gr": dict(w=1920, h=1080, fmt="yuv420p", opts=dict(level=3, coder=0, context=0, slices=24), clip=clip_s2, nclip=32, frames=1024,
                what="configs[1]'s clip with coder=0: Golomb-Rice / run mode, 24 slices"),
 }
