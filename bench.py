@@ -321,6 +321,7 @@ def main():
             enc2.submit(table)
             enc2.collect(out=host_out[i & 1], copy=False)
         barrier()
+        se0 = enc2.stats()
         t0 = time.perf_counter()
         enc2.submit(table)
         for i in range(args.steps - 1):
@@ -331,9 +332,12 @@ def main():
         torch.cuda.synchronize(dev)
         dt = max_over_ranks(time.perf_counter() - t0)
         parity_e2e = check_packets(gold, clip_ok, lambda i: (last[pk2[i].offset:pk2[i].offset + pk2[i].size].tobytes(), pk2[i].flags & 1), tail)
+        se1 = enc2.stats()
         d2h_step = int(sum(p.size for p in pk2)) + 12 * B + 72
         e2e = {"value": world * B * args.steps / dt, "unit": "frames/s", "h2d_bytes_per_step": B * FRAME_BYTES,
                "d2h_bytes_per_step": d2h_step, "numa_node": numa_node,
+               "kernels_ms_per_step": {k: (getattr(se1, "ms_" + k + "_kernel") - getattr(se0, "ms_" + k + "_kernel")) / args.steps
+                                       for k in ("pixel", "model", "coder", "pack")},
                "note": "ffv1b200_enc_submit_host / _collect_async: pinned host frames -> packets in pinned host memory, two "
                        "batches in flight (H2D of batch k+2, kernels of k+1 and D2H of k overlap), wall clock over all steps "
                        "incl. every copy, max over ranks"}

@@ -24,8 +24,8 @@
 using namespace ffv1;
 
 namespace {
-constexpr int kSlots = 2;       // batches in flight (three were measured: the copies of a third batch slow the kernels of the
-                                // others down more than they hide: e2e 9.1 k -> 8.4 k frames/s on one GPU)
+constexpr int kSlots = 2;       // batches in flight: H2D of batch k+2, kernels of k+1 and D2H of k overlap; in steady state that
+                                // already runs at min(kernel rate, link rate), a third slot only costs 10 GB
 constexpr int kCarry = 4;       // ring of model-state buffers: batch k reads [k % 4] and writes [(k+1) % 4]
 
 struct Slot {
