@@ -22,7 +22,10 @@ def run(args, rank, local_rank, world, dev, dist, barrier, max_over_ranks, clip,
     ranges = gop_aligned_ranges(T, GOP, world)
     start, count = ranges[rank]
     aligned = T % GOP == 0
-    Bmax = max(GOP, min(count, args.batch) // GOP * GOP) if count >= GOP else max(1, count)
+    # batches of equal size (whole GOPs): a 2400-frame range goes as 1200 + 1200, not 2048 + 352 -- the stages that are bound
+    # by the length of a chain (k_rangecode, the replay, the decoder) take as long for 352 frames as for 1200
+    nb = max(1, -(-count // max(GOP, args.batch // GOP * GOP)))
+    Bmax = max(GOP, -(-(-(-count // nb)) // GOP) * GOP) if count >= GOP else max(1, count)
     steps, warmup = args.steps, args.warmup
     sampler = ClockSampler(local_rank) if rank == 0 else None
 
@@ -130,7 +133,7 @@ def run(args, rank, local_rank, world, dev, dist, barrier, max_over_ranks, clip,
     # ------------------------------------------------------------ decode of the rank's own range (starts on a keyframe)
     dec_line = None
     if not args.no_decode:
-        dbatch = max(1, min(count, args.batch))
+        dbatch = max(1, min(count, Bmax))
         dec = ffv1_b200.FFV1Decoder(W, H, extradata, device=local_rank, max_batch_frames=dbatch)
         frames_out = torch.empty((max(count, 1), FB), dtype=torch.uint8, pin_memory=True)
         fo = frames_out.numpy().reshape(-1)
