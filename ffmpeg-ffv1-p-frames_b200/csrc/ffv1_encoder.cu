@@ -398,6 +398,7 @@ static EncOptions options_of(const FFV1B200EncParams *p)
     if (p->flags & FFV1B200_FLAG_PASS2) o.pass_flags |= kPass2;
     if (p->stats_in) o.stats_in = p->stats_in;
     o.strict_experimental = p->strict_std_compliance <= -2;
+    o.bits_per_raw_sample = p->bits_per_raw_sample;
     return o;
 }
 

@@ -293,6 +293,15 @@ int resolve_encoder(const EncOptions &o, Config &c, std::string &err)
     c.width = o.width; c.height = o.height;
     if (!parse_pix_fmt(o.pix_fmt, c)) { err = "format not supported"; return FFV1B200_ERR_ENOSYS; }        // ffv1enc.c:816-818
 
+    // a caller-set bits_per_raw_sample replaces the depth of 16-bit containers (ffv1enc.c:728-748, 796-805); 8-bit planar
+    // formats ignore it, and packed RGB would trip the reference's av_assert0(bits_per_raw_sample >= 8)
+    if (o.bits_per_raw_sample) {
+        if (c.bits > 8) {
+            if (o.bits_per_raw_sample <= 8 || o.bits_per_raw_sample > 16) { err = "bits_per_raw_sample invalid"; return FFV1B200_ERR_INVALIDDATA; }
+            c.bits = o.bits_per_raw_sample;
+        } else if (c.colorspace == 1) { err = "bits_per_raw_sample cannot be set for packed RGB"; return FFV1B200_ERR_EINVAL; }
+    }
+
     // version selection, ffv1enc.c:676-706
     int version = 0;
     if (o.slices > 1 || (o.pass_flags & (kPass1 | kPass2))) version = 2;

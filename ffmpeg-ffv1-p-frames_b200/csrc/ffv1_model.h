@@ -150,6 +150,8 @@ struct EncOptions {
     int pass_flags = 0;          // kPass1: collect statistics; kPass2 (or any stats_in): code with the tables derived from them
     std::string stats_in;        // AVCodecContext.stats_in: the text a first pass left in stats_out
     int strict_experimental = 0; // AVCodecContext.strict_std_compliance <= FF_COMPLIANCE_EXPERIMENTAL
+    int bits_per_raw_sample = 0; // AVCodecContext.bits_per_raw_sample: 0 = the format's depth; else the depth coded for 16-bit
+                                 // containers (ffv1enc.c:728-748, 796-805)
 };
 
 // encode_init: returns 0 or a negative AVERROR-style code with a message in err

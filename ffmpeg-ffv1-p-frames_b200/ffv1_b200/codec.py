@@ -18,7 +18,8 @@ class _EncParams(ctypes.Structure):
                 ("gop_size", ctypes.c_int), ("level", ctypes.c_int), ("slices", ctypes.c_int),
                 ("coder", ctypes.c_int), ("context", ctypes.c_int), ("slicecrc", ctypes.c_int),
                 ("device", ctypes.c_int), ("max_batch_frames", ctypes.c_int), ("first_picture_number", ctypes.c_int64),
-                ("flags", ctypes.c_int), ("stats_in", ctypes.c_char_p), ("strict_std_compliance", ctypes.c_int)]
+                ("flags", ctypes.c_int), ("stats_in", ctypes.c_char_p), ("strict_std_compliance", ctypes.c_int),
+                ("bits_per_raw_sample", ctypes.c_int)]
 
 FLAG_PASS1, FLAG_PASS2 = 1 << 9, 1 << 10      # AV_CODEC_FLAG_PASS1 / _PASS2
 
@@ -140,11 +141,13 @@ def plane_shapes(pix_fmt, w, h):
 def frame_bytes(pix_fmt, w, h):
     return sum(r * b for r, b in plane_shapes(pix_fmt, w, h))
 
-def resolve_encoder(width, height, pix_fmt, g=12, level=-1, coder=0, context=0, slices=0, slicecrc=-1, flags=0, stats_in=None, strict=0):
+def resolve_encoder(width, height, pix_fmt, g=12, level=-1, coder=0, context=0, slices=0, slicecrc=-1, flags=0, stats_in=None, strict=0,
+                    bits_per_raw_sample=0):
     """encode_init's host half (no GPU needed): returns (info, extradata) or raises FFV1Error like FFV1Encoder would"""
     if isinstance(stats_in, str):
         stats_in = stats_in.encode()
-    p = _EncParams(width, height, pix_fmt.encode(), g, level, slices, coder, context, slicecrc, 0, 0, 0, flags, stats_in, strict)
+    p = _EncParams(width, height, pix_fmt.encode(), g, level, slices, coder, context, slicecrc, 0, 0, 0, flags, stats_in, strict,
+                   bits_per_raw_sample)
     info, n = _EncInfo(), ctypes.c_int()
     L = lib()
     L.ffv1b200_enc_resolve.argtypes = [ctypes.POINTER(_EncParams), ctypes.POINTER(_EncInfo), ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
@@ -156,13 +159,13 @@ class FFV1Encoder:
     """Mirror of ff_ffv1_encoder (ffv1enc.c:1415-1444): __init__ = init, encode2/flush = encode2 (CAP_DELAY), close."""
 
     def __init__(self, width, height, pix_fmt, g=12, level=-1, coder=0, context=0, slices=0, slicecrc=-1,
-                 device=0, max_batch_frames=64, first_picture_number=0, flags=0, stats_in=None, strict=0):
+                 device=0, max_batch_frames=64, first_picture_number=0, flags=0, stats_in=None, strict=0, bits_per_raw_sample=0):
         self._h = ctypes.c_void_p()
         self.width, self.height, self.pix_fmt = width, height, pix_fmt
         if isinstance(stats_in, str):
             stats_in = stats_in.encode()
         p = _EncParams(width, height, pix_fmt.encode(), g, level, slices, coder, context, slicecrc, device,
-                       max_batch_frames, first_picture_number, flags, stats_in, strict)
+                       max_batch_frames, first_picture_number, flags, stats_in, strict, bits_per_raw_sample)
         _check(lib().ffv1b200_enc_open(ctypes.byref(self._h), ctypes.byref(p)))
         self.info = _EncInfo()
         _check(lib().ffv1b200_enc_info(self._h, ctypes.byref(self.info)))

@@ -65,6 +65,8 @@ typedef struct FFV1B200EncParams {
                                  (ffv1enc.c:680, 898-986, 1013-1027); 0 = single pass */
     const char *stats_in;     /* AVCodecContext.stats_in: the first pass's statistics text (ffv1b200_enc_stats_out), or NULL */
     int strict_std_compliance;/* AVCodecContext.strict_std_compliance; <= -2 (FF_COMPLIANCE_EXPERIMENTAL) unlocks level 4 */
+    int bits_per_raw_sample;  /* AVCodecContext.bits_per_raw_sample: 0 = the pix_fmt's depth; for formats in 16-bit containers the
+                                 depth that is coded instead (ffv1enc.c:728-748, 796-805), e.g. 12 for gbrp14le frames holding 12 bits */
 } FFV1B200EncParams;
 
 #define FFV1B200_FLAG_PASS1 (1 << 9)             /* = AV_CODEC_FLAG_PASS1 */

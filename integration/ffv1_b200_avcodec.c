@@ -403,6 +403,7 @@ static av_cold int b200_encode_init(AVCodecContext *avctx)
     p.flags = avctx->flags & (AV_CODEC_FLAG_PASS1 | AV_CODEC_FLAG_PASS2);
     p.stats_in = avctx->stats_in;
     p.strict_std_compliance = avctx->strict_std_compliance;
+    p.bits_per_raw_sample = avctx->bits_per_raw_sample;
     if ((ret = ffv1b200_enc_open(&s->enc, &p)) < 0)
         return b200_err(avctx, ret);
     /* from here on every failure goes through b200_encode_close (this codec cannot set the internal

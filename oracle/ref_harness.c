@@ -43,6 +43,8 @@ static void *enc_open_impl(AVCodec *codec, int w, int h, const char *pix_fmt, in
                            int slices, int slicecrc, int threads, int strict_experimental, int batch);
 static int g_pass;
 static const char *g_stats_in;
+static int g_bits;                       /* AVCodecContext.bits_per_raw_sample of the next encoder that is opened */
+void ffv1ref_set_next_bits_per_raw_sample(int bits) { g_bits = bits; }
 
 
 void *ffv1ref_enc_open(int w, int h, const char *pix_fmt, int gop, int level, int coder, int context,
@@ -122,6 +124,7 @@ static void *enc_open_impl(AVCodec *codec, int w, int h, const char *pix_fmt, in
     e->ctx->slices = slices;
     e->ctx->flags |= AV_CODEC_FLAG_BITEXACT;
     if (strict_experimental) e->ctx->strict_std_compliance = FF_COMPLIANCE_EXPERIMENTAL;
+    if (g_bits) { e->ctx->bits_per_raw_sample = g_bits; g_bits = 0; }
     if (g_pass == 1) e->ctx->flags |= AV_CODEC_FLAG_PASS1;
     if (g_pass == 2) e->ctx->flags |= AV_CODEC_FLAG_PASS2;
     if (g_stats_in) e->ctx->stats_in = av_strdup(g_stats_in);

@@ -251,3 +251,19 @@ def test_full_size_configs(B, case):
     out = d.decode_batch([p for p, _ in got])
     for i, f in enumerate(frames):
         assert np.array_equal(out[i][0], np.ascontiguousarray(f).view(np.uint8).reshape(-1)), "decoded frame %d differs" % i
+
+@pytest.mark.parametrize("fmt,bits,maxval", [("gbrp14le", 12, 4095), ("gbrp14le", 10, 1023), ("yuv420p16le", 12, 65535), ("yuv444p10le", 9, 511)])
+def test_caller_set_bits_per_raw_sample(B, fmt, bits, maxval):
+    """AVCodecContext.bits_per_raw_sample replaces the depth of formats in 16-bit containers (ffv1enc.c:728-748, 796-805):
+    extradata and packets against the live reference build"""
+    from oracle import ffv1_ref, synth
+    if not ffv1_ref.available():
+        pytest.skip("reference build not present")
+    w, h = 96, 80
+    frames = [synth.random_frame(w, h, fmt, 300 + i, maxval=maxval) for i in range(3)]
+    L = ffv1_ref.lib()
+    L.ffv1ref_set_next_bits_per_raw_sample(bits)
+    r = ffv1_ref.Encoder(w, h, fmt, gop=2, level=3, coder=1, slices=4)
+    g = B.FFV1Encoder(w, h, fmt, g=2, level=3, coder=1, slices=4, max_batch_frames=3, bits_per_raw_sample=bits)
+    assert g.extradata == r.extradata and g.info.bits_per_raw_sample == bits
+    assert g.encode_batch(frames) == [r.encode(f) for f in frames]
