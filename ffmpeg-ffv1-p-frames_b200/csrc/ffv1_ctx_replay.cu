@@ -54,7 +54,8 @@ __device__ __forceinline__ uint32_t same_key_lanes(uint32_t key, uint32_t active
 
 __device__ __forceinline__ uint32_t decisions_of(int d)
 {
-    return d ? (uint32_t)(2 * (31 - __clz((uint32_t)abs(d))) + 3) : 1u;       // put_symbol_inline: 1 or 2e+3
+    // put_symbol_inline: 1 decision for 0, else 2e+3 with e = floor(log2 |d|); branch-free: clz(0) = 32 gives 2*(-1)+3 = 1
+    return (uint32_t)(65 - 2 * __clz((uint32_t)abs(d)));
 }
 
 // Golomb-Rice mode (ffv1enc.c:327-357): which of the 32 samples of a group are coded in run mode.  Run mode starts at a
@@ -446,6 +447,23 @@ __global__ void __launch_bounds__(kScatterSmThreads) k_ctx_scatter_sm(const EncD
     }
 }
 
+// shared-memory accesses through 32-bit addresses kept in registers (the compiler otherwise rebuilds the shared-window
+// address, cluster rank included, at every atomic)
+__device__ __forceinline__ void sm_red_add(uint32_t addr, uint32_t v) { asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t sm_atom_add(uint32_t addr, uint32_t v)
+{
+    uint32_t old;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(v) : "memory");
+    return old;
+}
+__device__ __forceinline__ void sm_st32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t sm_ld16(uint32_t addr)
+{
+    uint16_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr) : "memory");
+    return v;
+}
+
 // ------------------------------------------------------------------------------------------------ k_tile_sort
 // Tile-sorted lists (Layout::tiled_lists).  The chain-wide lists above need the position of every tile inside every
 // list before a single entry can be placed: a histogram pass over all records and a scan along every chain.  Here a
@@ -484,6 +502,9 @@ __global__ void __launch_bounds__(kTileSortThreads) k_tile_sort(const EncDeviceT
     const int lpw = (ct.nlines + kTileSortThreads / 32 - 1) / (kTileSortThreads / 32);
     uint32_t *wh = s_wh + (warp >> 1) * nctx;
     const int sh = (warp & 1) * 16;
+    uint32_t wh_sa = (uint32_t)__cvta_generic_to_shared(wh), start_sa = (uint32_t)__cvta_generic_to_shared(s_start),
+             ent_sa = (uint32_t)__cvta_generic_to_shared(s_ent);
+    asm volatile("" : "+r"(wh_sa), "+r"(start_sa), "+r"(ent_sa));
     const uint32_t tile_rec0 = T.lines[g.line_first + my_lines[0]].rec_off;       // GOLOMB: record indices count from here
     {
         uint32_t nd = 0;
@@ -500,13 +521,13 @@ __global__ void __launch_bounds__(kTileSortThreads) k_tile_sort(const EncDeviceT
                         const uint32_t zero = __ballot_sync(0xFFFFFFFFu, act && (r & 0xFFFFu) == 0u);
                         const uint32_t ctx0 = __ballot_sync(0xFFFFFFFFu, act && (r >> 16) == 0u);
                         const uint32_t mem = gr_run_members(ctx0, zero, carry);
-                        if (act && !((mem & zero) >> lane & 1u)) atomicAdd(&wh[r >> 16], 1u << sh);
+                        if (act && !((mem & zero) >> lane & 1u)) sm_red_add(wh_sa + 4u * (r >> 16), 1u << sh);
                     }
                 } else
                 for (int x = lane; x < ld.w; x += 32) {
                     const uint32_t r = recp[x];
                     nd += decisions_of((int)(int16_t)(r & 0xFFFFu));
-                    atomicAdd(&wh[r >> 16], 1u << sh);
+                    sm_red_add(wh_sa + 4u * (r >> 16), 1u << sh);
                 }
             }
         }
@@ -576,11 +597,11 @@ __global__ void __launch_bounds__(kTileSortThreads) k_tile_sort(const EncDeviceT
                 const uint32_t grp = __match_any_sync(0xFFFFFFFFu, act ? ctx : 0xFFFFFFFFu);
                 const uint32_t rank = __popc(grp & lt_mask);
                 uint32_t off = 0u;
-                if (act && rank == 0u) off = (atomicAdd(&wh[ctx], (uint32_t)__popc(grp) << sh) >> sh) & 0xFFFFu;
+                if (act && rank == 0u) off = (sm_atom_add(wh_sa + 4u * ctx, (uint32_t)__popc(grp) << sh) >> sh) & 0xFFFFu;
                 off = __shfl_sync(0xFFFFFFFFu, off, (__ffs(grp) - 1) & 31);
                 if (act) {
                     const uint32_t where = GOLOMB ? ld.rec_off - tile_rec0 + (uint32_t)(x0 + lane) : pos + in - nd;
-                    s_ent[(uint32_t)s_start[ctx] + off + rank] = where | (r << kGrpPosBits);
+                    sm_st32(ent_sa + 4u * (sm_ld16(start_sa + 2u * ctx) + off + rank), where | (r << kGrpPosBits));
                 }
                 if (!GOLOMB) pos += __shfl_sync(0xFFFFFFFFu, in, 31);
             }
