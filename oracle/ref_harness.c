@@ -524,8 +524,7 @@ unsigned ffv1ref_crc32_ieee(unsigned init, const uint8_t *buf, int len)
 extern AVOutputFormat ff_avi_muxer;
 extern AVOutputFormat ff_nut_muxer;
 extern AVInputFormat ff_nut_demuxer;
-/* libavformat/nut.c lists the MOV video tags as a fallback table; libavformat/isom.c is not part of this build */
-const AVCodecTag ff_codec_movvideo_tags[] = { { AV_CODEC_ID_NONE, 0 } };
+extern AVOutputFormat ff_matroska_muxer;
 static AVOutputFormat *g_muxer = &ff_avi_muxer;          /* container fate_avi_impl writes */
 
 typedef struct MemOut { uint8_t *buf; int64_t cap, pos, size; } MemOut;
@@ -583,7 +582,7 @@ static int64_t fate_avi_impl(AVCodec *codec, int batch, const uint8_t *raw, int 
     uint8_t *iobuf;
     int i, ret, fsize;
     reg();
-    if (!fmt_registered) { av_register_output_format(&ff_avi_muxer); av_register_output_format(&ff_nut_muxer); fmt_registered = 1; }
+    if (!fmt_registered) { av_register_output_format(&ff_avi_muxer); av_register_output_format(&ff_nut_muxer); av_register_output_format(&ff_matroska_muxer); fmt_registered = 1; }
     if (avformat_alloc_output_context2(&oc, g_muxer, NULL, NULL) < 0) return -1;
     iobuf = av_malloc(32768);
     oc->pb = avio_alloc_context(iobuf, 32768, 1, &mo, NULL, mem_write, mem_seek);
@@ -662,7 +661,7 @@ int64_t ffv1ref_mux_named(const char *muxer, const char *name, int batch, const 
     reg();
     AVCodec *codec = avcodec_find_encoder_by_name(name);
     if (!codec) return -1;
-    g_muxer = !strcmp(muxer, "nut") ? &ff_nut_muxer : &ff_avi_muxer;
+    g_muxer = !strcmp(muxer, "nut") ? &ff_nut_muxer : (!strcmp(muxer, "matroska") ? &ff_matroska_muxer : &ff_avi_muxer);
     r = fate_avi_impl(codec, batch, raw, nframes, w, h, pix_fmt, level, slices, out, cap);
     g_muxer = &ff_avi_muxer;
     return r;

@@ -315,3 +315,17 @@ def test_level4_through_avcodec_api(lavc):
     lavc.ffv1ref_enc_open_named_ex.restype = ctypes.c_void_p
     for name in (b"ffv1", b"ffv1_b200"):
         assert not lavc.ffv1ref_enc_open_named_ex(name, 96, 80, b"bgr0", 3, 4, 1, 0, 4, -1, 2, 0, 0, None)
+
+@pytest.mark.parametrize("fmt,level,slices", [("yuv420p", 3, 4), ("yuv422p10le", 3, 0), ("bgr0", 3, 4)])
+def test_matroska_file_through_the_dropin(lavc, fmt, level, slices):
+    """SURVEY 8(f) rank 2, Matroska (libavformat/matroskaenc.c, codec private = BITMAPINFOHEADER + extradata, riff.c:316):
+    the file written from -c:v ffv1_b200 is byte-identical to the one written from the reference encoder"""
+    try:
+        raw, w, h = ffv1_ref.vsynth("vsynth1")
+    except Exception as ex:
+        pytest.skip("clip generator not available here: %r" % ex)
+    src = raw if fmt == "yuv420p" else ffv1_ref.sws_convert(raw, w, h, fmt)
+    ours = ffv1_ref.mux("matroska", "ffv1_b200", src, 50, w, h, fmt, level=level, slices=slices, batch=16)
+    theirs = ffv1_ref.mux("matroska", "ffv1", src, 50, w, h, fmt, level=level, slices=slices)
+    assert bytes(ours[:4]) == b"\x1a\x45\xdf\xa3" and len(ours) > 50 * 1000
+    assert np.array_equal(ours, theirs), "Matroska file differs from the one written with the reference encoder"
