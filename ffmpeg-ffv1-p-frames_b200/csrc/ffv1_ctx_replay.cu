@@ -15,6 +15,12 @@
 //   k_replay_ctx   one warp per (chain, context) list, longest lists first, lane = state slot: put_symbol_inline's
 //                  binarisation (ffv1enc.c:185-231) with the context's 32-byte state in registers; writes p | bit<<8
 //                  at the recorded positions of the decision stream that k_rangecode consumes
+//   k_replay_grp   the same for 8-bit content, two lists per warp (16 lanes per symbol)
+// Tile-sorted form of the lists (8-bit planar content, range coder and Golomb-Rice; Layout::tiled_lists): a context's
+// list stays cut into one run per tile, so no histogram pass and no scan along the chains are needed:
+//   k_tile_sort    counting sort of a 48-line tile by context in shared memory -> one contiguous block + run table
+//   k_tile_layout  tiles' decision counts -> their places in the decision region
+//   k_replay_grp<TILED> / k_gr_replay<TILED> (ffv1_enc_kernels.cu) walk a chain tile after tile
 #include "ffv1_enc_kernels.cuh"
 #include <cstdlib>
 #include <cstring>
