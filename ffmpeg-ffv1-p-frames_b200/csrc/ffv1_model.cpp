@@ -995,7 +995,7 @@ void build_tables(const Config &c, Tables &t)
                     if (ld.run != t.lines[g.line_first + t.pc_lines[g.pc_line_first[pc]]].run) tiled = false;   // one run per plane context
                     widest = std::max<uint32_t>(widest, ld.w);
                 }
-                if (widest * kTiledLines > (uint32_t)kTiledMaxSamples) tiled = false;
+                if (widest * (kTiledLines / 4) > (uint32_t)kTiledMaxSamples) tiled = false;      // slices up to 1408 samples wide
             }
         L.tiled_lists = tiled ? 1 : 0;
         for (size_t si = 0; si < t.slices.size(); si++) {
@@ -1003,12 +1003,13 @@ void build_tables(const Config &c, Tables &t)
             for (int pc = 0; pc < 3; pc++) {
                 int tile_lines = L.ctx_count > 1024 ? 4 * kCtxTileLines : (tiled ? kTiledLines : kCtxTileLines);
                 if (tiled) {
-                    // narrow planes (subsampled chroma) take twice the lines: a tile is the replay's window, and the
-                    // sort's per-tile set-up is the same whatever the tile holds
+                    // a tile is the replay's window, and the sort's per-tile set-up is the same whatever the tile holds
                     uint32_t widest = 0;
                     for (int i = 0; i < g.pc_nlines[pc]; i++)
                         widest = std::max<uint32_t>(widest, t.lines[g.line_first + t.pc_lines[g.pc_line_first[pc] + i]].w);
-                    if (widest * 2 * kTiledLines <= (uint32_t)kTiledMaxSamples) tile_lines = 2 * kTiledLines;
+                    // as many lines as the sort's shared-memory image holds: 96 (planes <= 176 wide), 48 (<= 352), 24, 12
+                    tile_lines = 2 * kTiledLines;
+                    while (tile_lines > kTiledLines / 4 && widest * tile_lines > (uint32_t)kTiledMaxSamples) tile_lines /= 2;
                 }
                 g.ct_first[pc] = (int32_t)t.ctiles.size();
                 uint32_t before = 0;

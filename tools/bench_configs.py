@@ -7,7 +7,7 @@ own CPU encoder on the same options and the same clip (one JSON line per configu
   c4   configs[3]  3840x2160 gbrp14le (the legal stand-in for RGB48), GOP 16, coder=2, 30 slices   -- clip S4
   gr   configs[1]'s clip with coder=0: Golomb-Rice / run mode, the reference's default for 8-bit content
 
-usage: bench_configs.py [c3|c4|gr|p10 ...] [--frames N] [--steps K]
+usage: bench_configs.py [c3|c4|gr|p10|uhd ...] [--frames N] [--steps K]
 value = frames resident in HBM (CUDA events); e2e = pinned host frames -> host packets through submit_host/collect_async.
 The packets of these configurations are compared with the oracle at full size by tests/test_gpu_encode.py
 (test_full_size_configs); here the stream is only decoded back by the CUDA decoder (first GOP, bit-exact round trip)."""
@@ -44,6 +44,19 @@ def clip_p10(n):
         out.append(np.concatenate([p.astype("<u2").ravel() for p in (Y, U, V)]).view(np.uint8))
     return np.stack(out)
 
+def clip_uhd(n):
+    """S2's formulas at 3840x2160, seed 1238"""
+    W, H = 3840, 2160
+    rng = np.random.default_rng(1238)
+    yy, xx = np.mgrid[0:H, 0:W]
+    out = []
+    for k in range(n):
+        Y = np.clip(((0.1 * xx + 0.07 * yy + 1.5 * k) % 256) + rng.normal(0, 2, (H, W)), 0, 255)
+        U = np.clip(128 + 20 * np.sin((xx[::2, ::2] + 3 * k) / 97) + rng.normal(0, 1.5, (H // 2, W // 2)), 0, 255)
+        V = np.clip(128 + 20 * np.cos((yy[::2, ::2] + 2 * k) / 71) + rng.normal(0, 1.5, (H // 2, W // 2)), 0, 255)
+        out.append(np.concatenate([p.astype(np.uint8).ravel() for p in (Y, U, V)]))
+    return np.stack(out)
+
 def clip_s4(n):
     """S4: three correlated 14-bit planes G, B, R (gbrp14le), seed 1236"""
     W, H = 3840, 2160
@@ -70,6 +83,8 @@ CONFIGS = {
                what="BASELINE configs[3]: 2160p gbrp14le (RCT, 15-bit residuals), GOP 16, coder=2, 30 slices"),
     "p10": dict(w=1920, h=1080, fmt="yuv420p10le", opts=dict(level=3, coder=1, context=0, slices=24), clip=clip_p10, nclip=16, frames=512,
                 what="1080p yuv420p10le, GOP 16, range coder, context=0 (666 contexts), 24 slices: the 10-bit sibling of configs[1]"),
+    "uhd": dict(w=3840, h=2160, fmt="yuv420p", opts=dict(level=3, coder=1, context=0, slices=30), clip=clip_uhd, nclip=8, frames=512,
+                what="2160p yuv420p8, GOP 16, range coder, context=0, 30 slices (640-sample slices)"),
     "gr": dict(w=1920, h=1080, fmt="yuv420p", opts=dict(level=3, coder=0, context=0, slices=24), clip=clip_s2, nclip=32, frames=1024,
                what="configs[1]'s clip with coder=0: Golomb-Rice / run mode, 24 slices"),
 }
