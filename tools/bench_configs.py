@@ -7,7 +7,7 @@ own CPU encoder on the same options and the same clip (one JSON line per configu
   c4   configs[3]  3840x2160 gbrp14le (the legal stand-in for RGB48), GOP 16, coder=2, 30 slices   -- clip S4
   gr   configs[1]'s clip with coder=0: Golomb-Rice / run mode, the reference's default for 8-bit content
 
-usage: bench_configs.py [c3|c4|gr|p10|uhd ...] [--frames N] [--steps K]
+usage: bench_configs.py [c3|c4|gr|p10|uhd|bgr0 ...] [--frames N] [--steps K]
 value = frames resident in HBM (CUDA events); e2e = pinned host frames -> host packets through submit_host/collect_async.
 The packets of these configurations are compared with the oracle at full size by tests/test_gpu_encode.py
 (test_full_size_configs); here the stream is only decoded back by the CUDA decoder (first GOP, bit-exact round trip)."""
@@ -57,6 +57,21 @@ def clip_uhd(n):
         out.append(np.concatenate([p.astype(np.uint8).ravel() for p in (Y, U, V)]))
     return np.stack(out)
 
+def clip_bgr0(n):
+    """1920x1080 bgr0: three correlated 8-bit channels (G = S2's luma formula, B and R = G + noise), seed 1239"""
+    W, H = 1920, 1080
+    rng = np.random.default_rng(1239)
+    yy, xx = np.mgrid[0:H, 0:W]
+    out = []
+    for k in range(n):
+        G = np.clip(((0.1 * xx + 0.07 * yy + 1.5 * k) % 256) + rng.normal(0, 2, (H, W)), 0, 255)
+        B = np.clip(G + rng.normal(0, 1.5, (H, W)), 0, 255)
+        R = np.clip(G + rng.normal(0, 1.5, (H, W)), 0, 255)
+        px = np.zeros((H, W, 4), np.uint8)
+        px[:, :, 0], px[:, :, 1], px[:, :, 2] = B.astype(np.uint8), G.astype(np.uint8), R.astype(np.uint8)
+        out.append(px.ravel())
+    return np.stack(out)
+
 def clip_s4(n):
     """S4: three correlated 14-bit planes G, B, R (gbrp14le), seed 1236"""
     W, H = 3840, 2160
@@ -85,6 +100,8 @@ CONFIGS = {
                 what="1080p yuv420p10le, GOP 16, range coder, context=0 (666 contexts), 24 slices: the 10-bit sibling of configs[1]"),
     "uhd": dict(w=3840, h=2160, fmt="yuv420p", opts=dict(level=3, coder=1, context=0, slices=30), clip=clip_uhd, nclip=8, frames=512,
                 what="2160p yuv420p8, GOP 16, range coder, context=0, 30 slices (640-sample slices)"),
+    "bgr0": dict(w=1920, h=1080, fmt="bgr0", opts=dict(level=3, coder=1, context=0, slices=24), clip=clip_bgr0, nclip=16, frames=512,
+                what="1080p bgr0 (packed 8-bit RGB through the RCT, 9-bit residuals), GOP 16, range coder, 24 slices"),
     "gr": dict(w=1920, h=1080, fmt="yuv420p", opts=dict(level=3, coder=0, context=0, slices=24), clip=clip_s2, nclip=32, frames=1024,
                what="configs[1]'s clip with coder=0: Golomb-Rice / run mode, 24 slices"),
 }
