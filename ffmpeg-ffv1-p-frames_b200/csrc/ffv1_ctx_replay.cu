@@ -1236,7 +1236,7 @@ void launch_ctx_replay(const EncDeviceTables &t, const EncBatch &b, int max_tile
     if (const char *v = getenv("FFV1B200_REPLAY_GROUPS")) grp = atoi(v);
     // 8-bit content (residuals folded to <= 9 bits): two lists per warp (k_replay_grp) over 4-byte list entries
     // (position | residual << 22): a (slice, plane context) decision region must stay below 2^22 entries
-    const bool grp_ok = (grp == 1 || grp == 2) && L.coded_bits <= 9 && L.dec_per_frame < 0x7FFFFFFFu && max_dec_cap < (1u << kGrpPosBits);
+    const bool grp_ok = (grp == 1 || grp == 2) && L.coded_bits <= 10 && L.dec_per_frame < 0x7FFFFFFFu && max_dec_cap < (1u << kGrpPosBits);
     // tiles that fit the shared-memory sort (slices up to 352 samples wide) take the staged scatter
     int staged = 1;
     if (const char *v = getenv("FFV1B200_SCATTER")) staged = strcmp(v, "direct") ? 1 : 0;

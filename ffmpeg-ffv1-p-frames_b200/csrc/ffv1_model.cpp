@@ -985,7 +985,7 @@ void build_tables(const Config &c, Tables &t)
     // (slice, plane context); 64 for the large context model (a tile carries a histogram of all 7563 contexts); 32 for the
     // tile-sorted lists of 8-bit planar range-coded content (see Layout::tiled_lists)
     {
-        bool tiled = L.ctx_count <= 1024 && L.coded_bits <= 9;
+        bool tiled = L.ctx_count <= 1024 && L.coded_bits <= 10;
         if (const char *v = getenv("FFV1B200_TILED")) { if (atoi(v) == 0) tiled = false; }     // A/B switch: the chain-wide lists
         for (const SliceGeom &g : t.slices)
             for (int pc = 0; pc < 3 && tiled; pc++) {

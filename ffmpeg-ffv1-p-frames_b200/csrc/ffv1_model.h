@@ -107,7 +107,7 @@ struct Layout {
     int32_t ctiles_per_frame;
     uint32_t samples_per_frame;  // coded samples (no padding)
     uint32_t dec_per_frame;  // decision entries per frame (all regions; set by layout_decisions)
-    int32_t tiled_lists;     // the per-context lists are kept tile by tile (k_tile_sort / k_replay_grp<TILED>): 8-bit content,
+    int32_t tiled_lists;     // the per-context lists are kept tile by tile (k_tile_sort / k_replay_grp<TILED>): 8..10-bit content,
                              // small context model, one run per plane context, slices <= 1408 samples wide
     int32_t rct_offset;      // 1 << bits for RGB
     PlaneInfo plane[4];
