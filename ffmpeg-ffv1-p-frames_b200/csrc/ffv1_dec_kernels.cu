@@ -490,23 +490,40 @@ constexpr int kDecSmemQuant = 2 * 5 * 256;
 
 constexpr int kDecWarps = 2;               // chains per CTA (they share the quantisation / transition tables)
 
+// PIPE (planar YUV, range coder): the two warps of a CTA work on ONE chain.  Inside a slice the planes follow each other
+// in one coder stream, but across the frames of a GOP the only thing a plane needs from the frame before is the model of
+// its own plane context (ffv1dec.c:419-420) -- luma of frame f+1 can be decoded while chroma of frame f still is.  Warp 0
+// decodes the luma plane of every frame (its model stays in shared memory) and hands the coder (low, range, position) and
+// the slice header to warp 1 through a small mailbox ring; warp 1 decodes the remaining planes (models in global memory:
+// it has half the samples and time to spare) and does the end-of-slice check.  A chain then takes the time of its luma
+// planes: 2/3 of the frames' samples for 4:2:0.  Used when the batch's chains fit the SMs at one chain per CTA.
+struct DecMail { uint32_t low, range, pos; int32_t err, sx, sy, sw, sh, qti, v4, bad; };
+constexpr int kDecMailSlots = 4;
+
 // MINB = resident CTAs per SM the register allocation aims at (8: no spills; 12: for batches with more chains than 8 CTAs hold)
-template <int MINB>
+template <int MINB, bool PIPE>
 __global__ void __launch_bounds__(32 * kDecWarps, MINB) k_decode(const DecDeviceTables T, const DecBatch B)
 {
     extern __shared__ __align__(16) unsigned char s_dyn[];      // per warp: [model of the current plane context][line ring]
     __shared__ int16_t s_quant[kDecSmemQuant];
     __shared__ uint16_t s_lut[256];                              // zero_state | one_state << 8
+    __shared__ DecMail s_mail[kDecMailSlots];
+    __shared__ int s_pub, s_ack;                                 // PIPE: slices handed over by warp 0 / taken by warp 1
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < kDecSmemQuant; i += 32 * kDecWarps) s_quant[i] = T.quant[i];
     for (int i = threadIdx.x; i < 256; i += 32 * kDecWarps) s_lut[i] = (uint16_t)(T.lut[i] | (T.lut[256 + i] << 8));
+    if (threadIdx.x == 0) { s_pub = 0; s_ack = 0; }
     __syncthreads();
 
-    const int chain = blockIdx.x * kDecWarps + warp;
+    const int chain = PIPE ? (int)blockIdx.x : (int)blockIdx.x * kDecWarps + warp;
     if (chain >= B.nseg * T.max_slices) return;
-    const int per_warp = T.smem_model + T.smem_ring_w * kDecSmemRingBytes;
-    uint8_t *s_model = s_dyn + (size_t)warp * per_warp;
-    int16_t *s_ring = reinterpret_cast<int16_t *>(s_model + T.smem_model);
+    const bool luma_warp = !PIPE || warp == 0, rest_warp = !PIPE || warp == 1;
+    const int ring_bytes = T.smem_ring_w * kDecSmemRingBytes;
+    const int per_warp = T.smem_model + ring_bytes;
+    // PIPE: [luma model][ring of warp 0][ring of warp 1]
+    uint8_t *s_model = PIPE ? s_dyn : s_dyn + (size_t)warp * per_warp;
+    int16_t *s_ring = reinterpret_cast<int16_t *>(PIPE ? s_dyn + T.smem_model + (size_t)warp * ring_bytes : s_model + T.smem_model);
+    int nhand = 0;                          // PIPE: slices handed over / taken so far by this warp
     const int seg = chain / T.max_slices, si = chain - seg * T.max_slices;
     const int f0 = B.seg_first[seg], f1 = B.seg_first[seg + 1];
     uint8_t *models = B.state + ((size_t)B.seg_set[seg] * T.max_slices + si) * 3 * T.state_stride;
@@ -535,6 +552,22 @@ __global__ void __launch_bounds__(32 * kDecWarps, MINB) k_decode(const DecDevice
         if (lane == 0) {
             sr.golomb = golomb; sr.run_index = 0; sr.err = 0;
             rd_init(sr.rc, sbeg, ssize);
+            if (PIPE && warp == 1) {
+                // the coder as warp 0 left it behind the luma plane, and the slice header it read
+                volatile int *pub = &s_pub;
+                int spins = 0;
+                while (*pub <= nhand && ++spins < (1 << 27)) __nanosleep(200);
+                __threadfence_block();
+                if (*pub <= nhand) bad = 1;                      // (never seen: warp 0 hands over every slice it starts)
+                else {
+                    const DecMail m = s_mail[nhand & (kDecMailSlots - 1)];
+                    __threadfence_block();
+                    *(volatile int *)&s_ack = nhand + 1;
+                    sr.rc.low = m.low; sr.rc.range = m.range; sr.rc.ptr = sbeg + m.pos; sr.err = m.err;
+                    sx = m.sx; sy = m.sy; sw = m.sw; sh = m.sh; v4 = m.v4; bad = m.bad ? 3 : 0;
+                    qti[0] = m.qti & 3; qti[1] = (m.qti >> 2) & 3; qti[2] = (m.qti >> 4) & 3;
+                }
+            } else
             if (T.version < 2) {
                 // versions 0/1: one slice = the frame; the host has read the keyframe bit and the in-band header
                 // (ffv1dec.c:646-696) and hands over the coder state behind them
@@ -595,7 +628,21 @@ __global__ void __launch_bounds__(32 * kDecWarps, MINB) k_decode(const DecDevice
             }
         }
         bad = __shfl_sync(0xFFFFFFFFu, bad, 0);
-        if (bad) { if (lane == 0) B.damaged[fs] |= 2u; continue; }
+        if (PIPE) nhand++;
+        if (bad) {
+            if (lane == 0) {
+                if (bad != 3) B.damaged[fs] |= 2u;               // (3: warp 0 has flagged the slice already)
+                if (PIPE && warp == 0) {
+                    volatile int *ack = &s_ack;
+                    while (nhand - 1 - *ack >= kDecMailSlots) __nanosleep(200);
+                    DecMail m{}; m.bad = 1;
+                    s_mail[(nhand - 1) & (kDecMailSlots - 1)] = m;
+                    __threadfence_block();
+                    *(volatile int *)&s_pub = nhand;
+                }
+            }
+            continue;
+        }
         sx = __shfl_sync(0xFFFFFFFFu, sx, 0); sy = __shfl_sync(0xFFFFFFFFu, sy, 0);
         sw = __shfl_sync(0xFFFFFFFFu, sw, 0); sh = __shfl_sync(0xFFFFFFFFu, sh, 0);
         qti[0] = __shfl_sync(0xFFFFFFFFu, qti[0], 0); qti[1] = __shfl_sync(0xFFFFFFFFu, qti[1], 0);
@@ -607,6 +654,7 @@ __global__ void __launch_bounds__(32 * kDecWarps, MINB) k_decode(const DecDevice
         // ---- keyframe (or a version-4 slice that asks for it, ffv1dec.c:419-420): reset the models (ffv1.c:177-202)
         if (key || (v4 >> 16)) {
             for (int pc = 0; pc < 3; pc++) {
+                if (PIPE && (pc == 0) != (warp == 0)) continue;  // every warp resets the models it decodes with
                 uint8_t *m = models + (size_t)pc * T.state_stride;
                 const int set = qti[pc < T.plane_count ? pc : 0];
                 const int nctx = T.ctx_count[set];
@@ -626,7 +674,7 @@ __global__ void __launch_bounds__(32 * kDecWarps, MINB) k_decode(const DecDevice
         uint8_t *frame = B.out + (size_t)f * T.frame_bytes;
         if (!T.colorspace) {
             // ---- decode_plane per plane (ffv1dec.c:183-224, 436-455)
-            for (int p = 0; p < nplanes; p++) {
+            for (int p = luma_warp ? 0 : 1; p < (rest_warp ? nplanes : 1); p++) {
                 int src, hs = 0, vs = 0, pc, pstep = T.bits > 8 ? 2 : 1, poff = 0;
                 if (T.ya8) { src = 0; pc = p; pstep = 2; poff = p; }
                 else if (p == 0) { src = 0; pc = 0; }
@@ -639,7 +687,7 @@ __global__ void __launch_bounds__(32 * kDecWarps, MINB) k_decode(const DecDevice
                 // the plane context's model moves to shared memory while its planes are decoded (U and V share one)
                 // (the slice header picks the quantisation table set per plane: only a set whose model fits is moved)
                 const int model_nb = (T.ctx_count[qti[pc < T.plane_count ? pc : 0]] * (golomb ? 8 : 32) + 15) >> 4;
-                const bool model_sm = T.smem_model && model_nb * 16 <= T.smem_model;
+                const bool model_sm = T.smem_model && model_nb * 16 <= T.smem_model && (!PIPE || warp == 0);
                 if (model_sm) {
                     if (pc != sm_pc) {
                         const int nb = model_nb;
@@ -706,7 +754,7 @@ __global__ void __launch_bounds__(32 * kDecWarps, MINB) k_decode(const DecDevice
                     }
                     continue;
                 }
-                int16_t *rows = ring_sm ? s_ring + kDecRingPad : ring;                    // plane slot 0: three rows
+                int16_t *rows = ring_sm ? s_ring + kDecRingPad : ring + (PIPE && warp ? 3 * T.ring_w : 0);   // plane slot 0 (1): three rows
                 for (int i = lane - kDecRingPad; i < 3 * rw - kDecRingPad; i += 32) rows[i] = 0;
                 __syncwarp();
                 if (lane == 0) sr.run_index = 0;
@@ -752,6 +800,22 @@ __global__ void __launch_bounds__(32 * kDecWarps, MINB) k_decode(const DecDevice
                 for (int i = lane; i < sm_nb; i += 32) dst[i] = reinterpret_cast<const uint4 *>(s_model)[i];
                 sm_pc = -1;
                 __syncwarp();
+            }
+            if (PIPE && warp == 0) {
+                // the luma plane is done: coder and header go to warp 1, this warp moves on to the next frame
+                if (lane == 0) {
+                    volatile int *ack = &s_ack;
+                    while (nhand - 1 - *ack >= kDecMailSlots) __nanosleep(200);
+                    DecMail m;
+                    m.low = sr.rc.low; m.range = sr.rc.range; m.pos = (uint32_t)(sr.rc.ptr - sbeg); m.err = sr.err;
+                    m.sx = sx; m.sy = sy; m.sw = sw; m.sh = sh; m.v4 = v4; m.bad = 0;
+                    m.qti = qti[0] | qti[1] << 2 | qti[2] << 4;
+                    s_mail[(nhand - 1) & (kDecMailSlots - 1)] = m;
+                    __threadfence_block();
+                    *(volatile int *)&s_pub = nhand;
+                }
+                __syncwarp();
+                continue;
             }
         } else {
             // ---- decode_rgb_frame (ffv1dec.c:226-280): planes interleaved per row, shared run_index
@@ -828,19 +892,35 @@ void launch_decode(const DecDeviceTables &t_in, const DecBatch &b, cudaStream_t 
         if (e && atoi(e) == 0) t.smem_model = 0;
     }
     const int chains = b.nseg * t.max_slices;
-    // Models in shared memory cap the chains an SM holds (a 21 KB model per chain); a batch with more chains than that
-    // runs faster with the models in global memory and twice the warps per scheduler to hide its latency.
+    const bool debug = getenv("FFV1B200_DEBUG") != nullptr;
     static int nsm = -1;
     if (nsm < 0) {
-        cudaFuncSetAttribute(k_decode<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDecWarps * (24 * 1024 + 11 * 1024));
-        cudaFuncSetAttribute(k_decode<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDecWarps * (24 * 1024 + 11 * 1024));
+        cudaFuncSetAttribute(k_decode<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDecWarps * (24 * 1024 + 11 * 1024));
+        cudaFuncSetAttribute(k_decode<12, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDecWarps * (24 * 1024 + 11 * 1024));
+        cudaFuncSetAttribute(k_decode<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 24 * 1024 + kDecWarps * 11 * 1024);
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
     }
+    // Planar YUV through the range coder, few enough chains for one CTA each: two warps per chain, luma one frame ahead of
+    // chroma (k_decode<.., PIPE>).  FFV1B200_DEC_PIPE=0/1 overrides the choice (1: whenever the stream allows it).
+    if (t.smem_model && t.smem_ring_w && t.ac != 0 && !t.colorspace && t.chroma_planes && !t.ya8) {
+        // (the second warp's models in shared memory as well: no faster -- the luma warp sets the pace -- and fewer CTAs per SM)
+        const int smem = t.smem_model + kDecWarps * t.smem_ring_w * kDecSmemRingBytes;
+        int nb = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_decode<8, true>, 32 * kDecWarps, smem);
+        const char *ev = getenv("FFV1B200_DEC_PIPE");
+        if (ev ? atoi(ev) != 0 : chains <= nb * nsm) {
+            if (debug) fprintf(stderr, "k_decode<8, pipe>: grid %d, %d B dynamic smem, %d CTAs per SM\n", chains, smem, nb);
+            k_decode<8, true><<<chains, 32 * kDecWarps, smem, s>>>(t, b);
+            return;
+        }
+    }
+    // Models in shared memory cap the chains an SM holds (a 21 KB model per chain); a batch with more chains than that
+    // runs faster with the models in global memory and twice the warps per scheduler to hide its latency.
     if (t.smem_model) {
         int nb = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_decode<8>, 32 * kDecWarps, kDecWarps * (t.smem_model + t.smem_ring_w * kDecSmemRingBytes));
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_decode<8, false>, 32 * kDecWarps, kDecWarps * (t.smem_model + t.smem_ring_w * kDecSmemRingBytes));
         if (chains > nb * nsm * kDecWarps) t.smem_model = 0;
     }
     const int smem = kDecWarps * (t.smem_model + t.smem_ring_w * kDecSmemRingBytes);
@@ -848,13 +928,13 @@ void launch_decode(const DecDeviceTables &t_in, const DecBatch &b, cudaStream_t 
     // more chains than the spill-free register allocation keeps resident, but few enough for the 80-register one to
     // hold in a single wave: take that one (2048 frames of 1080p: 1421 instead of 1239 frames/s)
     int nb8 = 0, nb12 = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb8, k_decode<8>, 32 * kDecWarps, smem);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb12, k_decode<12>, 32 * kDecWarps, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb8, k_decode<8, false>, 32 * kDecWarps, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb12, k_decode<12, false>, 32 * kDecWarps, smem);
     const char *ev = getenv("FFV1B200_DEC_MINB");
     const bool dense = ev ? atoi(ev) > 8 : (grid > nb8 * nsm && grid <= nb12 * nsm);
-    if (getenv("FFV1B200_DEBUG")) fprintf(stderr, "k_decode<%d>: grid %d, %d B dynamic smem\n", dense ? 12 : 8, grid, smem);
-    if (dense) k_decode<12><<<grid, 32 * kDecWarps, smem, s>>>(t, b);
-    else k_decode<8><<<grid, 32 * kDecWarps, smem, s>>>(t, b);
+    if (debug) fprintf(stderr, "k_decode<%d>: grid %d, %d B dynamic smem\n", dense ? 12 : 8, grid, smem);
+    if (dense) k_decode<12, false><<<grid, 32 * kDecWarps, smem, s>>>(t, b);
+    else k_decode<8, false><<<grid, 32 * kDecWarps, smem, s>>>(t, b);
 }
 
 // ------------------------------------------------------------------------------------------------ concealment

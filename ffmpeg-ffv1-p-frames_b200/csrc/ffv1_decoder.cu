@@ -9,6 +9,7 @@
 #include <string>
 #include <vector>
 #include <algorithm>
+#include <thread>
 
 using namespace ffv1;
 
@@ -194,6 +195,25 @@ int ffv1b200_dec_decode_host(FFV1B200Decoder *d, int n, const uint8_t *const *pk
     }
     if (d->h_pkt.n < total) CU_TRY(d->h_pkt.alloc(total + total / 4));
     if (d->d_pkt.n < total) CU_TRY(d->d_pkt.alloc(total + total / 4));
+    // the packets move into the pinned staging area: a large batch (2.5 GB at 2048 1080p frames) is copied by several
+    // threads, each a contiguous range of packets of about the same number of bytes
+    {
+        size_t o = 0;
+        for (int f = 0; f < n; f++) { d->h_pkt_off.p[f] = o; o += ((size_t)pkt_size[f] + 15) & ~(size_t)15; }
+        const int hw = (int)std::thread::hardware_concurrency();
+        const int nthr = (int)std::max<size_t>(1, std::min<size_t>({(size_t)8, (size_t)std::max(1, hw / 2), total >> 25, (size_t)n}));
+        auto copy_range = [&](int a, int b) { for (int f = a; f < b; f++) memcpy(d->h_pkt.p + d->h_pkt_off.p[f], pkt_data[f], (size_t)pkt_size[f]); };
+        std::vector<int> cut(nthr + 1, n);
+        cut[0] = 0;
+        for (int t = 1, f = 0; t < nthr; t++) {
+            while (f < n && d->h_pkt_off.p[f] < total / nthr * t) f++;
+            cut[t] = f;
+        }
+        std::vector<std::thread> pool;
+        for (int t = 1; t < nthr; t++) pool.emplace_back(copy_range, cut[t], cut[t + 1]);
+        copy_range(cut[0], cut[1]);                          // the caller's thread takes the first range
+        for (auto &th : pool) th.join();
+    }
     size_t off = 0;
     int nseg = 0;
     bool kfo = d->key_frame_ok;
@@ -201,9 +221,7 @@ int ffv1b200_dec_decode_host(FFV1B200Decoder *d, int n, const uint8_t *const *pk
     for (int f = 0; f < n; f++) {
         const uint8_t *pk = pkt_data[f];
         const long size = pkt_size[f];
-        memcpy(d->h_pkt.p + off, pk, (size_t)size);
-        d->h_pkt_off.p[f] = off;
-        off += ((size_t)size + 15) & ~(size_t)15;
+        off += ((size_t)size + 15) & ~(size_t)15;             // (staged above at h_pkt_off[f])
         // keyframe bit: get_rac on a fresh state 128 (range 0xFF00 -> range1 0x7F80)
         const unsigned low = (unsigned)pk[0] << 8 | pk[1];
         const bool key = low >= 0x7F80u;

@@ -98,12 +98,14 @@ def test_non_keyframe_first_is_refused(B):
         d.decode(pkts[1])
     assert e.value.code == -1094995529      # AVERROR_INVALIDDATA (ffv1dec.c:930-935)
 
-@pytest.mark.parametrize("env", [{"FFV1B200_DEC_SMEM": "0"}, {"FFV1B200_DEC_MINB": "12"},
-                                 {"FFV1B200_DEC_SMEM": "0", "FFV1B200_DEC_MINB": "12"}],
-                         ids=["models_global", "dense_regs", "models_global_dense_regs"])
+@pytest.mark.parametrize("env", [{"FFV1B200_DEC_SMEM": "0"}, {"FFV1B200_DEC_PIPE": "0", "FFV1B200_DEC_MINB": "12"},
+                                 {"FFV1B200_DEC_SMEM": "0", "FFV1B200_DEC_MINB": "12"}, {"FFV1B200_DEC_PIPE": "0"},
+                                 {"FFV1B200_DEC_PIPE": "1"}],
+                         ids=["models_global", "dense_regs", "models_global_dense_regs", "one_warp_per_chain", "two_warps_per_chain"])
 def test_large_batch_kernel_variants(B, env, monkeypatch):
-    """launch_decode switches model placement (shared -> global memory) and the register allocation with the number of
-    chains in the batch; the variants only big batches reach are forced here and must decode the same bytes"""
+    """launch_decode picks the kernel form by the number of chains in the batch: two warps per chain (luma a frame ahead
+    of chroma) for small batches, one warp per chain beyond, models in shared or global memory, two register
+    allocations; every form is forced here and must decode the same bytes"""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     for cid in ("c2_gop_range_24sl", "c1_cif_intra", "c3_422p10_ctx1", "fate_ffv1_golomb", "fate_v3_444p16", "yuva420p", "gray16", "v0_range"):
