@@ -415,6 +415,8 @@ def main():
                 sys.path.insert(0, os.path.join(ROOT, "tools"))
                 import bench_decode
                 line["decode"] = bench_decode.run(2048, 2048, 1, 0 if args.no_cpu_baseline else 33)     # 2048-frame batch, like the encoder's step
+                small = bench_decode.run(512, 512, 1, 0)                                                # two warps per chain (luma ahead of chroma)
+                line["decode"]["batch_512"] = {k: small[k] for k in ("value", "unit", "frames", "batch", "round_trip", "kernel_fps")}
             except Exception as ex:
                 line["decode"] = {"value": None, "note": repr(ex)}
         print(json.dumps(line))
