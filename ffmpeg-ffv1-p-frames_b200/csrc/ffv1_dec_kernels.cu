@@ -490,14 +490,14 @@ constexpr int kDecSmemQuant = 2 * 5 * 256;
 
 constexpr int kDecWarps = 2;               // chains per CTA (they share the quantisation / transition tables)
 
-// PIPE (planar YUV, range coder): the two warps of a CTA work on ONE chain.  Inside a slice the planes follow each other
+// PIPE (planar YUV): the two warps of a CTA work on ONE chain.  Inside a slice the planes follow each other
 // in one coder stream, but across the frames of a GOP the only thing a plane needs from the frame before is the model of
 // its own plane context (ffv1dec.c:419-420) -- luma of frame f+1 can be decoded while chroma of frame f still is.  Warp 0
 // decodes the luma plane of every frame (its model stays in shared memory) and hands the coder (low, range, position) and
 // the slice header to warp 1 through a small mailbox ring; warp 1 decodes the remaining planes (models in global memory:
 // it has half the samples and time to spare) and does the end-of-slice check.  A chain then takes the time of its luma
 // planes: 2/3 of the frames' samples for 4:2:0.  Used when the batch's chains fit the SMs at one chain per CTA.
-struct DecMail { uint32_t low, range, pos; int32_t err, sx, sy, sw, sh, qti, v4, bad; };
+struct DecMail { uint32_t low, range, pos; int32_t err, sx, sy, sw, sh, qti, v4, bad; uint32_t br_off, br_nbytes, br_pos; };
 constexpr int kDecMailSlots = 4;
 
 // MINB = resident CTAs per SM the register allocation aims at (8: no spills; 12: for batches with more chains than 8 CTAs hold)
@@ -564,6 +564,10 @@ __global__ void __launch_bounds__(32 * kDecWarps, MINB) k_decode(const DecDevice
                     __threadfence_block();
                     *(volatile int *)&s_ack = nhand + 1;
                     sr.rc.low = m.low; sr.rc.range = m.range; sr.rc.ptr = sbeg + m.pos; sr.err = m.err;
+                    if (golomb) {                                // the bit reader behind the luma plane
+                        sr.br.buf = sbeg + m.br_off; sr.br.nbytes = m.br_nbytes; sr.br.pos = m.br_pos;
+                        br_load(sr.br, m.br_pos >> 3);
+                    }
                     sx = m.sx; sy = m.sy; sw = m.sw; sh = m.sh; v4 = m.v4; bad = m.bad ? 3 : 0;
                     qti[0] = m.qti & 3; qti[1] = (m.qti >> 2) & 3; qti[2] = (m.qti >> 4) & 3;
                 }
@@ -810,6 +814,7 @@ __global__ void __launch_bounds__(32 * kDecWarps, MINB) k_decode(const DecDevice
                     m.low = sr.rc.low; m.range = sr.rc.range; m.pos = (uint32_t)(sr.rc.ptr - sbeg); m.err = sr.err;
                     m.sx = sx; m.sy = sy; m.sw = sw; m.sh = sh; m.v4 = v4; m.bad = 0;
                     m.qti = qti[0] | qti[1] << 2 | qti[2] << 4;
+                    m.br_off = golomb ? (uint32_t)(sr.br.buf - sbeg) : 0u; m.br_nbytes = sr.br.nbytes; m.br_pos = sr.br.pos;
                     s_mail[(nhand - 1) & (kDecMailSlots - 1)] = m;
                     __threadfence_block();
                     *(volatile int *)&s_pub = nhand;
@@ -902,15 +907,16 @@ void launch_decode(const DecDeviceTables &t_in, const DecBatch &b, cudaStream_t 
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
     }
-    // Planar YUV through the range coder, few enough chains for one CTA each: two warps per chain, luma one frame ahead of
+    // Planar YUV, few enough chains for one CTA each: two warps per chain, luma one frame ahead of
     // chroma (k_decode<.., PIPE>).  FFV1B200_DEC_PIPE=0/1 overrides the choice (1: whenever the stream allows it).
-    if (t.smem_model && t.smem_ring_w && t.ac != 0 && !t.colorspace && t.chroma_planes && !t.ya8) {
+    if (t.smem_model && t.smem_ring_w && !t.colorspace && t.chroma_planes && !t.ya8) {
         // (the second warp's models in shared memory as well: no faster -- the luma warp sets the pace -- and fewer CTAs per SM)
         const int smem = t.smem_model + kDecWarps * t.smem_ring_w * kDecSmemRingBytes;
         int nb = 0;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_decode<8, true>, 32 * kDecWarps, smem);
         const char *ev = getenv("FFV1B200_DEC_PIPE");
-        if (ev ? atoi(ev) != 0 : chains <= nb * nsm) {
+        // (intra-only streams have nothing to overlap: a chain is one frame)
+        if (ev ? atoi(ev) != 0 : (chains <= nb * nsm && b.nframes >= 2 * b.nseg)) {
             if (debug) fprintf(stderr, "k_decode<8, pipe>: grid %d, %d B dynamic smem, %d CTAs per SM\n", chains, smem, nb);
             k_decode<8, true><<<chains, 32 * kDecWarps, smem, s>>>(t, b);
             return;

@@ -210,8 +210,12 @@ int ffv1b200_dec_decode_host(FFV1B200Decoder *d, int n, const uint8_t *const *pk
             cut[t] = f;
         }
         std::vector<std::thread> pool;
-        for (int t = 1; t < nthr; t++) pool.emplace_back(copy_range, cut[t], cut[t + 1]);
-        copy_range(cut[0], cut[1]);                          // the caller's thread takes the first range
+        int started = 1;                                     // ranges that have a thread (the caller's thread takes the first)
+        try {
+            for (; started < nthr; started++) pool.emplace_back(copy_range, cut[started], cut[started + 1]);
+        } catch (...) {}                                     // no more threads to be had: the caller copies the rest itself
+        copy_range(cut[0], cut[1]);
+        if (started < nthr) copy_range(cut[started], n);
         for (auto &th : pool) th.join();
     }
     size_t off = 0;

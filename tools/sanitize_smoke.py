@@ -23,7 +23,9 @@ def run(w, h, fmt, n, g, dec=True, up=None, **o):
         assert all(np.array_equal(np.asarray(out[i][0])[keep], frames[i].view(np.uint8).reshape(-1)[keep]) for i in range(n))
     print("ok", fmt, o)
 
-run(384, 216, "yuv420p", 6, 4, level=3, coder=1, slices=24)                       # tile-sorted lists, k_pixel_fast
+run(384, 216, "yuv420p", 6, 4, level=3, coder=1, slices=24)                       # tile-sorted lists, k_pixel_fast, two-warp decode
+if os.environ.get("SANITIZE_FIRST_ONLY"):                                         # (racecheck is slow: one case)
+    sys.exit(0)
 run(704, 96, "yuv420p", 3, 2, level=3, coder=1, slices=4)                         # tall chroma tiles / wide slices
 run(192, 108, "yuv422p10le", 4, 4, level=3, coder=0, context=1)                   # large context model lists, five-table decode
 run(176, 144, "yuv420p", 4, 3, level=3, coder=0, slices=4)                        # Golomb-Rice lists
