@@ -556,7 +556,7 @@ __global__ void __launch_bounds__(32 * kDecWarps, MINB) k_decode(const DecDevice
                 // the coder as warp 0 left it behind the luma plane, and the slice header it read
                 volatile int *pub = &s_pub;
                 int spins = 0;
-                while (*pub <= nhand && ++spins < (1 << 27)) __nanosleep(200);
+                while (*pub <= nhand && ++spins < (1 << 25)) __nanosleep(1000);   // (a luma plane takes milliseconds)
                 __threadfence_block();
                 if (*pub <= nhand) bad = 1;                      // (never seen: warp 0 hands over every slice it starts)
                 else {
