@@ -98,8 +98,8 @@ def test_non_keyframe_first_is_refused(B):
         d.decode(pkts[1])
     assert e.value.code == -1094995529      # AVERROR_INVALIDDATA (ffv1dec.c:930-935)
 
-@pytest.mark.parametrize("env", [{"FFV1B200_DEC_SMEM": "0"}, {"FFV1B200_DEC_PIPE": "0", "FFV1B200_DEC_MINB": "12"},
-                                 {"FFV1B200_DEC_SMEM": "0", "FFV1B200_DEC_MINB": "12"}, {"FFV1B200_DEC_PIPE": "0"},
+@pytest.mark.parametrize("env", [{"FFV1B200_DEC_SMEM": "0", "FFV1B200_DEC_PIPE": "0"}, {"FFV1B200_DEC_PIPE": "0", "FFV1B200_DEC_MINB": "12"},
+                                 {"FFV1B200_DEC_SMEM": "0", "FFV1B200_DEC_MINB": "12", "FFV1B200_DEC_PIPE": "0"}, {"FFV1B200_DEC_PIPE": "0"},
                                  {"FFV1B200_DEC_PIPE": "1"}],
                          ids=["models_global", "dense_regs", "models_global_dense_regs", "one_warp_per_chain", "two_warps_per_chain"])
 def test_large_batch_kernel_variants(B, env, monkeypatch):
