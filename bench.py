@@ -401,8 +401,10 @@ def main():
             try:                                     # the same encode through the AVCodec shim and the reference's libavcodec
                 sys.path.insert(0, os.path.join(ROOT, "tools"))
                 import bench_avcodec
+                # as many frames as the e2e leg codes (its batches are 1024 frames: twice the steps)
                 line["e2e_avcodec"] = bench_avcodec.run(clip, gold if clip_ok else None, batch=B, opts=OPTS, gop=GOP,
-                                                        ref_frames=0 if args.no_cpu_baseline else 64)
+                                                        ref_frames=0 if args.no_cpu_baseline else 64,
+                                                        rounds=max(10, 2 * args.steps * B // 2048))
             except Exception as ex:
                 line["e2e_avcodec"] = {"value": None, "note": repr(ex)}
         if world == 1 and not args.no_cpu_baseline:

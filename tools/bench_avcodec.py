@@ -89,7 +89,7 @@ def run(clip, gold, batch=1024, opts=None, gop=16, ref_frames=64, copy_threads=8
            "rounds": rounds,
            "note": "avcodec_encode_video2(-c:v ffv1_b200) of the reference's libavcodec: pageable AVFrames in, AVPackets out, "
                    "first frame to last drained packet, i.e. with the pipeline's fill and drain (oracle/ref_harness.c:ffv1ref_bench_encode; "
-                   "5 batches: 5.9 k frames/s, 10 batches: 8.0 k)"}
+                   "5 batches: 5.9 k frames/s, 10 batches: 6.5-8.0 k depending on the box)"}
     if ref_frames:
         threads = min(os.cpu_count() or 1, 24)
         dtr, _, _ = encode("ffv1", clip, W, H, FMT, ref_frames, gop, opts, threads=threads)
