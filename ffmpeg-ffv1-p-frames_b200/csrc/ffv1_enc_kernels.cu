@@ -583,7 +583,7 @@ void launch_replay(const EncDeviceTables &t, const EncBatch &b, cudaStream_t s)
 //    instructions, split between the FMA pipe (mul.hi, subtract, add, shifts as mad) and the ALU pipe (select,
 //    compares, permutes) -- each pipe takes a warp instruction every other cycle, so the mix is what sets the speed.
 //  * The decision stream of a lane is produced by a small generator (prefix | runs of its slice | closing decision) that
-//    runs chunks of eight 16-byte vectors ahead of the coder through cp.async, across run boundaries.
+//    runs a chunk of 14 16-byte vectors ahead of the coder (bulk copies, see k_rangecode), across run boundaries.
 //  * A vector holds 8 decisions; entries behind the end of a run are replaced by 0x0000, which is an exact no-op for
 //    the coder (p = 0, bit = 0: range1 = 0, nothing moves, no renormalisation; real states are 1..255).
 //  * Output entries go through a per-lane ring in shared memory laid out [row][lane] (a lane always hits its own bank:
@@ -668,8 +668,13 @@ struct RacGen {
 };
 
 constexpr int kRangeThreads = 32;
-constexpr int kRangeChunk = 8;            // 16-byte decision vectors per chunk (128 bytes per lane)
-constexpr int kRangeDepth = 3;            // chunk slots per lane: kRangeDepth-1 chunks in flight
+// One 224-byte chunk in flight per lane (it has the ~1800 decisions' time of the chunk being coded to arrive): the per-lane
+// issue of the bulk copies is a fifth of the kernel's instructions at 128-byte chunks, and 14 vectors is what still lets
+// eleven warps share an SM (19.5 KB each).  8 vectors x 3 slots -> 14 x 2: 34.4 -> 30.7 ms per 2048 frames (44.7 -> 34.7 on
+// the boxes of the pool where the kernel runs slow).  The descriptor keeps the vector count in 4 bits: at most 15.
+constexpr int kRangeChunk = 14;           // 16-byte decision vectors per chunk (224 bytes per lane)
+constexpr int kRangeDepth = 2;            // chunk slots per lane: kRangeDepth-1 chunks in flight
+static_assert(kRangeChunk <= 15 && (kRangeChunk & 1) == 0, "4-bit vector count; chunk + 16 bytes must be an odd number of 16-byte units");
 constexpr int kRangeLanePitch = kRangeChunk * 16 + 16;    // bytes between the chunks of neighbouring lanes inside a slot: an odd
                                                           // number of 16-byte units, so the 128-bit reads of a warp spread over all banks
 
@@ -699,7 +704,7 @@ __device__ __forceinline__ void rc_mbar_wait(uint32_t bar, uint32_t phase)
 // load/store path while their addresses are translated -- with batches beyond the reach of the TLBs (>= 1024 frames)
 // every coder step then waited behind them (the kernel took twice as long per decision as with 512-frame batches).  A
 // bulk copy is a descriptor handed to the copy engine: translation and transfer happen off the warp's path, one request
-// per 128 bytes instead of eight.
+// per chunk of 224 bytes instead of fourteen loads.
 template <int LANES>        // coders per warp known at compile time (32: the common case, immediate strides) or 0 = `lanes_rt`
 __global__ void __launch_bounds__(kRangeThreads) k_rangecode(const EncDeviceTables T, const EncBatch B, const int lanes_rt)
 {
