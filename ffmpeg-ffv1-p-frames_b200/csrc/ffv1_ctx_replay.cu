@@ -714,7 +714,7 @@ __global__ void __launch_bounds__(kCtxThreads, 1) k_replay_ctx(const EncDeviceTa
     const uint32_t lut_base = (uint32_t)__cvta_generic_to_shared(s_lut);
     for (int i = tid; i < 512; i += kCtxThreads) s_lut[i] = T.trans_lut[i];
     if (B.status[0]) return;
-    const int chain = blockIdx.x;
+    const int chain = chain_of_block(L, T.slices);          // longest chains first
     const int pc = chain % L.npc, s = (chain / L.npc) % L.nslices, seg = chain / (L.npc * L.nslices);
     const SliceGeom &g = T.slices[s];
     const int f0 = B.seg_first[seg], f1 = B.seg_first[seg + 1];
@@ -929,21 +929,7 @@ __global__ void __launch_bounds__(THREADS, (TILED ? 768 : 1024) / THREADS) k_rep
         s_mask[tid] = make_uint2(sl ? 0u : v, bt);
     }
     if (B.status[0]) return;
-    // CTAs are handed out in blockIdx order: the chains of the plane context with the most samples (luma: twice the
-    // chroma chains' work for 4:2:0) go first, so that what runs while the grid drains is short chains
-    int chain = blockIdx.x;
-    {
-        const int per = (int)gridDim.x / L.npc, grp = chain / per, rest = chain - grp * per;
-        const SliceGeom &g0 = T.slices[0];
-        uint32_t n0 = g0.pc_samples[0], n1 = L.npc > 1 ? g0.pc_samples[1] : 0u, n2 = L.npc > 2 ? g0.pc_samples[2] : 0u;
-        int p0 = 0, p1 = 1, p2 = 2;
-        if (n1 > n0) { const int t = p0; p0 = p1; p1 = t; const uint32_t u = n0; n0 = n1; n1 = u; }
-        if (n2 > n1) {
-            { const int t = p1; p1 = p2; p2 = t; const uint32_t u = n1; n1 = n2; n2 = u; }
-            if (n1 > n0) { const int t = p0; p0 = p1; p1 = t; }
-        }
-        chain = rest * L.npc + (grp == 0 ? p0 : (grp == 1 ? p1 : p2));
-    }
+    const int chain = chain_of_block(L, T.slices);          // longest chains first
     const int pc = chain % L.npc, s = (chain / L.npc) % L.nslices, seg = chain / (L.npc * L.nslices);
     const SliceGeom &sg = T.slices[s];
     const int f0 = B.seg_first[seg], f1 = B.seg_first[seg + 1];

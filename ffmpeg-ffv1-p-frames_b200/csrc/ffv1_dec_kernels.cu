@@ -909,10 +909,12 @@ void launch_decode(const DecDeviceTables &t_in, const DecBatch &b, cudaStream_t 
     }
     // Planar YUV, few enough chains for one CTA each: two warps per chain, luma one frame ahead of
     // chroma (k_decode<.., PIPE>).  FFV1B200_DEC_PIPE=0/1 overrides the choice (1: whenever the stream allows it).
-    if (t.smem_model && t.smem_ring_w && !t.colorspace && t.chroma_planes && !t.ya8 && b.nframes >= 2 * b.nseg) {      // (intra-only: nothing to overlap)
+    if (t.smem_ring_w && !t.colorspace && t.chroma_planes && !t.ya8 && b.nframes >= 2 * b.nseg) {      // (intra-only: nothing to overlap)
         // Measured and dropped: the second warp's models in shared memory as well (no faster -- the luma warp sets the pace --
-        // and fewer CTAs per SM); every model in global memory with the 80-register build for batches of up to 1776 chains
-        // (768 frames: 1044 against 1062 frames/s with one warp per chain, 1024 frames: 1062 against 1186).
+        // and fewer CTAs per SM); for the small context model, every model in global memory with the 80-register build for
+        // batches of up to 1776 chains (768 frames: 1044 against 1062 frames/s with one warp per chain, 1024 frames: 1062
+        // against 1186).  The large context model (no model fits shared memory: t.smem_model == 0) comes with few, long
+        // chains (4 slices per frame): there the second warp is pure gain.
         const int smem = t.smem_model + kDecWarps * t.smem_ring_w * kDecSmemRingBytes;
         int nb = 0;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_decode<8, true>, 32 * kDecWarps, smem);

@@ -1104,7 +1104,7 @@ __global__ void __launch_bounds__(kGrThreads, 8) k_gr_replay(const EncDeviceTabl
     extern __shared__ __align__(16) uint32_t s_gr[];                        // [2][nctx] the window's part of every list
     const Layout &L = T.layout;
     const int tid = threadIdx.x;
-    const int chain = blockIdx.x;
+    const int chain = chain_of_block(L, T.slices);          // longest chains first
     const int pc = chain % L.npc, s = (chain / L.npc) % L.nslices, seg = chain / (L.npc * L.nslices);
     const SliceGeom &g = T.slices[s];
     const int f0 = B.seg_first[seg], f1 = B.seg_first[seg + 1];

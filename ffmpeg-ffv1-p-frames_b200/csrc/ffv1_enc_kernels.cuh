@@ -78,6 +78,25 @@ struct EncDeviceTables {
     int32_t nvar;                       // slice-header variants per (slice, keyframe flag): 15 for version-4 RGB, else 1
 };
 
+// One CTA per (GOP segment, slice, plane context) chain: CTAs are handed out in blockIdx order, so the chains of the plane
+// context with the most samples (luma: twice the chroma chains' work for 4:2:0; B+R for planar RGB) come first and what
+// runs while the grid drains is short chains.  Returns the chain index (seg * nslices + slice) * npc + pc of this CTA.
+#ifdef __CUDACC__
+__device__ __forceinline__ int chain_of_block(const Layout &L, const SliceGeom *slices)
+{
+    const int per = (int)gridDim.x / L.npc, grp = (int)blockIdx.x / per, rest = (int)blockIdx.x - grp * per;
+    const SliceGeom &g0 = slices[0];
+    uint32_t n0 = g0.pc_samples[0], n1 = L.npc > 1 ? g0.pc_samples[1] : 0u, n2 = L.npc > 2 ? g0.pc_samples[2] : 0u;
+    int p0 = 0, p1 = 1, p2 = 2;
+    if (n1 > n0) { const int t = p0; p0 = p1; p1 = t; const uint32_t u = n0; n0 = n1; n1 = u; }
+    if (n2 > n1) {
+        { const int t = p1; p1 = p2; p2 = t; const uint32_t u = n1; n1 = n2; n2 = u; }
+        if (n1 > n0) { const int t = p0; p0 = p1; p1 = t; }
+    }
+    return rest * L.npc + (grp == 0 ? p0 : (grp == 1 ? p1 : p2));
+}
+#endif
+
 int  pixel_smem_bytes(const Layout &L);
 void launch_pixel(const EncDeviceTables &t, const EncBatch &b, cudaStream_t s);
 // version 4, RGB: per-slice choice among the 15 RCT coefficient pairs (choose_rct_params, ffv1enc.c:1064-1144) -> b.rct_idx
