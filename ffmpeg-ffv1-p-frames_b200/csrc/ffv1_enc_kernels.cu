@@ -1481,16 +1481,47 @@ __device__ __forceinline__ uint32_t pack_resolved_byte(const uint16_t *v, uint32
 
 // One CTA per (frame, slice): copy the coder output to its final place, append the 24-bit length and the
 // error-check trailer.
-//   CRC (libavutil AV_CRC_32_IEEE: MSB-first 0x04C11DB7, init 0, no final xor = plain polynomial remainder):
-//   every thread runs a slicing-by-4 table CRC over one contiguous, word-aligned chunk of the payload; by linearity
-//   crc(message) = XOR over chunks of crc(chunk) * x^(8 * bytes after the chunk) mod P, so each thread scales its
-//   own partial CRC (square-and-multiply over precomputed x^(8*2^j)) and a XOR reduction finishes the job.
+//   CRC (libavutil AV_CRC_32_IEEE: MSB-first 0x04C11DB7, init 0, no final xor = plain polynomial remainder
+//   M(x) * x^32 mod P), computed in the SAME pass as the copy and over the same destination-aligned words: thread t
+//   takes the words t, t + 256, t + 512, ... (the accesses of a warp are contiguous) and keeps
+//       c = sum_j W[t + 256 j] * x^(32 * 256 * (J - 1 - j)) mod P      (Horner: c = c * x^8192 mod P  xor  W)
+//   where the multiplication by the constant x^8192 is four table lookups on the bytes of c -- the cost of an ordinary
+//   slicing-by-4 step.  By linearity crc(message) = XOR over threads of c * x^(8 * (bytes behind the thread's last word)
+//   + 32) mod P (square-and-multiply over precomputed x^(8*2^j)), plus the few head / tail / trailer bytes, which one
+//   thread each folds byte by byte.  (Before: a second pass in which every thread walked a contiguous chunk -- the 32
+//   lanes of a load 400 bytes apart -- took twice the copy's time.)
 //   Copy: the packet position has arbitrary byte alignment, so destination-aligned 32-bit words are built from two
-//   source words with a funnel shift; the stores of a warp are contiguous.
+//   source words with a funnel shift (Golomb-Rice) or from the 16-bit entries; the stores of a warp are contiguous.
+__device__ uint32_t g_pack_tab0[256];          // (b * x^32) mod P: the byte-wise table
+__device__ uint32_t g_pack_mul[4][256];        // (b * x^(8k + 32 * kPackThreads)) mod P
+__device__ uint32_t g_pack_pow[32];            // x^(8 * 2^j) mod P
+
+__global__ void __launch_bounds__(1024) k_pack_init()
+{
+    __shared__ uint32_t s_pow[32];
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        uint32_t p = 0x100u;                    // x^8
+        for (int j = 0; j < 32; j++) { s_pow[j] = p; g_pack_pow[j] = p; p = gf_mulmod(p, p); }
+    }
+    __syncthreads();
+    if (tid < 256) {
+        uint32_t c = (uint32_t)tid << 24;
+#pragma unroll
+        for (int k = 0; k < 8; k++) c = (c & 0x80000000u) ? (c << 1) ^ 0x04C11DB7u : (c << 1);
+        g_pack_tab0[tid] = c;
+    }
+    // x^(32 * 256) = x^(8 * 2^10)
+    static_assert(kPackThreads == 256, "the stride multiplier below is x^(8 * 2^10)");
+    const int k = tid >> 8, bb = tid & 255;
+    g_pack_mul[k][bb] = gf_mulmod((uint32_t)bb << (8 * k), s_pow[10]);
+}
+
 template <bool C16>       // C16: the coder output is k_rangecode's 16-bit entries (range-coder modes); else plain bytes (Golomb-Rice)
 __global__ void __launch_bounds__(kPackThreads) k_pack_slices(const EncDeviceTables T, const EncBatch B)
 {
-    __shared__ uint32_t s_tab[4][256];          // s_tab[k][b] = (b * x^(8k+32)) mod P
+    __shared__ uint32_t s_tab0[256];            // (b * x^32) mod P
+    __shared__ uint32_t s_mul[4][256];          // (b * x^(8k + 8192)) mod P
     __shared__ uint32_t s_pow[32];              // x^(8 * 2^j) mod P
     __shared__ uint32_t s_red[kPackThreads / 32];
     const Layout &L = T.layout;
@@ -1499,21 +1530,10 @@ __global__ void __launch_bounds__(kPackThreads) k_pack_slices(const EncDeviceTab
     const int tid = threadIdx.x, lane = tid & 31;
     if (B.status[0] | B.status[1] | B.status[2]) return;
 
-    for (int n = tid; n < 256; n += kPackThreads) {
-        uint32_t c = (uint32_t)n << 24;
+    s_tab0[tid] = g_pack_tab0[tid];
 #pragma unroll
-        for (int k = 0; k < 8; k++) c = (c & 0x80000000u) ? (c << 1) ^ 0x04C11DB7u : (c << 1);
-        s_tab[0][n] = c;
-    }
-    if (tid == 0) {
-        uint32_t p = 0x100u;                    // x^8
-        for (int j = 0; j < 32; j++) { s_pow[j] = p; p = gf_mulmod(p, p); }
-    }
-    __syncthreads();
-    for (int n = tid; n < 256; n += kPackThreads) {
-        uint32_t c = s_tab[0][n];
-        for (int k = 1; k < 4; k++) { c = (c << 8) ^ s_tab[0][c >> 24]; s_tab[k][n] = c; }
-    }
+    for (int k = 0; k < 4; k++) s_mul[k][tid] = g_pack_mul[k][tid];
+    if (tid < 32) s_pow[tid] = g_pack_pow[tid];
     const bool has_len = (T.version > 2) || s > 0;
     unsigned long long off = B.pkt_off[f];
     for (int k = 0; k < s; k++) off += B.slice_bytes[f * ns + k] + ((T.version > 2 || k > 0) ? 3 : 0) + (T.ec ? 5 : 0);
@@ -1524,91 +1544,92 @@ __global__ void __launch_bounds__(kPackThreads) k_pack_slices(const EncDeviceTab
     const uint32_t nent = nb + 1u;                                        // entries of the slice (C16)
     __syncthreads();
 
-    // ---- copy: head bytes up to the first aligned destination word, aligned words, tail bytes
-    if (C16) {
-        const uint32_t head = min(nb, (uint32_t)((4u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 3u)) & 3u));
-        if ((uint32_t)tid < head) dst[tid] = (uint8_t)pack_resolved_byte(v16, (uint32_t)tid, nent);
-        const uint32_t nwords = (nb - head) >> 2;
-        uint32_t *dst32 = reinterpret_cast<uint32_t *>(dst + head);
-        for (uint32_t w = tid; w < nwords; w += kPackThreads)
-            dst32[w] = __byte_perm(pack_resolved_be(v16, head + 4u * w, nent), 0u, 0x0123);
-        const uint32_t done = head + nwords * 4u;
-        if ((uint32_t)tid < nb - done) dst[done + tid] = (uint8_t)pack_resolved_byte(v16, done + (uint32_t)tid, nent);
-        if (tid == 0) {
-            uint32_t q = nb;
-            if (has_len) { dst[q] = (uint8_t)(nb >> 16); dst[q + 1] = (uint8_t)(nb >> 8); dst[q + 2] = (uint8_t)nb; q += 3; }
-            if (T.ec) dst[q] = 0;
-        }
-    } else {
-        const uint32_t head = min(nb, (uint32_t)((4u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 3u)) & 3u));
-        if ((uint32_t)tid < head) dst[tid] = src[tid];
-        const uint32_t nwords = (nb - head) >> 2;
-        const uint32_t *src32 = reinterpret_cast<const uint32_t *>(src);
-        uint32_t *dst32 = reinterpret_cast<uint32_t *>(dst + head);
-        const uint32_t sh = head * 8u;                                    // source byte offset inside a word
-        for (uint32_t w = tid; w < nwords; w += kPackThreads) {
+    // ---- head bytes up to the first aligned destination word, aligned words, tail bytes
+    const uint32_t head = min(nb, (uint32_t)((4u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 3u)) & 3u));
+    const uint32_t nwords = (nb - head) >> 2;
+    const uint32_t done = head + nwords * 4u;
+    const uint32_t tail_bytes = (has_len ? 3u : 0u) + 1u;                 // len24 | 0x00 (the CRC covers them)
+    uint32_t *dst32 = reinterpret_cast<uint32_t *>(dst + head);
+    const uint32_t *src32 = reinterpret_cast<const uint32_t *>(src);
+    const uint32_t sh = head * 8u;                                        // source byte offset inside a word (Golomb-Rice)
+    uint32_t c = 0u;                                                      // bit k = coefficient of x^k
+    uint32_t last_w = 0u;
+    bool any = false;
+    for (uint32_t w = tid; w < nwords; w += kPackThreads) {
+        uint32_t le;                                                      // the word as it lies in memory
+        if (C16) le = __byte_perm(pack_resolved_be(v16, head + 4u * w, nent), 0u, 0x0123);
+        else {
             const uint32_t lo = src32[w];
             const uint32_t hi = head ? src32[w + 1] : 0u;                 // within the scratch region (cap is padded)
-            dst32[w] = head ? __funnelshift_r(lo, hi, sh) : lo;
+            le = head ? __funnelshift_r(lo, hi, sh) : lo;
         }
-        const uint32_t done = head + nwords * 4u;
-        if ((uint32_t)tid < nb - done) dst[done + tid] = src[done + tid];
+        dst32[w] = le;
+        c = s_mul[0][c & 0xFFu] ^ s_mul[1][(c >> 8) & 0xFFu] ^ s_mul[2][(c >> 16) & 0xFFu] ^ s_mul[3][c >> 24];
+        c ^= __byte_perm(le, 0u, 0x0123);                                 // first message byte = highest degree
+        last_w = w; any = true;
+    }
+    if ((uint32_t)tid < head) dst[tid] = C16 ? (uint8_t)pack_resolved_byte(v16, (uint32_t)tid, nent) : src[tid];
+    if ((uint32_t)tid < nb - done) dst[done + tid] = C16 ? (uint8_t)pack_resolved_byte(v16, done + (uint32_t)tid, nent) : src[done + tid];
+    if (tid == 0) {
         // trailer: 24-bit big-endian payload length, then 0x00 (the CRC itself is written below)
-        if (tid == 0) {
-            uint32_t q = nb;
-            if (has_len) { dst[q] = (uint8_t)(nb >> 16); dst[q + 1] = (uint8_t)(nb >> 8); dst[q + 2] = (uint8_t)nb; q += 3; }
-            if (T.ec) dst[q] = 0;
-        }
+        uint32_t q = nb;
+        if (has_len) { dst[q] = (uint8_t)(nb >> 16); dst[q + 1] = (uint8_t)(nb >> 8); dst[q + 2] = (uint8_t)nb; q += 3; }
+        if (T.ec) dst[q] = 0;
     }
     if (!T.ec) return;
 
-    // ---- CRC over payload | len24 | 0x00
-    const uint32_t tail_bytes = (has_len ? 3u : 0u) + 1u;
-    const uint32_t nw_all = nb >> 2;                                      // whole source words
-    const uint32_t per = (nw_all + kPackThreads - 1) / kPackThreads;      // words per thread
-    const uint32_t w0 = min(nw_all, (uint32_t)tid * per), w1 = min(nw_all, w0 + per);
-    uint32_t crc = 0;
-    {
-        const uint32_t *src32 = reinterpret_cast<const uint32_t *>(src);
-        for (uint32_t w = w0; w < w1; w++) {
-            // message bytes are MSB-first: fold crc in byte order
-            const uint32_t v = (C16 ? __byte_perm(pack_resolved_be(v16, 4u * w, nent), 0u, 0x0123) : src32[w]) ^ __byte_perm(crc, 0, 0x0123);
-            crc = s_tab[3][v & 0xFFu] ^ s_tab[2][(v >> 8) & 0xFFu] ^ s_tab[1][(v >> 16) & 0xFFu] ^ s_tab[0][v >> 24];
-        }
-    }
-    uint32_t after = (nw_all - w1) * 4u + (nb & 3u) + tail_bytes;         // message bytes behind this thread's chunk
-    if (tid == kPackThreads - 1) {
-        // the last thread also takes the 0..3 payload bytes behind the last whole word and the trailer bytes
-        for (uint32_t i = nw_all * 4u; i < nb; i++) crc = (crc << 8) ^ s_tab[0][(crc >> 24) ^ (C16 ? pack_resolved_byte(v16, i, nent) : (uint32_t)src[i])];
-        if (has_len) {
-            crc = (crc << 8) ^ s_tab[0][(crc >> 24) ^ ((nb >> 16) & 0xFFu)];
-            crc = (crc << 8) ^ s_tab[0][(crc >> 24) ^ ((nb >> 8) & 0xFFu)];
-            crc = (crc << 8) ^ s_tab[0][(crc >> 24) ^ (nb & 0xFFu)];
-        }
-        crc = (crc << 8) ^ s_tab[0][crc >> 24];                          // the 0x00 byte
-        after = 0;
+    // ---- CRC over payload | len24 | 0x00: scale the partial remainders to the end of the message and XOR them
+    uint32_t crc = 0u, after = 0u;               // crc = (this thread's bytes) * x^32 mod P, `after` message bytes behind them
+    if (any) {
+        // c is a plain remainder (no x^32 yet): four more bytes of shift
+        crc = c;
+        after = (nwords - 1u - last_w) * 4u + (nb - done) + tail_bytes + 4u;
     }
     if (crc) {
         uint32_t mult = 1u;
         for (int j = 0; after; j++, after >>= 1) if (after & 1u) mult = gf_mulmod(mult, s_pow[j]);
         crc = gf_mulmod(crc, mult);
     }
+    // the head bytes and the tail + trailer bytes: one thread each, byte by byte
+    uint32_t extra = 0u;
+    if (tid == 0) {
+        uint32_t h = 0u;
+        for (uint32_t i = 0; i < head; i++) h = (h << 8) ^ s_tab0[(h >> 24) ^ (C16 ? pack_resolved_byte(v16, i, nent) : (uint32_t)src[i])];
+        if (h) {
+            uint32_t aft = nb - head + tail_bytes, mult = 1u;
+            for (int j = 0; aft; j++, aft >>= 1) if (aft & 1u) mult = gf_mulmod(mult, s_pow[j]);
+            extra = gf_mulmod(h, mult);
+        }
+    }
+    if (tid == 1) {
+        uint32_t t = 0u;
+        for (uint32_t i = done; i < nb; i++) t = (t << 8) ^ s_tab0[(t >> 24) ^ (C16 ? pack_resolved_byte(v16, i, nent) : (uint32_t)src[i])];
+        if (has_len) {
+            t = (t << 8) ^ s_tab0[(t >> 24) ^ ((nb >> 16) & 0xFFu)];
+            t = (t << 8) ^ s_tab0[(t >> 24) ^ ((nb >> 8) & 0xFFu)];
+            t = (t << 8) ^ s_tab0[(t >> 24) ^ (nb & 0xFFu)];
+        }
+        t = (t << 8) ^ s_tab0[t >> 24];                                  // the 0x00 byte
+        extra = t;
+    }
+    crc ^= extra;
 #pragma unroll
     for (int d = 16; d; d >>= 1) crc ^= __shfl_xor_sync(0xFFFFFFFFu, crc, d);
     if (lane == 0) s_red[tid >> 5] = crc;
     __syncthreads();
     if (tid == 0) {
-        uint32_t c = 0;
-        for (int i = 0; i < kPackThreads / 32; i++) c ^= s_red[i];
+        uint32_t r = 0;
+        for (int i = 0; i < kPackThreads / 32; i++) r ^= s_red[i];
         const uint32_t mlen = nb + tail_bytes;
-        dst[mlen + 0] = (uint8_t)(c >> 24); dst[mlen + 1] = (uint8_t)(c >> 16);
-        dst[mlen + 2] = (uint8_t)(c >> 8);  dst[mlen + 3] = (uint8_t)c;
+        dst[mlen + 0] = (uint8_t)(r >> 24); dst[mlen + 1] = (uint8_t)(r >> 16);
+        dst[mlen + 2] = (uint8_t)(r >> 8);  dst[mlen + 3] = (uint8_t)r;
     }
 }
 
 void launch_pack(const EncDeviceTables &t, const EncBatch &b, cudaStream_t s)
 {
     k_pack_layout<<<1, 1024, 0, s>>>(t, b);
+    k_pack_init<<<1, 1024, 0, s>>>();            // constant tables (per device; a microsecond)
     if (t.layout.golomb) k_pack_slices<false><<<b.nframes * t.layout.nslices, kPackThreads, 0, s>>>(t, b);
     else                 k_pack_slices<true><<<b.nframes * t.layout.nslices, kPackThreads, 0, s>>>(t, b);
 }
