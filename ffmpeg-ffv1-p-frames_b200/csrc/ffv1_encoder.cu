@@ -278,7 +278,7 @@ int enqueue_kernels(FFV1B200Encoder *e, Slot &sl, cudaStream_t s)
         CU_TRY(launch_pass1_stats(t, b, e->d_rc_stat.p, e->d_rc_stat2.p, s));
         e->stats.kernel_launches++;
     }
-    e->stats.kernel_launches += L.golomb ? (e->golomb_lists ? 8 : 4) : (e->ctx_replay ? (L.tiled_lists ? 7 : 9) : 5);
+    e->stats.kernel_launches += L.golomb ? (e->golomb_lists ? 9 : 5) : (e->ctx_replay ? (L.tiled_lists ? 8 : 10) : 6);     // (k_pack_init included)
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaMemcpyAsync(sl.h_status.p, sl.d_status.p, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost, s));
     CU_TRY(cudaMemcpyAsync(sl.h_pkt_size.p, sl.d_pkt_size.p, sizeof(uint32_t) * nframes, cudaMemcpyDeviceToHost, s));
