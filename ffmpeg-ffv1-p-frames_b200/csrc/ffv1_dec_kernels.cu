@@ -490,6 +490,29 @@ constexpr int kDecSmemQuant = 2 * 5 * 256;
 
 constexpr int kDecWarps = 2;               // chains per CTA (they share the quantisation / transition tables)
 
+// The rectangle the slice grid gives slice `si` (ffv1.c:124-143), cleared in the planes psel picks (-1: all, 0: the first,
+// 1: all but the first).  Used when the pictures are written straight into a buffer nobody has cleared (DecBatch::zero_fill)
+// for slices that are missing, refused, or announce another rectangle: what the staged path's memset leaves there.
+__device__ void dec_zero_slice(const DecDeviceTables &T, uint8_t *cur, int si, int psel, int lane)
+{
+    const int gx = si % T.num_h_slices, gy = si / T.num_h_slices;
+    const int x0 = T.width * gx / T.num_h_slices, x1 = T.width * (gx + 1) / T.num_h_slices;
+    const int y0 = T.height * gy / T.num_v_slices, y1 = T.height * (gy + 1) / T.num_v_slices;
+    const int nsrc = T.colorspace ? (T.rgb32 ? 1 : 3) : (T.ya8 ? 1 : 1 + 2 * T.chroma_planes + T.transparency);
+    for (int p = 0; p < nsrc; p++) {
+        if ((psel == 0 && p != 0) || (psel == 1 && p == 0)) continue;
+        const bool chroma = !T.colorspace && !T.ya8 && T.chroma_planes && (p == 1 || p == 2);
+        const int hs = chroma ? T.hshift : 0, vs = chroma ? T.vshift : 0;
+        const int src_plane = (!T.colorspace && !T.ya8 && !T.chroma_planes && p == 1) ? 3 : p;
+        const int bpp = T.rgb32 ? 4 : (T.ya8 ? 2 : (T.bits > 8 ? 2 : 1));
+        const int bx0 = (x0 >> hs) * bpp, bx1 = (-((-x1) >> hs)) * bpp;
+        const int ry0 = y0 >> vs, ry1 = -((-y1) >> vs);
+        const int rb = bx1 - bx0;
+        for (int i = lane; i < rb * (ry1 - ry0); i += 32)
+            cur[(size_t)T.plane_off[src_plane] + (size_t)(ry0 + i / rb) * T.plane_pitch[src_plane] + bx0 + i % rb] = 0;
+    }
+}
+
 // PIPE (planar YUV): the two warps of a CTA work on ONE chain.  Inside a slice the planes follow each other
 // in one coder stream, but across the frames of a GOP the only thing a plane needs from the frame before is the model of
 // its own plane context (ffv1dec.c:419-420) -- luma of frame f+1 can be decoded while chroma of frame f still is.  Warp 0
@@ -538,7 +561,11 @@ __global__ void __launch_bounds__(32 * kDecWarps, MINB) k_decode(const DecDevice
     const long long probe_t0 = clock64();
 #endif
     for (int f = f0; f < f1; f++) {
-        if (si >= B.slice_count[f]) continue;
+        const int zsel = PIPE ? warp : -1;                       // the planes this warp writes
+        if (si >= B.slice_count[f]) {
+            if (B.zero_fill) dec_zero_slice(T, B.out + (size_t)f * T.frame_bytes, si, zsel, lane);
+            continue;
+        }
         const int fs = f * T.max_slices + si;
         const uint8_t *sbeg = B.pkt + B.pkt_off[f] + B.slice_start[fs];
         const uint32_t ssize = B.slice_size[fs];
@@ -634,6 +661,7 @@ __global__ void __launch_bounds__(32 * kDecWarps, MINB) k_decode(const DecDevice
         bad = __shfl_sync(0xFFFFFFFFu, bad, 0);
         if (PIPE) nhand++;
         if (bad) {
+            if (B.zero_fill) dec_zero_slice(T, B.out + (size_t)f * T.frame_bytes, si, zsel, lane);
             if (lane == 0) {
                 if (bad != 3) B.damaged[fs] |= 2u;               // (3: warp 0 has flagged the slice already)
                 if (PIPE && warp == 0) {
@@ -652,6 +680,16 @@ __global__ void __launch_bounds__(32 * kDecWarps, MINB) k_decode(const DecDevice
         qti[0] = __shfl_sync(0xFFFFFFFFu, qti[0], 0); qti[1] = __shfl_sync(0xFFFFFFFFu, qti[1], 0);
         qti[2] = __shfl_sync(0xFFFFFFFFu, qti[2], 0);
         v4 = __shfl_sync(0xFFFFFFFFu, v4, 0);
+        if (B.zero_fill) {
+            // a slice header may announce any rectangle: what it leaves of the grid's rectangle is cleared first
+            const int gx = si % T.num_h_slices, gy = si / T.num_h_slices;
+            const int nx0 = T.width * gx / T.num_h_slices, nx1 = T.width * (gx + 1) / T.num_h_slices;
+            const int ny0 = T.height * gy / T.num_v_slices, ny1 = T.height * (gy + 1) / T.num_v_slices;
+            if (sx != nx0 || sy != ny0 || sw != nx1 - nx0 || sh != ny1 - ny0) {
+                dec_zero_slice(T, B.out + (size_t)f * T.frame_bytes, si, zsel, lane);
+                __syncwarp();
+            }
+        }
         const int rct_by = v4 & 15, rct_ry = (v4 >> 4) & 15, coding_mode = (v4 >> 8) & 255;
         const bool pcm = coding_mode == 1;
 

@@ -41,6 +41,8 @@ struct DecBatch {
     int16_t *ring;                      // [nseg*max_slices][4][3][ring_w]
     const uint32_t *init_state;         // version 0/1: [nframes][3] range-coder low, range, bytes consumed behind the in-band header
     uint32_t *damaged;                  // [nframes][max_slices]: bit0 CRC mismatch, bit1 header/end-of-slice check failed
+    int32_t zero_fill;                  // `out` has not been cleared (pictures written straight into the caller's pinned buffer):
+                                        // the kernel clears the rectangle of every slice it does not decode as announced by the grid
 };
 
 void launch_dec_crc(const DecDeviceTables &t, const DecBatch &b, cudaStream_t s);

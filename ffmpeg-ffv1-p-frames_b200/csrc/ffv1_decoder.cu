@@ -30,6 +30,7 @@ struct FFV1B200Decoder {
     int nsets = 0, cur_set = 0, width = 0, height = 0;
     bool configured = false;          // version 0/1 streams are configured by their first keyframe
     bool key_frame_ok = false, have_prev = false;
+    bool grid_covers = true;          // the slice grid's rectangles cover every sample of every plane (see configure)
     int slice_count = 0;
     int64_t frame_bytes = 0;
     FFV1B200DecStats stats{};
@@ -83,6 +84,23 @@ static int configure(FFV1B200Decoder *d)
         t.smem_ring_w = (!c.colorspace && rw * kDecSmemRingBytes <= 11 * 1024) ? rw : 0;
     }
 
+    // Subsampled planes: slice i covers [x0 >> shift, (x0 >> shift) + ceil(w / 2^shift)), which can stop short of the next
+    // slice's first chroma column (4:1:0 / 4:1:1 on odd grids): such samples are never coded, the reference leaves them as
+    // the frame allocator gave them, this decoder returns 0 there -- from the staged copy's memset, so streams with such
+    // holes do not take the direct write into pinned memory.
+    {
+        auto covers = [](int size, int nsl, int shift) {
+            int reach = 0;
+            for (int i = 0; i < nsl; i++) {
+                const int a = size * i / nsl, b = size * (i + 1) / nsl;
+                if ((a >> shift) > reach) return false;
+                reach = std::max(reach, (a >> shift) + (((b - a) + (1 << shift) - 1) >> shift));
+            }
+            return reach >= ((size + (1 << shift) - 1) >> shift);
+        };
+        d->grid_covers = c.colorspace || !c.chroma_planes ||
+                         (covers(c.width, c.num_h_slices, c.chroma_h_shift) && covers(c.height, c.num_v_slices, c.chroma_v_shift));
+    }
     CU_TRY(d->d_quant.upload(&c.quant_tables[0][0][0], 2 * 5 * 256, d->stream));
     uint8_t lut[512];
     coder_state_tables(c, lut, lut + 256);
@@ -287,15 +305,33 @@ int ffv1b200_dec_decode_host(FFV1B200Decoder *d, int n, const uint8_t *const *pk
     CU_TRY(cudaMemcpyAsync(d->d_seg_set.p, d->h_seg_set.p, sizeof(int32_t) * nseg, cudaMemcpyHostToDevice, s));
     CU_TRY(cudaMemsetAsync(d->d_damaged.p, 0, sizeof(uint32_t) * n * ms, s));
     if (inband) CU_TRY(cudaMemcpyAsync(d->d_init_state.p, d->h_init_state.p, sizeof(uint32_t) * 3 * n, cudaMemcpyHostToDevice, s));
+    // An output buffer in pinned, device-mapped memory (ffv1b200_host_alloc, cudaHostAlloc, torch pin_memory) is written by
+    // the kernel directly -- the pictures cross the bus while the batch is still being decoded (4.5 GB/s of posted writes
+    // at the decoder's pace) instead of in a copy of their own behind it; FFV1B200_DEC_ZEROCOPY=0 keeps the staged copy
+    uint8_t *zc_out = nullptr;
+    {
+        const char *ev = getenv("FFV1B200_DEC_ZEROCOPY");
+        cudaPointerAttributes at{};
+        if (!(ev && atoi(ev) == 0) && d->grid_covers && cudaPointerGetAttributes(&at, out) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) {
+            // (the last byte must belong to the same mapping)
+            cudaPointerAttributes ae{};
+            const size_t span = (size_t)n * d->frame_bytes;
+            if (cudaPointerGetAttributes(&ae, out + span - 1) == cudaSuccess && ae.type == cudaMemoryTypeHost &&
+                ae.devicePointer == (uint8_t *)at.devicePointer + span - 1)
+                zc_out = (uint8_t *)at.devicePointer;
+        }
+        cudaGetLastError();
+    }
     // samples no slice covers (chroma columns cut off by a slice edge that is not on the chroma grid) stay 0
-    CU_TRY(cudaMemsetAsync(d->d_out.p, 0, (size_t)n * d->frame_bytes, s));
+    if (!zc_out) CU_TRY(cudaMemsetAsync(d->d_out.p, 0, (size_t)n * d->frame_bytes, s));
 
     DecBatch b{};
     b.nframes = n; b.nseg = nseg;
     b.seg_first = d->d_seg_first.p; b.seg_set = d->d_seg_set.p; b.frame_key = d->d_frame_key.p;
     b.pkt = d->d_pkt.p; b.pkt_off = d->d_pkt_off.p; b.slice_start = d->d_slice_start.p; b.slice_size = d->d_slice_size.p;
-    b.slice_count = d->d_slice_count.p; b.out = d->d_out.p; b.prev_frame = d->have_prev ? d->d_prev.p : nullptr;
+    b.slice_count = d->d_slice_count.p; b.out = zc_out ? zc_out : d->d_out.p; b.prev_frame = d->have_prev ? d->d_prev.p : nullptr;
     b.state = d->d_state.p; b.ring = d->d_ring.p; b.damaged = d->d_damaged.p; b.init_state = d->d_init_state.p;
+    b.zero_fill = zc_out ? 1 : 0;
 
     cudaEventRecord(d->ev[1], s);
     launch_dec_crc(d->tab, b, s);
@@ -312,15 +348,15 @@ int ffv1b200_dec_decode_host(FFV1B200Decoder *d, int n, const uint8_t *const *pk
         if (damaged) damaged[f] = mask;
         if (mask) { launch_conceal(d->tab, b, f, s); d->stats.kernel_launches++; }     // in frame order: a frame may need its predecessor's fix
     }
-    CU_TRY(cudaMemcpyAsync(out, d->d_out.p, (size_t)n * d->frame_bytes, cudaMemcpyDeviceToHost, s));
-    CU_TRY(cudaMemcpyAsync(d->d_prev.p, d->d_out.p + (size_t)(n - 1) * d->frame_bytes, (size_t)d->frame_bytes, cudaMemcpyDeviceToDevice, s));
+    if (!zc_out) CU_TRY(cudaMemcpyAsync(out, d->d_out.p, (size_t)n * d->frame_bytes, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaMemcpyAsync(d->d_prev.p, b.out + (size_t)(n - 1) * d->frame_bytes, (size_t)d->frame_bytes, cudaMemcpyDefault, s));
     cudaEventRecord(d->ev[3], s);
     CU_TRY(cudaStreamSynchronize(s));
     float t0; cudaEventElapsedTime(&t0, d->ev[0], d->ev[3]); d->stats.ms_total += t0;
     cudaEventElapsedTime(&t0, d->ev[1], d->ev[2]); d->stats.ms_decode_kernel += t0;
     d->stats.frames += n;
     d->stats.h2d_bytes += (int64_t)off + (int64_t)n * (13 + 8 * ms) + 8 * nseg;
-    d->stats.d2h_bytes += (int64_t)n * d->frame_bytes + 4 * (int64_t)n * ms;
+    d->stats.d2h_bytes += (int64_t)n * d->frame_bytes + 4 * (int64_t)n * ms;      // (zero-copy: the same bytes, written by the kernel)
     d->cur_set = d->h_seg_set.p[nseg - 1];
     d->key_frame_ok = kfo; d->slice_count = scount; d->have_prev = true;
     return n;

@@ -247,7 +247,9 @@ int  ffv1b200_dec_info(const FFV1B200Decoder *dec, FFV1B200DecInfo *info);
  *   out + i*frame_bytes      : decoded frame i (planes back to back, as av_image_copy_to_buffer(align=1))
  *   key_flags[i]             : AVFrame.key_frame;  damaged[i] : bit s set = slice s failed CRC/end check
  *                              (and was concealed from the previous frame, ffv1dec.c:998-1021)
- * The first packet of a shard must be a keyframe (ffv1dec.c:930-935) unless state carried over from the previous call. */
+ * The first packet of a shard must be a keyframe (ffv1dec.c:930-935) unless state carried over from the previous call.
+ * `out` may be pageable memory (the pictures are staged on the device and copied behind the batch) or pinned memory that the
+ * device can address (ffv1b200_host_alloc, cudaHostAlloc): the decode kernel then writes the pictures there itself. */
 int  ffv1b200_dec_decode_host(FFV1B200Decoder *dec, int npackets,
                               const uint8_t *const *pkt_data, const int *pkt_size,
                               uint8_t *out, size_t out_cap, int *key_flags, uint64_t *damaged);

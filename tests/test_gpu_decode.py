@@ -119,3 +119,56 @@ def test_large_batch_kernel_variants(B, env, monkeypatch):
         for i in range(len(pkts)):
             assert got[i][2] == 0
             assert np.array_equal(got[i][0], ref[i][0]), "%s: frame %d differs (%s)" % (cid, i, env)
+
+
+def _pinned(nbytes):
+    import torch
+    return torch.empty(nbytes, dtype=torch.uint8, pin_memory=True).numpy()
+
+@pytest.mark.parametrize("cid", ["c2_gop_range_24sl", "fate_ffv1_golomb", "c3_422p10_ctx1", "c4_gbrp14_30sl", "yuva420p", "yuv410p_odd", "v0_range"])
+def test_pictures_written_straight_into_pinned_memory(B, cid):
+    """an output array in pinned (device-mapped) host memory is written by the kernel itself, no copy behind the batch:
+    same pictures as through the staged copy, for every layout family"""
+    sel = [c for c in CASES if c[0] == cid]
+    if not sel:
+        pytest.skip("no such case")
+    case = sel[0]
+    _, w, h, fmt, opts, kind, n = case
+    frames, extradata, pkts, ref = oracle_stream(case)
+    fb = len(ref[0][0])
+    out = _pinned(len(pkts) * fb)
+    out[:] = 0xA5                                                         # nothing may be left of this
+    got = B.FFV1Decoder(w, h, extradata, max_batch_frames=len(pkts)).decode_batch(pkts, out=out)
+    for i in range(len(pkts)):
+        assert got[i][2] == 0
+        assert np.array_equal(got[i][0], ref[i][0]), "%s: frame %d differs" % (cid, i)
+
+def test_refused_and_damaged_slices_in_pinned_memory(B, monkeypatch):
+    """slices the decoder refuses (header garbage) or conceals leave the same bytes in a pinned output array (cleared by
+    the kernel) as in a staged one (cleared by a memset)"""
+    case = [c for c in CASES if c[0] == "c2_gop_range_24sl"][0]
+    _, w, h, fmt, opts, kind, n = case
+    frames, extradata, pkts, ref = oracle_stream(case)
+    fb = len(ref[0][0])
+    bad0 = bytearray(pkts[0])
+    # second slice of the first frame: its first bytes hold the slice header
+    sizes, end = [], len(bad0)
+    for si in range(23, -1, -1):
+        size = int.from_bytes(pkts[0][end - 8:end - 5], "big") + 8
+        sizes.insert(0, size); end -= size
+    assert end == 0
+    start1 = sizes[0]
+    for k in range(12):
+        bad0[start1 + k] = 0xFF                                           # refused or garbage: flagged either way, nothing to conceal from
+    bad2 = bytearray(pkts[2]); bad2[len(bad2) // 3] ^= 0x40               # a CRC error in a later frame: concealed from frame 1
+    stream = [bytes(bad0), pkts[1], bytes(bad2), pkts[3]]
+    res = {}
+    for mode in ("staged", "pinned"):
+        out = _pinned(len(stream) * fb) if mode == "pinned" else np.empty(len(stream) * fb, np.uint8)
+        out[:] = 0x5A
+        got = B.FFV1Decoder(w, h, extradata, max_batch_frames=len(stream)).decode_batch(stream, out=out)
+        res[mode] = [(g[0].copy(), g[1], g[2]) for g in got]
+    assert res["staged"][0][2] != 0 and res["staged"][2][2] != 0
+    for a, b in zip(res["staged"], res["pinned"]):
+        assert a[1] == b[1] and a[2] == b[2]
+        assert np.array_equal(a[0], b[0])

@@ -61,7 +61,7 @@ def run(n=256, batch=None, coder=1, cpu_frames=0):
     return {"value": n / dt, "unit": "frames/s", "frames": n, "batch": batch, "round_trip": "bit-exact",
             "coder": coder, "cpu_baseline": cpu,
             "kernel_fps": 2 * n / (st["ms_decode_kernel"] * 1e-3) if st.get("ms_decode_kernel") else None,
-            "note": "ffv1b200_dec_decode_host: host packets in, host frames out (%s), copies included; "
+            "note": "ffv1b200_dec_decode_host: host packets in, host frames out (%s: the kernel writes them there itself), packet copy included; "
                     "k_decode = one (GOP, slice) chain per warp, or per warp pair with luma a frame ahead of chroma when the batch has few chains; serial inside a plane like decode_line"
                     % ("pinned host memory" if pinned else "pageable numpy buffers")}
 
