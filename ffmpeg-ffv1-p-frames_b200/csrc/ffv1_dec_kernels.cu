@@ -522,6 +522,7 @@ __device__ void dec_zero_slice(const DecDeviceTables &T, uint8_t *cur, int si, i
 // planes: 2/3 of the frames' samples for 4:2:0.  Used when the batch's chains fit the SMs at one chain per CTA.
 struct DecMail { uint32_t low, range, pos; int32_t err, sx, sy, sw, sh, qti, v4, bad; uint32_t br_off, br_nbytes, br_pos; };
 constexpr int kDecMailSlots = 4;
+constexpr int kBadSeen = 3;             // `bad` value in warp 1: warp 0 refused the slice and has flagged it already
 
 // MINB = resident CTAs per SM the register allocation aims at (8: no spills; 12: for batches with more chains than 8 CTAs hold)
 template <int MINB, bool PIPE>
@@ -595,7 +596,7 @@ __global__ void __launch_bounds__(32 * kDecWarps, MINB) k_decode(const DecDevice
                         sr.br.buf = sbeg + m.br_off; sr.br.nbytes = m.br_nbytes; sr.br.pos = m.br_pos;
                         br_load(sr.br, m.br_pos >> 3);
                     }
-                    sx = m.sx; sy = m.sy; sw = m.sw; sh = m.sh; v4 = m.v4; bad = m.bad ? 3 : 0;
+                    sx = m.sx; sy = m.sy; sw = m.sw; sh = m.sh; v4 = m.v4; bad = m.bad ? kBadSeen : 0;
                     qti[0] = m.qti & 3; qti[1] = (m.qti >> 2) & 3; qti[2] = (m.qti >> 4) & 3;
                 }
             } else
@@ -663,7 +664,7 @@ __global__ void __launch_bounds__(32 * kDecWarps, MINB) k_decode(const DecDevice
         if (bad) {
             if (B.zero_fill) dec_zero_slice(T, B.out + (size_t)f * T.frame_bytes, si, zsel, lane);
             if (lane == 0) {
-                if (bad != 3) B.damaged[fs] |= 2u;               // (3: warp 0 has flagged the slice already)
+                if (bad != kBadSeen) B.damaged[fs] |= 2u;
                 if (PIPE && warp == 0) {
                     volatile int *ack = &s_ack;
                     while (nhand - 1 - *ack >= kDecMailSlots) __nanosleep(200);
